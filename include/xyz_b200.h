@@ -1,0 +1,171 @@
+/* include/xyz_b200.h -- C ABI of libxyz_b200.so, the B200 (sm_100a) drop-in for the data-parallel
+ * hot path of xyz-autodiff-cuda.
+ *
+ * The reference has NO extern "C" surface: its only host-callable entry
+ * point on this path is the C++ function launch_gaussian_splatting(...)
+ * (reference: examples/mini-gaussian-splatting/gaussian_splatting_kernel.cuh:38-47) plus the
+ * GaussianCollection::{zero_gradients_gpu, adam_step_gpu, adam_step_gpu_individual} methods
+ * (examples/mini-gaussian-splatting/gaussian_parameters.h:78-91) and file-local kernels
+ * launched from main() (examples/optimization/linear_regression_sgd.cu:86-134).  Each entry
+ * point below cites the reference interface it replaces.  A C++ shim with the reference's
+ * exact launch_gaussian_splatting signature lives in include/xyz_b200_compat.hpp.
+ *
+ * Conventions (all entry points):
+ *   - every pointer is a DEVICE pointer unless its name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream, which is what
+ *     the reference uses);
+ *   - the return value is a cudaError_t as int (0 = success) or a negative XYZ_ERR_* code;
+ *     nothing throws; nothing prints;
+ *   - accumulation semantics are the reference's: gradient and loss outputs are ADDED to, the
+ *     caller zeroes them (gaussian_splatting_training.cu:131-135, linear_regression_sgd.cu:201);
+ *   - calls are asynchronous on `stream` except where stated.
+ */
+#ifndef XYZ_B200_H_
+#define XYZ_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- data layouts (bit-identical to the reference's structs) --------------------------- */
+
+/* gaussian_parameters.h:12-18 (GaussianParams) and :35-41 (GaussianGrads): 9 floats, 36 B. */
+typedef struct xyz_gaussian_params {
+    float center[2];
+    float scale[2];   /* log-scale: sigma = exp(scale) */
+    float rotation[1];
+    float color[3];
+    float opacity[1]; /* logit: alpha = sigmoid(opacity) */
+} xyz_gaussian_params;
+typedef xyz_gaussian_params xyz_gaussian_grads;
+
+/* gaussian_parameters.h:21-32 (AdamState): 18 floats, 72 B. */
+typedef struct xyz_adam_state {
+    float m_center[2], v_center[2];
+    float m_scale[2], v_scale[2];
+    float m_rotation[1], v_rotation[1];
+    float m_color[3], v_color[3];
+    float m_opacity[1], v_opacity[1];
+} xyz_adam_state;
+
+/* linear_regression_sgd.cu:31-33 (DataPoint) and :36-39 (Parameters). */
+typedef struct xyz_data_point {
+    double x1, x2, y;
+} xyz_data_point;
+typedef struct xyz_lsq_parameters {
+    double value[4]; /* a, b, c, d */
+    double grad[4];
+} xyz_lsq_parameters;
+
+/* ---- flags ------------------------------------------------------------------------------ */
+enum {
+    XYZ_FLAG_DETERMINISTIC = 1, /* fixed-order reductions: results are bit-identical run to run */
+    XYZ_FLAG_PRECISE_MATH  = 2, /* splat: IEEE expf/sinf/cosf/div (the reference's test builds);
+                                   default is the training app's fast-math/FTZ flavour
+                                   (examples/mini-gaussian-splatting/CMakeLists.txt:22-31) */
+    XYZ_FLAG_RESIDUAL_ONLY = 4, /* lsq: differentiate the residual, not its square -- what the
+                                   shipped example runs (linear_regression_sgd.cu:119-122) */
+    XYZ_FLAG_NO_CULL       = 8, /* splat: evaluate every (pixel, Gaussian) pair like the reference
+                                   kernel does; default skips pairs whose weight is exactly 0 */
+    XYZ_FLAG_IMPLICIT_IDS  = 16 /* accumulate: idx == NULL means id = i mod K */
+};
+
+enum {
+    XYZ_ERR_INVALID_ARGUMENT = -1,
+    XYZ_ERR_WORKSPACE        = -2,
+    XYZ_ERR_NOT_INITIALISED  = -3
+};
+
+/* ---- library ----------------------------------------------------------------------------- */
+const char* xyz_b200_version(void);
+/* Frees the library-owned scratch buffers of the current device (splat tile lists,
+ * reduction partials).  Synchronises the device. */
+int xyz_b200_shutdown(void);
+/* Number of kernels the library has launched since load / since the last reset (host counter). */
+uint64_t xyz_b200_launch_count(void);
+void xyz_b200_reset_launch_count(void);
+
+/* ---- C1: batched least-squares forward+reverse (fp64) --------------------------------------
+ * Replaces compute_gradient_kernel<Analytical>
+ * (examples/optimization/tests/test_linear_regression_gradient.cu:33-79) and, with
+ * XYZ_FLAG_RESIDUAL_ONLY, parallel_gradient_computation_kernel
+ * (examples/optimization/linear_regression_sgd.cu:86-123).  For every data point builds
+ * r = (a-x1)^2 + b(c-x2)^2 + d - y, loss = r^2, and ADDS d(loss)/d(a,b,c,d) into params->grad.
+ * loss_sum (optional, may be NULL) receives += sum of per-point root values.            */
+int xyz_lsq_grad_f64(const xyz_data_point* data, long long n_points, xyz_lsq_parameters* params,
+                     double* loss_sum, void* stream, int flags);
+/* update_parameters_kernel (linear_regression_sgd.cu:126-134): value -= lr * grad / batch. */
+int xyz_lsq_sgd_update_f64(xyz_lsq_parameters* params, double learning_rate, long long batch_size,
+                           void* stream);
+/* select_batch_kernel (linear_regression_sgd.cu:68-81) with a counter-based RNG instead of a
+ * per-thread curand_init: batch[i] = data[hash(seed, epoch, i) mod n_total].               */
+int xyz_lsq_select_batch(const xyz_data_point* data, long long n_total, xyz_data_point* batch,
+                         long long batch_size, uint64_t seed, uint64_t epoch, void* stream);
+
+/* ---- C2: accumulation of per-element gradients into K shared parameters (fp32) ---------------
+ * Replaces the VariableRef::add_grad pattern (include/xyz_autodiff/variable.cuh:48-50) as
+ * exercised by tests/test_parallel_gradient_accumulation.cu:25-49: grad[idx[i]] += val[i].   */
+int xyz_accumulate_f32(const int32_t* idx, const float* val, long long n, float* grad, int k,
+                       void* stream, int flags);
+/* fp64 flavour used by the reference's own accumulation tests (3 addresses, double). */
+int xyz_accumulate_f64(const int32_t* idx, const double* val, long long n, double* grad, int k,
+                       void* stream, int flags);
+
+/* ---- C3: batched covariance projection S' = (J W) S (J W)^T, forward + reverse (fp32) ----------
+ * The composition of op::matmul<2,3,3>, op::matmul<2,3,3>, op::matmul<2,3,2>
+ * (include/xyz_autodiff/operations/binary/matmul_logic.cuh:13-81) over a packed symmetric
+ * 3x3 (include/xyz_autodiff/symmetric_matrix_view.cuh:24-29) as one kernel.
+ * Per element e (all row-major, contiguous per array):
+ *   J[e]: 2x3 (6)   W[e]: 3x3 (9)   S[e]: packed upper-triangular 3x3 (6: 00 01 02 11 12 22)
+ *   g[e]: upstream adjoint of the packed 2x2 output (3: 00 01 11)
+ * writes out[e] (3), gJ[e] (6), gW[e] (9), gS[e] (6).  Outputs are OVERWRITTEN (per-element
+ * gradients have a single writer, nothing to accumulate into).                               */
+int xyz_covproj_fwd_bwd_f32(const float* J, const float* W, const float* S, const float* g,
+                            float* out, float* gJ, float* gW, float* gS, long long n,
+                            void* stream, int flags);
+
+/* ---- C4/C5: mini-gaussian-splatting -------------------------------------------------------------
+ * Replaces launch_gaussian_splatting (gaussian_splatting_kernel.cuh:38-47 /
+ * gaussian_splatting_kernel.cu:114-149): renders `output` (overwritten), ADDS the L1 loss into
+ * *total_loss and ADDS d(loss)/d(params) into `gradients`.  target/output are P x 3 floats
+ * (PixelOutput = ConstArray<float,3>).  Synchronises `stream` once internally (the tile-list
+ * length is data dependent); scratch is library-owned and grows on demand.                   */
+int xyz_launch_gaussian_splatting(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients,
+                                  const float* target_image, float* output_image, float* total_loss,
+                                  int image_width, int image_height, int num_gaussians,
+                                  void* stream, int flags);
+/* Row-band variant for sharding one image across GPUs: only pixel rows [row_begin, row_end)
+ * are rendered / contribute loss and gradients.  Buffers are full-image sized. */
+int xyz_launch_gaussian_splatting_rows(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients,
+                                       const float* target_image, float* output_image, float* total_loss,
+                                       int image_width, int image_height, int num_gaussians,
+                                       int row_begin, int row_end, void* stream, int flags);
+/* Statistics of the most recent splat launch on this host thread's device (host values):
+ * stats[0] = (tile, Gaussian) list entries, stats[1] = tiles, stats[2] = longest tile list,
+ * stats[3] = pixel-Gaussian pairs evaluated per pass. */
+int xyz_splat_last_stats(long long stats_host[4]);
+/* Copies the integer tile-binning results of the most recent splat launch to host buffers (for the
+ * bit-exact integer parity tests): per-Gaussian tile rectangles (N x 4 int32: tx0, ty0, tx1, ty1,
+ * half-open), per-tile [begin, end) ranges (tiles x 2 int32) and the sorted Gaussian ids
+ * (entries int32).  Any pointer may be NULL.  Synchronises the device. */
+int xyz_splat_debug_binning(int32_t* rects_host, int32_t* tile_ranges_host, int32_t* sorted_ids_host);
+
+/* zero_gradients_kernel (gaussian_parameters.cu:227-257). */
+int xyz_zero_gradients(xyz_gaussian_grads* gradients, int num_gaussians, void* stream);
+/* adam_step_individual_kernel (gaussian_parameters.cu:260-320, host wrapper :352-386); lr =
+ * {center, scale, rotation, color, opacity}.  No clamps, like the reference's GPU kernel. */
+int xyz_adam_step_individual(xyz_gaussian_params* params, const xyz_gaussian_grads* grads,
+                             xyz_adam_state* adam, int num_gaussians, const float lr_host[5],
+                             float beta1, float beta2, float epsilon, int iteration, void* stream);
+/* adam_step_kernel (gaussian_parameters.cu:173-224, host wrapper :322-350): single rate. */
+int xyz_adam_step(xyz_gaussian_params* params, const xyz_gaussian_grads* grads, xyz_adam_state* adam,
+                  int num_gaussians, float learning_rate, float beta1, float beta2, float epsilon,
+                  int iteration, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* XYZ_B200_H_ */
