@@ -1,0 +1,369 @@
+#!/usr/bin/env python
+"""bench.py -- the driver's benchmark contract for the xyz-autodiff-cuda hot path on B200.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload covproj|lsq|accumulate|splat]
+  torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W        (N > 1)
+
+Headline workload (BASELINE.json configs[2], the largest single-GPU "gradient evals/s" configuration and the
+only one whose working set (12.9 GB) exceeds L2): batched covariance projection S' = (J W) S (J W)^T,
+forward + reverse, 2^26 elements, fp32.  A step = one pass of the kernel over the batch.
+  value     evals/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
+  e2e       the same through the host-buffer pipeline (pinned host arrays -> H2D -> kernel -> D2H)
+  roofline  192 algorithmic bytes per eval / kernel time, against MEASURED_PEAKS.json hbm_gbs
+  cpu_baseline  the reference's own op::matmul graph compiled for the host (oracle/_ref), all host
+            cores, on a bounded sample
+The other BASELINE configs (least squares 1M, accumulation 16M->1K, splat 100K Gaussians 1024^2) are timed
+briefly at N=1 and reported under "also" in the same JSON line.
+--impl reference times the reference's CPU path alone (rank 0 only).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+METRIC = "fwd+bwd gradient evals/sec"
+UNIT = "evals/s"
+COVPROJ_BYTES = 192  # per eval: in J6 W9 S6 g3, out out3 gJ6 gW9 gS6, fp32
+FULL_E = 1 << 26
+
+
+def measured_peak_gbs():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
+    except Exception:
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks + throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [p.strip() for p in ln.split(",")]
+            if len(parts) < 8:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, val in zip(names, parts[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(nm)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_covproj(sample_elems, repeats=1):
+    """The reference's matmul graph on the host cores (oracle/_ref if present, else the port)."""
+    import numpy as np
+    import oracle_lib as orc
+    which = "ref" if orc.have_ref() else "port"
+    cores = os.cpu_count() or 1
+    J, W, S, g = orc.covproj_inputs(sample_elems, seed=42)
+    orc.covproj(J[:1024], W[:1024], S[:1024], g[:1024], np.float32, which=which, threads=cores)  # warm the library
+    best = None
+    for _ in range(repeats):
+        t0 = time.perf_counter()
+        orc.covproj(J, W, S, g, np.float32, which=which, threads=cores)
+        dt = time.perf_counter() - t0
+        best = dt if best is None else min(best, dt)
+    return {"value": sample_elems / best, "unit": UNIT, "cores": cores,
+            "kind": "reference" if which == "ref" else "port",
+            "sample": f"{sample_elems} of the {FULL_E} elements (seed 42), fp32, std::thread x {cores}, "
+                      f"{'reference op::matmul graph compiled for the host (oracle/_ref)' if which == 'ref' else 'oracle port'}"}, best
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    sample = 1 << 23
+    times = []
+    base = None
+    for i in range(args.warmup + args.steps):
+        base, dt = cpu_covproj(sample)
+        if i >= args.warmup:
+            times.append(dt)
+    ms = 1000.0 * sum(times) / len(times)
+    value = sample / (ms / 1000.0)
+    base["value"] = value
+    line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "covproj_fwd_bwd 3x3 chain S'=(JW)S(JW)^T, 2^26 elems (BASELINE configs[2]); "
+                                   "each step = a bounded sample of 2^23 elements on the host cores"},
+            "cpu_baseline": base,
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def time_kernel(fn, steps, warmup, stream):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record(stream)
+    for i in range(steps):
+        fn()
+        ev[i + 1].record(stream)
+    torch.cuda.synchronize()
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    return ev[0].elapsed_time(ev[steps]), per
+
+
+def also_workloads(dev, peak_gbs):
+    """Brief device-resident timings of the other BASELINE configs (N=1 only)."""
+    import numpy as np
+    import torch
+    import oracle_lib as orc
+    import xyz_autodiff_cuda_b200 as x
+    out = {}
+    st = torch.cuda.current_stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def timed(fn, reps=10, flush_l2=True):
+        ts = []
+        for i in range(reps + 3):
+            if flush_l2:
+                flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(st)
+            fn()
+            b.record(st)
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    # C1: least squares, 1M residuals fp64 (24 MB)
+    n = 1_000_000
+    data = torch.from_numpy(orc.lsq_data(n, 42)).to(dev)
+    prm = torch.zeros(8, dtype=torch.float64, device=dev)
+    prm[1] = 1.0
+    ms = timed(lambda: x.lsq_grad(data, prm))
+    out["c1_lsq_1M_f64"] = {"evals_per_s": n / (ms / 1e3), "ms": ms, "gbs": 24 * n / (ms / 1e3) / 1e9,
+                            "hbm_frac": 24 * n / (ms / 1e3) / 1e9 / peak_gbs, "l2": "flushed between iterations"}
+    n2 = 1 << 28
+    data2 = torch.empty((n2, 3), dtype=torch.float64, device=dev).uniform_(-5, 5)
+    ms = timed(lambda: x.lsq_grad(data2, prm), reps=5, flush_l2=False)
+    out["c1_lsq_2^28_f64"] = {"evals_per_s": n2 / (ms / 1e3), "ms": ms, "gbs": 24 * n2 / (ms / 1e3) / 1e9,
+                              "hbm_frac": 24 * n2 / (ms / 1e3) / 1e9 / peak_gbs, "l2": "6.4 GB input > L2"}
+    del data2
+    # C2: accumulation 2^24 -> 1024
+    n = 1 << 24
+    for dist in ("uniform", "zipf", "same"):
+        idx, val = orc.accumulate_inputs(n, 1024, dist, 42)
+        ti, tv = torch.from_numpy(idx).to(dev), torch.from_numpy(val).to(dev)
+        grad = torch.zeros(1024, device=dev)
+        ms = timed(lambda: x.accumulate(ti, tv, grad))
+        out[f"c2_accumulate_2^24_{dist}"] = {"elems_per_s": n / (ms / 1e3), "ms": ms, "gbs": 8 * n / (ms / 1e3) / 1e9,
+                                             "hbm_frac": 8 * n / (ms / 1e3) / 1e9 / peak_gbs,
+                                             "l2": "flushed between iterations"}
+    # C4: splat 100K Gaussians, 1024^2
+    W = H = 1024
+    N = 100_000
+    params, target = orc.splat_c4_scene(N, W, H, 42)
+    tp, tt = torch.from_numpy(params).to(dev), torch.from_numpy(target).to(dev)
+    grads = torch.zeros((N, 9), device=dev)
+    img = torch.zeros((W * H, 3), device=dev)
+    loss = torch.zeros(1, device=dev)
+
+    def splat_iter():
+        x.zero_gradients(grads)
+        loss.zero_()
+        x.launch_gaussian_splatting(tp, grads, tt, img, loss, W, H, N)
+
+    ms = timed(splat_iter, reps=5, flush_l2=False)
+    stats = x.splat_last_stats()
+    out["c4_splat_100K_1024x1024"] = {"ms_per_iter": ms, "tile_list_entries": stats["entries"],
+                                      "pairs_per_pass": stats["pairs_per_pass"],
+                                      "pair_evals_per_s": 2 * stats["pairs_per_pass"] / (ms / 1e3),
+                                      "reference_pairs_per_pass": N * W * H,
+                                      "iteration": "zero_grad + loss reset + launch (fwd + bwd), fast-math flavour"}
+    return out
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import xyz_autodiff_cuda_b200 as x
+    from importlib import import_module
+    host_api = import_module("xyz_autodiff_cuda_b200.host_api")
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise RuntimeError("bench.py needs a CUDA device: the hot path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    x.lib()
+    peak_gbs, peak_src = measured_peak_gbs()
+
+    # weak scaling: every rank owns E elements; the path has no data-path collective (per-element gradients)
+    E = args.elems
+    gen = torch.Generator(device=dev).manual_seed(42 + rank)
+    ins = [torch.empty((E, w), dtype=torch.float32, device=dev) for w in (6, 9, 6, 3)]
+    for t in ins:
+        t.uniform_(-1.0, 1.0, generator=gen)
+    outs = [torch.empty((E, w), dtype=torch.float32, device=dev) for w in (3, 6, 9, 6)]
+    st = torch.cuda.current_stream()
+
+    def step():
+        x.covproj_fwd_bwd(*ins, *outs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    x.reset_launch_count()
+    barrier()
+    total_ms, per = time_kernel(step, args.steps, 0, st)
+    launches = x.launch_count()
+    barrier()
+    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    total_ms = t.item()
+    ms_per_step = total_ms / args.steps
+    value = world * E / (ms_per_step / 1e3)
+    kernel_ms = sum(per) / len(per)  # one launch per step: the kernel's average launch duration on this rank
+    achieved = COVPROJ_BYTES * E / (kernel_ms / 1e3) / 1e9
+
+    # e2e: pinned host arrays -> chunked H2D / kernel / D2H pipeline, same metric
+    e2e_elems = min(E, args.e2e_elems)
+    del outs
+    h_in = [torch.empty((e2e_elems, w), dtype=torch.float32).pin_memory() for w in (6, 9, 6, 3)]
+    for h, d in zip(h_in, ins):
+        h.copy_(d[:e2e_elems])
+    h_out = [torch.empty((e2e_elems, w), dtype=torch.float32).pin_memory() for w in (3, 6, 9, 6)]
+    pipe = host_api.CovprojHostPipeline(dev)
+    h2d = d2h = 0
+    for _ in range(2):
+        h2d, d2h = pipe.run(h_in, h_out)
+    barrier()
+    e2e_steps = max(1, min(args.steps, 5))
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record(st)
+    for _ in range(e2e_steps):
+        pipe.run(h_in, h_out)
+    b.record(st)
+    barrier()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * e2e_elems * e2e_steps / (t.item() / 1e3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "covproj_fwd_bwd 3x3 chain S'=(JW)S(JW)^T fwd+bwd (BASELINE configs[2])",
+                       "elems_per_gpu": E, "bytes_per_eval": COVPROJ_BYTES, "l2": "inputs larger than L2 "
+                       f"({COVPROJ_BYTES * E / 1e9:.1f} GB per step per GPU)", "parallelism": f"dp{world} by element range, no collective"},
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
+                         "traffic": None, "peak_source": peak_src, "kernel": "covproj_tma_kernel",
+                         "kernel_ms": kernel_ms},
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "elems_per_step": e2e_elems, "steps": e2e_steps,
+                    "api": "host_api.CovprojHostPipeline (pinned host -> H2D -> xyz_covproj_fwd_bwd_f32 -> D2H, 3 streams)"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+        }
+        if world == 1:
+            base, _ = cpu_covproj(1 << 23)
+            line["cpu_baseline"] = base
+            if not args.no_also:
+                del ins, h_in, h_out, pipe
+                torch.cuda.empty_cache()
+                try:
+                    line["also"] = also_workloads(dev, peak_gbs)
+                except Exception as e:  # the headline must still be printed
+                    line["also"] = {"error": repr(e)}
+        traffic_file = os.path.join(ROOT, "profiles", "covproj_traffic.json")
+        if os.path.exists(traffic_file):
+            try:
+                with open(traffic_file) as f:
+                    tr = json.load(f)
+                line["roofline"]["traffic"] = tr["dram_bytes_per_eval"] * E
+                line["roofline"]["traffic_source"] = tr.get("source")
+            except Exception:
+                pass
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--elems", type=int, default=FULL_E, help="elements per GPU (default 2^26, BASELINE configs[2])")
+    ap.add_argument("--e2e-elems", type=int, default=1 << 25, help="elements per e2e step (host pinned memory bound)")
+    ap.add_argument("--no-also", action="store_true", help="skip the brief timings of the other configs")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -26,6 +26,12 @@
 #include <stddef.h>
 #include <stdint.h>
 
+#if defined(__GNUC__)
+#define XYZ_API __attribute__((visibility("default")))
+#else
+#define XYZ_API
+#endif
+
 #ifdef __cplusplus
 extern "C" {
 #endif
@@ -80,13 +86,13 @@ enum {
 };
 
 /* ---- library ----------------------------------------------------------------------------- */
-const char* xyz_b200_version(void);
+XYZ_API const char* xyz_b200_version(void);
 /* Frees the library-owned scratch buffers of the current device (splat tile lists,
  * reduction partials).  Synchronises the device. */
-int xyz_b200_shutdown(void);
+XYZ_API int xyz_b200_shutdown(void);
 /* Number of kernels the library has launched since load / since the last reset (host counter). */
-uint64_t xyz_b200_launch_count(void);
-void xyz_b200_reset_launch_count(void);
+XYZ_API uint64_t xyz_b200_launch_count(void);
+XYZ_API void xyz_b200_reset_launch_count(void);
 
 /* ---- C1: batched least-squares forward+reverse (fp64) --------------------------------------
  * Replaces compute_gradient_kernel<Analytical>
@@ -95,23 +101,23 @@ void xyz_b200_reset_launch_count(void);
  * (examples/optimization/linear_regression_sgd.cu:86-123).  For every data point builds
  * r = (a-x1)^2 + b(c-x2)^2 + d - y, loss = r^2, and ADDS d(loss)/d(a,b,c,d) into params->grad.
  * loss_sum (optional, may be NULL) receives += sum of per-point root values.            */
-int xyz_lsq_grad_f64(const xyz_data_point* data, long long n_points, xyz_lsq_parameters* params,
+XYZ_API int xyz_lsq_grad_f64(const xyz_data_point* data, long long n_points, xyz_lsq_parameters* params,
                      double* loss_sum, void* stream, int flags);
 /* update_parameters_kernel (linear_regression_sgd.cu:126-134): value -= lr * grad / batch. */
-int xyz_lsq_sgd_update_f64(xyz_lsq_parameters* params, double learning_rate, long long batch_size,
+XYZ_API int xyz_lsq_sgd_update_f64(xyz_lsq_parameters* params, double learning_rate, long long batch_size,
                            void* stream);
 /* select_batch_kernel (linear_regression_sgd.cu:68-81) with a counter-based RNG instead of a
  * per-thread curand_init: batch[i] = data[hash(seed, epoch, i) mod n_total].               */
-int xyz_lsq_select_batch(const xyz_data_point* data, long long n_total, xyz_data_point* batch,
+XYZ_API int xyz_lsq_select_batch(const xyz_data_point* data, long long n_total, xyz_data_point* batch,
                          long long batch_size, uint64_t seed, uint64_t epoch, void* stream);
 
 /* ---- C2: accumulation of per-element gradients into K shared parameters (fp32) ---------------
  * Replaces the VariableRef::add_grad pattern (include/xyz_autodiff/variable.cuh:48-50) as
  * exercised by tests/test_parallel_gradient_accumulation.cu:25-49: grad[idx[i]] += val[i].   */
-int xyz_accumulate_f32(const int32_t* idx, const float* val, long long n, float* grad, int k,
+XYZ_API int xyz_accumulate_f32(const int32_t* idx, const float* val, long long n, float* grad, int k,
                        void* stream, int flags);
 /* fp64 flavour used by the reference's own accumulation tests (3 addresses, double). */
-int xyz_accumulate_f64(const int32_t* idx, const double* val, long long n, double* grad, int k,
+XYZ_API int xyz_accumulate_f64(const int32_t* idx, const double* val, long long n, double* grad, int k,
                        void* stream, int flags);
 
 /* ---- C3: batched covariance projection S' = (J W) S (J W)^T, forward + reverse (fp32) ----------
@@ -123,7 +129,7 @@ int xyz_accumulate_f64(const int32_t* idx, const double* val, long long n, doubl
  *   g[e]: upstream adjoint of the packed 2x2 output (3: 00 01 11)
  * writes out[e] (3), gJ[e] (6), gW[e] (9), gS[e] (6).  Outputs are OVERWRITTEN (per-element
  * gradients have a single writer, nothing to accumulate into).                               */
-int xyz_covproj_fwd_bwd_f32(const float* J, const float* W, const float* S, const float* g,
+XYZ_API int xyz_covproj_fwd_bwd_f32(const float* J, const float* W, const float* S, const float* g,
                             float* out, float* gJ, float* gW, float* gS, long long n,
                             void* stream, int flags);
 
@@ -133,35 +139,38 @@ int xyz_covproj_fwd_bwd_f32(const float* J, const float* W, const float* S, cons
  * *total_loss and ADDS d(loss)/d(params) into `gradients`.  target/output are P x 3 floats
  * (PixelOutput = ConstArray<float,3>).  Synchronises `stream` once internally (the tile-list
  * length is data dependent); scratch is library-owned and grows on demand.                   */
-int xyz_launch_gaussian_splatting(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients,
+XYZ_API int xyz_launch_gaussian_splatting(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients,
                                   const float* target_image, float* output_image, float* total_loss,
                                   int image_width, int image_height, int num_gaussians,
                                   void* stream, int flags);
 /* Row-band variant for sharding one image across GPUs: only pixel rows [row_begin, row_end)
  * are rendered / contribute loss and gradients.  Buffers are full-image sized. */
-int xyz_launch_gaussian_splatting_rows(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients,
+XYZ_API int xyz_launch_gaussian_splatting_rows(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients,
                                        const float* target_image, float* output_image, float* total_loss,
                                        int image_width, int image_height, int num_gaussians,
                                        int row_begin, int row_end, void* stream, int flags);
 /* Statistics of the most recent splat launch on this host thread's device (host values):
  * stats[0] = (tile, Gaussian) list entries, stats[1] = tiles, stats[2] = longest tile list,
  * stats[3] = pixel-Gaussian pairs evaluated per pass. */
-int xyz_splat_last_stats(long long stats_host[4]);
+XYZ_API int xyz_splat_last_stats(long long stats_host[4]);
 /* Copies the integer tile-binning results of the most recent splat launch to host buffers (for the
  * bit-exact integer parity tests): per-Gaussian tile rectangles (N x 4 int32: tx0, ty0, tx1, ty1,
- * half-open), per-tile [begin, end) ranges (tiles x 2 int32) and the sorted Gaussian ids
- * (entries int32).  Any pointer may be NULL.  Synchronises the device. */
-int xyz_splat_debug_binning(int32_t* rects_host, int32_t* tile_ranges_host, int32_t* sorted_ids_host);
+ * half-open), per-tile [begin, end) ranges (tiles x 2 int32), the sorted Gaussian ids
+ * (entries int32) and the per-Gaussian float records the rectangles were derived from
+ * (N x 12 float: cx, cy, ia, ib, ic, sigmoid(opacity), r, g, b, 0, 0, 0).  Any pointer may be NULL.
+ * Synchronises the device. */
+XYZ_API int xyz_splat_debug_binning(int32_t* rects_host, int32_t* tile_ranges_host, int32_t* sorted_ids_host,
+                            float* records_host);
 
 /* zero_gradients_kernel (gaussian_parameters.cu:227-257). */
-int xyz_zero_gradients(xyz_gaussian_grads* gradients, int num_gaussians, void* stream);
+XYZ_API int xyz_zero_gradients(xyz_gaussian_grads* gradients, int num_gaussians, void* stream);
 /* adam_step_individual_kernel (gaussian_parameters.cu:260-320, host wrapper :352-386); lr =
  * {center, scale, rotation, color, opacity}.  No clamps, like the reference's GPU kernel. */
-int xyz_adam_step_individual(xyz_gaussian_params* params, const xyz_gaussian_grads* grads,
+XYZ_API int xyz_adam_step_individual(xyz_gaussian_params* params, const xyz_gaussian_grads* grads,
                              xyz_adam_state* adam, int num_gaussians, const float lr_host[5],
                              float beta1, float beta2, float epsilon, int iteration, void* stream);
 /* adam_step_kernel (gaussian_parameters.cu:173-224, host wrapper :322-350): single rate. */
-int xyz_adam_step(xyz_gaussian_params* params, const xyz_gaussian_grads* grads, xyz_adam_state* adam,
+XYZ_API int xyz_adam_step(xyz_gaussian_params* params, const xyz_gaussian_grads* grads, xyz_adam_state* adam,
                   int num_gaussians, float learning_rate, float beta1, float beta2, float epsilon,
                   int iteration, void* stream);
 

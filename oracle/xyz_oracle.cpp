@@ -348,10 +348,11 @@ inline void pair_forward(const T* gp, T px, T py, PairFwd<T>& f) {
 }
 
 // One pixel of the reference kernel.  grads += ; *loss += ; out[3] written.  `margin` (optional)
-// tracks min |color_diff_i| over all pairs: the distance of the closest L1 kink (tests use it to
-// make sure a sign cannot flip within fp32 noise).
+// tracks min |color_diff_i| over all pairs whose weight is not negligible (> 1e-10): the distance of the
+// closest L1 kink (tests use it to make sure a sign cannot flip within fp32 noise).
 template <class T>
-void splat_pixel(const T* params, T* grads, const T* tgt, T* out, T* loss, int px_i, int py_i, int N, T* margin) {
+void splat_pixel(const T* params, T* grads, const T* tgt, T* out, T* loss, int px_i, int py_i, int N, T* margin,
+                 T* absgrads, T* kinkgrads) {
     const T px = static_cast<T>(px_i), py = static_cast<T>(py_i);
     T pix[3] = {T(0), T(0), T(0)};
     PairFwd<T> f;
@@ -364,14 +365,19 @@ void splat_pixel(const T* params, T* grads, const T* tgt, T* out, T* loss, int p
     for (int g = 0; g < N; ++g) {                               // :73-111
         const T* gp = params + 9 * g;
         T* gg = grads + 9 * g;
+        T before[9];
+        if (absgrads) for (int k = 0; k < 9; ++k) before[k] = gg[k];
         pair_forward(gp, px, py, f);                            // l1_loss.run() -> forward
         T sgn[3];
+        bool near_kink = false;
         for (int i = 0; i < 3; ++i) {
             T rest = tgt[i] - pix[i];                           // rest_sum = target - pixel_out            :101
             rest += T(0);                                       // += un-forwarded weighted_color (Q2)      :102
             const T cd = f.wc[i] - rest;                        // color_diff = weighted_color - rest_sum   :106
             sgn[i] = cd > T(0) ? T(1) : (cd < T(0) ? T(-1) : T(0));  // l1 backward, seed 1.0
-            if (margin && std::abs(cd) < *margin) *margin = std::abs(cd);
+            if (margin && f.w > T(1e-10) && std::abs(cd) < *margin) *margin = std::abs(cd);
+            // sign(cd) is numerically ambiguous in fp32 when |cd| is within rounding distance of 0
+            if (std::abs(cd) <= T(2e-5) * std::max(std::abs(f.wc[i]), std::abs(rest))) near_kink = true;
         }
         // mul backward (binary/mul_logic.cuh:33-41): color.grad += g*bc ; bc(=weighted_gauss).grad += g*color
         T g_w = T(0);
@@ -401,6 +407,13 @@ void splat_pixel(const T* params, T* grads, const T* tgt, T* out, T* loss, int p
         gg[3] += g_es[1] * m_exp(gp[3]);
         const T s = m_sigmoid(gp[8]);                           // sigmoid backward (recomputed)
         gg[8] += g_so * (s * (T(1) - s));
+        if (absgrads)  // sum of |per-pair term|: the scale the 1e-4 tolerance on accumulated sums is stated against
+            for (int k = 0; k < 9; ++k) {
+                const T term = std::abs(gg[k] - before[k]);
+                absgrads[9 * g + k] += term;
+                // upper bound of what a flipped sign can change: |g_w| <= sum |color_i| instead of |sum s_i color_i|
+                if (kinkgrads && near_kink) kinkgrads[9 * g + k] += term + std::abs(f.w) + T(1e-30);
+            }
     }
 }
 
@@ -409,15 +422,17 @@ void splat_pixel(const T* params, T* grads, const T* tgt, T* out, T* loss, int p
 // the same order as oracle/ref_driver.cpp.
 template <class T>
 int splat_all_pairs(const T* params, T* grads, const T* target, T* output, T* loss, int W, int H, int N, int threads,
-                    T* margin_out) {
+                    T* margin_out, T* absgrads_out, T* kinkgrads_out) {
     constexpr int TS = 16;  // gaussian_splatting_kernel.cuh:21
     const int bx = (W + TS - 1) / TS, by = (H + TS - 1) / TS;
     const long long nblocks = 1LL * bx * by;
     threads = static_cast<int>(std::max<long long>(1, std::min<long long>(threads, nblocks)));
-    std::vector<std::vector<T>> priv_g(threads);
+    std::vector<std::vector<T>> priv_g(threads), priv_a(threads), priv_k(threads);
     std::vector<T> priv_l(threads, T(0)), priv_m(threads, T(1e30));
     parallel_ranges(nblocks, threads, [&](int t, long long lo, long long hi) {
         priv_g[t].assign(static_cast<size_t>(N) * 9, T(0));
+        if (absgrads_out) priv_a[t].assign(static_cast<size_t>(N) * 9, T(0));
+        if (kinkgrads_out) priv_k[t].assign(static_cast<size_t>(N) * 9, T(0));
         for (long long b = lo; b < hi; ++b) {
             const int bxi = static_cast<int>(b % bx), byi = static_cast<int>(b / bx);
             for (int ty = 0; ty < TS; ++ty)
@@ -426,13 +441,18 @@ int splat_all_pairs(const T* params, T* grads, const T* target, T* output, T* lo
                     if (x >= W || y >= H) continue;
                     const size_t p = static_cast<size_t>(y) * W + x;
                     splat_pixel<T>(params, priv_g[t].data(), target + 3 * p, output + 3 * p, &priv_l[t], x, y, N,
-                                   margin_out ? &priv_m[t] : nullptr);
+                                   margin_out ? &priv_m[t] : nullptr, absgrads_out ? priv_a[t].data() : nullptr,
+                                   kinkgrads_out ? priv_k[t].data() : nullptr);
                 }
         }
     });
     T m = T(1e30);
     for (int t = 0; t < threads; ++t) {
         for (size_t i = 0; i < static_cast<size_t>(N) * 9; ++i) grads[i] += priv_g[t][i];
+        if (absgrads_out)
+            for (size_t i = 0; i < static_cast<size_t>(N) * 9; ++i) absgrads_out[i] += priv_a[t][i];
+        if (kinkgrads_out)
+            for (size_t i = 0; i < static_cast<size_t>(N) * 9; ++i) kinkgrads_out[i] += priv_k[t][i];
         *loss += priv_l[t];
         m = std::min(m, priv_m[t]);
     }
@@ -587,12 +607,15 @@ int orc_eval_op_f32(int op, int aux, const float* in1, int n1, const float* in2,
 
 int orc_splat_f32(const float* params, float* grads, const float* target, float* output, float* loss, int W, int H,
                   int N, int threads) {
-    return splat_all_pairs<float>(params, grads, target, output, loss, W, H, N, threads, nullptr);
+    return splat_all_pairs<float>(params, grads, target, output, loss, W, H, N, threads, nullptr, nullptr, nullptr);
 }
-// fp64 ground truth of the same statements; *margin = min |color_diff| over all pairs and channels.
+// fp64 ground truth of the same statements; *margin = min |color_diff| over all pairs and channels;
+// absgrads (N x 9, optional, +=) = sum over pairs of |per-pair gradient term|; kinkgrads (N x 9, optional,
+// needs absgrads, +=) = the same sum restricted to pairs whose L1 argument is within fp32 rounding
+// distance of 0 (their sign, hence their term, is ambiguous for ANY fp32 implementation).
 int orc_splat_f64(const double* params, double* grads, const double* target, double* output, double* loss, int W,
-                  int H, int N, int threads, double* margin) {
-    return splat_all_pairs<double>(params, grads, target, output, loss, W, H, N, threads, margin);
+                  int H, int N, int threads, double* margin, double* absgrads, double* kinkgrads) {
+    return splat_all_pairs<double>(params, grads, target, output, loss, W, H, N, threads, margin, absgrads, kinkgrads);
 }
 
 // Least squares: examples/optimization/tests/test_linear_regression_gradient.cu:52-78 (squared loss),

@@ -1,0 +1,212 @@
+"""xyz-autodiff-cuda_b200 -- host-side mirror (Python) of the C ABI in include/xyz_b200.h.
+
+The product is libxyz_b200.so (hand-written sm_100a kernels, xyz-autodiff-cuda_b200/csrc/).  This
+module only binds it with ctypes and passes device pointers of torch tensors; torch is plumbing
+(device memory, streams, torch.distributed), not the compute path.  There is NO CPU fallback: if
+the library is missing or a kernel launch fails, a RuntimeError is raised.
+
+Names follow the reference's own host API where it has one:
+  launch_gaussian_splatting   examples/mini-gaussian-splatting/gaussian_splatting_kernel.cuh:38-47
+  zero_gradients / adam_step_individual / adam_step
+                              examples/mini-gaussian-splatting/gaussian_parameters.h:78-91
+  GaussianParams layout       examples/mini-gaussian-splatting/gaussian_parameters.h:12-41
+  DataPoint / Parameters      examples/optimization/linear_regression_sgd.cu:31-39
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libxyz_b200.so")
+
+FLAG_DETERMINISTIC = 1
+FLAG_PRECISE_MATH = 2
+FLAG_RESIDUAL_ONLY = 4
+FLAG_NO_CULL = 8
+FLAG_IMPLICIT_IDS = 16
+
+GAUSSIAN_FLOATS = 9   # center[2] scale[2] rotation[1] color[3] opacity[1]
+ADAM_FLOATS = 18
+EXPORTS = [
+    "xyz_b200_version", "xyz_b200_shutdown", "xyz_b200_launch_count", "xyz_b200_reset_launch_count",
+    "xyz_lsq_grad_f64", "xyz_lsq_sgd_update_f64", "xyz_lsq_select_batch",
+    "xyz_accumulate_f32", "xyz_accumulate_f64", "xyz_covproj_fwd_bwd_f32",
+    "xyz_launch_gaussian_splatting", "xyz_launch_gaussian_splatting_rows", "xyz_splat_last_stats",
+    "xyz_splat_debug_binning", "xyz_zero_gradients", "xyz_adam_step_individual", "xyz_adam_step",
+]
+
+_lib = None
+_vp, _ll, _i = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+
+
+def lib() -> ctypes.CDLL:
+    """Load libxyz_b200.so (once).  Raises if it has not been built: there is no fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a).  xyz-autodiff-cuda_b200 has no CPU or PyTorch fallback.")
+        L = ctypes.CDLL(LIB_PATH)
+        L.xyz_b200_version.restype = ctypes.c_char_p
+        L.xyz_b200_launch_count.restype = ctypes.c_uint64
+        L.xyz_b200_reset_launch_count.restype = None
+        L.xyz_lsq_grad_f64.argtypes = [_vp, _ll, _vp, _vp, _vp, _i]
+        L.xyz_lsq_sgd_update_f64.argtypes = [_vp, ctypes.c_double, _ll, _vp]
+        L.xyz_lsq_select_batch.argtypes = [_vp, _ll, _vp, _ll, ctypes.c_uint64, ctypes.c_uint64, _vp]
+        L.xyz_accumulate_f32.argtypes = [_vp, _vp, _ll, _vp, _i, _vp, _i]
+        L.xyz_accumulate_f64.argtypes = [_vp, _vp, _ll, _vp, _i, _vp, _i]
+        L.xyz_covproj_fwd_bwd_f32.argtypes = [_vp] * 8 + [_ll, _vp, _i]
+        L.xyz_launch_gaussian_splatting.argtypes = [_vp] * 5 + [_i, _i, _i, _vp, _i]
+        L.xyz_launch_gaussian_splatting_rows.argtypes = [_vp] * 5 + [_i, _i, _i, _i, _i, _vp, _i]
+        L.xyz_splat_last_stats.argtypes = [_vp]
+        L.xyz_splat_debug_binning.argtypes = [_vp, _vp, _vp, _vp]
+        L.xyz_zero_gradients.argtypes = [_vp, _i, _vp]
+        L.xyz_adam_step_individual.argtypes = [_vp, _vp, _vp, _i, _vp, ctypes.c_float, ctypes.c_float,
+                                               ctypes.c_float, _i, _vp]
+        L.xyz_adam_step.argtypes = [_vp, _vp, _vp, _i, ctypes.c_float, ctypes.c_float, ctypes.c_float,
+                                    ctypes.c_float, _i, _vp]
+        _lib = L
+    return _lib
+
+
+def _check(code: int, what: str) -> None:
+    if code != 0:
+        raise RuntimeError(f"{what} failed with code {code} "
+                           f"({'XYZ_ERR' if code < 0 else 'cudaError_t'}); no fallback path exists")
+
+
+def _dev(t: torch.Tensor, dtype: torch.dtype, what: str) -> int:
+    if not isinstance(t, torch.Tensor) or not t.is_cuda:
+        raise RuntimeError(f"{what}: expected a CUDA tensor (the hot path has no CPU implementation)")
+    if t.dtype != dtype:
+        raise TypeError(f"{what}: expected {dtype}, got {t.dtype}")
+    if not t.is_contiguous():
+        raise ValueError(f"{what}: tensor must be contiguous")
+    return t.data_ptr()
+
+
+def _stream(stream: Optional[torch.cuda.Stream]) -> int:
+    s = stream if stream is not None else torch.cuda.current_stream()
+    return s.cuda_stream
+
+
+def version() -> str:
+    return lib().xyz_b200_version().decode()
+
+
+def launch_count() -> int:
+    return int(lib().xyz_b200_launch_count())
+
+
+def reset_launch_count() -> None:
+    lib().xyz_b200_reset_launch_count()
+
+
+def shutdown() -> None:
+    _check(lib().xyz_b200_shutdown(), "xyz_b200_shutdown")
+
+
+# ---- C1 ------------------------------------------------------------------------------------------
+def lsq_grad(data: torch.Tensor, params: torch.Tensor, loss_sum: Optional[torch.Tensor] = None, flags: int = 0,
+             stream=None) -> None:
+    """data: (E, 3) float64 DataPoint{x1, x2, y}; params: (8,) float64 = value[4] + grad[4] (grad += )."""
+    n = data.shape[0]
+    _check(lib().xyz_lsq_grad_f64(_dev(data, torch.float64, "data"), n, _dev(params, torch.float64, "params"),
+                                  _dev(loss_sum, torch.float64, "loss_sum") if loss_sum is not None else None,
+                                  _stream(stream), flags), "xyz_lsq_grad_f64")
+
+
+def lsq_sgd_update(params: torch.Tensor, lr: float, batch: int, stream=None) -> None:
+    _check(lib().xyz_lsq_sgd_update_f64(_dev(params, torch.float64, "params"), lr, batch, _stream(stream)),
+           "xyz_lsq_sgd_update_f64")
+
+
+def lsq_select_batch(data: torch.Tensor, batch: torch.Tensor, seed: int, epoch: int, stream=None) -> None:
+    _check(lib().xyz_lsq_select_batch(_dev(data, torch.float64, "data"), data.shape[0],
+                                      _dev(batch, torch.float64, "batch"), batch.shape[0], seed, epoch,
+                                      _stream(stream)), "xyz_lsq_select_batch")
+
+
+# ---- C2 ------------------------------------------------------------------------------------------
+def accumulate(idx: Optional[torch.Tensor], val: torch.Tensor, grad: torch.Tensor, flags: int = 0, stream=None) -> None:
+    """grad[idx[i]] += val[i]  (VariableRef::add_grad over K shared parameters)."""
+    n, k = val.numel(), grad.numel()
+    if idx is None:
+        flags |= FLAG_IMPLICIT_IDS
+    ip = _dev(idx, torch.int32, "idx") if idx is not None else None
+    if val.dtype == torch.float32:
+        code = lib().xyz_accumulate_f32(ip, _dev(val, torch.float32, "val"), n, _dev(grad, torch.float32, "grad"), k,
+                                        _stream(stream), flags)
+    else:
+        code = lib().xyz_accumulate_f64(ip, _dev(val, torch.float64, "val"), n, _dev(grad, torch.float64, "grad"), k,
+                                        _stream(stream), flags)
+    _check(code, "xyz_accumulate")
+
+
+# ---- C3 ------------------------------------------------------------------------------------------
+def covproj_fwd_bwd(J, W, S, g, out, gJ, gW, gS, flags: int = 0, stream=None) -> None:
+    """Per element: out = packed (J W) S (J W)^T and the adjoints of J (6), W (9), S (6) given g (3)."""
+    n = J.shape[0]
+    f = torch.float32
+    _check(lib().xyz_covproj_fwd_bwd_f32(_dev(J, f, "J"), _dev(W, f, "W"), _dev(S, f, "S"), _dev(g, f, "g"),
+                                         _dev(out, f, "out"), _dev(gJ, f, "gJ"), _dev(gW, f, "gW"), _dev(gS, f, "gS"),
+                                         n, _stream(stream), flags), "xyz_covproj_fwd_bwd_f32")
+
+
+# ---- C4 / C5 ---------------------------------------------------------------------------------------
+def launch_gaussian_splatting(gaussians, gradients, target_image, output_image, total_loss, image_width: int,
+                              image_height: int, num_gaussians: int, flags: int = 0, stream=None,
+                              rows: Optional[tuple] = None) -> None:
+    """Same argument order as the reference's launch_gaussian_splatting; tensors are (N, 9) / (P, 3) float32."""
+    f = torch.float32
+    args = [_dev(gaussians, f, "gaussians"), _dev(gradients, f, "gradients"), _dev(target_image, f, "target_image"),
+            _dev(output_image, f, "output_image"), _dev(total_loss, f, "total_loss"), image_width, image_height,
+            num_gaussians]
+    if rows is None:
+        code = lib().xyz_launch_gaussian_splatting(*args, _stream(stream), flags)
+    else:
+        code = lib().xyz_launch_gaussian_splatting_rows(*args, int(rows[0]), int(rows[1]), _stream(stream), flags)
+    _check(code, "xyz_launch_gaussian_splatting")
+
+
+def splat_last_stats() -> dict:
+    buf = (ctypes.c_longlong * 4)()
+    _check(lib().xyz_splat_last_stats(buf), "xyz_splat_last_stats")
+    return {"entries": buf[0], "tiles": buf[1], "longest_tile_list": buf[2], "pairs_per_pass": buf[3]}
+
+
+def splat_debug_binning(num_gaussians: int, num_tiles: int, entries: int):
+    import numpy as np
+    rects = np.zeros((max(num_gaussians, 1), 4), np.int32)
+    ranges = np.zeros((num_tiles, 2), np.int32)
+    ids = np.zeros(max(entries, 1), np.int32)
+    recs = np.zeros((max(num_gaussians, 1), 12), np.float32)
+    _check(lib().xyz_splat_debug_binning(rects.ctypes.data, ranges.ctypes.data, ids.ctypes.data, recs.ctypes.data),
+           "xyz_splat_debug_binning")
+    return rects[:num_gaussians], ranges, ids[:entries], recs[:num_gaussians]
+
+
+def zero_gradients(gradients: torch.Tensor, stream=None) -> None:
+    _check(lib().xyz_zero_gradients(_dev(gradients, torch.float32, "gradients"), gradients.shape[0], _stream(stream)),
+           "xyz_zero_gradients")
+
+
+def adam_step_individual(params, grads, adam, lr_center, lr_scale, lr_rotation, lr_color, lr_opacity, beta1=0.9,
+                         beta2=0.999, epsilon=1e-8, iteration=1, stream=None) -> None:
+    f = torch.float32
+    lr = (ctypes.c_float * 5)(lr_center, lr_scale, lr_rotation, lr_color, lr_opacity)
+    _check(lib().xyz_adam_step_individual(_dev(params, f, "params"), _dev(grads, f, "grads"), _dev(adam, f, "adam"),
+                                          params.shape[0], lr, beta1, beta2, epsilon, iteration, _stream(stream)),
+           "xyz_adam_step_individual")
+
+
+def adam_step(params, grads, adam, learning_rate, beta1=0.9, beta2=0.999, epsilon=1e-8, iteration=1, stream=None) -> None:
+    f = torch.float32
+    _check(lib().xyz_adam_step(_dev(params, f, "params"), _dev(grads, f, "grads"), _dev(adam, f, "adam"),
+                               params.shape[0], learning_rate, beta1, beta2, epsilon, iteration, _stream(stream)),
+           "xyz_adam_step")

@@ -1,0 +1,246 @@
+// csrc/accumulate_kernels.cu -- C2: accumulation of per-element gradients into K shared
+// parameters: grad[idx[i]] += val[i].
+//
+// What it replaces (reference): every thread calling VariableRef::add_grad = atomicAdd on the
+// shared parameter's gradient (include/xyz_autodiff/variable.cuh:48-50), i.e. E same-address
+// L2 atomics (tests/test_parallel_gradient_accumulation.cu:25-49; on __shared__ memory:
+// tests/test_shared_memory_atomic.cu:29-64).
+//
+// Design (no floating-point atomics on the hot path):
+//   * every WARP owns a private K-bin table in shared memory (fp32 shared atomics are CAS loops
+//     on sm_100a -- ATOMS.CAST.SPIN -- so they are avoided altogether);
+//   * a warp consumes 128 consecutive elements per step (int4 + float4 per lane, fully coalesced)
+//     as 4 batches of 32; within a batch `match.any` finds lanes that hit the same bin, a shuffle
+//     tree folds each group onto its lowest lane, and that lane does a plain LDS/FADD/STS on the
+//     warp's table (distinct bins inside a batch => no race; the common no-duplicate batch skips
+//     the tree);
+//   * the CTA adds its 8 tables in warp order, then either
+//       fast:          one red.global.add.v4.f32 per 4 bins into grad (K/4 vector REDs per CTA), or
+//       deterministic: writes a partial row; a second tiny kernel adds the rows in CTA order.
+//   Element -> warp assignment is static, so the deterministic mode is bit-identical run to run.
+// 8 algorithmic bytes per element (4 with implicit ids) -> HBM bound once contention is gone.
+#include "common.cuh"
+
+namespace xyzb {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+constexpr int kCtasPerSM = 4;
+constexpr unsigned kFull = 0xffffffffu;
+
+// Fold the values of all lanes in `peers` (lanes holding the same bin) onto the lowest lane of the
+// group.  Fixed pairing order: deterministic.  Every lane of the warp must call it.
+template <class T>
+__device__ __forceinline__ T reduce_peers(unsigned peers, T x, int lane) {
+    int rel = __popc(peers & ((1u << lane) - 1u));   // my rank inside the group
+    unsigned above = peers & ~((2u << lane) - 1u);   // group members in higher lanes
+    while (__any_sync(kFull, above != 0u)) {
+        const int next = __ffs(above);               // 1-based lane of the next higher member, 0 = none
+        const T t = __shfl_sync(kFull, x, (next - 1) & 31);
+        if (next) x += t;
+        // members with an odd rank have been absorbed by their lower neighbour: drop them everywhere
+        const unsigned alive = __ballot_sync(kFull, (rel & 1) == 0);
+        above &= alive;
+        rel >>= 1;
+    }
+    return x;
+}
+
+template <class T>
+__device__ __forceinline__ void warp_batch(T* table, int id, T v, int k, int lane) {
+    const bool valid = (id >= 0) && (id < k);
+    const int key = valid ? id : (-1 - lane);        // invalid lanes never match anybody
+    const unsigned peers = __match_any_sync(kFull, key);
+    if (peers == kFull) {                            // whole batch on one bin (the reference's own pattern)
+        const T s = warp_sum(v);
+        if (lane == 0 && valid) table[id] += s;
+    } else {
+        const bool alone = (peers == (1u << lane));
+        if (!__all_sync(kFull, alone)) v = reduce_peers(peers, v, lane);
+        if (valid && lane == __ffs(peers) - 1) table[id] += v;
+    }
+    __syncwarp();
+}
+
+template <class T> struct Vec4;
+template <> struct Vec4<float> { using type = float4; };
+template <> struct Vec4<double> { using type = double4; };
+
+// tables: kWarps x k of T in dynamic shared memory.
+// kVec: idx/val 16-byte aligned (vector loads).  kImplicit: id = i mod k, idx ignored.
+template <class T, bool kVec, bool kImplicit, bool kDeterministic>
+__global__ void __launch_bounds__(kThreads, kCtasPerSM)
+    accumulate_kernel(const int32_t* __restrict__ idx, const T* __restrict__ val, long long n, T* grad, int k,
+                      T* partial_rows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* tables = reinterpret_cast<T*>(smem_raw);
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (int i = tid; i < kWarps * k; i += kThreads) tables[i] = T(0);
+    __syncthreads();
+    T* table = tables + static_cast<size_t>(warp) * k;
+
+    const long long n_chunks = (n + 127) / 128;
+    const long long gw = static_cast<long long>(blockIdx.x) * kWarps + warp;
+    const long long wstride = static_cast<long long>(gridDim.x) * kWarps;
+    for (long long c = gw; c < n_chunks; c += wstride) {
+        const long long e0 = c * 128 + lane * 4;
+        int id[4];
+        T v[4];
+        if (kVec && e0 + 4 <= n) {
+            if constexpr (kImplicit) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) id[j] = static_cast<int>((e0 + j) % k);
+            } else {
+                const int4 q = __ldcs(reinterpret_cast<const int4*>(idx + e0));
+                id[0] = q.x; id[1] = q.y; id[2] = q.z; id[3] = q.w;
+            }
+            if constexpr (sizeof(T) == 4) {
+                const float4 f = __ldcs(reinterpret_cast<const float4*>(val + e0));
+                v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+            } else {
+                const double2 f0 = __ldcs(reinterpret_cast<const double2*>(val + e0));
+                const double2 f1 = __ldcs(reinterpret_cast<const double2*>(val + e0 + 2));
+                v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long e = e0 + j;
+                if (e < n) {
+                    id[j] = kImplicit ? static_cast<int>(e % k) : __ldg(idx + e);
+                    v[j] = __ldg(val + e);
+                } else {
+                    id[j] = -1;
+                    v[j] = T(0);
+                }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < 4; ++j) warp_batch<T>(table, id[j], v[j], k, lane);
+    }
+    __syncthreads();
+
+    // CTA: add the warps' tables in warp order, 4 bins per thread-step
+    if constexpr (kDeterministic) {
+        T* row = partial_rows + static_cast<size_t>(blockIdx.x) * k;
+        for (int b = tid; b < k; b += kThreads) {
+            T s = T(0);
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) s += tables[static_cast<size_t>(w) * k + b];
+            row[b] = s;
+        }
+    } else {
+        if constexpr (sizeof(T) == 4) {
+            const bool v4 = ((k & 3) == 0) && ((reinterpret_cast<uintptr_t>(grad) & 15u) == 0);
+            if (v4) {
+                for (int b = tid * 4; b < k; b += kThreads * 4) {
+                    float s[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+                    for (int w = 0; w < kWarps; ++w) {
+                        const float4 t = *reinterpret_cast<const float4*>(tables + static_cast<size_t>(w) * k + b);
+                        s[0] += t.x; s[1] += t.y; s[2] += t.z; s[3] += t.w;
+                    }
+                    if (s[0] != 0.f || s[1] != 0.f || s[2] != 0.f || s[3] != 0.f)
+                        red_add_v4(reinterpret_cast<float*>(grad) + b, s[0], s[1], s[2], s[3]);
+                }
+                return;
+            }
+        }
+        for (int b = tid; b < k; b += kThreads) {
+            T s = T(0);
+#pragma unroll
+            for (int w = 0; w < kWarps; ++w) s += tables[static_cast<size_t>(w) * k + b];
+            if (s != T(0)) atomicAdd(grad + b, s);
+        }
+    }
+}
+
+// deterministic finish: grad[b] += sum over rows in CTA order
+template <class T>
+__global__ void accumulate_finish_kernel(const T* __restrict__ rows, int n_rows, T* grad, int k) {
+    const int b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= k) return;
+    T s = T(0);
+    for (int r = 0; r < n_rows; ++r) s += rows[static_cast<size_t>(r) * k + b];
+    grad[b] += s;
+}
+
+// K too large for shared-memory tables: coalesced loads + native global REDs (what the reference does,
+// minus its strided access); never deterministic.
+template <class T>
+__global__ void accumulate_global_kernel(const int32_t* __restrict__ idx, const T* __restrict__ val, long long n,
+                                         T* grad, int k) {
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
+         i += static_cast<long long>(gridDim.x) * blockDim.x) {
+        const int id = idx ? __ldg(idx + i) : static_cast<int>(i % k);
+        if (id >= 0 && id < k) atomicAdd(grad + id, __ldg(val + i));
+    }
+}
+
+template <class T, bool kVec, bool kImplicit>
+int launch_tables(const int32_t* idx, const T* val, long long n, T* grad, int k, cudaStream_t st, bool deterministic,
+                  int grid, size_t smem) {
+    if (deterministic) {
+        void* scratch = nullptr;
+        int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(grid) * k * sizeof(T), &scratch);
+        if (err) return err;
+        T* rows = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+        auto kern = accumulate_kernel<T, kVec, kImplicit, true>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        kern<<<grid, kThreads, smem, st>>>(idx, val, n, grad, k, rows);
+        accumulate_finish_kernel<T><<<(k + 255) / 256, 256, 0, st>>>(rows, grid, grad, k);
+        count_launch(2);
+    } else {
+        auto kern = accumulate_kernel<T, kVec, kImplicit, false>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        kern<<<grid, kThreads, smem, st>>>(idx, val, n, grad, k, nullptr);
+        count_launch();
+    }
+    return last_error();
+}
+
+template <class T>
+int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, void* stream, int flags) {
+    if (n < 0 || k <= 0 || !grad) return XYZ_ERR_INVALID_ARGUMENT;
+    if (n == 0) return 0;
+    if (!val) return XYZ_ERR_INVALID_ARGUMENT;
+    const bool implicit = (idx == nullptr);
+    if (implicit && !(flags & XYZ_FLAG_IMPLICIT_IDS)) return XYZ_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool deterministic = (flags & XYZ_FLAG_DETERMINISTIC) != 0;
+    const size_t smem = static_cast<size_t>(kWarps) * k * sizeof(T);
+    const int sms = sm_count();
+    if (smem > 200 * 1024) {
+        if (deterministic) return XYZ_ERR_INVALID_ARGUMENT;  // no fixed-order path for K this large
+        accumulate_global_kernel<T><<<sms * 8, 256, 0, st>>>(idx, val, n, grad, k);
+        count_launch();
+        return last_error();
+    }
+    int ctas_per_sm = static_cast<int>((220 * 1024) / (smem + 1024));
+    if (ctas_per_sm > kCtasPerSM) ctas_per_sm = kCtasPerSM;
+    if (ctas_per_sm < 1) ctas_per_sm = 1;
+    const long long n_chunks = (n + 127) / 128;
+    long long want = (n_chunks + kWarps - 1) / kWarps;
+    const long long max_ctas = static_cast<long long>(sms) * ctas_per_sm;
+    const int grid = static_cast<int>(want < max_ctas ? want : max_ctas);
+    const bool vec = aligned16(val) && (implicit || aligned16(idx));
+    if (vec) {
+        return implicit ? launch_tables<T, true, true>(idx, val, n, grad, k, st, deterministic, grid, smem)
+                        : launch_tables<T, true, false>(idx, val, n, grad, k, st, deterministic, grid, smem);
+    }
+    return implicit ? launch_tables<T, false, true>(idx, val, n, grad, k, st, deterministic, grid, smem)
+                    : launch_tables<T, false, false>(idx, val, n, grad, k, st, deterministic, grid, smem);
+}
+
+}  // namespace
+}  // namespace xyzb
+
+extern "C" int xyz_accumulate_f32(const int32_t* idx, const float* val, long long n, float* grad, int k, void* stream,
+                                  int flags) {
+    return xyzb::accumulate<float>(idx, val, n, grad, k, stream, flags);
+}
+extern "C" int xyz_accumulate_f64(const int32_t* idx, const double* val, long long n, double* grad, int k,
+                                  void* stream, int flags) {
+    return xyzb::accumulate<double>(idx, val, n, grad, k, stream, flags);
+}

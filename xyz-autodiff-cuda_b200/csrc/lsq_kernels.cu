@@ -1,0 +1,229 @@
+// csrc/lsq_kernels.cu -- C1: batched least-squares forward + reverse in fp64 with the four
+// shared-parameter adjoints reduced on chip.
+//
+// What it replaces (reference): compute_gradient_kernel<Analytical>
+// (examples/optimization/tests/test_linear_regression_gradient.cu:33-79) and
+// parallel_gradient_computation_kernel (examples/optimization/linear_regression_sgd.cu:86-123):
+// one thread per DataPoint builds the 9-node graph r = (a-x1)^2 + b (c-x2)^2 + d - y, loss = r^2,
+// calls run(), and every thread issues 4 same-address fp64 atomicAdds (variable.cuh:48-50).
+//
+// Here: node values and adjoints stay in registers, each thread folds many points into 5
+// private fp64 sums, a warp-shuffle tree + one shared-memory step reduce the CTA, each CTA
+// writes ONE partial row, and the last CTA to finish (ticket) adds the rows in CTA order into
+// params->grad.  No floating-point atomics at all, so the result is bit-identical run to run
+// (XYZ_FLAG_DETERMINISTIC is always honoured).  24 algorithmic bytes per point -> HBM bound;
+// points arrive by TMA 1-D bulk copies (256 points = 6 KB contiguous per tile, 4-stage ring).
+#include "common.cuh"
+
+namespace xyzb {
+namespace {
+
+constexpr int kThreads = 256;
+constexpr int kTileP = 256;  // points per tile
+constexpr int kStages = 4;
+constexpr int kCtasPerSM = 4;
+constexpr int kAcc = 5;  // ga gb gc gd loss
+
+struct LsqSmem {
+    double pts[kStages][kTileP * 3];
+    uint64_t full[kStages];
+    double red[kThreads / 32][kAcc];
+    int is_last;
+};
+
+struct LsqAcc {
+    double v[kAcc];
+};
+
+__device__ __forceinline__ void lsq_point(double x1, double x2, double yt, double a, double b, double c, double d,
+                                          bool residual_only, LsqAcc& acc) {
+    const double u = a - x1;          // sub_constant(a, x1)
+    const double v = c - x2;          // sub_constant(c, x2)
+    const double v2 = v * v;          // squared
+    const double r = ((u * u + b * v2) + d) - yt;
+    const double seed = residual_only ? 1.0 : 2.0 * r;  // squared backward: g * 2.0 * x with g = 1
+    acc.v[0] += seed * 2.0 * u;
+    acc.v[1] += seed * v2;
+    acc.v[2] += seed * b * 2.0 * v;
+    acc.v[3] += seed;
+    acc.v[4] += residual_only ? r : r * r;
+}
+
+// partials: [gridDim.x][kAcc]; ticket: one unsigned int, zero before the launch, reset by the last CTA.
+template <bool kTma>
+__global__ void __launch_bounds__(kThreads, kCtasPerSM)
+    lsq_grad_kernel(const double* __restrict__ data, long long n_points, xyz_lsq_parameters* params, double* loss_sum,
+                    double* partials, unsigned int* ticket, int residual_only) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    LsqSmem& sm = *reinterpret_cast<LsqSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    const double a = params->value[0], b = params->value[1], c = params->value[2], d = params->value[3];
+    LsqAcc acc;
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc.v[k] = 0.0;
+
+    const long long n_tiles = n_points / kTileP;
+    const long long first = blockIdx.x, stride = gridDim.x;
+    if constexpr (kTma) {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < kStages; ++s) {
+                const long long t = first + s * stride;
+                if (t < n_tiles) {
+                    mbar_arrive_expect_tx(&sm.full[s], kTileP * 24);
+                    bulk_load(sm.pts[s], data + t * kTileP * 3, kTileP * 24, &sm.full[s]);
+                }
+            }
+        }
+        int it = 0;
+        for (long long tile = first; tile < n_tiles; tile += stride, ++it) {
+            const int s = it % kStages;
+            mbar_wait(&sm.full[s], (it / kStages) & 1);
+            const double x1 = sm.pts[s][tid * 3], x2 = sm.pts[s][tid * 3 + 1], yt = sm.pts[s][tid * 3 + 2];
+            __syncthreads();  // stage consumed
+            if (tid == 0) {
+                const long long nt = tile + static_cast<long long>(kStages) * stride;
+                if (nt < n_tiles) {
+                    mbar_arrive_expect_tx(&sm.full[s], kTileP * 24);
+                    bulk_load(sm.pts[s], data + nt * kTileP * 3, kTileP * 24, &sm.full[s]);
+                }
+            }
+            lsq_point(x1, x2, yt, a, b, c, d, residual_only != 0, acc);
+        }
+    }
+    // tail (and the whole range when the base pointer is not 16-byte aligned): plain loads
+    {
+        const long long begin = kTma ? n_tiles * kTileP : 0;
+        for (long long i = begin + blockIdx.x * static_cast<long long>(kThreads) + tid; i < n_points;
+             i += static_cast<long long>(gridDim.x) * kThreads) {
+            lsq_point(__ldg(data + 3 * i), __ldg(data + 3 * i + 1), __ldg(data + 3 * i + 2), a, b, c, d,
+                      residual_only != 0, acc);
+        }
+    }
+
+    // CTA reduction: shuffle tree per warp, then 8 rows in shared memory, fixed order
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc.v[k] = warp_sum(acc.v[k]);
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) sm.red[tid >> 5][k] = acc.v[k];
+    }
+    __syncthreads();
+    if (tid < kAcc) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) s += sm.red[w][tid];
+        partials[static_cast<size_t>(blockIdx.x) * kAcc + tid] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) {
+        const unsigned int done = atomicAdd(ticket, 1u);
+        sm.is_last = (done == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!sm.is_last) return;
+    __threadfence();
+    // last CTA: one warp sums the rows in CTA order: lane-strided partial sums, then a shuffle tree
+    if (tid < 32) {
+        double s[kAcc];
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) s[k] = 0.0;
+        for (unsigned int r = tid; r < gridDim.x; r += 32) {
+#pragma unroll
+            for (int k = 0; k < kAcc; ++k) s[k] += __ldcg(partials + static_cast<size_t>(r) * kAcc + k);
+        }
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) s[k] = warp_sum(s[k]);
+        if (tid == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) params->grad[k] += s[k];
+            if (loss_sum) *loss_sum += s[4];
+            *ticket = 0u;
+        }
+    }
+}
+
+__global__ void lsq_sgd_update_kernel(xyz_lsq_parameters* p, double lr, double batch) {
+    const int i = threadIdx.x;
+    if (i < 4) p->value[i] -= lr * p->grad[i] / batch;
+}
+
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
+__global__ void lsq_select_batch_kernel(const xyz_data_point* __restrict__ data, long long n_total,
+                                        xyz_data_point* __restrict__ batch, long long batch_size, uint64_t seed,
+                                        uint64_t epoch) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= batch_size) return;
+    const uint64_t h = splitmix64(splitmix64(seed ^ (epoch * 0xD1B54A32D192ED03ull)) + static_cast<uint64_t>(i));
+    batch[i] = data[h % static_cast<uint64_t>(n_total)];
+}
+
+}  // namespace
+}  // namespace xyzb
+
+extern "C" int xyz_lsq_grad_f64(const xyz_data_point* data, long long n_points, xyz_lsq_parameters* params,
+                                double* loss_sum, void* stream, int flags) {
+    using namespace xyzb;
+    if (n_points < 0 || !params) return XYZ_ERR_INVALID_ARGUMENT;
+    if (n_points == 0) return 0;
+    if (!data) return XYZ_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long max_ctas = static_cast<long long>(sm_count()) * kCtasPerSM;
+    const long long want = (n_points + kTileP - 1) / kTileP;
+    const int grid = static_cast<int>(want < max_ctas ? want : max_ctas);
+    void* scratch = nullptr;
+    const size_t bytes = 256 + static_cast<size_t>(max_ctas) * kAcc * sizeof(double);
+    int err = scratch_get(SCRATCH_REDUCE, bytes, &scratch);
+    if (err) return err;
+    // scratch arenas are zero-filled when allocated and every kernel leaves its ticket at zero
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
+    double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+    const int residual_only = (flags & XYZ_FLAG_RESIDUAL_ONLY) ? 1 : 0;
+    const double* d = reinterpret_cast<const double*>(data);
+    if (aligned16(data) && n_points >= kTileP) {
+        cudaFuncSetAttribute(lsq_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(LsqSmem)));
+        lsq_grad_kernel<true><<<grid, kThreads, sizeof(LsqSmem), st>>>(d, n_points, params, loss_sum, partials, ticket,
+                                                                       residual_only);
+    } else {
+        lsq_grad_kernel<false><<<grid, kThreads, sizeof(LsqSmem), st>>>(d, n_points, params, loss_sum, partials, ticket,
+                                                                        residual_only);
+    }
+    count_launch();
+    return last_error();
+}
+
+extern "C" int xyz_lsq_sgd_update_f64(xyz_lsq_parameters* params, double learning_rate, long long batch_size,
+                                      void* stream) {
+    using namespace xyzb;
+    if (!params || batch_size <= 0) return XYZ_ERR_INVALID_ARGUMENT;
+    lsq_sgd_update_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(params, learning_rate,
+                                                                            static_cast<double>(batch_size));
+    count_launch();
+    return last_error();
+}
+
+extern "C" int xyz_lsq_select_batch(const xyz_data_point* data, long long n_total, xyz_data_point* batch,
+                                    long long batch_size, uint64_t seed, uint64_t epoch, void* stream) {
+    using namespace xyzb;
+    if (!data || !batch || n_total <= 0 || batch_size < 0) return XYZ_ERR_INVALID_ARGUMENT;
+    if (batch_size == 0) return 0;
+    const int grid = static_cast<int>((batch_size + 255) / 256);
+    lsq_select_batch_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(data, n_total, batch, batch_size, seed,
+                                                                                  epoch);
+    count_launch();
+    return last_error();
+}

@@ -1,0 +1,69 @@
+// csrc/splat_common.cuh -- shared definitions of the splat pipeline (C4/C5).
+//
+// The reference kernel (examples/mini-gaussian-splatting/gaussian_splatting_kernel.cu:8-112)
+// evaluates EVERY (pixel, Gaussian) pair twice and issues 9 scalar atomicAdds per pair.  Its cull
+// (:48-50, :90-92) is dead code.  This pipeline produces the same image, loss and
+// gradients from
+//   1. splat_preprocess_kernel : per Gaussian, once: exp(scale), R(theta), Sigma, Sigma^-1,
+//      sigmoid(opacity) -> a 48-byte record; plus the rectangle of 16x16 tiles outside which the
+//      pair weight exp(-d2/2) is EXACTLY 0.0f (so skipping those pairs cannot change any result);
+//   2. integer work: (tile, Gaussian) keys in Gaussian order -> stable radix sort by tile ->
+//      per-tile [begin, end) ranges (each tile list ascending in Gaussian index = the reference's
+//      summation order);
+//   3. splat_forward_kernel  : one CTA per tile, one pixel per thread, records staged in shared
+//      memory; writes the image and one loss partial per tile;
+//   4. splat_backward_kernel : one THREAD per (tile, Gaussian) list entry looping over the tile's
+//      256 pixels (pixel residuals broadcast from shared memory), 9 adjoint sums in registers,
+//      the per-Gaussian chain rule applied once per entry, then 9 REDs (or a partial row in
+//      deterministic mode) -- instead of 9 atomics per PAIR.
+#pragma once
+
+#include "common.cuh"
+
+namespace xyzb {
+
+constexpr int kTile = 16;                 // TILE_SIZE, gaussian_splatting_kernel.cuh:21
+constexpr int kTilePixels = kTile * kTile;
+constexpr int kRecFloats = 12;            // {cx, cy, ia, ib, ic, sigmoid(opacity), r, g, b, 0, 0, 0}
+
+// exp(-d2/2) == 0.0f exactly beyond these:
+//   fast-math/FTZ (ex2.approx.ftz): 0.5*d2*log2(e) > 126   <=> 0.5*d2 > 87.34 ; margin -> 88
+//   IEEE expf:                      0.5*d2 > 103.98 (below half the smallest denormal) ; margin -> 104.5
+constexpr float kD2MaxFast = 176.0f;
+constexpr float kD2MaxPrecise = 209.0f;
+
+struct SplatView {  // what one launch renders
+    int width, height, num_gaussians;
+    int row_begin, row_end;  // pixel rows [row_begin, row_end)
+    int tiles_x, tiles_y;    // full image, in tiles
+};
+
+struct SplatBuffers {  // device scratch of one launch (library-owned)
+    float4* records;          // N x 3 float4
+    int4* rects;              // N: tx0, ty0, tx1, ty1 (half-open)
+    unsigned int* touched;    // N: tiles per Gaussian
+    unsigned long long* offsets;  // N: inclusive scan of touched (64-bit: N x tiles can exceed 2^32)
+    unsigned int* keys_in;    // entries: tile id, Gaussian order
+    unsigned int* keys_out;   // entries: sorted
+    unsigned int* vals_in;    // entries: entry index in Gaussian order (== position)
+    unsigned int* vals_out;   // entries: sorted -> original entry index
+    int* sorted_gid;          // entries: Gaussian id per sorted entry
+    int2* tile_ranges;        // tiles: [begin, end)
+    float* tile_loss;         // tiles
+    float* entry_grads;       // deterministic mode: entries x 9 (indexed by ORIGINAL entry index)
+};
+
+// flavour launchers (splat_fast.cu is built with -use_fast_math like the reference's training app,
+// splat_precise.cu without, like the reference's tests)
+int splat_forward_launch_fast(const SplatView&, const SplatBuffers&, const float* target, float* output,
+                              cudaStream_t);
+int splat_forward_launch_precise(const SplatView&, const SplatBuffers&, const float* target, float* output,
+                                 cudaStream_t);
+int splat_backward_launch_fast(const SplatView&, const SplatBuffers&, const xyz_gaussian_params* params,
+                               xyz_gaussian_grads* grads, const float* target, const float* output,
+                               long long entries, bool deterministic, cudaStream_t);
+int splat_backward_launch_precise(const SplatView&, const SplatBuffers&, const xyz_gaussian_params* params,
+                                  xyz_gaussian_grads* grads, const float* target, const float* output,
+                                  long long entries, bool deterministic, cudaStream_t);
+
+}  // namespace xyzb

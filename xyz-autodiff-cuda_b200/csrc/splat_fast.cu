@@ -1,0 +1,3 @@
+// csrc/splat_fast.cu -- fast-math flavour of the splat kernels (built with -use_fast_math).
+#define XYZ_SPLAT_FLAVOR fast
+#include "splat_kernels.cuh"

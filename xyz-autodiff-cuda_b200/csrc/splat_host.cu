@@ -1,0 +1,352 @@
+// csrc/splat_host.cu -- host side of the splat pipeline: per-Gaussian preprocessing, the integer
+// tile-binning work, scratch management and the C entry points that replace
+// launch_gaussian_splatting (reference examples/mini-gaussian-splatting/gaussian_splatting_kernel.cu:114-149).
+// See splat_common.cuh for the pipeline overview.  This translation unit is ALWAYS compiled with
+// IEEE arithmetic: the tile rectangles are integer results that the CPU oracle reproduces
+// bit for bit from the same record floats (oracle/xyz_oracle.cpp::tile_rect).
+#include <algorithm>
+#include <vector>
+
+#include <cub/device/device_radix_sort.cuh>
+#include <cub/device/device_scan.cuh>
+#include <cub/iterator/transform_input_iterator.cuh>
+
+#include "splat_common.cuh"
+
+namespace xyzb {
+namespace {
+
+// ---- 1. per-Gaussian records + tile rectangles -----------------------------------------------------
+// Every float op that feeds an integer decision is a single rounded IEEE operation (__f*_rn: no
+// FMA contraction), mirrored by oracle/xyz_oracle.cpp::tile_rect.
+__device__ __forceinline__ int4 gaussian_tile_rect(float cx, float cy, float ia, float ib, float ic, const SplatView& v,
+                                                   float d2max, int no_cull) {
+    const int ty_lo = v.row_begin / kTile, ty_hi = (v.row_end + kTile - 1) / kTile;
+    int4 r = make_int4(0, ty_lo, v.tiles_x, ty_hi);
+    const float det = __fsub_rn(__fmul_rn(ia, ic), __fmul_rn(ib, ib));
+    const bool ok = !no_cull && det > 0.0f && ia > 0.0f && ic > 0.0f && isfinite(det) && isfinite(cx) && isfinite(cy) &&
+                    isfinite(ia) && isfinite(ic);
+    if (ok) {
+        const float hx = __fadd_rn(__fmul_rn(__fsqrt_rn(__fdiv_rn(__fmul_rn(d2max, ic), det)), 1.001f), 1.0f);
+        const float hy = __fadd_rn(__fmul_rn(__fsqrt_rn(__fdiv_rn(__fmul_rn(d2max, ia), det)), 1.001f), 1.0f);
+        if (isfinite(hx) && isfinite(hy)) {
+            const float x_lo = floorf(__fsub_rn(cx, hx)), x_hi = ceilf(__fadd_rn(cx, hx));
+            const float y_lo = floorf(__fsub_rn(cy, hy)), y_hi = ceilf(__fadd_rn(cy, hy));
+            if (x_hi < 0.0f || y_hi < static_cast<float>(v.row_begin) || x_lo > static_cast<float>(v.width - 1) ||
+                y_lo > static_cast<float>(v.row_end - 1)) {
+                r = make_int4(0, 0, 0, 0);
+            } else {
+                const int xi0 = static_cast<int>(fmaxf(x_lo, 0.0f));
+                const int xi1 = static_cast<int>(fminf(x_hi, static_cast<float>(v.width - 1)));
+                const int yi0 = static_cast<int>(fmaxf(y_lo, static_cast<float>(v.row_begin)));
+                const int yi1 = static_cast<int>(fminf(y_hi, static_cast<float>(v.row_end - 1)));
+                r = make_int4(xi0 / kTile, yi0 / kTile, xi1 / kTile + 1, yi1 / kTile + 1);
+            }
+        }
+    }
+    return r;
+}
+
+__global__ void __launch_bounds__(256)
+    splat_preprocess_kernel(SplatView v, const xyz_gaussian_params* __restrict__ params, float4* __restrict__ records,
+                            int4* __restrict__ rects, unsigned int* __restrict__ touched, float d2max, int no_cull) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= v.num_gaussians) return;
+    const xyz_gaussian_params p = params[g];
+    // exp_logic.cuh:17-25, covariance_generation.cuh:154-172, sym_matrix2_inv_logic.cuh:21-40,
+    // math.cuh:200-204 (sigmoid) -- computed once per Gaussian instead of once per pair per pass
+    const float es0 = expf(p.scale[0]), es1 = expf(p.scale[1]);
+    const float ct = cosf(p.rotation[0]), sn = sinf(p.rotation[0]);
+    const float m00 = __fmul_rn(es0, ct), m01 = __fmul_rn(-es1, sn), m10 = __fmul_rn(es0, sn), m11 = __fmul_rn(es1, ct);
+    const float A = __fadd_rn(__fmul_rn(m00, m00), __fmul_rn(m01, m01));
+    const float B = __fadd_rn(__fmul_rn(m00, m10), __fmul_rn(m01, m11));
+    const float C = __fadd_rn(__fmul_rn(m10, m10), __fmul_rn(m11, m11));
+    float det = __fsub_rn(__fmul_rn(A, C), __fmul_rn(B, B));
+    if (fabsf(det) < 1e-8f) det = 1e-8f;
+    const float inv_det = __fdiv_rn(1.0f, det);
+    const float ia = __fmul_rn(C, inv_det), ib = __fmul_rn(-B, inv_det), ic = __fmul_rn(A, inv_det);
+    const float so = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-p.opacity[0])));
+    records[3 * g] = make_float4(p.center[0], p.center[1], ia, ib);
+    records[3 * g + 1] = make_float4(ic, so, p.color[0], p.color[1]);
+    records[3 * g + 2] = make_float4(p.color[2], 0.f, 0.f, 0.f);
+    const int4 r = gaussian_tile_rect(p.center[0], p.center[1], ia, ib, ic, v, d2max, no_cull);
+    rects[g] = r;
+    touched[g] = static_cast<unsigned int>((r.z - r.x) * (r.w - r.y));
+}
+
+// ---- 2. keys in Gaussian order ----------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+    splat_emit_keys_kernel(int n, int tiles_x, const int4* __restrict__ rects, const unsigned int* __restrict__ touched,
+                           const unsigned long long* __restrict__ offsets_incl, unsigned int* __restrict__ keys,
+                           unsigned int* __restrict__ vals) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const int4 r = rects[g];
+    unsigned int o = static_cast<unsigned int>(offsets_incl[g] - touched[g]);
+    for (int ty = r.y; ty < r.w; ++ty)
+        for (int tx = r.x; tx < r.z; ++tx) {
+            keys[o] = static_cast<unsigned int>(ty * tiles_x + tx);
+            vals[o] = o;
+            ++o;
+        }
+}
+
+// entry index in Gaussian order -> Gaussian id (binary search over the inclusive scan)
+__device__ __forceinline__ int entry_to_gaussian(const unsigned long long* __restrict__ offsets_incl, int n,
+                                                 unsigned int e) {
+    int lo = 0, hi = n - 1;  // first g with offsets_incl[g] > e
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (offsets_incl[mid] > e) hi = mid; else lo = mid + 1;
+    }
+    return lo;
+}
+
+// ---- per-tile ranges + Gaussian id per sorted entry ---------------------------------------------------
+__global__ void __launch_bounds__(256)
+    splat_ranges_kernel(long long entries, const unsigned int* __restrict__ keys_sorted,
+                        const unsigned int* __restrict__ vals_sorted, const unsigned long long* __restrict__ offsets_incl, int n,
+                        int2* __restrict__ tile_ranges, int* __restrict__ sorted_gid) {
+    const long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
+    if (i >= entries) return;
+    const unsigned int k = keys_sorted[i];
+    if (i == 0 || keys_sorted[i - 1] != k) tile_ranges[k].x = static_cast<int>(i);
+    if (i == entries - 1 || keys_sorted[i + 1] != k) tile_ranges[k].y = static_cast<int>(i + 1);
+    sorted_gid[i] = entry_to_gaussian(offsets_incl, n, vals_sorted[i]);
+}
+
+// ---- loss: tile partials summed in tile order (no float atomics) ---------------------------------------
+__global__ void __launch_bounds__(256) splat_loss_finish_kernel(const float* __restrict__ tile_loss, int tile_begin,
+                                                                 int tile_end, float* total_loss) {
+    __shared__ float s[256];
+    float acc = 0.f;
+    for (int t = tile_begin + threadIdx.x; t < tile_end; t += 256) acc += tile_loss[t];
+    s[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = 128; w > 0; w >>= 1) {
+        if (threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total_loss += s[0];  // the reference accumulates into the caller's value
+}
+
+// ---- deterministic mode: per-Gaussian sum of its entries' rows, in entry order ----------------------------
+__global__ void __launch_bounds__(256)
+    splat_grads_finish_kernel(int n, const unsigned int* __restrict__ touched,
+                              const unsigned long long* __restrict__ offsets_incl, const float* __restrict__ entry_grads,
+                              xyz_gaussian_grads* grads) {
+    const int g = blockIdx.x * blockDim.x + threadIdx.x;
+    if (g >= n) return;
+    const unsigned int end = static_cast<unsigned int>(offsets_incl[g]), begin = end - touched[g];
+    float s[9] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    for (unsigned int e = begin; e < end; ++e) {
+#pragma unroll
+        for (int k = 0; k < 9; ++k) s[k] += entry_grads[static_cast<size_t>(e) * 9 + k];
+    }
+    float* gg = reinterpret_cast<float*>(grads + g);
+#pragma unroll
+    for (int k = 0; k < 9; ++k) gg[k] += s[k];
+}
+
+struct ToU64 {
+    __host__ __device__ unsigned long long operator()(unsigned int x) const { return x; }
+};
+using TouchedIter = cub::TransformInputIterator<unsigned long long, ToU64, const unsigned int*>;
+
+struct LastLaunch {
+    bool valid = false;
+    SplatView view{};
+    SplatBuffers buf{};
+    long long entries = 0;
+    long long stats[4] = {0, 0, 0, 0};
+};
+thread_local LastLaunch g_last;
+
+inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
+
+int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients, const float* target,
+                 float* output, float* total_loss, int W, int H, int N, int row_begin, int row_end, void* stream,
+                 int flags) {
+    if (W <= 0 || H <= 0 || N < 0 || row_begin < 0 || row_end > H || row_begin > row_end) return XYZ_ERR_INVALID_ARGUMENT;
+    if (!target || !output || !total_loss || (N > 0 && (!gaussians || !gradients))) return XYZ_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const bool precise = (flags & XYZ_FLAG_PRECISE_MATH) != 0;
+    const bool deterministic = (flags & XYZ_FLAG_DETERMINISTIC) != 0;
+    const int no_cull = (flags & XYZ_FLAG_NO_CULL) ? 1 : 0;
+
+    SplatView v;
+    v.width = W; v.height = H; v.num_gaussians = N;
+    v.row_begin = row_begin; v.row_end = row_end;
+    v.tiles_x = (W + kTile - 1) / kTile;
+    v.tiles_y = (H + kTile - 1) / kTile;
+    const int n_tiles = v.tiles_x * v.tiles_y;
+    const int ng = N > 0 ? N : 1;
+
+    // ---- fixed-size scratch (depends on N and the tile count only)
+    size_t off = 0;
+    auto take = [&off](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+    const size_t o_rec = take(sizeof(float4) * 3 * ng), o_rect = take(sizeof(int4) * ng),
+                 o_touched = take(sizeof(unsigned int) * ng), o_offsets = take(sizeof(unsigned long long) * ng),
+                 o_ranges = take(sizeof(int2) * n_tiles), o_tloss = take(sizeof(float) * n_tiles);
+    size_t scan_tmp_bytes = 0;
+    cub::DeviceScan::InclusiveSum(nullptr, scan_tmp_bytes, TouchedIter(nullptr, ToU64()),
+                                  static_cast<unsigned long long*>(nullptr), ng, st);
+    const size_t o_scan_tmp = take(scan_tmp_bytes + 16);
+    unsigned char* base = nullptr;
+    int err = scratch_get(SCRATCH_SPLAT, off, reinterpret_cast<void**>(&base));
+    if (err) return err;
+    SplatBuffers b{};
+    b.records = reinterpret_cast<float4*>(base + o_rec);
+    b.rects = reinterpret_cast<int4*>(base + o_rect);
+    b.touched = reinterpret_cast<unsigned int*>(base + o_touched);
+    b.offsets = reinterpret_cast<unsigned long long*>(base + o_offsets);
+    b.tile_ranges = reinterpret_cast<int2*>(base + o_ranges);
+    b.tile_loss = reinterpret_cast<float*>(base + o_tloss);
+
+    cudaError_t ce = cudaMemsetAsync(b.tile_ranges, 0, sizeof(int2) * n_tiles, st);
+    if (ce != cudaSuccess) return static_cast<int>(ce);
+
+    long long entries = 0;
+    if (N > 0) {
+        splat_preprocess_kernel<<<(N + 255) / 256, 256, 0, st>>>(v, gaussians, b.records, b.rects, b.touched,
+                                                                 precise ? kD2MaxPrecise : kD2MaxFast, no_cull);
+        count_launch();
+        ce = cub::DeviceScan::InclusiveSum(base + o_scan_tmp, scan_tmp_bytes, TouchedIter(b.touched, ToU64()), b.offsets,
+                                           N, st);
+        if (ce != cudaSuccess) return static_cast<int>(ce);
+        count_launch();
+        // the list length is data dependent: one 8-byte read-back (the only synchronisation)
+        unsigned long long total = 0;
+        ce = cudaMemcpyAsync(&total, b.offsets + (N - 1), sizeof(total), cudaMemcpyDeviceToHost, st);
+        if (ce != cudaSuccess) return static_cast<int>(ce);
+        ce = cudaStreamSynchronize(st);
+        if (ce != cudaSuccess) return static_cast<int>(ce);
+        entries = static_cast<long long>(total);
+    }
+    if (entries >= (1LL << 31) - 512) return XYZ_ERR_WORKSPACE;
+
+    // ---- entry-sized scratch
+    int key_bits = 1;
+    while ((1 << key_bits) < n_tiles) ++key_bits;
+    const long long ne = entries > 0 ? entries : 1;
+    size_t soff = 0;
+    auto stake = [&soff](size_t bytes) { size_t o = soff; soff += align_up(bytes); return o; };
+    const size_t o_kin = stake(4 * ne), o_kout = stake(4 * ne), o_vin = stake(4 * ne), o_vout = stake(4 * ne),
+                 o_gid = stake(4 * ne), o_eg = stake(deterministic ? 36 * ne : 0);
+    size_t sort_tmp_bytes = 0;
+    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, static_cast<unsigned int*>(nullptr),
+                                    static_cast<unsigned int*>(nullptr), static_cast<unsigned int*>(nullptr),
+                                    static_cast<unsigned int*>(nullptr), static_cast<int>(ne), 0, key_bits, st);
+    const size_t o_sort_tmp = stake(sort_tmp_bytes + 16);
+    unsigned char* sbase = nullptr;
+    err = scratch_get(SCRATCH_SPLAT_SORT, soff, reinterpret_cast<void**>(&sbase));
+    if (err) return err;
+    b.keys_in = reinterpret_cast<unsigned int*>(sbase + o_kin);
+    b.keys_out = reinterpret_cast<unsigned int*>(sbase + o_kout);
+    b.vals_in = reinterpret_cast<unsigned int*>(sbase + o_vin);
+    b.vals_out = reinterpret_cast<unsigned int*>(sbase + o_vout);
+    b.sorted_gid = reinterpret_cast<int*>(sbase + o_gid);
+    b.entry_grads = deterministic ? reinterpret_cast<float*>(sbase + o_eg) : nullptr;
+
+    if (entries > 0) {
+        splat_emit_keys_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, v.tiles_x, b.rects, b.touched, b.offsets, b.keys_in,
+                                                                b.vals_in);
+        count_launch();
+        ce = cub::DeviceRadixSort::SortPairs(sbase + o_sort_tmp, sort_tmp_bytes, b.keys_in, b.keys_out, b.vals_in,
+                                             b.vals_out, static_cast<int>(entries), 0, key_bits, st);
+        if (ce != cudaSuccess) return static_cast<int>(ce);
+        count_launch(3);
+        splat_ranges_kernel<<<static_cast<unsigned int>((entries + 255) / 256), 256, 0, st>>>(
+            entries, b.keys_out, b.vals_out, b.offsets, N, b.tile_ranges, b.sorted_gid);
+        count_launch();
+    }
+
+    err = precise ? splat_forward_launch_precise(v, b, target, output, st)
+                  : splat_forward_launch_fast(v, b, target, output, st);
+    if (err) return err;
+    {
+        const int ty0 = row_begin / kTile, ty1 = (row_end + kTile - 1) / kTile;
+        if (ty1 > ty0) {
+            splat_loss_finish_kernel<<<1, 256, 0, st>>>(b.tile_loss, ty0 * v.tiles_x, ty1 * v.tiles_x, total_loss);
+            count_launch();
+        }
+    }
+    err = precise ? splat_backward_launch_precise(v, b, gaussians, gradients, target, output, entries, deterministic, st)
+                  : splat_backward_launch_fast(v, b, gaussians, gradients, target, output, entries, deterministic, st);
+    if (err) return err;
+    if (deterministic && entries > 0) {
+        splat_grads_finish_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, b.touched, b.offsets, b.entry_grads, gradients);
+        count_launch();
+    }
+
+    g_last.valid = true;
+    g_last.view = v;
+    g_last.buf = b;
+    g_last.entries = entries;
+    g_last.stats[0] = entries;
+    g_last.stats[1] = n_tiles;
+    g_last.stats[2] = -1;  // longest list: filled lazily by xyz_splat_last_stats
+    g_last.stats[3] = entries * kTilePixels;
+    return last_error();
+}
+
+}  // namespace
+}  // namespace xyzb
+
+extern "C" int xyz_launch_gaussian_splatting(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients,
+                                             const float* target_image, float* output_image, float* total_loss,
+                                             int image_width, int image_height, int num_gaussians, void* stream,
+                                             int flags) {
+    return xyzb::splat_launch(gaussians, gradients, target_image, output_image, total_loss, image_width, image_height,
+                              num_gaussians, 0, image_height, stream, flags);
+}
+
+extern "C" int xyz_launch_gaussian_splatting_rows(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients,
+                                                  const float* target_image, float* output_image, float* total_loss,
+                                                  int image_width, int image_height, int num_gaussians, int row_begin,
+                                                  int row_end, void* stream, int flags) {
+    return xyzb::splat_launch(gaussians, gradients, target_image, output_image, total_loss, image_width, image_height,
+                              num_gaussians, row_begin, row_end, stream, flags);
+}
+
+extern "C" int xyz_splat_last_stats(long long stats_host[4]) {
+    using namespace xyzb;
+    if (!g_last.valid || !stats_host) return XYZ_ERR_NOT_INITIALISED;
+    if (g_last.stats[2] < 0) {
+        const int n_tiles = g_last.view.tiles_x * g_last.view.tiles_y;
+        std::vector<int2> r(n_tiles);
+        cudaError_t e = cudaMemcpy(r.data(), g_last.buf.tile_ranges, sizeof(int2) * n_tiles, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        long long mx = 0;
+        for (const int2& t : r) mx = std::max<long long>(mx, t.y - t.x);
+        g_last.stats[2] = mx;
+    }
+    for (int i = 0; i < 4; ++i) stats_host[i] = g_last.stats[i];
+    return 0;
+}
+
+extern "C" int xyz_splat_debug_binning(int32_t* rects_host, int32_t* tile_ranges_host, int32_t* sorted_ids_host,
+                                       float* records_host) {
+    using namespace xyzb;
+    if (!g_last.valid) return XYZ_ERR_NOT_INITIALISED;
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    const int n = g_last.view.num_gaussians, n_tiles = g_last.view.tiles_x * g_last.view.tiles_y;
+    if (rects_host && n > 0) {
+        e = cudaMemcpy(rects_host, g_last.buf.rects, sizeof(int4) * n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    if (tile_ranges_host) {
+        e = cudaMemcpy(tile_ranges_host, g_last.buf.tile_ranges, sizeof(int2) * n_tiles, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    if (sorted_ids_host && g_last.entries > 0) {
+        e = cudaMemcpy(sorted_ids_host, g_last.buf.sorted_gid, sizeof(int) * g_last.entries, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    if (records_host && n > 0) {
+        e = cudaMemcpy(records_host, g_last.buf.records, sizeof(float4) * 3 * n, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) return static_cast<int>(e);
+    }
+    return 0;
+}

@@ -1,0 +1,3 @@
+// csrc/splat_precise.cu -- IEEE flavour of the splat kernels (built without fast-math flags).
+#define XYZ_SPLAT_FLAVOR precise
+#include "splat_kernels.cuh"
