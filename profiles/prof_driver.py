@@ -1,0 +1,68 @@
+"""profiles/prof_driver.py -- launches every hot kernel twice at BASELINE size, for ncu.
+
+  ncu --set full --clock-control none --import-source on \
+      -k regex:'covproj_tma|lsq_grad|accumulate_kernel|splat_forward|splat_backward|adam_kernel' -c 24 \
+      -o gpurun_out/prof_rNN python profiles/prof_driver.py
+"""
+import os
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as orc  # noqa: E402  (input generators only)
+import xyz_autodiff_cuda_b200 as x  # noqa: E402
+
+dev = torch.device("cuda:0")
+reps = int(os.environ.get("PROF_REPS", "2"))
+which = os.environ.get("PROF_ONLY", "covproj,lsq,accumulate,splat,adam").split(",")
+
+if "covproj" in which:
+    E = 1 << 26
+    ins = [torch.empty((E, w), device=dev).uniform_(-1, 1) for w in (6, 9, 6, 3)]
+    outs = [torch.empty((E, w), device=dev) for w in (3, 6, 9, 6)]
+    for _ in range(reps):
+        x.covproj_fwd_bwd(*ins, *outs)
+    torch.cuda.synchronize()
+    del ins, outs
+
+if "lsq" in which:
+    n = 1 << 28
+    data = torch.empty((n, 3), dtype=torch.float64, device=dev).uniform_(-5, 5)
+    prm = torch.zeros(8, dtype=torch.float64, device=dev)
+    prm[1] = 1.0
+    for _ in range(reps):
+        x.lsq_grad(data, prm)
+    torch.cuda.synchronize()
+    del data
+
+if "accumulate" in which:
+    n = 1 << 24
+    for dist in ("uniform", "same"):
+        idx, val = orc.accumulate_inputs(n, 1024, dist, 42)
+        ti, tv = torch.from_numpy(idx).to(dev), torch.from_numpy(val).to(dev)
+        grad = torch.zeros(1024, device=dev)
+        for _ in range(reps):
+            x.accumulate(ti, tv, grad)
+        torch.cuda.synchronize()
+
+if "splat" in which or "adam" in which:
+    W = H = 1024
+    N = 100_000
+    params, target = orc.splat_c4_scene(N, W, H, 42)
+    tp, tt = torch.from_numpy(params).to(dev), torch.from_numpy(target).to(dev)
+    grads = torch.zeros((N, 9), device=dev)
+    img = torch.zeros((W * H, 3), device=dev)
+    loss = torch.zeros(1, device=dev)
+    adam = torch.zeros((N, 18), device=dev)
+    for it in range(reps):
+        x.zero_gradients(grads)
+        loss.zero_()
+        if "splat" in which:
+            x.launch_gaussian_splatting(tp, grads, tt, img, loss, W, H, N)
+        if "adam" in which:
+            x.adam_step_individual(tp, grads, adam, 0.1, 0.01, 0.001, 0.02, 0.05, iteration=it + 1)
+    torch.cuda.synchronize()
+print("prof_driver done", x.launch_count(), "launches")
