@@ -1,0 +1,52 @@
+// tests/csrc/api_probe_host.cpp -- TEST INFRASTRUCTURE: THIS repo's include/xyz_autodiff compiled by a
+// plain host C++20 compiler (no CUDA, no shim) and driven by tests/csrc/api_eval.inc -- the same text
+// oracle/ref_driver.cpp compiles against the REFERENCE headers.  Exports mine_* with the ref_* signatures.
+#include "api_headers.inc"
+
+#define API_FN inline
+#include "api_eval.inc"
+
+extern "C" {
+int mine_eval_op_f64(int op, int aux, const double* in1, int n1, const double* in2, int n2, double cst,
+                     const double* gout, double* out, int* nout, double* gin1, double* gin2) {
+    return api_eval::eval_op<double>(op, aux, in1, n1, in2, n2, cst, gout, out, nout, gin1, gin2);
+}
+int mine_eval_op_f32(int op, int aux, const float* in1, int n1, const float* in2, int n2, float cst, const float* gout,
+                     float* out, int* nout, float* gin1, float* gin2) {
+    return api_eval::eval_op<float>(op, aux, in1, n1, in2, n2, cst, gout, out, nout, gin1, gin2);
+}
+int mine_kat_dag(double* res) { return api_eval::kat_dag(res); }
+int mine_kat_shared_subgraph(double* res) { return api_eval::kat_shared_subgraph(res); }
+int mine_kat_broadcast(double* res) { return api_eval::kat_broadcast(res); }
+int mine_kat_chain(double x, double y, double z, double up, double* res) { return api_eval::kat_chain(x, y, z, up, res); }
+int mine_kat_operators(const double* a, const double* b, const double* c, const double* d, double* res) {
+    return api_eval::kat_operators(a, b, c, d, res);
+}
+int mine_kat_lsq_point(const double* p, double x1, double x2, double yt, double delta, double* res) {
+    return api_eval::kat_lsq_point(p, x1, x2, yt, delta, res);
+}
+int mine_kat_splat_pair(const double* in, double* res) { return api_eval::kat_splat_pair(in, res); }
+int mine_kat_math_f64(double x, double* res) { return api_eval::kat_math<double>(x, res); }
+int mine_kat_math_f32(float x, float* res) { return api_eval::kat_math<float>(x, res); }
+int mine_kat_matrices(float* res) { return api_eval::kat_matrices(res); }
+
+// ternary node + RegisterLeaf on the host: y = a*b + c ; returns {y, da, db, dc}
+int mine_kat_ternary(double a0, double b0, double c0, double* res) {
+    using namespace xyz_autodiff;
+    Variable<1, double> a(a0), b(b0), c(c0);
+    api_static_checks::Tern node(api_static_checks::TernaryProbeLogic{}, a, b, c);
+    node.run();
+    res[0] = node[0];
+    res[1] = a.grad(0);
+    res[2] = b.grad(0);
+    res[3] = c.grad(0);
+    // same graph evaluated numerically
+    Variable<1, double> a2(a0), b2(b0), c2(c0);
+    api_static_checks::Tern node2(api_static_checks::TernaryProbeLogic{}, a2, b2, c2);
+    node2.run_numerical(1e-6);
+    res[4] = a2.grad(0);
+    res[5] = b2.grad(0);
+    res[6] = c2.grad(0);
+    return 7;
+}
+}

@@ -1,0 +1,246 @@
+"""Public header set (include/xyz_autodiff/, examples/.../operations/) against the REFERENCE's own headers.
+
+tests/csrc/api_eval.inc is ONE source text written against the public API; it is compiled
+  * against the reference headers through oracle/shim   -> oracle/_ref/libxyz_ref.so            (ref_*)
+  * against this repo's headers by g++ for the host     -> tests/csrc/_build/libxyz_api_host.so (mine_*)
+  * against this repo's headers by nvcc inside kernels  -> tests/csrc/_build/libxyz_api_cuda.so (cuda_*, -m gpu)
+so "drop-in" is checked by construction (the same user code compiles against both) and by value.
+Where the reference tree is absent (GPU box) the prebuilt _ref library travels with the snapshot, and the
+plain-C++ restatement (oracle port, orc_*) is always available as a second checker.
+"""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HOST_SO = os.path.join(ROOT, "tests", "csrc", "_build", "libxyz_api_host.so")
+CUDA_SO = os.path.join(ROOT, "tests", "csrc", "_build", "libxyz_api_cuda.so")
+
+
+def P(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def _build():
+    subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "csrc")], check=True, stdout=subprocess.DEVNULL)
+
+
+@pytest.fixture(scope="module")
+def host():
+    if not os.path.exists(HOST_SO):
+        _build()
+    return ctypes.CDLL(HOST_SO)
+
+
+@pytest.fixture(scope="module")
+def cuda():
+    if not os.path.exists(CUDA_SO):
+        _build()
+    return ctypes.CDLL(CUDA_SO)
+
+
+def _checkers():
+    return ["port", "ref"] if orc.have_ref() else ["port"]
+
+
+UNARY = ["EXP", "SIN", "COS", "SIGMOID", "SQUARED", "NEG", "L1", "L2", "SUM"]
+CONST = ["ADD_C", "SUB_C", "MUL_C", "DIV_C"]
+BINARY = ["ADD", "SUB", "MUL", "DIV"]
+MATMUL_SHAPES = [222, 333, 444, 233, 232, 332, 423, 331, 134]
+
+
+def op_cases(rng):
+    """(op, in1, in2, cst, gout, aux) over the whole op table of tests/csrc/api_eval.inc."""
+    cases = []
+    for n in (1, 2, 3, 4, 6, 9):
+        for op in UNARY:
+            cases.append((op, rng.uniform(-2, 2, n), None, 0.0, rng.uniform(-1, 1, 16), 0))
+        for op in CONST:
+            cases.append((op, rng.uniform(-2, 2, n), None, float(rng.uniform(0.5, 3)), rng.uniform(-1, 1, 16), 0))
+        for op in ("CONST_ADD", "CONST_SUB"):
+            cases.append((op, rng.uniform(-2, 2, n), rng.uniform(-2, 2, n), 0.0, rng.uniform(-1, 1, 16), 0))
+    for n in (1, 2, 3, 4, 9):
+        for op in BINARY:
+            b = rng.uniform(0.5, 2, n) * rng.choice([-1, 1], n)
+            cases.append((op, rng.uniform(-2, 2, n), b, 0.0, rng.uniform(-1, 1, 16), 0))
+    for shp in MATMUL_SHAPES:
+        a, b, c = shp // 100, (shp // 10) % 10, shp % 10
+        cases.append(("MATMUL", rng.uniform(-1, 1, a * b), rng.uniform(-1, 1, b * c), 0.0, rng.uniform(-1, 1, 16), shp))
+    cases.append(("SYM_INV", np.array([2.0, 0.3, 1.5]), None, 0.0, rng.uniform(-1, 1, 16), 0))
+    cases.append(("SYM_INV", np.array([1e-5, 0.0, 1e-5]), None, 0.0, rng.uniform(-1, 1, 16), 0))  # |det| < 1e-8 (Q15)
+    cases.append(("QUAT", rng.uniform(-1, 1, 4), None, 0.0, rng.uniform(-1, 1, 16), 0))
+    cases.append(("BROADCAST3", rng.uniform(-1, 1, 1), None, 0.0, rng.uniform(-1, 1, 16), 0))
+    cases.append(("COV_GEN", rng.uniform(0.5, 2, 2), rng.uniform(-3, 3, 1), 0.0, rng.uniform(-1, 1, 16), 0))
+    cases.append(("MAT_TO_COV3", rng.uniform(-2, 2, 4), None, 0.0, rng.uniform(-1, 1, 16), 0))
+    cases.append(("SCALE_ROT_COV3", rng.uniform(0.5, 2, 2), rng.uniform(-3, 3, 1), 0.0, rng.uniform(-1, 1, 16), 0))
+    cases.append(("MAHALANOBIS", rng.uniform(-2, 2, 2), rng.uniform(0.1, 3, 3), 0.0, rng.uniform(-1, 1, 16), 0))
+    cases.append(("MAHALANOBIS_CENTER", rng.uniform(0.1, 3, 2), rng.uniform(0.1, 3, 3), 1.7, rng.uniform(-1, 1, 16), 0))
+    # kinks: l1 at exactly 0 (subgradient 0), l2 of the zero vector (no adjoint)
+    cases.append(("L1", np.array([0.0, -1.0, 2.0]), None, 0.0, rng.uniform(-1, 1, 16), 0))
+    cases.append(("L2", np.zeros(3), None, 0.0, rng.uniform(-1, 1, 16), 0))
+    return cases
+
+
+def compare_ops(fn64, fn32, tol64, tol32):
+    n = 0
+    for which in _checkers():
+        rng = np.random.default_rng(123)
+        for op, in1, in2, cst, gout, aux in op_cases(rng):
+            for dtype, fn, tol in ((np.float64, fn64, tol64), (np.float32, fn32, tol32)):
+                want = orc.eval_op(which, op, in1, in2, cst, gout, aux, dtype)
+                got = orc.eval_op(which, op, in1, in2, cst, gout, aux, dtype, fn=fn)
+                for a, b, what in zip(got, want, ("value", "grad1", "grad2")):
+                    scale = np.maximum(np.abs(b), np.abs(b).max() if b.size else 1.0) + 1e-30
+                    assert (np.abs(a - b) <= tol * scale).all(), (which, op, aux, dtype.__name__, what, a, b)
+                n += 1
+    return n
+
+
+def test_host_headers_match_reference_ops(host):
+    """Every op of the public header set, host-compiled, fp64 and fp32, against the reference's Logic structs
+    (and the port): same formulas in the same order -> agreement to a few ulp."""
+    n = compare_ops(host.mine_eval_op_f64, host.mine_eval_op_f32, 1e-14, 1e-6)
+    assert n > 300
+
+
+def test_host_known_answers(host):
+    """The reference tests' known answers on the host path."""
+    res = np.zeros(64)
+    k = host.mine_kat_dag(P(res))
+    assert list(res[:k]) == [6.0, 4.0, 9.0, 4.0, 12.0, 7.0]                # tests/test_dag_backward.cu:80,130,171
+    k = host.mine_kat_shared_subgraph(P(res))
+    assert res[1] == 0.0 and abs(res[3] - 2 * np.exp(0.5)) < 1e-12         # Q3: deep-shared stops, shallow works
+    k = host.mine_kat_broadcast(P(res))
+    assert list(res[:5]) == [3.5] * 4 + [10.0] and list(res[5:14]) == [-2.25] * 8 + [4.0]
+    assert list(res[14:21]) == [3.0, 5.0, 7.0, 3.0, 1.0, 1.0, 1.0]         # tests/operation/unary/test_broadcast.cu
+    host.mine_kat_chain.argtypes = [ctypes.c_double] * 4 + [ctypes.c_void_p]
+    k = host.mine_kat_chain(1.5, -0.7, 2.25, 0.3, P(res))                  # f = x z + y: dx = g z, dy = g, dz = g x
+    assert np.allclose(res[:4], [1.5 * 2.25 - 0.7, 0.3 * 2.25, 0.3, 0.3 * 1.5], rtol=1e-15)
+    fres = np.zeros(64, np.float32)
+    k = host.mine_kat_matrices(P(fres))
+    assert list(fres[:12]) == [1, 2, 6, 8, 15, 18, 1, 4, 9, 4, 10, 18]      # tests/test_diagonal_matrix.cu:145,167
+    assert list(fres[12:21]) == [1, 2, 3, 4, 5, 6, 2, 3, 5]                 # tests/test_symmetric_matrix.cu
+    assert list(fres[21:27]) == [1, 4, 2, 5, 3, 6]                          # tests/test_matrix_transpose.cu
+    host.mine_kat_ternary.argtypes = [ctypes.c_double] * 3 + [ctypes.c_void_p]
+    k = host.mine_kat_ternary(1.5, -2.0, 0.25, P(res))
+    assert np.allclose(res[:4], [1.5 * -2.0 + 0.25, -2.0, 1.5, 1.0]) and np.allclose(res[4:7], res[1:4], atol=1e-8)
+
+
+def _all_kats(run):
+    out = {}
+    out["dag"] = run("dag")
+    out["shared_subgraph"] = run("shared_subgraph")
+    out["broadcast"] = run("broadcast")
+    out["chain"] = run("chain", 1.5, -0.7, 2.25, 0.3)
+    out["operators"] = run("operators", np.array([0.5, -1.5]), np.array([2.0, 0.25]), np.array([0.1, 0.2]),
+                           np.array([1.5, -3.0]))
+    out["lsq_point"] = run("lsq_point", np.array([1.0, 1.5, 0.5, 0.2]), 2.0, 3.0, 5.0, 1e-6)
+    out["splat_pair"] = run("splat_pair", np.array([0.5, 0.3, 0.2, 0.4, 0.3, 0.8, 0.4, 0.16, 0.1, 1.0, 0.7]))
+    out["math_f64"] = run("math_f64", 0.73)
+    return out
+
+
+def _kat_runner(lib, prefix):
+    def run(name, *args):
+        res = np.zeros(64)
+        cargs = [P(a) if isinstance(a, np.ndarray) else ctypes.c_double(a) for a in args]
+        k = getattr(lib, f"{prefix}_kat_{name}")(*cargs, P(res))
+        return res[:k].copy()
+    return run
+
+
+@pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref/libxyz_ref.so not present")
+def test_host_graphs_match_reference_graphs(host):
+    """Whole graphs (DAG protocol, operator sugar, least-squares point analytic + numerical, the splat pair
+    graph, math dispatcher, matrix views): this repo's headers vs the reference's headers, same source text."""
+    mine = _all_kats(_kat_runner(host, "mine"))
+    ref = _all_kats(_kat_runner(orc.load("ref"), "ref"))
+    for name in mine:
+        assert mine[name].size == ref[name].size and mine[name].size > 0, name
+        assert np.allclose(mine[name], ref[name], rtol=1e-13, atol=1e-15), name
+    # analytic vs numerical on the least-squares point: the reference's acceptance rule min(abs, rel) <= 1e-5
+    a, n = mine["lsq_point"][1:5], mine["lsq_point"][5:9]
+    assert (np.minimum(np.abs(a - n), np.abs(a - n) / (np.abs(a) + 1e-15)) <= 1e-5).all()
+    fa, fb = np.zeros(64, np.float32), np.zeros(64, np.float32)
+    ka = host.mine_kat_matrices(P(fa))
+    kb = orc.load("ref").ref_kat_matrices(P(fb))
+    assert ka == kb and np.array_equal(fa[:ka], fb[:kb])
+    host.mine_kat_math_f32.argtypes = [ctypes.c_float, ctypes.c_void_p]
+    orc.load("ref").ref_kat_math_f32.argtypes = [ctypes.c_float, ctypes.c_void_p]
+    ka = host.mine_kat_math_f32(0.73, P(fa))
+    kb = orc.load("ref").ref_kat_math_f32(0.73, P(fb))
+    assert ka == kb == 20 and np.allclose(fa[:ka], fb[:kb], rtol=1e-6)
+
+
+# ---- device side ----------------------------------------------------------------------------------------
+@pytest.mark.gpu
+def test_device_headers_match_reference_ops(cuda):
+    """The same op table evaluated INSIDE a kernel on the B200 against the reference's host-compiled Logic
+    structs: fp64 to 1e-12 (FMA contraction + libdevice transcendentals), fp32 to 1e-5 relative."""
+    n = compare_ops(cuda.cuda_eval_op_f64, cuda.cuda_eval_op_f32, 1e-12, 1e-5)
+    assert n > 300
+
+
+@pytest.mark.gpu
+def test_device_known_answers(cuda, host):
+    res, fres, inp, want = np.zeros(64), np.zeros(64, np.float32), np.zeros(16), np.zeros(64)
+    k = cuda.cuda_kat(0, None, P(res), None)
+    assert list(res[:k]) == [6.0, 4.0, 9.0, 4.0, 12.0, 7.0]
+    k = cuda.cuda_kat(1, None, P(res), None)
+    assert res[1] == 0.0 and abs(res[3] - 2 * np.exp(0.5)) < 1e-12
+    k = cuda.cuda_kat(2, None, P(res), None)
+    assert list(res[:5]) == [3.5] * 4 + [10.0] and list(res[14:21]) == [3.0, 5.0, 7.0, 3.0, 1.0, 1.0, 1.0]
+    k = cuda.cuda_kat(9, None, None, P(fres))
+    assert list(fres[:12]) == [1, 2, 6, 8, 15, 18, 1, 4, 9, 4, 10, 18] and list(fres[21:27]) == [1, 4, 2, 5, 3, 6]
+    # graphs with inputs: device vs this repo's host path (which test_host_graphs pins to the reference)
+    inp[:11] = [0.5, 0.3, 0.2, 0.4, 0.3, 0.8, 0.4, 0.16, 0.1, 1.0, 0.7]
+    k = cuda.cuda_kat(6, P(inp), P(res), None)
+    host.mine_kat_splat_pair(P(inp[:11].copy()), P(want))
+    assert k == 13 and np.allclose(res[:k], want[:k], rtol=1e-12)
+    inp[:8] = [1.0, 1.5, 0.5, 0.2, 2.0, 3.0, 5.0, 1e-6]
+    k = cuda.cuda_kat(5, P(inp), P(res), None)
+    r = (1.0 - 2.0) ** 2 + 1.5 * (0.5 - 3.0) ** 2 + 0.2 - 5.0
+    assert np.allclose(res[1:5], 2 * r * np.array([2 * (1.0 - 2.0), (0.5 - 3.0) ** 2, 2 * 1.5 * (0.5 - 3.0), 1.0]),
+                       rtol=1e-12)
+    assert np.allclose(res[5:9], res[1:5], rtol=1e-5)                       # numerical backward on the device
+    inp[0] = 0.73
+    k = cuda.cuda_kat(7, P(inp), P(res), None)
+    host.mine_kat_math_f64.argtypes = [ctypes.c_double, ctypes.c_void_p]
+    host.mine_kat_math_f64(0.73, P(want))
+    assert k == 20 and np.allclose(res[:k], want[:k], rtol=1e-13)
+
+
+@pytest.mark.gpu
+def test_device_concurrent_accumulation_known_answers(cuda):
+    """The reference's concurrency tests (Appendix D): VariableRef::add_grad from 10 000 / 100 000 threads onto 3
+    fp64 addresses, and onto __shared__ memory; then accumulate.cuh's on-chip pre-reduction on the same sums."""
+    g = np.zeros(3)
+    cuda.cuda_global_accumulation.argtypes = [ctypes.c_longlong, ctypes.c_int, ctypes.c_void_p]
+    assert cuda.cuda_global_accumulation(10_000, 256, P(g)) == 0
+    tid = np.arange(10_000)
+    assert abs(g[0] - 10000.0) < 1e-10 and abs(g[1] - 10000.0) < 1e-10      # test_parallel_gradient_accumulation.cu:94-101
+    assert abs(g[2] - ((1.0 + tid * 0.001) + (2.0 + tid * 0.001)).sum()) < 1e-6
+    assert cuda.cuda_global_accumulation(100_000, 512, P(g)) == 0
+    assert g[0] == 100000.0 and g[1] == 100000.0                             # :162-167
+    out = np.zeros(8, np.float32)
+    assert cuda.cuda_shared_accumulation(1, 128, P(out)) == 0
+    assert out[0] == 128.0 and out[1] == 256.0                               # test_shared_memory_atomic.cu:102-109
+    assert cuda.cuda_shared_accumulation(4, 64, P(out)) == 0
+    assert list(out) == [64.0, 128.0] * 4                                    # :179-186
+    # RegisterLeaf + block_accumulate: the least-squares graph through the PUBLIC headers, one RED per CTA
+    data = orc.lsq_data(100_000, seed=3)
+    values = np.array([0.3, 1.2, -0.4, 0.1])
+    grads = np.zeros(4)
+    cuda.cuda_lsq_register_leaf.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p]
+    assert cuda.cuda_lsq_register_leaf(P(data), 100_000, P(values), P(grads)) == 0
+    want, _ = orc.lsq_grad(data, values)
+    assert (np.abs(grads - want) <= 1e-10 * np.abs(want)).all()
+    vals = np.random.default_rng(0).uniform(-1, 1, 100_000).astype(np.float32)
+    tgt = np.zeros(8, np.float32)
+    assert cuda.cuda_block_accumulate_f32(P(vals), vals.size, P(tgt)) == 0
+    assert np.allclose(tgt, vals.astype(np.float64).sum() * np.arange(1, 9), rtol=1e-4, atol=1e-2)

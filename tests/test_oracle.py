@@ -1,0 +1,135 @@
+"""Pins the CPU oracle port (oracle/xyz_oracle.cpp) before anything else trusts it:
+  (1) against the committed golden vectors generated from the reference itself (tests/golden/);
+  (2) live against oracle/_ref/libxyz_ref.so (the reference's own code on the host) where present;
+  (3) against the reference tests' known answers.
+Both libraries are built with -O2 -ffp-contract=off, so fp32 and fp64 comparisons are BIT-EXACT when both
+run single-threaded."""
+import os
+
+import numpy as np
+import pytest
+
+import oracle_lib as orc
+from test_api_headers import op_cases
+
+GOLD = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "reference_vectors.npz"))
+need_ref = pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref/libxyz_ref.so not present")
+
+
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_port_splat_equals_golden_bit_for_bit(tag):
+    W, H, N, _ = GOLD[f"splat_{tag}_shape"]
+    g, o, l, _ = orc.splat(GOLD[f"splat_{tag}_params"], GOLD[f"splat_{tag}_target"], int(W), int(H), np.float32, threads=1)
+    assert np.array_equal(g, GOLD[f"splat_{tag}_grads"])
+    assert np.array_equal(o, GOLD[f"splat_{tag}_output"])
+    assert np.float32(l) == GOLD[f"splat_{tag}_loss"]
+
+
+def test_port_splat_c4_distribution_equals_golden():
+    params, target = orc.splat_c4_scene(64, 48, 32, seed=42)  # std::mt19937(42) emulation is part of what is pinned
+    assert np.array_equal(params, GOLD["splat_c4_params"]) and np.array_equal(target, GOLD["splat_c4_target"])
+    g, o, l, _ = orc.splat(params, target, 48, 32, np.float32, threads=1)
+    assert np.array_equal(g, GOLD["splat_c4_grads"]) and np.array_equal(o, GOLD["splat_c4_output"])
+    assert np.float32(l) == GOLD["splat_c4_loss"]
+    assert orc.std_mt19937_u32(42, 2).tolist() == [1608637542, 3421126067]  # first outputs of std::mt19937(42)
+
+
+def test_port_lsq_accumulate_covproj_equal_golden():
+    for ro in (0, 1):
+        g, l = orc.lsq_grad(GOLD["lsq_data"], (0.0, 1.0, 0.0, 0.0), bool(ro), threads=1)
+        assert np.array_equal(g, GOLD[f"lsq_grad_{ro}"]) and l == GOLD[f"lsq_loss_{ro}"]
+    assert np.array_equal(orc.accumulate(GOLD["acc_idx"], GOLD["acc_val"], 64), GOLD["acc_grad_f32"])
+    assert np.array_equal(orc.accumulate(GOLD["acc_idx"], GOLD["acc_val"].astype(np.float64), 64), GOLD["acc_grad_f64"])
+    for dt, tag in ((np.float32, "f32"), (np.float64, "f64")):
+        outs = orc.covproj(GOLD["cov_J"], GOLD["cov_W"], GOLD["cov_S"], GOLD["cov_g"], dt, threads=1)
+        for name, a in zip(("out", "gJ", "gW", "gS"), outs):
+            assert np.array_equal(a, GOLD[f"cov_{tag}_{name}"]), (tag, name)
+
+
+def test_port_op_table_equals_golden():
+    rng = np.random.default_rng(123)
+    rows = []
+    for op, in1, in2, cst, gout, aux in op_cases(rng):
+        o, g1, g2 = orc.eval_op("port", op, in1, in2, cst, gout, aux, np.float64)
+        rows.append(np.concatenate([o, g1, g2]))
+    assert np.array_equal(np.array([r.size for r in rows]), GOLD["op_table_rows"])
+    got, want = np.concatenate(rows), GOLD["op_table_f64"]
+    # (g*c)*v vs g*(c*v) in the quaternion rule is the only reassociation: 1 ulp
+    assert np.allclose(got, want, rtol=1e-15, atol=1e-300)
+    assert (got == want).mean() > 0.99
+
+
+def test_threaded_oracle_matches_single_thread():
+    params, target = orc.splat_scene(30, 80, 64, seed=4)
+    g1, o1, l1, _ = orc.splat(params, target, 80, 64, np.float64, threads=1)
+    g8, o8, l8, _ = orc.splat(params, target, 80, 64, np.float64, threads=8)
+    assert np.array_equal(o1, o8) and np.allclose(g1, g8, rtol=1e-12) and abs(l1 - l8) <= 1e-12 * l1
+    data = orc.lsq_data(10_000, seed=2)
+    a, _ = orc.lsq_grad(data, (0.3, 1.2, -0.4, 0.1), threads=1)
+    b, _ = orc.lsq_grad(data, (0.3, 1.2, -0.4, 0.1), threads=8)
+    assert np.allclose(a, b, rtol=1e-12)
+
+
+def test_known_answers_from_reference_tests():
+    # tests/test_dag_backward.cu:80,130,171 ; tests/operation/unary/test_broadcast.cu ; closed-form least squares
+    assert GOLD["kat_dag"].tolist() == [6.0, 4.0, 9.0, 4.0, 12.0, 7.0]
+    assert GOLD["kat_shared_subgraph"][1] == 0.0
+    assert GOLD["kat_broadcast"][4] == 10.0 and GOLD["kat_broadcast"][13] == 4.0
+    for (x1, x2, y), (a, b, c, d) in [((2.0, 3.0, 5.0), (1.0, 1.5, 0.5, 0.2)), ((-2.0, -1.5, 3.0), (-1.0, 2.0, -0.5, -0.3)),
+                                      ((100.0, 150.0, 500.0), (50.0, 30.0, 70.0, 20.0))]:
+        r = (a - x1) ** 2 + b * (c - x2) ** 2 + d - y
+        want = 2 * r * np.array([2 * (a - x1), (c - x2) ** 2, 2 * b * (c - x2), 1.0])
+        got, loss = orc.lsq_grad(np.array([[x1, x2, y]]), (a, b, c, d))
+        assert np.allclose(got, want, rtol=1e-13) and np.isclose(loss, r * r, rtol=1e-13)
+    # accumulation: 10 000 x (+1, +1, 3 + 0.002 tid), tests/test_parallel_gradient_accumulation.cu:94-110
+    tid = np.arange(10_000)
+    idx = np.tile(np.array([0, 1, 2], np.int32), 10_000)
+    val = np.stack([np.ones(10_000), np.ones(10_000), (1.0 + tid * 0.001) + (2.0 + tid * 0.001)], -1).reshape(-1)
+    got = orc.accumulate(idx, val, 3)
+    assert got[0] == 10000.0 and got[1] == 10000.0 and abs(got[2] - val[2::3].sum()) < 1e-6
+    # splat quirks Q1/Q2: a far-away Gaussian is NOT culled (all-pairs), and the L1 argument is wc + out - target
+    p = np.array([[5.0, 5.0, 0.0, 0.0, 0.0, 0.5, 0.5, 0.5, 0.0]], np.float32)
+    t = np.full((16 * 16, 3), 10.0, np.float32)                       # target > out everywhere -> sign is -1
+    g, o, l, _ = orc.splat(p, t, 16, 16, np.float64)
+    assert (g[0, 5:8] < 0).all() and o.max() < 0.26
+
+
+@need_ref
+def test_port_equals_reference_live_bit_for_bit():
+    params, target = orc.splat_scene(40, 70, 50, seed=9)
+    a = orc.splat(params, target, 70, 50, np.float32, which="ref", threads=1)
+    b = orc.splat(params, target, 70, 50, np.float32, which="port", threads=1)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
+    data = orc.lsq_data(5000, seed=8)
+    for ro in (False, True):
+        assert np.array_equal(orc.lsq_grad(data, (0.1, 0.9, -0.2, 0.3), ro, "ref")[0],
+                              orc.lsq_grad(data, (0.1, 0.9, -0.2, 0.3), ro, "port")[0])
+    J, W, S, g = orc.covproj_inputs(3000, seed=1)
+    for dt in (np.float32, np.float64):
+        for x, y in zip(orc.covproj(J, W, S, g, dt, "ref", 1), orc.covproj(J, W, S, g, dt, "port", 1)):
+            assert np.array_equal(x, y)
+    idx, val = orc.accumulate_inputs(20_000, 1024, "zipf", seed=3)
+    assert np.array_equal(orc.accumulate(idx, val, 1024, "ref"), orc.accumulate(idx, val, 1024, "port"))
+
+
+def test_tile_binning_restatement_properties():
+    """The integer oracle (this repo's own; 'parity unpinned' by the reference, which has no binning): lists are
+    ascending per tile, ranges partition the list, and every pair with a non-zero fp32 weight is inside its
+    Gaussian's rectangle -- the property that makes the cull result-preserving."""
+    W, H, N = 200, 150, 300
+    params, _ = orc.splat_scene(N, W, H, seed=5)
+    rec = orc.splat_records(params)
+    rects, ranges, ids = orc.splat_binning(rec, W, H, d2max=176.0)
+    assert ranges[0, 0] == 0 and ranges[-1, 1] == ids.size and (ranges[1:, 0] == ranges[:-1, 1]).all()
+    for t in range(ranges.shape[0]):
+        seg = ids[ranges[t, 0]:ranges[t, 1]]
+        assert (np.diff(seg) > 0).all()
+    ys, xs = np.mgrid[0:H, 0:W]
+    for g in range(0, N, 7):
+        cx, cy, ia, ib, ic = rec[g, :5]
+        dx, dy = xs.astype(np.float32) - cx, ys.astype(np.float32) - cy
+        d2 = ia * dx * dx + 2 * ib * dx * dy + ic * dy * dy
+        nz = np.exp(-(0.5 * d2.astype(np.float64))) > 2.0 ** -126      # FTZ threshold of the fast-math flavour
+        tx0, ty0, tx1, ty1 = rects[g]
+        inside = (xs >= tx0 * 16) & (xs < tx1 * 16) & (ys >= ty0 * 16) & (ys < ty1 * 16)
+        assert not (nz & ~inside).any()
