@@ -223,7 +223,67 @@ def also_workloads(dev, peak_gbs):
                                       "pair_evals_per_s": 2 * stats["pairs_per_pass"] / (ms / 1e3),
                                       "reference_pairs_per_pass": N * W * H,
                                       "iteration": "zero_grad + loss reset + launch (fwd + bwd), fast-math flavour"}
+    out["reference_cuda_same_b200"] = reference_cuda(dev, timed, x, tp, tt, W, H, N, ms)
     return out
+
+
+def reference_cuda(dev, timed, x, tp, tt, W, H, N, ours_splat_ms):
+    """The reference's own CUDA kernels built unmodified for sm_100a (oracle/_ref/libxyz_ref_cuda.so), timed on
+    the same GPU with the same CUDA-event harness.  Splat is run at a reduced Gaussian count and scaled by N
+    (its cost is exactly linear in N: every pixel visits every Gaussian)."""
+    import ctypes
+    import numpy as np
+    import torch
+    import oracle_lib as orc
+    path = os.path.join(ROOT, "oracle", "_ref", "libxyz_ref_cuda.so")
+    if not os.path.exists(path):
+        return {"unavailable": "oracle/_ref/libxyz_ref_cuda.so not built (needs /root/reference at build time)"}
+    R = ctypes.CDLL(path)
+    vp, ll = ctypes.c_void_p, ctypes.c_longlong
+    R.refcuda_splat.argtypes = [vp] * 5 + [ctypes.c_int] * 3
+    R.refcuda_lsq.argtypes = [vp, ll, vp]
+    R.refcuda_accumulate.argtypes = [vp, vp, ll, vp]
+    R.refcuda_covproj.argtypes = [vp] * 8 + [ll]
+    res = {}
+    # splat, reduced N
+    n_ref = 256
+    grads = torch.zeros((n_ref, 9), device=dev)
+    img = torch.zeros((W * H, 3), device=dev)
+    loss = torch.zeros(1, device=dev)
+    sub = tp[:n_ref].contiguous()
+    ms = timed(lambda: R.refcuda_splat(sub.data_ptr(), grads.data_ptr(), tt.data_ptr(), img.data_ptr(), loss.data_ptr(),
+                                       W, H, n_ref), reps=3, flush_l2=False)
+    scaled = ms * N / n_ref
+    res["c4_splat"] = {"ms_at_N": {str(n_ref): ms}, "ms_per_iter_scaled_to_100K": scaled,
+                       "speedup_of_this_repo": scaled / ours_splat_ms,
+                       "note": "reference kernel cost is linear in N (all pairs, 9 atomics per pair)"}
+    # covproj 2^24
+    n = 1 << 24
+    ins = [torch.empty((n, w), device=dev).uniform_(-1, 1) for w in (6, 9, 6, 3)]
+    outs = [torch.empty((n, w), device=dev) for w in (3, 6, 9, 6)]
+    ms_ref = timed(lambda: R.refcuda_covproj(*[t.data_ptr() for t in ins], *[t.data_ptr() for t in outs], n), reps=5,
+                   flush_l2=False)
+    ms_our = timed(lambda: x.covproj_fwd_bwd(*ins, *outs), reps=5, flush_l2=False)
+    res["c3_covproj_2^24"] = {"reference_ms": ms_ref, "this_repo_ms": ms_our, "speedup_of_this_repo": ms_ref / ms_our}
+    del ins, outs
+    # least squares 1M
+    n = 1_000_000
+    data = torch.from_numpy(orc.lsq_data(n, 42)).to(dev)
+    prm = torch.zeros(8, dtype=torch.float64, device=dev)
+    prm[1] = 1.0
+    ms_ref = timed(lambda: R.refcuda_lsq(data.data_ptr(), n, prm.data_ptr()), reps=5)
+    ms_our = timed(lambda: x.lsq_grad(data, prm), reps=5)
+    res["c1_lsq_1M"] = {"reference_ms": ms_ref, "this_repo_ms": ms_our, "speedup_of_this_repo": ms_ref / ms_our}
+    # accumulation 2^24 -> 1024, uniform ids
+    n = 1 << 24
+    idx, val = orc.accumulate_inputs(n, 1024, "uniform", 42)
+    ti, tv = torch.from_numpy(idx).to(dev), torch.from_numpy(val).to(dev)
+    grad = torch.zeros(1024, device=dev)
+    ms_ref = timed(lambda: R.refcuda_accumulate(ti.data_ptr(), tv.data_ptr(), n, grad.data_ptr()), reps=5)
+    ms_our = timed(lambda: x.accumulate(ti, tv, grad), reps=5)
+    res["c2_accumulate_2^24_uniform"] = {"reference_ms": ms_ref, "this_repo_ms": ms_our,
+                                         "speedup_of_this_repo": ms_ref / ms_our}
+    return res
 
 
 def run_ours(args):

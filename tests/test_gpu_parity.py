@@ -8,6 +8,8 @@ Bars (BASELINE.json north_star):
     more accurate than that in any summation order), and bit-exact run to run in deterministic mode;
   * fp64 least squares: 1e-10 relative (reference tests use 1e-10, tests/test_parallel_gradient_accumulation.cu:94).
 """
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -444,6 +446,64 @@ def test_zero_gradients_and_adam_match_oracle():
     x.adam_step(tp, dev(g), ta, 0.01, 0.9, 0.999, 1e-8, 3)
     wp, wa = orc.adam_step_individual(p, g, a, (0.01,) * 5, 0.9, 0.999, 1e-8, 3)
     assert np.allclose(tp.cpu().numpy(), wp, rtol=1e-5, atol=1e-7)
+
+
+REF_CUDA = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle", "_ref", "libxyz_ref_cuda.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CUDA), reason="oracle/_ref/libxyz_ref_cuda.so (reference CUDA kernels for sm_100a) not present")
+def test_against_the_reference_cuda_kernels_on_the_same_gpu():
+    """north_star: results must match the reference's own CUDA path on the same inputs.  The reference's kernels are
+    built unmodified for sm_100a (fast-math flags for the splat kernel, as its CMake does) and run on this GPU."""
+    import ctypes
+    R = ctypes.CDLL(REF_CUDA)
+    vp, ll = ctypes.c_void_p, ctypes.c_longlong
+    R.refcuda_splat.argtypes = [vp] * 5 + [ctypes.c_int] * 3
+    R.refcuda_lsq.argtypes = [vp, ll, vp]
+    R.refcuda_accumulate.argtypes = [vp, vp, ll, vp]
+    R.refcuda_covproj.argtypes = [vp] * 8 + [ll]
+    # splat (fast-math flavour on both sides)
+    for (W, H, N, seed) in [(64, 48, 50, 3), (100, 70, 300, 11)]:
+        params, target = orc.splat_scene(N, W, H, seed=seed)
+        g, o, l = run_splat(params, target, W, H, 0)
+        tp, tt = dev(params), dev(target)
+        rg = torch.zeros((N, 9), device=DEV)
+        ro = torch.zeros((W * H, 3), device=DEV)
+        rl = torch.zeros(1, device=DEV)
+        assert R.refcuda_splat(tp.data_ptr(), rg.data_ptr(), tt.data_ptr(), ro.data_ptr(), rl.data_ptr(), W, H, N) == 0
+        torch.cuda.synchronize()
+        ro, rg, rl = ro.cpu().numpy(), rg.cpu().numpy(), rl.item()
+        tol = orc.splat_tolerance(params, target, W, H)[3]
+        assert (np.abs(o - ro) <= 1e-5 * np.maximum(np.abs(ro), np.abs(ro).max() * 1e-3)).all()
+        assert abs(l - rl) <= 1e-4 * abs(rl)
+        assert (np.abs(g - rg) <= 2 * tol).all()   # both sides are fp32 sums in different orders
+    # covariance chain
+    n = 10_000
+    J, W9, S, gg = orc.covproj_inputs(n, seed=3)
+    got = run_covproj(J, W9, S, gg)
+    ins = [dev(a) for a in (J, W9, S, gg)]
+    outs = [torch.zeros((n, k), device=DEV) for k in (3, 6, 9, 6)]
+    assert R.refcuda_covproj(*[t.data_ptr() for t in ins], *[t.data_ptr() for t in outs], n) == 0
+    torch.cuda.synchronize()
+    for a, b in zip(got, outs):
+        b = b.cpu().numpy()
+        assert rel_err(a, b, np.abs(b).max(axis=1, keepdims=True)).max() < 1e-5
+    # least squares
+    data = orc.lsq_data(100_000, seed=6)
+    got, _ = run_lsq(data, (0.3, 1.2, -0.4, 0.1))
+    prm = dev(np.array([0.3, 1.2, -0.4, 0.1, 0, 0, 0, 0], np.float64))
+    td = dev(data)
+    assert R.refcuda_lsq(td.data_ptr(), data.shape[0], prm.data_ptr()) == 0
+    torch.cuda.synchronize()
+    assert rel_err(got, prm[4:].cpu().numpy()).max() < 1e-10
+    # accumulation
+    idx, val = orc.accumulate_inputs(1 << 20, 1024, "zipf", seed=4)
+    got = run_acc(idx, val, 1024)
+    ti, tv = dev(idx), dev(val)
+    grad = torch.zeros(1024, device=DEV)
+    assert R.refcuda_accumulate(ti.data_ptr(), tv.data_ptr(), idx.size, grad.data_ptr()) == 0
+    torch.cuda.synchronize()
+    assert (np.abs(got - grad.cpu().numpy()) <= 2e-4 * orc.accumulate_exact(idx, np.abs(val), 1024) + 1e-30).all()
 
 
 def test_no_cpu_fallback():
