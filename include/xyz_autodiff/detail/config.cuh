@@ -22,12 +22,18 @@ namespace xyz_autodiff::detail {
 
 // Leaf-gradient accumulation primitive behind VariableRef::add_grad
 // (reference: include/xyz_autodiff/variable.cuh:48-50 -- an unconditional atomicAdd).
-// Device: one native RED (red.global.add / atoms) on whatever address space the pointer is in.
+// Device: one native RED (red.global.add / atoms) when the pointer is in global or shared memory; a plain
+// += when it points into the calling thread's own local storage (atomics on the local window are illegal --
+// the reference documents "CANNOT USE BUFFER ON A LOCAL VARIABLE", variable.cuh:9-10; here it just works).
 // Host: plain read-modify-write (a host thread owns its accumulators).
 template <typename T>
 XYZ_HD void accumulate(T* address, T value) noexcept {
 #if defined(__CUDA_ARCH__)
-    atomicAdd(address, value);
+    if (__isLocal(address)) {
+        *address += value;
+    } else {
+        atomicAdd(address, value);
+    }
 #else
     *address += value;
 #endif

@@ -377,7 +377,9 @@ void splat_pixel(const T* params, T* grads, const T* tgt, T* out, T* loss, int p
             sgn[i] = cd > T(0) ? T(1) : (cd < T(0) ? T(-1) : T(0));  // l1 backward, seed 1.0
             if (margin && f.w > T(1e-10) && std::abs(cd) < *margin) *margin = std::abs(cd);
             // sign(cd) is numerically ambiguous in fp32 when |cd| is within rounding distance of 0
-            if (std::abs(cd) <= T(2e-5) * std::max(std::abs(f.wc[i]), std::abs(rest))) near_kink = true;
+            // (rest = tgt - out carries the ABSOLUTE rounding error of the fp32 image, ~1e-6 * |out|)
+            if (std::abs(cd) <= T(2e-5) * std::max(std::abs(f.wc[i]), std::max(std::abs(tgt[i]), std::abs(pix[i]))))
+                near_kink = true;
         }
         // mul backward (binary/mul_logic.cuh:33-41): color.grad += g*bc ; bc(=weighted_gauss).grad += g*color
         T g_w = T(0);

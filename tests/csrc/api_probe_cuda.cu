@@ -7,6 +7,7 @@
 #define API_FN __host__ __device__ inline
 #include "api_eval.inc"
 
+#include <cstdio>
 #include <cstring>
 #include <vector>
 
@@ -57,16 +58,17 @@ struct KatArgs {
     double in[16];
     double res[64];
     float fres[64];
+    double scratch[8];  // global memory for VariableRef leaves
 };
 
 __global__ void kat_kernel(KatArgs* a) {
     switch (a->which) {
-        case 0: a->n = api_eval::kat_dag(a->res); break;
+        case 0: a->n = api_eval::kat_dag(a->res, a->scratch); break;
         case 1: a->n = api_eval::kat_shared_subgraph(a->res); break;
         case 2: a->n = api_eval::kat_broadcast(a->res); break;
         case 3: a->n = api_eval::kat_chain(a->in[0], a->in[1], a->in[2], a->in[3], a->res); break;
         case 4: a->n = api_eval::kat_operators(a->in, a->in + 2, a->in + 4, a->in + 6, a->res); break;
-        case 5: a->n = api_eval::kat_lsq_point(a->in, a->in[4], a->in[5], a->in[6], a->in[7], a->res); break;
+        case 5: a->n = api_eval::kat_lsq_point(a->in, a->in[4], a->in[5], a->in[6], a->in[7], a->res, a->scratch); break;
         case 6: a->n = api_eval::kat_splat_pair(a->in, a->res); break;
         case 7: a->n = api_eval::kat_math<double>(a->in[0], a->res); break;
         case 8: a->n = api_eval::kat_math<float>(float(a->in[0]), a->fres); break;
@@ -154,6 +156,7 @@ int cuda_kat(int which, const double* in, double* res, float* fres) {
     cudaMemcpy(d, &h, sizeof(h), cudaMemcpyHostToDevice);
     kat_kernel<<<1, 1>>>(d);
     const cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) fprintf(stderr, "kat_kernel(%d): %s\n", which, cudaGetErrorString(e));
     cudaMemcpy(&h, d, sizeof(h), cudaMemcpyDeviceToHost);
     cudaFree(d);
     if (e != cudaSuccess) return -101;

@@ -15,7 +15,7 @@ int mine_eval_op_f32(int op, int aux, const float* in1, int n1, const float* in2
                      float* out, int* nout, float* gin1, float* gin2) {
     return api_eval::eval_op<float>(op, aux, in1, n1, in2, n2, cst, gout, out, nout, gin1, gin2);
 }
-int mine_kat_dag(double* res) { return api_eval::kat_dag(res); }
+int mine_kat_dag(double* res) { double scratch[8]; return api_eval::kat_dag(res, scratch); }
 int mine_kat_shared_subgraph(double* res) { return api_eval::kat_shared_subgraph(res); }
 int mine_kat_broadcast(double* res) { return api_eval::kat_broadcast(res); }
 int mine_kat_chain(double x, double y, double z, double up, double* res) { return api_eval::kat_chain(x, y, z, up, res); }
@@ -23,7 +23,8 @@ int mine_kat_operators(const double* a, const double* b, const double* c, const 
     return api_eval::kat_operators(a, b, c, d, res);
 }
 int mine_kat_lsq_point(const double* p, double x1, double x2, double yt, double delta, double* res) {
-    return api_eval::kat_lsq_point(p, x1, x2, yt, delta, res);
+    double scratch[8];
+    return api_eval::kat_lsq_point(p, x1, x2, yt, delta, res, scratch);
 }
 int mine_kat_splat_pair(const double* in, double* res) { return api_eval::kat_splat_pair(in, res); }
 int mine_kat_math_f64(double x, double* res) { return api_eval::kat_math<double>(x, res); }

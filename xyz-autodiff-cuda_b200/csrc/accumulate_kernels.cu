@@ -156,6 +156,134 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM)
     }
 }
 
+
+// ---- replica tables: the fast path -------------------------------------------------------------------
+// `match.any` costs ~one pass per distinct value on sm_100a (ncu: it is the top stall of the kernel above when
+// ids are spread), so the hot kernel avoids it: every warp's table has R REPLICAS per bin, lane l uses column
+// l % R, and only the 32/R - 1 lanes that share a column can collide.  They are checked with 32/R - 1 shuffles;
+// a batch without collision is one plain LDS/FADD/STS per lane; a batch with a collision is replayed as 32/R
+// rounds in which each column is touched by one lane.  Bins are folded over replicas and warps at the end.
+// Layout: table[bin * R + column]  -> lanes of one column never share a bank with another column.
+template <class T, int R>
+__device__ __forceinline__ void replica_batch(T* table, int id, T v, int k, int lane) {
+    constexpr int kPeers = 32 / R;
+    const bool valid = (id >= 0) && (id < k);
+    // whole batch on one bin: fold in registers first (the reference's own all-threads-one-parameter pattern)
+    const int id0 = __shfl_sync(kFull, id, 0);
+    if (__all_sync(kFull, id == id0)) {
+        const T s = warp_sum(v);
+        if (lane == 0 && valid) table[id * R] += s;
+        __syncwarp();
+        return;
+    }
+    bool clash = false;
+#pragma unroll
+    for (int p = 1; p < kPeers; ++p) clash |= (__shfl_xor_sync(kFull, id, p * R) == id);
+    T* slot = table + (valid ? id : 0) * R + (lane % R);
+    if (!__any_sync(kFull, clash && valid)) {
+        if (valid) *slot += v;
+    } else {
+#pragma unroll
+        for (int round = 0; round < kPeers; ++round) {
+            if (valid && (lane / R) == round) *slot += v;
+            __syncwarp();
+        }
+    }
+    __syncwarp();
+}
+
+template <class T, int R, int kWarpsT, bool kImplicit, bool kDeterministic>
+__global__ void __launch_bounds__(kWarpsT * 32, 1)
+    accumulate_replica_kernel(const int32_t* __restrict__ idx, const T* __restrict__ val, long long n, T* grad, int k,
+                              T* partial_rows) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    T* tables = reinterpret_cast<T*>(smem_raw);
+    constexpr int kThreadsT = kWarpsT * 32;
+    constexpr int kDepth = 4;  // chunks in flight per warp (register double buffer of kDepth chunks)
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int table_elems = k * R;
+    for (int i = tid; i < kWarpsT * table_elems; i += kThreadsT) tables[i] = T(0);
+    __syncthreads();
+    T* table = tables + static_cast<size_t>(warp) * table_elems;
+
+    const long long n_chunks = (n + 127) / 128;
+    const long long gw = static_cast<long long>(blockIdx.x) * kWarpsT + warp;
+    const long long wstride = static_cast<long long>(gridDim.x) * kWarpsT;
+
+    int id_cur[kDepth][4], id_nxt[kDepth][4];
+    T v_cur[kDepth][4], v_nxt[kDepth][4];
+    auto load_chunk = [&](long long c, int (&id)[4], T (&v)[4]) {
+        const long long e0 = c * 128 + lane * 4;
+        if (c < n_chunks && e0 + 4 <= n) {
+            if constexpr (kImplicit) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) id[j] = static_cast<int>((e0 + j) % k);
+            } else {
+                const int4 q = __ldcs(reinterpret_cast<const int4*>(idx + e0));
+                id[0] = q.x; id[1] = q.y; id[2] = q.z; id[3] = q.w;
+            }
+            if constexpr (sizeof(T) == 4) {
+                const float4 f = __ldcs(reinterpret_cast<const float4*>(val + e0));
+                v[0] = f.x; v[1] = f.y; v[2] = f.z; v[3] = f.w;
+            } else {
+                const double2 f0 = __ldcs(reinterpret_cast<const double2*>(val + e0));
+                const double2 f1 = __ldcs(reinterpret_cast<const double2*>(val + e0 + 2));
+                v[0] = f0.x; v[1] = f0.y; v[2] = f1.x; v[3] = f1.y;
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const long long e = e0 + j;
+                const bool in = (c < n_chunks) && (e < n);
+                id[j] = in ? (kImplicit ? static_cast<int>(e % k) : __ldg(idx + e)) : -1;
+                v[j] = in ? __ldg(val + e) : T(0);
+            }
+        }
+    };
+
+#pragma unroll
+    for (int d = 0; d < kDepth; ++d) load_chunk(gw + d * wstride, id_cur[d], v_cur[d]);
+    for (long long c = gw; c < n_chunks; c += wstride * kDepth) {
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) load_chunk(c + (kDepth + d) * wstride, id_nxt[d], v_nxt[d]);
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) {
+            if (c + d * wstride < n_chunks) {
+#pragma unroll
+                for (int j = 0; j < 4; ++j) replica_batch<T, R>(table, id_cur[d][j], v_cur[d][j], k, lane);
+            }
+        }
+#pragma unroll
+        for (int d = 0; d < kDepth; ++d) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                id_cur[d][j] = id_nxt[d][j];
+                v_cur[d][j] = v_nxt[d][j];
+            }
+        }
+    }
+    __syncthreads();
+
+    // fold replicas, then warps, in fixed order
+    T* row = kDeterministic ? partial_rows + static_cast<size_t>(blockIdx.x) * k : nullptr;
+    for (int b = tid; b < k; b += kThreadsT) {
+        T s = T(0);
+#pragma unroll
+        for (int w = 0; w < kWarpsT; ++w) {
+            const T* t = tables + static_cast<size_t>(w) * table_elems + static_cast<size_t>(b) * R;
+            T sw = T(0);
+#pragma unroll
+            for (int r = 0; r < R; ++r) sw += t[r];
+            s += sw;
+        }
+        if constexpr (kDeterministic) {
+            row[b] = s;
+        } else {
+            if (s != T(0)) atomicAdd(grad + b, s);
+        }
+    }
+}
+
 // deterministic finish: grad[b] += sum over rows in CTA order
 template <class T>
 __global__ void accumulate_finish_kernel(const T* __restrict__ rows, int n_rows, T* grad, int k) {
@@ -200,6 +328,32 @@ int launch_tables(const int32_t* idx, const T* val, long long n, T* grad, int k,
     return last_error();
 }
 
+template <class T, int R, int W, bool kImplicit>
+int launch_replicas(const int32_t* idx, const T* val, long long n, T* grad, int k, cudaStream_t st, bool deterministic) {
+    const size_t smem = static_cast<size_t>(W) * k * R * sizeof(T);
+    const long long n_chunks = (n + 127) / 128;
+    const long long want = (n_chunks + W - 1) / W;
+    const int sms = sm_count();
+    const int grid = static_cast<int>(want < sms ? want : sms);  // one CTA per SM (the tables fill shared memory)
+    if (deterministic) {
+        void* scratch = nullptr;
+        int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(grid) * k * sizeof(T), &scratch);
+        if (err) return err;
+        T* rows = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+        auto kern = accumulate_replica_kernel<T, R, W, kImplicit, true>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        kern<<<grid, W * 32, smem, st>>>(idx, val, n, grad, k, rows);
+        accumulate_finish_kernel<T><<<(k + 255) / 256, 256, 0, st>>>(rows, grid, grad, k);
+        count_launch(2);
+    } else {
+        auto kern = accumulate_replica_kernel<T, R, W, kImplicit, false>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        kern<<<grid, W * 32, smem, st>>>(idx, val, n, grad, k, nullptr);
+        count_launch();
+    }
+    return last_error();
+}
+
 template <class T>
 int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, void* stream, int flags) {
     if (n < 0 || k <= 0 || !grad) return XYZ_ERR_INVALID_ARGUMENT;
@@ -209,6 +363,15 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
     if (implicit && !(flags & XYZ_FLAG_IMPLICIT_IDS)) return XYZ_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool deterministic = (flags & XYZ_FLAG_DETERMINISTIC) != 0;
+    const bool vec_ok = aligned16(val) && (implicit || aligned16(idx));
+    // replica tables (fast path): R columns per bin, as many warps as 192 KB of shared memory hold
+    if (vec_ok && n >= (1 << 16)) {
+        const size_t per_warp8 = static_cast<size_t>(k) * 8 * sizeof(T);
+        if (per_warp8 * 6 <= 196608) {
+            return implicit ? launch_replicas<T, 8, 6, true>(idx, val, n, grad, k, st, deterministic)
+                            : launch_replicas<T, 8, 6, false>(idx, val, n, grad, k, st, deterministic);
+        }
+    }
     const size_t smem = static_cast<size_t>(kWarps) * k * sizeof(T);
     const int sms = sm_count();
     if (smem > 200 * 1024) {
