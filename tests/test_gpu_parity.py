@@ -252,10 +252,21 @@ def test_accumulate_deterministic_is_bit_identical_and_variants():
     grad = torch.zeros(k, device=DEV)
     x.accumulate(ti[1:], tv[1:], grad)
     assert (np.abs(grad.cpu().numpy() - orc.accumulate_exact(idx, val, k)) <= 1e-4 * orc.accumulate_exact(idx, np.abs(val), k)).all()
-    for kk in (1, 3, 1001, 100_000):
+    # K = 1, 3 (32 warps), 1001 (odd K), 5000 (8-warp tables), 30000 (match.any tables), 100000 (global REDs)
+    for kk in (1, 3, 1001, 5000, 30_000, 100_000):
         i3, v3 = orc.accumulate_inputs(200_000, kk, "uniform", seed=kk)
         got = run_acc(i3, v3, kk)
         assert (np.abs(got - orc.accumulate_exact(i3, v3, kk)) <= 1e-4 * orc.accumulate_exact(i3, np.abs(v3), kk) + 1e-30).all()
+    # fp64 values through the tagged-table kernel (16 warps at K = 1024), all three id distributions
+    for dist in ("uniform", "zipf", "same"):
+        i4, v4 = orc.accumulate_inputs(1 << 19, k, dist, seed=11)
+        v4 = v4.astype(np.float64) * (1.0 + 1e-9)
+        got = run_acc(i4, v4, k, dtype=torch.float64)
+        exact = np.zeros(k)
+        np.add.at(exact, i4, v4)
+        abs_sum = np.zeros(k)
+        np.add.at(abs_sum, i4, np.abs(v4))
+        assert (np.abs(got - exact) <= 1e-12 * abs_sum + 1e-300).all()
     # accumulates into the caller's values
     grad = torch.ones(k, device=DEV)
     x.accumulate(dev(idx), dev(val), grad)

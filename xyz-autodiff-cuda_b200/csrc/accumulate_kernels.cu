@@ -157,61 +157,80 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM)
 }
 
 
-// ---- replica tables: the fast path -------------------------------------------------------------------
-// `match.any` costs ~one pass per distinct value on sm_100a (ncu: it is the top stall of the kernel above when
-// ids are spread), so the hot kernel avoids it: every warp's table has R REPLICAS per bin, lane l uses column
-// l % R, and only the 32/R - 1 lanes that share a column can collide.  They are checked with 32/R - 1 shuffles;
-// a batch without collision is one plain LDS/FADD/STS per lane; a batch with a collision is replayed as 32/R
-// rounds in which each column is touched by one lane.  Bins are folded over replicas and warps at the end.
-// Layout: table[bin * R + column]  -> lanes of one column never share a bank with another column.
-template <class T, int R>
-__device__ __forceinline__ void replica_batch(T* table, int id, T v, int k, int lane) {
-    constexpr int kPeers = 32 / R;
-    const bool valid = (id >= 0) && (id < k);
-    // whole batch on one bin: fold in registers first (the reference's own all-threads-one-parameter pattern)
-    const int id0 = __shfl_sync(kFull, id, 0);
-    if (__all_sync(kFull, id == id0)) {
-        const T s = warp_sum(v);
-        if (lane == 0 && valid) table[id * R] += s;
-        __syncwarp();
-        return;
-    }
-    bool clash = false;
-#pragma unroll
-    for (int p = 1; p < kPeers; ++p) clash |= (__shfl_xor_sync(kFull, id, p * R) == id);
-    T* slot = table + (valid ? id : 0) * R + (lane % R);
-    if (!__any_sync(kFull, clash && valid)) {
-        if (valid) *slot += v;
-    } else {
-#pragma unroll
-        for (int round = 0; round < kPeers; ++round) {
-            if (valid && (lane / R) == round) *slot += v;
-            __syncwarp();
-        }
-    }
-    __syncwarp();
-}
-
-template <class T, int R, int kWarpsT, bool kImplicit, bool kDeterministic>
+// ---- tagged tables: the fast path ------------------------------------------------------------------------
+// ncu on the kernel above: `match.any` is its top stall when ids are spread, and a design with R replica
+// columns per bin (collision check by shuffles) leaves room for only 6 warps per SM -- latency bound (102 us
+// for 2^24 uniform ids).  The hot kernel therefore arbitrates through shared memory itself:
+//   * every warp owns a K-bin value table plus a K-byte TAG table; 32 warps per SM (160 KB for K = 1024);
+//   * a batch of 32 elements: every lane stores its lane id to tag[id], reads it back, and the lane whose
+//     store landed ("winner", exactly one per distinct id) does the plain LDS/FADD/STS on the value table;
+//   * losers (duplicates inside the batch: 38 % of uniform batches have one) are replayed one lane at a time
+//     when there are <= 2 of them, else grouped with `match.any` over the losers only (few distinct keys =>
+//     cheap), folded with the fixed-order shuffle tree and added by each group's lowest lane;
+//   * when half a batch or more lost (the reference's own all-threads-one-parameter pattern) the warp turns on
+//     a register-level check "whole batch on one bin" (one shuffle + vote, then a shuffle-tree sum and ONE
+//     table update); it turns itself off at the first batch that fails the check.
+// Which duplicate wins the tag store is the hardware's choice, so this path is not the deterministic one.
+// ncu (profiles/): 15.4 shared-memory wavefronts per batch, 14 of them the 4 table/tag accesses at the
+// ~3.5-way bank conflict degree of 32 random banks; l1tex 93 % busy -- the kernel sits on the shared-memory
+// pipe, 41 us for 2^24 uniform ids against 29 us for a kernel that only streams idx+val with this grid.
+template <class T, int kWarpsT, bool kImplicit>
 __global__ void __launch_bounds__(kWarpsT * 32, 1)
-    accumulate_replica_kernel(const int32_t* __restrict__ idx, const T* __restrict__ val, long long n, T* grad, int k,
-                              T* partial_rows) {
+    accumulate_tagged_kernel(const int32_t* __restrict__ idx, const T* __restrict__ val, long long n, T* grad, int k) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tables = reinterpret_cast<T*>(smem_raw);
+    uint8_t* tags = reinterpret_cast<uint8_t*>(tables + static_cast<size_t>(kWarpsT) * k);
     constexpr int kThreadsT = kWarpsT * 32;
-    constexpr int kDepth = 4;  // chunks in flight per warp (register double buffer of kDepth chunks)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int table_elems = k * R;
-    for (int i = tid; i < kWarpsT * table_elems; i += kThreadsT) tables[i] = T(0);
+    for (int i = tid; i < kWarpsT * k; i += kThreadsT) tables[i] = T(0);
     __syncthreads();
-    T* table = tables + static_cast<size_t>(warp) * table_elems;
+    T* table = tables + static_cast<size_t>(warp) * k;
+    uint8_t* tag = tags + static_cast<size_t>(warp) * k;
 
     const long long n_chunks = (n + 127) / 128;
     const long long gw = static_cast<long long>(blockIdx.x) * kWarpsT + warp;
     const long long wstride = static_cast<long long>(gridDim.x) * kWarpsT;
+    bool same_mode = false;  // warp-uniform
 
-    int id_cur[kDepth][4], id_nxt[kDepth][4];
-    T v_cur[kDepth][4], v_nxt[kDepth][4];
+    auto batch = [&](int id, T v) {
+        const bool valid = static_cast<unsigned>(id) < static_cast<unsigned>(k);
+        if (same_mode) {
+            const int id0 = __shfl_sync(kFull, id, 0);
+            if (__all_sync(kFull, id == id0)) {
+                const T s = warp_sum(v);
+                if (lane == 0 && valid) table[id] += s;
+                __syncwarp();
+                return;
+            }
+            same_mode = false;
+        }
+        if (valid) tag[id] = static_cast<uint8_t>(lane);
+        __syncwarp();
+        const bool won = valid && tag[id] == lane;
+        if (won) table[id] += v;
+        const bool mine = valid && !won;
+        unsigned lost = __ballot_sync(kFull, mine);
+        __syncwarp();
+        if (lost == 0u) return;
+        if (__popc(lost) <= 2) {
+            while (lost) {
+                const int l = __ffs(lost) - 1;
+                if (lane == l) table[id] += v;
+                __syncwarp();
+                lost &= lost - 1u;
+            }
+            return;
+        }
+        same_mode = __popc(lost) >= 16;
+        unsigned peers = __match_any_sync(kFull, mine ? id : -1);
+        if (!mine) peers = 1u << lane;
+        v = reduce_peers(peers, v, lane);
+        if (mine && lane == __ffs(peers) - 1) table[id] += v;
+        __syncwarp();
+    };
+
+    int id_nxt[4];
+    T v_nxt[4];
     auto load_chunk = [&](long long c, int (&id)[4], T (&v)[4]) {
         const long long e0 = c * 128 + lane * 4;
         if (c < n_chunks && e0 + 4 <= n) {
@@ -241,46 +260,29 @@ __global__ void __launch_bounds__(kWarpsT * 32, 1)
         }
     };
 
+    // one chunk (1 KB of idx+val per warp) in flight per warp while the previous one is accumulated:
+    // 32 warps x 1 KB per SM covers the HBM latency (a second chunk in flight measured slower)
+    load_chunk(gw, id_nxt, v_nxt);
+    for (long long c = gw; c < n_chunks; c += wstride) {
+        int id_cur[4];
+        T v_cur[4];
 #pragma unroll
-    for (int d = 0; d < kDepth; ++d) load_chunk(gw + d * wstride, id_cur[d], v_cur[d]);
-    for (long long c = gw; c < n_chunks; c += wstride * kDepth) {
-#pragma unroll
-        for (int d = 0; d < kDepth; ++d) load_chunk(c + (kDepth + d) * wstride, id_nxt[d], v_nxt[d]);
-#pragma unroll
-        for (int d = 0; d < kDepth; ++d) {
-            if (c + d * wstride < n_chunks) {
-#pragma unroll
-                for (int j = 0; j < 4; ++j) replica_batch<T, R>(table, id_cur[d][j], v_cur[d][j], k, lane);
-            }
+        for (int j = 0; j < 4; ++j) {
+            id_cur[j] = id_nxt[j];
+            v_cur[j] = v_nxt[j];
         }
+        load_chunk(c + wstride, id_nxt, v_nxt);
 #pragma unroll
-        for (int d = 0; d < kDepth; ++d) {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                id_cur[d][j] = id_nxt[d][j];
-                v_cur[d][j] = v_nxt[d][j];
-            }
-        }
+        for (int j = 0; j < 4; ++j) batch(id_cur[j], v_cur[j]);
     }
     __syncthreads();
 
-    // fold replicas, then warps, in fixed order
-    T* row = kDeterministic ? partial_rows + static_cast<size_t>(blockIdx.x) * k : nullptr;
+    // fold the warps' tables in warp order
     for (int b = tid; b < k; b += kThreadsT) {
         T s = T(0);
-#pragma unroll
-        for (int w = 0; w < kWarpsT; ++w) {
-            const T* t = tables + static_cast<size_t>(w) * table_elems + static_cast<size_t>(b) * R;
-            T sw = T(0);
-#pragma unroll
-            for (int r = 0; r < R; ++r) sw += t[r];
-            s += sw;
-        }
-        if constexpr (kDeterministic) {
-            row[b] = s;
-        } else {
-            if (s != T(0)) atomicAdd(grad + b, s);
-        }
+#pragma unroll 8
+        for (int w = 0; w < kWarpsT; ++w) s += tables[static_cast<size_t>(w) * k + b];
+        if (s != T(0)) atomicAdd(grad + b, s);
     }
 }
 
@@ -328,30 +330,30 @@ int launch_tables(const int32_t* idx, const T* val, long long n, T* grad, int k,
     return last_error();
 }
 
-template <class T, int R, int W, bool kImplicit>
-int launch_replicas(const int32_t* idx, const T* val, long long n, T* grad, int k, cudaStream_t st, bool deterministic) {
-    const size_t smem = static_cast<size_t>(W) * k * R * sizeof(T);
+template <class T, int W, bool kImplicit>
+int launch_tagged(const int32_t* idx, const T* val, long long n, T* grad, int k, cudaStream_t st) {
+    const size_t smem = static_cast<size_t>(W) * k * (sizeof(T) + 1);
     const long long n_chunks = (n + 127) / 128;
     const long long want = (n_chunks + W - 1) / W;
     const int sms = sm_count();
     const int grid = static_cast<int>(want < sms ? want : sms);  // one CTA per SM (the tables fill shared memory)
-    if (deterministic) {
-        void* scratch = nullptr;
-        int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(grid) * k * sizeof(T), &scratch);
-        if (err) return err;
-        T* rows = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(scratch) + 256);
-        auto kern = accumulate_replica_kernel<T, R, W, kImplicit, true>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        kern<<<grid, W * 32, smem, st>>>(idx, val, n, grad, k, rows);
-        accumulate_finish_kernel<T><<<(k + 255) / 256, 256, 0, st>>>(rows, grid, grad, k);
-        count_launch(2);
-    } else {
-        auto kern = accumulate_replica_kernel<T, R, W, kImplicit, false>;
-        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        kern<<<grid, W * 32, smem, st>>>(idx, val, n, grad, k, nullptr);
-        count_launch();
-    }
+    auto kern = accumulate_tagged_kernel<T, W, kImplicit>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    kern<<<grid, W * 32, smem, st>>>(idx, val, n, grad, k);
+    count_launch();
     return last_error();
+}
+
+template <class T, bool kImplicit>
+int launch_tagged_any(const int32_t* idx, const T* val, long long n, T* grad, int k, cudaStream_t st, bool* done) {
+    const size_t per_warp = static_cast<size_t>(k) * (sizeof(T) + 1);
+    const size_t budget = 200 * 1024;
+    *done = true;
+    if (per_warp * 32 <= budget) return launch_tagged<T, 32, kImplicit>(idx, val, n, grad, k, st);
+    if (per_warp * 16 <= budget) return launch_tagged<T, 16, kImplicit>(idx, val, n, grad, k, st);
+    if (per_warp * 8 <= budget) return launch_tagged<T, 8, kImplicit>(idx, val, n, grad, k, st);
+    *done = false;
+    return 0;
 }
 
 template <class T>
@@ -364,13 +366,12 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool deterministic = (flags & XYZ_FLAG_DETERMINISTIC) != 0;
     const bool vec_ok = aligned16(val) && (implicit || aligned16(idx));
-    // replica tables (fast path): R columns per bin, as many warps as 192 KB of shared memory hold
-    if (vec_ok && n >= (1 << 16)) {
-        const size_t per_warp8 = static_cast<size_t>(k) * 8 * sizeof(T);
-        if (per_warp8 * 6 <= 196608) {
-            return implicit ? launch_replicas<T, 8, 6, true>(idx, val, n, grad, k, st, deterministic)
-                            : launch_replicas<T, 8, 6, false>(idx, val, n, grad, k, st, deterministic);
-        }
+    // tagged tables (fast path; not run-to-run deterministic): as many warps as 200 KB of shared memory hold
+    if (!deterministic && vec_ok && n >= (1 << 16)) {
+        bool done = false;
+        const int err = implicit ? launch_tagged_any<T, true>(idx, val, n, grad, k, st, &done)
+                                 : launch_tagged_any<T, false>(idx, val, n, grad, k, st, &done);
+        if (done) return err;
     }
     const size_t smem = static_cast<size_t>(kWarps) * k * sizeof(T);
     const int sms = sm_count();

@@ -130,23 +130,32 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM)
     __syncthreads();
     if (!sm.is_last) return;
     __threadfence();
-    // last CTA: one warp sums the rows in CTA order: lane-strided partial sums, then a shuffle tree
-    if (tid < 32) {
+    // last CTA: thread t sums rows t, t+256, ... (independent loads, all in flight together), then the same
+    // fixed-order shuffle/shared-memory tree as above -> bit-identical for a given grid
+    {
         double s[kAcc];
 #pragma unroll
         for (int k = 0; k < kAcc; ++k) s[k] = 0.0;
-        for (unsigned int r = tid; r < gridDim.x; r += 32) {
+        for (unsigned int r = tid; r < gridDim.x; r += kThreads) {
 #pragma unroll
             for (int k = 0; k < kAcc; ++k) s[k] += __ldcg(partials + static_cast<size_t>(r) * kAcc + k);
         }
 #pragma unroll
         for (int k = 0; k < kAcc; ++k) s[k] = warp_sum(s[k]);
-        if (tid == 0) {
+        __syncthreads();  // sm.red is reused
+        if ((tid & 31) == 0) {
 #pragma unroll
-            for (int k = 0; k < 4; ++k) params->grad[k] += s[k];
-            if (loss_sum) *loss_sum += s[4];
-            *ticket = 0u;
+            for (int k = 0; k < kAcc; ++k) sm.red[tid >> 5][k] = s[k];
         }
+        __syncthreads();
+        if (tid < kAcc) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) t += sm.red[w][tid];
+            if (tid < 4) params->grad[tid] += t;
+            else if (loss_sum) *loss_sum += t;
+        }
+        if (tid == 0) *ticket = 0u;
     }
 }
 

@@ -47,8 +47,9 @@ struct SplatBuffers {  // device scratch of one launch (library-owned)
     unsigned int* keys_out;   // entries: sorted
     unsigned int* vals_in;    // entries: entry index in Gaussian order (== position)
     unsigned int* vals_out;   // entries: sorted -> original entry index
-    int* sorted_gid;          // entries: Gaussian id per sorted entry
+    int* sorted_gid;          // entries: Gaussian id per sorted entry (fast mode: aliases vals_out)
     int2* tile_ranges;        // tiles: [begin, end)
+    int* chunk_offsets;       // tiles + 1: exclusive scan of ceil(list length / 256) = backward CTAs before a tile
     float* tile_loss;         // tiles
     float* entry_grads;       // deterministic mode: entries x 9 (indexed by ORIGINAL entry index)
 };

@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(256)
     splat_emit_keys_kernel(int n, int tiles_x, const int4* __restrict__ rects, const unsigned int* __restrict__ touched,
                            const unsigned long long* __restrict__ offsets_incl, unsigned int* __restrict__ keys,
-                           unsigned int* __restrict__ vals) {
+                           unsigned int* __restrict__ vals, int by_gid) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= n) return;
     const int4 r = rects[g];
@@ -86,7 +86,9 @@ __global__ void __launch_bounds__(256)
     for (int ty = r.y; ty < r.w; ++ty)
         for (int tx = r.x; tx < r.z; ++tx) {
             keys[o] = static_cast<unsigned int>(ty * tiles_x + tx);
-            vals[o] = o;
+            // payload: the Gaussian id itself, or (deterministic mode) the entry's position in Gaussian order,
+            // which names its row of entry_grads
+            vals[o] = by_gid ? static_cast<unsigned int>(g) : o;
             ++o;
         }
 }
@@ -112,7 +114,51 @@ __global__ void __launch_bounds__(256)
     const unsigned int k = keys_sorted[i];
     if (i == 0 || keys_sorted[i - 1] != k) tile_ranges[k].x = static_cast<int>(i);
     if (i == entries - 1 || keys_sorted[i + 1] != k) tile_ranges[k].y = static_cast<int>(i + 1);
-    sorted_gid[i] = entry_to_gaussian(offsets_incl, n, vals_sorted[i]);
+    // sorted_gid == nullptr: the sort payload already is the Gaussian id
+    if (sorted_gid) sorted_gid[i] = entry_to_gaussian(offsets_incl, n, vals_sorted[i]);
+}
+
+// ---- backward work list: exclusive scan over the tiles of ceil(list length / 256) -------------------------
+__global__ void __launch_bounds__(1024)
+    splat_chunk_scan_kernel(const int2* __restrict__ tile_ranges, int n_tiles, int* __restrict__ chunk_offsets) {
+    __shared__ int s_warp[32];
+    __shared__ int s_carry;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int t = base + tid;
+        int c = 0;
+        if (t < n_tiles) {
+            const int2 r = tile_ranges[t];
+            c = (r.y - r.x + kTilePixels - 1) / kTilePixels;
+        }
+        int x = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int w = s_warp[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_warp[lane] = w;  // inclusive over warps
+        }
+        __syncthreads();
+        const int carry = s_carry;
+        const int before = carry + (warp > 0 ? s_warp[warp - 1] : 0) + (x - c);
+        if (t < n_tiles) chunk_offsets[t] = before;
+        __syncthreads();
+        if (tid == 1023) s_carry = carry + s_warp[31];
+        __syncthreads();
+    }
+    if (tid == 0) chunk_offsets[n_tiles] = s_carry;
 }
 
 // ---- loss: tile partials summed in tile order (no float atomics) ---------------------------------------
@@ -187,7 +233,8 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     auto take = [&off](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
     const size_t o_rec = take(sizeof(float4) * 3 * ng), o_rect = take(sizeof(int4) * ng),
                  o_touched = take(sizeof(unsigned int) * ng), o_offsets = take(sizeof(unsigned long long) * ng),
-                 o_ranges = take(sizeof(int2) * n_tiles), o_tloss = take(sizeof(float) * n_tiles);
+                 o_ranges = take(sizeof(int2) * n_tiles), o_tloss = take(sizeof(float) * n_tiles),
+                 o_chunks = take(sizeof(int) * (n_tiles + 1));
     size_t scan_tmp_bytes = 0;
     cub::DeviceScan::InclusiveSum(nullptr, scan_tmp_bytes, TouchedIter(nullptr, ToU64()),
                                   static_cast<unsigned long long*>(nullptr), ng, st);
@@ -202,6 +249,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     b.offsets = reinterpret_cast<unsigned long long*>(base + o_offsets);
     b.tile_ranges = reinterpret_cast<int2*>(base + o_ranges);
     b.tile_loss = reinterpret_cast<float*>(base + o_tloss);
+    b.chunk_offsets = reinterpret_cast<int*>(base + o_chunks);
 
     cudaError_t ce = cudaMemsetAsync(b.tile_ranges, 0, sizeof(int2) * n_tiles, st);
     if (ce != cudaSuccess) return static_cast<int>(ce);
@@ -232,7 +280,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     size_t soff = 0;
     auto stake = [&soff](size_t bytes) { size_t o = soff; soff += align_up(bytes); return o; };
     const size_t o_kin = stake(4 * ne), o_kout = stake(4 * ne), o_vin = stake(4 * ne), o_vout = stake(4 * ne),
-                 o_gid = stake(4 * ne), o_eg = stake(deterministic ? 36 * ne : 0);
+                 o_gid = stake(deterministic ? 4 * ne : 0), o_eg = stake(deterministic ? 36 * ne : 0);
     size_t sort_tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, static_cast<unsigned int*>(nullptr),
                                     static_cast<unsigned int*>(nullptr), static_cast<unsigned int*>(nullptr),
@@ -245,20 +293,22 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     b.keys_out = reinterpret_cast<unsigned int*>(sbase + o_kout);
     b.vals_in = reinterpret_cast<unsigned int*>(sbase + o_vin);
     b.vals_out = reinterpret_cast<unsigned int*>(sbase + o_vout);
-    b.sorted_gid = reinterpret_cast<int*>(sbase + o_gid);
+    // fast mode: the sort payload is the Gaussian id; deterministic mode: payload = entry position, ids derived
+    b.sorted_gid = deterministic ? reinterpret_cast<int*>(sbase + o_gid) : reinterpret_cast<int*>(b.vals_out);
     b.entry_grads = deterministic ? reinterpret_cast<float*>(sbase + o_eg) : nullptr;
 
     if (entries > 0) {
         splat_emit_keys_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, v.tiles_x, b.rects, b.touched, b.offsets, b.keys_in,
-                                                                b.vals_in);
+                                                                b.vals_in, deterministic ? 0 : 1);
         count_launch();
         ce = cub::DeviceRadixSort::SortPairs(sbase + o_sort_tmp, sort_tmp_bytes, b.keys_in, b.keys_out, b.vals_in,
                                              b.vals_out, static_cast<int>(entries), 0, key_bits, st);
         if (ce != cudaSuccess) return static_cast<int>(ce);
         count_launch(3);
         splat_ranges_kernel<<<static_cast<unsigned int>((entries + 255) / 256), 256, 0, st>>>(
-            entries, b.keys_out, b.vals_out, b.offsets, N, b.tile_ranges, b.sorted_gid);
-        count_launch();
+            entries, b.keys_out, b.vals_out, b.offsets, N, b.tile_ranges, deterministic ? b.sorted_gid : nullptr);
+        splat_chunk_scan_kernel<<<1, 1024, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets);
+        count_launch(2);
     }
 
     err = precise ? splat_forward_launch_precise(v, b, target, output, st)

@@ -17,30 +17,34 @@
 namespace xyzb {
 namespace {
 
-struct PairRec {  // per Gaussian, staged in shared memory for the forward pass
-    float4 a;     // cx, cy, ia, 2*ib
-    float4 b;     // ic, sigmoid(opacity), r, g
-    float c;      // b
-};
+// Exponent of one pair.  The reference evaluates exp(-(d2 * 0.5)) (mul_constant / neg / exp nodes); both
+// flavours fold the constant into the per-Gaussian conic (A2, B2, C2) = kappa * (ia, 2 ib, ic) so the pair costs
+// two FMAs and one special-function op:
+//   fast    kappa = -0.5 * log2(e), e = ex2.approx.ftz(arg)   (what -use_fast_math makes of expf: ex2(x * log2 e))
+//   precise kappa = -0.5,           e = expf(arg)             (IEEE flavour)
+// Both underflow to exactly 0.0f beyond the d2 bounds in splat_common.cuh (checked by the cull parity test).
+#if XYZ_SPLAT_IS_FAST
+constexpr float kKappa = -0.72134752044448170368f;
+__device__ __forceinline__ float pair_exp(float arg) { return exp2f(arg); }
+#else
+constexpr float kKappa = -0.5f;
+__device__ __forceinline__ float pair_exp(float arg) { return expf(arg); }
+#endif
 
-// weight of one pair: mahalanobis_distance.cuh:88-97, then *0.5f, neg, exp, * sigmoid(opacity)
-__device__ __forceinline__ float pair_weight(float px, float py, float cx, float cy, float ia, float ib2, float ic,
-                                             float so, float& dx, float& dy, float& e) {
-    dx = px - cx;
-    dy = py - cy;
-    const float d2 = ia * dx * dx + ib2 * dx * dy + ic * dy * dy;
-    e = expf(-(d2 * 0.5f));
-    return e * so;
+__device__ __forceinline__ float xor_sign(float v, unsigned int sign_bit) {
+    return __uint_as_float(__float_as_uint(v) ^ sign_bit);
 }
 
 // ---- forward: one CTA per tile, one pixel per thread -------------------------------------------
+// Staged per Gaussian (shared memory, 32 B): {cx, cy, A2, B2} {C2, so*r, so*g, so*b}.
+// Per pair: dx, dy, arg = dx*(A2*dx + B2*dy) + (C2*dy)*dy, e, out_i += (so*c_i) * e   -- ascending Gaussian
+// index, the reference's summation order (gaussian_splatting_kernel.cu:33-62).
 __global__ void __launch_bounds__(kTilePixels)
     splat_forward_kernel(SplatView v, const float4* __restrict__ records, const int* __restrict__ sorted_gid,
                          const int2* __restrict__ tile_ranges, const float* __restrict__ target,
                          float* __restrict__ output, float* __restrict__ tile_loss, int tile_y0) {
     __shared__ float4 s_a[kTilePixels];
     __shared__ float4 s_b[kTilePixels];
-    __shared__ float s_c[kTilePixels];
     __shared__ float s_red[kTilePixels / 32];
 
     const int tid = threadIdx.x;
@@ -59,21 +63,21 @@ __global__ void __launch_bounds__(kTilePixels)
         if (tid < n) {
             const int g = sorted_gid[base + tid];
             const float4 r0 = __ldg(records + 3 * g), r1 = __ldg(records + 3 * g + 1), r2 = __ldg(records + 3 * g + 2);
-            s_a[tid] = make_float4(r0.x, r0.y, r0.z, 2.0f * r0.w);
-            s_b[tid] = make_float4(r1.x, r1.y, r1.z, r1.w);
-            s_c[tid] = r2.x;
+            s_a[tid] = make_float4(r0.x, r0.y, kKappa * r0.z, (2.0f * kKappa) * r0.w);
+            s_b[tid] = make_float4(kKappa * r1.x, r1.y * r1.z, r1.y * r1.w, r1.y * r2.x);
         }
         __syncthreads();
-#pragma unroll 4
+#pragma unroll 8
         for (int j = 0; j < n; ++j) {
             const float4 a = s_a[j];
             const float4 b = s_b[j];
-            const float cb = s_c[j];
-            float dx, dy, e;
-            const float w = pair_weight(px, py, a.x, a.y, a.z, a.w, b.x, b.y, dx, dy, e);
-            o0 += b.z * w;  // color * broadcast(weighted_gauss), ascending Gaussian index
-            o1 += b.w * w;
-            o2 += cb * w;
+            const float dx = px - a.x, dy = py - a.y;
+            const float q = fmaf(a.z, dx, a.w * dy);
+            const float arg = fmaf(dx, q, (b.x * dy) * dy);
+            const float e = pair_exp(arg);
+            o0 = fmaf(b.y, e, o0);
+            o1 = fmaf(b.z, e, o1);
+            o2 = fmaf(b.w, e, o2);
         }
     }
     float l = 0.f;
@@ -98,34 +102,110 @@ __global__ void __launch_bounds__(kTilePixels)
 }
 
 // ---- backward: one thread per (tile, Gaussian) list entry ----------------------------------------
-// Per pair (gaussian_splatting_kernel.cu:84-110, run() of the l1_norm root):
-//   cd_i = wc_i - (tgt_i - out_i)          (rest_sum += un-forwarded weighted_color adds 0: Q2)
+// Per pair (gaussian_splatting_kernel.cu:84-110, run() of the l1_norm root), with w = e * so:
+//   cd_i = c_i w - (tgt_i - out_i)         (rest_sum += un-forwarded weighted_color adds 0: Q2)
 //   s_i  = sign(cd_i)                      l1_norm_logic.cuh:29-37
-//   d color_i += s_i * w ; g_w = sum s_i * color_i          mul_logic.cuh:33-41
-//   g_e = g_w * so ; d so += g_w * e
-//   g_d2 = -(g_e * e) * 0.5                exp / neg / mul_constant backward
-//   d center -= g_d2 * (2 ia dx + 2 ib dy , 2 ib dx + 2 ic dy)     mahalanobis_distance.cuh:100-113
-//   d inv += g_d2 * (dx^2, 2 dx dy, dy^2)                           :116-118
-// Everything after this is linear with per-Gaussian coefficients and is applied once per entry.
+//   d color_i += s_i w ; g_w = sum s_i c_i                  mul_logic.cuh:33-41
+//   d so += g_w e ; g_d2 = -0.5 so (g_w e)                   exp / neg / mul_constant backward
+//   d center -= g_d2 (2 ia dx + 2 ib dy , 2 ib dx + 2 ic dy)  mahalanobis_distance.cuh:100-113
+//   d inv += g_d2 (dx^2, 2 dx dy, dy^2)                      :116-118
+// Everything is LINEAR in the per-pair quantity t = g_w e with per-Gaussian (and per-row: dy) coefficients, so
+// the pixel loop only accumulates   sum s_i e (3),  and per row  sum t, sum t dx, sum t dx^2 ;
+// rows fold into  T0 = sum t, Tx, Ty, Txx, Txy, Tyy ; the conic / center / opacity / covariance chain rule is
+// applied once per entry.  27 instructions per pair instead of the reference's ~200 + 9 atomics.
+// sign(): s_i e and s_i c_i are formed by XOR-ing the sign bit of cd_i into e and c_i.  cd_i == 0 with e != 0
+// (an exact cancellation c_i w == tgt_i - out_i) gets +-1 where the reference's l1_norm gives 0: one pair's term,
+// inside the stated kink tolerance; with e == 0 every product is 0 either way.
+template <bool kMasked>
+__device__ __forceinline__ void entry_tile_pass(const float4* __restrict__ s_rest, float px0, float py0, float cx,
+                                                float cy, float A2, float B2, float C2, float cs0, float cs1,
+                                                float cs2, float c0, float c1, float c2, float (&ac)[3],
+                                                float (&T)[6]) {
+#pragma unroll 1
+    for (int r = 0; r < kTile; ++r) {
+        const float dy = (py0 + static_cast<float>(r)) - cy;
+        const float u = B2 * dy;
+        const float t = (C2 * dy) * dy;
+        float S0 = 0.f, Sx = 0.f, Sxx = 0.f;
+#pragma unroll
+        for (int j = 0; j < kTile; ++j) {
+            const float4 rest = s_rest[r * kTile + j];
+            const float dx = (px0 + static_cast<float>(j)) - cx;
+            const float q = fmaf(A2, dx, u);
+            const float arg = fmaf(dx, q, t);
+            float e = pair_exp(arg);
+            if (kMasked) e *= rest.w;  // 0 for pixels outside the image / row band
+            const unsigned int b0 = __float_as_uint(fmaf(cs0, e, -rest.x)) & 0x80000000u;
+            const unsigned int b1 = __float_as_uint(fmaf(cs1, e, -rest.y)) & 0x80000000u;
+            const unsigned int b2 = __float_as_uint(fmaf(cs2, e, -rest.z)) & 0x80000000u;
+            ac[0] += xor_sign(e, b0);
+            ac[1] += xor_sign(e, b1);
+            ac[2] += xor_sign(e, b2);
+            const float gw = (xor_sign(c0, b0) + xor_sign(c1, b1)) + xor_sign(c2, b2);
+            const float tt = gw * e;
+            const float tx = tt * dx;
+            S0 += tt;
+            Sx += tx;
+            Sxx = fmaf(tx, dx, Sxx);
+        }
+        T[0] += S0;
+        T[1] += Sx;
+        T[2] = fmaf(dy, S0, T[2]);
+        T[3] += Sxx;
+        T[4] = fmaf(dy, Sx, T[4]);
+        T[5] = fmaf(dy * dy, S0, T[5]);
+    }
+}
+
+// One CTA = up to 256 consecutive list entries of ONE tile (chunk_offsets: exclusive scan of ceil(len/256) over
+// the tiles; the grid is an upper bound, surplus CTAs exit).
 __global__ void __launch_bounds__(kTilePixels)
-    splat_backward_kernel(SplatView v, const float4* __restrict__ records, const unsigned int* __restrict__ keys_sorted,
-                          const int* __restrict__ sorted_gid, const unsigned int* __restrict__ sorted_orig,
-                          const xyz_gaussian_params* __restrict__ params, xyz_gaussian_grads* grads,
-                          const float* __restrict__ target, const float* __restrict__ output, long long entries,
-                          float* __restrict__ entry_grads) {
-    __shared__ float4 s_rest[kTilePixels];  // tgt - out per pixel of the current tile; w < 0: pixel inactive
-    __shared__ int s_tiles[kTilePixels];
-    __shared__ int s_ntiles;
+    splat_backward_kernel(SplatView v, const float4* __restrict__ records, const int2* __restrict__ tile_ranges,
+                          const int* __restrict__ chunk_offsets, int n_tiles, const int* __restrict__ sorted_gid,
+                          const unsigned int* __restrict__ sorted_orig, const xyz_gaussian_params* __restrict__ params,
+                          xyz_gaussian_grads* grads, const float* __restrict__ target,
+                          const float* __restrict__ output, float* __restrict__ entry_grads) {
+    __shared__ float4 s_rest[kTilePixels];  // (tgt - out) per pixel of the tile; .w = 1 active, 0 inactive
+    __shared__ int s_tile;
+    __shared__ int s_all_active;
 
     const int tid = threadIdx.x;
-    const long long i = blockIdx.x * static_cast<long long>(kTilePixels) + tid;
-    const bool valid = i < entries;
-    const int my_tile = valid ? static_cast<int>(keys_sorted[i]) : -1;
-    if (tid == 0) s_ntiles = 0;
+    if (tid == 0) {
+        // the tile owning chunk blockIdx.x: last t with chunk_offsets[t] <= blockIdx.x
+        const int c = static_cast<int>(blockIdx.x);
+        int lo = 0, hi = n_tiles;  // chunk_offsets has n_tiles + 1 entries
+        if (c >= chunk_offsets[n_tiles]) {
+            lo = -1;
+        } else {
+            while (hi - lo > 1) {
+                const int mid = (lo + hi) >> 1;
+                if (chunk_offsets[mid] <= c) lo = mid; else hi = mid;
+            }
+        }
+        s_tile = lo;
+        s_all_active = 1;
+    }
     __syncthreads();
+    const int tile = s_tile;
+    if (tile < 0) return;
+    const int2 range = tile_ranges[tile];
+    const int i = range.x + (static_cast<int>(blockIdx.x) - chunk_offsets[tile]) * kTilePixels + tid;
+    const bool valid = i < range.y;
+    const int tile_x = tile % v.tiles_x, tile_y = tile / v.tiles_x;
     {
-        const int prev = (tid > 0 && valid) ? static_cast<int>(keys_sorted[i - 1]) : -2;
-        if (valid && (tid == 0 || prev != my_tile)) s_tiles[atomicAdd(&s_ntiles, 1)] = my_tile;
+        const int pxi = tile_x * kTile + (tid & (kTile - 1));
+        const int pyi = tile_y * kTile + (tid >> 4);
+        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (pxi < v.width && pyi >= v.row_begin && pyi < v.row_end) {
+            const size_t p = static_cast<size_t>(pyi) * v.width + pxi;
+            r.x = __ldg(target + 3 * p) - __ldg(output + 3 * p);  // rest_sum = target_color - pixel_out
+            r.y = __ldg(target + 3 * p + 1) - __ldg(output + 3 * p + 1);
+            r.z = __ldg(target + 3 * p + 2) - __ldg(output + 3 * p + 2);
+            r.w = 1.f;
+        } else {
+            s_all_active = 0;
+        }
+        s_rest[tid] = r;
     }
 
     float cx = 0.f, cy = 0.f, ia = 0.f, ib = 0.f, ic = 0.f, so = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
@@ -136,57 +216,28 @@ __global__ void __launch_bounds__(kTilePixels)
         cx = r0.x; cy = r0.y; ia = r0.z; ib = r0.w;
         ic = r1.x; so = r1.y; c0 = r1.z; c1 = r1.w; c2 = r2.x;
     }
-    const float ib2 = 2.0f * ib;
-    float a_c0 = 0.f, a_c1 = 0.f, a_c2 = 0.f, a_so = 0.f, a_cx = 0.f, a_cy = 0.f, a_ia = 0.f, a_ib = 0.f, a_ic = 0.f;
     __syncthreads();
-    const int ntiles = s_ntiles;
-
-    for (int k = 0; k < ntiles; ++k) {
-        const int tile = s_tiles[k];
-        const int tile_x = tile % v.tiles_x, tile_y = tile / v.tiles_x;
-        __syncthreads();
-        {
-            const int pxi = tile_x * kTile + (tid & (kTile - 1));
-            const int pyi = tile_y * kTile + (tid >> 4);
-            float4 r = make_float4(0.f, 0.f, 0.f, -1.f);
-            if (pxi < v.width && pyi >= v.row_begin && pyi < v.row_end) {
-                const size_t p = static_cast<size_t>(pyi) * v.width + pxi;
-                r.x = __ldg(target + 3 * p) - __ldg(output + 3 * p);  // rest_sum = target_color - pixel_out
-                r.y = __ldg(target + 3 * p + 1) - __ldg(output + 3 * p + 1);
-                r.z = __ldg(target + 3 * p + 2) - __ldg(output + 3 * p + 2);
-                r.w = 1.f;
-            }
-            s_rest[tid] = r;
-        }
-        __syncthreads();
-        if (my_tile != tile) continue;
-        const float px0 = static_cast<float>(tile_x * kTile), py0 = static_cast<float>(tile_y * kTile);
-#pragma unroll 2
-        for (int p = 0; p < kTilePixels; ++p) {
-            const float4 rest = s_rest[p];
-            if (rest.w < 0.f) continue;  // uniform across the CTA
-            const float px = px0 + static_cast<float>(p & (kTile - 1));
-            const float py = py0 + static_cast<float>(p >> 4);
-            float dx, dy, e;
-            const float w = pair_weight(px, py, cx, cy, ia, ib2, ic, so, dx, dy, e);
-            const float cd0 = c0 * w - rest.x, cd1 = c1 * w - rest.y, cd2 = c2 * w - rest.z;
-            const float s0 = cd0 > 0.f ? 1.f : (cd0 < 0.f ? -1.f : 0.f);
-            const float s1 = cd1 > 0.f ? 1.f : (cd1 < 0.f ? -1.f : 0.f);
-            const float s2 = cd2 > 0.f ? 1.f : (cd2 < 0.f ? -1.f : 0.f);
-            a_c0 += s0 * w;
-            a_c1 += s1 * w;
-            a_c2 += s2 * w;
-            const float g_w = s0 * c0 + s1 * c1 + s2 * c2;
-            a_so += g_w * e;
-            const float g_d2 = -((g_w * so) * e) * 0.5f;
-            a_cx -= g_d2 * (2.0f * ia * dx + ib2 * dy);
-            a_cy -= g_d2 * (ib2 * dx + 2.0f * ic * dy);
-            a_ia += g_d2 * dx * dx;
-            a_ib += g_d2 * 2.0f * dx * dy;
-            a_ic += g_d2 * dy * dy;
-        }
-    }
     if (!valid) return;
+
+    float ac[3] = {0.f, 0.f, 0.f};
+    float T[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // sum t {1, dx, dy, dx^2, dx dy, dy^2}
+    {
+        const float px0 = static_cast<float>(tile_x * kTile), py0 = static_cast<float>(tile_y * kTile);
+        const float A2 = kKappa * ia, B2 = (2.0f * kKappa) * ib, C2 = kKappa * ic;
+        const float cs0 = so * c0, cs1 = so * c1, cs2 = so * c2;
+        if (s_all_active)
+            entry_tile_pass<false>(s_rest, px0, py0, cx, cy, A2, B2, C2, cs0, cs1, cs2, c0, c1, c2, ac, T);
+        else
+            entry_tile_pass<true>(s_rest, px0, py0, cx, cy, A2, B2, C2, cs0, cs1, cs2, c0, c1, c2, ac, T);
+    }
+    // per-pair g_d2 = gamma * t with gamma = -0.5 so
+    const float gamma = -0.5f * so;
+    const float Gx = gamma * T[1], Gy = gamma * T[2];
+    const float a_ia = gamma * T[3], a_ib = 2.0f * (gamma * T[4]), a_ic = gamma * T[5];
+    const float ib2 = 2.0f * ib;
+    const float a_cx = -(2.0f * ia * Gx + ib2 * Gy);
+    const float a_cy = -(ib2 * Gx + 2.0f * ic * Gy);
+    const float a_so = T[0];
 
     // Per-Gaussian chain rule, once per entry (linear in the sums above).
     const xyz_gaussian_params gp = params[g];
@@ -217,9 +268,9 @@ __global__ void __launch_bounds__(kTilePixels)
     out9[2] = g_es0 * es0;  // exp backward recomputes exp(scale)
     out9[3] = g_es1 * es1;
     out9[4] = g_theta;
-    out9[5] = a_c0;
-    out9[6] = a_c1;
-    out9[7] = a_c2;
+    out9[5] = so * ac[0];  // sum s_i w = so * sum s_i e
+    out9[6] = so * ac[1];
+    out9[7] = so * ac[2];
     out9[8] = a_so * (so * (1.0f - so));  // sigmoid_logic.cuh:27-36
     if (entry_grads) {
         float* row = entry_grads + static_cast<size_t>(sorted_orig[i]) * 9;
@@ -250,9 +301,11 @@ int XYZ_CAT(splat_backward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const 
                                                       const float* target, const float* output, long long entries,
                                                       bool deterministic, cudaStream_t st) {
     if (entries <= 0) return 0;
-    const long long blocks = (entries + kTilePixels - 1) / kTilePixels;
+    const int n_tiles = v.tiles_x * v.tiles_y;
+    // upper bound of sum over tiles of ceil(len / 256)
+    const long long blocks = entries / kTilePixels + n_tiles;
     splat_backward_kernel<<<static_cast<unsigned int>(blocks), kTilePixels, 0, st>>>(
-        v, b.records, b.keys_out, b.sorted_gid, b.vals_out, params, grads, target, output, entries,
+        v, b.records, b.tile_ranges, b.chunk_offsets, n_tiles, b.sorted_gid, b.vals_out, params, grads, target, output,
         deterministic ? b.entry_grads : nullptr);
     count_launch();
     return last_error();
