@@ -31,64 +31,87 @@ constexpr float kKappa = -0.5f;
 __device__ __forceinline__ float pair_exp(float arg) { return expf(arg); }
 #endif
 
-__device__ __forceinline__ float xor_sign(float v, unsigned int sign_bit) {
-    return __uint_as_float(__float_as_uint(v) ^ sign_bit);
+// v with the sign of `from` XOR-ed in: one LOP3 (v ^ (from & 0x80000000)), lut 0x78
+__device__ __forceinline__ float xor_sign(float v, float from) {
+    unsigned int r;
+    asm("lop3.b32 %0, %1, %2, 0x80000000, 0x78;" : "=r"(r) : "r"(__float_as_uint(v)), "r"(__float_as_uint(from)));
+    return __uint_as_float(r);
 }
 
-// ---- forward: one CTA per tile, one pixel per thread -------------------------------------------
-// Staged per Gaussian (shared memory, 32 B): {cx, cy, A2, B2} {C2, so*r, so*g, so*b}.
-// Per pair: dx, dy, arg = dx*(A2*dx + B2*dy) + (C2*dy)*dy, e, out_i += (so*c_i) * e   -- ascending Gaussian
-// index, the reference's summation order (gaussian_splatting_kernel.cu:33-62).
-__global__ void __launch_bounds__(kTilePixels)
+// ---- forward: one CTA (64 threads) per tile, four pixels per thread -------------------------------------
+// Staged per Gaussian (shared memory, 32 B): {cx, cy, A2, B2} {C2, so*r, so*g, so*b}.  ncu on the one-pixel-per-
+// thread version: 87 % of the shared-memory pipe (two broadcast LDS.128 = 4 wavefronts per pair per warp), so a
+// thread now owns the pixels (x, y), (x, y+4), (x, y+8), (x, y+12) and reads each Gaussian once for all four:
+//   dx = x - cx ; t0 = (A2 dx) dx ; bdx = B2 dx                          shared by the four pixels
+//   dy = y_k - cy ; arg = dy (C2 dy + bdx) + t0 ; e = exp(arg) ; out_k,i += (so c_i) e
+// = 1 shared-memory wavefront, 1 MUFU and ~8.5 issue slots per pair.  Summation runs in ascending Gaussian
+// index per pixel, the reference's order (gaussian_splatting_kernel.cu:33-62).
+constexpr int kFwdThreads = 64;
+constexpr int kFwdStage = 128;  // Gaussians staged per pass
+constexpr int kFwdRows = kTilePixels / kFwdThreads;  // 4 pixel rows per thread
+
+__global__ void __launch_bounds__(kFwdThreads)
     splat_forward_kernel(SplatView v, const float4* __restrict__ records, const int* __restrict__ sorted_gid,
                          const int2* __restrict__ tile_ranges, const float* __restrict__ target,
                          float* __restrict__ output, float* __restrict__ tile_loss, int tile_y0) {
-    __shared__ float4 s_a[kTilePixels];
-    __shared__ float4 s_b[kTilePixels];
-    __shared__ float s_red[kTilePixels / 32];
+    __shared__ float4 s_a[kFwdStage];
+    __shared__ float4 s_b[kFwdStage];
+    __shared__ float s_red[kFwdThreads / 32];
 
     const int tid = threadIdx.x;
     const int tile_x = blockIdx.x, tile_y = tile_y0 + blockIdx.y;
     const int tile = tile_y * v.tiles_x + tile_x;
     const int pxi = tile_x * kTile + (tid & (kTile - 1));
-    const int pyi = tile_y * kTile + (tid >> 4);
-    const bool active = pxi < v.width && pyi >= v.row_begin && pyi < v.row_end;
-    const float px = static_cast<float>(pxi), py = static_cast<float>(pyi);
+    const int pyi0 = tile_y * kTile + (tid >> 4);  // rows pyi0 + 4 k
+    const float px = static_cast<float>(pxi);
+    float py[kFwdRows];
+#pragma unroll
+    for (int k = 0; k < kFwdRows; ++k) py[k] = static_cast<float>(pyi0 + 4 * k);
 
     const int2 range = tile_ranges[tile];
-    float o0 = 0.f, o1 = 0.f, o2 = 0.f;
-    for (int base = range.x; base < range.y; base += kTilePixels) {
-        const int n = min(kTilePixels, range.y - base);
+    float o[kFwdRows][3];
+#pragma unroll
+    for (int k = 0; k < kFwdRows; ++k) o[k][0] = o[k][1] = o[k][2] = 0.f;
+    for (int base = range.x; base < range.y; base += kFwdStage) {
+        const int n = min(kFwdStage, range.y - base);
         __syncthreads();
-        if (tid < n) {
-            const int g = sorted_gid[base + tid];
+        for (int t = tid; t < n; t += kFwdThreads) {
+            const int g = sorted_gid[base + t];
             const float4 r0 = __ldg(records + 3 * g), r1 = __ldg(records + 3 * g + 1), r2 = __ldg(records + 3 * g + 2);
-            s_a[tid] = make_float4(r0.x, r0.y, kKappa * r0.z, (2.0f * kKappa) * r0.w);
-            s_b[tid] = make_float4(kKappa * r1.x, r1.y * r1.z, r1.y * r1.w, r1.y * r2.x);
+            s_a[t] = make_float4(r0.x, r0.y, kKappa * r0.z, (2.0f * kKappa) * r0.w);
+            s_b[t] = make_float4(kKappa * r1.x, r1.y * r1.z, r1.y * r1.w, r1.y * r2.x);
         }
         __syncthreads();
-#pragma unroll 8
+#pragma unroll 4
         for (int j = 0; j < n; ++j) {
             const float4 a = s_a[j];
             const float4 b = s_b[j];
-            const float dx = px - a.x, dy = py - a.y;
-            const float q = fmaf(a.z, dx, a.w * dy);
-            const float arg = fmaf(dx, q, (b.x * dy) * dy);
-            const float e = pair_exp(arg);
-            o0 = fmaf(b.y, e, o0);
-            o1 = fmaf(b.z, e, o1);
-            o2 = fmaf(b.w, e, o2);
+            const float dx = px - a.x;
+            const float t0 = (a.z * dx) * dx;
+            const float bdx = a.w * dx;
+#pragma unroll
+            for (int k = 0; k < kFwdRows; ++k) {
+                const float dy = py[k] - a.y;
+                const float e = pair_exp(fmaf(dy, fmaf(b.x, dy, bdx), t0));
+                o[k][0] = fmaf(b.y, e, o[k][0]);
+                o[k][1] = fmaf(b.z, e, o[k][1]);
+                o[k][2] = fmaf(b.w, e, o[k][2]);
+            }
         }
     }
     float l = 0.f;
-    if (active) {
-        const size_t p = static_cast<size_t>(pyi) * v.width + pxi;
-        output[3 * p] = o0;
-        output[3 * p + 1] = o1;
-        output[3 * p + 2] = o2;
-        // gaussian_splatting_kernel.cu:68-70
-        l = fabsf(o0 - __ldg(target + 3 * p)) + fabsf(o1 - __ldg(target + 3 * p + 1)) +
-            fabsf(o2 - __ldg(target + 3 * p + 2));
+#pragma unroll
+    for (int k = 0; k < kFwdRows; ++k) {
+        const int pyi = pyi0 + 4 * k;
+        if (pxi < v.width && pyi >= v.row_begin && pyi < v.row_end) {
+            const size_t p = static_cast<size_t>(pyi) * v.width + pxi;
+            output[3 * p] = o[k][0];
+            output[3 * p + 1] = o[k][1];
+            output[3 * p + 2] = o[k][2];
+            // gaussian_splatting_kernel.cu:68-70
+            l += fabsf(o[k][0] - __ldg(target + 3 * p)) + fabsf(o[k][1] - __ldg(target + 3 * p + 1)) +
+                 fabsf(o[k][2] - __ldg(target + 3 * p + 2));
+        }
     }
     l = warp_sum(l);
     if ((tid & 31) == 0) s_red[tid >> 5] = l;
@@ -96,7 +119,7 @@ __global__ void __launch_bounds__(kTilePixels)
     if (tid == 0) {
         float s = 0.f;
 #pragma unroll
-        for (int w = 0; w < kTilePixels / 32; ++w) s += s_red[w];
+        for (int w = 0; w < kFwdThreads / 32; ++w) s += s_red[w];
         tile_loss[tile] = s;
     }
 }
@@ -112,8 +135,8 @@ __global__ void __launch_bounds__(kTilePixels)
 // Everything is LINEAR in the per-pair quantity t = g_w e with per-Gaussian (and per-row: dy) coefficients, so
 // the pixel loop only accumulates   sum s_i e (3),  and per row  sum t, sum t dx, sum t dx^2 ;
 // rows fold into  T0 = sum t, Tx, Ty, Txx, Txy, Tyy ; the conic / center / opacity / covariance chain rule is
-// applied once per entry.  27 instructions per pair instead of the reference's ~200 + 9 atomics.
-// sign(): s_i e and s_i c_i are formed by XOR-ing the sign bit of cd_i into e and c_i.  cd_i == 0 with e != 0
+// applied once per entry.  22 instructions per pair instead of the reference's ~200 + 9 atomics.
+// sign(): s_i e is formed by XOR-ing the sign bit of cd_i into e.  cd_i == 0 with e != 0
 // (an exact cancellation c_i w == tgt_i - out_i) gets +-1 where the reference's l1_norm gives 0: one pair's term,
 // inside the stated kink tolerance; with e == 0 every product is 0 either way.
 template <bool kMasked>
@@ -121,6 +144,7 @@ __device__ __forceinline__ void entry_tile_pass(const float4* __restrict__ s_res
                                                 float cy, float A2, float B2, float C2, float cs0, float cs1,
                                                 float cs2, float c0, float c1, float c2, float (&ac)[3],
                                                 float (&T)[6]) {
+    const float dx0 = px0 - cx;
 #pragma unroll 1
     for (int r = 0; r < kTile; ++r) {
         const float dy = (py0 + static_cast<float>(r)) - cy;
@@ -130,19 +154,18 @@ __device__ __forceinline__ void entry_tile_pass(const float4* __restrict__ s_res
 #pragma unroll
         for (int j = 0; j < kTile; ++j) {
             const float4 rest = s_rest[r * kTile + j];
-            const float dx = (px0 + static_cast<float>(j)) - cx;
+            const float dx = dx0 + static_cast<float>(j);  // (px0 - cx) + j: one rounding more than the forward pass
             const float q = fmaf(A2, dx, u);
             const float arg = fmaf(dx, q, t);
             float e = pair_exp(arg);
             if (kMasked) e *= rest.w;  // 0 for pixels outside the image / row band
-            const unsigned int b0 = __float_as_uint(fmaf(cs0, e, -rest.x)) & 0x80000000u;
-            const unsigned int b1 = __float_as_uint(fmaf(cs1, e, -rest.y)) & 0x80000000u;
-            const unsigned int b2 = __float_as_uint(fmaf(cs2, e, -rest.z)) & 0x80000000u;
-            ac[0] += xor_sign(e, b0);
-            ac[1] += xor_sign(e, b1);
-            ac[2] += xor_sign(e, b2);
-            const float gw = (xor_sign(c0, b0) + xor_sign(c1, b1)) + xor_sign(c2, b2);
-            const float tt = gw * e;
+            const float se0 = xor_sign(e, fmaf(cs0, e, -rest.x));  // s_i e
+            const float se1 = xor_sign(e, fmaf(cs1, e, -rest.y));
+            const float se2 = xor_sign(e, fmaf(cs2, e, -rest.z));
+            ac[0] += se0;
+            ac[1] += se1;
+            ac[2] += se2;
+            const float tt = fmaf(c2, se2, fmaf(c1, se1, c0 * se0));  // g_w e = sum c_i (s_i e)
             const float tx = tt * dx;
             S0 += tt;
             Sx += tx;
@@ -290,7 +313,7 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
     const int ty0 = v.row_begin / kTile, ty1 = (v.row_end + kTile - 1) / kTile;
     if (ty1 <= ty0) return 0;
     dim3 grid(v.tiles_x, ty1 - ty0);
-    splat_forward_kernel<<<grid, kTilePixels, 0, st>>>(v, b.records, b.sorted_gid, b.tile_ranges, target, output,
+    splat_forward_kernel<<<grid, kFwdThreads, 0, st>>>(v, b.records, b.sorted_gid, b.tile_ranges, target, output,
                                                        b.tile_loss, ty0);
     count_launch();
     return last_error();
