@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the driver's benchmark contract for the xyz-autodiff-cuda hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload covproj|lsq|accumulate|splat]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload covproj|splat_c5]
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W        (N > 1)
 
 Headline workload (BASELINE.json configs[2], the largest single-GPU "gradient evals/s" configuration and the
@@ -286,6 +286,90 @@ def reference_cuda(dev, timed, x, tp, tt, W, H, N, ours_splat_ms):
     return res
 
 
+def run_splat_c5(args):
+    """BASELINE configs[4]: N Gaussians replicated, V views (targets) sharded round-robin over the ranks; one
+    iteration = zero_grad + this rank's views (forward + backward each) + NCCL all-reduce of the N x 9 gradient
+    buffer and the loss + Adam on every replica.  Strong scaling: V is fixed, ranks share it.
+    The reference has one target image only; view v = the reference's test image rolled by 64 v pixels in x and
+    37 v in y (our definition)."""
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import oracle_lib as orc
+    import xyz_autodiff_cuda_b200 as x
+    from importlib import import_module
+    par = import_module("xyz_autodiff_cuda_b200.parallel")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = H = 1024
+    N, V = args.gaussians, args.views
+    params, target = orc.splat_c4_scene(N, W, H, 42)
+    tp = torch.from_numpy(params).to(dev)
+    base = torch.from_numpy(target).to(dev).reshape(H, W, 3)
+    mine = par.views_for_rank(V, rank, world)
+    targets = [torch.roll(base, shifts=(37 * v, 64 * v), dims=(0, 1)).reshape(W * H, 3).contiguous() for v in mine]
+    outs = [torch.zeros((W * H, 3), device=dev) for _ in mine]
+    grads = torch.zeros((N, 9), device=dev)
+    loss = torch.zeros(1, device=dev)
+    adam = torch.zeros((N, 18), device=dev)
+    st = torch.cuda.current_stream()
+    ar_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+
+    def step(it):
+        x.zero_gradients(grads)
+        loss.zero_()
+        for t, o in zip(targets, outs):
+            x.launch_gaussian_splatting(tp, grads, t, o, loss, W, H, N)
+        ar_ev[0].record(st)
+        par.allreduce_shared_grads(grads, loss)
+        ar_ev[1].record(st)
+        x.adam_step_individual(tp, grads, adam, 0.1, 0.01, 0.001, 0.02, 0.05, iteration=it + 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    barrier()
+    x.reset_launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record(st)
+    for i in range(args.steps):
+        step(i)
+    b.record(st)
+    barrier()
+    launches = x.launch_count()
+    t = torch.tensor([a.elapsed_time(b), ar_ev[0].elapsed_time(ar_ev[1])], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t[0].item() / args.steps
+    if rank == 0:
+        stats = x.splat_last_stats()
+        print(json.dumps({
+            "metric": "splat fwd+bwd ms/iter", "value": ms, "unit": "ms/iter", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"mini-gaussian-splatting {N} Gaussians, {V} views of 1024x1024 sharded over "
+                                   f"{world} GPUs, NCCL all-reduce of N x 9 grads (BASELINE configs[4])",
+                       "views_per_gpu": len(mine), "allreduce_bytes": N * 36 + 4,
+                       "allreduce_ms_last_iter_max_over_ranks": t[1].item(),
+                       "tile_list_entries_per_view": stats["entries"], "l2": "per-iteration working set "
+                       f"{(stats['entries'] * 16 + N * 160) / 1e6:.0f} MB"},
+            "gpu_launches": int(launches)}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -418,9 +502,15 @@ def main():
     ap.add_argument("--elems", type=int, default=FULL_E, help="elements per GPU (default 2^26, BASELINE configs[2])")
     ap.add_argument("--e2e-elems", type=int, default=1 << 25, help="elements per e2e step (host pinned memory bound)")
     ap.add_argument("--no-also", action="store_true", help="skip the brief timings of the other configs")
+    ap.add_argument("--workload", default="covproj", choices=["covproj", "splat_c5"],
+                    help="covproj = the headline (BASELINE configs[2]); splat_c5 = configs[4], views sharded over the ranks")
+    ap.add_argument("--gaussians", type=int, default=3_000_000, help="splat_c5: number of Gaussians")
+    ap.add_argument("--views", type=int, default=8, help="splat_c5: number of views (targets)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "splat_c5":
+        run_splat_c5(args)
     else:
         run_ours(args)
 

@@ -50,6 +50,8 @@ struct SplatBuffers {  // device scratch of one launch (library-owned)
     int* sorted_gid;          // entries: Gaussian id per sorted entry (fast mode: aliases vals_out)
     int2* tile_ranges;        // tiles: [begin, end)
     int* chunk_offsets;       // tiles + 1: exclusive scan of ceil(list length / 256) = backward CTAs before a tile
+    int4* chunk_info;         // backward CTAs (upper bound entries/256 + tiles): {tile or -1, first entry, list end, 0}
+    float4* rest_tiles;       // tiles x 256: (target - output, active) per pixel, tile-major, written by the forward pass
     float* tile_loss;         // tiles
     float* entry_grads;       // deterministic mode: entries x 9 (indexed by ORIGINAL entry index)
 };

@@ -120,7 +120,8 @@ __global__ void __launch_bounds__(256)
 
 // ---- backward work list: exclusive scan over the tiles of ceil(list length / 256) -------------------------
 __global__ void __launch_bounds__(1024)
-    splat_chunk_scan_kernel(const int2* __restrict__ tile_ranges, int n_tiles, int* __restrict__ chunk_offsets) {
+    splat_chunk_scan_kernel(const int2* __restrict__ tile_ranges, int n_tiles, int* __restrict__ chunk_offsets,
+                            int4* __restrict__ chunk_info) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -153,7 +154,11 @@ __global__ void __launch_bounds__(1024)
         __syncthreads();
         const int carry = s_carry;
         const int before = carry + (warp > 0 ? s_warp[warp - 1] : 0) + (x - c);
-        if (t < n_tiles) chunk_offsets[t] = before;
+        if (t < n_tiles) {
+            chunk_offsets[t] = before;
+            const int2 r = tile_ranges[t];
+            for (int k = 0; k < c; ++k) chunk_info[before + k] = make_int4(t, r.x + k * kTilePixels, r.y, 0);
+        }
         __syncthreads();
         if (tid == 1023) s_carry = carry + s_warp[31];
         __syncthreads();
@@ -234,7 +239,8 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     const size_t o_rec = take(sizeof(float4) * 3 * ng), o_rect = take(sizeof(int4) * ng),
                  o_touched = take(sizeof(unsigned int) * ng), o_offsets = take(sizeof(unsigned long long) * ng),
                  o_ranges = take(sizeof(int2) * n_tiles), o_tloss = take(sizeof(float) * n_tiles),
-                 o_chunks = take(sizeof(int) * (n_tiles + 1));
+                 o_chunks = take(sizeof(int) * (n_tiles + 1)),
+                 o_rest = take(sizeof(float4) * kTilePixels * static_cast<size_t>(n_tiles));
     size_t scan_tmp_bytes = 0;
     cub::DeviceScan::InclusiveSum(nullptr, scan_tmp_bytes, TouchedIter(nullptr, ToU64()),
                                   static_cast<unsigned long long*>(nullptr), ng, st);
@@ -250,6 +256,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     b.tile_ranges = reinterpret_cast<int2*>(base + o_ranges);
     b.tile_loss = reinterpret_cast<float*>(base + o_tloss);
     b.chunk_offsets = reinterpret_cast<int*>(base + o_chunks);
+    b.rest_tiles = reinterpret_cast<float4*>(base + o_rest);
 
     cudaError_t ce = cudaMemsetAsync(b.tile_ranges, 0, sizeof(int2) * n_tiles, st);
     if (ce != cudaSuccess) return static_cast<int>(ce);
@@ -280,7 +287,8 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     size_t soff = 0;
     auto stake = [&soff](size_t bytes) { size_t o = soff; soff += align_up(bytes); return o; };
     const size_t o_kin = stake(4 * ne), o_kout = stake(4 * ne), o_vin = stake(4 * ne), o_vout = stake(4 * ne),
-                 o_gid = stake(deterministic ? 4 * ne : 0), o_eg = stake(deterministic ? 36 * ne : 0);
+                 o_gid = stake(deterministic ? 4 * ne : 0),
+                 o_cinfo = stake(sizeof(int4) * static_cast<size_t>(ne / kTilePixels + n_tiles)), o_eg = stake(deterministic ? 36 * ne : 0);
     size_t sort_tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, static_cast<unsigned int*>(nullptr),
                                     static_cast<unsigned int*>(nullptr), static_cast<unsigned int*>(nullptr),
@@ -296,6 +304,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     // fast mode: the sort payload is the Gaussian id; deterministic mode: payload = entry position, ids derived
     b.sorted_gid = deterministic ? reinterpret_cast<int*>(sbase + o_gid) : reinterpret_cast<int*>(b.vals_out);
     b.entry_grads = deterministic ? reinterpret_cast<float*>(sbase + o_eg) : nullptr;
+    b.chunk_info = reinterpret_cast<int4*>(sbase + o_cinfo);
 
     if (entries > 0) {
         splat_emit_keys_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, v.tiles_x, b.rects, b.touched, b.offsets, b.keys_in,
@@ -307,7 +316,10 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
         count_launch(3);
         splat_ranges_kernel<<<static_cast<unsigned int>((entries + 255) / 256), 256, 0, st>>>(
             entries, b.keys_out, b.vals_out, b.offsets, N, b.tile_ranges, deterministic ? b.sorted_gid : nullptr);
-        splat_chunk_scan_kernel<<<1, 1024, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets);
+        // surplus backward CTAs (the grid is an upper bound) read tile = -1
+        ce = cudaMemsetAsync(b.chunk_info, 0xff, sizeof(int4) * static_cast<size_t>(entries / kTilePixels + n_tiles), st);
+        if (ce != cudaSuccess) return static_cast<int>(ce);
+        splat_chunk_scan_kernel<<<1, 1024, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets, b.chunk_info);
         count_launch(2);
     }
 

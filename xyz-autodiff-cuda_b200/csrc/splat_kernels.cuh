@@ -53,7 +53,8 @@ constexpr int kFwdRows = kTilePixels / kFwdThreads;  // 4 pixel rows per thread
 __global__ void __launch_bounds__(kFwdThreads)
     splat_forward_kernel(SplatView v, const float4* __restrict__ records, const int* __restrict__ sorted_gid,
                          const int2* __restrict__ tile_ranges, const float* __restrict__ target,
-                         float* __restrict__ output, float* __restrict__ tile_loss, int tile_y0) {
+                         float* __restrict__ output, float* __restrict__ tile_loss, float4* __restrict__ rest_tiles,
+                         int tile_y0) {
     __shared__ float4 s_a[kFwdStage];
     __shared__ float4 s_b[kFwdStage];
     __shared__ float s_red[kFwdThreads / 32];
@@ -103,15 +104,22 @@ __global__ void __launch_bounds__(kFwdThreads)
 #pragma unroll
     for (int k = 0; k < kFwdRows; ++k) {
         const int pyi = pyi0 + 4 * k;
+        // rest_sum = target_color - pixel_out (gaussian_splatting_kernel.cu:99-101) for the backward pass, stored
+        // tile-major (4 KB contiguous per tile); .w = 1 for pixels of this launch, 0 outside the image / row band
+        float4 rest = make_float4(0.f, 0.f, 0.f, 0.f);
         if (pxi < v.width && pyi >= v.row_begin && pyi < v.row_end) {
             const size_t p = static_cast<size_t>(pyi) * v.width + pxi;
             output[3 * p] = o[k][0];
             output[3 * p + 1] = o[k][1];
             output[3 * p + 2] = o[k][2];
-            // gaussian_splatting_kernel.cu:68-70
-            l += fabsf(o[k][0] - __ldg(target + 3 * p)) + fabsf(o[k][1] - __ldg(target + 3 * p + 1)) +
-                 fabsf(o[k][2] - __ldg(target + 3 * p + 2));
+            rest.x = __ldg(target + 3 * p) - o[k][0];
+            rest.y = __ldg(target + 3 * p + 1) - o[k][1];
+            rest.z = __ldg(target + 3 * p + 2) - o[k][2];
+            rest.w = 1.f;
+            // gaussian_splatting_kernel.cu:68-70: |out - target|
+            l += fabsf(rest.x) + fabsf(rest.y) + fabsf(rest.z);
         }
+        rest_tiles[static_cast<size_t>(tile) * kTilePixels + (tid + kFwdThreads * k)] = rest;
     }
     l = warp_sum(l);
     if ((tid & 31) == 0) s_red[tid >> 5] = l;
@@ -180,56 +188,25 @@ __device__ __forceinline__ void entry_tile_pass(const float4* __restrict__ s_res
     }
 }
 
-// One CTA = up to 256 consecutive list entries of ONE tile (chunk_offsets: exclusive scan of ceil(len/256) over
-// the tiles; the grid is an upper bound, surplus CTAs exit).
+// One CTA = up to 256 consecutive list entries of ONE tile: chunk_info[c] = {tile, first entry, end of the tile's
+// list, -} written by splat_chunk_scan_kernel; the grid is an upper bound, surplus CTAs see tile = -1 and exit.
 __global__ void __launch_bounds__(kTilePixels)
-    splat_backward_kernel(SplatView v, const float4* __restrict__ records, const int2* __restrict__ tile_ranges,
-                          const int* __restrict__ chunk_offsets, int n_tiles, const int* __restrict__ sorted_gid,
+    splat_backward_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ chunk_info,
+                          const float4* __restrict__ rest_tiles, const int* __restrict__ sorted_gid,
                           const unsigned int* __restrict__ sorted_orig, const xyz_gaussian_params* __restrict__ params,
-                          xyz_gaussian_grads* grads, const float* __restrict__ target,
-                          const float* __restrict__ output, float* __restrict__ entry_grads) {
+                          xyz_gaussian_grads* grads, float* __restrict__ entry_grads) {
     __shared__ float4 s_rest[kTilePixels];  // (tgt - out) per pixel of the tile; .w = 1 active, 0 inactive
-    __shared__ int s_tile;
-    __shared__ int s_all_active;
 
     const int tid = threadIdx.x;
-    if (tid == 0) {
-        // the tile owning chunk blockIdx.x: last t with chunk_offsets[t] <= blockIdx.x
-        const int c = static_cast<int>(blockIdx.x);
-        int lo = 0, hi = n_tiles;  // chunk_offsets has n_tiles + 1 entries
-        if (c >= chunk_offsets[n_tiles]) {
-            lo = -1;
-        } else {
-            while (hi - lo > 1) {
-                const int mid = (lo + hi) >> 1;
-                if (chunk_offsets[mid] <= c) lo = mid; else hi = mid;
-            }
-        }
-        s_tile = lo;
-        s_all_active = 1;
-    }
-    __syncthreads();
-    const int tile = s_tile;
+    const int4 info = __ldg(chunk_info + blockIdx.x);
+    const int tile = info.x;
     if (tile < 0) return;
-    const int2 range = tile_ranges[tile];
-    const int i = range.x + (static_cast<int>(blockIdx.x) - chunk_offsets[tile]) * kTilePixels + tid;
-    const bool valid = i < range.y;
+    const int i = info.y + tid;
+    const bool valid = i < info.z;
     const int tile_x = tile % v.tiles_x, tile_y = tile / v.tiles_x;
-    {
-        const int pxi = tile_x * kTile + (tid & (kTile - 1));
-        const int pyi = tile_y * kTile + (tid >> 4);
-        float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (pxi < v.width && pyi >= v.row_begin && pyi < v.row_end) {
-            const size_t p = static_cast<size_t>(pyi) * v.width + pxi;
-            r.x = __ldg(target + 3 * p) - __ldg(output + 3 * p);  // rest_sum = target_color - pixel_out
-            r.y = __ldg(target + 3 * p + 1) - __ldg(output + 3 * p + 1);
-            r.z = __ldg(target + 3 * p + 2) - __ldg(output + 3 * p + 2);
-            r.w = 1.f;
-        } else {
-            s_all_active = 0;
-        }
-        s_rest[tid] = r;
-    }
+    s_rest[tid] = __ldg(rest_tiles + static_cast<size_t>(tile) * kTilePixels + tid);
+    const bool all_active = (tile_x * kTile + kTile <= v.width) && (tile_y * kTile >= v.row_begin) &&
+                            (tile_y * kTile + kTile <= v.row_end);
 
     float cx = 0.f, cy = 0.f, ia = 0.f, ib = 0.f, ic = 0.f, so = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
     int g = 0;
@@ -248,7 +225,7 @@ __global__ void __launch_bounds__(kTilePixels)
         const float px0 = static_cast<float>(tile_x * kTile), py0 = static_cast<float>(tile_y * kTile);
         const float A2 = kKappa * ia, B2 = (2.0f * kKappa) * ib, C2 = kKappa * ic;
         const float cs0 = so * c0, cs1 = so * c1, cs2 = so * c2;
-        if (s_all_active)
+        if (all_active)
             entry_tile_pass<false>(s_rest, px0, py0, cx, cy, A2, B2, C2, cs0, cs1, cs2, c0, c1, c2, ac, T);
         else
             entry_tile_pass<true>(s_rest, px0, py0, cx, cy, A2, B2, C2, cs0, cs1, cs2, c0, c1, c2, ac, T);
@@ -314,7 +291,7 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
     if (ty1 <= ty0) return 0;
     dim3 grid(v.tiles_x, ty1 - ty0);
     splat_forward_kernel<<<grid, kFwdThreads, 0, st>>>(v, b.records, b.sorted_gid, b.tile_ranges, target, output,
-                                                       b.tile_loss, ty0);
+                                                       b.tile_loss, b.rest_tiles, ty0);
     count_launch();
     return last_error();
 }
@@ -327,8 +304,10 @@ int XYZ_CAT(splat_backward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const 
     const int n_tiles = v.tiles_x * v.tiles_y;
     // upper bound of sum over tiles of ceil(len / 256)
     const long long blocks = entries / kTilePixels + n_tiles;
+    (void)target;
+    (void)output;
     splat_backward_kernel<<<static_cast<unsigned int>(blocks), kTilePixels, 0, st>>>(
-        v, b.records, b.tile_ranges, b.chunk_offsets, n_tiles, b.sorted_gid, b.vals_out, params, grads, target, output,
+        v, b.records, b.chunk_info, b.rest_tiles, b.sorted_gid, b.vals_out, params, grads,
         deterministic ? b.entry_grads : nullptr);
     count_launch();
     return last_error();
