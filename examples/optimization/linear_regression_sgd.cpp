@@ -1,0 +1,182 @@
+// examples/optimization/linear_regression_sgd.cpp -- host driver of the least-squares fit, on libxyz_b200.so.
+//
+// Role of the reference's examples/optimization/linear_regression_sgd.cu main() (:154-243): fit
+//   y = (x1 - a)^2 + b (x2 - c)^2 + d     (true a, b, c, d = 2.5, 1.8, -1.2, 0.7; noise sigma 0.5; :17-28)
+// from (0, 1, 0, 0) by minibatch SGD with an exponentially decaying rate (:137-140).  Per epoch the reference
+// launches select_batch_kernel, clears the four gradients, launches parallel_gradient_computation_kernel and
+// update_parameters_kernel (:185-209); here each of those is one extern "C" call of include/xyz_b200.h, queued on
+// one stream with no host synchronisation inside the epoch loop (the reference synchronises twice per epoch).
+//
+// Differences from the shipped reference main (all switchable back):
+//   * the gradient kernel runs the WHOLE batch (the reference launches <<<1,1>>> on one sample, "debug", :204-205)
+//     and differentiates the squared residual (the graph of the reference's own gradient test,
+//     examples/optimization/tests/test_linear_regression_gradient.cu:52-71).  --reference-loss switches to the
+//     shipped loss.run() on the residual (XYZ_FLAG_RESIDUAL_ONLY); --batch 1 reproduces the one-sample update;
+//   * data comes from std::mt19937(--seed) instead of std::random_device, so runs are reproducible.
+//
+//   linear_regression_sgd [--samples N] [--batch B] [--epochs E] [--lr0 x] [--lr1 x] [--seed s]
+//                         [--reference-loss] [--quiet] [--check tol]
+#include <cuda_runtime.h>
+
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include <xyz_autodiff/util/cuda_unique_ptr.cuh>
+#include <xyz_b200.h>
+
+namespace {
+
+constexpr double kTrue[4] = {2.5, 1.8, -1.2, 0.7};
+
+struct Options {
+    long long samples = 100000;   // TOTAL_SAMPLES
+    long long batch = 256 * 32;   // BATCH_SIZE
+    int epochs = 10000;           // NUM_EPOCHS
+    double lr0 = 1e-4;            // INITIAL_LR
+    double lr1 = 1e-6;            // FINAL_LR = INITIAL_LR / 100
+    double noise = 0.5;           // NOISE_LEVEL
+    unsigned seed = 42;
+    bool reference_loss = false;
+    bool quiet = false;
+    double check = -1.0;          // > 0: exit 1 unless the final total parameter error is below it
+};
+
+Options parse(int argc, char** argv) {
+    Options o;
+    for (int i = 1; i < argc; ++i) {
+        const std::string a = argv[i];
+        auto need = [&](const char* name) -> const char* {
+            if (i + 1 >= argc) {
+                std::fprintf(stderr, "%s needs a value\n", name);
+                std::exit(2);
+            }
+            return argv[++i];
+        };
+        if (a == "--samples") o.samples = std::atoll(need("--samples"));
+        else if (a == "--batch") o.batch = std::atoll(need("--batch"));
+        else if (a == "--epochs") o.epochs = std::atoi(need("--epochs"));
+        else if (a == "--lr0") o.lr0 = std::atof(need("--lr0"));
+        else if (a == "--lr1") o.lr1 = std::atof(need("--lr1"));
+        else if (a == "--seed") o.seed = static_cast<unsigned>(std::atoll(need("--seed")));
+        else if (a == "--check") o.check = std::atof(need("--check"));
+        else if (a == "--reference-loss") o.reference_loss = true;
+        else if (a == "--quiet") o.quiet = true;
+        else {
+            std::fprintf(stderr, "unknown argument %s\n", a.c_str());
+            std::exit(2);
+        }
+    }
+    if (o.samples <= 0 || o.batch <= 0 || o.epochs <= 0 || o.lr0 <= 0 || o.lr1 <= 0) {
+        std::fprintf(stderr, "samples, batch, epochs and learning rates must be positive\n");
+        std::exit(2);
+    }
+    return o;
+}
+
+std::vector<xyz_data_point> generate_data(const Options& o) {
+    std::vector<xyz_data_point> data(static_cast<size_t>(o.samples));
+    std::mt19937 gen(o.seed);
+    std::uniform_real_distribution<double> x_dist(-5.0, 5.0);
+    std::normal_distribution<double> noise(0.0, o.noise);
+    for (auto& p : data) {
+        p.x1 = x_dist(gen);
+        p.x2 = x_dist(gen);
+        const double u = p.x1 - kTrue[0], v = p.x2 - kTrue[2];
+        p.y = u * u + kTrue[1] * v * v + kTrue[3] + noise(gen);
+    }
+    return data;
+}
+
+double total_error(const double* v) {
+    double e = 0.0;
+    for (int i = 0; i < 4; ++i) e += std::fabs(v[i] - kTrue[i]);
+    return e;
+}
+
+void report(int epoch, double lr, const xyz_lsq_parameters& p) {
+    std::printf("Epoch %d: LR=%.6f, grads=[%.6f,%.6f,%.6f,%.6f] - a=%.4f(err:%.4f), b=%.4f(err:%.4f), "
+                "c=%.4f(err:%.4f), d=%.4f(err:%.4f), total_err=%.4f\n",
+                epoch, lr, p.grad[0], p.grad[1], p.grad[2], p.grad[3], p.value[0], std::fabs(p.value[0] - kTrue[0]),
+                p.value[1], std::fabs(p.value[1] - kTrue[1]), p.value[2], std::fabs(p.value[2] - kTrue[2]), p.value[3],
+                std::fabs(p.value[3] - kTrue[3]), total_error(p.value));
+}
+
+#define XYZ_CALL(expr)                                                          \
+    do {                                                                        \
+        const int rc_ = (expr);                                                 \
+        if (rc_ != 0) {                                                         \
+            std::fprintf(stderr, "%s failed with %d\n", #expr, rc_);            \
+            return 1;                                                           \
+        }                                                                       \
+    } while (0)
+
+}  // namespace
+
+int main(int argc, char** argv) {
+    const Options opt = parse(argc, argv);
+    CHECK_CUDA_ERROR(cudaSetDevice(0));
+    std::printf("%s\n", xyz_b200_version());
+
+    const std::vector<xyz_data_point> data = generate_data(opt);
+    std::printf("Generated %lld data points with noise level %.2f\n", opt.samples, opt.noise);
+    std::printf("True parameters: a=%.2f, b=%.2f, c=%.2f, d=%.2f\n", kTrue[0], kTrue[1], kTrue[2], kTrue[3]);
+
+    auto d_data = makeCudaUniqueArray<xyz_data_point>(data.size());
+    auto d_batch = makeCudaUniqueArray<xyz_data_point>(static_cast<size_t>(opt.batch));
+    auto d_params = makeCudaUnique<xyz_lsq_parameters>();
+    cudaStream_t stream;
+    CHECK_CUDA_ERROR(cudaStreamCreate(&stream));
+    CHECK_CUDA_ERROR(cudaMemcpyAsync(d_data.get(), data.data(), data.size() * sizeof(xyz_data_point),
+                                     cudaMemcpyHostToDevice, stream));
+    xyz_lsq_parameters host{};  // a, b, c, d = 0, 1, 0, 0 (reference :171-174)
+    host.value[1] = 1.0;
+    CHECK_CUDA_ERROR(cudaMemcpyAsync(d_params.get(), &host, sizeof(host), cudaMemcpyHostToDevice, stream));
+    if (!opt.quiet) report(0, opt.lr0, host);
+
+    const int flags = opt.reference_loss ? XYZ_FLAG_RESIDUAL_ONLY : 0;
+    const double decay = std::log(opt.lr1 / opt.lr0) / opt.epochs;
+    double* d_grad = d_params.get()->grad;  // device address of the 4 gradients
+    const auto t0 = std::chrono::steady_clock::now();
+    for (int epoch = 0; epoch < opt.epochs; ++epoch) {
+        const double lr = opt.lr0 * std::exp(decay * epoch);
+        XYZ_CALL(xyz_lsq_select_batch(d_data.get(), opt.samples, d_batch.get(), opt.batch, opt.seed,
+                                      static_cast<uint64_t>(epoch), stream));
+        CHECK_CUDA_ERROR(cudaMemsetAsync(d_grad, 0, sizeof(double) * 4, stream));
+        XYZ_CALL(xyz_lsq_grad_f64(d_batch.get(), opt.batch, d_params.get(), nullptr, stream, flags));
+        XYZ_CALL(xyz_lsq_sgd_update_f64(d_params.get(), lr, opt.batch, stream));
+        if ((epoch + 1) % 100 == 0) {  // the only synchronisation point, like the reference's progress print
+            CHECK_CUDA_ERROR(cudaMemcpyAsync(&host, d_params.get(), sizeof(host), cudaMemcpyDeviceToHost, stream));
+            CHECK_CUDA_ERROR(cudaStreamSynchronize(stream));
+            if (!opt.quiet) report(epoch + 1, lr, host);
+            bool bad = false;
+            for (double v : host.value) bad = bad || std::isnan(v);
+            if (bad) {
+                std::printf("ERROR: NaN detected at epoch %d, stopping...\n", epoch + 1);
+                return 1;
+            }
+        }
+    }
+    CHECK_CUDA_ERROR(cudaMemcpyAsync(&host, d_params.get(), sizeof(host), cudaMemcpyDeviceToHost, stream));
+    CHECK_CUDA_ERROR(cudaStreamSynchronize(stream));
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+
+    std::printf("\n=== Final Results ===\n");
+    std::printf("True parameters:  a=%.4f, b=%.4f, c=%.4f, d=%.4f\n", kTrue[0], kTrue[1], kTrue[2], kTrue[3]);
+    std::printf("Final parameters: a=%.4f, b=%.4f, c=%.4f, d=%.4f\n", host.value[0], host.value[1], host.value[2],
+                host.value[3]);
+    std::printf("total_err=%.6f  epochs=%d  batch=%lld  wall=%.3f s  (%.1f us/epoch, %.3g gradient evals/s)\n",
+                total_error(host.value), opt.epochs, opt.batch, secs, 1e6 * secs / opt.epochs,
+                static_cast<double>(opt.epochs) * opt.batch / secs);
+    CHECK_CUDA_ERROR(cudaStreamDestroy(stream));
+    if (opt.check > 0.0 && !(total_error(host.value) < opt.check)) {
+        std::printf("CHECK FAILED: total_err >= %.4f\n", opt.check);
+        return 1;
+    }
+    return 0;
+}
