@@ -223,6 +223,16 @@ def also_workloads(dev, peak_gbs):
                                       "pair_evals_per_s": 2 * stats["pairs_per_pass"] / (ms / 1e3),
                                       "reference_pairs_per_pass": N * W * H,
                                       "iteration": "zero_grad + loss reset + launch (fwd + bwd), fast-math flavour"}
+    def splat_iter_tail():
+        x.zero_gradients(grads)
+        loss.zero_()
+        x.launch_gaussian_splatting(tp, grads, tt, img, loss, W, H, N, x.FLAG_TAIL_CULL)
+
+    ms_tail = timed(splat_iter_tail, reps=5, flush_l2=False)
+    out["c4_splat_100K_1024x1024_tail_cull_opt_in"] = {
+        "ms_per_iter": ms_tail, "tile_list_entries": x.splat_last_stats()["entries"],
+        "note": "XYZ_FLAG_TAIL_CULL: NOT the parity path -- also skips pairs with weight < exp(-28) (bounded error, "
+                "include/xyz_b200.h); the headline c4 number above is the result-preserving default"}
     out["reference_cuda_same_b200"] = reference_cuda(dev, timed, x, tp, tt, W, H, N, ms)
     return out
 

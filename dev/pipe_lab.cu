@@ -72,6 +72,33 @@ __global__ void k_mix1(float* out, float a, float b) {
     for (int i = 0; i < ILP; ++i) s += x[i] + y[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = s;
 }
+
+// NP packed FFMA2 chains + NS scalar FFMA chains per thread: do the scalar ones run on the "lite" FMA pipe beside the packed ones?
+template <int NP, int NS>
+__global__ void k_mixps(float* out, float a, float b) {
+    unsigned long long x[NP > 0 ? NP : 1];
+    float y[NS > 0 ? NS : 1];
+    float2 av = make_float2(a, a), bv = make_float2(b, b);
+    unsigned long long aa = *reinterpret_cast<unsigned long long*>(&av), bb = *reinterpret_cast<unsigned long long*>(&bv);
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { float2 t = make_float2(threadIdx.x * 1e-3f + i, i); x[i] = *reinterpret_cast<unsigned long long*>(&t); }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) y[i] = threadIdx.x * 1e-3f + i;
+    for (int it = 0; it < ITERS; ++it) {
+#pragma unroll
+        for (int i = 0; i < (NP > NS ? NP : NS); ++i) {
+            if (i < NP) x[i] = ffma2(x[i], aa, bb);
+            if (i < NS) asm volatile("fma.rn.f32 %0, %0, %1, %2;" : "+f"(y[i]) : "f"(a), "f"(b));
+        }
+    }
+    float s = 0;
+#pragma unroll
+    for (int i = 0; i < NP; ++i) { float2 t = *reinterpret_cast<float2*>(&x[i]); s += t.x + t.y; }
+#pragma unroll
+    for (int i = 0; i < NS; ++i) s += y[i];
+    out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
 __global__ void k_mufu(float* out, float a) {
     float x[ILP];
 #pragma unroll
@@ -153,6 +180,20 @@ int main() {
     report("LDS.32 broadcast", time_it([&] { k_lds<1><<<blocks, threads>>>(out); }), 1);
     report("LDS.64 broadcast", time_it([&] { k_lds<2><<<blocks, threads>>>(out); }), 1);
     report("LDS.128 broadcast", time_it([&] { k_lds<4><<<blocks, threads>>>(out); }), 1);
+    {
+        auto fm = [&](const char* name, float ms, int np, int ns) {
+            const double groups = double(blocks) * (threads / 32) * ITERS;
+            const double fma_lane_ops = groups * (2.0 * np + ns);
+            printf("%-28s %8.3f ms  %6.2f FMA-warp-equivalents/clk/SM  (%d packed + %d scalar per group)\n", name, ms,
+                   fma_lane_ops / (ms * 1e-3) / sms / (clk * 1e3), np, ns);
+        };
+        fm("mix 8 FFMA2 + 0 FFMA", time_it([&] { k_mixps<8, 0><<<blocks, threads>>>(out, 1.0001f, 0.5f); }), 8, 0);
+        fm("mix 0 FFMA2 + 8 FFMA", time_it([&] { k_mixps<0, 8><<<blocks, threads>>>(out, 1.0001f, 0.5f); }), 0, 8);
+        fm("mix 8 FFMA2 + 4 FFMA", time_it([&] { k_mixps<8, 4><<<blocks, threads>>>(out, 1.0001f, 0.5f); }), 8, 4);
+        fm("mix 8 FFMA2 + 8 FFMA", time_it([&] { k_mixps<8, 8><<<blocks, threads>>>(out, 1.0001f, 0.5f); }), 8, 8);
+        fm("mix 4 FFMA2 + 8 FFMA", time_it([&] { k_mixps<4, 8><<<blocks, threads>>>(out, 1.0001f, 0.5f); }), 4, 8);
+        fm("mix 6 FFMA2 + 6 FFMA", time_it([&] { k_mixps<6, 6><<<blocks, threads>>>(out, 1.0001f, 0.5f); }), 6, 6);
+    }
     CK(cudaDeviceSynchronize());
     return 0;
 }

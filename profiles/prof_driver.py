@@ -1,7 +1,7 @@
 """profiles/prof_driver.py -- launches every hot kernel twice at BASELINE size, for ncu.
 
   ncu --set full --clock-control none --import-source on \
-      -k regex:'covproj_tma|lsq_grad|accumulate_kernel|splat_forward|splat_backward|adam_kernel' -c 24 \
+      -k regex:'covproj_tma|lsq_grad|accumulate|splat_forward|splat_backward|adam_kernel' -c 24 \
       -o gpurun_out/prof_rNN python profiles/prof_driver.py
 """
 import os
@@ -37,10 +37,15 @@ if "lsq" in which:
         x.lsq_grad(data, prm)
     torch.cuda.synchronize()
     del data
+    data = torch.from_numpy(orc.lsq_data(1_000_000, 42)).to(dev)  # BASELINE configs[0] size: 24 MB, launch/latency bound
+    for _ in range(reps):
+        x.lsq_grad(data, prm)
+    torch.cuda.synchronize()
+    del data
 
 if "accumulate" in which:
     n = 1 << 24
-    for dist in ("uniform", "same"):
+    for dist in ("uniform", "zipf", "same"):
         idx, val = orc.accumulate_inputs(n, 1024, dist, 42)
         ti, tv = torch.from_numpy(idx).to(dev), torch.from_numpy(val).to(dev)
         grad = torch.zeros(1024, device=dev)

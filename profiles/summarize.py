@@ -62,11 +62,12 @@ def main():
         rows = list(csv.reader(open(sys.argv[3])))
         h = next(i for i, r in enumerate(rows) if "Kernel Name" in r)
         hdr = rows[h]
-        kn, mv = hdr.index("Kernel Name"), hdr.index("Metric Value")
+        kn, mv, mu = hdr.index("Kernel Name"), hdr.index("Metric Value"), hdr.index("Metric Unit")
+        to_ns = {"ns": 1.0, "us": 1e3, "ms": 1e6, "s": 1e9}
         agg = collections.OrderedDict()
         for r in rows[h + 1:]:
             if len(r) > mv:
-                agg.setdefault(r[kn].split("(")[0][-70:], []).append(float(r[mv].replace(",", "")))
+                agg.setdefault(r[kn].split("(")[0][-70:], []).append(float(r[mv].replace(",", "")) * to_ns.get(r[mu], 1.0))
         tot = sum(sum(v) for v in agg.values())
         out = os.path.join(HERE, f"launches_{tag}_summary.csv")
         with open(out, "w", newline="") as f:

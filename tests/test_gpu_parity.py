@@ -339,6 +339,21 @@ def test_splat_cull_is_result_preserving_and_deterministic():
         assert (np.abs(d0[0] - g0) <= tol).all()
 
 
+def test_splat_tail_cull_stays_inside_the_stated_bound():
+    """XYZ_FLAG_TAIL_CULL (opt-in) drops pairs with weight < exp(-28): the image moves by at most
+    N * exp(-28) * max|sigmoid(opacity) * color| and the result still meets the fp64 tolerances."""
+    W, H, N = 160, 128, 400
+    params, target = orc.splat_scene(N, W, H, seed=21)
+    g0, o0, l0 = run_splat(params, target, W, H, 0)
+    e0 = x.splat_last_stats()["entries"]
+    g1, o1, l1 = run_splat(params, target, W, H, x.FLAG_TAIL_CULL)
+    e1 = x.splat_last_stats()["entries"]
+    assert e1 < e0
+    bound = N * np.exp(-28.0) * np.abs(params[:, 5:8]).max()
+    assert np.abs(o1 - o0).max() <= bound + 1e-12
+    check_splat_against_fp64(params, target, W, H, (g1, o1, l1))
+
+
 def test_splat_tile_binning_is_bit_exact():
     """Integer work: tile rectangles, stably sorted tile lists and per-tile ranges equal the CPU restatement
     computed from the same per-Gaussian records."""

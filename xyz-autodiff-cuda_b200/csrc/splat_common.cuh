@@ -31,6 +31,7 @@ constexpr int kRecFloats = 12;            // {cx, cy, ia, ib, ic, sigmoid(opacit
 //   IEEE expf:                      0.5*d2 > 103.98 (below half the smallest denormal) ; margin -> 104.5
 constexpr float kD2MaxFast = 176.0f;
 constexpr float kD2MaxPrecise = 209.0f;
+constexpr float kD2MaxTail = 56.0f;  // XYZ_FLAG_TAIL_CULL (opt-in, bounded error): weights below exp(-28)
 
 struct SplatView {  // what one launch renders
     int width, height, num_gaussians;

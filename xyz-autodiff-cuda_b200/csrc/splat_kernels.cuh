@@ -147,44 +147,115 @@ __global__ void __launch_bounds__(kFwdThreads)
 // sign(): s_i e is formed by XOR-ing the sign bit of cd_i into e.  cd_i == 0 with e != 0
 // (an exact cancellation c_i w == tgt_i - out_i) gets +-1 where the reference's l1_norm gives 0: one pair's term,
 // inside the stated kink tolerance; with e == 0 every product is 0 either way.
+// Packed fp32 (Blackwell FFMA2 / FADD2 / FMUL2 = PTX fma/add/mul.rn.f32x2): the pixel loop handles the pixels
+// (2p, 2p+1) of a row in the two halves of 64-bit registers, so the ~15 floating-point operations per pixel
+// cost 7.5 issue slots; only the exponential (MUFU) and the sign transfer (LOP3) work on single lanes.
+// Measured on B200 (dev/pipe_lab.cu): FFMA2 issues at half the FFMA rate (same flops) but leaves the other issue
+// slots to the ALU / MUFU pipes -- the scalar version of this loop was issue bound (ncu: 79 % issue active).
+struct F2 {
+    unsigned long long v;
+};
+#if XYZ_SPLAT_IS_FAST
+#define XYZ_F2_FTZ ".ftz"
+#else
+#define XYZ_F2_FTZ ""
+#endif
+__device__ __forceinline__ F2 f2_pack(float lo, float hi) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(F2 a, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+    F2 r;
+    asm("fma.rn" XYZ_F2_FTZ ".f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+    F2 r;
+    asm("mul.rn" XYZ_F2_FTZ ".f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+    F2 r;
+    asm("add.rn" XYZ_F2_FTZ ".f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ float f2_hsum(F2 a) {
+    float lo, hi;
+    f2_unpack(a, lo, hi);
+    return lo + hi;
+}
+
+// Shared-memory layout of the residuals for the packed loop: per pixel pair (2p, 2p+1) two float4
+//   A = {-rest.x[2p], -rest.x[2p+1], -rest.y[2p], -rest.y[2p+1]}   B = {-rest.z[2p], -rest.z[2p+1], m[2p], m[2p+1]}
+// (negated so cd_i = fma(cs_i, e, -rest_i) takes them as the addend; m = 1 active / 0 inactive pixel).
+struct RestPair {
+    float4 A, B;
+};
+
 template <bool kMasked>
-__device__ __forceinline__ void entry_tile_pass(const float4* __restrict__ s_rest, float px0, float py0, float cx,
+__device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_rest, float px0, float py0, float cx,
                                                 float cy, float A2, float B2, float C2, float cs0, float cs1,
                                                 float cs2, float c0, float c1, float c2, float (&ac)[3],
                                                 float (&T)[6]) {
     const float dx0 = px0 - cx;
+    F2 dxs[kTile / 2];  // (px0 - cx) + j: one rounding more than the forward pass
+#pragma unroll
+    for (int p = 0; p < kTile / 2; ++p) dxs[p] = f2_pack(dx0 + static_cast<float>(2 * p), dx0 + static_cast<float>(2 * p + 1));
+    const F2 A2p = f2_pack(A2, A2);
+    const F2 cs0p = f2_pack(cs0, cs0), cs1p = f2_pack(cs1, cs1), cs2p = f2_pack(cs2, cs2);
+    const F2 c0p = f2_pack(c0, c0), c1p = f2_pack(c1, c1), c2p = f2_pack(c2, c2);
 #pragma unroll 1
     for (int r = 0; r < kTile; ++r) {
         const float dy = (py0 + static_cast<float>(r)) - cy;
         const float u = B2 * dy;
         const float t = (C2 * dy) * dy;
-        float S0 = 0.f, Sx = 0.f, Sxx = 0.f;
+        const F2 up = f2_pack(u, u), tp = f2_pack(t, t);
+        F2 acp0 = f2_pack(0.f, 0.f), acp1 = acp0, acp2 = acp0;  // this row's sum s_i e
+        F2 Sx = acp0, Sxx = acp0;
 #pragma unroll
-        for (int j = 0; j < kTile; ++j) {
-            const float4 rest = s_rest[r * kTile + j];
-            const float dx = dx0 + static_cast<float>(j);  // (px0 - cx) + j: one rounding more than the forward pass
-            const float q = fmaf(A2, dx, u);
-            const float arg = fmaf(dx, q, t);
-            float e = pair_exp(arg);
-            if (kMasked) e *= rest.w;  // 0 for pixels outside the image / row band
-            const float se0 = xor_sign(e, fmaf(cs0, e, -rest.x));  // s_i e
-            const float se1 = xor_sign(e, fmaf(cs1, e, -rest.y));
-            const float se2 = xor_sign(e, fmaf(cs2, e, -rest.z));
-            ac[0] += se0;
-            ac[1] += se1;
-            ac[2] += se2;
-            const float tt = fmaf(c2, se2, fmaf(c1, se1, c0 * se0));  // g_w e = sum c_i (s_i e)
-            const float tx = tt * dx;
-            S0 += tt;
-            Sx += tx;
-            Sxx = fmaf(tx, dx, Sxx);
+        for (int p = 0; p < kTile / 2; ++p) {
+            const RestPair rp = s_rest[r * (kTile / 2) + p];
+            const F2 dx = dxs[p];
+            const F2 arg = f2_fma(dx, f2_fma(A2p, dx, up), tp);
+            float a_lo, a_hi;
+            f2_unpack(arg, a_lo, a_hi);
+            float e_lo = pair_exp(a_lo), e_hi = pair_exp(a_hi);
+            if (kMasked) {  // 0 for pixels outside the image / row band
+                e_lo *= rp.B.z;
+                e_hi *= rp.B.w;
+            }
+            const F2 e = f2_pack(e_lo, e_hi);
+            float d_lo, d_hi;
+            f2_unpack(f2_fma(cs0p, e, f2_pack(rp.A.x, rp.A.y)), d_lo, d_hi);  // cd_0 of both pixels
+            const F2 se0 = f2_pack(xor_sign(e_lo, d_lo), xor_sign(e_hi, d_hi));  // s_0 e
+            f2_unpack(f2_fma(cs1p, e, f2_pack(rp.A.z, rp.A.w)), d_lo, d_hi);
+            const F2 se1 = f2_pack(xor_sign(e_lo, d_lo), xor_sign(e_hi, d_hi));
+            f2_unpack(f2_fma(cs2p, e, f2_pack(rp.B.x, rp.B.y)), d_lo, d_hi);
+            const F2 se2 = f2_pack(xor_sign(e_lo, d_lo), xor_sign(e_hi, d_hi));
+            acp0 = f2_add(acp0, se0);
+            acp1 = f2_add(acp1, se1);
+            acp2 = f2_add(acp2, se2);
+            const F2 tt = f2_fma(c2p, se2, f2_fma(c1p, se1, f2_mul(c0p, se0)));  // t = g_w e = sum c_i (s_i e)
+            const F2 tx = f2_mul(tt, dx);
+            Sx = f2_add(Sx, tx);
+            Sxx = f2_fma(tx, dx, Sxx);
         }
-        T[0] += S0;
-        T[1] += Sx;
-        T[2] = fmaf(dy, S0, T[2]);
-        T[3] += Sxx;
-        T[4] = fmaf(dy, Sx, T[4]);
-        T[5] = fmaf(dy * dy, S0, T[5]);
+        // the row's sum of t follows from its sums of s_i e (t is linear in them): no per-pixel accumulator
+        const float r0 = f2_hsum(acp0), r1 = f2_hsum(acp1), r2 = f2_hsum(acp2);
+        ac[0] += r0;
+        ac[1] += r1;
+        ac[2] += r2;
+        const float s0 = fmaf(c2, r2, fmaf(c1, r1, c0 * r0)), sx = f2_hsum(Sx), sxx = f2_hsum(Sxx);
+        T[0] += s0;
+        T[1] += sx;
+        T[2] = fmaf(dy, s0, T[2]);
+        T[3] += sxx;
+        T[4] = fmaf(dy, sx, T[4]);
+        T[5] = fmaf(dy * dy, s0, T[5]);
     }
 }
 
@@ -195,7 +266,7 @@ __global__ void __launch_bounds__(kTilePixels)
                           const float4* __restrict__ rest_tiles, const int* __restrict__ sorted_gid,
                           const unsigned int* __restrict__ sorted_orig, const xyz_gaussian_params* __restrict__ params,
                           xyz_gaussian_grads* grads, float* __restrict__ entry_grads) {
-    __shared__ float4 s_rest[kTilePixels];  // (tgt - out) per pixel of the tile; .w = 1 active, 0 inactive
+    __shared__ RestPair s_rest[kTilePixels / 2];  // -(tgt - out) and the active mask, pixel pairs (see RestPair)
 
     const int tid = threadIdx.x;
     const int4 info = __ldg(chunk_info + blockIdx.x);
@@ -204,7 +275,14 @@ __global__ void __launch_bounds__(kTilePixels)
     const int i = info.y + tid;
     const bool valid = i < info.z;
     const int tile_x = tile % v.tiles_x, tile_y = tile / v.tiles_x;
-    s_rest[tid] = __ldg(rest_tiles + static_cast<size_t>(tile) * kTilePixels + tid);
+    {
+        const float4 rest = __ldg(rest_tiles + static_cast<size_t>(tile) * kTilePixels + tid);
+        float* pair = reinterpret_cast<float*>(&s_rest[tid >> 1]) + (tid & 1);
+        pair[0] = -rest.x;
+        pair[2] = -rest.y;
+        pair[4] = -rest.z;
+        pair[6] = rest.w;
+    }
     const bool all_active = (tile_x * kTile + kTile <= v.width) && (tile_y * kTile >= v.row_begin) &&
                             (tile_y * kTile + kTile <= v.row_end);
 
