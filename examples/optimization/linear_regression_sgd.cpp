@@ -4,8 +4,9 @@
 //   y = (x1 - a)^2 + b (x2 - c)^2 + d     (true a, b, c, d = 2.5, 1.8, -1.2, 0.7; noise sigma 0.5; :17-28)
 // from (0, 1, 0, 0) by minibatch SGD with an exponentially decaying rate (:137-140).  Per epoch the reference
 // launches select_batch_kernel, clears the four gradients, launches parallel_gradient_computation_kernel and
-// update_parameters_kernel (:185-209); here each of those is one extern "C" call of include/xyz_b200.h, queued on
-// one stream with no host synchronisation inside the epoch loop (the reference synchronises twice per epoch).
+// update_parameters_kernel (:185-209); here the whole epoch is ONE extern "C" call (xyz_lsq_sgd_step_f64), or with
+// --four-calls one call per reference kernel; everything is queued on one stream with no host synchronisation
+// inside the epoch loop (the reference synchronises twice per epoch).
 //
 // Differences from the shipped reference main (all switchable back):
 //   * the gradient kernel runs the WHOLE batch (the reference launches <<<1,1>>> on one sample, "debug", :204-205)
@@ -15,7 +16,7 @@
 //   * data comes from std::mt19937(--seed) instead of std::random_device, so runs are reproducible.
 //
 //   linear_regression_sgd [--samples N] [--batch B] [--epochs E] [--lr0 x] [--lr1 x] [--seed s]
-//                         [--reference-loss] [--quiet] [--check tol]
+//                         [--reference-loss] [--four-calls] [--quiet] [--check tol]
 #include <cuda_runtime.h>
 
 #include <chrono>
@@ -43,6 +44,7 @@ struct Options {
     double noise = 0.5;           // NOISE_LEVEL
     unsigned seed = 42;
     bool reference_loss = false;
+    bool four_calls = false;      // --four-calls: the reference's epoch as four launches instead of the fused one
     bool quiet = false;
     double check = -1.0;          // > 0: exit 1 unless the final total parameter error is below it
 };
@@ -66,6 +68,7 @@ Options parse(int argc, char** argv) {
         else if (a == "--seed") o.seed = static_cast<unsigned>(std::atoll(need("--seed")));
         else if (a == "--check") o.check = std::atof(need("--check"));
         else if (a == "--reference-loss") o.reference_loss = true;
+        else if (a == "--four-calls") o.four_calls = true;
         else if (a == "--quiet") o.quiet = true;
         else {
             std::fprintf(stderr, "unknown argument %s\n", a.c_str());
@@ -145,11 +148,16 @@ int main(int argc, char** argv) {
     const auto t0 = std::chrono::steady_clock::now();
     for (int epoch = 0; epoch < opt.epochs; ++epoch) {
         const double lr = opt.lr0 * std::exp(decay * epoch);
-        XYZ_CALL(xyz_lsq_select_batch(d_data.get(), opt.samples, d_batch.get(), opt.batch, opt.seed,
-                                      static_cast<uint64_t>(epoch), stream));
-        CHECK_CUDA_ERROR(cudaMemsetAsync(d_grad, 0, sizeof(double) * 4, stream));
-        XYZ_CALL(xyz_lsq_grad_f64(d_batch.get(), opt.batch, d_params.get(), nullptr, stream, flags));
-        XYZ_CALL(xyz_lsq_sgd_update_f64(d_params.get(), lr, opt.batch, stream));
+        if (opt.four_calls) {  // the reference's epoch body, call for call (:185-209)
+            XYZ_CALL(xyz_lsq_select_batch(d_data.get(), opt.samples, d_batch.get(), opt.batch, opt.seed,
+                                          static_cast<uint64_t>(epoch), stream));
+            CHECK_CUDA_ERROR(cudaMemsetAsync(d_grad, 0, sizeof(double) * 4, stream));
+            XYZ_CALL(xyz_lsq_grad_f64(d_batch.get(), opt.batch, d_params.get(), nullptr, stream, flags));
+            XYZ_CALL(xyz_lsq_sgd_update_f64(d_params.get(), lr, opt.batch, stream));
+        } else {  // the same epoch in one launch
+            XYZ_CALL(xyz_lsq_sgd_step_f64(d_data.get(), opt.samples, d_params.get(), opt.batch, opt.seed,
+                                          static_cast<uint64_t>(epoch), lr, nullptr, stream, flags));
+        }
         if ((epoch + 1) % 100 == 0) {  // the only synchronisation point, like the reference's progress print
             CHECK_CUDA_ERROR(cudaMemcpyAsync(&host, d_params.get(), sizeof(host), cudaMemcpyDeviceToHost, stream));
             CHECK_CUDA_ERROR(cudaStreamSynchronize(stream));

@@ -115,6 +115,15 @@ XYZ_API int xyz_lsq_sgd_update_f64(xyz_lsq_parameters* params, double learning_r
 XYZ_API int xyz_lsq_select_batch(const xyz_data_point* data, long long n_total, xyz_data_point* batch,
                          long long batch_size, uint64_t seed, uint64_t epoch, void* stream);
 
+/* One whole SGD epoch of the reference driver (linear_regression_sgd.cu:185-209: select_batch_kernel, cudaMemset of
+ * the gradients, parallel_gradient_computation_kernel, update_parameters_kernel) in ONE launch: sample i of the
+ * batch is data[hash(seed, epoch, i) mod n_total] (the sampling of xyz_lsq_select_batch), params->grad is
+ * OVERWRITTEN with the batch gradient, then value -= learning_rate * grad / batch_size.  loss_sum (optional)
+ * receives += the batch loss.  Deterministic.  Flags: XYZ_FLAG_RESIDUAL_ONLY.                        */
+XYZ_API int xyz_lsq_sgd_step_f64(const xyz_data_point* data, long long n_total, xyz_lsq_parameters* params,
+                         long long batch_size, uint64_t seed, uint64_t epoch, double learning_rate,
+                         double* loss_sum, void* stream, int flags);
+
 /* ---- C2: accumulation of per-element gradients into K shared parameters (fp32) ---------------
  * Replaces the VariableRef::add_grad pattern (include/xyz_autodiff/variable.cuh:48-50) as
  * exercised by tests/test_parallel_gradient_accumulation.cu:25-49: grad[idx[i]] += val[i].   */

@@ -60,6 +60,10 @@ def test_lsq_driver_converges_to_the_true_parameters():
     m = re.search(r"Final parameters: a=([-0-9.]+), b=([-0-9.]+), c=([-0-9.]+), d=([-0-9.]+)", final)
     a, b, c, d = (float(v) for v in m.groups())
     assert abs(a - 2.5) < 0.05 and abs(b - 1.8) < 0.05 and abs(c + 1.2) < 0.05 and abs(d - 0.7) < 0.55
+    # the four-launch epoch gives the same fit (same sampling, sums reassociated)
+    r4 = run([LSQ, "--epochs", "10000", "--quiet", "--four-calls"])
+    m4 = re.search(r"Final parameters: a=([-0-9.]+), b=([-0-9.]+), c=([-0-9.]+), d=([-0-9.]+)", r4.stdout)
+    assert r4.returncode == 0 and all(abs(float(u) - v) < 2e-4 for u, v in zip(m4.groups(), (a, b, c, d)))
     # the shipped reference update (one sample, residual loss) also runs through the same entry points
     r = run([LSQ, "--epochs", "500", "--batch", "1", "--reference-loss", "--quiet"])
     assert r.returncode == 0, r.stdout[-2000:]

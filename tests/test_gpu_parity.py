@@ -183,6 +183,37 @@ def test_lsq_sgd_update_and_select_batch():
     assert np.array_equal(batch.cpu().numpy(), orc.lsq_select_batch(data, 8192, 12345, 7))  # index work: bit-exact
 
 
+def test_lsq_fused_sgd_step_equals_the_four_call_epoch():
+    """xyz_lsq_sgd_step_f64 == select_batch + clear + lsq_grad + sgd_update (the reference's epoch body,
+    linear_regression_sgd.cu:185-209), same sampling; sums differ only by fp64 reassociation."""
+    data = dev(orc.lsq_data(100_000, seed=3))
+    for flags in (0, x.FLAG_RESIDUAL_ONLY):
+        pa = torch.zeros(8, dtype=torch.float64, device=DEV)
+        pa[1] = 1.0
+        pb = pa.clone()
+        batch = torch.empty((8192, 3), dtype=torch.float64, device=DEV)
+        la = torch.zeros(1, dtype=torch.float64, device=DEV)
+        lb = torch.zeros(1, dtype=torch.float64, device=DEV)
+        for epoch in range(5):
+            x.lsq_select_batch(data, batch, 42, epoch)
+            pa[4:] = 0.0
+            x.lsq_grad(batch, pa, la, flags)
+            x.lsq_sgd_update(pa, 1e-4, 8192)
+            x.lsq_sgd_step(data, pb, 8192, 42, epoch, 1e-4, lb, flags)
+            torch.cuda.synchronize()
+            a, b = pa.cpu().numpy(), pb.cpu().numpy()
+            assert np.allclose(a[4:], b[4:], rtol=1e-12, atol=1e-9), (epoch, a, b)
+            assert np.allclose(a[:4], b[:4], rtol=1e-12, atol=1e-14)
+        assert abs(la.item() - lb.item()) <= 1e-12 * abs(la.item())
+        # deterministic: a second run from the same state is bit-identical
+        pc = torch.zeros(8, dtype=torch.float64, device=DEV)
+        pc[1] = 1.0
+        for epoch in range(5):
+            x.lsq_sgd_step(data, pc, 8192, 42, epoch, 1e-4, None, flags)
+        torch.cuda.synchronize()
+        assert torch.equal(pc, pb)
+
+
 # ---------------------------------------------------------------------------------------------------
 # C2 accumulation
 # ---------------------------------------------------------------------------------------------------

@@ -34,7 +34,7 @@ GAUSSIAN_FLOATS = 9   # center[2] scale[2] rotation[1] color[3] opacity[1]
 ADAM_FLOATS = 18
 EXPORTS = [
     "xyz_b200_version", "xyz_b200_shutdown", "xyz_b200_launch_count", "xyz_b200_reset_launch_count",
-    "xyz_lsq_grad_f64", "xyz_lsq_sgd_update_f64", "xyz_lsq_select_batch",
+    "xyz_lsq_grad_f64", "xyz_lsq_sgd_update_f64", "xyz_lsq_select_batch", "xyz_lsq_sgd_step_f64",
     "xyz_accumulate_f32", "xyz_accumulate_f64", "xyz_covproj_fwd_bwd_f32",
     "xyz_launch_gaussian_splatting", "xyz_launch_gaussian_splatting_rows", "xyz_splat_last_stats",
     "xyz_splat_debug_binning", "xyz_zero_gradients", "xyz_adam_step_individual", "xyz_adam_step",
@@ -59,6 +59,7 @@ def lib() -> ctypes.CDLL:
         L.xyz_lsq_grad_f64.argtypes = [_vp, _ll, _vp, _vp, _vp, _i]
         L.xyz_lsq_sgd_update_f64.argtypes = [_vp, ctypes.c_double, _ll, _vp]
         L.xyz_lsq_select_batch.argtypes = [_vp, _ll, _vp, _ll, ctypes.c_uint64, ctypes.c_uint64, _vp]
+        L.xyz_lsq_sgd_step_f64.argtypes = [_vp, _ll, _vp, _ll, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_double, _vp, _vp, _i]
         L.xyz_accumulate_f32.argtypes = [_vp, _vp, _ll, _vp, _i, _vp, _i]
         L.xyz_accumulate_f64.argtypes = [_vp, _vp, _ll, _vp, _i, _vp, _i]
         L.xyz_covproj_fwd_bwd_f32.argtypes = [_vp] * 8 + [_ll, _vp, _i]
@@ -131,6 +132,16 @@ def lsq_select_batch(data: torch.Tensor, batch: torch.Tensor, seed: int, epoch: 
     _check(lib().xyz_lsq_select_batch(_dev(data, torch.float64, "data"), data.shape[0],
                                       _dev(batch, torch.float64, "batch"), batch.shape[0], seed, epoch,
                                       _stream(stream)), "xyz_lsq_select_batch")
+
+
+def lsq_sgd_step(data: torch.Tensor, params: torch.Tensor, batch: int, seed: int, epoch: int, lr: float,
+                 loss_sum: Optional[torch.Tensor] = None, flags: int = 0, stream=None) -> None:
+    """One SGD epoch in one launch: sample the batch (same hash as lsq_select_batch), params.grad = batch gradient,
+    params.value -= lr * grad / batch."""
+    _check(lib().xyz_lsq_sgd_step_f64(_dev(data, torch.float64, "data"), data.shape[0],
+                                      _dev(params, torch.float64, "params"), batch, seed, epoch, lr,
+                                      _dev(loss_sum, torch.float64, "loss_sum") if loss_sum is not None else None,
+                                      _stream(stream), flags), "xyz_lsq_sgd_step_f64")
 
 
 # ---- C2 ------------------------------------------------------------------------------------------

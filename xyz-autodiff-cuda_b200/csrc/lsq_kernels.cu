@@ -49,6 +49,13 @@ __device__ __forceinline__ void lsq_point(double x1, double x2, double yt, doubl
     acc.v[4] += residual_only ? r : r * r;
 }
 
+__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
+    x += 0x9E3779B97F4A7C15ull;
+    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
+    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
+    return x ^ (x >> 31);
+}
+
 // partials: [gridDim.x][kAcc]; ticket: one unsigned int, zero before the launch, reset by the last CTA.
 template <bool kTma>
 __global__ void __launch_bounds__(kThreads, kCtasPerSM)
@@ -164,13 +171,6 @@ __global__ void lsq_sgd_update_kernel(xyz_lsq_parameters* p, double lr, double b
     if (i < 4) p->value[i] -= lr * p->grad[i] / batch;
 }
 
-__device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
-    x += 0x9E3779B97F4A7C15ull;
-    x = (x ^ (x >> 30)) * 0xBF58476D1CE4E5B9ull;
-    x = (x ^ (x >> 27)) * 0x94D049BB133111EBull;
-    return x ^ (x >> 31);
-}
-
 __global__ void lsq_select_batch_kernel(const xyz_data_point* __restrict__ data, long long n_total,
                                         xyz_data_point* __restrict__ batch, long long batch_size, uint64_t seed,
                                         uint64_t epoch) {
@@ -178,6 +178,81 @@ __global__ void lsq_select_batch_kernel(const xyz_data_point* __restrict__ data,
     if (i >= batch_size) return;
     const uint64_t h = splitmix64(splitmix64(seed ^ (epoch * 0xD1B54A32D192ED03ull)) + static_cast<uint64_t>(i));
     batch[i] = data[h % static_cast<uint64_t>(n_total)];
+}
+
+
+// ---- one SGD epoch in ONE launch ---------------------------------------------------------------------------
+// The reference's epoch body (linear_regression_sgd.cu:185-209) is four operations on a 196 KB batch: gather,
+// clear the gradients, gradient kernel, parameter update -- launch bound.  Here thread i of the batch gathers
+// its own sample straight from the (L2-resident) data set with the same counter-based hash as
+// lsq_select_batch_kernel, runs the graph, the CTA reduces as above, and the last CTA to finish adds the rows in
+// CTA order, STORES the batch gradient (what cudaMemset + accumulation leaves behind) and applies
+// value -= lr * grad / batch.  Deterministic; identical sampling to xyz_lsq_select_batch.
+__global__ void __launch_bounds__(kThreads)
+    lsq_sgd_step_kernel(const xyz_data_point* __restrict__ data, long long n_total, xyz_lsq_parameters* params,
+                        long long batch_size, uint64_t seed, uint64_t epoch, double lr, double* loss_sum,
+                        double* partials, unsigned int* ticket, int residual_only) {
+    __shared__ double red[kThreads / 32][kAcc];
+    __shared__ int is_last;
+    const int tid = threadIdx.x;
+    const double a = params->value[0], b = params->value[1], c = params->value[2], d = params->value[3];
+    LsqAcc acc;
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc.v[k] = 0.0;
+    const uint64_t base = splitmix64(seed ^ (epoch * 0xD1B54A32D192ED03ull));
+    for (long long i = blockIdx.x * static_cast<long long>(kThreads) + tid; i < batch_size;
+         i += static_cast<long long>(gridDim.x) * kThreads) {
+        const uint64_t h = splitmix64(base + static_cast<uint64_t>(i));
+        const double* p = reinterpret_cast<const double*>(data + h % static_cast<uint64_t>(n_total));
+        lsq_point(__ldg(p), __ldg(p + 1), __ldg(p + 2), a, b, c, d, residual_only != 0, acc);
+    }
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) acc.v[k] = warp_sum(acc.v[k]);
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) red[tid >> 5][k] = acc.v[k];
+    }
+    __syncthreads();
+    if (tid < kAcc) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) s += red[w][tid];
+        partials[static_cast<size_t>(blockIdx.x) * kAcc + tid] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    double s[kAcc];
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) s[k] = 0.0;
+    for (unsigned int r = tid; r < gridDim.x; r += kThreads) {
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) s[k] += __ldcg(partials + static_cast<size_t>(r) * kAcc + k);
+    }
+#pragma unroll
+    for (int k = 0; k < kAcc; ++k) s[k] = warp_sum(s[k]);
+    __syncthreads();
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) red[tid >> 5][k] = s[k];
+    }
+    __syncthreads();
+    if (tid < kAcc) {
+        double t = 0.0;
+#pragma unroll
+        for (int w = 0; w < kThreads / 32; ++w) t += red[w][tid];
+        if (tid < 4) {
+            params->grad[tid] = t;
+            // update_parameters_kernel, linear_regression_sgd.cu:126-134 (every other CTA has long read `value`)
+            params->value[tid] -= lr * t / static_cast<double>(batch_size);
+        } else if (loss_sum) {
+            *loss_sum += t;
+        }
+    }
+    if (tid == 0) *ticket = 0u;
 }
 
 }  // namespace
@@ -233,6 +308,26 @@ extern "C" int xyz_lsq_select_batch(const xyz_data_point* data, long long n_tota
     const int grid = static_cast<int>((batch_size + 255) / 256);
     lsq_select_batch_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(data, n_total, batch, batch_size, seed,
                                                                                   epoch);
+    count_launch();
+    return last_error();
+}
+
+extern "C" int xyz_lsq_sgd_step_f64(const xyz_data_point* data, long long n_total, xyz_lsq_parameters* params,
+                                    long long batch_size, uint64_t seed, uint64_t epoch, double learning_rate,
+                                    double* loss_sum, void* stream, int flags) {
+    using namespace xyzb;
+    if (!data || !params || n_total <= 0 || batch_size <= 0) return XYZ_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const long long max_ctas = static_cast<long long>(sm_count()) * kCtasPerSM;
+    const long long want = (batch_size + kThreads - 1) / kThreads;
+    const int grid = static_cast<int>(want < max_ctas ? want : max_ctas);
+    void* scratch = nullptr;
+    int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(max_ctas) * kAcc * sizeof(double), &scratch);
+    if (err) return err;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
+    double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+    lsq_sgd_step_kernel<<<grid, kThreads, 0, st>>>(data, n_total, params, batch_size, seed, epoch, learning_rate, loss_sum,
+                                                    partials, ticket, (flags & XYZ_FLAG_RESIDUAL_ONLY) ? 1 : 0);
     count_launch();
     return last_error();
 }
