@@ -124,6 +124,32 @@ XYZ_API int xyz_lsq_sgd_step_f64(const xyz_data_point* data, long long n_total, 
                          long long batch_size, uint64_t seed, uint64_t epoch, double learning_rate,
                          double* loss_sum, void* stream, int flags);
 
+/* ---- fused reduce + all-reduce over NVLink peer memory (one process per GPU, one box) -----------------------
+ * The reference is single-GPU.  When the elements of C1 are sharded over the GPUs of an NVSwitch box the only
+ * exchange is the sum of the 4 shared-parameter gradients (+ loss); xyz_lsq_grad_f64_allreduce does it inside the
+ * gradient kernel: its last CTA stores the partial row into every rank's MAILBOX (device memory exported with CUDA
+ * IPC), publishes a sequence number with st.release.sys, waits for all ranks and adds the rows in rank order --
+ * bit-identical on every rank, no NCCL call, no second launch.
+ *   setup (once):  xyz_peer_mailbox_create -> exchange the 64-byte handles by any host channel ->
+ *                  xyz_peer_mailbox_open for every other rank -> fill xyz_peer_group (mailbox[rank] = own pointer)
+ *   per call:      seq must be 1, 2, 3, ... identically on every rank (two calls may be in flight).            */
+#define XYZ_PEER_MAX_WORLD 8
+#define XYZ_PEER_SLOT_DOUBLES 8
+typedef struct xyz_peer_group {
+    void* mailbox[XYZ_PEER_MAX_WORLD]; /* device pointers, index = rank; entries >= world are ignored */
+    int rank;
+    int world;
+} xyz_peer_group;
+XYZ_API size_t xyz_peer_mailbox_bytes(void);
+XYZ_API int xyz_peer_mailbox_create(void** local_ptr, unsigned char ipc_handle_out[64]);
+XYZ_API int xyz_peer_mailbox_open(const unsigned char ipc_handle[64], void** peer_ptr);
+XYZ_API int xyz_peer_mailbox_close(void* peer_ptr);
+XYZ_API int xyz_peer_mailbox_destroy(void* local_ptr);
+/* xyz_lsq_grad_f64 on this rank's points + the all-reduce: params->grad += sum over ALL ranks, *loss_sum likewise. */
+XYZ_API int xyz_lsq_grad_f64_allreduce(const xyz_data_point* data, long long n_points, xyz_lsq_parameters* params,
+                               double* loss_sum, const xyz_peer_group* group, unsigned long long seq,
+                               void* stream, int flags);
+
 /* ---- C2: accumulation of per-element gradients into K shared parameters (fp32) ---------------
  * Replaces the VariableRef::add_grad pattern (include/xyz_autodiff/variable.cuh:48-50) as
  * exercised by tests/test_parallel_gradient_accumulation.cu:25-49: grad[idx[i]] += val[i].   */

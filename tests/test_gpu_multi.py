@@ -41,6 +41,47 @@ full_g, full_l = orc.lsq_grad(data, vals)
 assert np.allclose(g.cpu().numpy(), full_g, rtol=1e-10), (g, full_g)
 assert abs(loss.item() - full_l) <= 1e-10 * full_l
 
+# C1 again with the exchange INSIDE the kernel (peer mailboxes over NVLink, no NCCL call): bit-identical on all ranks
+pg = par.make_peer_group(x)
+ref_bits = None
+for it in range(6):   # several calls: sequence numbers, both mailbox parities
+    prm2 = torch.zeros(8, dtype=torch.float64, device=dev); prm2[:4] = torch.tensor(vals, dtype=torch.float64)
+    loss2 = torch.zeros(1, dtype=torch.float64, device=dev)
+    x.lsq_grad_allreduce(D(data[b:e]), prm2, pg, loss2)
+    torch.cuda.synchronize()
+    g2 = prm2[4:].clone()
+    assert np.allclose(g2.cpu().numpy(), full_g, rtol=1e-10), (it, g2, full_g)
+    assert abs(loss2.item() - full_l) <= 1e-10 * full_l
+    same = g2.clone(); dist.broadcast(same, 0)
+    assert torch.equal(same, g2), "ranks disagree bitwise"
+    if ref_bits is None: ref_bits = g2.clone()
+    assert torch.equal(ref_bits, g2), "run-to-run bits differ"
+# timing, informational (rank 0 prints): kernel + NCCL all-reduce of the 5 sums vs. the fused kernel
+dd = D(data[b:e])
+def timed(fn, n=200):
+    for _ in range(20): fn()
+    torch.cuda.synchronize(); dist.barrier()
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n): fn()
+    b_.record(); torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b_) / n], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item() * 1e3
+buf = torch.zeros(8, dtype=torch.float64, device=dev)
+def nccl_path():
+    x.lsq_grad(dd, buf, None)
+    dist.all_reduce(buf[4:])
+def fused_path():
+    x.lsq_grad_allreduce(dd, buf, pg, None)
+t_nccl, t_fused = timed(nccl_path), timed(fused_path)
+if rank == 0:
+    print(f"TIMING lsq 1M points over {world} GPUs: kernel + NCCL all-reduce {t_nccl:.1f} us/iter, fused peer-memory kernel {t_fused:.1f} us/iter")
+# a rank with no points still takes part
+x.lsq_grad_allreduce(D(data[b:e]) if rank else torch.empty((0, 3), dtype=torch.float64, device=dev), prm2, pg, None)
+torch.cuda.synchronize()
+dist.barrier()
+pg.close()
+
 # C2: K = 1024 fp32 accumulators
 idx, val = orc.accumulate_inputs(1 << 21, 1024, "zipf", seed=2)
 b, e = par.shard_range(idx.size, rank, world)
@@ -108,3 +149,6 @@ def test_sharded_paths_match_single_gpu_and_oracle_over_nccl():
                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=600)
         assert res.returncode == 0, res.stdout[-4000:]
         assert res.stdout.count("ok") >= n
+        for line in res.stdout.splitlines():
+            if line.startswith("TIMING"):
+                print(line)

@@ -35,6 +35,8 @@ ADAM_FLOATS = 18
 EXPORTS = [
     "xyz_b200_version", "xyz_b200_shutdown", "xyz_b200_launch_count", "xyz_b200_reset_launch_count",
     "xyz_lsq_grad_f64", "xyz_lsq_sgd_update_f64", "xyz_lsq_select_batch", "xyz_lsq_sgd_step_f64",
+    "xyz_peer_mailbox_bytes", "xyz_peer_mailbox_create", "xyz_peer_mailbox_open", "xyz_peer_mailbox_close",
+    "xyz_peer_mailbox_destroy", "xyz_lsq_grad_f64_allreduce",
     "xyz_accumulate_f32", "xyz_accumulate_f64", "xyz_covproj_fwd_bwd_f32",
     "xyz_launch_gaussian_splatting", "xyz_launch_gaussian_splatting_rows", "xyz_splat_last_stats",
     "xyz_splat_debug_binning", "xyz_zero_gradients", "xyz_adam_step_individual", "xyz_adam_step",
@@ -42,6 +44,13 @@ EXPORTS = [
 
 _lib = None
 _vp, _ll, _i = ctypes.c_void_p, ctypes.c_longlong, ctypes.c_int
+PEER_MAX_WORLD = 8
+
+
+class PeerGroupStruct(ctypes.Structure):
+    """xyz_peer_group (include/xyz_b200.h)."""
+    _fields_ = [("mailbox", ctypes.c_void_p * PEER_MAX_WORLD), ("rank", ctypes.c_int), ("world", ctypes.c_int)]
+
 
 
 def lib() -> ctypes.CDLL:
@@ -60,6 +69,13 @@ def lib() -> ctypes.CDLL:
         L.xyz_lsq_sgd_update_f64.argtypes = [_vp, ctypes.c_double, _ll, _vp]
         L.xyz_lsq_select_batch.argtypes = [_vp, _ll, _vp, _ll, ctypes.c_uint64, ctypes.c_uint64, _vp]
         L.xyz_lsq_sgd_step_f64.argtypes = [_vp, _ll, _vp, _ll, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_double, _vp, _vp, _i]
+        L.xyz_peer_mailbox_bytes.restype = ctypes.c_size_t
+        L.xyz_peer_mailbox_create.argtypes = [ctypes.POINTER(_vp), ctypes.c_char_p]
+        L.xyz_peer_mailbox_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(_vp)]
+        L.xyz_peer_mailbox_close.argtypes = [_vp]
+        L.xyz_peer_mailbox_destroy.argtypes = [_vp]
+        L.xyz_lsq_grad_f64_allreduce.argtypes = [_vp, _ll, _vp, _vp, ctypes.POINTER(PeerGroupStruct), ctypes.c_ulonglong,
+                                                 _vp, _i]
         L.xyz_accumulate_f32.argtypes = [_vp, _vp, _ll, _vp, _i, _vp, _i]
         L.xyz_accumulate_f64.argtypes = [_vp, _vp, _ll, _vp, _i, _vp, _i]
         L.xyz_covproj_fwd_bwd_f32.argtypes = [_vp] * 8 + [_ll, _vp, _i]
@@ -121,6 +137,59 @@ def lsq_grad(data: torch.Tensor, params: torch.Tensor, loss_sum: Optional[torch.
     _check(lib().xyz_lsq_grad_f64(_dev(data, torch.float64, "data"), n, _dev(params, torch.float64, "params"),
                                   _dev(loss_sum, torch.float64, "loss_sum") if loss_sum is not None else None,
                                   _stream(stream), flags), "xyz_lsq_grad_f64")
+
+
+class PeerGroup:
+    """This rank's mailbox + the opened mailboxes of the other ranks of one NVSwitch box (xyz_peer_* in
+    include/xyz_b200.h).  `exchange(handle_bytes) -> list of every rank's handle` is the host channel (e.g. an
+    all-gather over torch.distributed); the kernels themselves talk over NVLink peer memory only."""
+
+    def __init__(self, rank: int, world: int, exchange):
+        if not 1 <= world <= PEER_MAX_WORLD:
+            raise ValueError("world must be 1..8")
+        L = lib()
+        self.rank, self.world, self.seq = rank, world, 0
+        self._local = _vp()
+        handle = ctypes.create_string_buffer(64)
+        _check(L.xyz_peer_mailbox_create(ctypes.byref(self._local), handle), "xyz_peer_mailbox_create")
+        handles = exchange(handle.raw)
+        self.struct = PeerGroupStruct()
+        self.struct.rank, self.struct.world = rank, world
+        self._opened = []
+        for r in range(world):
+            if r == rank:
+                self.struct.mailbox[r] = self._local.value
+            else:
+                ptr = _vp()
+                _check(L.xyz_peer_mailbox_open(ctypes.create_string_buffer(handles[r], 64), ctypes.byref(ptr)),
+                       "xyz_peer_mailbox_open")
+                self._opened.append(ptr)
+                self.struct.mailbox[r] = ptr.value
+
+    def next_seq(self) -> int:
+        self.seq += 1
+        return self.seq
+
+    def close(self) -> None:
+        L = lib()
+        for ptr in self._opened:
+            L.xyz_peer_mailbox_close(ptr)
+        self._opened = []
+        if self._local:
+            L.xyz_peer_mailbox_destroy(self._local)
+            self._local = _vp()
+
+
+def lsq_grad_allreduce(data: torch.Tensor, params: torch.Tensor, group: PeerGroup,
+                       loss_sum: Optional[torch.Tensor] = None, flags: int = 0, stream=None) -> None:
+    """lsq_grad on this rank's points, with the sum over all ranks of the 4 gradients (+ loss) done inside the
+    kernel over NVLink peer memory: params.grad += global sum on every rank (bit-identical)."""
+    n = data.shape[0]
+    dp = _dev(data, torch.float64, "data") if n > 0 else None
+    _check(lib().xyz_lsq_grad_f64_allreduce(dp, n, _dev(params, torch.float64, "params"),
+                                            _dev(loss_sum, torch.float64, "loss_sum") if loss_sum is not None else None,
+                                            ctypes.byref(group.struct), group.next_seq(), _stream(stream), flags),
+           "xyz_lsq_grad_f64_allreduce")
 
 
 def lsq_sgd_update(params: torch.Tensor, lr: float, batch: int, stream=None) -> None:

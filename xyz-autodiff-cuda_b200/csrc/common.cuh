@@ -5,6 +5,7 @@
 #include <stdint.h>
 
 #include <atomic>
+#include <cstring>
 
 #include "../../include/xyz_b200.h"
 
@@ -31,8 +32,71 @@ int sm_count();  // SMs of the current device (148 on B200)
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// ---- peer mailboxes (csrc/peer.cu) ---------------------------------------------------------------
+struct PeerMailbox {
+    double data[2][XYZ_PEER_MAX_WORLD][XYZ_PEER_SLOT_DOUBLES];
+    unsigned long long flag[XYZ_PEER_MAX_WORLD];
+};
+struct PeerArgs {  // passed to kernels by value; world <= 1 means "no exchange"
+    PeerMailbox* box[XYZ_PEER_MAX_WORLD];
+    int rank, world;
+    unsigned long long seq;
+};
+
 // ---- device side -------------------------------------------------------------------------------
 #ifdef __CUDACC__
+
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+    double v;
+    asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long global_timer_ns() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+// All-reduce (sum, rank order) of `len` <= XYZ_PEER_SLOT_DOUBLES doubles held by threads 0..len-1 of ONE CTA per
+// rank.  Must be called by every thread of the CTA (it synchronises); returns the sum in threads 0..len-1.
+// If a peer does not show up within ~4 s the result is NaN (loud, not a hang).
+__device__ __forceinline__ double peer_allreduce_cta(const PeerArgs& pa, double mine, int len, int tid) {
+    const int par = static_cast<int>(pa.seq & 1ull);
+    if (tid < len) {
+        for (int p = 0; p < pa.world; ++p) pa.box[p]->data[par][pa.rank][tid] = mine;  // NVLink stores (and one local)
+        __threadfence_system();
+    }
+    __syncthreads();
+    __shared__ int s_ok;
+    if (tid == 0) s_ok = 1;
+    __syncthreads();
+    if (tid < pa.world) {
+        st_release_sys(&pa.box[tid]->flag[pa.rank], pa.seq);
+        const unsigned long long* f = &pa.box[pa.rank]->flag[tid];
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(f) < pa.seq) {
+            if (global_timer_ns() - t0 > 4000000000ull) {
+                s_ok = 0;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    double s = 0.0;
+    if (tid < len) {
+        for (int q = 0; q < pa.world; ++q) s += ld_relaxed_sys_f64(&pa.box[pa.rank]->data[par][q][tid]);
+        if (!s_ok) s = __longlong_as_double(0x7ff8000000000000ll);
+    }
+    return s;
+}
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
     return static_cast<uint32_t>(__cvta_generic_to_shared(p));

@@ -60,7 +60,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 template <bool kTma>
 __global__ void __launch_bounds__(kThreads, kCtasPerSM)
     lsq_grad_kernel(const double* __restrict__ data, long long n_points, xyz_lsq_parameters* params, double* loss_sum,
-                    double* partials, unsigned int* ticket, int residual_only) {
+                    double* partials, unsigned int* ticket, int residual_only, PeerArgs peer) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LsqSmem& sm = *reinterpret_cast<LsqSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -155,10 +155,14 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM)
             for (int k = 0; k < kAcc; ++k) sm.red[tid >> 5][k] = s[k];
         }
         __syncthreads();
+        double t = 0.0;
         if (tid < kAcc) {
-            double t = 0.0;
 #pragma unroll
             for (int w = 0; w < kThreads / 32; ++w) t += sm.red[w][tid];
+        }
+        // multi-GPU: exchange the row with the other ranks over NVLink peer memory, rank-ordered sum (common.cuh)
+        if (peer.world > 1) t = peer_allreduce_cta(peer, t, kAcc, tid);
+        if (tid < kAcc) {
             if (tid < 4) params->grad[tid] += t;
             else if (loss_sum) *loss_sum += t;
         }
@@ -258,17 +262,18 @@ __global__ void __launch_bounds__(kThreads)
 }  // namespace
 }  // namespace xyzb
 
-extern "C" int xyz_lsq_grad_f64(const xyz_data_point* data, long long n_points, xyz_lsq_parameters* params,
-                                double* loss_sum, void* stream, int flags) {
-    using namespace xyzb;
+namespace xyzb {
+namespace {
+int lsq_grad_launch(const xyz_data_point* data, long long n_points, xyz_lsq_parameters* params, double* loss_sum,
+                    const PeerArgs& peer, void* stream, int flags) {
     if (n_points < 0 || !params) return XYZ_ERR_INVALID_ARGUMENT;
-    if (n_points == 0) return 0;
-    if (!data) return XYZ_ERR_INVALID_ARGUMENT;
+    if (n_points == 0 && peer.world <= 1) return 0;
+    if (n_points > 0 && !data) return XYZ_ERR_INVALID_ARGUMENT;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const long long max_ctas = static_cast<long long>(sm_count()) * kCtasPerSM;
     const long long want = (n_points + kTileP - 1) / kTileP;
-    const int grid = static_cast<int>(want < max_ctas ? want : max_ctas);
-    void* scratch = nullptr;
+    const int grid = static_cast<int>(want < 1 ? 1 : (want < max_ctas ? want : max_ctas));  // >= 1: a rank with no
+    void* scratch = nullptr;                                                                // points still exchanges
     const size_t bytes = 256 + static_cast<size_t>(max_ctas) * kAcc * sizeof(double);
     int err = scratch_get(SCRATCH_REDUCE, bytes, &scratch);
     if (err) return err;
@@ -281,13 +286,39 @@ extern "C" int xyz_lsq_grad_f64(const xyz_data_point* data, long long n_points, 
         cudaFuncSetAttribute(lsq_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(sizeof(LsqSmem)));
         lsq_grad_kernel<true><<<grid, kThreads, sizeof(LsqSmem), st>>>(d, n_points, params, loss_sum, partials, ticket,
-                                                                       residual_only);
+                                                                       residual_only, peer);
     } else {
         lsq_grad_kernel<false><<<grid, kThreads, sizeof(LsqSmem), st>>>(d, n_points, params, loss_sum, partials, ticket,
-                                                                        residual_only);
+                                                                        residual_only, peer);
     }
     count_launch();
     return last_error();
+}
+}  // namespace
+}  // namespace xyzb
+
+extern "C" int xyz_lsq_grad_f64(const xyz_data_point* data, long long n_points, xyz_lsq_parameters* params,
+                                double* loss_sum, void* stream, int flags) {
+    xyzb::PeerArgs none{};
+    none.world = 1;
+    return xyzb::lsq_grad_launch(data, n_points, params, loss_sum, none, stream, flags);
+}
+
+extern "C" int xyz_lsq_grad_f64_allreduce(const xyz_data_point* data, long long n_points, xyz_lsq_parameters* params,
+                                          double* loss_sum, const xyz_peer_group* group, unsigned long long seq,
+                                          void* stream, int flags) {
+    if (!group || group->world < 1 || group->world > XYZ_PEER_MAX_WORLD || group->rank < 0 || group->rank >= group->world ||
+        seq == 0)
+        return XYZ_ERR_INVALID_ARGUMENT;
+    xyzb::PeerArgs pa{};
+    pa.rank = group->rank;
+    pa.world = group->world;
+    pa.seq = seq;
+    for (int i = 0; i < group->world; ++i) {
+        if (!group->mailbox[i]) return XYZ_ERR_INVALID_ARGUMENT;
+        pa.box[i] = static_cast<xyzb::PeerMailbox*>(group->mailbox[i]);
+    }
+    return xyzb::lsq_grad_launch(data, n_points, params, loss_sum, pa, stream, flags);
 }
 
 extern "C" int xyz_lsq_sgd_update_f64(xyz_lsq_parameters* params, double learning_rate, long long batch_size,

@@ -71,3 +71,22 @@ def splat_iteration_sharded(x, params, grads, targets, outputs, loss, width, hei
     else:
         raise ValueError(mode)
     allreduce_shared_grads(grads, loss)
+
+
+def make_peer_group(x):
+    """PeerGroup over the ranks of the default process group (all on one NVSwitch box): the 64-byte CUDA IPC handles
+    travel through one all_gather_object; everything after that is NVLink loads/stores issued by the kernels."""
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+
+    def exchange(handle: bytes):
+        if world == 1:
+            return [handle]
+        out = [None] * world
+        dist.all_gather_object(out, handle)
+        return out
+
+    group = x.PeerGroup(rank, world, exchange)
+    if world > 1:
+        dist.barrier()  # every rank has opened every mailbox before the first kernel stores into them
+    return group
