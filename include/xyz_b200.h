@@ -135,6 +135,7 @@ XYZ_API int xyz_lsq_sgd_step_f64(const xyz_data_point* data, long long n_total, 
  *   per call:      seq must be 1, 2, 3, ... identically on every rank (two calls may be in flight).            */
 #define XYZ_PEER_MAX_WORLD 8
 #define XYZ_PEER_SLOT_DOUBLES 8
+#define XYZ_PEER_VEC_FLOATS 4096
 typedef struct xyz_peer_group {
     void* mailbox[XYZ_PEER_MAX_WORLD]; /* device pointers, index = rank; entries >= world are ignored */
     int rank;
@@ -150,11 +151,19 @@ XYZ_API int xyz_lsq_grad_f64_allreduce(const xyz_data_point* data, long long n_p
                                double* loss_sum, const xyz_peer_group* group, unsigned long long seq,
                                void* stream, int flags);
 
+/* xyz_accumulate_f32 on this rank's elements + the all-reduce of the K sums (K <= XYZ_PEER_VEC_FLOATS), declared
+ * below next to xyz_accumulate_f32. */
+
 /* ---- C2: accumulation of per-element gradients into K shared parameters (fp32) ---------------
  * Replaces the VariableRef::add_grad pattern (include/xyz_autodiff/variable.cuh:48-50) as
  * exercised by tests/test_parallel_gradient_accumulation.cu:25-49: grad[idx[i]] += val[i].   */
 XYZ_API int xyz_accumulate_f32(const int32_t* idx, const float* val, long long n, float* grad, int k,
                        void* stream, int flags);
+/* Multi-GPU: the elements are sharded over the ranks of an xyz_peer_group, grad[b] += sum over ALL ranks.  The CTAs
+ * write partial rows, and ONE finishing kernel adds them, stores the row into every rank's mailbox over NVLink,
+ * waits for the other ranks and adds the rows in rank order (bit-identical on every rank; no NCCL call). */
+XYZ_API int xyz_accumulate_f32_allreduce(const int32_t* idx, const float* val, long long n, float* grad, int k,
+                                 const xyz_peer_group* group, unsigned long long seq, void* stream, int flags);
 /* fp64 flavour used by the reference's own accumulation tests (3 addresses, double). */
 XYZ_API int xyz_accumulate_f64(const int32_t* idx, const double* val, long long n, double* grad, int k,
                        void* stream, int flags);

@@ -27,6 +27,15 @@ dev = torch.device("cuda", local)
 dist.init_process_group("nccl", device_id=dev)
 rank, world = dist.get_rank(), dist.get_world_size()
 D = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+def timed(fn, n=200):
+    for _ in range(20): fn()
+    torch.cuda.synchronize(); dist.barrier()
+    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n): fn()
+    b_.record(); torch.cuda.synchronize()
+    t = torch.tensor([a.elapsed_time(b_) / n], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return t.item() * 1e3
 
 # C1: element ranges, all-reduce of 4 fp64 sums + loss
 data = orc.lsq_data(1_000_003, seed=5)
@@ -58,15 +67,6 @@ for it in range(6):   # several calls: sequence numbers, both mailbox parities
     assert torch.equal(ref_bits, g2), "run-to-run bits differ"
 # timing, informational (rank 0 prints): kernel + NCCL all-reduce of the 5 sums vs. the fused kernel
 dd = D(data[b:e])
-def timed(fn, n=200):
-    for _ in range(20): fn()
-    torch.cuda.synchronize(); dist.barrier()
-    a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record()
-    for _ in range(n): fn()
-    b_.record(); torch.cuda.synchronize()
-    t = torch.tensor([a.elapsed_time(b_) / n], device=dev); dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    return t.item() * 1e3
 buf = torch.zeros(8, dtype=torch.float64, device=dev)
 def nccl_path():
     x.lsq_grad(dd, buf, None)
@@ -90,6 +90,31 @@ x.accumulate(D(idx[b:e]), D(val[b:e]), grad)
 par.allreduce_shared_grads(grad)
 exact = orc.accumulate_exact(idx, val, 1024)
 assert (np.abs(grad.cpu().numpy() - exact) <= 1e-4 * orc.accumulate_exact(idx, np.abs(val), 1024) + 1e-30).all()
+# ... and with the exchange inside the finishing kernel (peer mailboxes), odd shard boundaries included
+pg2 = par.make_peer_group(x)
+for n_el in (idx.size, idx.size - 3, 1000):
+    b2, e2 = par.shard_range(n_el, rank, world)
+    if n_el == idx.size - 3: b2, e2 = min(b2 + 1, e2), e2      # unaligned slice
+    lo = dist.get_rank()
+    spans = [None] * world; dist.all_gather_object(spans, (b2, e2))
+    keep = np.zeros(idx.size, bool)
+    for (bb, ee) in spans: keep[bb:ee] = True
+    grad2 = torch.zeros(1024, device=dev)
+    x.accumulate_allreduce(D(idx[b2:e2]), D(val[b2:e2]), grad2, pg2)
+    torch.cuda.synchronize()
+    ex = orc.accumulate_exact(idx[keep], val[keep], 1024)
+    assert (np.abs(grad2.cpu().numpy() - ex) <= 1e-4 * orc.accumulate_exact(idx[keep], np.abs(val[keep]), 1024) + 1e-30).all()
+    same = grad2.clone(); dist.broadcast(same, 0)
+    assert torch.equal(same, grad2), "ranks disagree bitwise"
+ti_, tv_ = D(idx[b:e]), D(val[b:e])
+def acc_nccl():
+    x.accumulate(ti_, tv_, grad); dist.all_reduce(grad)
+def acc_fused():
+    x.accumulate_allreduce(ti_, tv_, grad, pg2)
+t_a, t_b = timed(acc_nccl), timed(acc_fused)
+if rank == 0:
+    print(f"TIMING accumulate 2^21 -> 1024 over {world} GPUs: kernel + NCCL all-reduce {t_a:.1f} us/iter, fused peer-memory finish {t_b:.1f} us/iter")
+dist.barrier(); pg2.close()
 
 # C3: element ranges, no collective: every rank's slice equals the oracle on that slice
 J, W_, S, go = orc.covproj_inputs(100_000, seed=3)
@@ -140,7 +165,7 @@ print("rank", rank, "ok")
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs >= 2 GPUs")
 def test_sharded_paths_match_single_gpu_and_oracle_over_nccl():
-    n = min(torch.cuda.device_count(), 4)
+    n = min(torch.cuda.device_count(), 8)
     with tempfile.TemporaryDirectory() as d:
         w = os.path.join(d, "worker.py")
         open(w, "w").write(WORKER)

@@ -36,7 +36,7 @@ EXPORTS = [
     "xyz_b200_version", "xyz_b200_shutdown", "xyz_b200_launch_count", "xyz_b200_reset_launch_count",
     "xyz_lsq_grad_f64", "xyz_lsq_sgd_update_f64", "xyz_lsq_select_batch", "xyz_lsq_sgd_step_f64",
     "xyz_peer_mailbox_bytes", "xyz_peer_mailbox_create", "xyz_peer_mailbox_open", "xyz_peer_mailbox_close",
-    "xyz_peer_mailbox_destroy", "xyz_lsq_grad_f64_allreduce",
+    "xyz_peer_mailbox_destroy", "xyz_lsq_grad_f64_allreduce", "xyz_accumulate_f32_allreduce",
     "xyz_accumulate_f32", "xyz_accumulate_f64", "xyz_covproj_fwd_bwd_f32",
     "xyz_launch_gaussian_splatting", "xyz_launch_gaussian_splatting_rows", "xyz_splat_last_stats",
     "xyz_splat_debug_binning", "xyz_zero_gradients", "xyz_adam_step_individual", "xyz_adam_step",
@@ -76,6 +76,8 @@ def lib() -> ctypes.CDLL:
         L.xyz_peer_mailbox_destroy.argtypes = [_vp]
         L.xyz_lsq_grad_f64_allreduce.argtypes = [_vp, _ll, _vp, _vp, ctypes.POINTER(PeerGroupStruct), ctypes.c_ulonglong,
                                                  _vp, _i]
+        L.xyz_accumulate_f32_allreduce.argtypes = [_vp, _vp, _ll, _vp, _i, ctypes.POINTER(PeerGroupStruct),
+                                                   ctypes.c_ulonglong, _vp, _i]
         L.xyz_accumulate_f32.argtypes = [_vp, _vp, _ll, _vp, _i, _vp, _i]
         L.xyz_accumulate_f64.argtypes = [_vp, _vp, _ll, _vp, _i, _vp, _i]
         L.xyz_covproj_fwd_bwd_f32.argtypes = [_vp] * 8 + [_ll, _vp, _i]
@@ -227,6 +229,20 @@ def accumulate(idx: Optional[torch.Tensor], val: torch.Tensor, grad: torch.Tenso
         code = lib().xyz_accumulate_f64(ip, _dev(val, torch.float64, "val"), n, _dev(grad, torch.float64, "grad"), k,
                                         _stream(stream), flags)
     _check(code, "xyz_accumulate")
+
+
+def accumulate_allreduce(idx: Optional[torch.Tensor], val: torch.Tensor, grad: torch.Tensor, group: "PeerGroup",
+                         flags: int = 0, stream=None) -> None:
+    """accumulate on this rank's elements; grad[b] += the sum over ALL ranks, exchanged over NVLink peer memory by
+    the finishing kernel (fp32, K <= 4096)."""
+    n, k = val.numel(), grad.numel()
+    if idx is None:
+        flags |= FLAG_IMPLICIT_IDS
+    ip = _dev(idx, torch.int32, "idx") if (idx is not None and n > 0) else None
+    vp = _dev(val, torch.float32, "val") if n > 0 else None
+    _check(lib().xyz_accumulate_f32_allreduce(ip, vp, n, _dev(grad, torch.float32, "grad"), k,
+                                              ctypes.byref(group.struct), group.next_seq(), _stream(stream), flags),
+           "xyz_accumulate_f32_allreduce")
 
 
 # ---- C3 ------------------------------------------------------------------------------------------

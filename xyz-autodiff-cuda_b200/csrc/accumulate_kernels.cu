@@ -174,9 +174,10 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM)
 // ncu (profiles/): 15.4 shared-memory wavefronts per batch, 14 of them the 4 table/tag accesses at the
 // ~3.5-way bank conflict degree of 32 random banks; l1tex 93 % busy -- the kernel sits on the shared-memory
 // pipe, 41 us for 2^24 uniform ids against 29 us for a kernel that only streams idx+val with this grid.
-template <class T, int kWarpsT, bool kImplicit>
+template <class T, int kWarpsT, bool kImplicit, bool kRows>
 __global__ void __launch_bounds__(kWarpsT * 32, 1)
-    accumulate_tagged_kernel(const int32_t* __restrict__ idx, const T* __restrict__ val, long long n, T* grad, int k) {
+    accumulate_tagged_kernel(const int32_t* __restrict__ idx, const T* __restrict__ val, long long n, T* grad, int k,
+                             T* partial_rows, int aligned) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     T* tables = reinterpret_cast<T*>(smem_raw);
     uint8_t* tags = reinterpret_cast<uint8_t*>(tables + static_cast<size_t>(kWarpsT) * k);
@@ -233,7 +234,7 @@ __global__ void __launch_bounds__(kWarpsT * 32, 1)
     T v_nxt[4];
     auto load_chunk = [&](long long c, int (&id)[4], T (&v)[4]) {
         const long long e0 = c * 128 + lane * 4;
-        if (c < n_chunks && e0 + 4 <= n) {
+        if (aligned && c < n_chunks && e0 + 4 <= n) {  // 16-byte aligned bases: one vector load per array
             if constexpr (kImplicit) {
 #pragma unroll
                 for (int j = 0; j < 4; ++j) id[j] = static_cast<int>((e0 + j) % k);
@@ -282,7 +283,31 @@ __global__ void __launch_bounds__(kWarpsT * 32, 1)
         T s = T(0);
 #pragma unroll 8
         for (int w = 0; w < kWarpsT; ++w) s += tables[static_cast<size_t>(w) * k + b];
-        if (s != T(0)) atomicAdd(grad + b, s);
+        if constexpr (kRows) {
+            partial_rows[static_cast<size_t>(blockIdx.x) * k + b] = s;  // summed (and exchanged) by the finishing kernel
+        } else {
+            if (s != T(0)) atomicAdd(grad + b, s);
+        }
+    }
+}
+
+// Multi-GPU finish (ONE CTA): add the CTAs' rows in CTA order, store the result into every rank's mailbox over
+// NVLink, publish the sequence number, wait for all ranks, add the rows in rank order: grad[b] += global sum.
+__global__ void __launch_bounds__(1024)
+    accumulate_finish_allreduce_kernel(const float* __restrict__ rows, int n_rows, float* grad, int k, PeerArgs pa) {
+    const int tid = threadIdx.x;
+    const int par = static_cast<int>(pa.seq & 1ull);
+    for (int b = tid; b < k; b += 1024) {
+        float s = 0.f;
+        for (int r = 0; r < n_rows; ++r) s += rows[static_cast<size_t>(r) * k + b];
+        for (int p = 0; p < pa.world; ++p) pa.box[p]->vec[par][pa.rank][b] = s;
+    }
+    __threadfence_system();
+    const bool ok = peer_publish_and_wait_cta(pa, tid);
+    for (int b = tid; b < k; b += 1024) {
+        float s = 0.f;
+        for (int q = 0; q < pa.world; ++q) s += ld_relaxed_sys_f32(&pa.box[pa.rank]->vec[par][q][b]);
+        grad[b] += ok ? s : __int_as_float(0x7fc00000);
     }
 }
 
@@ -337,10 +362,27 @@ int launch_tagged(const int32_t* idx, const T* val, long long n, T* grad, int k,
     const long long want = (n_chunks + W - 1) / W;
     const int sms = sm_count();
     const int grid = static_cast<int>(want < sms ? want : sms);  // one CTA per SM (the tables fill shared memory)
-    auto kern = accumulate_tagged_kernel<T, W, kImplicit>;
+    auto kern = accumulate_tagged_kernel<T, W, kImplicit, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-    kern<<<grid, W * 32, smem, st>>>(idx, val, n, grad, k);
+    kern<<<grid, W * 32, smem, st>>>(idx, val, n, grad, k, nullptr, 1);
     count_launch();
+    return last_error();
+}
+
+// rows flavour for the multi-GPU path (fp32, K <= XYZ_PEER_VEC_FLOATS): returns the number of rows written
+template <int W, bool kImplicit>
+int launch_tagged_rows(const int32_t* idx, const float* val, long long n, int k, cudaStream_t st, float* rows, int* n_rows) {
+    const size_t smem = static_cast<size_t>(W) * k * 5;
+    const long long n_chunks = (n + 127) / 128;
+    const long long want = (n_chunks + W - 1) / W;
+    const int sms = sm_count();
+    const int grid = static_cast<int>(want < sms ? want : sms);
+    auto kern = accumulate_tagged_kernel<float, W, kImplicit, true>;
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+    kern<<<grid, W * 32, smem, st>>>(idx, val, n, nullptr, k, rows,
+                                     (aligned16(val) && (kImplicit || aligned16(idx))) ? 1 : 0);
+    count_launch();
+    *n_rows = grid;
     return last_error();
 }
 
@@ -407,4 +449,46 @@ extern "C" int xyz_accumulate_f32(const int32_t* idx, const float* val, long lon
 extern "C" int xyz_accumulate_f64(const int32_t* idx, const double* val, long long n, double* grad, int k,
                                   void* stream, int flags) {
     return xyzb::accumulate<double>(idx, val, n, grad, k, stream, flags);
+}
+
+extern "C" int xyz_accumulate_f32_allreduce(const int32_t* idx, const float* val, long long n, float* grad, int k,
+                                            const xyz_peer_group* group, unsigned long long seq, void* stream, int flags) {
+    using namespace xyzb;
+    if (!group || group->world < 1 || group->world > XYZ_PEER_MAX_WORLD || group->rank < 0 || group->rank >= group->world ||
+        seq == 0 || n < 0 || k <= 0 || k > XYZ_PEER_VEC_FLOATS || !grad)
+        return XYZ_ERR_INVALID_ARGUMENT;
+    const bool implicit = (idx == nullptr);
+    if (n > 0 && (!val || (implicit && !(flags & XYZ_FLAG_IMPLICIT_IDS)))) return XYZ_ERR_INVALID_ARGUMENT;
+    PeerArgs pa{};
+    pa.rank = group->rank;
+    pa.world = group->world;
+    pa.seq = seq;
+    for (int i = 0; i < group->world; ++i) {
+        if (!group->mailbox[i]) return XYZ_ERR_INVALID_ARGUMENT;
+        pa.box[i] = static_cast<PeerMailbox*>(group->mailbox[i]);
+    }
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    void* scratch = nullptr;
+    int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * k * sizeof(float), &scratch);
+    if (err) return err;
+    float* rows = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+    int n_rows = 0;
+    if (n > 0) {
+        // tables of 8 / 16 / 32 warps as shared memory allows (K <= 4096 always fits 8 warps); unaligned slices
+        // (shard boundaries) take the same kernel with scalar loads
+        const size_t per_warp = static_cast<size_t>(k) * 5;
+        if (per_warp * 32 <= 200 * 1024)
+            err = implicit ? launch_tagged_rows<32, true>(idx, val, n, k, st, rows, &n_rows)
+                           : launch_tagged_rows<32, false>(idx, val, n, k, st, rows, &n_rows);
+        else if (per_warp * 16 <= 200 * 1024)
+            err = implicit ? launch_tagged_rows<16, true>(idx, val, n, k, st, rows, &n_rows)
+                           : launch_tagged_rows<16, false>(idx, val, n, k, st, rows, &n_rows);
+        else
+            err = implicit ? launch_tagged_rows<8, true>(idx, val, n, k, st, rows, &n_rows)
+                           : launch_tagged_rows<8, false>(idx, val, n, k, st, rows, &n_rows);
+        if (err) return err;
+    }
+    accumulate_finish_allreduce_kernel<<<1, 1024, 0, st>>>(rows, n_rows, grad, k, pa);
+    count_launch();
+    return last_error();
 }

@@ -34,8 +34,9 @@ inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 
 
 // ---- peer mailboxes (csrc/peer.cu) ---------------------------------------------------------------
 struct PeerMailbox {
-    double data[2][XYZ_PEER_MAX_WORLD][XYZ_PEER_SLOT_DOUBLES];
-    unsigned long long flag[XYZ_PEER_MAX_WORLD];
+    double data[2][XYZ_PEER_MAX_WORLD][XYZ_PEER_SLOT_DOUBLES];   // small rows (least squares: 5 doubles)
+    unsigned long long flag[XYZ_PEER_MAX_WORLD];                 // shared by both areas: one sequence per group
+    float vec[2][XYZ_PEER_MAX_WORLD][XYZ_PEER_VEC_FLOATS];       // K-bin rows (accumulation), K <= XYZ_PEER_VEC_FLOATS
 };
 struct PeerArgs {  // passed to kernels by value; world <= 1 means "no exchange"
     PeerMailbox* box[XYZ_PEER_MAX_WORLD];
@@ -57,6 +58,11 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
 __device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
     double v;
     asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_relaxed_sys_f32(const float* p) {
+    float v;
+    asm volatile("ld.relaxed.sys.global.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
     return v;
 }
 __device__ __forceinline__ unsigned long long global_timer_ns() {
@@ -96,6 +102,28 @@ __device__ __forceinline__ double peer_allreduce_cta(const PeerArgs& pa, double 
         if (!s_ok) s = __longlong_as_double(0x7ff8000000000000ll);
     }
     return s;
+}
+
+// Publish + wait half of the same protocol for rows the caller has already stored into every rank's
+// vec[seq & 1][rank][...] (and fenced with __threadfence_system()).  Every thread of the CTA must call it.
+// Returns false on timeout.
+__device__ __forceinline__ bool peer_publish_and_wait_cta(const PeerArgs& pa, int tid) {
+    __shared__ int s_ok2;
+    if (tid == 0) s_ok2 = 1;
+    __syncthreads();  // also orders the callers' fenced row stores before the flags
+    if (tid < pa.world) {
+        st_release_sys(&pa.box[tid]->flag[pa.rank], pa.seq);
+        const unsigned long long* f = &pa.box[pa.rank]->flag[tid];
+        const unsigned long long t0 = global_timer_ns();
+        while (ld_acquire_sys(f) < pa.seq) {
+            if (global_timer_ns() - t0 > 4000000000ull) {
+                s_ok2 = 0;
+                break;
+            }
+        }
+    }
+    __syncthreads();
+    return s_ok2 != 0;
 }
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
