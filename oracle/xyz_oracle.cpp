@@ -592,6 +592,62 @@ inline void tile_rect(const float* rec, int W, int H, int row_begin, int row_end
     rect[3] = ty1;
 }
 
+// Second level of the cull: the span of tiles of row ty that the ellipse d2 <= d2max can reach (mirrors
+// csrc/splat_host.cu::span_coef / span_edge / tile_row_span operation for operation).
+struct SpanCoef {
+    float cx, cy, k, a, b, hxv, hyv_m, dyR;
+    int ok;
+};
+inline SpanCoef span_coef(const float* rec, float d2max, int no_cull) {
+    SpanCoef c;
+    const float cx = rec[0], cy = rec[1], ia = rec[2], ib = rec[3], ic = rec[4];
+    c.cx = cx;
+    c.cy = cy;
+    const float det = ia * ic - ib * ib;
+    c.ok = !no_cull && det > 0.0f && ia > 0.0f && ic > 0.0f && std::isfinite(det) && std::isfinite(cx) &&
+           std::isfinite(cy) && std::isfinite(ia) && std::isfinite(ic);
+    c.k = ib / ia;
+    c.a = d2max / ia;
+    c.b = det / (ia * ia);
+    c.hxv = std::sqrt(d2max * ic / det);
+    c.hyv_m = std::sqrt(d2max * ia / det) * 1.001f + 1.0f;
+    c.dyR = -(ib / ic) * c.hxv;
+    if (!(std::isfinite(c.k) && std::isfinite(c.a) && std::isfinite(c.b) && std::isfinite(c.hxv) && std::isfinite(c.hyv_m) &&
+          std::isfinite(c.dyR)))
+        c.ok = 0;
+    return c;
+}
+inline float span_edge(const SpanCoef& c, float dy, float sign) {
+    const float rad = std::max(c.a - c.b * (dy * dy), 0.0f);
+    return (-c.k) * dy + sign * std::sqrt(rad);
+}
+inline void tile_row_span(const SpanCoef& c, const int32_t* r, int ty, int W, int row_begin, int row_end, int* s0, int* s1) {
+    *s0 = r[0];
+    *s1 = r[2];
+    if (!c.ok) return;
+    const int y0 = std::max(ty * kTile, row_begin), y1 = std::min(ty * kTile + kTile - 1, row_end - 1);
+    const float lo = std::max(static_cast<float>(y0) - c.cy, -c.hyv_m);
+    const float hi = std::min(static_cast<float>(y1) - c.cy, c.hyv_m);
+    if (lo > hi) {
+        *s0 = *s1 = 0;
+        return;
+    }
+    const float fmx = (lo <= c.dyR && c.dyR <= hi) ? c.hxv : std::max(span_edge(c, lo, 1.0f), span_edge(c, hi, 1.0f));
+    const float gmn = (lo <= -c.dyR && -c.dyR <= hi) ? -c.hxv : std::min(span_edge(c, lo, -1.0f), span_edge(c, hi, -1.0f));
+    const float xr = std::ceil(c.cx + (fmx + (std::fabs(fmx) * 0.001f + 1.0f)));
+    const float xl = std::floor(c.cx - (-gmn + (std::fabs(gmn) * 0.001f + 1.0f)));
+    if (!(std::isfinite(xr) && std::isfinite(xl))) return;
+    if (xr < 0.0f || xl > static_cast<float>(W - 1)) {
+        *s0 = *s1 = 0;
+        return;
+    }
+    const int xi0 = static_cast<int>(std::max(xl, 0.0f));
+    const int xi1 = static_cast<int>(std::min(xr, static_cast<float>(W - 1)));
+    *s0 = std::max(xi0 / kTile, r[0]);
+    *s1 = std::min(xi1 / kTile + 1, r[2]);
+    if (*s1 < *s0) *s1 = *s0;
+}
+
 }  // namespace
 
 extern "C" {
@@ -799,8 +855,12 @@ long long orc_splat_binning(const float* rec, int N, int W, int H, int row_begin
     std::vector<int32_t> rl(static_cast<size_t>(N) * 4);
     for (int g = 0; g < N; ++g) {
         tile_rect(rec + 12 * g, W, H, row_begin, row_end, d2max, no_cull, &rl[4 * g]);
-        for (int ty = rl[4 * g + 1]; ty < rl[4 * g + 3]; ++ty)
-            for (int tx = rl[4 * g]; tx < rl[4 * g + 2]; ++tx) count[ty * tiles_x + tx + 1]++;
+        const SpanCoef sc = span_coef(rec + 12 * g, d2max, no_cull);
+        for (int ty = rl[4 * g + 1]; ty < rl[4 * g + 3]; ++ty) {
+            int s0, s1;
+            tile_row_span(sc, &rl[4 * g], ty, W, row_begin, row_end, &s0, &s1);
+            for (int tx = s0; tx < s1; ++tx) count[ty * tiles_x + tx + 1]++;
+        }
     }
     if (rects) std::memcpy(rects, rl.data(), rl.size() * sizeof(int32_t));
     for (int t = 0; t < ntiles; ++t) count[t + 1] += count[t];
@@ -812,9 +872,14 @@ long long orc_splat_binning(const float* rec, int N, int W, int H, int row_begin
         }
     if (sorted_ids && total <= capacity) {
         std::vector<long long> cur(count.begin(), count.end() - 1);
-        for (int g = 0; g < N; ++g)  // ascending g => each tile list is ascending (stable)
-            for (int ty = rl[4 * g + 1]; ty < rl[4 * g + 3]; ++ty)
-                for (int tx = rl[4 * g]; tx < rl[4 * g + 2]; ++tx) sorted_ids[cur[ty * tiles_x + tx]++] = g;
+        for (int g = 0; g < N; ++g) {  // ascending g => each tile list is ascending (stable)
+            const SpanCoef sc = span_coef(rec + 12 * g, d2max, no_cull);
+            for (int ty = rl[4 * g + 1]; ty < rl[4 * g + 3]; ++ty) {
+                int s0, s1;
+                tile_row_span(sc, &rl[4 * g], ty, W, row_begin, row_end, &s0, &s1);
+                for (int tx = s0; tx < s1; ++tx) sorted_ids[cur[ty * tiles_x + tx]++] = g;
+            }
+        }
     }
     return total;
 }

@@ -133,3 +133,30 @@ def test_tile_binning_restatement_properties():
         tx0, ty0, tx1, ty1 = rects[g]
         inside = (xs >= tx0 * 16) & (xs < tx1 * 16) & (ys >= ty0 * 16) & (ys < ty1 * 16)
         assert not (nz & ~inside).any()
+
+
+@pytest.mark.parametrize("seed,small", [(5, True), (6, False), (7, True)])
+def test_tile_row_spans_keep_every_nonzero_pair(seed, small):
+    """Second cull level (per tile row, the span the ellipse can reach): every (pixel, Gaussian) pair whose fp32
+    weight is not exactly zero lies in a tile that lists the Gaussian; the lists are a strict subset of the
+    rectangles for anisotropic / rotated Gaussians; d2max = 56 (XYZ_FLAG_TAIL_CULL) keeps every pair above e^-28."""
+    W, H, N = 230, 170, 160
+    params, _ = orc.splat_scene(N, W, H, seed=seed, small=small)
+    params[:, 2] += 0.4                                   # anisotropic
+    rec = orc.splat_records(params)
+    tiles_x = (W + 15) // 16
+    ys, xs = np.mgrid[0:H, 0:W]
+    tile_of = (ys // 16) * tiles_x + xs // 16
+    for d2max, thresh in ((176.0, 2.0 ** -126), (56.0, np.exp(-28.0))):
+        rects, ranges, ids = orc.splat_binning(rec, W, H, d2max=d2max)
+        member = np.zeros((ranges.shape[0], N), bool)
+        for t in range(ranges.shape[0]):
+            member[t, ids[ranges[t, 0]:ranges[t, 1]]] = True
+        rect_tiles = ((rects[:, 2] - rects[:, 0]) * (rects[:, 3] - rects[:, 1])).sum()
+        assert ids.size < rect_tiles
+        for g in range(N):
+            cx, cy, ia, ib, ic = rec[g, :5].astype(np.float64)
+            dx, dy = xs - cx, ys - cy
+            d2 = ia * dx * dx + 2 * ib * dx * dy + ic * dy * dy
+            nz = np.exp(-0.5 * d2) > thresh
+            assert member[tile_of[nz], g].all(), (g, d2max)

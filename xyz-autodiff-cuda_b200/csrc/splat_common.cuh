@@ -24,6 +24,7 @@ namespace xyzb {
 
 constexpr int kTile = 16;                 // TILE_SIZE, gaussian_splatting_kernel.cuh:21
 constexpr int kTilePixels = kTile * kTile;
+constexpr int kSpanRows = 16;              // tile-row spans kept per Gaussian between preprocess and key emission
 constexpr int kRecFloats = 12;            // {cx, cy, ia, ib, ic, sigmoid(opacity), r, g, b, 0, 0, 0}
 
 // exp(-d2/2) == 0.0f exactly beyond these:
@@ -43,6 +44,7 @@ struct SplatBuffers {  // device scratch of one launch (library-owned)
     float4* records;          // N x 3 float4
     int4* rects;              // N: tx0, ty0, tx1, ty1 (half-open)
     unsigned int* touched;    // N: tiles per Gaussian
+    int2* spans;              // N x kSpanRows: [tx0, tx1) of the first kSpanRows tile rows of the rectangle
     unsigned long long* offsets;  // N: inclusive scan of touched (64-bit: N x tiles can exceed 2^32)
     unsigned int* keys_in;    // entries: tile id, Gaussian order
     unsigned int* keys_out;   // entries: sorted

@@ -47,9 +47,58 @@ __device__ __forceinline__ int4 gaussian_tile_rect(float cx, float cy, float ia,
     return r;
 }
 
+// Exact-zero cull, second level: inside the rectangle, tile row ty only needs the tiles between the leftmost and
+// the rightmost pixel of the ellipse d2 <= d2max over that row's pixel rows (the ellipse is convex, so the tiles of
+// a row form one span; at C4 this drops 21 % of the rectangle's tiles).  For dy = y - cy the ellipse covers
+//   dx in [-k dy - w(dy), -k dy + w(dy)],  k = ib / ia,  w = sqrt(d2max / ia - (det / ia^2) dy^2);
+// the right edge is concave in dy with its maximum hx at dy_R = -(ib / ic) hx, the left edge is its mirror image.
+// Same margins as the rectangle (0.1 % + 1 pixel); every float op is a single rounded IEEE operation, mirrored by
+// oracle/xyz_oracle.cpp::tile_row_span.  Returns the half-open tile span [x, y) (empty: x >= y).
+struct SpanCoef {
+    float cx, cy, k, a, b, hxv, hyv_m, dyR;
+    int ok;
+};
+__device__ __forceinline__ SpanCoef span_coef(float cx, float cy, float ia, float ib, float ic, float d2max, int no_cull) {
+    SpanCoef c;
+    c.cx = cx;
+    c.cy = cy;
+    const float det = __fsub_rn(__fmul_rn(ia, ic), __fmul_rn(ib, ib));
+    c.ok = !no_cull && det > 0.0f && ia > 0.0f && ic > 0.0f && isfinite(det) && isfinite(cx) && isfinite(cy) &&
+           isfinite(ia) && isfinite(ic);
+    c.k = __fdiv_rn(ib, ia);
+    c.a = __fdiv_rn(d2max, ia);
+    c.b = __fdiv_rn(det, __fmul_rn(ia, ia));
+    c.hxv = __fsqrt_rn(__fdiv_rn(__fmul_rn(d2max, ic), det));
+    c.hyv_m = __fadd_rn(__fmul_rn(__fsqrt_rn(__fdiv_rn(__fmul_rn(d2max, ia), det)), 1.001f), 1.0f);
+    c.dyR = __fmul_rn(-__fdiv_rn(ib, ic), c.hxv);
+    if (!(isfinite(c.k) && isfinite(c.a) && isfinite(c.b) && isfinite(c.hxv) && isfinite(c.hyv_m) && isfinite(c.dyR))) c.ok = 0;
+    return c;
+}
+__device__ __forceinline__ float span_edge(const SpanCoef& c, float dy, float sign) {
+    const float rad = fmaxf(__fsub_rn(c.a, __fmul_rn(c.b, __fmul_rn(dy, dy))), 0.0f);
+    return __fadd_rn(__fmul_rn(-c.k, dy), __fmul_rn(sign, __fsqrt_rn(rad)));
+}
+__device__ __forceinline__ int2 tile_row_span(const SpanCoef& c, const int4& r, int ty, const SplatView& v) {
+    if (!c.ok) return make_int2(r.x, r.z);
+    const int y0 = max(ty * kTile, v.row_begin), y1 = min(ty * kTile + kTile - 1, v.row_end - 1);
+    const float lo = fmaxf(__fsub_rn(static_cast<float>(y0), c.cy), -c.hyv_m);
+    const float hi = fminf(__fsub_rn(static_cast<float>(y1), c.cy), c.hyv_m);
+    if (lo > hi) return make_int2(0, 0);
+    const float fmx = (lo <= c.dyR && c.dyR <= hi) ? c.hxv : fmaxf(span_edge(c, lo, 1.0f), span_edge(c, hi, 1.0f));
+    const float gmn = (lo <= -c.dyR && -c.dyR <= hi) ? -c.hxv : fminf(span_edge(c, lo, -1.0f), span_edge(c, hi, -1.0f));
+    const float xr = ceilf(__fadd_rn(c.cx, __fadd_rn(fmx, __fadd_rn(__fmul_rn(fabsf(fmx), 0.001f), 1.0f))));
+    const float xl = floorf(__fsub_rn(c.cx, __fadd_rn(-gmn, __fadd_rn(__fmul_rn(fabsf(gmn), 0.001f), 1.0f))));
+    if (!(isfinite(xr) && isfinite(xl))) return make_int2(r.x, r.z);
+    if (xr < 0.0f || xl > static_cast<float>(v.width - 1)) return make_int2(0, 0);
+    const int xi0 = static_cast<int>(fmaxf(xl, 0.0f));
+    const int xi1 = static_cast<int>(fminf(xr, static_cast<float>(v.width - 1)));
+    return make_int2(max(xi0 / kTile, r.x), min(xi1 / kTile + 1, r.z));
+}
+
 __global__ void __launch_bounds__(256)
     splat_preprocess_kernel(SplatView v, const xyz_gaussian_params* __restrict__ params, float4* __restrict__ records,
-                            int4* __restrict__ rects, unsigned int* __restrict__ touched, float d2max, int no_cull) {
+                            int4* __restrict__ rects, unsigned int* __restrict__ touched, int2* __restrict__ spans,
+                            float d2max, int no_cull) {
     const int g = blockIdx.x * blockDim.x + threadIdx.x;
     if (g >= v.num_gaussians) return;
     const xyz_gaussian_params p = params[g];
@@ -71,30 +120,68 @@ __global__ void __launch_bounds__(256)
     records[3 * g + 2] = make_float4(p.color[2], 0.f, 0.f, 0.f);
     const int4 r = gaussian_tile_rect(p.center[0], p.center[1], ia, ib, ic, v, d2max, no_cull);
     rects[g] = r;
-    touched[g] = static_cast<unsigned int>((r.z - r.x) * (r.w - r.y));
+    const SpanCoef sc = span_coef(p.center[0], p.center[1], ia, ib, ic, d2max, no_cull);
+    unsigned int cnt = 0;
+    for (int ty = r.y; ty < r.w; ++ty) {
+        const int2 s = tile_row_span(sc, r, ty, v);
+        cnt += static_cast<unsigned int>(max(s.y - s.x, 0));
+        // the first kSpanRows rows are kept for the key emission (rows beyond that are recomputed there)
+        if (ty - r.y < kSpanRows) spans[static_cast<size_t>(g) * kSpanRows + (ty - r.y)] = make_int2(s.x, max(s.y, s.x));
+    }
+    touched[g] = cnt;
 }
 
 // ---- 2. keys in Gaussian order ----------------------------------------------------------------------
-// One warp per Gaussian: lane l writes the rectangle's tiles l, l + 32, ... (row-major inside the rectangle), so a
-// warp's stores are consecutive (the one-thread-per-Gaussian version wrote 50-entry runs per thread: 83 us at C4).
+// Half a warp per Gaussian: the 16 lanes take the spans of 16 tile rows at a time (stored by the preprocess kernel
+// for the first 16 rows, recomputed beyond), a shuffle scan gives each row its offset, then every row's span is
+// written with consecutive lanes -> coalesced stores.  Order inside a Gaussian: row-major (ty, tx).
 __global__ void __launch_bounds__(256)
-    splat_emit_keys_kernel(int n, int tiles_x, const int4* __restrict__ rects, const unsigned int* __restrict__ touched,
-                           const unsigned long long* __restrict__ offsets_incl, unsigned int* __restrict__ keys,
-                           unsigned int* __restrict__ vals, int by_gid) {
-    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-    const int lane = threadIdx.x & 31;
-    if (g >= n) return;
+    splat_emit_keys_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ rects,
+                           const unsigned int* __restrict__ touched, const unsigned long long* __restrict__ offsets_incl,
+                           const int2* __restrict__ spans, unsigned int* __restrict__ keys, unsigned int* __restrict__ vals,
+                           float d2max, int no_cull, int by_gid) {
+    const int g = (blockIdx.x * blockDim.x + threadIdx.x) >> 4;
+    const int hl = threadIdx.x & 15;
+    const unsigned int half_mask = 0xffffu << (threadIdx.x & 16);
+    if (g >= v.num_gaussians) return;
     const unsigned int cnt = touched[g];
     if (cnt == 0u) return;
     const int4 r = rects[g];
-    const unsigned int w = static_cast<unsigned int>(r.z - r.x);
-    const unsigned int o = static_cast<unsigned int>(offsets_incl[g] - cnt);
-    for (unsigned int t = lane; t < cnt; t += 32) {
-        const unsigned int row = t / w, col = t - row * w;
-        keys[o + t] = static_cast<unsigned int>((r.y + row) * tiles_x + (r.x + col));
-        // payload: the Gaussian id itself, or (deterministic mode) the entry's position in Gaussian order,
-        // which names its row of entry_grads
-        vals[o + t] = by_gid ? static_cast<unsigned int>(g) : o + t;
+    unsigned int o = static_cast<unsigned int>(offsets_incl[g] - cnt);
+    for (int rb = r.y; rb < r.w; rb += kSpanRows) {
+        const int ty = rb + hl;
+        int2 s = make_int2(0, 0);
+        if (ty < r.w) {
+            if (rb == r.y) {
+                s = spans[static_cast<size_t>(g) * kSpanRows + hl];
+            } else {
+                const float4 r0 = __ldg(records + 3 * g), r1 = __ldg(records + 3 * g + 1);
+                const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
+                s = tile_row_span(sc, r, ty, v);
+            }
+        }
+        const int wdt = max(s.y - s.x, 0);
+        int incl = wdt;
+#pragma unroll
+        for (int d = 1; d < 16; d <<= 1) {
+            const int y = __shfl_up_sync(half_mask, incl, d, 16);
+            if (hl >= d) incl += y;
+        }
+        const int excl = incl - wdt;
+        const int rows = min(kSpanRows, r.w - rb);
+        for (int j = 0; j < rows; ++j) {
+            const int wj = __shfl_sync(half_mask, wdt, j, 16);
+            const int oj = __shfl_sync(half_mask, excl, j, 16);
+            const int sj = __shfl_sync(half_mask, s.x, j, 16);
+            for (int t = hl; t < wj; t += 16) {
+                const unsigned int e = o + static_cast<unsigned int>(oj + t);
+                keys[e] = static_cast<unsigned int>((rb + j) * v.tiles_x + sj + t);
+                // payload: the Gaussian id itself, or (deterministic mode) the entry's position in Gaussian
+                // order, which names its row of entry_grads
+                vals[e] = by_gid ? static_cast<unsigned int>(g) : e;
+            }
+        }
+        o += static_cast<unsigned int>(__shfl_sync(half_mask, incl, 15, 16));
     }
 }
 
@@ -242,7 +329,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     size_t off = 0;
     auto take = [&off](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
     const size_t o_rec = take(sizeof(float4) * 3 * ng), o_rect = take(sizeof(int4) * ng),
-                 o_touched = take(sizeof(unsigned int) * ng), o_offsets = take(sizeof(unsigned long long) * ng),
+                 o_touched = take(sizeof(unsigned int) * ng), o_spans = take(sizeof(int2) * kSpanRows * ng), o_offsets = take(sizeof(unsigned long long) * ng),
                  o_ranges = take(sizeof(int2) * n_tiles), o_tloss = take(sizeof(float) * n_tiles),
                  o_chunks = take(sizeof(int) * (n_tiles + 1)),
                  o_rest = take(sizeof(float4) * kTilePixels * static_cast<size_t>(n_tiles));
@@ -257,6 +344,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     b.records = reinterpret_cast<float4*>(base + o_rec);
     b.rects = reinterpret_cast<int4*>(base + o_rect);
     b.touched = reinterpret_cast<unsigned int*>(base + o_touched);
+    b.spans = reinterpret_cast<int2*>(base + o_spans);
     b.offsets = reinterpret_cast<unsigned long long*>(base + o_offsets);
     b.tile_ranges = reinterpret_cast<int2*>(base + o_ranges);
     b.tile_loss = reinterpret_cast<float*>(base + o_tloss);
@@ -268,7 +356,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
 
     long long entries = 0;
     if (N > 0) {
-        splat_preprocess_kernel<<<(N + 255) / 256, 256, 0, st>>>(v, gaussians, b.records, b.rects, b.touched,
+        splat_preprocess_kernel<<<(N + 255) / 256, 256, 0, st>>>(v, gaussians, b.records, b.rects, b.touched, b.spans,
                                                                  (flags & XYZ_FLAG_TAIL_CULL) ? kD2MaxTail : (precise ? kD2MaxPrecise : kD2MaxFast), no_cull);
         count_launch();
         ce = cub::DeviceScan::InclusiveSum(base + o_scan_tmp, scan_tmp_bytes, TouchedIter(b.touched, ToU64()), b.offsets,
@@ -312,8 +400,9 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     b.chunk_info = reinterpret_cast<int4*>(sbase + o_cinfo);
 
     if (entries > 0) {
-        splat_emit_keys_kernel<<<(N + 7) / 8, 256, 0, st>>>(N, v.tiles_x, b.rects, b.touched, b.offsets, b.keys_in,
-                                                                b.vals_in, deterministic ? 0 : 1);
+        splat_emit_keys_kernel<<<(N + 15) / 16, 256, 0, st>>>(
+            v, b.records, b.rects, b.touched, b.offsets, b.spans, b.keys_in, b.vals_in,
+            (flags & XYZ_FLAG_TAIL_CULL) ? kD2MaxTail : (precise ? kD2MaxPrecise : kD2MaxFast), no_cull, deterministic ? 0 : 1);
         count_launch();
         ce = cub::DeviceRadixSort::SortPairs(sbase + o_sort_tmp, sort_tmp_bytes, b.keys_in, b.keys_out, b.vals_in,
                                              b.vals_out, static_cast<int>(entries), 0, key_bits, st);
