@@ -244,3 +244,20 @@ def test_device_concurrent_accumulation_known_answers(cuda):
     tgt = np.zeros(8, np.float32)
     assert cuda.cuda_block_accumulate_f32(P(vals), vals.size, P(tgt)) == 0
     assert np.allclose(tgt, vals.astype(np.float64).sum() * np.arange(1, 9), rtol=1e-4, atol=1e-2)
+
+
+@pytest.mark.gpu
+def test_gradient_testers_rehosted_without_gtest():
+    """include/xyz_autodiff/testing.cuh (the reference's Unary/Binary/NetworkGradientTester API, gtest-free, one launch
+    for all random cases) over the op table and the splat example's custom Logics: every Logic passes at the
+    reference's 1e-5 rule, a deliberately wrong Logic and a forbidden tolerance are rejected."""
+    path = os.path.join(os.path.dirname(__file__), "csrc", "_build", "libxyz_testers.so")
+    if not os.path.exists(path):
+        subprocess.run(["make", "-C", os.path.join(os.path.dirname(__file__), "csrc")], check=True, stdout=subprocess.DEVNULL)
+    L = ctypes.CDLL(path)
+    buf = ctypes.create_string_buffer(1 << 16)
+    code = L.tester_run_all(buf, len(buf))
+    text = buf.value.decode()
+    assert code // 1000 == 0, text
+    assert code % 1000 >= 27, text
+    assert "FAIL" not in text
