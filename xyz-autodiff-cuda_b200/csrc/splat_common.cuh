@@ -24,6 +24,7 @@ namespace xyzb {
 
 constexpr int kTile = 16;                 // TILE_SIZE, gaussian_splatting_kernel.cuh:21
 constexpr int kTilePixels = kTile * kTile;
+constexpr int kBwdChunk = 128;             // list entries (= threads) per backward CTA; chunks never straddle tiles
 constexpr int kSpanRows = 16;              // tile-row spans kept per Gaussian between preprocess and key emission
 constexpr int kRecFloats = 12;            // {cx, cy, ia, ib, ic, sigmoid(opacity), r, g, b, 0, 0, 0}
 

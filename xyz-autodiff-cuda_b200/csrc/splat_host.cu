@@ -210,10 +210,9 @@ __global__ void __launch_bounds__(256)
     if (sorted_gid) sorted_gid[i] = entry_to_gaussian(offsets_incl, n, vals_sorted[i]);
 }
 
-// ---- backward work list: exclusive scan over the tiles of ceil(list length / 256) -------------------------
+// ---- backward work list: exclusive scan over the tiles of ceil(list length / kBwdChunk) -------------------------
 __global__ void __launch_bounds__(1024)
-    splat_chunk_scan_kernel(const int2* __restrict__ tile_ranges, int n_tiles, int* __restrict__ chunk_offsets,
-                            int4* __restrict__ chunk_info) {
+    splat_chunk_scan_kernel(const int2* __restrict__ tile_ranges, int n_tiles, int* __restrict__ chunk_offsets) {
     __shared__ int s_warp[32];
     __shared__ int s_carry;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -224,7 +223,7 @@ __global__ void __launch_bounds__(1024)
         int c = 0;
         if (t < n_tiles) {
             const int2 r = tile_ranges[t];
-            c = (r.y - r.x + kTilePixels - 1) / kTilePixels;
+            c = (r.y - r.x + kBwdChunk - 1) / kBwdChunk;
         }
         int x = c;
 #pragma unroll
@@ -246,16 +245,23 @@ __global__ void __launch_bounds__(1024)
         __syncthreads();
         const int carry = s_carry;
         const int before = carry + (warp > 0 ? s_warp[warp - 1] : 0) + (x - c);
-        if (t < n_tiles) {
-            chunk_offsets[t] = before;
-            const int2 r = tile_ranges[t];
-            for (int k = 0; k < c; ++k) chunk_info[before + k] = make_int4(t, r.x + k * kTilePixels, r.y, 0);
-        }
+        if (t < n_tiles) chunk_offsets[t] = before;
         __syncthreads();
         if (tid == 1023) s_carry = carry + s_warp[31];
         __syncthreads();
     }
     if (tid == 0) chunk_offsets[n_tiles] = s_carry;
+}
+
+// one record per backward CTA: {tile, first entry, end of the tile's list, 0}
+__global__ void __launch_bounds__(256)
+    splat_chunk_fill_kernel(const int2* __restrict__ tile_ranges, int n_tiles, const int* __restrict__ chunk_offsets,
+                            int4* __restrict__ chunk_info) {
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_tiles) return;
+    const int2 r = tile_ranges[t];
+    const int first = chunk_offsets[t], c = chunk_offsets[t + 1] - first;
+    for (int k = 0; k < c; ++k) chunk_info[first + k] = make_int4(t, r.x + k * kBwdChunk, r.y, 0);
 }
 
 // ---- loss: tile partials summed in tile order (no float atomics) ---------------------------------------
@@ -381,7 +387,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     auto stake = [&soff](size_t bytes) { size_t o = soff; soff += align_up(bytes); return o; };
     const size_t o_kin = stake(4 * ne), o_kout = stake(4 * ne), o_vin = stake(4 * ne), o_vout = stake(4 * ne),
                  o_gid = stake(deterministic ? 4 * ne : 0),
-                 o_cinfo = stake(sizeof(int4) * static_cast<size_t>(ne / kTilePixels + n_tiles)), o_eg = stake(deterministic ? 36 * ne : 0);
+                 o_cinfo = stake(sizeof(int4) * static_cast<size_t>(ne / kBwdChunk + n_tiles)), o_eg = stake(deterministic ? 36 * ne : 0);
     size_t sort_tmp_bytes = 0;
     cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, static_cast<unsigned int*>(nullptr),
                                     static_cast<unsigned int*>(nullptr), static_cast<unsigned int*>(nullptr),
@@ -411,10 +417,11 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
         splat_ranges_kernel<<<static_cast<unsigned int>((entries + 255) / 256), 256, 0, st>>>(
             entries, b.keys_out, b.vals_out, b.offsets, N, b.tile_ranges, deterministic ? b.sorted_gid : nullptr);
         // surplus backward CTAs (the grid is an upper bound) read tile = -1
-        ce = cudaMemsetAsync(b.chunk_info, 0xff, sizeof(int4) * static_cast<size_t>(entries / kTilePixels + n_tiles), st);
+        ce = cudaMemsetAsync(b.chunk_info, 0xff, sizeof(int4) * static_cast<size_t>(entries / kBwdChunk + n_tiles), st);
         if (ce != cudaSuccess) return static_cast<int>(ce);
-        splat_chunk_scan_kernel<<<1, 1024, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets, b.chunk_info);
-        count_launch(2);
+        splat_chunk_scan_kernel<<<1, 1024, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets);
+        splat_chunk_fill_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets, b.chunk_info);
+        count_launch(3);
     }
 
     err = precise ? splat_forward_launch_precise(v, b, target, output, st)

@@ -259,9 +259,9 @@ __device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_r
     }
 }
 
-// One CTA = up to 256 consecutive list entries of ONE tile: chunk_info[c] = {tile, first entry, end of the tile's
+// One CTA = up to kBwdChunk consecutive list entries of ONE tile: chunk_info[c] = {tile, first entry, end of the tile's
 // list, -} written by splat_chunk_scan_kernel; the grid is an upper bound, surplus CTAs see tile = -1 and exit.
-__global__ void __launch_bounds__(kTilePixels)
+__global__ void __launch_bounds__(kBwdChunk)
     splat_backward_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ chunk_info,
                           const float4* __restrict__ rest_tiles, const int* __restrict__ sorted_gid,
                           const unsigned int* __restrict__ sorted_orig, const xyz_gaussian_params* __restrict__ params,
@@ -275,9 +275,10 @@ __global__ void __launch_bounds__(kTilePixels)
     const int i = info.y + tid;
     const bool valid = i < info.z;
     const int tile_x = tile % v.tiles_x, tile_y = tile / v.tiles_x;
-    {
-        const float4 rest = __ldg(rest_tiles + static_cast<size_t>(tile) * kTilePixels + tid);
-        float* pair = reinterpret_cast<float*>(&s_rest[tid >> 1]) + (tid & 1);
+#pragma unroll
+    for (int p = tid; p < kTilePixels; p += kBwdChunk) {
+        const float4 rest = __ldg(rest_tiles + static_cast<size_t>(tile) * kTilePixels + p);
+        float* pair = reinterpret_cast<float*>(&s_rest[p >> 1]) + (p & 1);
         pair[0] = -rest.x;
         pair[2] = -rest.y;
         pair[4] = -rest.z;
@@ -380,11 +381,11 @@ int XYZ_CAT(splat_backward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const 
                                                       bool deterministic, cudaStream_t st) {
     if (entries <= 0) return 0;
     const int n_tiles = v.tiles_x * v.tiles_y;
-    // upper bound of sum over tiles of ceil(len / 256)
-    const long long blocks = entries / kTilePixels + n_tiles;
+    // upper bound of sum over tiles of ceil(len / kBwdChunk)
+    const long long blocks = entries / kBwdChunk + n_tiles;
     (void)target;
     (void)output;
-    splat_backward_kernel<<<static_cast<unsigned int>(blocks), kTilePixels, 0, st>>>(
+    splat_backward_kernel<<<static_cast<unsigned int>(blocks), kBwdChunk, 0, st>>>(
         v, b.records, b.chunk_info, b.rest_tiles, b.sorted_gid, b.vals_out, params, grads,
         deterministic ? b.entry_grads : nullptr);
     count_launch();
