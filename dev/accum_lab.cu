@@ -11,6 +11,7 @@
 #include <algorithm>
 #include <vector>
 
+#define CKV(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); exit(1); } } while (0)
 
 constexpr unsigned kFull = 0xffffffffu;
@@ -438,6 +439,76 @@ __global__ void __launch_bounds__(WARPS * 32, MINB)
     }
 }
 
+
+// ---- variant G: tags for most batches, plain global REDs (per-CTA table in L2) for every GLOBAL_EVERY-th batch ----
+template <int WARPS, int GLOBAL_MASK>
+__global__ void __launch_bounds__(WARPS * 32, 1)
+    accum_mixed_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, long long n, float* grad, int k,
+                       float* gtables) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    float* tables = reinterpret_cast<float*>(smem_raw);
+    uint8_t* tags = reinterpret_cast<uint8_t*>(tables + static_cast<size_t>(WARPS) * k);
+    constexpr int kThreads = WARPS * 32;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float* gtab = gtables + static_cast<size_t>(blockIdx.x) * k;
+    for (int i = tid; i < WARPS * k; i += kThreads) tables[i] = 0.f;
+    for (int i = tid; i < k; i += kThreads) gtab[i] = 0.f;
+    __syncthreads();
+    float* table = tables + static_cast<size_t>(warp) * k;
+    uint8_t* tag = tags + static_cast<size_t>(warp) * k;
+    const long long n_chunks = (n + 127) / 128;
+    const long long gw = static_cast<long long>(blockIdx.x) * WARPS + warp;
+    const long long wstride = static_cast<long long>(gridDim.x) * WARPS;
+    auto batch = [&](int id, float v) {
+        const bool valid = static_cast<unsigned>(id) < static_cast<unsigned>(k);
+        if (valid) tag[id] = static_cast<uint8_t>(lane);
+        __syncwarp();
+        const bool won = valid && tag[id] == lane;
+        if (won) table[id] += v;
+        const bool mine = valid && !won;
+        unsigned lost = __ballot_sync(kFull, mine);
+        __syncwarp();
+        if (lost == 0u) return;
+        if (__popc(lost) <= 2) {
+            while (lost) {
+                const int l = __ffs(lost) - 1;
+                if (lane == l) table[id] += v;
+                __syncwarp();
+                lost &= lost - 1u;
+            }
+            return;
+        }
+        unsigned peers = __match_any_sync(kFull, mine ? id : -1);
+        if (!mine) peers = 1u << lane;
+        v = reduce_peers(peers, v, lane);
+        if (mine && lane == __ffs(peers) - 1) table[id] += v;
+        __syncwarp();
+    };
+    auto gbatch = [&](int id, float v) {
+        if (static_cast<unsigned>(id) < static_cast<unsigned>(k)) atomicAdd(gtab + id, v);
+    };
+    for (long long c = gw; c < n_chunks; c += wstride) {
+        const long long e0 = c * 128 + lane * 4;
+        if (e0 + 4 <= n) {
+            const int4 q = __ldcs(reinterpret_cast<const int4*>(idx + e0));
+            const float4 f = __ldcs(reinterpret_cast<const float4*>(val + e0));
+            if (GLOBAL_MASK & 1) gbatch(q.x, f.x); else batch(q.x, f.x);
+            if (GLOBAL_MASK & 2) gbatch(q.y, f.y); else batch(q.y, f.y);
+            if (GLOBAL_MASK & 4) gbatch(q.z, f.z); else batch(q.z, f.z);
+            if (GLOBAL_MASK & 8) gbatch(q.w, f.w); else batch(q.w, f.w);
+        }
+    }
+    __syncthreads();
+    __threadfence();
+    for (int b = tid; b < k; b += kThreads) {
+        float s = 0.f;
+#pragma unroll 8
+        for (int w = 0; w < WARPS; ++w) s += tables[static_cast<size_t>(w) * k + b];
+        s += __ldcg(gtab + b);
+        if (s != 0.f) atomicAdd(grad + b, s);
+    }
+}
+
 // ---- variant L: load-only (roofline probe: how fast can this grid shape stream idx+val?) ----------------
 template <int WARPS, int DEPTH>
 __global__ void __launch_bounds__(WARPS * 32, 1)
@@ -530,6 +601,16 @@ static void launch_adaptive(const int32_t* idx, const float* val, long long n, f
     CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     kern<<<grid * MINB, WARPS * 32, smem>>>(idx, val, n, grad, k);
 }
+
+static float* g_gtables = nullptr;
+template <int WARPS, int GLOBAL_MASK>
+static void launch_mixed(const int32_t* idx, const float* val, long long n, float* grad, int k, int grid) {
+    if (!g_gtables) CKV(cudaMalloc(&g_gtables, sizeof(float) * 4096 * 1024));
+    const size_t smem = static_cast<size_t>(WARPS) * k * 5;
+    auto kern = accum_mixed_kernel<WARPS, GLOBAL_MASK>;
+    CK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+    kern<<<grid, WARPS * 32, smem>>>(idx, val, n, grad, k, g_gtables);
+}
 template <int WARPS, int DEPTH>
 static void launch_stream(const int32_t* idx, const float* val, long long n, float* grad, int k, int grid) {
     stream_only_kernel<WARPS, DEPTH><<<grid, WARPS * 32>>>(idx, val, n, grad);
@@ -557,15 +638,12 @@ int main(int argc, char** argv) {
 
     struct Variant { const char* name; LaunchFn fn; bool check; };
     Variant variants[] = {
-        {"hot0 same1 w32 d1", launch_hot<32, 1, 0, 1, false, 1>, true},
+        {"stream32x2", launch_stream<32, 2>, false},
         {"hot0 same0 w32 d1", launch_hot<32, 1, 0, 0, false, 1>, true},
-        {"adapt h1 a5 w32 d1", launch_adaptive<32, 1, 1, 5, 1>, true},
-        {"adapt h1 a8 w32 d1", launch_adaptive<32, 1, 1, 8, 1>, true},
-        {"adapt h2 a5 w32 d1", launch_adaptive<32, 1, 2, 5, 1>, true},
-        {"adapt h2 a6 w32 d1", launch_adaptive<32, 1, 2, 6, 1>, true},
-        {"adapt h3 a5 w32 d1", launch_adaptive<32, 1, 3, 5, 1>, true},
-        {"adapt h4 a5 w32 d1", launch_adaptive<32, 1, 4, 5, 1>, true},
-        {"adapt h2 a5 w32 d2", launch_adaptive<32, 2, 2, 5, 1>, true},
+        {"mixed none (0/4 global)", launch_mixed<32, 0>, true},
+        {"mixed 1/4 global", launch_mixed<32, 8>, true},
+        {"mixed 2/4 global", launch_mixed<32, 10>, true},
+        {"mixed 4/4 global", launch_mixed<32, 15>, true},
     };
     const char* filter = argc > 1 ? argv[1] : nullptr;
     const int iters = argc > 2 ? atoi(argv[2]) : 13;
