@@ -234,6 +234,47 @@ def also_workloads(dev, peak_gbs):
         "note": "XYZ_FLAG_TAIL_CULL: NOT the parity path -- also skips pairs with weight < exp(-28) (bounded error, "
                 "include/xyz_b200.h); the headline c4 number above is the result-preserving default"}
     out["reference_cuda_same_b200"] = reference_cuda(dev, timed, x, tp, tt, W, H, N, ms)
+    try:
+        out["reference_cpu_host_path"] = cpu_reference_other_configs()
+    except Exception as e:
+        out["reference_cpu_host_path"] = {"error": repr(e)}
+    return out
+
+
+def cpu_reference_other_configs():
+    """The reference's host-compiled path (oracle/_ref, else the port) on all host cores for the configs that are
+    not the headline: C1 at full size, C2 on a 2^22-element sample, C4 on a reduced shape scaled by the pair count
+    (the reference evaluates every (pixel, Gaussian) pair, so its cost is exactly proportional to pairs)."""
+    import numpy as np
+    import oracle_lib as orc
+    which = "ref" if orc.have_ref() else "port"
+    cores = os.cpu_count() or 1
+    out = {"kind": "reference" if which == "ref" else "port", "cores": cores}
+
+    def best(fn, reps=2):
+        ts = []
+        for _ in range(reps):
+            t0 = time.perf_counter()
+            fn()
+            ts.append(time.perf_counter() - t0)
+        return min(ts)
+
+    data = orc.lsq_data(1_000_000, 42)
+    t = best(lambda: orc.lsq_grad(data, (0.0, 1.0, 0.0, 0.0), which=which, threads=cores))
+    out["c1_lsq_1M_f64"] = {"evals_per_s": data.shape[0] / t, "ms": t * 1e3, "sample": "all 10^6 points"}
+    n = 1 << 22
+    idx, val = orc.accumulate_inputs(n, 1024, "uniform", 42)
+    t = best(lambda: orc.accumulate(idx, val, 1024, which=which, threads=cores))
+    out["c2_accumulate_uniform"] = {"elems_per_s": n / t, "ms_scaled_to_2^24": t * 1e3 * 4, "sample": "2^22 of 2^24 elements"}
+    W = H = 256
+    N = 1000
+    params, target = orc.splat_c4_scene(N, W, H, 42)
+    t = best(lambda: orc.splat(params, target, W, H, np.float32, which=which, threads=cores), reps=1)
+    pairs = N * W * H
+    full_pairs = 100_000 * 1024 * 1024
+    out["c4_splat"] = {"pairs_per_s_both_passes": pairs / t, "ms_at_sample": t * 1e3,
+                       "ms_per_iter_scaled_to_100K_1024x1024": t * 1e3 * full_pairs / pairs,
+                       "sample": f"{N} Gaussians on {W}x{H} ({pairs} pairs), scaled by pair count"}
     return out
 
 
