@@ -5,6 +5,7 @@
 // gaussian_splatting_training.cu:15-233) + TrainingConfigParser (training_config.cpp:28-146) +
 // GaussianCollection (gaussian_parameters.cu): random Gaussians (initialize_random, :27-66), then per iteration
 //   zero_gradients_gpu -> total_loss = 0 -> launch_gaussian_splatting -> read total_loss -> adam_step_gpu_individual
+// (here the zero-grad pass is fused into the Adam pass: xyz_adam_step_individual_zero_grads)
 // (training loop :127-175).  The launch goes through include/xyz_b200_compat.hpp, i.e. the reference's own
 // launch_gaussian_splatting(...) signature; zero-grad and Adam are the C-ABI replacements of the reference kernels.
 //
@@ -227,16 +228,17 @@ int main(int argc, char** argv) {
         const float lr[5] = {config.lr_center, config.lr_scale, config.lr_rotation, config.lr_color, config.lr_opacity};
         float first_loss = 0.f, last_loss = 0.f;
         double total_ms = 0.0;
+        // zero_gradients_gpu(): once up front; afterwards the Adam pass clears every gradient it has consumed
+        XYZ_CALL(xyz_zero_gradients(reinterpret_cast<xyz_gaussian_grads*>(d_grads.get()), N, nullptr));
         for (int iteration = 0; iteration < config.max_iterations; ++iteration) {
             const auto t0 = std::chrono::high_resolution_clock::now();
-            XYZ_CALL(xyz_zero_gradients(reinterpret_cast<xyz_gaussian_grads*>(d_grads.get()), N, nullptr));
             CHECK_CUDA_ERROR(cudaMemsetAsync(d_loss.get(), 0, sizeof(float), nullptr));
             launch_gaussian_splatting(d_params.get(), d_grads.get(), d_target.get(), d_output.get(), d_loss.get(), W, H, N);
             float total_loss = 0.0f;  // the reference's only synchronisation point (:150-151)
             CHECK_CUDA_ERROR(cudaMemcpy(&total_loss, d_loss.get(), sizeof(float), cudaMemcpyDeviceToHost));
-            XYZ_CALL(xyz_adam_step_individual(reinterpret_cast<xyz_gaussian_params*>(d_params.get()),
-                                              reinterpret_cast<const xyz_gaussian_grads*>(d_grads.get()), d_adam.get(), N, lr,
-                                              config.beta1, config.beta2, config.epsilon, iteration + 1, nullptr));
+            XYZ_CALL(xyz_adam_step_individual_zero_grads(reinterpret_cast<xyz_gaussian_params*>(d_params.get()),
+                                                         reinterpret_cast<xyz_gaussian_grads*>(d_grads.get()), d_adam.get(), N,
+                                                         lr, config.beta1, config.beta2, config.epsilon, iteration + 1, nullptr));
             const double ms = std::chrono::duration<double, std::milli>(std::chrono::high_resolution_clock::now() - t0).count();
             total_ms += ms;
             const float average_loss = total_loss / (static_cast<float>(H) * W);

@@ -217,6 +217,11 @@ XYZ_API int xyz_zero_gradients(xyz_gaussian_grads* gradients, int num_gaussians,
 XYZ_API int xyz_adam_step_individual(xyz_gaussian_params* params, const xyz_gaussian_grads* grads,
                              xyz_adam_state* adam, int num_gaussians, const float lr_host[5],
                              float beta1, float beta2, float epsilon, int iteration, void* stream);
+/* The same step with zero_gradients_kernel fused in: every gradient is cleared right after it has been consumed, so
+ * the training loop needs no xyz_zero_gradients call between iterations (one pass over the gradients less). */
+XYZ_API int xyz_adam_step_individual_zero_grads(xyz_gaussian_params* params, xyz_gaussian_grads* grads,
+                                        xyz_adam_state* adam, int num_gaussians, const float lr_host[5],
+                                        float beta1, float beta2, float epsilon, int iteration, void* stream);
 /* adam_step_kernel (gaussian_parameters.cu:173-224, host wrapper :322-350): single rate. */
 XYZ_API int xyz_adam_step(xyz_gaussian_params* params, const xyz_gaussian_grads* grads, xyz_adam_state* adam,
                   int num_gaussians, float learning_rate, float beta1, float beta2, float epsilon,

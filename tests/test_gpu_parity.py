@@ -501,6 +501,12 @@ def test_zero_gradients_and_adam_match_oracle():
         # FMA contraction on the device side: 1 ulp of the TERMS (|beta m| ~ 0.1, |g| ~ 1), results may cancel
         assert np.allclose(ta.cpu().numpy(), wa, rtol=1e-5, atol=2e-7)
         assert np.allclose(tp.cpu().numpy(), wp, rtol=1e-5, atol=1e-6)
+    # fused zero-grad flavour: same update, gradients cleared in the same pass
+    tp, ta, tg = dev(p), dev(a), dev(g)
+    tp2, ta2 = dev(p), dev(a)
+    x.adam_step_individual(tp, tg, ta, *lr, 0.9, 0.999, 1e-8, 7, zero_grads=True)
+    x.adam_step_individual(tp2, dev(g), ta2, *lr, 0.9, 0.999, 1e-8, 7)
+    assert torch.equal(tp, tp2) and torch.equal(ta, ta2) and (tg == 0).all()
     tp, ta = dev(p), dev(a)
     x.adam_step(tp, dev(g), ta, 0.01, 0.9, 0.999, 1e-8, 3)
     wp, wa = orc.adam_step_individual(p, g, a, (0.01,) * 5, 0.9, 0.999, 1e-8, 3)

@@ -40,6 +40,7 @@ EXPORTS = [
     "xyz_accumulate_f32", "xyz_accumulate_f64", "xyz_covproj_fwd_bwd_f32",
     "xyz_launch_gaussian_splatting", "xyz_launch_gaussian_splatting_rows", "xyz_splat_last_stats",
     "xyz_splat_debug_binning", "xyz_zero_gradients", "xyz_adam_step_individual", "xyz_adam_step",
+    "xyz_adam_step_individual_zero_grads",
 ]
 
 _lib = None
@@ -88,6 +89,7 @@ def lib() -> ctypes.CDLL:
         L.xyz_zero_gradients.argtypes = [_vp, _i, _vp]
         L.xyz_adam_step_individual.argtypes = [_vp, _vp, _vp, _i, _vp, ctypes.c_float, ctypes.c_float,
                                                ctypes.c_float, _i, _vp]
+        L.xyz_adam_step_individual_zero_grads.argtypes = L.xyz_adam_step_individual.argtypes
         L.xyz_adam_step.argtypes = [_vp, _vp, _vp, _i, ctypes.c_float, ctypes.c_float, ctypes.c_float,
                                     ctypes.c_float, _i, _vp]
         _lib = L
@@ -294,10 +296,12 @@ def zero_gradients(gradients: torch.Tensor, stream=None) -> None:
 
 
 def adam_step_individual(params, grads, adam, lr_center, lr_scale, lr_rotation, lr_color, lr_opacity, beta1=0.9,
-                         beta2=0.999, epsilon=1e-8, iteration=1, stream=None) -> None:
+                         beta2=0.999, epsilon=1e-8, iteration=1, stream=None, zero_grads=False) -> None:
+    """zero_grads=True: the gradients are cleared in the same pass (no zero_gradients call next iteration)."""
     f = torch.float32
     lr = (ctypes.c_float * 5)(lr_center, lr_scale, lr_rotation, lr_color, lr_opacity)
-    _check(lib().xyz_adam_step_individual(_dev(params, f, "params"), _dev(grads, f, "grads"), _dev(adam, f, "adam"),
+    fn = lib().xyz_adam_step_individual_zero_grads if zero_grads else lib().xyz_adam_step_individual
+    _check(fn(_dev(params, f, "params"), _dev(grads, f, "grads"), _dev(adam, f, "adam"),
                                           params.shape[0], lr, beta1, beta2, epsilon, iteration, _stream(stream)),
            "xyz_adam_step_individual")
 

@@ -37,8 +37,8 @@ __device__ __forceinline__ void adam_slot(int j, int& group, int& m_off, int& v_
 }
 
 __global__ void __launch_bounds__(256)
-    adam_kernel(float* __restrict__ params, const float* __restrict__ grads, float* __restrict__ adam, long long n_comp,
-                AdamLr lr, float beta1, float beta2, float eps) {
+    adam_kernel(float* __restrict__ params, const float* grads, float* __restrict__ adam, long long n_comp, AdamLr lr,
+                float beta1, float beta2, float eps, float* grads_to_zero /* == grads or nullptr */) {
     const long long f = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x;
     if (f >= n_comp) return;
     const long long g = f / 9;
@@ -52,10 +52,14 @@ __global__ void __launch_bounds__(256)
     st[m_off] = m;
     st[v_off] = v;
     params[f] -= lr.lr_corrected[group] * m / (sqrtf(v) + eps);
+    // fused zero_gradients_kernel (gaussian_parameters.cu:227-241): the gradient has been consumed, the next
+    // iteration's kernels accumulate into zeros without a separate pass
+    if (grads_to_zero) grads_to_zero[f] = 0.f;
 }
 
 int adam_launch(xyz_gaussian_params* params, const xyz_gaussian_grads* grads, xyz_adam_state* adam, int n,
-                const float lr[5], float beta1, float beta2, float eps, int iteration, void* stream) {
+                const float lr[5], float beta1, float beta2, float eps, int iteration, void* stream,
+                xyz_gaussian_grads* grads_to_zero = nullptr) {
     if (n < 0 || iteration < 1) return XYZ_ERR_INVALID_ARGUMENT;
     if (n == 0) return 0;
     if (!params || !grads || !adam) return XYZ_ERR_INVALID_ARGUMENT;
@@ -69,7 +73,7 @@ int adam_launch(xyz_gaussian_params* params, const xyz_gaussian_grads* grads, xy
     adam_kernel<<<grid, 256, 0, static_cast<cudaStream_t>(stream)>>>(reinterpret_cast<float*>(params),
                                                                      reinterpret_cast<const float*>(grads),
                                                                      reinterpret_cast<float*>(adam), n_comp, l, beta1,
-                                                                     beta2, eps);
+                                                                     beta2, eps, reinterpret_cast<float*>(grads_to_zero));
     count_launch();
     return last_error();
 }
@@ -114,4 +118,11 @@ extern "C" int xyz_adam_step(xyz_gaussian_params* params, const xyz_gaussian_gra
                              int iteration, void* stream) {
     const float lr[5] = {learning_rate, learning_rate, learning_rate, learning_rate, learning_rate};
     return xyzb::adam_launch(params, grads, adam, num_gaussians, lr, beta1, beta2, epsilon, iteration, stream);
+}
+
+extern "C" int xyz_adam_step_individual_zero_grads(xyz_gaussian_params* params, xyz_gaussian_grads* grads,
+                                                   xyz_adam_state* adam, int num_gaussians, const float lr_host[5],
+                                                   float beta1, float beta2, float epsilon, int iteration, void* stream) {
+    if (!lr_host) return XYZ_ERR_INVALID_ARGUMENT;
+    return xyzb::adam_launch(params, grads, adam, num_gaussians, lr_host, beta1, beta2, epsilon, iteration, stream, grads);
 }
