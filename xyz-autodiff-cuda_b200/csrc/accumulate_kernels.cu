@@ -170,11 +170,12 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM)
 //   * when half a batch or more lost (the reference's own all-threads-one-parameter pattern) the warp turns on
 //     a register-level check "whole batch on one bin" (one shuffle + vote, then a shuffle-tree sum and ONE
 //     table update); it turns itself off at the first batch that fails the check.
-// Which duplicate wins the tag store is the hardware's choice, so this path is not the deterministic one.
+// Which duplicate wins the tag store is the hardware's choice; the kDet flavour (XYZ_FLAG_DETERMINISTIC) therefore
+// never lets the winner add first: every duplicate group is folded in lane order and added once (see below).
 // ncu (profiles/): 15.4 shared-memory wavefronts per batch, 14 of them the 4 table/tag accesses at the
 // ~3.5-way bank conflict degree of 32 random banks; l1tex 93 % busy -- the kernel sits on the shared-memory
 // pipe, 41 us for 2^24 uniform ids against 29 us for a kernel that only streams idx+val with this grid.
-template <class T, int kWarpsT, bool kImplicit, bool kRows>
+template <class T, int kWarpsT, bool kImplicit, bool kRows, bool kDet>
 __global__ void __launch_bounds__(kWarpsT * 32, 1)
     accumulate_tagged_kernel(const int32_t* __restrict__ idx, const T* __restrict__ val, long long n, T* grad, int k,
                              T* partial_rows, int aligned) {
@@ -207,6 +208,29 @@ __global__ void __launch_bounds__(kWarpsT * 32, 1)
         }
         if (valid) tag[id] = static_cast<uint8_t>(lane);
         __syncwarp();
+        if constexpr (kDet) {
+            // Deterministic flavour: WHICH duplicate's tag store landed must not matter.  rep = the lane whose store
+            // landed (the same value for every member of a duplicate group); groups with losers are folded in lane
+            // order by the fixed shuffle tree and added once by their lowest lane; everybody else adds directly.
+            const unsigned int rep = valid ? tag[id] : static_cast<unsigned int>(lane);
+            const bool mine = valid && rep != static_cast<unsigned int>(lane);
+            const unsigned lost = __ballot_sync(kFull, mine);
+            if (lost == 0u) {
+                if (valid) table[id] += v;
+                __syncwarp();
+                return;
+            }
+            same_mode = __popc(lost) >= 16;
+            const unsigned repmask = __reduce_or_sync(kFull, mine ? (1u << rep) : 0u);
+            const bool ingroup = mine || ((repmask >> lane) & 1u);
+            if (valid && !ingroup) table[id] += v;
+            unsigned peers = __match_any_sync(kFull, ingroup ? static_cast<int>(rep) : 64);
+            if (!ingroup) peers = 1u << lane;
+            v = reduce_peers(peers, v, lane);
+            if (ingroup && lane == __ffs(peers) - 1) table[id] += v;
+            __syncwarp();
+            return;
+        }
         const bool won = valid && tag[id] == lane;
         if (won) table[id] += v;
         const bool mine = valid && !won;
@@ -356,13 +380,26 @@ int launch_tables(const int32_t* idx, const T* val, long long n, T* grad, int k,
 }
 
 template <class T, int W, bool kImplicit>
-int launch_tagged(const int32_t* idx, const T* val, long long n, T* grad, int k, cudaStream_t st) {
+int launch_tagged(const int32_t* idx, const T* val, long long n, T* grad, int k, cudaStream_t st, bool deterministic) {
     const size_t smem = static_cast<size_t>(W) * k * (sizeof(T) + 1);
     const long long n_chunks = (n + 127) / 128;
     const long long want = (n_chunks + W - 1) / W;
     const int sms = sm_count();
     const int grid = static_cast<int>(want < sms ? want : sms);  // one CTA per SM (the tables fill shared memory)
-    auto kern = accumulate_tagged_kernel<T, W, kImplicit, false>;
+    if (deterministic) {
+        // rows per CTA (static element -> warp -> CTA assignment, lane-ordered duplicate folding), summed in CTA order
+        void* scratch = nullptr;
+        int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(grid) * k * sizeof(T), &scratch);
+        if (err) return err;
+        T* rows = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+        auto kern = accumulate_tagged_kernel<T, W, kImplicit, true, true>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        kern<<<grid, W * 32, smem, st>>>(idx, val, n, grad, k, rows, 1);
+        accumulate_finish_kernel<T><<<(k + 255) / 256, 256, 0, st>>>(rows, grid, grad, k);
+        count_launch(2);
+        return last_error();
+    }
+    auto kern = accumulate_tagged_kernel<T, W, kImplicit, false, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     kern<<<grid, W * 32, smem, st>>>(idx, val, n, grad, k, nullptr, 1);
     count_launch();
@@ -377,7 +414,7 @@ int launch_tagged_rows(const int32_t* idx, const float* val, long long n, int k,
     const long long want = (n_chunks + W - 1) / W;
     const int sms = sm_count();
     const int grid = static_cast<int>(want < sms ? want : sms);
-    auto kern = accumulate_tagged_kernel<float, W, kImplicit, true>;
+    auto kern = accumulate_tagged_kernel<float, W, kImplicit, true, false>;
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
     kern<<<grid, W * 32, smem, st>>>(idx, val, n, nullptr, k, rows,
                                      (aligned16(val) && (kImplicit || aligned16(idx))) ? 1 : 0);
@@ -387,13 +424,14 @@ int launch_tagged_rows(const int32_t* idx, const float* val, long long n, int k,
 }
 
 template <class T, bool kImplicit>
-int launch_tagged_any(const int32_t* idx, const T* val, long long n, T* grad, int k, cudaStream_t st, bool* done) {
+int launch_tagged_any(const int32_t* idx, const T* val, long long n, T* grad, int k, cudaStream_t st, bool deterministic,
+                      bool* done) {
     const size_t per_warp = static_cast<size_t>(k) * (sizeof(T) + 1);
     const size_t budget = 200 * 1024;
     *done = true;
-    if (per_warp * 32 <= budget) return launch_tagged<T, 32, kImplicit>(idx, val, n, grad, k, st);
-    if (per_warp * 16 <= budget) return launch_tagged<T, 16, kImplicit>(idx, val, n, grad, k, st);
-    if (per_warp * 8 <= budget) return launch_tagged<T, 8, kImplicit>(idx, val, n, grad, k, st);
+    if (per_warp * 32 <= budget) return launch_tagged<T, 32, kImplicit>(idx, val, n, grad, k, st, deterministic);
+    if (per_warp * 16 <= budget) return launch_tagged<T, 16, kImplicit>(idx, val, n, grad, k, st, deterministic);
+    if (per_warp * 8 <= budget) return launch_tagged<T, 8, kImplicit>(idx, val, n, grad, k, st, deterministic);
     *done = false;
     return 0;
 }
@@ -408,11 +446,12 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool deterministic = (flags & XYZ_FLAG_DETERMINISTIC) != 0;
     const bool vec_ok = aligned16(val) && (implicit || aligned16(idx));
-    // tagged tables (fast path; not run-to-run deterministic): as many warps as 200 KB of shared memory hold
-    if (!deterministic && vec_ok && n >= (1 << 16)) {
+    // tagged tables (fast path; with XYZ_FLAG_DETERMINISTIC its lane-ordered flavour): as many warps as 200 KB of
+    // shared memory hold
+    if (vec_ok && n >= (1 << 16)) {
         bool done = false;
-        const int err = implicit ? launch_tagged_any<T, true>(idx, val, n, grad, k, st, &done)
-                                 : launch_tagged_any<T, false>(idx, val, n, grad, k, st, &done);
+        const int err = implicit ? launch_tagged_any<T, true>(idx, val, n, grad, k, st, deterministic, &done)
+                                 : launch_tagged_any<T, false>(idx, val, n, grad, k, st, deterministic, &done);
         if (done) return err;
     }
     const size_t smem = static_cast<size_t>(kWarps) * k * sizeof(T);
