@@ -304,6 +304,39 @@ def test_accumulate_deterministic_is_bit_identical_and_variants():
     assert np.allclose(grad.cpu().numpy() - 1.0, orc.accumulate_exact(idx, val, k), atol=1e-2)
 
 
+def test_accumulate_striped_tables_variants():
+    """The lane-striped fast path (fp32, aligned, n >= 2^16): every table count T (12, 6, 4, 3, 2 tables per SM), partial
+    last unit, implicit ids with K below and above the 128-element row, invalid ids, all-invalid input, and bit-identical
+    deterministic results for every id distribution."""
+    def tol_ok(got, idx, val, k):
+        exact = orc.accumulate_exact(idx, val, k)
+        abs_sum = orc.accumulate_exact(idx, np.abs(val), k)
+        return (np.abs(got - exact) <= 1e-4 * abs_sum + 1e-30).all()
+    for kk, n in ((1, 70_001), (7, 65_536), (200, 131_072 + 5), (300, 100_000), (500, 99_999), (800, 1 << 17), (1024, 600_000),
+                  (1025, 1 << 17), (1500, 250_001), (1771, 1 << 17)):
+        for dist in ("uniform", "zipf", "same"):
+            i, v = orc.accumulate_inputs(n, kk, dist, seed=kk + n)
+            assert tol_ok(run_acc(i, v, kk), i, v, kk), (kk, n, dist)
+            a = run_acc(i, v, kk, x.FLAG_DETERMINISTIC)
+            b = run_acc(i, v, kk, x.FLAG_DETERMINISTIC)
+            assert np.array_equal(a, b) and tol_ok(a, i, v, kk), (kk, n, dist)
+        _, v = orc.accumulate_inputs(n, kk, "uniform", seed=3)
+        got = run_acc(None, v, kk)
+        assert (np.abs(got - orc.accumulate_exact(None, v, kk)) <= 1e-4 * orc.accumulate_exact(None, np.abs(v), kk) + 1e-30).all(), kk
+    # nothing but invalid ids: grad stays untouched
+    n, k = 1 << 17, 1024
+    grad = torch.full((k,), 2.5, device=DEV)
+    x.accumulate(torch.full((n,), -1, dtype=torch.int32, device=DEV), torch.ones(n, device=DEV), grad)
+    assert (grad.cpu().numpy() == 2.5).all()
+    grad = torch.full((k,), 2.5, device=DEV)
+    x.accumulate(torch.full((n,), k, dtype=torch.int32, device=DEV), torch.ones(n, device=DEV), grad, x.FLAG_DETERMINISTIC)
+    assert (grad.cpu().numpy() == 2.5).all()
+    # integer-valued inputs: every partial sum is exact, so the result must equal the exact sum bit for bit
+    i, _ = orc.accumulate_inputs(1 << 22, k, "zipf", seed=5)
+    v = (np.arange(1 << 22) % 7 - 3).astype(np.float32)
+    assert np.array_equal(run_acc(i, v, k).astype(np.float64), orc.accumulate_exact(i, v, k))
+
+
 # ---------------------------------------------------------------------------------------------------
 # C4 splat
 # ---------------------------------------------------------------------------------------------------

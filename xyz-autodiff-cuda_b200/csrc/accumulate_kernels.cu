@@ -315,6 +315,245 @@ __global__ void __launch_bounds__(kWarpsT * 32, 1)
     }
 }
 
+
+// ---- lane-striped tables shared by warps that take turns: the fp32 fast path ------------------------------------
+// ncu on the tagged kernel above: 15.4 shared-memory wavefronts per batch of 32 elements, 14 of them the tag / table
+// accesses at the ~3.5-way conflict degree of 32 random banks; 43 us for 2^24 uniform ids, 76 us for Zipf ids.
+// This kernel removes both the tags and the random bank pattern:
+//   * a table holds 16 COPIES of every bin, copy = lane & 15, word (id * 16 + copy): lanes L and L ^ 16 are the only
+//     two lanes of a warp that can touch the same word, and the 16 lanes of a half-warp always hit 16 different
+//     banks => an update costs 2 + 2 wavefronts, and duplicates are found with ONE shuffle of the id;
+//   * 64 B per bin => T = 3 tables per SM at K = 1024.  A table is shared by a GROUP of GW = 12 / T warps that take
+//     turns (token = a ring of mbarriers, try_wait sleeps in hardware).  While one warp holds the token the others
+//     load their next unit (16 batches = 512 elements, straight into registers, prefetch depth 1) and resolve
+//     duplicates in registers;
+//   * duplicates are resolved exactly inside groups of two batches (stripe_front2: per lane pair the first
+//     occurrence of an id absorbs the later ones in a fixed order, absorbed items are pointed at a dummy row), so a
+//     group's two updates never touch the same word and issue back to back: LDS LDS FADD FADD STS STS, no votes, no
+//     branches, no match.any.  The cost is the same for every id distribution;
+//   * element -> (CTA, table, turn) is static and every sum has a fixed order, so per-CTA rows are bit-identical run
+//     to run: XYZ_FLAG_DETERMINISTIC only swaps the final REDs for rows + the finishing kernel.
+// Measured (dev/accum_lab.cu, B200): 30.9 us for 2^24 uniform, Zipf(1.2) and all-equal ids alike = the time of a
+// kernel that only streams idx + val with a one-CTA-per-SM grid.
+constexpr int kStripeWarps = 12;
+constexpr int kStripeUnit = 512;  // elements per warp turn: 16 batches of 32
+
+__device__ __forceinline__ void stripe_front2(unsigned base, int k, int lower, int a0, int a1, int p0, int p1, float v0,
+                                              float v1, float pv0, float pv1, unsigned& addr0, unsigned& addr1,
+                                              float& acc0, float& acc1) {
+    // items in canonical order: (batch 0, lower lane) (batch 0, upper lane) (batch 1, lower) (batch 1, upper);
+    // a* / v* are this lane's, p* / pv* the partner lane's (lane ^ 16).
+    asm("{\n"
+        ".reg .pred lo, e00, e01, e0p1, e1p0, e11, ok0, ok1, t;\n"
+        ".reg .s32 s0, s1;\n"
+        "setp.ne.s32 lo, %12, 0;\n"
+        "setp.eq.s32 e00, %6, %4;\n"
+        "setp.eq.s32 e01, %5, %4;\n"
+        "setp.eq.s32 e0p1, %7, %4;\n"
+        "setp.eq.s32 e1p0, %6, %5;\n"
+        "setp.eq.s32 e11, %7, %5;\n"
+        "mov.f32 %2, %8;\n"
+        "mov.f32 %3, %9;\n"
+        "and.pred t, e00, lo;\n"
+        "@t add.f32 %2, %2, %10;\n"
+        "@e01 add.f32 %2, %2, %9;\n"
+        "@e0p1 add.f32 %2, %2, %11;\n"
+        "and.pred t, e11, lo;\n"
+        "@t add.f32 %3, %3, %11;\n"
+        "setp.lt.u32 ok0, %4, %13;\n"   // valid id and (lower lane or the partner's batch-0 id differs)
+        "not.pred t, e00;\n"
+        "or.pred t, t, lo;\n"
+        "and.pred ok0, ok0, t;\n"
+        "setp.lt.u32 ok1, %5, %13;\n"   // valid, not absorbed by either batch-0 item, and first of batch 1
+        "not.pred t, e11;\n"
+        "or.pred t, t, lo;\n"
+        "and.pred ok1, ok1, t;\n"
+        "not.pred t, e01;\n"
+        "and.pred ok1, ok1, t;\n"
+        "not.pred t, e1p0;\n"
+        "and.pred ok1, ok1, t;\n"
+        "selp.s32 s0, %4, %13, ok0;\n"  // absorbed / invalid items go to the dummy row k
+        "selp.s32 s1, %5, %13, ok1;\n"
+        "shl.b32 s0, s0, 6;\n"
+        "shl.b32 s1, s1, 6;\n"
+        "add.s32 %0, s0, %14;\n"
+        "add.s32 %1, s1, %14;\n"
+        "}\n"
+        : "=r"(addr0), "=r"(addr1), "=f"(acc0), "=f"(acc1)
+        : "r"(a0), "r"(a1), "r"(p0), "r"(p1), "f"(v0), "f"(v1), "f"(pv0), "f"(pv1), "r"(lower), "r"(k), "r"(base));
+}
+__device__ __forceinline__ float lds_f32(unsigned addr) {
+    float v;
+    asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f32(unsigned addr, float v) {
+    asm volatile("st.shared.f32 [%0], %1;" ::"r"(addr), "f"(v) : "memory");
+}
+
+template <bool kImplicit, bool kRows>
+__global__ void __launch_bounds__(kStripeWarps * 32, 1)
+    accumulate_striped_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, long long n, float* grad,
+                              int k, float* partial_rows, int T) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    constexpr int kThreadsS = kStripeWarps * 32;
+    const int GW = kStripeWarps / T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = warp % T, j = warp / T;
+    const int lower = lane < 16 ? 1 : 0;
+    const size_t table_floats = static_cast<size_t>(k + 1) * 16;  // row k = dummy
+    float* tables = reinterpret_cast<float*>(smem_raw);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(T) * table_floats * 4);  // [T][GW]
+    if (tid == 0) {
+        for (int i = 0; i < kStripeWarps; ++i) mbar_init(bars + i, 1);
+        mbar_fence_init();
+        for (int i = 0; i < T; ++i) mbar_arrive(bars + i * GW);  // the first warp of every table starts with the token
+    }
+    const long long n_units = (n + kStripeUnit - 1) / kStripeUnit;
+    const long long nstreams = static_cast<long long>(gridDim.x) * T;
+    const long long stream = static_cast<long long>(blockIdx.x) * T + t;
+    int na[16];
+    float nv[16];
+    auto load = [&](long long u) {
+        const long long e0 = u * kStripeUnit + lane * 4;
+        if ((u + 1) * kStripeUnit <= n) {
+            const float4* gv = reinterpret_cast<const float4*>(val + e0);
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+                const float4 f = __ldcs(gv + 32 * m);
+                nv[4 * m] = f.x; nv[4 * m + 1] = f.y; nv[4 * m + 2] = f.z; nv[4 * m + 3] = f.w;
+            }
+            if constexpr (kImplicit) {
+                const unsigned uk = static_cast<unsigned>(k);
+                const unsigned r0 = static_cast<unsigned>(static_cast<unsigned long long>(e0) % uk);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    unsigned r = (r0 + 128u * m) % uk;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        na[4 * m + c] = static_cast<int>(r);
+                        r = (r + 1u == uk) ? 0u : r + 1u;
+                    }
+                }
+            } else {
+                const int4* gi = reinterpret_cast<const int4*>(idx + e0);
+#pragma unroll
+                for (int m = 0; m < 4; ++m) {
+                    const int4 q = __ldcs(gi + 32 * m);
+                    na[4 * m] = q.x; na[4 * m + 1] = q.y; na[4 * m + 2] = q.z; na[4 * m + 3] = q.w;
+                }
+            }
+        } else {  // the last, partial unit
+#pragma unroll
+            for (int m = 0; m < 4; ++m) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const long long e = e0 + 128 * m + c;
+                    const bool in = e < n;
+                    na[4 * m + c] = in ? (kImplicit ? static_cast<int>(e % k) : __ldg(idx + e)) : -1;
+                    nv[4 * m + c] = in ? __ldg(val + e) : 0.f;
+                }
+            }
+        }
+    };
+    long long u = stream + static_cast<long long>(j) * nstreams;
+    const long long ustep = static_cast<long long>(GW) * nstreams;
+    if (u < n_units) load(u);
+    {
+        float4* t4 = reinterpret_cast<float4*>(tables);
+        const int n4 = static_cast<int>(T * table_floats / 4);
+        for (int i = tid; i < n4; i += kThreadsS) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const unsigned base = smem_u32(tables + static_cast<size_t>(t) * table_floats + (lane & 15));
+    uint64_t* my_bar = bars + t * GW + j;
+    uint64_t* next_bar = bars + t * GW + (j + 1 == GW ? 0 : j + 1);
+    unsigned round = 0;
+    for (; u < n_units; u += ustep, ++round) {
+        int a[16];
+        float v[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) {
+            a[i] = na[i];
+            v[i] = nv[i];
+        }
+        if (u + ustep < n_units) load(u + ustep);
+        unsigned addr[16];
+        float acc[16];
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const int p0 = __shfl_xor_sync(kFull, a[2 * g], 16), p1 = __shfl_xor_sync(kFull, a[2 * g + 1], 16);
+            const float pv0 = __shfl_xor_sync(kFull, v[2 * g], 16), pv1 = __shfl_xor_sync(kFull, v[2 * g + 1], 16);
+            stripe_front2(base, k, lower, a[2 * g], a[2 * g + 1], p0, p1, v[2 * g], v[2 * g + 1], pv0, pv1, addr[2 * g],
+                          addr[2 * g + 1], acc[2 * g], acc[2 * g + 1]);
+        }
+        mbar_wait(my_bar, round & 1u);  // my turn on table t
+#pragma unroll
+        for (int g = 0; g < 8; ++g) {
+            const float t0 = lds_f32(addr[2 * g]);
+            const float t1 = lds_f32(addr[2 * g + 1]);
+            sts_f32(addr[2 * g], t0 + acc[2 * g]);
+            sts_f32(addr[2 * g + 1], t1 + acc[2 * g + 1]);
+            __syncwarp();  // lane L ^ 16 may read these words in the next group
+        }
+        if (lane == 0) mbar_arrive(next_bar);  // release: ordered after the warp's stores by the __syncwarp above
+    }
+    __syncthreads();
+    // fold: bin b = 16 copies x T tables, fixed order; the float4 order is rotated by b / 2 so that a quarter-warp
+    // reads eight different bank groups
+    for (int b = tid; b < k; b += kThreadsS) {
+        float s = 0.f;
+        for (int w = 0; w < T; ++w) {
+            const float4* row =
+                reinterpret_cast<const float4*>(tables + static_cast<size_t>(w) * table_floats + static_cast<size_t>(b) * 16);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const float4 x = row[(q + (b >> 1)) & 3];
+                s += (x.x + x.y) + (x.z + x.w);
+            }
+        }
+        if constexpr (kRows) {
+            partial_rows[static_cast<size_t>(blockIdx.x) * k + b] = s;
+        } else {
+            if (s != 0.f) atomicAdd(grad + b, s);
+        }
+    }
+}
+
+// number of striped tables that fit one SM for K bins (a divisor of kStripeWarps), 0 = does not fit twice
+inline int stripe_tables(int k) {
+    const size_t budget = 227 * 1024 - 256;
+    const size_t per_table = (static_cast<size_t>(k) + 1) * 64;
+    const int choices[5] = {12, 6, 4, 3, 2};
+    for (int c : choices)
+        if (per_table * c <= budget) return c;
+    return 0;
+}
+
+// rows == nullptr: REDs into grad; else one row per CTA (returns the number of rows in *n_rows)
+template <bool kImplicit>
+int launch_striped(const int32_t* idx, const float* val, long long n, float* grad, int k, cudaStream_t st, float* rows,
+                   int* n_rows) {
+    const int T = stripe_tables(k);
+    const size_t smem = static_cast<size_t>(T) * (k + 1) * 64 + kStripeWarps * 8;
+    const long long n_units = (n + kStripeUnit - 1) / kStripeUnit;
+    const long long want = (n_units + kStripeWarps - 1) / kStripeWarps;
+    const int sms = sm_count();
+    const int grid = static_cast<int>(want < sms ? want : sms);
+    if (rows) {
+        auto kern = accumulate_striped_kernel<kImplicit, true>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        kern<<<grid, kStripeWarps * 32, smem, st>>>(idx, val, n, grad, k, rows, T);
+    } else {
+        auto kern = accumulate_striped_kernel<kImplicit, false>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        kern<<<grid, kStripeWarps * 32, smem, st>>>(idx, val, n, grad, k, nullptr, T);
+    }
+    count_launch();
+    if (n_rows) *n_rows = grid;
+    return last_error();
+}
+
 // Multi-GPU finish (ONE CTA): add the CTAs' rows in CTA order, store the result into every rank's mailbox over
 // NVLink, publish the sequence number, wait for all ranks, add the rows in rank order: grad[b] += global sum.
 __global__ void __launch_bounds__(1024)
@@ -448,6 +687,25 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
     const bool vec_ok = aligned16(val) && (implicit || aligned16(idx));
     // tagged tables (fast path; with XYZ_FLAG_DETERMINISTIC its lane-ordered flavour): as many warps as 200 KB of
     // shared memory hold
+    if constexpr (sizeof(T) == 4) {
+        // lane-striped tables with turn-taking warps: fp32, aligned arrays, K small enough for two tables per SM
+        if (vec_ok && n >= (1 << 16) && stripe_tables(k) > 0) {
+            float* rows = nullptr;
+            int n_rows = 0;
+            if (deterministic) {
+                void* scratch = nullptr;
+                const int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * k * sizeof(float), &scratch);
+                if (err) return err;
+                rows = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+            }
+            const int err = implicit ? launch_striped<true>(idx, val, n, grad, k, st, rows, &n_rows)
+                                     : launch_striped<false>(idx, val, n, grad, k, st, rows, &n_rows);
+            if (err || !deterministic) return err;
+            accumulate_finish_kernel<float><<<(k + 255) / 256, 256, 0, st>>>(rows, n_rows, grad, k);
+            count_launch();
+            return last_error();
+        }
+    }
     if (vec_ok && n >= (1 << 16)) {
         bool done = false;
         const int err = implicit ? launch_tagged_any<T, true>(idx, val, n, grad, k, st, deterministic, &done)
@@ -516,7 +774,10 @@ extern "C" int xyz_accumulate_f32_allreduce(const int32_t* idx, const float* val
         // tables of 8 / 16 / 32 warps as shared memory allows (K <= 4096 always fits 8 warps); unaligned slices
         // (shard boundaries) take the same kernel with scalar loads
         const size_t per_warp = static_cast<size_t>(k) * 5;
-        if (per_warp * 32 <= 200 * 1024)
+        if (n >= (1 << 16) && aligned16(val) && (implicit || aligned16(idx)) && stripe_tables(k) > 0)
+            err = implicit ? launch_striped<true>(idx, val, n, nullptr, k, st, rows, &n_rows)
+                           : launch_striped<false>(idx, val, n, nullptr, k, st, rows, &n_rows);
+        else if (per_warp * 32 <= 200 * 1024)
             err = implicit ? launch_tagged_rows<32, true>(idx, val, n, k, st, rows, &n_rows)
                            : launch_tagged_rows<32, false>(idx, val, n, k, st, rows, &n_rows);
         else if (per_warp * 16 <= 200 * 1024)
