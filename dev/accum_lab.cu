@@ -1210,7 +1210,7 @@ static void launch_stripe6(const int32_t* idx, const float* val, long long n, fl
 }
 
 int main(int argc, char** argv) {
-    const long long n = 1LL << 24;
+    const long long n = 1LL << (argc > 3 ? atoi(argv[3]) : 24);
     const int k = 1024;
     cudaDeviceProp prop;
     CK(cudaGetDeviceProperties(&prop, 0));
@@ -1223,7 +1223,9 @@ int main(int argc, char** argv) {
     make_case(cases[2], "same", n, k, 2);
 
     int32_t* d_idx; float* d_val; float* d_grad; unsigned char* d_flush;
-    CK(cudaMalloc(&d_idx, n * 4)); CK(cudaMalloc(&d_val, n * 4)); CK(cudaMalloc(&d_grad, k * 4));
+    const int mode = argc > 4 ? atoi(argv[4]) : 0;  // 0 write flush, 1 write + read flush, 2 rotate over 8 input copies (no flush)
+    const int copies = mode == 2 ? 8 : 1;
+    CK(cudaMalloc(&d_idx, n * 4 * copies)); CK(cudaMalloc(&d_val, n * 4 * copies)); CK(cudaMalloc(&d_grad, k * 4));
     const size_t flush_bytes = 256u << 20;
     CK(cudaMalloc(&d_flush, flush_bytes));
     cudaEvent_t e0, e1;
@@ -1244,18 +1246,22 @@ int main(int argc, char** argv) {
     const char* filter = argc > 1 ? argv[1] : nullptr;
     const int iters = argc > 2 ? atoi(argv[2]) : 13;
     for (Case& c : cases) {
-        CK(cudaMemcpy(d_idx, c.idx.data(), n * 4, cudaMemcpyHostToDevice));
-        CK(cudaMemcpy(d_val, c.val.data(), n * 4, cudaMemcpyHostToDevice));
+        for (int r = 0; r < copies; ++r) {
+            CK(cudaMemcpy(d_idx + r * n, c.idx.data(), n * 4, cudaMemcpyHostToDevice));
+            CK(cudaMemcpy(d_val + r * n, c.val.data(), n * 4, cudaMemcpyHostToDevice));
+        }
         for (const Variant& v : variants) {
             if (filter && !strstr(v.name, filter)) continue;
             std::vector<float> ts;
             std::vector<float> got(k);
             double worst = 0;
             for (int it = 0; it < iters; ++it) {
-                CK(cudaMemset(d_flush, it, flush_bytes));
+                if (mode != 2) CK(cudaMemset(d_flush, it, flush_bytes));
+                if (mode == 1)  // read it back: evicts the dirty lines the memset left in L2
+                    stream_only_kernel<32, 2><<<sms * 2, 1024>>>(reinterpret_cast<const int32_t*>(d_flush), reinterpret_cast<const float*>(d_flush + flush_bytes / 2), static_cast<long long>(flush_bytes / 8), d_grad);
                 CK(cudaMemset(d_grad, 0, k * 4));
                 CK(cudaEventRecord(e0));
-                v.fn(d_idx, d_val, n, d_grad, k, sms);
+                v.fn(d_idx + (it % copies) * n, d_val + (it % copies) * n, n, d_grad, k, sms);
                 CK(cudaEventRecord(e1));
                 CK(cudaDeviceSynchronize());
                 CK(cudaGetLastError());

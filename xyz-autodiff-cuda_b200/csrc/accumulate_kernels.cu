@@ -574,14 +574,32 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
-// deterministic finish: grad[b] += sum over rows in CTA order
+// deterministic finish: grad[b] += sum over the rows in a FIXED order.  Block = 32 bins x 8 row groups: thread (b, g)
+// adds rows g, g + 8, g + 16, ... (coalesced 128-byte reads per row), the 8 group sums are then added in group order.
 template <class T>
-__global__ void accumulate_finish_kernel(const T* __restrict__ rows, int n_rows, T* grad, int k) {
-    const int b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= k) return;
+__global__ void __launch_bounds__(256) accumulate_finish_kernel(const T* __restrict__ rows, int n_rows, T* grad, int k) {
+    __shared__ T part[8][33];
+    const int bl = threadIdx.x & 31, g = threadIdx.x >> 5;
+    const int b = blockIdx.x * 32 + bl;
     T s = T(0);
-    for (int r = 0; r < n_rows; ++r) s += rows[static_cast<size_t>(r) * k + b];
-    grad[b] += s;
+    if (b < k) {
+        T s0 = T(0), s1 = T(0);
+        int r = g;
+        for (; r + 8 < n_rows; r += 16) {
+            s0 += rows[static_cast<size_t>(r) * k + b];
+            s1 += rows[static_cast<size_t>(r + 8) * k + b];
+        }
+        if (r < n_rows) s0 += rows[static_cast<size_t>(r) * k + b];
+        s = s0 + s1;
+    }
+    part[g][bl] = s;
+    __syncthreads();
+    if (g == 0 && b < k) {
+        T t = part[0][bl];
+#pragma unroll
+        for (int q = 1; q < 8; ++q) t += part[q][bl];
+        grad[b] += t;
+    }
 }
 
 // K too large for shared-memory tables: coalesced loads + native global REDs (what the reference does,
@@ -607,7 +625,7 @@ int launch_tables(const int32_t* idx, const T* val, long long n, T* grad, int k,
         auto kern = accumulate_kernel<T, kVec, kImplicit, true>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         kern<<<grid, kThreads, smem, st>>>(idx, val, n, grad, k, rows);
-        accumulate_finish_kernel<T><<<(k + 255) / 256, 256, 0, st>>>(rows, grid, grad, k);
+        accumulate_finish_kernel<T><<<(k + 31) / 32, 256, 0, st>>>(rows, grid, grad, k);
         count_launch(2);
     } else {
         auto kern = accumulate_kernel<T, kVec, kImplicit, false>;
@@ -634,7 +652,7 @@ int launch_tagged(const int32_t* idx, const T* val, long long n, T* grad, int k,
         auto kern = accumulate_tagged_kernel<T, W, kImplicit, true, true>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
         kern<<<grid, W * 32, smem, st>>>(idx, val, n, grad, k, rows, 1);
-        accumulate_finish_kernel<T><<<(k + 255) / 256, 256, 0, st>>>(rows, grid, grad, k);
+        accumulate_finish_kernel<T><<<(k + 31) / 32, 256, 0, st>>>(rows, grid, grad, k);
         count_launch(2);
         return last_error();
     }
@@ -701,7 +719,7 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
             const int err = implicit ? launch_striped<true>(idx, val, n, grad, k, st, rows, &n_rows)
                                      : launch_striped<false>(idx, val, n, grad, k, st, rows, &n_rows);
             if (err || !deterministic) return err;
-            accumulate_finish_kernel<float><<<(k + 255) / 256, 256, 0, st>>>(rows, n_rows, grad, k);
+            accumulate_finish_kernel<float><<<(k + 31) / 32, 256, 0, st>>>(rows, n_rows, grad, k);
             count_launch();
             return last_error();
         }

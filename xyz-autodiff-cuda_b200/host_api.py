@@ -20,7 +20,7 @@ class CovprojHostPipeline:
     WIDTHS_IN = (6, 9, 6, 3)
     WIDTHS_OUT = (3, 6, 9, 6)
 
-    def __init__(self, device: torch.device, chunk_elems: int = 1 << 22, depth: int = 3):
+    def __init__(self, device: torch.device, chunk_elems: int = 1 << 20, depth: int = 4):
         self.device = device
         self.chunk = chunk_elems
         self.depth = depth
