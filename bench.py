@@ -202,6 +202,19 @@ def also_workloads(dev, peak_gbs):
         out[f"c2_accumulate_2^24_{dist}"] = {"elems_per_s": n / (ms / 1e3), "ms": ms, "gbs": 8 * n / (ms / 1e3) / 1e9,
                                              "hbm_frac": 8 * n / (ms / 1e3) / 1e9 / peak_gbs,
                                              "l2": "flushed between iterations"}
+    # C3 variant B: one shared W, per-element adjoints of W accumulated into 9 gradients; 2^26 elements (8 GB > L2)
+    n3 = 1 << 26
+    ins3 = [torch.empty((n3, w), device=dev).uniform_(-1, 1) for w in (6, 6, 3)]
+    outs3 = [torch.empty((n3, w), device=dev) for w in (3, 6, 6)]
+    w9 = torch.empty(9, device=dev).uniform_(-1, 1)
+    gw9 = torch.zeros(9, device=dev)
+    ms = timed(lambda: x.covproj_shared_w_fwd_bwd(ins3[0], w9, ins3[1], ins3[2], outs3[0], outs3[1], gw9, outs3[2]),
+               reps=5, flush_l2=False)
+    out["c3b_covproj_shared_w_2^26"] = {"evals_per_s": n3 / (ms / 1e3), "ms": ms, "bytes_per_eval": 120,
+                                        "gbs": 120 * n3 / (ms / 1e3) / 1e9, "hbm_frac": 120 * n3 / (ms / 1e3) / 1e9 / peak_gbs,
+                                        "l2": "8.05 GB per step > L2"}
+    del ins3, outs3
+    torch.cuda.empty_cache()
     # C4: splat 100K Gaussians, 1024^2
     W = H = 1024
     N = 100_000

@@ -181,6 +181,21 @@ XYZ_API int xyz_covproj_fwd_bwd_f32(const float* J, const float* W, const float*
                             float* out, float* gJ, float* gW, float* gS, long long n,
                             void* stream, int flags);
 
+/* Variant with ONE shared W (BASELINE configs[2] "variant B"): W9 is a single 3x3 parameter used by
+ * every element, gW9 its 9 gradient accumulators.  out / gJ / gS are per element and OVERWRITTEN as above; the
+ * per-element adjoints of W are summed and ADDED into gW9 (the VariableRef::add_grad accumulation of
+ * include/xyz_autodiff/variable.cuh:48-50, done with a fixed-order reduction instead of 9 atomics per element:
+ * bit-identical run to run).  120 algorithmic bytes per element.                                              */
+XYZ_API int xyz_covproj_shared_w_fwd_bwd_f32(const float* J, const float* W9, const float* S, const float* g,
+                                     float* out, float* gJ, float* gW9, float* gS, long long n,
+                                     void* stream, int flags);
+/* Multi-GPU: elements sharded over the ranks of an xyz_peer_group; gW9 += the sum over ALL ranks (exchanged by the
+ * kernel's last CTA over NVLink mailboxes, rank-ordered, bit-identical on every rank).  n may be 0 on a rank.  */
+XYZ_API int xyz_covproj_shared_w_fwd_bwd_f32_allreduce(const float* J, const float* W9, const float* S, const float* g,
+                                               float* out, float* gJ, float* gW9, float* gS, long long n,
+                                               const xyz_peer_group* group, unsigned long long seq,
+                                               void* stream, int flags);
+
 /* ---- C4/C5: mini-gaussian-splatting -------------------------------------------------------------
  * Replaces launch_gaussian_splatting (gaussian_splatting_kernel.cuh:38-47 /
  * gaussian_splatting_kernel.cu:114-149): renders `output` (overwritten), ADDS the L1 loss into

@@ -1,7 +1,7 @@
 """profiles/prof_driver.py -- launches every hot kernel twice at BASELINE size, for ncu.
 
   ncu --set full --clock-control none --import-source on \
-      -k regex:'covproj_tma|lsq_grad|accumulate|splat_forward|splat_backward|adam_kernel' -c 24 \
+      -k regex:'covproj_tma|covproj_sharedw|lsq_grad|accumulate|splat_forward|splat_backward|adam_kernel' -c 24 \
       -o gpurun_out/prof_rNN python profiles/prof_driver.py
 """
 import os
@@ -17,7 +17,7 @@ import xyz_autodiff_cuda_b200 as x  # noqa: E402
 
 dev = torch.device("cuda:0")
 reps = int(os.environ.get("PROF_REPS", "2"))
-which = os.environ.get("PROF_ONLY", "covproj,lsq,accumulate,splat,adam").split(",")
+which = os.environ.get("PROF_ONLY", "covproj,covproj_shared_w,lsq,accumulate,splat,adam").split(",")
 
 if "covproj" in which:
     E = 1 << 26
@@ -25,6 +25,17 @@ if "covproj" in which:
     outs = [torch.empty((E, w), device=dev) for w in (3, 6, 9, 6)]
     for _ in range(reps):
         x.covproj_fwd_bwd(*ins, *outs)
+    torch.cuda.synchronize()
+    del ins, outs
+
+if "covproj_shared_w" in which:
+    E = 1 << 26
+    ins = [torch.empty((E, w), device=dev).uniform_(-1, 1) for w in (6, 6, 3)]
+    outs = [torch.empty((E, w), device=dev) for w in (3, 6, 6)]
+    w9 = torch.empty(9, device=dev).uniform_(-1, 1)
+    gw9 = torch.zeros(9, device=dev)
+    for _ in range(reps):
+        x.covproj_shared_w_fwd_bwd(ins[0], w9, ins[1], ins[2], outs[0], outs[1], gw9, outs[2])
     torch.cuda.synchronize()
     del ins, outs
 

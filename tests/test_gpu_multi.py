@@ -125,6 +125,24 @@ ref = orc.covproj(J[b:e], W_[b:e], S[b:e], go[b:e], np.float64)
 for got, want in zip(outs, ref):
     assert np.abs(got.cpu().numpy() - want).max() <= 1e-5 * np.abs(want).max()
 
+# C3 variant B (one shared W): element ranges + the all-reduce of the 9 shared gradients inside the kernel
+pg3 = par.make_peer_group(x)
+W9 = W_[0].copy()
+Wrep = np.broadcast_to(W9, (J.shape[0], 9)).copy()
+ref_gW = orc.covproj(J, Wrep, S, go, np.float64)[2]
+for it in range(3):
+    o3, gJ3, gS3 = [torch.empty((e - b, k), device=dev) for k in (3, 6, 6)]
+    gW3 = torch.zeros(9, device=dev)
+    x.covproj_shared_w_fwd_bwd(D(J[b:e]), D(W9), D(S[b:e]), D(go[b:e]), o3, gJ3, gW3, gS3, group=pg3)
+    torch.cuda.synchronize()
+    assert (np.abs(gW3.cpu().numpy() - ref_gW.sum(0)) <= 1e-4 * np.abs(ref_gW).sum(0)).all(), it
+    same = gW3.clone(); dist.broadcast(same, 0)
+    assert torch.equal(same, gW3), "ranks disagree bitwise"
+    want_slice = orc.covproj(J[b:e], Wrep[b:e], S[b:e], go[b:e], np.float64)
+    assert np.abs(o3.cpu().numpy() - want_slice[0]).max() <= 1e-5 * np.abs(want_slice[0]).max()
+    assert np.abs(gJ3.cpu().numpy() - want_slice[1]).max() <= 1e-5 * np.abs(want_slice[1]).max()
+dist.barrier(); pg3.close()
+
 # C4 on G GPUs: tile-aligned row bands of one image, Gaussians replicated, all-reduce of grads + loss
 W, H, N = 160, 128, 300
 params, target = orc.splat_scene(N, W, H, seed=21)

@@ -101,6 +101,84 @@ def test_covproj_full_size_properties():
         assert torch.equal(a, b[:m])
 
 
+def run_covproj_shared_w(J, W9, S, g, gW0=None):
+    n = J.shape[0]
+    out, gJ, gS = [torch.full((n, k), float("nan"), dtype=torch.float32, device=DEV) for k in (3, 6, 6)]
+    gW = torch.zeros(9, dtype=torch.float32, device=DEV) if gW0 is None else dev(np.asarray(gW0, np.float32))
+    x.covproj_shared_w_fwd_bwd(dev(J), dev(W9), dev(S), dev(g), out, gJ, gW, gS)
+    torch.cuda.synchronize()
+    return out.cpu().numpy(), gJ.cpu().numpy(), gW.cpu().numpy(), gS.cpu().numpy()
+
+
+@pytest.mark.parametrize("n", [1, 127, 128, 129, 1000, 128 * 148 * 4 * 2 + 77, 300_001])
+def test_covproj_shared_w_matches_fp64_oracle(n):
+    """Variant B: one shared W.  Oracle = the reference's own matmul graph evaluated per element with W replicated
+    (oracle.covproj, fp64); the shared gradient is the fp64 sum of its per-element adjoints.  Per-element outputs
+    1e-5 relative; the accumulated gW 1e-4 relative to the sum of |terms| (BASELINE tolerance for accumulated sums)."""
+    J, W, S, g = orc.covproj_inputs(n, seed=n + 1)
+    W9 = W[0].copy()
+    Wrep = np.broadcast_to(W9, (n, 9)).copy()
+    out, gJ, gW, gS = run_covproj_shared_w(J, W9, S, g)
+    w_out, w_gJ, w_gW, w_gS = orc.covproj(J, Wrep, S, g, np.float64)
+    for a, b, name in ((out, w_out, "out"), (gJ, w_gJ, "gJ"), (gS, w_gS, "gS")):
+        assert rel_err(a, b, np.abs(b).max(axis=1, keepdims=True)).max() < 1e-5, name
+    assert (np.abs(gW - w_gW.sum(0)) <= 1e-4 * np.abs(w_gW).sum(0) + 1e-30).all()
+    # per-element results are bit-identical to the per-element-W kernel fed the replicated W
+    o2 = run_covproj(J, Wrep, S, g)
+    assert np.array_equal(out, o2[0]) and np.array_equal(gJ, o2[1]) and np.array_equal(gS, o2[3])
+
+
+def test_covproj_shared_w_accumulates_deterministically_and_unaligned():
+    n = 70_003
+    J, W, S, g = orc.covproj_inputs(n, seed=12)
+    W9 = W[3].copy()
+    a = run_covproj_shared_w(J, W9, S, g)
+    b = run_covproj_shared_w(J, W9, S, g)
+    assert np.array_equal(a[2], b[2])                      # fixed-order reduction: bit-identical run to run
+    c = run_covproj_shared_w(J, W9, S, g, gW0=np.arange(9) * 10.0)
+    assert np.allclose(c[2] - np.arange(9) * 10.0, a[2], rtol=0, atol=1e-3 * np.abs(a[2]).max())  # adds into the caller's values
+    # unaligned bases: the plain-load path of the same kernel
+    bufs = []
+    for arr in (J, S, g):
+        t = torch.zeros(arr.size + 1, dtype=torch.float32, device=DEV)
+        t[1:] = dev(arr).flatten()
+        bufs.append(t[1:].view(arr.shape))
+    out, gJ, gS = [torch.zeros(n * k + 1, dtype=torch.float32, device=DEV)[1:].view(n, k) for k in (3, 6, 6)]
+    gW = torch.zeros(9, device=DEV)
+    x.covproj_shared_w_fwd_bwd(bufs[0], dev(W9), bufs[1], bufs[2], out, gJ, gW, gS)
+    assert np.array_equal(out.cpu().numpy(), a[0]) and np.array_equal(gJ.cpu().numpy(), a[1]) and np.array_equal(gS.cpu().numpy(), a[3])
+    Wrep = np.broadcast_to(W9, (n, 9)).copy()
+    w_gW = orc.covproj(J, Wrep, S, g, np.float64)[2]
+    assert (np.abs(gW.cpu().numpy() - w_gW.sum(0)) <= 1e-4 * np.abs(w_gW).sum(0)).all()
+    # empty batch: nothing happens, gW untouched
+    z6, z3 = torch.empty((0, 6), device=DEV), torch.empty((0, 3), device=DEV)
+    gW = torch.full((9,), 1.5, device=DEV)
+    x.covproj_shared_w_fwd_bwd(z6, dev(W9), z6, z3, z3, z6, gW, z6)
+    assert (gW.cpu().numpy() == 1.5).all()
+
+
+def test_covproj_shared_w_full_size_properties():
+    """2^24 elements: out, gJ, gS equal the per-element-W kernel; gW is linear in g (exact power-of-two scaling) and
+    equals the fp64 sum of the per-element kernel's gW within the accumulated-sum tolerance."""
+    n = 1 << 24
+    gen = torch.Generator(device=DEV).manual_seed(8)
+    J = torch.rand((n, 6), device=DEV, generator=gen) * 2 - 1
+    S = torch.rand((n, 6), device=DEV, generator=gen) * 2 - 1
+    g = torch.rand((n, 3), device=DEV, generator=gen) * 2 - 1
+    W9 = torch.rand(9, device=DEV, generator=gen) * 2 - 1
+    out, gJ, gS = [torch.empty((n, k), device=DEV) for k in (3, 6, 6)]
+    gW = torch.zeros(9, device=DEV)
+    x.covproj_shared_w_fwd_bwd(J, W9, S, g, out, gJ, gW, gS)
+    gW4 = torch.zeros(9, device=DEV)
+    x.covproj_shared_w_fwd_bwd(J, W9, S, g * 4, out, gJ, gW4, gS)
+    assert torch.equal(gW4, gW * 4)
+    o = [torch.empty((n, k), device=DEV) for k in (3, 6, 9, 6)]
+    x.covproj_fwd_bwd(J, W9.expand(n, 9).contiguous(), S, g * 4, *o)
+    assert torch.equal(o[0], out) and torch.equal(o[1], gJ) and torch.equal(o[3], gS)
+    ref = o[2].double().sum(0)
+    assert ((gW4.double() - ref).abs() <= 1e-4 * o[2].double().abs().sum(0)).all()
+
+
 # ---------------------------------------------------------------------------------------------------
 # C1 least squares
 # ---------------------------------------------------------------------------------------------------

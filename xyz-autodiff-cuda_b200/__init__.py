@@ -37,7 +37,8 @@ EXPORTS = [
     "xyz_lsq_grad_f64", "xyz_lsq_sgd_update_f64", "xyz_lsq_select_batch", "xyz_lsq_sgd_step_f64",
     "xyz_peer_mailbox_bytes", "xyz_peer_mailbox_create", "xyz_peer_mailbox_open", "xyz_peer_mailbox_close",
     "xyz_peer_mailbox_destroy", "xyz_lsq_grad_f64_allreduce", "xyz_accumulate_f32_allreduce",
-    "xyz_accumulate_f32", "xyz_accumulate_f64", "xyz_covproj_fwd_bwd_f32",
+    "xyz_accumulate_f32", "xyz_accumulate_f64", "xyz_covproj_fwd_bwd_f32", "xyz_covproj_shared_w_fwd_bwd_f32",
+    "xyz_covproj_shared_w_fwd_bwd_f32_allreduce",
     "xyz_launch_gaussian_splatting", "xyz_launch_gaussian_splatting_rows", "xyz_splat_last_stats",
     "xyz_splat_debug_binning", "xyz_zero_gradients", "xyz_adam_step_individual", "xyz_adam_step",
     "xyz_adam_step_individual_zero_grads",
@@ -82,6 +83,9 @@ def lib() -> ctypes.CDLL:
         L.xyz_accumulate_f32.argtypes = [_vp, _vp, _ll, _vp, _i, _vp, _i]
         L.xyz_accumulate_f64.argtypes = [_vp, _vp, _ll, _vp, _i, _vp, _i]
         L.xyz_covproj_fwd_bwd_f32.argtypes = [_vp] * 8 + [_ll, _vp, _i]
+        L.xyz_covproj_shared_w_fwd_bwd_f32.argtypes = [_vp] * 8 + [_ll, _vp, _i]
+        L.xyz_covproj_shared_w_fwd_bwd_f32_allreduce.argtypes = [_vp] * 8 + [_ll, ctypes.POINTER(PeerGroupStruct),
+                                                                 ctypes.c_ulonglong, _vp, _i]
         L.xyz_launch_gaussian_splatting.argtypes = [_vp] * 5 + [_i, _i, _i, _vp, _i]
         L.xyz_launch_gaussian_splatting_rows.argtypes = [_vp] * 5 + [_i, _i, _i, _i, _i, _vp, _i]
         L.xyz_splat_last_stats.argtypes = [_vp]
@@ -255,6 +259,25 @@ def covproj_fwd_bwd(J, W, S, g, out, gJ, gW, gS, flags: int = 0, stream=None) ->
     _check(lib().xyz_covproj_fwd_bwd_f32(_dev(J, f, "J"), _dev(W, f, "W"), _dev(S, f, "S"), _dev(g, f, "g"),
                                          _dev(out, f, "out"), _dev(gJ, f, "gJ"), _dev(gW, f, "gW"), _dev(gS, f, "gS"),
                                          n, _stream(stream), flags), "xyz_covproj_fwd_bwd_f32")
+
+
+def covproj_shared_w_fwd_bwd(J, W9, S, g, out, gJ, gW9, gS, flags: int = 0, stream=None, group: "Optional[PeerGroup]" = None) -> None:
+    """Variant with ONE shared 3x3 W (9 floats): out / gJ / gS per element (overwritten), gW9 += the sum over the elements
+    of the per-element adjoints of W (fixed-order reduction).  With `group` the elements are this rank's shard and
+    gW9 += the sum over ALL ranks (exchanged inside the kernel over NVLink mailboxes)."""
+    n = J.shape[0]
+    f = torch.float32
+    ptr = lambda t, nm: _dev(t, f, nm) if n > 0 else None  # noqa: E731
+    args = [ptr(J, "J"), _dev(W9, f, "W9"), ptr(S, "S"), ptr(g, "g"), ptr(out, "out"), ptr(gJ, "gJ"), _dev(gW9, f, "gW9"),
+            ptr(gS, "gS"), n]
+    if W9.numel() != 9 or gW9.numel() != 9:
+        raise ValueError("W9 and gW9 must hold 9 floats")
+    if group is None:
+        _check(lib().xyz_covproj_shared_w_fwd_bwd_f32(*args, _stream(stream), flags), "xyz_covproj_shared_w_fwd_bwd_f32")
+    else:
+        _check(lib().xyz_covproj_shared_w_fwd_bwd_f32_allreduce(*args, ctypes.byref(group.struct), group.next_seq(),
+                                                                _stream(stream), flags),
+               "xyz_covproj_shared_w_fwd_bwd_f32_allreduce")
 
 
 # ---- C4 / C5 ---------------------------------------------------------------------------------------

@@ -280,6 +280,235 @@ __global__ void __launch_bounds__(128) covproj_plain_kernel(CovArgs a, long long
     for (int k = 0; k < 3; ++k) a.out[e * 3 + k] = out[k];
 }
 
+
+// ---- variant B: W is ONE shared 3x3 parameter -----------------------------------------------------------------
+// The complete north-star pattern in one launch: per-element forward + reverse, and the per-element adjoints of the
+// shared parameter accumulated into its 9 gradients (what E threads calling VariableRef::add_grad on the shared W
+// do in the reference: 9 same-address atomics per element, variable.cuh:48-50).
+// 120 algorithmic bytes per element (in J6 S6 g3, out out3 gJ6 gS6).  Same TMA ring as above with three arrays per
+// direction; dW stays in 9 registers per thread for the whole persistent loop, then shuffle tree -> shared memory ->
+// one row per CTA -> the last CTA (ticket) adds the rows in CTA order: no floating-point atomics, bit-identical run
+// to run.  With a peer group the last CTA also exchanges the row with the other ranks over NVLink mailboxes.
+constexpr int kSwInStages = 4;
+constexpr int kSwOutStages = 2;
+constexpr int kSwCtasPerSM = 4;
+constexpr int kSwAcc = 9;
+
+struct SwTile {  // [J|gJ: 6][S|gS: 6][g|out: 3] x 128
+    float a6[kTileE * 6];
+    float c6[kTileE * 6];
+    float d3[kTileE * 3];
+};
+struct SwSmem {
+    SwTile in[kSwInStages];
+    SwTile out[kSwOutStages];
+    uint64_t full[kSwInStages];
+    float red[kTileE / 32][kSwAcc];
+    int is_last;
+};
+
+__device__ __forceinline__ void issue_sw_tile_load(SwTile* st, uint64_t* bar, const CovArgs& a, long long tile) {
+    const long long e0 = tile * kTileE;
+    mbar_arrive_expect_tx(bar, sizeof(SwTile));
+    bulk_load(st->a6, a.J + e0 * 6, kTileE * 6 * 4, bar);
+    bulk_load(st->c6, a.S + e0 * 6, kTileE * 6 * 4, bar);
+    bulk_load(st->d3, a.g + e0 * 3, kTileE * 3 * 4, bar);
+}
+
+// a.W: the shared 3x3 (9 floats), a.gW: its 9 gradient accumulators (+=).  partials: [gridDim.x][9]; ticket: zero before
+// the launch, reset by the last CTA.
+template <bool kTma>
+__global__ void __launch_bounds__(kTileE, kSwCtasPerSM)
+    covproj_sharedw_kernel(CovArgs a, long long n, float* partials, unsigned int* ticket, PeerArgs peer) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SwSmem& sm = *reinterpret_cast<SwSmem*>(smem_raw);
+    const int tid = threadIdx.x;
+    float W[9];
+#pragma unroll
+    for (int k = 0; k < 9; ++k) W[k] = __ldg(a.W + k);
+    float acc[kSwAcc];
+#pragma unroll
+    for (int k = 0; k < kSwAcc; ++k) acc[k] = 0.f;
+
+    const long long n_tiles = kTma ? n / kTileE : 0;
+    if constexpr (kTma) {
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < kSwInStages; ++s) mbar_init(&sm.full[s], 1);
+            mbar_fence_init();
+        }
+        __syncthreads();
+        const long long first = blockIdx.x, stride = gridDim.x;
+        if (tid == 0) {
+#pragma unroll
+            for (int s = 0; s < kSwInStages; ++s) {
+                const long long t = first + s * stride;
+                if (t < n_tiles) issue_sw_tile_load(&sm.in[s], &sm.full[s], a, t);
+            }
+        }
+        int it = 0;
+        for (long long tile = first; tile < n_tiles; tile += stride, ++it) {
+            const int s = it % kSwInStages;
+            mbar_wait(&sm.full[s], (it / kSwInStages) & 1);
+            float J[6], S[6], g[3];
+            {
+                const SwTile& in = sm.in[s];
+                const float2* j2 = reinterpret_cast<const float2*>(in.a6 + tid * 6);
+                const float2* s2 = reinterpret_cast<const float2*>(in.c6 + tid * 6);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const float2 v = j2[k];
+                    J[2 * k] = v.x;
+                    J[2 * k + 1] = v.y;
+                    const float2 u = s2[k];
+                    S[2 * k] = u.x;
+                    S[2 * k + 1] = u.y;
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) g[k] = in.d3[tid * 3 + k];
+            }
+            if (tid == 0) bulk_wait_read<kSwOutStages - 1>();
+            __syncthreads();
+            if (tid == 0) {
+                const long long nt = tile + static_cast<long long>(kSwInStages) * stride;
+                if (nt < n_tiles) issue_sw_tile_load(&sm.in[s], &sm.full[s], a, nt);
+            }
+            float out[3], gJ[6], gW[9], gS[6];
+            covproj_element(J, W, S, g, out, gJ, gW, gS);
+#pragma unroll
+            for (int k = 0; k < kSwAcc; ++k) acc[k] += gW[k];
+            SwTile& o = sm.out[it % kSwOutStages];
+            {
+                float2* j2 = reinterpret_cast<float2*>(o.a6 + tid * 6);
+                float2* s2 = reinterpret_cast<float2*>(o.c6 + tid * 6);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    j2[k] = make_float2(gJ[2 * k], gJ[2 * k + 1]);
+                    s2[k] = make_float2(gS[2 * k], gS[2 * k + 1]);
+                }
+#pragma unroll
+                for (int k = 0; k < 3; ++k) o.d3[tid * 3 + k] = out[k];
+            }
+            fence_proxy_async_smem();
+            __syncthreads();
+            if (tid == 0) {
+                const long long e0 = tile * kTileE;
+                bulk_store(a.gJ + e0 * 6, o.a6, kTileE * 6 * 4);
+                bulk_store(a.gS + e0 * 6, o.c6, kTileE * 6 * 4);
+                bulk_store(a.out + e0 * 3, o.d3, kTileE * 3 * 4);
+                bulk_commit();
+            }
+        }
+        if (tid == 0) bulk_wait_all<0>();
+    }
+    // tail (and the whole range when a base pointer is not 16-byte aligned): plain loads and stores
+    for (long long e = n_tiles * kTileE + blockIdx.x * static_cast<long long>(kTileE) + tid; e < n;
+         e += static_cast<long long>(gridDim.x) * kTileE) {
+        float J[6], S[6], g[3], out[3], gJ[6], gW[9], gS[6];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) J[k] = __ldg(a.J + e * 6 + k);
+#pragma unroll
+        for (int k = 0; k < 6; ++k) S[k] = __ldg(a.S + e * 6 + k);
+#pragma unroll
+        for (int k = 0; k < 3; ++k) g[k] = __ldg(a.g + e * 3 + k);
+        covproj_element(J, W, S, g, out, gJ, gW, gS);
+#pragma unroll
+        for (int k = 0; k < kSwAcc; ++k) acc[k] += gW[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a.gJ[e * 6 + k] = gJ[k];
+#pragma unroll
+        for (int k = 0; k < 6; ++k) a.gS[e * 6 + k] = gS[k];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.out[e * 3 + k] = out[k];
+    }
+
+    // CTA reduction (fixed order), one row per CTA, last CTA adds the rows in CTA order
+#pragma unroll
+    for (int k = 0; k < kSwAcc; ++k) acc[k] = warp_sum(acc[k]);
+    if ((tid & 31) == 0) {
+#pragma unroll
+        for (int k = 0; k < kSwAcc; ++k) sm.red[tid >> 5][k] = acc[k];
+    }
+    __syncthreads();
+    if (tid < kSwAcc) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kTileE / 32; ++w) s += sm.red[w][tid];
+        partials[static_cast<size_t>(blockIdx.x) * kSwAcc + tid] = s;
+        __threadfence();
+    }
+    __syncthreads();
+    if (tid == 0) sm.is_last = (atomicAdd(ticket, 1u) == gridDim.x - 1);
+    __syncthreads();
+    if (!sm.is_last) return;
+    __threadfence();
+    {
+        float s[kSwAcc];
+#pragma unroll
+        for (int k = 0; k < kSwAcc; ++k) s[k] = 0.f;
+        for (unsigned int r = tid; r < gridDim.x; r += kTileE) {
+#pragma unroll
+            for (int k = 0; k < kSwAcc; ++k) s[k] += __ldcg(partials + static_cast<size_t>(r) * kSwAcc + k);
+        }
+#pragma unroll
+        for (int k = 0; k < kSwAcc; ++k) s[k] = warp_sum(s[k]);
+        __syncthreads();
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < kSwAcc; ++k) sm.red[tid >> 5][k] = s[k];
+        }
+        __syncthreads();
+        float t = 0.f;
+        if (tid < kSwAcc) {
+#pragma unroll
+            for (int w = 0; w < kTileE / 32; ++w) t += sm.red[w][tid];
+        }
+        if (peer.world > 1) {  // rank-ordered sum over NVLink mailboxes (bit-identical on every rank)
+            const int par = static_cast<int>(peer.seq & 1ull);
+            if (tid < kSwAcc) {
+                for (int p = 0; p < peer.world; ++p) peer.box[p]->vec[par][peer.rank][tid] = t;
+                __threadfence_system();
+            }
+            const bool ok = peer_publish_and_wait_cta(peer, tid);
+            if (tid < kSwAcc) {
+                t = 0.f;
+                for (int q = 0; q < peer.world; ++q) t += ld_relaxed_sys_f32(&peer.box[peer.rank]->vec[par][q][tid]);
+                if (!ok) t = __int_as_float(0x7fc00000);
+            }
+        }
+        if (tid < kSwAcc) a.gW[tid] += t;
+        if (tid == 0) *ticket = 0u;
+    }
+}
+
+int covproj_sharedw_launch(const float* J, const float* W9, const float* S, const float* g, float* out, float* gJ,
+                           float* gW9, float* gS, long long n, const PeerArgs& peer, void* stream) {
+    if (n < 0 || !W9 || !gW9) return XYZ_ERR_INVALID_ARGUMENT;
+    if (n == 0 && peer.world <= 1) return 0;
+    if (n > 0 && (!J || !S || !g || !out || !gJ || !gS)) return XYZ_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    CovArgs a{J, W9, S, g, out, gJ, gW9, gS};
+    const long long max_ctas = static_cast<long long>(sm_count()) * kSwCtasPerSM;
+    const long long want = (n + kTileE - 1) / kTileE;
+    const int grid = static_cast<int>(want < 1 ? 1 : (want < max_ctas ? want : max_ctas));
+    void* scratch = nullptr;
+    const int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(max_ctas) * kSwAcc * sizeof(float), &scratch);
+    if (err) return err;
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
+    float* partials = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+    const bool tma_ok = n >= kTileE && aligned16(J) && aligned16(S) && aligned16(g) && aligned16(out) && aligned16(gJ) &&
+                        aligned16(gS);
+    if (tma_ok) {
+        cudaFuncSetAttribute(covproj_sharedw_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             static_cast<int>(sizeof(SwSmem)));
+        covproj_sharedw_kernel<true><<<grid, kTileE, sizeof(SwSmem), st>>>(a, n, partials, ticket, peer);
+    } else {
+        covproj_sharedw_kernel<false><<<grid, kTileE, sizeof(SwSmem), st>>>(a, n, partials, ticket, peer);
+    }
+    count_launch();
+    return last_error();
+}
+
 }  // namespace
 }  // namespace xyzb
 
@@ -316,4 +545,31 @@ extern "C" int xyz_covproj_fwd_bwd_f32(const float* J, const float* W, const flo
         count_launch();
     }
     return last_error();
+}
+
+extern "C" int xyz_covproj_shared_w_fwd_bwd_f32(const float* J, const float* W9, const float* S, const float* g, float* out,
+                                                float* gJ, float* gW9, float* gS, long long n, void* stream, int flags) {
+    (void)flags;
+    xyzb::PeerArgs pa{};
+    return xyzb::covproj_sharedw_launch(J, W9, S, g, out, gJ, gW9, gS, n, pa, stream);
+}
+
+extern "C" int xyz_covproj_shared_w_fwd_bwd_f32_allreduce(const float* J, const float* W9, const float* S, const float* g,
+                                                          float* out, float* gJ, float* gW9, float* gS, long long n,
+                                                          const xyz_peer_group* group, unsigned long long seq, void* stream,
+                                                          int flags) {
+    using namespace xyzb;
+    (void)flags;
+    if (!group || group->world < 1 || group->world > XYZ_PEER_MAX_WORLD || group->rank < 0 || group->rank >= group->world ||
+        seq == 0)
+        return XYZ_ERR_INVALID_ARGUMENT;
+    PeerArgs pa{};
+    pa.rank = group->rank;
+    pa.world = group->world;
+    pa.seq = seq;
+    for (int i = 0; i < group->world; ++i) {
+        if (!group->mailbox[i]) return XYZ_ERR_INVALID_ARGUMENT;
+        pa.box[i] = static_cast<PeerMailbox*>(group->mailbox[i]);
+    }
+    return covproj_sharedw_launch(J, W9, S, g, out, gJ, gW9, gS, n, pa, stream);
 }
