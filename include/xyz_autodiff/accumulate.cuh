@@ -9,6 +9,7 @@
 //   RegisterLeaf<N, T>   a leaf (satisfies DifferentiableVariableConcept) whose VALUES are read from memory
 //                        once and whose ADJOINTS accumulate in the thread's registers across as many
 //                        graph evaluations as the thread performs;
+//   LeafSlice / slice    a view of some components of a RegisterLeaf as a leaf of its own;
 //   warp_reduce_add      shuffle-tree sum of N per-thread values over the 32 lanes (fixed order);
 //   block_accumulate     warp shuffle -> one shared-memory row per warp -> fixed-order sum -> ONE
 //                        atomic/RED per component per CTA (vector red.global.add.v4.f32 when N % 4 == 0
@@ -57,6 +58,34 @@ private:
     T v_[N];
     T g_[N];
 };
+
+// View of components [Offset, Offset + N) of a RegisterLeaf (or of any leaf with data() / grad() arrays): lets ONE
+// parameter block be used as several graph leaves (a, b, c, d of the least-squares example; W of the matrix chain).
+// Values and adjoints stay where the parent keeps them (registers); add_grad is the parent's plain +=.
+template <std::size_t Offset, std::size_t N, class Leaf>
+class LeafSlice {
+public:
+    using value_type = typename Leaf::value_type;
+    static constexpr std::size_t size = N;
+    static_assert(Offset + N <= Leaf::size, "slice exceeds the leaf");
+
+    XYZ_HD explicit LeafSlice(Leaf& leaf) : leaf_(&leaf) {}
+    XYZ_HD value_type& operator[](std::size_t i) const noexcept { return (*leaf_)[Offset + i]; }
+    XYZ_HD const value_type& grad(std::size_t i) const noexcept { return leaf_->grad(Offset + i); }
+    XYZ_HD void add_grad(std::size_t i, value_type value) const noexcept { leaf_->add_grad(Offset + i, value); }
+    XYZ_HD void zero_grad() const noexcept {
+#pragma unroll
+        for (std::size_t i = 0; i < N; ++i) leaf_->grad()[Offset + i] = value_type(0);
+    }
+
+private:
+    Leaf* leaf_;
+};
+
+template <std::size_t Offset, std::size_t N, class Leaf>
+XYZ_HD LeafSlice<Offset, N, Leaf> slice(Leaf& leaf) {
+    return LeafSlice<Offset, N, Leaf>(leaf);
+}
 
 #if defined(__CUDACC__)
 // Sum `values[0..N)` over the 32 lanes of the calling warp; every lane receives the totals.
