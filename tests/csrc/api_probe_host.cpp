@@ -31,6 +31,38 @@ int mine_kat_math_f64(double x, double* res) { return api_eval::kat_math<double>
 int mine_kat_math_f32(float x, float* res) { return api_eval::kat_math<float>(x, res); }
 int mine_kat_matrices(float* res) { return api_eval::kat_matrices(res); }
 
+// accum::slice: the least-squares graph on four one-component views of ONE RegisterLeaf<4> (what batched::for_each
+// hands to a user graph); res = {loss, da, db, dc, dd} accumulated over `reps` evaluations of the same point
+int mine_kat_leaf_slices(const double* p, double x1, double x2, double yt, int reps, double* res) {
+    using namespace xyz_autodiff;
+    accum::RegisterLeaf<4, double> shared(p);
+    static_assert(DifferentiableVariableConcept<accum::LeafSlice<1, 2, accum::RegisterLeaf<4, double>>>);
+    double loss_value = 0.0;
+    for (int r = 0; r < reps; ++r) {
+        auto a = accum::slice<0, 1>(shared);
+        auto b = accum::slice<1, 1>(shared);
+        auto c = accum::slice<2, 1>(shared);
+        auto d = accum::slice<3, 1>(shared);
+        auto x1_minus_a = op::sub_constant(a, x1);
+        auto x1_term = op::squared(x1_minus_a);
+        auto x2_minus_c = op::sub_constant(c, x2);
+        auto x2_squared = op::squared(x2_minus_c);
+        auto x2_term = op::mul(b, x2_squared);
+        auto combined = op::add(x1_term, x2_term);
+        auto y_pred = op::add(combined, d);
+        auto y_diff = op::sub_constant(y_pred, yt);
+        auto loss = op::squared(y_diff);
+        loss.run();
+        loss_value = loss[0];
+    }
+    res[0] = loss_value;
+    for (int i = 0; i < 4; ++i) res[1 + i] = shared.grad(i);
+    auto bc = accum::slice<1, 2>(shared);
+    bc.zero_grad();                      // zeroes components 1 and 2 of the parent only
+    for (int i = 0; i < 4; ++i) res[5 + i] = shared.grad(i);
+    return 9;
+}
+
 // ternary node + RegisterLeaf on the host: y = a*b + c ; returns {y, da, db, dc}
 int mine_kat_ternary(double a0, double b0, double c0, double* res) {
     using namespace xyz_autodiff;

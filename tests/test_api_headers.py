@@ -126,6 +126,16 @@ def test_host_known_answers(host):
     assert list(fres[:12]) == [1, 2, 6, 8, 15, 18, 1, 4, 9, 4, 10, 18]      # tests/test_diagonal_matrix.cu:145,167
     assert list(fres[12:21]) == [1, 2, 3, 4, 5, 6, 2, 3, 5]                 # tests/test_symmetric_matrix.cu
     assert list(fres[21:27]) == [1, 4, 2, 5, 3, 6]                          # tests/test_matrix_transpose.cu
+    # accum::slice views of one RegisterLeaf: same gradients as the VariableRef graph, accumulated over 3 evaluations
+    host.mine_kat_leaf_slices.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 3 + [ctypes.c_int, ctypes.c_void_p]
+    prm = np.array([1.0, 1.5, 0.5, 0.2])
+    sl = np.zeros(9)
+    assert host.mine_kat_leaf_slices(P(prm), 2.0, 3.0, 5.0, 3, P(sl)) == 9
+    one = np.zeros(9)
+    host.mine_kat_lsq_point.argtypes = [ctypes.c_void_p] + [ctypes.c_double] * 4 + [ctypes.c_void_p]
+    host.mine_kat_lsq_point(P(prm), 2.0, 3.0, 5.0, 1e-6, P(one))
+    assert sl[0] == one[0] and np.allclose(sl[1:5], 3 * one[1:5], rtol=1e-15)
+    assert sl[5] == sl[1] and sl[6] == 0.0 and sl[7] == 0.0 and sl[8] == sl[4]
     host.mine_kat_ternary.argtypes = [ctypes.c_double] * 3 + [ctypes.c_void_p]
     k = host.mine_kat_ternary(1.5, -2.0, 0.25, P(res))
     assert np.allclose(res[:4], [1.5 * -2.0 + 0.25, -2.0, 1.5, 1.0]) and np.allclose(res[4:7], res[1:4], atol=1e-8)
