@@ -321,6 +321,19 @@ def reference_cuda(dev, timed, x, tp, tt, W, H, N, ours_splat_ms):
     res["c4_splat"] = {"ms_at_N": {str(n_ref): ms}, "ms_per_iter_scaled_to_100K": scaled,
                        "speedup_of_this_repo": scaled / ours_splat_ms,
                        "note": "reference kernel cost is linear in N (all pairs, 9 atomics per pair)"}
+    # the same reference sources compiled against THIS repo's headers (warp-aggregated add_grad): drop-in speed-up of
+    # unmodified user kernels
+    path2 = os.path.join(ROOT, "oracle", "_ref", "libxyz_ref_cuda_ourhdr.so")
+    R2 = None
+    if os.path.exists(path2):
+        R2 = ctypes.CDLL(path2)
+        R2.refcuda_splat.argtypes = [vp] * 5 + [ctypes.c_int] * 3
+        R2.refcuda_lsq.argtypes = [vp, ll, vp]
+        R2.refcuda_accumulate.argtypes = [vp, vp, ll, vp]
+        ms2 = timed(lambda: R2.refcuda_splat(sub.data_ptr(), grads.data_ptr(), tt.data_ptr(), img.data_ptr(), loss.data_ptr(),
+                                             W, H, n_ref), reps=3, flush_l2=False)
+        res["c4_splat"]["reference_source_on_this_repos_headers_ms_at_N"] = {str(n_ref): ms2}
+        res["c4_splat"]["header_drop_in_speedup"] = ms / ms2
     # covproj 2^24
     n = 1 << 24
     ins = [torch.empty((n, w), device=dev).uniform_(-1, 1) for w in (6, 9, 6, 3)]
@@ -338,6 +351,9 @@ def reference_cuda(dev, timed, x, tp, tt, W, H, N, ours_splat_ms):
     ms_ref = timed(lambda: R.refcuda_lsq(data.data_ptr(), n, prm.data_ptr()), reps=5)
     ms_our = timed(lambda: x.lsq_grad(data, prm), reps=5)
     res["c1_lsq_1M"] = {"reference_ms": ms_ref, "this_repo_ms": ms_our, "speedup_of_this_repo": ms_ref / ms_our}
+    if R2 is not None:
+        res["c1_lsq_1M"]["reference_source_on_this_repos_headers_ms"] = timed(
+            lambda: R2.refcuda_lsq(data.data_ptr(), n, prm.data_ptr()), reps=5)
     # accumulation 2^24 -> 1024, uniform ids
     n = 1 << 24
     idx, val = orc.accumulate_inputs(n, 1024, "uniform", 42)
@@ -347,6 +363,9 @@ def reference_cuda(dev, timed, x, tp, tt, W, H, N, ours_splat_ms):
     ms_our = timed(lambda: x.accumulate(ti, tv, grad), reps=5)
     res["c2_accumulate_2^24_uniform"] = {"reference_ms": ms_ref, "this_repo_ms": ms_our,
                                          "speedup_of_this_repo": ms_ref / ms_our}
+    if R2 is not None:
+        res["c2_accumulate_2^24_uniform"]["reference_source_on_this_repos_headers_ms"] = timed(
+            lambda: R2.refcuda_accumulate(ti.data_ptr(), tv.data_ptr(), n, grad.data_ptr()), reps=5)
     return res
 
 

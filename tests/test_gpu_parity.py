@@ -682,6 +682,73 @@ def test_against_the_reference_cuda_kernels_on_the_same_gpu():
     assert (np.abs(got - grad.cpu().numpy()) <= 2e-4 * orc.accumulate_exact(idx, np.abs(val), 1024) + 1e-30).all()
 
 
+REF_CUDA_OURHDR = os.path.join(os.path.dirname(REF_CUDA), "libxyz_ref_cuda_ourhdr.so")
+
+
+@pytest.mark.skipif(not os.path.exists(REF_CUDA_OURHDR), reason="oracle/_ref/libxyz_ref_cuda_ourhdr.so not built")
+def test_reference_kernel_sources_on_this_repos_headers():
+    """Drop-in check of the header library at kernel level: the reference's splat kernel file (unmodified, with its own
+    custom Logics) and the reference-style least-squares / accumulation / matmul-chain kernels of
+    oracle/ref_cuda_driver.cu, compiled against include/xyz_autodiff of THIS repo (oracle/Makefile), must give the
+    results of the same sources compiled against the reference's headers: values bit-identical (same user code, same
+    flags), atomically accumulated sums within the accumulated-sum tolerance (the warp-aggregated add_grad changes the
+    summation order)."""
+    import ctypes
+    vp, ll = ctypes.c_void_p, ctypes.c_longlong
+    libs = []
+    for path in (REF_CUDA, REF_CUDA_OURHDR):
+        R = ctypes.CDLL(path)
+        R.refcuda_splat.argtypes = [vp] * 5 + [ctypes.c_int] * 3
+        R.refcuda_lsq.argtypes = [vp, ll, vp]
+        R.refcuda_accumulate.argtypes = [vp, vp, ll, vp]
+        R.refcuda_covproj.argtypes = [vp] * 8 + [ll]
+        libs.append(R)
+    for (W, H, N, seed) in [(64, 48, 50, 3), (100, 70, 300, 11)]:
+        params, target = orc.splat_scene(N, W, H, seed=seed)
+        tp, tt = dev(params), dev(target)
+        res = []
+        for R in libs:
+            rg = torch.zeros((N, 9), device=DEV)
+            ro = torch.zeros((W * H, 3), device=DEV)
+            rl = torch.zeros(1, device=DEV)
+            assert R.refcuda_splat(tp.data_ptr(), rg.data_ptr(), tt.data_ptr(), ro.data_ptr(), rl.data_ptr(), W, H, N) == 0
+            torch.cuda.synchronize()
+            res.append((ro.cpu().numpy(), rg.cpu().numpy(), rl.item()))
+        assert np.array_equal(res[0][0], res[1][0]), "image"
+        tol = orc.splat_tolerance(params, target, W, H)[3]
+        assert (np.abs(res[0][1] - res[1][1]) <= 2 * tol).all()
+        assert abs(res[0][2] - res[1][2]) <= 1e-4 * abs(res[0][2])
+    n = 10_000
+    J, W9, S, gg = orc.covproj_inputs(n, seed=3)
+    ins = [dev(a) for a in (J, W9, S, gg)]
+    outs = []
+    for R in libs:
+        o = [torch.zeros((n, k), device=DEV) for k in (3, 6, 9, 6)]
+        assert R.refcuda_covproj(*[t.data_ptr() for t in ins], *[t.data_ptr() for t in o], n) == 0
+        torch.cuda.synchronize()
+        outs.append([t.cpu().numpy() for t in o])
+    for a, b in zip(*outs):
+        assert np.array_equal(a, b)
+    data = orc.lsq_data(100_000, seed=6)
+    td = dev(data)
+    grads = []
+    for R in libs:
+        prm = dev(np.array([0.3, 1.2, -0.4, 0.1, 0, 0, 0, 0], np.float64))
+        assert R.refcuda_lsq(td.data_ptr(), data.shape[0], prm.data_ptr()) == 0
+        torch.cuda.synchronize()
+        grads.append(prm[4:].cpu().numpy())
+    assert rel_err(grads[1], grads[0]).max() < 1e-10
+    idx, val = orc.accumulate_inputs(1 << 20, 1024, "zipf", seed=4)
+    ti, tv = dev(idx), dev(val)
+    exact = orc.accumulate_exact(idx, val, 1024)
+    abs_sum = orc.accumulate_exact(idx, np.abs(val), 1024)
+    for R in libs:
+        grad = torch.zeros(1024, device=DEV)
+        assert R.refcuda_accumulate(ti.data_ptr(), tv.data_ptr(), idx.size, grad.data_ptr()) == 0
+        torch.cuda.synchronize()
+        assert (np.abs(grad.cpu().numpy() - exact) <= 1e-4 * abs_sum + 1e-30).all()
+
+
 def test_no_cpu_fallback():
     with pytest.raises(RuntimeError):
         x.covproj_fwd_bwd(*[torch.zeros((4, k)) for k in (6, 9, 6, 3, 3, 6, 9, 6)])
