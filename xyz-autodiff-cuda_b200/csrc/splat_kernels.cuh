@@ -11,6 +11,9 @@
 #ifndef XYZ_SPLAT_FLAVOR
 #error "define XYZ_SPLAT_FLAVOR (fast|precise) before including splat_kernels.cuh"
 #endif
+#ifndef XYZ_BWD_MINBLOCKS
+#define XYZ_BWD_MINBLOCKS 6  // resident backward CTAs per SM the register budget is sized for
+#endif
 #define XYZ_CAT2(a, b) a##b
 #define XYZ_CAT(a, b) XYZ_CAT2(a, b)
 
@@ -261,7 +264,7 @@ __device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_r
 
 // One CTA = up to kBwdChunk consecutive list entries of ONE tile: chunk_info[c] = {tile, first entry, end of the tile's
 // list, -} written by splat_chunk_scan_kernel; the grid is an upper bound, surplus CTAs see tile = -1 and exit.
-__global__ void __launch_bounds__(kBwdChunk)
+__global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
     splat_backward_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ chunk_info,
                           const float4* __restrict__ rest_tiles, const int* __restrict__ sorted_gid,
                           const unsigned int* __restrict__ sorted_orig, const xyz_gaussian_params* __restrict__ params,
