@@ -215,6 +215,44 @@ def also_workloads(dev, peak_gbs):
                                         "l2": "8.05 GB per step > L2"}
     del ins3, outs3
     torch.cuda.empty_cache()
+    # the same two graphs written by a USER with the public op:: API and run through include/xyz_autodiff/batched.cuh
+    # (tests/csrc/batched_probe.cu; the probe library is built by __graft_entry__.build())
+    try:
+        import ctypes
+        so = os.path.join(ROOT, "tests", "csrc", "_build", "libxyz_batched.so")
+        if os.path.exists(so):
+            B = ctypes.CDLL(so)
+            B.batched_chain.restype = ctypes.c_float
+            B.batched_chain.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+            B.batched_lsq.restype = ctypes.c_float
+            B.batched_lsq.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+            nb = 1 << 26
+            tin = torch.empty((nb, 15), device=dev).uniform_(-1, 1)
+            tout = torch.empty((nb, 15), device=dev)
+            w18 = torch.empty(18, device=dev).uniform_(-1, 1)
+            gw18 = torch.zeros(18, device=dev)
+            B.batched_chain(tin.data_ptr(), tout.data_ptr(), nb, w18.data_ptr(), gw18.data_ptr(), 2)
+            ms = B.batched_chain(tin.data_ptr(), tout.data_ptr(), nb, w18.data_ptr(), gw18.data_ptr(), 5)
+            out["batched_for_each_matmul_chain_shared_w_2^26"] = {
+                "evals_per_s": nb / (ms / 1e3), "ms": ms, "gbs": 120 * nb / (ms / 1e3) / 1e9,
+                "hbm_frac": 120 * nb / (ms / 1e3) / 1e9 / peak_gbs,
+                "what": "user graph of op::matmul nodes through batched::for_each (include/xyz_autodiff/batched.cuh)"}
+            del tin, tout
+            torch.cuda.empty_cache()
+            mb = 1 << 28
+            dpts = torch.empty((mb, 3), dtype=torch.float64, device=dev).uniform_(-5, 5)
+            v5 = torch.tensor([0.0, 1.0, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
+            g5 = torch.zeros(5, dtype=torch.float64, device=dev)
+            B.batched_lsq(dpts.data_ptr(), mb, v5.data_ptr(), g5.data_ptr(), 2)
+            ms = B.batched_lsq(dpts.data_ptr(), mb, v5.data_ptr(), g5.data_ptr(), 5)
+            out["batched_for_each_least_squares_2^28_f64"] = {
+                "evals_per_s": mb / (ms / 1e3), "ms": ms, "gbs": 24 * mb / (ms / 1e3) / 1e9,
+                "hbm_frac": 24 * mb / (ms / 1e3) / 1e9 / peak_gbs,
+                "what": "user graph of op:: nodes (fp64) through batched::for_each"}
+            del dpts
+            torch.cuda.empty_cache()
+    except Exception as e:
+        out["batched_for_each"] = {"error": repr(e)}
     # C4: splat 100K Gaussians, 1024^2
     W = H = 1024
     N = 100_000

@@ -1,7 +1,7 @@
 """profiles/prof_driver.py -- launches every hot kernel twice at BASELINE size, for ncu.
 
   ncu --set full --clock-control none --import-source on \
-      -k regex:'covproj_tma|covproj_sharedw|lsq_grad|accumulate|splat_forward|splat_backward|adam_kernel' -c 24 \
+      -k regex:'covproj_tma|covproj_sharedw|batched_kernel|lsq_grad|accumulate|splat_forward|splat_backward|adam_kernel' -c 24 \
       -o gpurun_out/prof_rNN python profiles/prof_driver.py
 """
 import os
@@ -17,7 +17,7 @@ import xyz_autodiff_cuda_b200 as x  # noqa: E402
 
 dev = torch.device("cuda:0")
 reps = int(os.environ.get("PROF_REPS", "2"))
-which = os.environ.get("PROF_ONLY", "covproj,covproj_shared_w,lsq,accumulate,splat,adam").split(",")
+which = os.environ.get("PROF_ONLY", "covproj,covproj_shared_w,batched,lsq,accumulate,splat,adam").split(",")
 
 if "covproj" in which:
     E = 1 << 26
@@ -38,6 +38,31 @@ if "covproj_shared_w" in which:
         x.covproj_shared_w_fwd_bwd(ins[0], w9, ins[1], ins[2], outs[0], outs[1], gw9, outs[2])
     torch.cuda.synchronize()
     del ins, outs
+
+if "batched" in which:
+    # include/xyz_autodiff/batched.cuh through the two user graphs of tests/csrc/batched_probe.cu
+    import ctypes
+    so = os.path.join(ROOT, "tests", "csrc", "_build", "libxyz_batched.so")
+    if os.path.exists(so):
+        B = ctypes.CDLL(so)
+        B.batched_lsq.restype = ctypes.c_float
+        B.batched_lsq.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        B.batched_chain.restype = ctypes.c_float
+        B.batched_chain.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+        n = 1 << 25
+        tin = torch.empty((n, 15), device=dev).uniform_(-1, 1)
+        tout = torch.empty((n, 15), device=dev)
+        w18 = torch.empty(18, device=dev).uniform_(-1, 1)
+        gw18 = torch.zeros(18, device=dev)
+        B.batched_chain(tin.data_ptr(), tout.data_ptr(), n, w18.data_ptr(), gw18.data_ptr(), reps)
+        del tin, tout
+        m = 1 << 27
+        data = torch.empty((m, 3), dtype=torch.float64, device=dev).uniform_(-5, 5)
+        v5 = torch.tensor([0.0, 1.0, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
+        g5 = torch.zeros(5, dtype=torch.float64, device=dev)
+        B.batched_lsq(data.data_ptr(), m, v5.data_ptr(), g5.data_ptr(), reps)
+        torch.cuda.synchronize()
+        del data
 
 if "lsq" in which:
     n = 1 << 28

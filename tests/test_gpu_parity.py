@@ -382,6 +382,35 @@ def test_accumulate_deterministic_is_bit_identical_and_variants():
     assert np.allclose(grad.cpu().numpy() - 1.0, orc.accumulate_exact(idx, val, k), atol=1e-2)
 
 
+def test_accumulate_random_shapes():
+    """Seeded sweep over (n, K, id distribution, flags, invalid ids, alignment): every dispatch path of xyz_accumulate_f32
+    against the exact fp64 sums, tolerance 1e-4 of the sum of |terms| (BASELINE's bound for accumulated sums)."""
+    rng = np.random.default_rng(20260)
+    for case in range(40):
+        k = int(rng.choice([1, 2, 5, 33, 128, 777, 1024, 1200, 1771, 1772, 2500, 6000]))
+        n = int(rng.choice([1, 63, 4097, 65_535, 65_536, 65_537, 200_000, 524_288 + 3, 1_000_001]))
+        dist = str(rng.choice(["uniform", "zipf", "same"]))
+        flags = int(rng.choice([0, x.FLAG_DETERMINISTIC]))
+        if k > 4096 and flags:
+            flags = 0
+        idx, val = orc.accumulate_inputs(n, k, dist, seed=1000 + case)
+        if rng.random() < 0.3 and n > 10:
+            bad = rng.integers(0, n, size=max(1, n // 50))
+            idx[bad] = rng.choice([-1, -7, k, k + 100, 2**31 - 1], size=bad.size)
+        keep = (idx >= 0) & (idx < k)
+        shift = int(rng.random() < 0.25)
+        ti = torch.zeros(n + 1, dtype=torch.int32, device=DEV)
+        tv = torch.zeros(n + 1, dtype=torch.float32, device=DEV)
+        ti[shift:shift + n] = dev(idx)
+        tv[shift:shift + n] = dev(val)
+        grad = torch.zeros(k, device=DEV)
+        x.accumulate(ti[shift:shift + n], tv[shift:shift + n], grad, flags)
+        got = grad.cpu().numpy()
+        exact = orc.accumulate_exact(idx[keep], val[keep], k)
+        abs_sum = orc.accumulate_exact(idx[keep], np.abs(val[keep]), k)
+        assert (np.abs(got - exact) <= 1e-4 * abs_sum + 1e-30).all(), (case, k, n, dist, flags, shift)
+
+
 def test_accumulate_striped_tables_variants():
     """The lane-striped fast path (fp32, aligned, n >= 2^16): every table count T (12, 6, 4, 3, 2 tables per SM), partial
     last unit, implicit ids with K below and above the 128-element row, invalid ids, all-invalid input, and bit-identical
