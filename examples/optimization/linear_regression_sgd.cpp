@@ -4,8 +4,9 @@
 //   y = (x1 - a)^2 + b (x2 - c)^2 + d     (true a, b, c, d = 2.5, 1.8, -1.2, 0.7; noise sigma 0.5; :17-28)
 // from (0, 1, 0, 0) by minibatch SGD with an exponentially decaying rate (:137-140).  Per epoch the reference
 // launches select_batch_kernel, clears the four gradients, launches parallel_gradient_computation_kernel and
-// update_parameters_kernel (:185-209); here the whole epoch is ONE extern "C" call (xyz_lsq_sgd_step_f64), or with
-// --four-calls one call per reference kernel; everything is queued on one stream with no host synchronisation
+// update_parameters_kernel (:185-209); here all epochs between two progress prints are ONE extern "C" call
+// (xyz_lsq_sgd_run_f64: a cooperative kernel with one grid barrier per epoch), with --per-epoch-calls one call per
+// epoch (xyz_lsq_sgd_step_f64), with --four-calls one call per reference kernel; everything is queued on one stream with no host synchronisation
 // inside the epoch loop (the reference synchronises twice per epoch).
 //
 // Differences from the shipped reference main (all switchable back):
@@ -16,9 +17,10 @@
 //   * data comes from std::mt19937(--seed) instead of std::random_device, so runs are reproducible.
 //
 //   linear_regression_sgd [--samples N] [--batch B] [--epochs E] [--lr0 x] [--lr1 x] [--seed s]
-//                         [--reference-loss] [--four-calls] [--quiet] [--check tol]
+//                         [--reference-loss] [--four-calls] [--per-epoch-calls] [--quiet] [--check tol]
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -45,6 +47,7 @@ struct Options {
     unsigned seed = 42;
     bool reference_loss = false;
     bool four_calls = false;      // --four-calls: the reference's epoch as four launches instead of the fused one
+    bool per_epoch_calls = false; // --per-epoch-calls: one fused launch per epoch instead of one per 100 epochs
     bool quiet = false;
     double check = -1.0;          // > 0: exit 1 unless the final total parameter error is below it
 };
@@ -69,6 +72,7 @@ Options parse(int argc, char** argv) {
         else if (a == "--check") o.check = std::atof(need("--check"));
         else if (a == "--reference-loss") o.reference_loss = true;
         else if (a == "--four-calls") o.four_calls = true;
+        else if (a == "--per-epoch-calls") o.per_epoch_calls = true;
         else if (a == "--quiet") o.quiet = true;
         else {
             std::fprintf(stderr, "unknown argument %s\n", a.c_str());
@@ -147,8 +151,19 @@ int main(int argc, char** argv) {
     double* d_grad = d_params.get()->grad;  // device address of the 4 gradients
     const auto t0 = std::chrono::steady_clock::now();
     for (int epoch = 0; epoch < opt.epochs; ++epoch) {
-        const double lr = opt.lr0 * std::exp(decay * epoch);
-        if (opt.four_calls) {  // the reference's epoch body, call for call (:185-209)
+        double lr = opt.lr0 * std::exp(decay * epoch);
+        if (!opt.four_calls && !opt.per_epoch_calls) {
+            // default: all epochs up to the next progress print in ONE cooperative launch (bit-identical to the
+            // one-launch-per-epoch path below)
+            const int until = std::min(opt.epochs, (epoch / 100 + 1) * 100);
+            std::vector<double> lrs;
+            for (int e = epoch; e < until; ++e) lrs.push_back(opt.lr0 * std::exp(decay * e));
+            XYZ_CALL(xyz_lsq_sgd_run_f64(d_data.get(), opt.samples, d_params.get(), opt.batch, opt.seed,
+                                         static_cast<uint64_t>(epoch), static_cast<int>(lrs.size()), lrs.data(), nullptr,
+                                         stream, flags));
+            epoch = until - 1;
+            lr = lrs.back();
+        } else if (opt.four_calls) {  // the reference's epoch body, call for call (:185-209)
             XYZ_CALL(xyz_lsq_select_batch(d_data.get(), opt.samples, d_batch.get(), opt.batch, opt.seed,
                                           static_cast<uint64_t>(epoch), stream));
             CHECK_CUDA_ERROR(cudaMemsetAsync(d_grad, 0, sizeof(double) * 4, stream));

@@ -124,6 +124,15 @@ XYZ_API int xyz_lsq_sgd_step_f64(const xyz_data_point* data, long long n_total, 
                          long long batch_size, uint64_t seed, uint64_t epoch, double learning_rate,
                          double* loss_sum, void* stream, int flags);
 
+/* n_epochs epochs of xyz_lsq_sgd_step_f64 (epochs epoch_begin .. epoch_begin + n_epochs - 1, learning rate
+ * learning_rates_host[e] for the e-th of them; the array is read before the call returns) in ONE cooperative launch:
+ * parameters stay in registers, one grid barrier per epoch.  The final params (value and grad) and *loss_sum are
+ * bit-identical to n_epochs single-epoch calls.  Falls back to one launch per epoch when the grid cannot be
+ * co-resident.  The driver loop of linear_regression_sgd.cu:185-229 between two progress prints.            */
+XYZ_API int xyz_lsq_sgd_run_f64(const xyz_data_point* data, long long n_total, xyz_lsq_parameters* params,
+                        long long batch_size, uint64_t seed, uint64_t epoch_begin, int n_epochs,
+                        const double* learning_rates_host, double* loss_sum, void* stream, int flags);
+
 /* ---- fused reduce + all-reduce over NVLink peer memory (one process per GPU, one box) -----------------------
  * The reference is single-GPU.  When the elements of C1 are sharded over the GPUs of an NVSwitch box the only
  * exchange is the sum of the 4 shared-parameter gradients (+ loss); xyz_lsq_grad_f64_allreduce does it inside the

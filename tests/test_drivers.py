@@ -64,6 +64,14 @@ def test_lsq_driver_converges_to_the_true_parameters():
     r4 = run([LSQ, "--epochs", "10000", "--quiet", "--four-calls"])
     m4 = re.search(r"Final parameters: a=([-0-9.]+), b=([-0-9.]+), c=([-0-9.]+), d=([-0-9.]+)", r4.stdout)
     assert r4.returncode == 0 and all(abs(float(u) - v) < 2e-4 for u, v in zip(m4.groups(), (a, b, c, d)))
+    # one fused launch per epoch: bit-identical to the default (100 epochs per cooperative launch), so the printed
+    # parameters agree to the last digit; the us/epoch figures of the three modes are printed for the record
+    r1 = run([LSQ, "--epochs", "10000", "--quiet", "--per-epoch-calls"])
+    m1 = re.search(r"Final parameters: a=([-0-9.]+), b=([-0-9.]+), c=([-0-9.]+), d=([-0-9.]+)", r1.stdout)
+    assert r1.returncode == 0 and m1.groups() == m.groups()
+    for name, out in (("100 epochs per launch", r.stdout), ("one launch per epoch", r1.stdout), ("four launches per epoch", r4.stdout)):
+        t = re.search(r"\(([0-9.]+) us/epoch", out)
+        print(f"LSQ driver, {name}: {t.group(1) if t else '?'} us/epoch")
     # the shipped reference update (one sample, residual loss) also runs through the same entry points
     r = run([LSQ, "--epochs", "500", "--batch", "1", "--reference-loss", "--quiet"])
     assert r.returncode == 0, r.stdout[-2000:]

@@ -292,6 +292,31 @@ def test_lsq_fused_sgd_step_equals_the_four_call_epoch():
         assert torch.equal(pc, pb)
 
 
+def test_lsq_many_epochs_in_one_launch_equal_single_epoch_calls():
+    """xyz_lsq_sgd_run_f64 (cooperative kernel, parameters in registers, one grid barrier per epoch) against the same
+    epochs run one call at a time: parameters, last gradient and accumulated loss bit for bit; several batch sizes
+    (1 CTA, partial CTA, the driver's 8192, more CTAs than SMs), both losses, a second chunk continuing the first."""
+    data = dev(orc.lsq_data(100_000, seed=9))
+    for batch, flags in ((1, 0), (100, 0), (8192, 0), (8192, x.FLAG_RESIDUAL_ONLY), (70_000, 0)):
+        epochs = 37
+        lrs = [1e-4 * np.exp(-0.01 * e) for e in range(2 * epochs)]
+        p1 = torch.zeros(8, dtype=torch.float64, device=DEV); p1[1] = 1.0
+        l1 = torch.zeros(1, dtype=torch.float64, device=DEV)
+        for e in range(2 * epochs):
+            x.lsq_sgd_step(data, p1, batch, 42, e, lrs[e], l1, flags)
+        p2 = torch.zeros(8, dtype=torch.float64, device=DEV); p2[1] = 1.0
+        l2 = torch.zeros(1, dtype=torch.float64, device=DEV)
+        x.lsq_sgd_run(data, p2, batch, 42, 0, lrs[:epochs], l2, flags)
+        x.lsq_sgd_run(data, p2, batch, 42, epochs, lrs[epochs:], l2, flags)
+        torch.cuda.synchronize()
+        assert torch.equal(p1, p2), (batch, flags, p1, p2)
+        assert torch.equal(l1, l2), (batch, flags)
+    # zero epochs: nothing changes
+    p3 = p2.clone()
+    x.lsq_sgd_run(data, p3, 8192, 42, 0, [])
+    assert torch.equal(p3, p2)
+
+
 # ---------------------------------------------------------------------------------------------------
 # C2 accumulation
 # ---------------------------------------------------------------------------------------------------

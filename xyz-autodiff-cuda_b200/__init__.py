@@ -34,7 +34,7 @@ GAUSSIAN_FLOATS = 9   # center[2] scale[2] rotation[1] color[3] opacity[1]
 ADAM_FLOATS = 18
 EXPORTS = [
     "xyz_b200_version", "xyz_b200_shutdown", "xyz_b200_launch_count", "xyz_b200_reset_launch_count",
-    "xyz_lsq_grad_f64", "xyz_lsq_sgd_update_f64", "xyz_lsq_select_batch", "xyz_lsq_sgd_step_f64",
+    "xyz_lsq_grad_f64", "xyz_lsq_sgd_update_f64", "xyz_lsq_select_batch", "xyz_lsq_sgd_step_f64", "xyz_lsq_sgd_run_f64",
     "xyz_peer_mailbox_bytes", "xyz_peer_mailbox_create", "xyz_peer_mailbox_open", "xyz_peer_mailbox_close",
     "xyz_peer_mailbox_destroy", "xyz_lsq_grad_f64_allreduce", "xyz_accumulate_f32_allreduce",
     "xyz_accumulate_f32", "xyz_accumulate_f64", "xyz_covproj_fwd_bwd_f32", "xyz_covproj_shared_w_fwd_bwd_f32",
@@ -71,6 +71,8 @@ def lib() -> ctypes.CDLL:
         L.xyz_lsq_sgd_update_f64.argtypes = [_vp, ctypes.c_double, _ll, _vp]
         L.xyz_lsq_select_batch.argtypes = [_vp, _ll, _vp, _ll, ctypes.c_uint64, ctypes.c_uint64, _vp]
         L.xyz_lsq_sgd_step_f64.argtypes = [_vp, _ll, _vp, _ll, ctypes.c_uint64, ctypes.c_uint64, ctypes.c_double, _vp, _vp, _i]
+        L.xyz_lsq_sgd_run_f64.argtypes = [_vp, _ll, _vp, _ll, ctypes.c_uint64, ctypes.c_uint64, _i, ctypes.POINTER(ctypes.c_double),
+                                          _vp, _vp, _i]
         L.xyz_peer_mailbox_bytes.restype = ctypes.c_size_t
         L.xyz_peer_mailbox_create.argtypes = [ctypes.POINTER(_vp), ctypes.c_char_p]
         L.xyz_peer_mailbox_open.argtypes = [ctypes.c_char_p, ctypes.POINTER(_vp)]
@@ -219,6 +221,18 @@ def lsq_sgd_step(data: torch.Tensor, params: torch.Tensor, batch: int, seed: int
                                       _dev(params, torch.float64, "params"), batch, seed, epoch, lr,
                                       _dev(loss_sum, torch.float64, "loss_sum") if loss_sum is not None else None,
                                       _stream(stream), flags), "xyz_lsq_sgd_step_f64")
+
+
+def lsq_sgd_run(data: torch.Tensor, params: torch.Tensor, batch: int, seed: int, epoch_begin: int, learning_rates,
+                loss_sum: Optional[torch.Tensor] = None, flags: int = 0, stream=None) -> None:
+    """len(learning_rates) SGD epochs (epoch_begin, epoch_begin + 1, ...) in ONE cooperative launch; the final state is
+    bit-identical to calling lsq_sgd_step once per epoch."""
+    lrs = [float(v) for v in learning_rates]
+    arr = (ctypes.c_double * len(lrs))(*lrs)
+    _check(lib().xyz_lsq_sgd_run_f64(_dev(data, torch.float64, "data"), data.shape[0],
+                                     _dev(params, torch.float64, "params"), batch, seed, epoch_begin, len(lrs), arr,
+                                     _dev(loss_sum, torch.float64, "loss_sum") if loss_sum is not None else None,
+                                     _stream(stream), flags), "xyz_lsq_sgd_run_f64")
 
 
 # ---- C2 ------------------------------------------------------------------------------------------

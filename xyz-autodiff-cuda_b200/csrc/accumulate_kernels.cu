@@ -395,7 +395,7 @@ template <bool kImplicit, bool kRows>
 __global__ void __launch_bounds__(kStripeWarps * 32, 1)
     accumulate_striped_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, long long n, float* grad,
                               int k, float* partial_rows, int T) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
+    extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kThreadsS = kStripeWarps * 32;
     const int GW = kStripeWarps / T;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;

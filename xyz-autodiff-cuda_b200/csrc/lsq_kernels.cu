@@ -13,6 +13,8 @@
 // params->grad.  No floating-point atomics at all, so the result is bit-identical run to run
 // (XYZ_FLAG_DETERMINISTIC is always honoured).  24 algorithmic bytes per point -> HBM bound;
 // points arrive by TMA 1-D bulk copies (256 points = 6 KB contiguous per tile, 4-stage ring).
+#include <cooperative_groups.h>
+
 #include "common.cuh"
 
 namespace xyzb {
@@ -259,6 +261,99 @@ __global__ void __launch_bounds__(kThreads)
     if (tid == 0) *ticket = 0u;
 }
 
+
+// ---- MANY SGD epochs in ONE cooperative launch ----------------------------------------------------------------
+// The epoch loop of the driver is launch bound even at one launch per epoch (6.6 us/epoch against ~2 us of device
+// work).  This kernel keeps the parameters in registers and runs `n_epochs` epochs back to back; the only global
+// synchronisation per epoch is one grid barrier between "every CTA has written its partial row" and "every CTA
+// reads all rows".  EVERY CTA then adds the rows with exactly the instruction sequence of lsq_sgd_step_kernel's last
+// CTA (same thread -> row mapping, same shuffle tree, same warp order) and applies the same update expression, so
+// all CTAs hold bit-identical parameters and the final state is bit-identical to n_epochs calls of
+// xyz_lsq_sgd_step_f64.  Rows are double-buffered by epoch parity (a CTA cannot be two barriers ahead).
+// Launched with cudaLaunchCooperativeKernel (co-residency is guaranteed or the launch fails).
+__global__ void __launch_bounds__(kThreads)
+    lsq_sgd_run_kernel(const xyz_data_point* __restrict__ data, long long n_total, xyz_lsq_parameters* params,
+                       long long batch_size, uint64_t seed, uint64_t epoch0, int n_epochs, const double* __restrict__ lrs,
+                       double* loss_sum, double* partials, int residual_only) {
+    namespace cg = cooperative_groups;
+    cg::grid_group grid = cg::this_grid();
+    __shared__ double red[kThreads / 32][kAcc];
+    __shared__ double s_tot[kAcc];
+    const int tid = threadIdx.x;
+    double a = params->value[0], b = params->value[1], c = params->value[2], d = params->value[3];
+    double loss_running = (loss_sum && blockIdx.x == 0 && tid == 0) ? *loss_sum : 0.0;
+    double last_grad = 0.0;  // thread t < 4 of CTA 0: the last epoch's gradient component t
+    const size_t row_stride = static_cast<size_t>(gridDim.x) * kAcc;
+    for (int e = 0; e < n_epochs; ++e) {
+        const uint64_t epoch = epoch0 + static_cast<uint64_t>(e);
+        const double lr = lrs[e];
+        double* rows = partials + static_cast<size_t>(e & 1) * row_stride;
+        LsqAcc acc;
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) acc.v[k] = 0.0;
+        const uint64_t base = splitmix64(seed ^ (epoch * 0xD1B54A32D192ED03ull));
+        for (long long i = blockIdx.x * static_cast<long long>(kThreads) + tid; i < batch_size;
+             i += static_cast<long long>(gridDim.x) * kThreads) {
+            const uint64_t h = splitmix64(base + static_cast<uint64_t>(i));
+            const double* p = reinterpret_cast<const double*>(data + h % static_cast<uint64_t>(n_total));
+            lsq_point(__ldg(p), __ldg(p + 1), __ldg(p + 2), a, b, c, d, residual_only != 0, acc);
+        }
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) acc.v[k] = warp_sum(acc.v[k]);
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < kAcc; ++k) red[tid >> 5][k] = acc.v[k];
+        }
+        __syncthreads();
+        if (tid < kAcc) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) s += red[w][tid];
+            rows[static_cast<size_t>(blockIdx.x) * kAcc + tid] = s;
+        }
+        grid.sync();  // all rows of this epoch are visible
+        double s[kAcc];
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) s[k] = 0.0;
+        for (unsigned int r = tid; r < gridDim.x; r += kThreads) {
+#pragma unroll
+            for (int k = 0; k < kAcc; ++k) s[k] += __ldcg(rows + static_cast<size_t>(r) * kAcc + k);
+        }
+#pragma unroll
+        for (int k = 0; k < kAcc; ++k) s[k] = warp_sum(s[k]);
+        __syncthreads();  // red is reused
+        if ((tid & 31) == 0) {
+#pragma unroll
+            for (int k = 0; k < kAcc; ++k) red[tid >> 5][k] = s[k];
+        }
+        __syncthreads();
+        if (tid < kAcc) {
+            double t = 0.0;
+#pragma unroll
+            for (int w = 0; w < kThreads / 32; ++w) t += red[w][tid];
+            s_tot[tid] = t;
+            if (blockIdx.x == 0 && tid < 4) last_grad = t;
+        }
+        __syncthreads();
+        // update_parameters_kernel, linear_regression_sgd.cu:126-134 -- the expression of lsq_sgd_step_kernel
+        a -= lr * s_tot[0] / static_cast<double>(batch_size);
+        b -= lr * s_tot[1] / static_cast<double>(batch_size);
+        c -= lr * s_tot[2] / static_cast<double>(batch_size);
+        d -= lr * s_tot[3] / static_cast<double>(batch_size);
+        if (blockIdx.x == 0 && tid == 0) loss_running += s_tot[4];
+    }
+    if (blockIdx.x == 0) {
+        if (tid < 4) params->grad[tid] = last_grad;
+        if (tid == 0) {
+            params->value[0] = a;
+            params->value[1] = b;
+            params->value[2] = c;
+            params->value[3] = d;
+            if (loss_sum) *loss_sum = loss_running;
+        }
+    }
+}
+
 }  // namespace
 }  // namespace xyzb
 
@@ -360,5 +455,54 @@ extern "C" int xyz_lsq_sgd_step_f64(const xyz_data_point* data, long long n_tota
     lsq_sgd_step_kernel<<<grid, kThreads, 0, st>>>(data, n_total, params, batch_size, seed, epoch, learning_rate, loss_sum,
                                                     partials, ticket, (flags & XYZ_FLAG_RESIDUAL_ONLY) ? 1 : 0);
     count_launch();
+    return last_error();
+}
+
+extern "C" int xyz_lsq_sgd_run_f64(const xyz_data_point* data, long long n_total, xyz_lsq_parameters* params,
+                                   long long batch_size, uint64_t seed, uint64_t epoch_begin, int n_epochs,
+                                   const double* learning_rates_host, double* loss_sum, void* stream, int flags) {
+    using namespace xyzb;
+    if (!data || !params || n_total <= 0 || batch_size <= 0 || n_epochs < 0 || (n_epochs > 0 && !learning_rates_host))
+        return XYZ_ERR_INVALID_ARGUMENT;
+    if (n_epochs == 0) return 0;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // the grid of xyz_lsq_sgd_step_f64 (the row order is part of the result), provided it can be co-resident
+    const long long max_ctas = static_cast<long long>(sm_count()) * kCtasPerSM;
+    const long long want = (batch_size + kThreads - 1) / kThreads;
+    const int grid = static_cast<int>(want < max_ctas ? want : max_ctas);
+    int per_sm = 0;
+    cudaError_t ce = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, lsq_sgd_run_kernel, kThreads, 0);
+    int coop = 0, dev = 0;
+    if (ce == cudaSuccess) ce = cudaGetDevice(&dev);
+    if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
+    if (ce != cudaSuccess) return static_cast<int>(ce);
+    const int residual_only = (flags & XYZ_FLAG_RESIDUAL_ONLY) ? 1 : 0;
+    if (!coop || static_cast<long long>(per_sm) * sm_count() < grid) {  // cannot be co-resident: one launch per epoch
+        for (int e = 0; e < n_epochs; ++e) {
+            const int err = xyz_lsq_sgd_step_f64(data, n_total, params, batch_size, seed, epoch_begin + static_cast<uint64_t>(e),
+                                                 learning_rates_host[e], loss_sum, stream, flags);
+            if (err) return err;
+        }
+        return 0;
+    }
+    constexpr int kMaxEpochsPerLaunch = 4096;
+    void* scratch = nullptr;
+    const size_t rows_bytes = 2 * static_cast<size_t>(max_ctas) * kAcc * sizeof(double);
+    int err = scratch_get(SCRATCH_REDUCE, 256 + rows_bytes + kMaxEpochsPerLaunch * sizeof(double), &scratch);
+    if (err) return err;
+    double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+    double* lrs_dev = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256 + rows_bytes);
+    for (int done = 0; done < n_epochs; done += kMaxEpochsPerLaunch) {
+        int n = n_epochs - done < kMaxEpochsPerLaunch ? n_epochs - done : kMaxEpochsPerLaunch;
+        ce = cudaMemcpyAsync(lrs_dev, learning_rates_host + done, sizeof(double) * n, cudaMemcpyHostToDevice, st);
+        if (ce != cudaSuccess) return static_cast<int>(ce);
+        uint64_t epoch0 = epoch_begin + static_cast<uint64_t>(done);
+        const double* lrs_arg = lrs_dev;
+        void* args[] = {&data, &n_total, &params, &batch_size, &seed, &epoch0, &n, &lrs_arg, &loss_sum, &partials,
+                        const_cast<int*>(&residual_only)};
+        ce = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lsq_sgd_run_kernel), dim3(grid), dim3(kThreads), args, 0, st);
+        if (ce != cudaSuccess) return static_cast<int>(ce);
+        count_launch();
+    }
     return last_error();
 }
