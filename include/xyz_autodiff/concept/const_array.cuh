@@ -5,21 +5,33 @@
 #include <concepts>
 #include <cstddef>
 #include <type_traits>
+#include <utility>
 
 namespace xyz_autodiff {
 
+namespace detail {
+
 template <typename A>
-concept ConstArrayLike = requires(A a, std::size_t i) {
+concept NamesElementAndLength = requires {
     typename A::value_type;
     { A::size } -> std::convertible_to<std::size_t>;
-    { a[i] } -> std::convertible_to<typename A::value_type>;
 };
 
+template <typename A>
+concept ReadableByIndex =
+    std::convertible_to<decltype(std::declval<A&>()[std::declval<std::size_t>()]), typename A::value_type>;
+
+}  // namespace detail
+
+template <typename A>
+concept ConstArrayLike = detail::NamesElementAndLength<A> && detail::ReadableByIndex<A>;
+
+// two arrays of the same element type / of the same length
 template <typename A, typename B>
-concept ConstArrayCompatible = ConstArrayLike<A> && ConstArrayLike<B> &&
-    std::same_as<typename A::value_type, typename B::value_type>;
+concept ConstArrayCompatible =
+    ConstArrayLike<A> && ConstArrayLike<B> && std::is_same_v<typename A::value_type, typename B::value_type>;
 
 template <typename A, typename B>
-concept ConstArraySameSize = ConstArrayLike<A> && ConstArrayLike<B> && (A::size == B::size);
+concept ConstArraySameSize = ConstArrayLike<A> && ConstArrayLike<B> && (static_cast<std::size_t>(A::size) == static_cast<std::size_t>(B::size));
 
 }  // namespace xyz_autodiff

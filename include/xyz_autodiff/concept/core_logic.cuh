@@ -1,56 +1,57 @@
 // xyz_autodiff/concept/core_logic.cuh -- the Logic contract: a stateless-or-small functor with
 // `outputDim`, `forward(out, in...)` and `backward(out, in...)`.
-// Contract of reference include/xyz_autodiff/concept/core_logic.cuh:10-75.
+// Contract of reference include/xyz_autodiff/concept/core_logic.cuh:10-75.  One variadic definition serves every
+// arity; the reference's three named concepts (and the three operand constraints used by the factories) are its
+// instances.
 #pragma once
 
 #include <concepts>
+#include <cstddef>
 #include <type_traits>
+#include <utility>
 
 #include "variable.cuh"
 
 namespace xyz_autodiff {
 
 namespace detail {
+
 template <typename L>
 concept HasOutputDim = requires {
     { L::outputDim } -> std::convertible_to<std::size_t>;
 };
+
+// logic.forward(result, const operands...) and logic.backward(const result, operands...) both return void
+template <typename L, typename Result, typename... Operands>
+concept LogicOver = HasOutputDim<L> && VariableConcept<Result> && (VariableConcept<Operands> && ...) &&
+    requires(L logic, Result& result, const Result& frozen_result) {
+        { logic.forward(result, std::declval<const Operands&>()...) } -> std::same_as<void>;
+        { logic.backward(frozen_result, std::declval<Operands&>()...) } -> std::same_as<void>;
+    };
+
+// operands a factory accepts: differentiable, and all of one scalar type
+template <typename First, typename... Others>
+concept OperandsOfOneScalar = DifferentiableVariableConcept<First> && (DifferentiableVariableConcept<Others> && ...) &&
+    (std::is_same_v<typename First::value_type, typename Others::value_type> && ...);
+
 }  // namespace detail
 
 template <typename L, typename Input, typename Output>
-concept UnaryLogicConcept = VariableConcept<Input> && VariableConcept<Output> && detail::HasOutputDim<L> &&
-    requires(L logic, Output& out, const Output& cout, const Input& cin, Input& in) {
-        { logic.forward(out, cin) } -> std::same_as<void>;
-        { logic.backward(cout, in) } -> std::same_as<void>;
-    };
+concept UnaryLogicConcept = detail::LogicOver<L, Output, Input>;
 
 template <typename L, typename Input1, typename Input2, typename Output>
-concept BinaryLogicConcept = VariableConcept<Input1> && VariableConcept<Input2> && VariableConcept<Output> &&
-    detail::HasOutputDim<L> &&
-    requires(L logic, Output& out, const Output& cout, const Input1& c1, const Input2& c2, Input1& i1, Input2& i2) {
-        { logic.forward(out, c1, c2) } -> std::same_as<void>;
-        { logic.backward(cout, i1, i2) } -> std::same_as<void>;
-    };
+concept BinaryLogicConcept = detail::LogicOver<L, Output, Input1, Input2>;
 
 template <typename L, typename Input1, typename Input2, typename Input3, typename Output>
-concept TernaryLogicConcept = VariableConcept<Input1> && VariableConcept<Input2> && VariableConcept<Input3> &&
-    VariableConcept<Output> && detail::HasOutputDim<L> &&
-    requires(L logic, Output& out, const Output& cout, const Input1& c1, const Input2& c2, const Input3& c3, Input1& i1,
-             Input2& i2, Input3& i3) {
-        { logic.forward(out, c1, c2, c3) } -> std::same_as<void>;
-        { logic.backward(cout, i1, i2, i3) } -> std::same_as<void>;
-    };
+concept TernaryLogicConcept = detail::LogicOver<L, Output, Input1, Input2, Input3>;
 
-// Constraints on the operands handed to factories.
 template <typename Input>
-concept UnaryLogicParameterConcept = DifferentiableVariableConcept<Input>;
+concept UnaryLogicParameterConcept = detail::OperandsOfOneScalar<Input>;
 
 template <typename Input1, typename Input2>
-concept BinaryLogicParameterConcept = DifferentiableVariableConcept<Input1> && DifferentiableVariableConcept<Input2> &&
-    std::is_same_v<typename Input1::value_type, typename Input2::value_type>;
+concept BinaryLogicParameterConcept = detail::OperandsOfOneScalar<Input1, Input2>;
 
 template <typename Input1, typename Input2, typename Input3>
-concept TernaryLogicParameterConcept = BinaryLogicParameterConcept<Input1, Input2> &&
-    DifferentiableVariableConcept<Input3> && std::is_same_v<typename Input1::value_type, typename Input3::value_type>;
+concept TernaryLogicParameterConcept = detail::OperandsOfOneScalar<Input1, Input2, Input3>;
 
 }  // namespace xyz_autodiff

@@ -9,15 +9,28 @@
 
 namespace xyz_autodiff {
 
+namespace detail {
+
 template <typename M>
-concept MatrixViewConcept = requires(M m) {
+concept HasStaticExtents = requires {
     typename M::value_type;
     { M::rows } -> std::convertible_to<std::size_t>;
     { M::cols } -> std::convertible_to<std::size_t>;
-    { m(std::size_t{}, std::size_t{}) } -> std::convertible_to<typename M::value_type>;
-    { std::as_const(m)(std::size_t{}, std::size_t{}) } -> std::convertible_to<typename M::value_type>;
-    { m.data() } -> std::convertible_to<const typename M::value_type*>;
-    { m.transpose() };
+};
+
+// (row, column) access on a mutable and on a const view
+template <typename M>
+concept ElementAt = requires(M view, const M const_view, std::size_t r, std::size_t c) {
+    { view(r, c) } -> std::convertible_to<typename M::value_type>;
+    { const_view(r, c) } -> std::convertible_to<typename M::value_type>;
+};
+
+}  // namespace detail
+
+template <typename M>
+concept MatrixViewConcept = detail::HasStaticExtents<M> && detail::ElementAt<M> && requires(M view) {
+    { view.data() } -> std::convertible_to<const typename M::value_type*>;
+    { view.transpose() };
 };
 
 }  // namespace xyz_autodiff

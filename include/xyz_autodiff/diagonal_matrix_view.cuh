@@ -3,50 +3,43 @@
 #pragma once
 
 #include "detail/config.cuh"
+#include "detail/variable_facade.cuh"
 #include "variable.cuh"
 
 namespace xyz_autodiff {
 
 template <typename T, std::size_t N, typename VariableType = VariableRef<N, T>>
-class DiagonalMatrixView {
+class DiagonalMatrixView : public detail::VariableFacade<DiagonalMatrixView<T, N, VariableType>> {
 public:
     using value_type = T;
-    static constexpr std::size_t rows = N;
-    static constexpr std::size_t cols = N;
-    static constexpr std::size_t size = N;  // stored (diagonal) entries
+    static constexpr std::size_t rows = N, cols = N;
+    static constexpr std::size_t size = N;  // stored entries: the diagonal (the variable interface is inherited)
 
-    XYZ_HD DiagonalMatrixView(VariableType& diagonal) : diag_(diagonal) {}
-    DiagonalMatrixView(const DiagonalMatrixView&) = default;
-    DiagonalMatrixView& operator=(const DiagonalMatrixView&) = delete;  // a reference cannot be re-seated
-    DiagonalMatrixView& operator=(DiagonalMatrixView&&) = delete;
+    XYZ_HD DiagonalMatrixView(VariableType& diagonal_entries) : entries_(&diagonal_entries) {}
 
-    // variable interface over the diagonal
-    XYZ_HD T* data() const { return diag_.data(); }
-    XYZ_HD T* grad() const { return diag_.grad(); }
-    XYZ_HD T& operator[](std::size_t i) const { return diag_[i]; }
-    XYZ_HD const T& grad(std::size_t i) const { return diag_.grad(i); }
-    XYZ_HD void add_grad(std::size_t i, T value) const { diag_.add_grad(i, value); }
-    XYZ_HD void zero_grad() const { diag_.zero_grad(); }
-
-    // matrix interface: by value, zero off the diagonal
-    XYZ_HD T operator()(std::size_t r, std::size_t c) { return r == c ? diag_[r] : T{0}; }
-    XYZ_HD constexpr T operator()(std::size_t r, std::size_t c) const { return r == c ? diag_[r] : T{0}; }
+    // matrix interface: entries by value, exact zeros off the diagonal; diag(v) is its own transpose
+    XYZ_HD constexpr T operator()(std::size_t r, std::size_t c) const { return r != c ? T{0} : (*entries_)[r]; }
     XYZ_HD DiagonalMatrixView transpose() const { return *this; }
 
-    XYZ_HD VariableType& underlying_variable() { return diag_; }
-    XYZ_HD const VariableType& underlying_variable() const { return diag_; }
+    XYZ_HD VariableType& underlying_variable() { return *entries_; }
+    XYZ_HD const VariableType& underlying_variable() const { return *entries_; }
+    XYZ_HD VariableType& stored() const { return *entries_; }
+
+    DiagonalMatrixView(const DiagonalMatrixView&) = default;
+    DiagonalMatrixView& operator=(const DiagonalMatrixView&) = delete;  // a view is bound once, like a reference
+    DiagonalMatrixView& operator=(DiagonalMatrixView&&) = delete;
 
 private:
-    VariableType& diag_;
+    VariableType* const entries_;
 };
 
 template <std::size_t N, typename T>
-XYZ_HD auto make_diagonal_matrix_view(VariableRef<N, T>& v) {
-    return DiagonalMatrixView<T, N, VariableRef<N, T>>(v);
+XYZ_HD auto make_diagonal_matrix_view(VariableRef<N, T>& diagonal_entries) {
+    return DiagonalMatrixView<T, N, VariableRef<N, T>>(diagonal_entries);
 }
 template <std::size_t N, typename T>
-XYZ_HD auto make_diagonal_matrix_view(Variable<N, T>& v) {
-    return DiagonalMatrixView<T, N, Variable<N, T>>(v);
+XYZ_HD auto make_diagonal_matrix_view(Variable<N, T>& diagonal_entries) {
+    return DiagonalMatrixView<T, N, Variable<N, T>>(diagonal_entries);
 }
 
 }  // namespace xyz_autodiff

@@ -1,16 +1,29 @@
 // xyz_autodiff/operations/binary/matmul_logic.cuh -- small dense matrix product C(a x c) = A(a x b) B(b x c),
-// row-major, fully unrolled into registers (no tensor cores: 2x2..4x4 chains are not dense
-// contractions).  Contract of reference include/xyz_autodiff/operations/binary/matmul_logic.cuh:13-123;
-// adjoint terms are issued in the reference's order: for each (i, j): all k into A, then all k into B.
+// row-major, fully unrolled into registers (no tensor cores: 2x2..4x4 chains are not dense contractions).
+// Contract of reference include/xyz_autodiff/operations/binary/matmul_logic.cuh:13-123.  The product is walked
+// output element by output element (e = i c + j); per element the adjoint terms go first to row i of A (k ascending),
+// then to column j of B (k ascending) -- the order in which the reference issues them.
 #pragma once
 
+#include "../../detail/pointwise.cuh"
 #include "../operation.cuh"
 
 namespace xyz_autodiff {
+namespace detail {
+// flat index of (row, column) in a row-major matrix with `Columns` columns
+template <std::size_t Columns>
+XYZ_HD constexpr std::size_t row_major(std::size_t row, std::size_t column) {
+    return row * Columns + column;
+}
+// two operands of one scalar type holding exactly LeftCount and RightCount components
+template <typename Left, std::size_t LeftCount, typename Right, std::size_t RightCount>
+concept OperandExtents = BinaryLogicParameterConcept<Left, Right> && (Left::size == LeftCount) && (Right::size == RightCount);
+}  // namespace detail
+
 namespace op {
 
 template <std::size_t a, std::size_t b, std::size_t c, typename Input1, typename Input2>
-    requires BinaryLogicParameterConcept<Input1, Input2> && (Input1::size == a * b) && (Input2::size == b * c)
+    requires detail::OperandExtents<Input1, a * b, Input2, b * c>
 struct MatMulLogic {
     using T = typename Input1::value_type;
     static constexpr std::size_t rows_A = a;
@@ -20,72 +33,56 @@ struct MatMulLogic {
     static constexpr std::size_t outputDim = output_size;
     using Output = Variable<output_size, T>;
 
-    XYZ_HD void forward(Output& C, const Input1& A, const Input2& B) const {
+    XYZ_HD void forward(Output& product, const Input1& left, const Input2& right) const {
 #pragma unroll
-        for (std::size_t i = 0; i < a; ++i) {
+        for (std::size_t e = 0; e < output_size; ++e) {
+            const std::size_t i = e / c, j = e % c;
+            T dot = T(0);
 #pragma unroll
-            for (std::size_t j = 0; j < c; ++j) {
-                T acc = T(0);
-#pragma unroll
-                for (std::size_t k = 0; k < b; ++k) acc += A[i * b + k] * B[k * c + j];
-                C[i * c + j] = acc;
-            }
+            for (std::size_t k = 0; k < b; ++k) dot += left[detail::row_major<b>(i, k)] * right[detail::row_major<c>(k, j)];
+            product[e] = dot;
         }
     }
 
-    XYZ_HD void backward(const Output& C, Input1& A, Input2& B) const {
+    XYZ_HD void backward(const Output& product, Input1& left, Input2& right) const {
 #pragma unroll
-        for (std::size_t i = 0; i < a; ++i) {
+        for (std::size_t e = 0; e < output_size; ++e) {
+            const std::size_t i = e / c, j = e % c;
+            const T upstream = product.grad(e);
 #pragma unroll
-            for (std::size_t j = 0; j < c; ++j) {
-                const T g = C.grad(i * c + j);
+            for (std::size_t k = 0; k < b; ++k)
+                left.add_grad(detail::row_major<b>(i, k), upstream * right[detail::row_major<c>(k, j)]);
 #pragma unroll
-                for (std::size_t k = 0; k < b; ++k) A.add_grad(i * b + k, g * B[k * c + j]);
-#pragma unroll
-                for (std::size_t k = 0; k < b; ++k) B.add_grad(k * c + j, g * A[i * b + k]);
-            }
+            for (std::size_t k = 0; k < b; ++k)
+                right.add_grad(detail::row_major<c>(k, j), upstream * left[detail::row_major<b>(i, k)]);
         }
     }
 };
 
 template <std::size_t a, std::size_t b, std::size_t c, typename Input1, typename Input2>
-    requires BinaryLogicParameterConcept<Input1, Input2> && (Input1::size == a * b) && (Input2::size == b * c)
+    requires detail::OperandExtents<Input1, a * b, Input2, b * c>
 XYZ_HD auto matmul(Input1& A, Input2& B) {
-    using Logic = MatMulLogic<a, b, c, Input1, Input2>;
-    return BinaryOperation<Logic::outputDim, Logic, Input1, Input2>(Logic{}, A, B);
+    return detail::make_binary_node<MatMulLogic<a, b, c, Input1, Input2>>(A, B);
 }
 
-template <typename Input1, typename Input2>
-    requires BinaryLogicParameterConcept<Input1, Input2> && (Input1::size == 4) && (Input2::size == 4)
-XYZ_HD auto matmul_2x2(Input1& A, Input2& B) {
-    return matmul<2, 2, 2>(A, B);
-}
-
-template <typename Input1, typename Input2>
-    requires BinaryLogicParameterConcept<Input1, Input2> && (Input1::size == 9) && (Input2::size == 9)
-XYZ_HD auto matmul_3x3(Input1& A, Input2& B) {
-    return matmul<3, 3, 3>(A, B);
-}
-
-template <typename Input1, typename Input2>
-    requires BinaryLogicParameterConcept<Input1, Input2> && (Input1::size == 16) && (Input2::size == 16)
-XYZ_HD auto matmul_4x4(Input1& A, Input2& B) {
-    return matmul<4, 4, 4>(A, B);
-}
-
-// A (m x n) times a column vector
-template <std::size_t m, std::size_t n, typename Input1, typename Input2>
-    requires BinaryLogicParameterConcept<Input1, Input2> && (Input1::size == m * n) && (Input2::size == n)
-XYZ_HD auto matvec(Input1& A, Input2& x) {
-    return matmul<m, n, 1>(A, x);
-}
-
-// a row vector times A (m x n)
-template <std::size_t m, std::size_t n, typename Input1, typename Input2>
-    requires BinaryLogicParameterConcept<Input1, Input2> && (Input1::size == m) && (Input2::size == m * n)
-XYZ_HD auto vecmat(Input1& x, Input2& A) {
-    return matmul<1, m, n>(x, A);
-}
+// The reference's named shapes, all instances of matmul<rows, inner, columns>: NAME(left, right) with the operand
+// lengths LEFT and RIGHT; matvec / vecmat take their shape as template arguments <m, n>.
+#define XYZ_AUTODIFF_MATMUL_ALIAS(NAME, SHAPE_PARAMS, LEFT, RIGHT, ...)                   \
+    template <SHAPE_PARAMS typename Input1, typename Input2>                              \
+        requires detail::OperandExtents<Input1, LEFT, Input2, RIGHT>                      \
+    XYZ_HD auto NAME(Input1& left, Input2& right) {                                       \
+        return matmul<__VA_ARGS__>(left, right);                                          \
+    }
+#define XYZ_AUTODIFF_NO_SHAPE
+#define XYZ_AUTODIFF_MN std::size_t m, std::size_t n,
+XYZ_AUTODIFF_MATMUL_ALIAS(matmul_2x2, XYZ_AUTODIFF_NO_SHAPE, 4, 4, 2, 2, 2)
+XYZ_AUTODIFF_MATMUL_ALIAS(matmul_3x3, XYZ_AUTODIFF_NO_SHAPE, 9, 9, 3, 3, 3)
+XYZ_AUTODIFF_MATMUL_ALIAS(matmul_4x4, XYZ_AUTODIFF_NO_SHAPE, 16, 16, 4, 4, 4)
+XYZ_AUTODIFF_MATMUL_ALIAS(matvec, XYZ_AUTODIFF_MN, m * n, n, m, n, 1)  // A (m x n) times a column vector
+XYZ_AUTODIFF_MATMUL_ALIAS(vecmat, XYZ_AUTODIFF_MN, m, m * n, 1, m, n)  // a row vector times A (m x n)
+#undef XYZ_AUTODIFF_MN
+#undef XYZ_AUTODIFF_NO_SHAPE
+#undef XYZ_AUTODIFF_MATMUL_ALIAS
 
 }  // namespace op
 }  // namespace xyz_autodiff

@@ -2,39 +2,34 @@
 // Contract of reference include/xyz_autodiff/operations/binary/mul_logic.cuh:11-50.
 #pragma once
 
+#include "../../detail/pointwise.cuh"
 #include "../operation.cuh"
 
 namespace xyz_autodiff {
+namespace detail::rule {
+struct Product {
+    template <typename S>
+    XYZ_HD static S value(S a, S b) {
+        return a * b;
+    }
+    template <typename S>
+    XYZ_HD static void pullback(S a, S b, S g, S& to_a, S& to_b) {
+        to_a = g * b;
+        to_b = g * a;
+    }
+};
+}  // namespace detail::rule
+
 namespace op {
 
 template <typename Input1, typename Input2>
     requires BinaryLogicParameterConcept<Input1, Input2> && (Input1::size == Input2::size)
-struct MulLogic {
-    using T = typename Input1::value_type;
-    static constexpr std::size_t Dim = Input1::size;
-    static constexpr std::size_t outputDim = Dim;
-    using Output = Variable<Dim, T>;
-
-    XYZ_HD void forward(Output& y, const Input1& a, const Input2& b) const {
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) y[i] = a[i] * b[i];
-    }
-
-    XYZ_HD void backward(const Output& y, Input1& a, Input2& b) const {
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) {
-            const T g = y.grad(i);
-            a.add_grad(i, g * b[i]);
-            b.add_grad(i, g * a[i]);
-        }
-    }
-};
+struct MulLogic : detail::PointwisePair<Input1, Input2, detail::rule::Product> {};
 
 template <typename Input1, typename Input2>
     requires BinaryLogicParameterConcept<Input1, Input2>
 XYZ_HD auto mul(Input1& a, Input2& b) {
-    using Logic = MulLogic<Input1, Input2>;
-    return BinaryOperation<Logic::outputDim, Logic, Input1, Input2>(Logic{}, a, b);
+    return detail::make_binary_node<MulLogic<Input1, Input2>>(a, b);
 }
 
 }  // namespace op

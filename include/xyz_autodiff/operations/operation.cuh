@@ -28,6 +28,7 @@
 #include "../concept/operation_node.cuh"
 #include "../concept/variable.cuh"
 #include "../detail/config.cuh"
+#include "../detail/traversal.cuh"
 #include "../variable.cuh"
 
 namespace xyz_autodiff {
@@ -66,26 +67,26 @@ public:
         : OperandSlot<Is, Operands>(static_cast<OperandSlot<Is, Operands>&>(other).ref)...,
           logic_(other.logic_),
           output_(other.output_),
-          pending_consumers_(0) {}
+          consumers_() {}
 
     // Construction does not evaluate anything: the output starts at zero until forward() runs.
     XYZ_HD GraphNode(const Logic& logic, Operands&... operands)
-        : OperandSlot<Is, Operands>(operands)..., logic_(logic), output_(), pending_consumers_(0) {}
+        : OperandSlot<Is, Operands>(operands)..., logic_(logic), output_(), consumers_() {}
 
     XYZ_HD void forward() {
-        (forward_operand(operand<Is>()), ...);
+        (sweep_down(operand<Is>()), ...);
         logic_.forward(output_, operand<Is>()...);
     }
 
     XYZ_HD void backward() {
         logic_.backward(output_, operand<Is>()...);
-        (backward_operand(operand<Is>()), ...);
+        (sweep_up(operand<Is>()), ...);
     }
 
     XYZ_HD void backward_numerical(const value_type delta = value_type(1e-5)) {
         const output_type saved = output_;
         (numerical_operand(operand<Is>(), saved, delta), ...);
-        (backward_numerical_operand(operand<Is>(), delta), ...);
+        (sweep_up_numerically(operand<Is>(), delta), ...);
     }
 
     XYZ_HD void run() {
@@ -101,8 +102,8 @@ public:
     }
 
     // DAG bookkeeping: one increment per consumer's forward(), one decrement per consumer's backward().
-    XYZ_HD void increment_ref_count() const { ++pending_consumers_; }
-    XYZ_HD bool decrement_ref_count_and_check() const { return --pending_consumers_ == 0; }
+    XYZ_HD void increment_ref_count() const { consumers_.check_in(); }
+    XYZ_HD bool decrement_ref_count_and_check() const { return consumers_.check_out_was_last(); }
 
     // The node is itself a (differentiable) variable: consumers read its output and add to its adjoint.
     XYZ_HD output_type& output() { return output_; }
@@ -131,26 +132,6 @@ private:
         for (std::size_t j = 0; j < OutputSize; ++j) output_.add_grad(j, value_type(1));
     }
 
-    template <typename Operand>
-    XYZ_HD static void forward_operand(Operand& x) {
-        if constexpr (OperationNode<Operand>) {
-            x.forward();
-            x.increment_ref_count();
-        }
-    }
-    template <typename Operand>
-    XYZ_HD static void backward_operand(Operand& x) {
-        if constexpr (OperationNode<Operand>) {
-            if (x.decrement_ref_count_and_check()) x.backward();
-        }
-    }
-    template <typename Operand>
-    XYZ_HD static void backward_numerical_operand(Operand& x, value_type delta) {
-        if constexpr (OperationNode<Operand>) {
-            if (x.decrement_ref_count_and_check()) x.backward_numerical(delta);
-        }
-    }
-
     // central differences of logic.forward w.r.t. every component of one operand
     template <typename Operand>
     XYZ_HD void numerical_operand(Operand& x, const output_type& saved, value_type delta) {
@@ -173,7 +154,7 @@ private:
 
     Logic logic_;
     output_type output_;
-    mutable std::uint8_t pending_consumers_;
+    ConsumerLedger consumers_;
 };
 
 }  // namespace detail

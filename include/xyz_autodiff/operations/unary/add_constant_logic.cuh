@@ -2,39 +2,36 @@
 // Contract of reference include/xyz_autodiff/operations/unary/add_constant_logic.cuh:11-48.
 #pragma once
 
+#include "../../detail/pointwise.cuh"
 #include "../operation.cuh"
 
 namespace xyz_autodiff {
+namespace detail::rule {
+struct ShiftUp {
+    template <typename S>
+    XYZ_HD static S value(S x, S c) {
+        return x + c;
+    }
+    template <typename S>
+    XYZ_HD static S pullback(S g, S c) {
+        (void)c;
+        return g;
+    }
+};
+}  // namespace detail::rule
+
 namespace op {
 
 template <typename Input>
     requires UnaryLogicParameterConcept<Input>
-struct AddConstantLogic {
-    using T = typename Input::value_type;
-    static constexpr std::size_t Dim = Input::size;
-    static constexpr std::size_t outputDim = Dim;
-    using Output = Variable<Dim, T>;
-
-    T constant_c;
-
-    XYZ_HD explicit AddConstantLogic(T c) : constant_c(c) {}
-
-    XYZ_HD void forward(Output& y, const Input& x) const {
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) y[i] = x[i] + constant_c;
-    }
-
-    XYZ_HD void backward(const Output& y, Input& x) const {
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) x.add_grad(i, y.grad(i));
-    }
+struct AddConstantLogic : detail::PointwiseWithScalar<Input, detail::rule::ShiftUp> {
+    using detail::PointwiseWithScalar<Input, detail::rule::ShiftUp>::PointwiseWithScalar;
 };
 
 template <typename Input>
     requires UnaryLogicParameterConcept<Input>
 XYZ_HD auto add_constant(Input& x, typename Input::value_type constant) {
-    using Logic = AddConstantLogic<Input>;
-    return UnaryOperation<Logic::outputDim, Logic, Input>(Logic(constant), x);
+    return detail::make_unary_node<AddConstantLogic<Input>>(x, constant);
 }
 
 }  // namespace op

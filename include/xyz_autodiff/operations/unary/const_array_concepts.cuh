@@ -5,15 +5,15 @@
 #include <concepts>
 #include <cstddef>
 #include <type_traits>
+#include <utility>
 
 namespace xyz_autodiff {
 namespace op {
 
-// indexable with a value_type: ConstArray, Variable, VariableRef, operation nodes, ...
+// Anything that names its element type and can be subscripted: ConstArray, Variable, VariableRef, operation nodes.
 template <typename A>
-concept ArrayLikeConcept = requires(A a, std::size_t i) {
-    { a[i] } -> std::convertible_to<typename std::remove_reference_t<A>::value_type>;
-};
+concept ArrayLikeConcept =
+    std::convertible_to<decltype(std::declval<A&>()[std::size_t{}]), typename std::remove_reference_t<A>::value_type>;
 
 }  // namespace op
 }  // namespace xyz_autodiff

@@ -2,43 +2,33 @@
 // Contract of reference include/xyz_autodiff/operations/unary/exp_logic.cuh:13-51.
 #pragma once
 
+#include "../../detail/pointwise.cuh"
 #include "../math.cuh"
 #include "../operation.cuh"
 
 namespace xyz_autodiff {
+namespace detail::rule {
+struct Exponential {
+    template <typename S>
+    XYZ_HD static S value(S x) {
+        return math::exp(x);
+    }
+    template <typename S>
+    XYZ_HD static S pullback(S x, S g) {
+        return g * math::exp(x);
+    }
+};
+}  // namespace detail::rule
+
 namespace op {
 
 template <std::size_t Dim>
-struct ExpLogic {
-    static constexpr std::size_t outputDim = Dim;
-
-    template <typename Output, typename Input>
-    XYZ_HD void forward(Output& y, const Input& x) const {
-        using T = typename Input::value_type;
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) {
-            const T v = x[i];
-            y[i] = math::exp(v);
-        }
-    }
-
-    // the local derivative is recomputed from the INPUT (nothing is cached between the passes)
-    template <typename Output, typename Input>
-    XYZ_HD void backward(const Output& y, Input& x) const {
-        using T = typename Input::value_type;
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) {
-            const T v = x[i];
-            const T g = y.grad(i);
-            x.add_grad(i, g * math::exp(v));
-        }
-    }
-};
+struct ExpLogic : detail::PointwiseMap<Dim, detail::rule::Exponential> {};
 
 template <std::size_t Dim, DifferentiableVariableConcept Input>
     requires(Input::size == Dim)
 XYZ_HD auto exp(Input& x) {
-    return UnaryOperation<Dim, ExpLogic<Dim>, Input>(ExpLogic<Dim>{}, x);
+    return detail::make_unary_node<ExpLogic<Dim>>(x);
 }
 
 template <DifferentiableVariableConcept Input>

@@ -2,42 +2,44 @@
 // Contract of reference include/xyz_autodiff/operations/unary/l1_norm_logic.cuh:13-54.
 #pragma once
 
+#include "../../detail/pointwise.cuh"
 #include "../math.cuh"
 #include "../operation.cuh"
 
 namespace xyz_autodiff {
+namespace detail::rule {
+struct AbsoluteSum {
+    template <typename S>
+    XYZ_HD static S term(S x) {
+        return math::abs(x);
+    }
+    template <typename S>
+    XYZ_HD static S finish(S total) {
+        return total;
+    }
+    template <typename S>
+    XYZ_HD static bool has_adjoint(S result) {
+        (void)result;
+        return true;
+    }
+    template <typename S>
+    XYZ_HD static S pullback(S x, S result, S g) {
+        (void)result;
+        const S sign = x > S(0) ? S(1) : (x < S(0) ? S(-1) : S(0));  // subgradient 0 at the kink
+        return g * sign;
+    }
+};
+}  // namespace detail::rule
+
 namespace op {
 
 template <std::size_t InputDim>
-struct L1NormLogic {
-    static constexpr std::size_t outputDim = 1;
-
-    template <typename Output, typename Input>
-    XYZ_HD void forward(Output& y, const Input& x) const {
-        using T = typename Input::value_type;
-        T acc = T(0);
-#pragma unroll
-        for (std::size_t i = 0; i < InputDim; ++i) acc += math::abs(x[i]);
-        y[0] = acc;
-    }
-
-    template <typename Output, typename Input>
-    XYZ_HD void backward(const Output& y, Input& x) const {
-        using T = typename Input::value_type;
-        const T g = y.grad(0);
-#pragma unroll
-        for (std::size_t i = 0; i < InputDim; ++i) {
-            const T v = x[i];
-            const T s = v > T(0) ? T(1) : (v < T(0) ? T(-1) : T(0));  // subgradient 0 at the kink
-            x.add_grad(i, g * s);
-        }
-    }
-};
+struct L1NormLogic : detail::FoldToScalar<InputDim, detail::rule::AbsoluteSum> {};
 
 template <std::size_t Dim, DifferentiableVariableConcept Input>
     requires(Input::size == Dim)
 XYZ_HD auto l1_norm(Input& x) {
-    return UnaryOperation<1, L1NormLogic<Dim>, Input>(L1NormLogic<Dim>{}, x);
+    return detail::make_unary_node<L1NormLogic<Dim>>(x);
 }
 
 template <DifferentiableVariableConcept Input>

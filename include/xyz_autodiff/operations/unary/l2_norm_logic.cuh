@@ -2,41 +2,41 @@
 // Contract of reference include/xyz_autodiff/operations/unary/l2_norm_logic.cuh:13-57.
 #pragma once
 
+#include "../../detail/pointwise.cuh"
 #include "../math.cuh"
 #include "../operation.cuh"
 
 namespace xyz_autodiff {
+namespace detail::rule {
+struct EuclideanLength {
+    template <typename S>
+    XYZ_HD static S term(S x) {
+        return x * x;
+    }
+    template <typename S>
+    XYZ_HD static S finish(S total) {
+        return math::sqrt(total);
+    }
+    template <typename S>
+    XYZ_HD static bool has_adjoint(S result) {
+        return result > S(1e-8);  // no adjoint at (numerically) zero vectors, like the reference
+    }
+    template <typename S>
+    XYZ_HD static S pullback(S x, S result, S g) {
+        return g * x / result;
+    }
+};
+}  // namespace detail::rule
+
 namespace op {
 
 template <std::size_t InputDim>
-struct L2NormLogic {
-    static constexpr std::size_t outputDim = 1;
-
-    template <typename Output, typename Input>
-    XYZ_HD void forward(Output& y, const Input& x) const {
-        using T = typename Input::value_type;
-        T acc = T(0);
-#pragma unroll
-        for (std::size_t i = 0; i < InputDim; ++i) acc += x[i] * x[i];
-        y[0] = math::sqrt(acc);
-    }
-
-    template <typename Output, typename Input>
-    XYZ_HD void backward(const Output& y, Input& x) const {
-        using T = typename Input::value_type;
-        const T g = y.grad(0);
-        const T norm = y[0];
-        if (norm > T(1e-8)) {  // no adjoint at (numerically) zero vectors, like the reference
-#pragma unroll
-            for (std::size_t i = 0; i < InputDim; ++i) x.add_grad(i, g * x[i] / norm);
-        }
-    }
-};
+struct L2NormLogic : detail::FoldToScalar<InputDim, detail::rule::EuclideanLength> {};
 
 template <std::size_t Dim, DifferentiableVariableConcept Input>
     requires(Input::size == Dim)
 XYZ_HD auto l2_norm(Input& x) {
-    return UnaryOperation<1, L2NormLogic<Dim>, Input>(L2NormLogic<Dim>{}, x);
+    return detail::make_unary_node<L2NormLogic<Dim>>(x);
 }
 
 template <DifferentiableVariableConcept Input>

@@ -2,39 +2,35 @@
 // Contract of reference include/xyz_autodiff/operations/unary/mul_constant_logic.cuh:11-48.
 #pragma once
 
+#include "../../detail/pointwise.cuh"
 #include "../operation.cuh"
 
 namespace xyz_autodiff {
+namespace detail::rule {
+struct ScaleBy {
+    template <typename S>
+    XYZ_HD static S value(S x, S c) {
+        return x * c;
+    }
+    template <typename S>
+    XYZ_HD static S pullback(S g, S c) {
+        return g * c;
+    }
+};
+}  // namespace detail::rule
+
 namespace op {
 
 template <typename Input>
     requires UnaryLogicParameterConcept<Input>
-struct MulConstantLogic {
-    using T = typename Input::value_type;
-    static constexpr std::size_t Dim = Input::size;
-    static constexpr std::size_t outputDim = Dim;
-    using Output = Variable<Dim, T>;
-
-    T constant_c;
-
-    XYZ_HD explicit MulConstantLogic(T c) : constant_c(c) {}
-
-    XYZ_HD void forward(Output& y, const Input& x) const {
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) y[i] = x[i] * constant_c;
-    }
-
-    XYZ_HD void backward(const Output& y, Input& x) const {
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) x.add_grad(i, y.grad(i) * constant_c);
-    }
+struct MulConstantLogic : detail::PointwiseWithScalar<Input, detail::rule::ScaleBy> {
+    using detail::PointwiseWithScalar<Input, detail::rule::ScaleBy>::PointwiseWithScalar;
 };
 
 template <typename Input>
     requires UnaryLogicParameterConcept<Input>
 XYZ_HD auto mul_constant(Input& x, typename Input::value_type constant) {
-    using Logic = MulConstantLogic<Input>;
-    return UnaryOperation<Logic::outputDim, Logic, Input>(Logic(constant), x);
+    return detail::make_unary_node<MulConstantLogic<Input>>(x, constant);
 }
 
 }  // namespace op

@@ -2,41 +2,34 @@
 // Contract of reference include/xyz_autodiff/operations/unary/neg_logic.cuh:13-49.
 #pragma once
 
+#include "../../detail/pointwise.cuh"
 #include "../math.cuh"
 #include "../operation.cuh"
 
 namespace xyz_autodiff {
+namespace detail::rule {
+struct Negation {
+    template <typename S>
+    XYZ_HD static S value(S x) {
+        return -x;
+    }
+    template <typename S>
+    XYZ_HD static S pullback(S x, S g) {
+        (void)x;
+        return -g;
+    }
+};
+}  // namespace detail::rule
+
 namespace op {
 
 template <std::size_t Dim>
-struct NegLogic {
-    static constexpr std::size_t outputDim = Dim;
-
-    template <typename Output, typename Input>
-    XYZ_HD void forward(Output& y, const Input& x) const {
-        using T = typename Input::value_type;
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) {
-            const T v = x[i];
-            y[i] = -v;
-        }
-    }
-
-    template <typename Output, typename Input>
-    XYZ_HD void backward(const Output& y, Input& x) const {
-        using T = typename Input::value_type;
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) {
-            const T g = y.grad(i);
-            x.add_grad(i, -g);
-        }
-    }
-};
+struct NegLogic : detail::PointwiseMap<Dim, detail::rule::Negation> {};
 
 template <std::size_t Dim, DifferentiableVariableConcept Input>
     requires(Input::size == Dim)
 XYZ_HD auto neg(Input& x) {
-    return UnaryOperation<Dim, NegLogic<Dim>, Input>(NegLogic<Dim>{}, x);
+    return detail::make_unary_node<NegLogic<Dim>>(x);
 }
 
 template <DifferentiableVariableConcept Input>

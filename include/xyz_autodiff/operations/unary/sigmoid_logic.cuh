@@ -2,44 +2,34 @@
 // Contract of reference include/xyz_autodiff/operations/unary/sigmoid_logic.cuh:13-52.
 #pragma once
 
+#include "../../detail/pointwise.cuh"
 #include "../math.cuh"
 #include "../operation.cuh"
 
 namespace xyz_autodiff {
+namespace detail::rule {
+struct Logistic {
+    template <typename S>
+    XYZ_HD static S value(S x) {
+        return math::sigmoid(x);
+    }
+    template <typename S>
+    XYZ_HD static S pullback(S x, S g) {
+        const S s = math::sigmoid(x);
+        return g * (s * (S(1) - s));
+    }
+};
+}  // namespace detail::rule
+
 namespace op {
 
 template <std::size_t Dim>
-struct SigmoidLogic {
-    static constexpr std::size_t outputDim = Dim;
-
-    template <typename Output, typename Input>
-    XYZ_HD void forward(Output& y, const Input& x) const {
-        using T = typename Input::value_type;
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) {
-            const T v = x[i];
-            y[i] = math::sigmoid(v);
-        }
-    }
-
-    // the local derivative is recomputed from the INPUT (nothing is cached between the passes)
-    template <typename Output, typename Input>
-    XYZ_HD void backward(const Output& y, Input& x) const {
-        using T = typename Input::value_type;
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) {
-            const T v = x[i];
-            const T g = y.grad(i);
-            const T s = math::sigmoid(v);
-            x.add_grad(i, g * (s * (T(1) - s)));
-        }
-    }
-};
+struct SigmoidLogic : detail::PointwiseMap<Dim, detail::rule::Logistic> {};
 
 template <std::size_t Dim, DifferentiableVariableConcept Input>
     requires(Input::size == Dim)
 XYZ_HD auto sigmoid(Input& x) {
-    return UnaryOperation<Dim, SigmoidLogic<Dim>, Input>(SigmoidLogic<Dim>{}, x);
+    return detail::make_unary_node<SigmoidLogic<Dim>>(x);
 }
 
 template <DifferentiableVariableConcept Input>

@@ -2,43 +2,33 @@
 // Contract of reference include/xyz_autodiff/operations/unary/sin_logic.cuh:13-51.
 #pragma once
 
+#include "../../detail/pointwise.cuh"
 #include "../math.cuh"
 #include "../operation.cuh"
 
 namespace xyz_autodiff {
+namespace detail::rule {
+struct Sine {
+    template <typename S>
+    XYZ_HD static S value(S x) {
+        return math::sin(x);
+    }
+    template <typename S>
+    XYZ_HD static S pullback(S x, S g) {
+        return g * math::cos(x);
+    }
+};
+}  // namespace detail::rule
+
 namespace op {
 
 template <std::size_t Dim>
-struct SinLogic {
-    static constexpr std::size_t outputDim = Dim;
-
-    template <typename Output, typename Input>
-    XYZ_HD void forward(Output& y, const Input& x) const {
-        using T = typename Input::value_type;
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) {
-            const T v = x[i];
-            y[i] = math::sin(v);
-        }
-    }
-
-    // the local derivative is recomputed from the INPUT (nothing is cached between the passes)
-    template <typename Output, typename Input>
-    XYZ_HD void backward(const Output& y, Input& x) const {
-        using T = typename Input::value_type;
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) {
-            const T v = x[i];
-            const T g = y.grad(i);
-            x.add_grad(i, g * math::cos(v));
-        }
-    }
-};
+struct SinLogic : detail::PointwiseMap<Dim, detail::rule::Sine> {};
 
 template <std::size_t Dim, DifferentiableVariableConcept Input>
     requires(Input::size == Dim)
 XYZ_HD auto sin(Input& x) {
-    return UnaryOperation<Dim, SinLogic<Dim>, Input>(SinLogic<Dim>{}, x);
+    return detail::make_unary_node<SinLogic<Dim>>(x);
 }
 
 template <DifferentiableVariableConcept Input>

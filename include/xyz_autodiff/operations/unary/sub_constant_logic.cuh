@@ -1,40 +1,37 @@
-// xyz_autodiff/operations/unary/sub_constant_logic.cuh -- shift (subtraction) by a scalar constant held in the Logic.
+// xyz_autodiff/operations/unary/sub_constant_logic.cuh -- shift down by a scalar constant held in the Logic.
 // Contract of reference include/xyz_autodiff/operations/unary/sub_constant_logic.cuh:11-48.
 #pragma once
 
+#include "../../detail/pointwise.cuh"
 #include "../operation.cuh"
 
 namespace xyz_autodiff {
+namespace detail::rule {
+struct ShiftDown {
+    template <typename S>
+    XYZ_HD static S value(S x, S c) {
+        return x - c;
+    }
+    template <typename S>
+    XYZ_HD static S pullback(S g, S c) {
+        (void)c;
+        return g;
+    }
+};
+}  // namespace detail::rule
+
 namespace op {
 
 template <typename Input>
     requires UnaryLogicParameterConcept<Input>
-struct SubConstantLogic {
-    using T = typename Input::value_type;
-    static constexpr std::size_t Dim = Input::size;
-    static constexpr std::size_t outputDim = Dim;
-    using Output = Variable<Dim, T>;
-
-    T constant_c;
-
-    XYZ_HD explicit SubConstantLogic(T c) : constant_c(c) {}
-
-    XYZ_HD void forward(Output& y, const Input& x) const {
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) y[i] = x[i] - constant_c;
-    }
-
-    XYZ_HD void backward(const Output& y, Input& x) const {
-#pragma unroll
-        for (std::size_t i = 0; i < Dim; ++i) x.add_grad(i, y.grad(i));
-    }
+struct SubConstantLogic : detail::PointwiseWithScalar<Input, detail::rule::ShiftDown> {
+    using detail::PointwiseWithScalar<Input, detail::rule::ShiftDown>::PointwiseWithScalar;
 };
 
 template <typename Input>
     requires UnaryLogicParameterConcept<Input>
 XYZ_HD auto sub_constant(Input& x, typename Input::value_type constant) {
-    using Logic = SubConstantLogic<Input>;
-    return UnaryOperation<Logic::outputDim, Logic, Input>(Logic(constant), x);
+    return detail::make_unary_node<SubConstantLogic<Input>>(x, constant);
 }
 
 }  // namespace op

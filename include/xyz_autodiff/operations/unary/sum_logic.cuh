@@ -2,38 +2,44 @@
 // Contract of reference include/xyz_autodiff/operations/unary/sum_logic.cuh:13-53.
 #pragma once
 
+#include "../../detail/pointwise.cuh"
 #include "../math.cuh"
 #include "../operation.cuh"
 
 namespace xyz_autodiff {
+namespace detail::rule {
+struct PlainSum {
+    template <typename S>
+    XYZ_HD static S term(S x) {
+        return x;
+    }
+    template <typename S>
+    XYZ_HD static S finish(S total) {
+        return total;
+    }
+    template <typename S>
+    XYZ_HD static bool has_adjoint(S result) {
+        (void)result;
+        return true;
+    }
+    template <typename S>
+    XYZ_HD static S pullback(S x, S result, S g) {
+        (void)x;
+        (void)result;
+        return g;
+    }
+};
+}  // namespace detail::rule
+
 namespace op {
 
 template <std::size_t InputDim>
-struct SumLogic {
-    static constexpr std::size_t outputDim = 1;
-
-    template <typename Output, typename Input>
-    XYZ_HD void forward(Output& y, const Input& x) const {
-        using T = typename Input::value_type;
-        T acc = T(0);
-#pragma unroll
-        for (std::size_t i = 0; i < InputDim; ++i) acc += x[i];
-        y[0] = acc;
-    }
-
-    template <typename Output, typename Input>
-    XYZ_HD void backward(const Output& y, Input& x) const {
-        using T = typename Input::value_type;
-        const T g = y.grad(0);
-#pragma unroll
-        for (std::size_t i = 0; i < InputDim; ++i) x.add_grad(i, g);
-    }
-};
+struct SumLogic : detail::FoldToScalar<InputDim, detail::rule::PlainSum> {};
 
 template <std::size_t Dim, DifferentiableVariableConcept Input>
     requires(Input::size == Dim)
 XYZ_HD auto sum(Input& x) {
-    return UnaryOperation<1, SumLogic<Dim>, Input>(SumLogic<Dim>{}, x);
+    return detail::make_unary_node<SumLogic<Dim>>(x);
 }
 
 template <DifferentiableVariableConcept Input>
