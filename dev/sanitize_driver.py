@@ -1,0 +1,49 @@
+"""dev/sanitize_driver.py -- one modest-size call of every kernel added late in round 1, for compute-sanitizer:
+  compute-sanitizer --tool memcheck|racecheck python dev/sanitize_driver.py
+(striped accumulation incl. deterministic rows and implicit ids, shared-W chain, multi-epoch SGD, batched::for_each)."""
+import ctypes, os, sys
+import numpy as np, torch
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT); sys.path.insert(0, os.path.join(ROOT, "tests"))
+import oracle_lib as orc
+import xyz_autodiff_cuda_b200 as x
+dev = torch.device("cuda:0")
+D = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)
+# striped accumulation: T = 3 (K = 1024), T = 12 (K = 5), T = 2 (K = 1700); partial last unit; deterministic; implicit ids
+for k, n in ((1024, (1 << 17) + 77), (5, 1 << 16), (1700, 70_001)):
+    for dist in ("uniform", "same"):
+        idx, val = orc.accumulate_inputs(n, k, dist, seed=k)
+        for flags in (0, x.FLAG_DETERMINISTIC):
+            g = torch.zeros(k, device=dev)
+            x.accumulate(D(idx), D(val), g, flags)
+            ex = orc.accumulate_exact(idx, val, k)
+            assert np.allclose(g.cpu().numpy(), ex, rtol=0, atol=1e-4 * np.abs(val).sum()), (k, dist, flags)
+    g = torch.zeros(k, device=dev)
+    x.accumulate(None, D(val), g)
+# shared-W chain: TMA path + tail, and the plain path
+J, W, S, gg = orc.covproj_inputs(5000 + 13, seed=1)
+for sl in (slice(None), slice(1, 900)):
+    n = J[sl].shape[0]
+    o, gJ, gS = [torch.empty((n, w), device=dev) for w in (3, 6, 6)]
+    gW = torch.zeros(9, device=dev)
+    x.covproj_shared_w_fwd_bwd(D(J[sl]), D(W[0]), D(S[sl]), D(gg[sl]), o, gJ, gW, gS)
+# multi-epoch SGD (cooperative launch)
+data = D(orc.lsq_data(20_000, seed=2))
+p = torch.zeros(8, dtype=torch.float64, device=dev); p[1] = 1.0
+x.lsq_sgd_run(data, p, 4096, 7, 0, [1e-4] * 9)
+# batched::for_each through the probe library
+so = os.path.join(ROOT, "tests", "csrc", "_build", "libxyz_batched.so")
+B = ctypes.CDLL(so)
+B.batched_chain.restype = ctypes.c_float
+B.batched_chain.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+B.batched_lsq.restype = ctypes.c_float
+B.batched_lsq.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+n = 40_000 + 5
+tin = torch.rand((n, 15), device=dev); tout = torch.empty((n, 15), device=dev)
+w18 = torch.rand(18, device=dev); gw = torch.zeros(18, device=dev)
+assert B.batched_chain(tin.data_ptr(), tout.data_ptr(), n, w18.data_ptr(), gw.data_ptr(), 1) >= 0
+pts = torch.rand((n, 3), dtype=torch.float64, device=dev)
+v5 = torch.tensor([0.0, 1.0, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev); g5 = torch.zeros(5, dtype=torch.float64, device=dev)
+assert B.batched_lsq(pts.data_ptr(), n, v5.data_ptr(), g5.data_ptr(), 1) >= 0
+torch.cuda.synchronize()
+print("sanitize_driver ok")

@@ -324,7 +324,7 @@ __global__ void __launch_bounds__(kWarpsT * 32, 1)
 //     two lanes of a warp that can touch the same word, and the 16 lanes of a half-warp always hit 16 different
 //     banks => an update costs 2 + 2 wavefronts, and duplicates are found with ONE shuffle of the id;
 //   * 64 B per bin => T = 3 tables per SM at K = 1024.  A table is shared by a GROUP of GW = 12 / T warps that take
-//     turns (token = a ring of mbarriers, try_wait sleeps in hardware).  While one warp holds the token the others
+//     turns (token = a ring of named barriers: the predecessor does bar.arrive, the successor bar.sync).  While one warp holds the token the others
 //     load their next unit (16 batches = 512 elements, straight into registers, prefetch depth 1) and resolve
 //     duplicates in registers;
 //   * duplicates are resolved exactly inside groups of two batches (stripe_front2: per lane pair the first
@@ -338,8 +338,8 @@ __global__ void __launch_bounds__(kWarpsT * 32, 1)
 constexpr int kStripeWarps = 12;
 constexpr int kStripeUnit = 512;  // elements per warp turn: 16 batches of 32
 
-__device__ __forceinline__ void stripe_front2(unsigned base, int k, int lower, int a0, int a1, int p0, int p1, float v0,
-                                              float v1, float pv0, float pv1, unsigned& addr0, unsigned& addr1,
+__device__ __forceinline__ void stripe_front2(unsigned base, int k, int dummy_row, int lower, int a0, int a1, int p0, int p1,
+                                              float v0, float v1, float pv0, float pv1, unsigned& addr0, unsigned& addr1,
                                               float& acc0, float& acc1) {
     // items in canonical order: (batch 0, lower lane) (batch 0, upper lane) (batch 1, lower) (batch 1, upper);
     // a* / v* are this lane's, p* / pv* the partner lane's (lane ^ 16).
@@ -372,15 +372,25 @@ __device__ __forceinline__ void stripe_front2(unsigned base, int k, int lower, i
         "and.pred ok1, ok1, t;\n"
         "not.pred t, e1p0;\n"
         "and.pred ok1, ok1, t;\n"
-        "selp.s32 s0, %4, %13, ok0;\n"  // absorbed / invalid items go to the dummy row k
-        "selp.s32 s1, %5, %13, ok1;\n"
+        "selp.s32 s0, %4, %15, ok0;\n"  // absorbed / invalid items go to this half-warp's dummy row
+        "selp.s32 s1, %5, %15, ok1;\n"
         "shl.b32 s0, s0, 6;\n"
         "shl.b32 s1, s1, 6;\n"
         "add.s32 %0, s0, %14;\n"
         "add.s32 %1, s1, %14;\n"
         "}\n"
         : "=r"(addr0), "=r"(addr1), "=f"(acc0), "=f"(acc1)
-        : "r"(a0), "r"(a1), "r"(p0), "r"(p1), "f"(v0), "f"(v1), "f"(pv0), "f"(pv1), "r"(lower), "r"(k), "r"(base));
+        : "r"(a0), "r"(a1), "r"(p0), "r"(p1), "f"(v0), "f"(v1), "f"(pv0), "f"(pv1), "r"(lower), "r"(k), "r"(base),
+          "r"(dummy_row));
+}
+// Named barriers (bar.sync / bar.arrive with an id and a thread count) as the turn token between two warps: the
+// predecessor ARRIVES (does not wait), the successor SYNCs; 64 = both warps.  compute-sanitizer's racecheck tracks
+// these, unlike hand-rolled mbarrier polling.
+__device__ __forceinline__ void named_bar_sync(int id, int threads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory");
+}
+__device__ __forceinline__ void named_bar_arrive(int id, int threads) {
+    asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(threads) : "memory");
 }
 __device__ __forceinline__ float lds_f32(unsigned addr) {
     float v;
@@ -401,14 +411,10 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int t = warp % T, j = warp / T;
     const int lower = lane < 16 ? 1 : 0;
-    const size_t table_floats = static_cast<size_t>(k + 1) * 16;  // row k = dummy
+    // rows k and k + 1 = dummies, one per half-warp (lanes L and L ^ 16 share a copy, so they must not share a dummy)
+    const size_t table_floats = static_cast<size_t>(k + 2) * 16;
     float* tables = reinterpret_cast<float*>(smem_raw);
-    uint64_t* bars = reinterpret_cast<uint64_t*>(smem_raw + static_cast<size_t>(T) * table_floats * 4);  // [T][GW]
-    if (tid == 0) {
-        for (int i = 0; i < kStripeWarps; ++i) mbar_init(bars + i, 1);
-        mbar_fence_init();
-        for (int i = 0; i < T; ++i) mbar_arrive(bars + i * GW);  // the first warp of every table starts with the token
-    }
+    const int dummy_row = k + (lane >> 4);
     const long long n_units = (n + kStripeUnit - 1) / kStripeUnit;
     const long long nstreams = static_cast<long long>(gridDim.x) * T;
     const long long stream = static_cast<long long>(blockIdx.x) * T + t;
@@ -466,8 +472,10 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
     }
     __syncthreads();
     const unsigned base = smem_u32(tables + static_cast<size_t>(t) * table_floats + (lane & 15));
-    uint64_t* my_bar = bars + t * GW + j;
-    uint64_t* next_bar = bars + t * GW + (j + 1 == GW ? 0 : j + 1);
+    // turn token of table t: named barrier 1 + t * GW + j belongs to warp j of the group (ids 1 .. 12; 0 is
+    // __syncthreads).  Warp j's predecessor arrives on it when its turn ends; warp 0 owns the first turn.
+    const int my_bar = 1 + t * GW + j;
+    const int next_bar = 1 + t * GW + (j + 1 == GW ? 0 : j + 1);
     unsigned round = 0;
     for (; u < n_units; u += ustep, ++round) {
         int a[16];
@@ -484,10 +492,10 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
         for (int g = 0; g < 8; ++g) {
             const int p0 = __shfl_xor_sync(kFull, a[2 * g], 16), p1 = __shfl_xor_sync(kFull, a[2 * g + 1], 16);
             const float pv0 = __shfl_xor_sync(kFull, v[2 * g], 16), pv1 = __shfl_xor_sync(kFull, v[2 * g + 1], 16);
-            stripe_front2(base, k, lower, a[2 * g], a[2 * g + 1], p0, p1, v[2 * g], v[2 * g + 1], pv0, pv1, addr[2 * g],
+            stripe_front2(base, k, dummy_row, lower, a[2 * g], a[2 * g + 1], p0, p1, v[2 * g], v[2 * g + 1], pv0, pv1, addr[2 * g],
                           addr[2 * g + 1], acc[2 * g], acc[2 * g + 1]);
         }
-        mbar_wait(my_bar, round & 1u);  // my turn on table t
+        if (GW > 1 && (round | static_cast<unsigned>(j)) != 0u) named_bar_sync(my_bar, 64);  // my turn on table t
 #pragma unroll
         for (int g = 0; g < 8; ++g) {
             const float t0 = lds_f32(addr[2 * g]);
@@ -496,7 +504,7 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
             sts_f32(addr[2 * g + 1], t1 + acc[2 * g + 1]);
             __syncwarp();  // lane L ^ 16 may read these words in the next group
         }
-        if (lane == 0) mbar_arrive(next_bar);  // release: ordered after the warp's stores by the __syncwarp above
+        if (GW > 1) named_bar_arrive(next_bar, 64);  // hand the table on (all 32 lanes arrive; nobody waits here)
     }
     __syncthreads();
     // fold: bin b = 16 copies x T tables, fixed order; the float4 order is rotated by b / 2 so that a quarter-warp
@@ -523,7 +531,7 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
 // number of striped tables that fit one SM for K bins (a divisor of kStripeWarps), 0 = does not fit twice
 inline int stripe_tables(int k) {
     const size_t budget = 227 * 1024 - 256;
-    const size_t per_table = (static_cast<size_t>(k) + 1) * 64;
+    const size_t per_table = (static_cast<size_t>(k) + 2) * 64;
     const int choices[5] = {12, 6, 4, 3, 2};
     for (int c : choices)
         if (per_table * c <= budget) return c;
@@ -535,7 +543,7 @@ template <bool kImplicit>
 int launch_striped(const int32_t* idx, const float* val, long long n, float* grad, int k, cudaStream_t st, float* rows,
                    int* n_rows) {
     const int T = stripe_tables(k);
-    const size_t smem = static_cast<size_t>(T) * (k + 1) * 64 + kStripeWarps * 8;
+    const size_t smem = static_cast<size_t>(T) * (k + 2) * 64;
     const long long n_units = (n + kStripeUnit - 1) / kStripeUnit;
     const long long want = (n_units + kStripeWarps - 1) / kStripeWarps;
     const int sms = sm_count();
