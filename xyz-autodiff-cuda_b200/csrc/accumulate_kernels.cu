@@ -6,18 +6,19 @@
 // L2 atomics (tests/test_parallel_gradient_accumulation.cu:25-49; on __shared__ memory:
 // tests/test_shared_memory_atomic.cu:29-64).
 //
-// Design (no floating-point atomics on the hot path):
-//   * every WARP owns a private K-bin table in shared memory (fp32 shared atomics are CAS loops
-//     on sm_100a -- ATOMS.CAST.SPIN -- so they are avoided altogether);
-//   * a warp consumes 128 consecutive elements per step (int4 + float4 per lane, fully coalesced)
-//     as 4 batches of 32; within a batch `match.any` finds lanes that hit the same bin, a shuffle
-//     tree folds each group onto its lowest lane, and that lane does a plain LDS/FADD/STS on the
-//     warp's table (distinct bins inside a batch => no race; the common no-duplicate batch skips
-//     the tree);
-//   * the CTA adds its 8 tables in warp order, then either
-//       fast:          one red.global.add.v4.f32 per 4 bins into grad (K/4 vector REDs per CTA), or
-//       deterministic: writes a partial row; a second tiny kernel adds the rows in CTA order.
-//   Element -> warp assignment is static, so the deterministic mode is bit-identical run to run.
+// Three kernels, picked by accumulate() below (no floating-point atomics on shared memory anywhere -- fp32 shared
+// atomics are CAS loops on sm_100a, ATOMS.CAST.SPIN):
+//   1. accumulate_striped_kernel   fp32, 16-byte aligned arrays, n >= 2^16, K <= 1810: lane-striped tables shared by
+//                                  turn-taking warps, exact in-register duplicate merge; same cost for every id
+//                                  distribution; deterministic per CTA by construction (the hot path, see below);
+//   2. accumulate_tagged_kernel    fp64, or K up to ~40 K bins: one value table + one byte TAG table per warp,
+//                                  arbitration by "store my lane id, read it back";
+//   3. accumulate_kernel           small n / unaligned bases: per-warp tables, duplicates grouped with match.any and
+//                                  folded by a fixed-order shuffle tree;
+//   (K too large for shared memory: accumulate_global_kernel, plain global REDs.)
+// Every table kernel ends the same way: the CTA folds its tables in a fixed order, then either issues one RED per
+// bin (fast) or writes a partial row that a finishing kernel adds in CTA order (XYZ_FLAG_DETERMINISTIC, and the
+// multi-GPU path whose finishing kernel also exchanges the row over NVLink mailboxes).
 // 8 algorithmic bytes per element (4 with implicit ids) -> HBM bound once contention is gone.
 #include "common.cuh"
 
