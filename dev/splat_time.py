@@ -17,4 +17,11 @@ for i in range(12):
     a.record(); it(); b.record(); torch.cuda.synchronize()
     if i >= 3: ts.append(a.elapsed_time(b))
 ts.sort()
-print(f"{sys.argv[1] if len(sys.argv) > 1 else ''} C4 splat: median {ts[len(ts)//2]:.4f} ms, min {ts[0]:.4f} ms, loss {loss.item():.6g}")
+import hashlib
+h = hashlib.sha1(img.cpu().numpy().tobytes()).hexdigest()[:16]
+gh = float(grads.abs().sum().item())
+print(f"{sys.argv[1] if len(sys.argv) > 1 else ''} C4 splat: median {ts[len(ts)//2]:.4f} ms, min {ts[0]:.4f} ms, loss {loss.item():.9g}, image sha1 {h}, sum|grads| {gh:.9g}")
+for fl, nm in ((x.FLAG_PRECISE_MATH, "precise"),):
+    x.zero_gradients(grads); loss.zero_(); x.launch_gaussian_splatting(tp, grads, tt, img, loss, W, H, N, fl)
+    torch.cuda.synchronize()
+    print(f"   {nm}: loss {loss.item():.9g}, image sha1 {hashlib.sha1(img.cpu().numpy().tobytes()).hexdigest()[:16]}")
