@@ -178,6 +178,23 @@ def also_workloads(dev, peak_gbs):
         ts.sort()
         return ts[len(ts) // 2]
 
+    def timed_rotating(make_call, n_sets, rounds=6):
+        """Back-to-back launches over n_sets DIFFERENT input sets (together larger than L2, so every launch still reads
+        from HBM) between one pair of events: the steady-state cost per launch, without the event / launch gap that a
+        single ~20 us launch between two events carries."""
+        calls = [make_call(i) for i in range(n_sets)]
+        for c in calls:
+            c()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for _ in range(rounds):
+            for c in calls:
+                c()
+        b.record(st)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / (rounds * n_sets)
+
     # C1: least squares, 1M residuals fp64 (24 MB)
     n = 1_000_000
     data = torch.from_numpy(orc.lsq_data(n, 42)).to(dev)
@@ -186,6 +203,11 @@ def also_workloads(dev, peak_gbs):
     ms = timed(lambda: x.lsq_grad(data, prm))
     out["c1_lsq_1M_f64"] = {"evals_per_s": n / (ms / 1e3), "ms": ms, "gbs": 24 * n / (ms / 1e3) / 1e9,
                             "hbm_frac": 24 * n / (ms / 1e3) / 1e9 / peak_gbs, "l2": "flushed between iterations"}
+    sets = [data] + [data.clone() for _ in range(7)]   # 8 x 24 MB = 192 MB > L2
+    ms_rot = timed_rotating(lambda i: (lambda: x.lsq_grad(sets[i], prm)), len(sets))
+    out["c1_lsq_1M_f64"].update({"ms_back_to_back": ms_rot, "hbm_frac_back_to_back": 24 * n / (ms_rot / 1e3) / 1e9 / peak_gbs,
+                                 "back_to_back": "8 input sets (192 MB > L2) launched back to back, 48 launches between two events"})
+    del sets
     n2 = 1 << 28
     data2 = torch.empty((n2, 3), dtype=torch.float64, device=dev).uniform_(-5, 5)
     ms = timed(lambda: x.lsq_grad(data2, prm), reps=5, flush_l2=False)
@@ -202,6 +224,13 @@ def also_workloads(dev, peak_gbs):
         out[f"c2_accumulate_2^24_{dist}"] = {"elems_per_s": n / (ms / 1e3), "ms": ms, "gbs": 8 * n / (ms / 1e3) / 1e9,
                                              "hbm_frac": 8 * n / (ms / 1e3) / 1e9 / peak_gbs,
                                              "l2": "flushed between iterations"}
+        if dist == "uniform":
+            pairs = [(ti, tv)] + [(ti.clone(), tv.clone()) for _ in range(7)]   # 8 x 134 MB > L2
+            ms_rot = timed_rotating(lambda i: (lambda: x.accumulate(pairs[i][0], pairs[i][1], grad)), len(pairs))
+            out[f"c2_accumulate_2^24_{dist}"].update({
+                "ms_back_to_back": ms_rot, "hbm_frac_back_to_back": 8 * n / (ms_rot / 1e3) / 1e9 / peak_gbs,
+                "back_to_back": "8 input sets (1.07 GB > L2) launched back to back, 48 launches between two events"})
+            del pairs
     # C3 variant B: one shared W, per-element adjoints of W accumulated into 9 gradients; 2^26 elements (8 GB > L2)
     n3 = 1 << 26
     ins3 = [torch.empty((n3, w), device=dev).uniform_(-1, 1) for w in (6, 6, 3)]
