@@ -18,3 +18,16 @@ prm = torch.zeros(8, dtype=torch.float64, device=dev); prm[1] = 1.0
 for n in (100_000, 1_000_000, 10_000_000):
     data = torch.from_numpy(orc.lsq_data(n, 42)).to(dev)
     print(f"lsq_grad n={n}: {timed(lambda: x.lsq_grad(data, prm)):.1f} us (L2 flushed), {timed(lambda: x.lsq_grad(data, prm), fl=False):.1f} us (warm)")
+# steady state: 8 input sets (192 MB > L2) back to back
+n = 1_000_000
+sets = [torch.from_numpy(orc.lsq_data(n, 42 + i)).to(dev) for i in range(8)]
+for s_ in sets: x.lsq_grad(s_, prm)
+torch.cuda.synchronize()
+a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+a.record()
+for _ in range(6):
+    for s_ in sets: x.lsq_grad(s_, prm)
+b.record(); torch.cuda.synchronize()
+print(f"lsq_grad n=1M back to back over 8 sets: {a.elapsed_time(b) / 48 * 1e3:.2f} us per launch")
+big = torch.empty((1 << 28, 3), dtype=torch.float64, device=dev).uniform_(-5, 5)
+print(f"lsq_grad n=2^28: {timed(lambda: x.lsq_grad(big, prm), reps=5, fl=False):.1f} us")
