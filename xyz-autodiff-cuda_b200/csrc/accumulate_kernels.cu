@@ -583,6 +583,18 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
+// one extra partial row holding the (< 4) head elements peeled off a misaligned shard
+__global__ void __launch_bounds__(256)
+    accumulate_head_row_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, int head, float* row, int k) {
+    for (int b = threadIdx.x; b < k; b += 256) {
+        float s = 0.f;
+        for (int e = 0; e < head; ++e) {
+            if (idx[e] == b) s += val[e];
+        }
+        row[b] = s;
+    }
+}
+
 // deterministic finish: grad[b] += sum over the rows in a FIXED order.  Block = 32 bins x 8 row groups: thread (b, g)
 // adds rows g, g + 8, g + 16, ... (coalesced 128-byte reads per row), the 8 group sums are then added in group order.
 template <class T>
@@ -712,6 +724,21 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const bool deterministic = (flags & XYZ_FLAG_DETERMINISTIC) != 0;
     const bool vec_ok = aligned16(val) && (implicit || aligned16(idx));
+    // A slice [b, e) of two 16-byte aligned arrays (a multi-GPU shard) is misaligned by the SAME number of elements in
+    // idx and val: peel the head elements (< 16 bytes' worth) with the small kernel and run the vector paths on the
+    // aligned remainder.  Two launches, fixed order, so XYZ_FLAG_DETERMINISTIC still holds.
+    if (!vec_ok && !implicit && n >= (1 << 16) + 4) {
+        const uintptr_t mv = reinterpret_cast<uintptr_t>(val) & 15u, mi = reinterpret_cast<uintptr_t>(idx) & 15u;
+        if (mv % sizeof(T) == 0 && mi % sizeof(int32_t) == 0) {
+            const long long head_v = static_cast<long long>(((16u - mv) & 15u) / sizeof(T));
+            const long long head_i = static_cast<long long>(((16u - mi) & 15u) / sizeof(int32_t));
+            if (head_v == head_i && head_v > 0) {
+                const int err = accumulate<T>(idx, val, head_v, grad, k, stream, flags);
+                if (err) return err;
+                return accumulate<T>(idx + head_v, val + head_v, n - head_v, grad, k, stream, flags);
+            }
+        }
+    }
     // tagged tables (fast path; with XYZ_FLAG_DETERMINISTIC its lane-ordered flavour): as many warps as 200 KB of
     // shared memory hold
     if constexpr (sizeof(T) == 4) {
@@ -793,7 +820,7 @@ extern "C" int xyz_accumulate_f32_allreduce(const int32_t* idx, const float* val
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     void* scratch = nullptr;
-    int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * k * sizeof(float), &scratch);
+    int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count() + 1) * k * sizeof(float), &scratch);
     if (err) return err;
     float* rows = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
     int n_rows = 0;
@@ -801,7 +828,16 @@ extern "C" int xyz_accumulate_f32_allreduce(const int32_t* idx, const float* val
         // tables of 8 / 16 / 32 warps as shared memory allows (K <= 4096 always fits 8 warps); unaligned slices
         // (shard boundaries) take the same kernel with scalar loads
         const size_t per_warp = static_cast<size_t>(k) * 5;
-        if (n >= (1 << 16) && aligned16(val) && (implicit || aligned16(idx)) && stripe_tables(k) > 0)
+        // misaligned shard of aligned arrays: head elements into one extra row, the vector kernel on the rest
+        const uintptr_t mv = reinterpret_cast<uintptr_t>(val) & 15u, mi = reinterpret_cast<uintptr_t>(idx) & 15u;
+        const int head = (!implicit && mv == mi && mv != 0 && (mv & 3u) == 0) ? static_cast<int>((16u - mv) / 4u) : 0;
+        if (head > 0 && n >= (1 << 16) + 4 && stripe_tables(k) > 0) {
+            err = launch_striped<false>(idx + head, val + head, n - head, nullptr, k, st, rows, &n_rows);
+            if (err) return err;
+            accumulate_head_row_kernel<<<1, 256, 0, st>>>(idx, val, head, rows + static_cast<size_t>(n_rows) * k, k);
+            count_launch();
+            ++n_rows;
+        } else if (n >= (1 << 16) && aligned16(val) && (implicit || aligned16(idx)) && stripe_tables(k) > 0)
             err = implicit ? launch_striped<true>(idx, val, n, nullptr, k, st, rows, &n_rows)
                            : launch_striped<false>(idx, val, n, nullptr, k, st, rows, &n_rows);
         else if (per_warp * 32 <= 200 * 1024)
