@@ -455,6 +455,22 @@ def test_accumulate_striped_tables_variants():
         _, v = orc.accumulate_inputs(n, kk, "uniform", seed=3)
         got = run_acc(None, v, kk)
         assert (np.abs(got - orc.accumulate_exact(None, v, kk)) <= 1e-4 * orc.accumulate_exact(None, np.abs(v), kk) + 1e-30).all(), kk
+    # fp64 flavour (8 copies per bin, two half-warp update phases): every table count, partial units, implicit ids,
+    # deterministic bit-identity; the sums are exact to 1e-12 of the sum of |terms|
+    for kk, n in ((1, 70_001), (3, 65_536), (100, 131_072 + 5), (700, 99_999), (1024, 600_000), (1500, 250_001), (1770, 1 << 17)):
+        for dist in ("uniform", "zipf", "same"):
+            i, v = orc.accumulate_inputs(n, kk, dist, seed=kk + n + 1)
+            v64 = v.astype(np.float64) * (1.0 + 1e-9)
+            exact = np.zeros(kk); np.add.at(exact, i, v64)
+            abs_sum = np.zeros(kk); np.add.at(abs_sum, i, np.abs(v64))
+            got = run_acc(i, v64, kk, dtype=torch.float64)
+            assert (np.abs(got - exact) <= 1e-12 * abs_sum + 1e-300).all(), (kk, n, dist)
+            a = run_acc(i, v64, kk, x.FLAG_DETERMINISTIC, dtype=torch.float64)
+            b = run_acc(i, v64, kk, x.FLAG_DETERMINISTIC, dtype=torch.float64)
+            assert np.array_equal(a, b) and (np.abs(a - exact) <= 1e-12 * abs_sum + 1e-300).all(), (kk, n, dist)
+        got = run_acc(None, v64, kk, dtype=torch.float64)
+        exact = np.zeros(kk); np.add.at(exact, np.arange(n) % kk, v64)
+        assert (np.abs(got - exact) <= 1e-12 * np.abs(v64).sum() + 1e-300).all(), kk
     # nothing but invalid ids: grad stays untouched
     n, k = 1 << 17, 1024
     grad = torch.full((k,), 2.5, device=DEV)

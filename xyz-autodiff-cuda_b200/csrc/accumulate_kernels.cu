@@ -563,6 +563,233 @@ int launch_striped(const int32_t* idx, const float* val, long long n, float* gra
     return last_error();
 }
 
+
+// ---- fp64 flavour of the striped tables ----------------------------------------------------------------------------
+// Same design with 8-byte words: a bin row is still 64 bytes = 8 COPIES (copy = lane & 7), so T = 3 tables still fit at
+// K = 1024.  Now four lanes (L, L ^ 8, L ^ 16, L ^ 24) share a word.  The warp is treated as two half-warps that use
+// the table one after the other: inside a half only L and L ^ 8 collide -- the pair structure of the fp32 kernel with
+// partner lane ^ 8 -- and the two halves are ordered by a __syncwarp between their update phases.  Duplicate merging
+// (stripe_front2_f64) therefore runs for all 32 lanes at once, and a group's update is
+// [LDS LDS DADD DADD STS STS](lanes 0-15) [the same](lanes 16-31).  Units are 8 batches (256 elements) to keep the
+// register footprint of the 64-bit values at the fp32 kernel's level.
+constexpr int kStripeUnit64 = 256;
+
+__device__ __forceinline__ void stripe_front2_f64(unsigned base, int k, int dummy_row, int lower, int a0, int a1, int p0,
+                                                  int p1, double v0, double v1, double pv0, double pv1, unsigned& addr0,
+                                                  unsigned& addr1, double& acc0, double& acc1) {
+    asm("{\n"
+        ".reg .pred lo, e00, e01, e0p1, e1p0, e11, ok0, ok1, t;\n"
+        ".reg .s32 s0, s1;\n"
+        "setp.ne.s32 lo, %12, 0;\n"
+        "setp.eq.s32 e00, %6, %4;\n"
+        "setp.eq.s32 e01, %5, %4;\n"
+        "setp.eq.s32 e0p1, %7, %4;\n"
+        "setp.eq.s32 e1p0, %6, %5;\n"
+        "setp.eq.s32 e11, %7, %5;\n"
+        "mov.f64 %2, %8;\n"
+        "mov.f64 %3, %9;\n"
+        "and.pred t, e00, lo;\n"
+        "@t add.f64 %2, %2, %10;\n"
+        "@e01 add.f64 %2, %2, %9;\n"
+        "@e0p1 add.f64 %2, %2, %11;\n"
+        "and.pred t, e11, lo;\n"
+        "@t add.f64 %3, %3, %11;\n"
+        "setp.lt.u32 ok0, %4, %13;\n"
+        "not.pred t, e00;\n"
+        "or.pred t, t, lo;\n"
+        "and.pred ok0, ok0, t;\n"
+        "setp.lt.u32 ok1, %5, %13;\n"
+        "not.pred t, e11;\n"
+        "or.pred t, t, lo;\n"
+        "and.pred ok1, ok1, t;\n"
+        "not.pred t, e01;\n"
+        "and.pred ok1, ok1, t;\n"
+        "not.pred t, e1p0;\n"
+        "and.pred ok1, ok1, t;\n"
+        "selp.s32 s0, %4, %15, ok0;\n"
+        "selp.s32 s1, %5, %15, ok1;\n"
+        "shl.b32 s0, s0, 6;\n"
+        "shl.b32 s1, s1, 6;\n"
+        "add.s32 %0, s0, %14;\n"
+        "add.s32 %1, s1, %14;\n"
+        "}\n"
+        : "=r"(addr0), "=r"(addr1), "=d"(acc0), "=d"(acc1)
+        : "r"(a0), "r"(a1), "r"(p0), "r"(p1), "d"(v0), "d"(v1), "d"(pv0), "d"(pv1), "r"(lower), "r"(k), "r"(base),
+          "r"(dummy_row));
+}
+__device__ __forceinline__ double lds_f64(unsigned addr) {
+    double v;
+    asm volatile("ld.shared.f64 %0, [%1];" : "=d"(v) : "r"(addr) : "memory");
+    return v;
+}
+__device__ __forceinline__ void sts_f64(unsigned addr, double v) {
+    asm volatile("st.shared.f64 [%0], %1;" ::"r"(addr), "d"(v) : "memory");
+}
+
+template <bool kImplicit, bool kRows>
+__global__ void __launch_bounds__(kStripeWarps * 32, 1)
+    accumulate_striped64_kernel(const int32_t* __restrict__ idx, const double* __restrict__ val, long long n, double* grad,
+                                int k, double* partial_rows, int T) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int kThreadsS = kStripeWarps * 32;
+    const int GW = kStripeWarps / T;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int t = warp % T, j = warp / T;
+    const int lower = (lane & 8) ? 0 : 1;   // the lower lane of the pair (L, L ^ 8)
+    const bool first_half = lane < 16;
+    // rows k .. k + 3 = dummies: one per (half-warp, pair side), so no two lanes ever share a dummy word
+    const size_t table_doubles = static_cast<size_t>(k + 4) * 8;
+    double* tables = reinterpret_cast<double*>(smem_raw);
+    const int dummy_row = k + (lane >> 3);
+    const long long n_units = (n + kStripeUnit64 - 1) / kStripeUnit64;
+    const long long nstreams = static_cast<long long>(gridDim.x) * T;
+    const long long stream = static_cast<long long>(blockIdx.x) * T + t;
+    int na[8];
+    double nv[8];
+    auto load = [&](long long u) {
+        const long long e0 = u * kStripeUnit64 + lane * 4;
+        if ((u + 1) * kStripeUnit64 <= n) {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+                const double2* gv = reinterpret_cast<const double2*>(val + e0 + 128 * m);
+                const double2 f0 = __ldcs(gv), f1 = __ldcs(gv + 1);
+                nv[4 * m] = f0.x; nv[4 * m + 1] = f0.y; nv[4 * m + 2] = f1.x; nv[4 * m + 3] = f1.y;
+            }
+            if constexpr (kImplicit) {
+                const unsigned uk = static_cast<unsigned>(k);
+                const unsigned r0 = static_cast<unsigned>(static_cast<unsigned long long>(e0) % uk);
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    unsigned r = (r0 + 128u * m) % uk;
+#pragma unroll
+                    for (int c = 0; c < 4; ++c) {
+                        na[4 * m + c] = static_cast<int>(r);
+                        r = (r + 1u == uk) ? 0u : r + 1u;
+                    }
+                }
+            } else {
+#pragma unroll
+                for (int m = 0; m < 2; ++m) {
+                    const int4 q = __ldcs(reinterpret_cast<const int4*>(idx + e0 + 128 * m));
+                    na[4 * m] = q.x; na[4 * m + 1] = q.y; na[4 * m + 2] = q.z; na[4 * m + 3] = q.w;
+                }
+            }
+        } else {
+#pragma unroll
+            for (int m = 0; m < 2; ++m) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const long long e = e0 + 128 * m + c;
+                    const bool in = e < n;
+                    na[4 * m + c] = in ? (kImplicit ? static_cast<int>(e % k) : __ldg(idx + e)) : -1;
+                    nv[4 * m + c] = in ? __ldg(val + e) : 0.0;
+                }
+            }
+        }
+    };
+    long long u = stream + static_cast<long long>(j) * nstreams;
+    const long long ustep = static_cast<long long>(GW) * nstreams;
+    if (u < n_units) load(u);
+    {
+        float4* t4 = reinterpret_cast<float4*>(tables);
+        const int n4 = static_cast<int>(T * table_doubles / 2);
+        for (int i = tid; i < n4; i += kThreadsS) t4[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncthreads();
+    const unsigned base = smem_u32(tables + static_cast<size_t>(t) * table_doubles + (lane & 7));
+    const int my_bar = 1 + t * GW + j;
+    const int next_bar = 1 + t * GW + (j + 1 == GW ? 0 : j + 1);
+    unsigned round = 0;
+    for (; u < n_units; u += ustep, ++round) {
+        int a[8];
+        double v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            a[i] = na[i];
+            v[i] = nv[i];
+        }
+        if (u + ustep < n_units) load(u + ustep);
+        unsigned addr[8];
+        double acc[8];
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            const int p0 = __shfl_xor_sync(kFull, a[2 * g], 8), p1 = __shfl_xor_sync(kFull, a[2 * g + 1], 8);
+            const double pv0 = __shfl_xor_sync(kFull, v[2 * g], 8), pv1 = __shfl_xor_sync(kFull, v[2 * g + 1], 8);
+            stripe_front2_f64(base, k, dummy_row, lower, a[2 * g], a[2 * g + 1], p0, p1, v[2 * g], v[2 * g + 1], pv0, pv1,
+                              addr[2 * g], addr[2 * g + 1], acc[2 * g], acc[2 * g + 1]);
+        }
+        if (GW > 1 && (round | static_cast<unsigned>(j)) != 0u) named_bar_sync(my_bar, 64);
+#pragma unroll
+        for (int g = 0; g < 4; ++g) {
+            if (first_half) {
+                const double t0 = lds_f64(addr[2 * g]);
+                const double t1 = lds_f64(addr[2 * g + 1]);
+                sts_f64(addr[2 * g], t0 + acc[2 * g]);
+                sts_f64(addr[2 * g + 1], t1 + acc[2 * g + 1]);
+            }
+            __syncwarp();  // lanes 16-31 may touch the words lanes 0-15 just wrote
+            if (!first_half) {
+                const double t0 = lds_f64(addr[2 * g]);
+                const double t1 = lds_f64(addr[2 * g + 1]);
+                sts_f64(addr[2 * g], t0 + acc[2 * g]);
+                sts_f64(addr[2 * g + 1], t1 + acc[2 * g + 1]);
+            }
+            __syncwarp();
+        }
+        if (GW > 1) named_bar_arrive(next_bar, 64);
+    }
+    __syncthreads();
+    // fold: bin b = 8 copies x T tables, fixed order (copy order rotated by b so that a quarter-warp spreads over banks)
+    for (int b = tid; b < k; b += kThreadsS) {
+        double s = 0.0;
+        for (int w = 0; w < T; ++w) {
+            const double2* row = reinterpret_cast<const double2*>(tables + static_cast<size_t>(w) * table_doubles + static_cast<size_t>(b) * 8);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const double2 x = row[(q + (b >> 1)) & 3];
+                s += x.x + x.y;
+            }
+        }
+        if constexpr (kRows) {
+            partial_rows[static_cast<size_t>(blockIdx.x) * k + b] = s;
+        } else {
+            if (s != 0.0) atomicAdd(grad + b, s);
+        }
+    }
+}
+
+inline int stripe_tables64(int k) {
+    const size_t budget = 227 * 1024 - 256;
+    const size_t per_table = (static_cast<size_t>(k) + 4) * 64;
+    const int choices[5] = {12, 6, 4, 3, 2};
+    for (int c : choices)
+        if (per_table * c <= budget) return c;
+    return 0;
+}
+
+template <bool kImplicit>
+int launch_striped64(const int32_t* idx, const double* val, long long n, double* grad, int k, cudaStream_t st, double* rows,
+                     int* n_rows) {
+    const int T = stripe_tables64(k);
+    const size_t smem = static_cast<size_t>(T) * (k + 4) * 64;
+    const long long n_units = (n + kStripeUnit64 - 1) / kStripeUnit64;
+    const long long want = (n_units + kStripeWarps - 1) / kStripeWarps;
+    const int sms = sm_count();
+    const int grid = static_cast<int>(want < sms ? want : sms);
+    if (rows) {
+        auto kern = accumulate_striped64_kernel<kImplicit, true>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        kern<<<grid, kStripeWarps * 32, smem, st>>>(idx, val, n, grad, k, rows, T);
+    } else {
+        auto kern = accumulate_striped64_kernel<kImplicit, false>;
+        cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+        kern<<<grid, kStripeWarps * 32, smem, st>>>(idx, val, n, grad, k, nullptr, T);
+    }
+    count_launch();
+    if (n_rows) *n_rows = grid;
+    return last_error();
+}
+
 // Multi-GPU finish (ONE CTA): add the CTAs' rows in CTA order, store the result into every rank's mailbox over
 // NVLink, publish the sequence number, wait for all ranks, add the rows in rank order: grad[b] += global sum.
 __global__ void __launch_bounds__(1024)
@@ -756,6 +983,25 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
                                      : launch_striped<false>(idx, val, n, grad, k, st, rows, &n_rows);
             if (err || !deterministic) return err;
             accumulate_finish_kernel<float><<<(k + 31) / 32, 256, 0, st>>>(rows, n_rows, grad, k);
+            count_launch();
+            return last_error();
+        }
+    }
+    if constexpr (sizeof(T) == 8) {
+        // fp64: the same striped design with 8 copies per bin and two half-warp update phases
+        if (vec_ok && n >= (1 << 16) && stripe_tables64(k) > 0) {
+            double* rows = nullptr;
+            int n_rows = 0;
+            if (deterministic) {
+                void* scratch = nullptr;
+                const int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * k * sizeof(double), &scratch);
+                if (err) return err;
+                rows = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+            }
+            const int err = implicit ? launch_striped64<true>(idx, val, n, grad, k, st, rows, &n_rows)
+                                     : launch_striped64<false>(idx, val, n, grad, k, st, rows, &n_rows);
+            if (err || !deterministic) return err;
+            accumulate_finish_kernel<double><<<(k + 31) / 32, 256, 0, st>>>(rows, n_rows, grad, k);
             count_launch();
             return last_error();
         }
