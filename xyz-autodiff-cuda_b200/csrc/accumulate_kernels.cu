@@ -572,7 +572,11 @@ int launch_striped(const int32_t* idx, const float* val, long long n, float* gra
 // (stripe_front2_f64) therefore runs for all 32 lanes at once, and a group's update is
 // [LDS LDS DADD DADD STS STS](lanes 0-15) [the same](lanes 16-31).  Units are 8 batches (256 elements) to keep the
 // register footprint of the 64-bit values at the fp32 kernel's level.
-constexpr int kStripeUnit64 = 256;
+#ifndef XYZ_STRIPE64_BATCHES
+#define XYZ_STRIPE64_BATCHES 8
+#endif
+constexpr int kB64 = XYZ_STRIPE64_BATCHES;   // batches of 32 elements per warp turn
+constexpr int kStripeUnit64 = 32 * kB64;
 
 __device__ __forceinline__ void stripe_front2_f64(unsigned base, int k, int dummy_row, int lower, int a0, int a1, int p0,
                                                   int p1, double v0, double v1, double pv0, double pv1, unsigned& addr0,
@@ -644,13 +648,13 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
     const long long n_units = (n + kStripeUnit64 - 1) / kStripeUnit64;
     const long long nstreams = static_cast<long long>(gridDim.x) * T;
     const long long stream = static_cast<long long>(blockIdx.x) * T + t;
-    int na[8];
-    double nv[8];
+    int na[kB64];
+    double nv[kB64];
     auto load = [&](long long u) {
         const long long e0 = u * kStripeUnit64 + lane * 4;
         if ((u + 1) * kStripeUnit64 <= n) {
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
+            for (int m = 0; m < kB64 / 4; ++m) {
                 const double2* gv = reinterpret_cast<const double2*>(val + e0 + 128 * m);
                 const double2 f0 = __ldcs(gv), f1 = __ldcs(gv + 1);
                 nv[4 * m] = f0.x; nv[4 * m + 1] = f0.y; nv[4 * m + 2] = f1.x; nv[4 * m + 3] = f1.y;
@@ -659,7 +663,7 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
                 const unsigned uk = static_cast<unsigned>(k);
                 const unsigned r0 = static_cast<unsigned>(static_cast<unsigned long long>(e0) % uk);
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
+                for (int m = 0; m < kB64 / 4; ++m) {
                     unsigned r = (r0 + 128u * m) % uk;
 #pragma unroll
                     for (int c = 0; c < 4; ++c) {
@@ -669,14 +673,14 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
                 }
             } else {
 #pragma unroll
-                for (int m = 0; m < 2; ++m) {
+                for (int m = 0; m < kB64 / 4; ++m) {
                     const int4 q = __ldcs(reinterpret_cast<const int4*>(idx + e0 + 128 * m));
                     na[4 * m] = q.x; na[4 * m + 1] = q.y; na[4 * m + 2] = q.z; na[4 * m + 3] = q.w;
                 }
             }
         } else {
 #pragma unroll
-            for (int m = 0; m < 2; ++m) {
+            for (int m = 0; m < kB64 / 4; ++m) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     const long long e = e0 + 128 * m + c;
@@ -701,18 +705,18 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
     const int next_bar = 1 + t * GW + (j + 1 == GW ? 0 : j + 1);
     unsigned round = 0;
     for (; u < n_units; u += ustep, ++round) {
-        int a[8];
-        double v[8];
+        int a[kB64];
+        double v[kB64];
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
+        for (int i = 0; i < kB64; ++i) {
             a[i] = na[i];
             v[i] = nv[i];
         }
         if (u + ustep < n_units) load(u + ustep);
-        unsigned addr[8];
-        double acc[8];
+        unsigned addr[kB64];
+        double acc[kB64];
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < kB64 / 2; ++g) {
             const int p0 = __shfl_xor_sync(kFull, a[2 * g], 8), p1 = __shfl_xor_sync(kFull, a[2 * g + 1], 8);
             const double pv0 = __shfl_xor_sync(kFull, v[2 * g], 8), pv1 = __shfl_xor_sync(kFull, v[2 * g + 1], 8);
             stripe_front2_f64(base, k, dummy_row, lower, a[2 * g], a[2 * g + 1], p0, p1, v[2 * g], v[2 * g + 1], pv0, pv1,
@@ -720,7 +724,7 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
         }
         if (GW > 1 && (round | static_cast<unsigned>(j)) != 0u) named_bar_sync(my_bar, 64);
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
+        for (int g = 0; g < kB64 / 2; ++g) {
             if (first_half) {
                 const double t0 = lds_f64(addr[2 * g]);
                 const double t1 = lds_f64(addr[2 * g + 1]);
