@@ -20,6 +20,23 @@ for k, n in ((1024, (1 << 17) + 77), (5, 1 << 16), (1700, 70_001)):
             assert np.allclose(g.cpu().numpy(), ex, rtol=0, atol=1e-4 * np.abs(val).sum()), (k, dist, flags)
     g = torch.zeros(k, device=dev)
     x.accumulate(None, D(val), g)
+# fp64 striped flavour (T = 3, 12, 2), deterministic rows, implicit ids; and a shard misaligned by one element
+for k, n in ((1024, (1 << 16) + 300), (7, 1 << 16), (1700, 70_001)):
+    idx, val = orc.accumulate_inputs(n, k, "zipf", seed=k + 1)
+    v64 = val.astype(np.float64)
+    for flags in (0, x.FLAG_DETERMINISTIC):
+        g = torch.zeros(k, dtype=torch.float64, device=dev)
+        x.accumulate(D(idx), D(v64), g, flags)
+        ex = np.zeros(k); np.add.at(ex, idx, v64)
+        assert np.allclose(g.cpu().numpy(), ex, rtol=0, atol=1e-9 * np.abs(v64).sum()), (k, flags)
+    g = torch.zeros(k, dtype=torch.float64, device=dev)
+    x.accumulate(None, D(v64), g)
+idx, val = orc.accumulate_inputs((1 << 17) + 9, 1024, "uniform", seed=77)
+ti = torch.zeros(idx.size + 1, dtype=torch.int32, device=dev); ti[1:] = D(idx)
+tv = torch.zeros(val.size + 1, dtype=torch.float32, device=dev); tv[1:] = D(val)
+g = torch.zeros(1024, device=dev)
+x.accumulate(ti[1:], tv[1:], g)
+assert np.allclose(g.cpu().numpy(), orc.accumulate_exact(idx, val, 1024), rtol=0, atol=1e-4 * np.abs(val).sum())
 # shared-W chain: TMA path + tail, and the plain path
 J, W, S, gg = orc.covproj_inputs(5000 + 13, seed=1)
 for sl in (slice(None), slice(1, 900)):
