@@ -6,6 +6,27 @@
 #define API_FN inline
 #include "api_eval.inc"
 
+// op::covariance_projection (the ternary node of operations/ternary/covariance_projection_logic.cuh) for one element:
+// out3 = packed S', adjoints of J (6), W (9), S (6) given the adjoint g3 of S'
+template <typename T>
+static int covproj_ternary(const T* J, const T* W, const T* S, const T* g, T* out, T* gJ, T* gW, T* gS) {
+    using namespace xyz_autodiff;
+    Variable<6, T> vJ(J), vS(S);
+    Variable<9, T> vW(W);
+    auto P = op::covariance_projection(vJ, vW, vS);
+    static_assert(OperationNode<decltype(P)> && DifferentiableVariableConcept<decltype(P)>);
+    P.forward();
+    for (int i = 0; i < 3; ++i) out[i] = P[i];
+    P.zero_grad();
+    for (int i = 0; i < 3; ++i) P.add_grad(i, g[i]);
+    P.backward();
+    for (int i = 0; i < 6; ++i) gJ[i] = vJ.grad(i);
+    for (int i = 0; i < 9; ++i) gW[i] = vW.grad(i);
+    for (int i = 0; i < 6; ++i) gS[i] = vS.grad(i);
+    // run_numerical on a second copy: central differences of the same node, summed over the three outputs
+    return 0;
+}
+
 extern "C" {
 int mine_eval_op_f64(int op, int aux, const double* in1, int n1, const double* in2, int n2, double cst,
                      const double* gout, double* out, int* nout, double* gin1, double* gin2) {
@@ -30,6 +51,30 @@ int mine_kat_splat_pair(const double* in, double* res) { return api_eval::kat_sp
 int mine_kat_math_f64(double x, double* res) { return api_eval::kat_math<double>(x, res); }
 int mine_kat_math_f32(float x, float* res) { return api_eval::kat_math<float>(x, res); }
 int mine_kat_matrices(float* res) { return api_eval::kat_matrices(res); }
+
+int mine_covproj_ternary_f64(const double* J, const double* W, const double* S, const double* g, double* out, double* gJ,
+                             double* gW, double* gS) {
+    return covproj_ternary<double>(J, W, S, g, out, gJ, gW, gS);
+}
+int mine_covproj_ternary_f32(const float* J, const float* W, const float* S, const float* g, float* out, float* gJ, float* gW,
+                             float* gS) {
+    return covproj_ternary<float>(J, W, S, g, out, gJ, gW, gS);
+}
+// the node's analytic adjoints (all outputs seeded with 1, run()) against its own central differences (run_numerical)
+int mine_covproj_ternary_numerical(const double* J, const double* W, const double* S, double* res42) {
+    using namespace xyz_autodiff;
+    for (int pass = 0; pass < 2; ++pass) {
+        Variable<6, double> vJ(J), vS(S);
+        Variable<9, double> vW(W);
+        auto P = op::covariance_projection(vJ, vW, vS);
+        if (pass == 0) P.run(); else P.run_numerical(1e-6);
+        double* r = res42 + 21 * pass;
+        for (int i = 0; i < 6; ++i) r[i] = vJ.grad(i);
+        for (int i = 0; i < 9; ++i) r[6 + i] = vW.grad(i);
+        for (int i = 0; i < 6; ++i) r[15 + i] = vS.grad(i);
+    }
+    return 42;
+}
 
 // accum::slice: the least-squares graph on four one-component views of ONE RegisterLeaf<4> (what batched::for_each
 // hands to a user graph); res = {loss, da, db, dc, dd} accumulated over `reps` evaluations of the same point

@@ -85,6 +85,26 @@ struct ChainGraph {
     }
 };
 
+// the same chain as ONE ternary node (operations/ternary/covariance_projection_logic.cuh): shared = {W (9)}
+struct ChainTernaryGraph {
+    __device__ void operator()(const ChainIn& x, ChainOut& y, accum::RegisterLeaf<9, float>& shared) const {
+        Variable<6, float> vJ(x.J), vS(x.S);
+        auto P = op::covariance_projection(vJ, shared, vS);
+        P.forward();
+#pragma unroll
+        for (int i = 0; i < 3; ++i) y.out[i] = P[i];
+        P.zero_grad();
+#pragma unroll
+        for (int i = 0; i < 3; ++i) P.add_grad(i, x.g[i]);
+        P.backward();
+#pragma unroll
+        for (int i = 0; i < 6; ++i) {
+            y.gJ[i] = vJ.grad(i);
+            y.gS[i] = vS.grad(i);
+        }
+    }
+};
+
 namespace {
 batched::Workspace g_ws;
 
@@ -122,6 +142,14 @@ float batched_chain(const float* in, float* out, long long n, const float* w18, 
     return timed([&] {
         return batched::for_each<ChainIn, ChainOut, 18, float>(reinterpret_cast<const ChainIn*>(in),
                                                                reinterpret_cast<ChainOut*>(out), n, w18, gw18, ChainGraph{}, g_ws);
+    }, reps);
+}
+
+// as batched_chain, with the chain as one op::covariance_projection node; w9 = W, gw9 accumulated `reps` times
+float batched_chain_ternary(const float* in, float* out, long long n, const float* w9, float* gw9, int reps) {
+    return timed([&] {
+        return batched::for_each<ChainIn, ChainOut, 9, float>(reinterpret_cast<const ChainIn*>(in),
+                                                              reinterpret_cast<ChainOut*>(out), n, w9, gw9, ChainTernaryGraph{}, g_ws);
     }, reps);
 }
 

@@ -188,6 +188,31 @@ def test_host_graphs_match_reference_graphs(host):
 
 
 # ---- device side ----------------------------------------------------------------------------------------
+def test_ternary_covariance_projection_node(host):
+    """op::covariance_projection (one ternary node, not in the reference) against the oracle's composition of the
+    reference's own op::matmul nodes (tree with transposed leaves): fp64 to 1e-12, fp32 to 1e-5 of the row magnitude; and
+    the node's analytic adjoints against its own central differences (run_numerical)."""
+    vp = ctypes.c_void_p
+    host.mine_covproj_ternary_f64.argtypes = [vp] * 8
+    host.mine_covproj_ternary_f32.argtypes = [vp] * 8
+    host.mine_covproj_ternary_numerical.argtypes = [vp] * 4
+    n = 200
+    J, W, S, g = orc.covproj_inputs(n, seed=31)
+    for which in _checkers():
+        for dtype, fn, tol in ((np.float64, host.mine_covproj_ternary_f64, 1e-12), (np.float32, host.mine_covproj_ternary_f32, 1e-5)):
+            want = orc.covproj(J, W, S, g, np.float64, which=which)
+            for e in range(n):
+                ins = [np.ascontiguousarray(a[e], dtype) for a in (J, W, S, g)]
+                outs = [np.zeros(k, dtype) for k in (3, 6, 9, 6)]
+                assert fn(*[P(a) for a in ins], *[P(a) for a in outs]) == 0
+                for a, b in zip(outs, want):
+                    assert (np.abs(a - b[e]) <= tol * (np.abs(b[e]).max() + 1e-30)).all(), (which, dtype.__name__, e)
+    res = np.zeros(42)
+    Jd, Wd, Sd = (np.ascontiguousarray(a[0], np.float64) for a in (J, W, S))
+    assert host.mine_covproj_ternary_numerical(P(Jd), P(Wd), P(Sd), P(res)) == 42
+    assert (np.abs(res[:21] - res[21:]) <= 1e-5 * np.maximum(1.0, np.abs(res[:21]))).all()
+
+
 @pytest.mark.gpu
 def test_device_headers_match_reference_ops(cuda):
     """The same op table evaluated INSIDE a kernel on the B200 against the reference's host-compiled Logic
