@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- the driver's benchmark contract for the xyz-autodiff-cuda hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload covproj|splat_c5]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload covproj|splat_c5|splat_c4_rows]
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W        (N > 1)
 
 Headline workload (BASELINE.json configs[2], the largest single-GPU "gradient evals/s" configuration and the
@@ -520,6 +520,75 @@ def run_splat_c5(args):
 
 
 
+def run_splat_c4_rows(args):
+    """BASELINE configs[3] on G GPUs (north_star: partition "by image tile"): ONE 1024 x 1024 target, Gaussians replicated,
+    every rank renders and back-propagates a tile-aligned band of rows, then the N x 9 gradients + loss are
+    all-reduced (NCCL, in place) and Adam runs on every replica.  Strong scaling."""
+    import torch
+    import torch.distributed as dist
+    import oracle_lib as orc
+    import xyz_autodiff_cuda_b200 as x
+    from importlib import import_module
+    par = import_module("xyz_autodiff_cuda_b200.parallel")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    W = H = 1024
+    N = args.gaussians if args.gaussians != 3_000_000 else 100_000
+    params, target = orc.splat_c4_scene(N, W, H, 42)
+    tp, tt = torch.from_numpy(params).to(dev), torch.from_numpy(target).to(dev)
+    out = torch.zeros((W * H, 3), device=dev)
+    grads = torch.zeros((N, 9), device=dev)
+    loss = torch.zeros(1, device=dev)
+    adam = torch.zeros((N, 18), device=dev)
+    st = torch.cuda.current_stream()
+
+    def step(it):
+        x.zero_gradients(grads)
+        loss.zero_()
+        par.splat_iteration_sharded(x, tp, grads, [tt], [out], loss, W, H, mode="rows")
+        x.adam_step_individual(tp, grads, adam, 0.1, 0.01, 0.001, 0.02, 0.05, iteration=it + 1)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    barrier()
+    x.reset_launch_count()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    a.record(st)
+    for i in range(args.steps):
+        step(i)
+    b.record(st)
+    barrier()
+    launches = x.launch_count()
+    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t[0].item() / args.steps
+    if rank == 0:
+        print(json.dumps({
+            "metric": "splat fwd+bwd ms/iter", "value": ms, "unit": "ms/iter", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": f"mini-gaussian-splatting {N} Gaussians, one 1024x1024 image split into {world} row bands, "
+                                   f"NCCL all-reduce of N x 9 grads + Adam on every replica (BASELINE configs[3] on {world} GPUs)",
+                       "rows_per_gpu": H // world, "allreduce_bytes": N * 36 + 4,
+                       "l2": "per-iteration working set (entries + records + rest tiles) streamed once; Adam moves the Gaussians every step"},
+            "gpu_launches": int(launches)}), flush=True)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
 def run_ours(args):
     import torch
     import torch.distributed as dist
@@ -652,8 +721,9 @@ def main():
     ap.add_argument("--elems", type=int, default=FULL_E, help="elements per GPU (default 2^26, BASELINE configs[2])")
     ap.add_argument("--e2e-elems", type=int, default=1 << 25, help="elements per e2e step (host pinned memory bound)")
     ap.add_argument("--no-also", action="store_true", help="skip the brief timings of the other configs")
-    ap.add_argument("--workload", default="covproj", choices=["covproj", "splat_c5"],
-                    help="covproj = the headline (BASELINE configs[2]); splat_c5 = configs[4], views sharded over the ranks")
+    ap.add_argument("--workload", default="covproj", choices=["covproj", "splat_c5", "splat_c4_rows"],
+                    help="covproj = the headline (BASELINE configs[2]); splat_c5 = configs[4], views sharded over the ranks; "
+                         "splat_c4_rows = configs[3] with ONE image split into row bands over the ranks")
     ap.add_argument("--gaussians", type=int, default=3_000_000, help="splat_c5: number of Gaussians")
     ap.add_argument("--views", type=int, default=8, help="splat_c5: number of views (targets)")
     args = ap.parse_args()
@@ -661,6 +731,8 @@ def main():
         run_reference(args)
     elif args.workload == "splat_c5":
         run_splat_c5(args)
+    elif args.workload == "splat_c4_rows":
+        run_splat_c4_rows(args)
     else:
         run_ours(args)
 
