@@ -15,6 +15,8 @@ forward + reverse, 2^26 elements, fp32.  A step = one pass of the kernel over th
 The other BASELINE configs (least squares 1M, accumulation 16M->1K, splat 100K Gaussians 1024^2) are timed
 briefly at N=1 and reported under "also" in the same JSON line.
 --impl reference times the reference's CPU path alone (rank 0 only).
+--workload splat_c5        BASELINE configs[4]: 3M Gaussians, 8 views sharded over the ranks, NCCL all-reduce of the gradients.
+--workload splat_c4_rows   BASELINE configs[3] with ONE image split into row bands over the ranks (strong scaling).
 """
 import argparse
 import json

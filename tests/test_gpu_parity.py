@@ -457,7 +457,7 @@ def test_accumulate_striped_tables_variants():
         assert (np.abs(got - orc.accumulate_exact(None, v, kk)) <= 1e-4 * orc.accumulate_exact(None, np.abs(v), kk) + 1e-30).all(), kk
     # fp64 flavour (8 copies per bin, two half-warp update phases): every table count, partial units, implicit ids,
     # deterministic bit-identity; the sums are exact to 1e-12 of the sum of |terms|
-    for kk, n in ((1, 70_001), (3, 65_536), (100, 131_072 + 5), (700, 99_999), (1024, 600_000), (1500, 250_001), (1770, 1 << 17)):
+    for kk, n in ((1, 70_001), (3, 65_536), (100, 131_072 + 5), (500, 80_000), (700, 99_999), (1024, 600_000), (1500, 250_001), (1770, 1 << 17)):
         for dist in ("uniform", "zipf", "same"):
             i, v = orc.accumulate_inputs(n, kk, dist, seed=kk + n + 1)
             v64 = v.astype(np.float64) * (1.0 + 1e-9)
