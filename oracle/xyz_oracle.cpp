@@ -347,18 +347,36 @@ inline void pair_forward(const T* gp, T px, T py, PairFwd<T>& f) {
     for (int i = 0; i < 3; ++i) f.wc[i] = gp[5 + i] * f.w;     // color * broadcast<3>(weighted_gauss)    :56-57
 }
 
+// How many units of relative rounding error of the INPUTS the exponent d2 / 2 of one pair amplifies: the size of the
+// three products whose signed sum it is, times the conditioning of the 2x2 inverse they are built from
+// (det = A C - B^2 cancels for strongly anisotropic, rotated covariances: every entry of Sigma^-1 inherits the
+// relative error (|A C| + B^2) / |det| ulp).
+template <class T>
+T exponent_sensitivity(const PairFwd<T>& f) {
+    const T mag = T(0.5) * (std::abs(f.inv[0]) * f.dx * f.dx + T(2) * std::abs(f.inv[1] * f.dx * f.dy) +
+                            std::abs(f.inv[2]) * f.dy * f.dy);
+    const T det = f.cov[0] * f.cov[2] - f.cov[1] * f.cov[1];
+    const T det_cond = (std::abs(f.cov[0] * f.cov[2]) + f.cov[1] * f.cov[1]) / std::max(std::abs(det), T(1e-30));
+    return mag * (T(1) + det_cond);
+}
+
 // One pixel of the reference kernel.  grads += ; *loss += ; out[3] written.  `margin` (optional)
 // tracks min |color_diff_i| over all pairs whose weight is not negligible (> 1e-10): the distance of the
 // closest L1 kink (tests use it to make sure a sign cannot flip within fp32 noise).
 template <class T>
 void splat_pixel(const T* params, T* grads, const T* tgt, T* out, T* loss, int px_i, int py_i, int N, T* margin,
-                 T* absgrads, T* kinkgrads) {
+                 T* absgrads, T* kinkgrads, T* condgrads = nullptr, T* condimg = nullptr) {
     const T px = static_cast<T>(px_i), py = static_cast<T>(py_i);
     T pix[3] = {T(0), T(0), T(0)};
     PairFwd<T> f;
     for (int g = 0; g < N; ++g) {                               // kernel.cu:33-62
         pair_forward(params + 9 * g, px, py, f);
         for (int i = 0; i < 3; ++i) pix[i] += f.wc[i];
+        // conditioning of the exponent: the size of the three terms whose signed sum is d2 / 2 (see condgrads below)
+        if (condimg) {
+            const T mag = exponent_sensitivity(f);
+            for (int i = 0; i < 3; ++i) condimg[i] += std::abs(f.wc[i]) * mag;
+        }
     }
     for (int i = 0; i < 3; ++i) out[i] = pix[i];                // :63
     for (int i = 0; i < 3; ++i) *loss += std::abs(pix[i] - tgt[i]);  // :68-70
@@ -415,6 +433,13 @@ void splat_pixel(const T* params, T* grads, const T* tgt, T* out, T* loss, int p
                 absgrads[9 * g + k] += term;
                 // upper bound of what a flipped sign can change: |g_w| <= sum |color_i| instead of |sum s_i color_i|
                 if (kinkgrads && near_kink) kinkgrads[9 * g + k] += term + std::abs(f.w) + T(1e-30);
+                // every term is proportional to exp(-d2 / 2); an fp32 evaluation of d2 / 2 = sum of three products of
+                // rounded factors carries an ABSOLUTE error of a few ulp of their magnitudes, i.e. the term a RELATIVE
+                // error of (a few 2^-24) x mag.  condgrads = sum |term| x mag is that sensitivity.
+                if (condgrads) {
+                    const T mag = exponent_sensitivity(f);
+                    condgrads[9 * g + k] += term * mag;
+                }
             }
     }
 }
@@ -424,17 +449,18 @@ void splat_pixel(const T* params, T* grads, const T* tgt, T* out, T* loss, int p
 // the same order as oracle/ref_driver.cpp.
 template <class T>
 int splat_all_pairs(const T* params, T* grads, const T* target, T* output, T* loss, int W, int H, int N, int threads,
-                    T* margin_out, T* absgrads_out, T* kinkgrads_out) {
+                    T* margin_out, T* absgrads_out, T* kinkgrads_out, T* condgrads_out = nullptr, T* condimg_out = nullptr) {
     constexpr int TS = 16;  // gaussian_splatting_kernel.cuh:21
     const int bx = (W + TS - 1) / TS, by = (H + TS - 1) / TS;
     const long long nblocks = 1LL * bx * by;
     threads = static_cast<int>(std::max<long long>(1, std::min<long long>(threads, nblocks)));
-    std::vector<std::vector<T>> priv_g(threads), priv_a(threads), priv_k(threads);
+    std::vector<std::vector<T>> priv_g(threads), priv_a(threads), priv_k(threads), priv_c(threads);
     std::vector<T> priv_l(threads, T(0)), priv_m(threads, T(1e30));
     parallel_ranges(nblocks, threads, [&](int t, long long lo, long long hi) {
         priv_g[t].assign(static_cast<size_t>(N) * 9, T(0));
         if (absgrads_out) priv_a[t].assign(static_cast<size_t>(N) * 9, T(0));
         if (kinkgrads_out) priv_k[t].assign(static_cast<size_t>(N) * 9, T(0));
+        if (condgrads_out) priv_c[t].assign(static_cast<size_t>(N) * 9, T(0));
         for (long long b = lo; b < hi; ++b) {
             const int bxi = static_cast<int>(b % bx), byi = static_cast<int>(b / bx);
             for (int ty = 0; ty < TS; ++ty)
@@ -444,7 +470,9 @@ int splat_all_pairs(const T* params, T* grads, const T* target, T* output, T* lo
                     const size_t p = static_cast<size_t>(y) * W + x;
                     splat_pixel<T>(params, priv_g[t].data(), target + 3 * p, output + 3 * p, &priv_l[t], x, y, N,
                                    margin_out ? &priv_m[t] : nullptr, absgrads_out ? priv_a[t].data() : nullptr,
-                                   kinkgrads_out ? priv_k[t].data() : nullptr);
+                                   kinkgrads_out ? priv_k[t].data() : nullptr,
+                                   (condgrads_out && absgrads_out) ? priv_c[t].data() : nullptr,
+                                   condimg_out ? condimg_out + 3 * p : nullptr);  // one writer per pixel
                 }
         }
     });
@@ -455,6 +483,8 @@ int splat_all_pairs(const T* params, T* grads, const T* target, T* output, T* lo
             for (size_t i = 0; i < static_cast<size_t>(N) * 9; ++i) absgrads_out[i] += priv_a[t][i];
         if (kinkgrads_out)
             for (size_t i = 0; i < static_cast<size_t>(N) * 9; ++i) kinkgrads_out[i] += priv_k[t][i];
+        if (condgrads_out && absgrads_out)
+            for (size_t i = 0; i < static_cast<size_t>(N) * 9; ++i) condgrads_out[i] += priv_c[t][i];
         *loss += priv_l[t];
         m = std::min(m, priv_m[t]);
     }
@@ -674,6 +704,17 @@ int orc_splat_f32(const float* params, float* grads, const float* target, float*
 int orc_splat_f64(const double* params, double* grads, const double* target, double* output, double* loss, int W,
                   int H, int N, int threads, double* margin, double* absgrads, double* kinkgrads) {
     return splat_all_pairs<double>(params, grads, target, output, loss, W, H, N, threads, margin, absgrads, kinkgrads);
+}
+// As orc_splat_f64, plus the fp32 CONDITIONING of the scene: condgrads (N x 9, +=, needs absgrads) = sum over pairs of
+// |term| x mag and condimage (P x 3, +=) = sum over Gaussians of |contribution| x mag, where mag = (|a| dx^2 +
+// 2 |b dx dy| + |c| dy^2) / 2 is the size of the products whose signed sum is the exponent.  An fp32 evaluation of the
+// exponent is off by a few 2^-24 x mag, so (a few 2^-24) x cond* bounds what ANY fp32 implementation -- the
+// reference's included -- can promise on scenes with sub-pixel or strongly anisotropic Gaussians.
+int orc_splat_f64_cond(const double* params, double* grads, const double* target, double* output, double* loss, int W,
+                       int H, int N, int threads, double* margin, double* absgrads, double* kinkgrads, double* condgrads,
+                       double* condimage) {
+    return splat_all_pairs<double>(params, grads, target, output, loss, W, H, N, threads, margin, absgrads, kinkgrads,
+                                   condgrads, condimage);
 }
 
 // Least squares: examples/optimization/tests/test_linear_regression_gradient.cu:52-78 (squared loss),

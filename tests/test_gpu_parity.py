@@ -519,6 +519,21 @@ def test_splat_small_scenes_match_fp64_oracle(W, H, N, seed, flags):
 
 
 @pytest.mark.skipif(not orc.have_ref(), reason="oracle/_ref/libxyz_ref.so (reference built for the host) not present")
+@pytest.mark.parametrize("case", range(12))
+def test_splat_ill_conditioned_scenes_within_the_fp32_bound(case):
+    """Sub-pixel to image-sized, arbitrarily rotated Gaussians, odd image sizes, centres outside the image: every flag
+    combination of the CUDA path against fp64 under the fp32 conditioning bound that the reference's own fp32 kernel
+    is shown to need (tests/test_oracle.py::test_fp32_conditioning_bound_holds_for_the_reference_kernel)."""
+    params, target, W, H = orc.splat_hard_scene(case)
+    N = params.shape[0]
+    rg, ro, rl, tol_g, tol_i = orc.splat_tolerance_fp32(params, target, W, H)
+    for flags in (0, x.FLAG_PRECISE_MATH, x.FLAG_DETERMINISTIC, x.FLAG_NO_CULL, x.FLAG_PRECISE_MATH | x.FLAG_DETERMINISTIC):
+        g, o, l = run_splat(params, target, W, H, flags)
+        assert (np.abs(o - ro) <= tol_i).all(), (case, flags, "image")
+        assert abs(l - rl) <= 1e-4 * abs(rl) + tol_i.sum(), (case, flags, "loss")
+        assert (np.abs(g - rg) <= tol_g).all(), (case, flags, "gradients")
+
+
 def test_splat_matches_reference_kernel_on_host():
     """Against the reference's OWN kernel body compiled for the host (fp32, IEEE): the GPU's IEEE flavour differs
     only by FMA contraction and summation order."""
