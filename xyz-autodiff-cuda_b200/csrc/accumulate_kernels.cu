@@ -405,7 +405,7 @@ __device__ __forceinline__ void sts_f32(unsigned addr, float v) {
 template <bool kImplicit, bool kRows>
 __global__ void __launch_bounds__(kStripeWarps * 32, 1)
     accumulate_striped_kernel(const int32_t* __restrict__ idx, const float* __restrict__ val, long long n, float* grad,
-                              int k, float* partial_rows, int T) {
+                              int k, float* partial_rows, int T, int id_base, int k_ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kThreadsS = kStripeWarps * 32;
     const int GW = kStripeWarps / T;
@@ -431,7 +431,7 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
                 nv[4 * m] = f.x; nv[4 * m + 1] = f.y; nv[4 * m + 2] = f.z; nv[4 * m + 3] = f.w;
             }
             if constexpr (kImplicit) {
-                const unsigned uk = static_cast<unsigned>(k);
+                const unsigned uk = static_cast<unsigned>(k_ids);  // implicit id = element index mod the TOTAL bin count
                 const unsigned r0 = static_cast<unsigned>(static_cast<unsigned long long>(e0) % uk);
 #pragma unroll
                 for (int m = 0; m < 4; ++m) {
@@ -457,7 +457,7 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
                 for (int c = 0; c < 4; ++c) {
                     const long long e = e0 + 128 * m + c;
                     const bool in = e < n;
-                    na[4 * m + c] = in ? (kImplicit ? static_cast<int>(e % k) : __ldg(idx + e)) : -1;
+                    na[4 * m + c] = in ? (kImplicit ? static_cast<int>(e % k_ids) : __ldg(idx + e)) : -1;
                     nv[4 * m + c] = in ? __ldg(val + e) : 0.f;
                 }
             }
@@ -483,7 +483,7 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
         float v[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) {
-            a[i] = na[i];
+            a[i] = na[i] - id_base;  // bins [id_base, id_base + k) of this pass; everything else fails the range check
             v[i] = nv[i];
         }
         if (u + ustep < n_units) load(u + ustep);
@@ -539,10 +539,12 @@ inline int stripe_tables(int k) {
     return 0;
 }
 
-// rows == nullptr: REDs into grad; else one row per CTA (returns the number of rows in *n_rows)
+// One pass over the elements for the bins [id_base, id_base + k) (k small enough for stripe_tables(k) >= 2).
+// rows == nullptr: REDs into grad + id_base; else one row of k sums per CTA (returns the number of rows in *n_rows).
 template <bool kImplicit>
 int launch_striped(const int32_t* idx, const float* val, long long n, float* grad, int k, cudaStream_t st, float* rows,
-                   int* n_rows) {
+                   int* n_rows, int id_base = 0, int k_total = 0) {
+    const int k_ids = k_total > 0 ? k_total : k;
     const int T = stripe_tables(k);
     const size_t smem = static_cast<size_t>(T) * (k + 2) * 64;
     const long long n_units = (n + kStripeUnit - 1) / kStripeUnit;
@@ -552,17 +554,23 @@ int launch_striped(const int32_t* idx, const float* val, long long n, float* gra
     if (rows) {
         auto kern = accumulate_striped_kernel<kImplicit, true>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        kern<<<grid, kStripeWarps * 32, smem, st>>>(idx, val, n, grad, k, rows, T);
+        kern<<<grid, kStripeWarps * 32, smem, st>>>(idx, val, n, grad ? grad + id_base : nullptr, k, rows, T, id_base, k_ids);
     } else {
         auto kern = accumulate_striped_kernel<kImplicit, false>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        kern<<<grid, kStripeWarps * 32, smem, st>>>(idx, val, n, grad, k, nullptr, T);
+        kern<<<grid, kStripeWarps * 32, smem, st>>>(idx, val, n, grad + id_base, k, nullptr, T, id_base, k_ids);
     }
     count_launch();
     if (n_rows) *n_rows = grid;
     return last_error();
 }
 
+// Bins per pass when K does not fit two striped tables: the largest count that does (1810), and the K up to which
+// re-reading the elements once per 1810 bins beats the alternatives on their WORST case (measured, 2^24 elements:
+// K = 8192 in 5 passes = 155 us for any distribution; the tagged tables need 88 / 201 us at K = 4096 (uniform / Zipf),
+// plain global atomics 233 us / 5.9 ms at K = 8192).
+constexpr int kStripePassBins = 1810;
+constexpr int kStripeMultiPassMaxK = 16384;
 
 // ---- fp64 flavour of the striped tables ----------------------------------------------------------------------------
 // Same design with 8-byte words: a bin row is still 64 bytes = 8 COPIES (copy = lane & 7), so T = 3 tables still fit at
@@ -854,15 +862,34 @@ __global__ void __launch_bounds__(256) accumulate_finish_kernel(const T* __restr
     }
 }
 
-// K too large for shared-memory tables: coalesced loads + native global REDs (what the reference does,
-// minus its strided access); never deterministic.
+// K too large for shared-memory tables: coalesced loads + native global REDs (what the reference does, minus its
+// strided access), warp-aggregated: lanes of a warp that hit the same bin are grouped with match.any, their values
+// are summed with shuffles and ONE atomic per distinct bin per warp goes to L2 -- skewed ids (Zipf) would otherwise
+// serialise millions of same-address atomics (5.9 ms for 2^24 elements before, measured).  Never deterministic.
 template <class T>
 __global__ void accumulate_global_kernel(const int32_t* __restrict__ idx, const T* __restrict__ val, long long n,
                                          T* grad, int k) {
-    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-         i += static_cast<long long>(gridDim.x) * blockDim.x) {
-        const int id = idx ? __ldg(idx + i) : static_cast<int>(i % k);
-        if (id >= 0 && id < k) atomicAdd(grad + id, __ldg(val + i));
+    const int lane = threadIdx.x & 31;
+    const long long stride = static_cast<long long>(gridDim.x) * blockDim.x;
+    const long long n_up = (n + 31) / 32 * 32;  // whole warps iterate together
+    for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n_up; i += stride) {
+        int id = -1;
+        T v = T(0);
+        if (i < n) {
+            id = idx ? __ldg(idx + i) : static_cast<int>(i % k);
+            v = __ldg(val + i);
+        }
+        const bool valid = id >= 0 && id < k;
+        const unsigned peers = __match_any_sync(kFull, valid ? id : (-1 - lane));
+        const int leader = __ffs(static_cast<int>(peers)) - 1;
+        unsigned rest = peers & (peers - 1u);
+        while (rest) {  // same trip count for every lane of a group
+            const int src = __ffs(static_cast<int>(rest)) - 1;
+            const T other = __shfl_sync(peers, v, src);
+            if (lane == leader) v += other;
+            rest &= rest - 1u;
+        }
+        if (valid && lane == leader) atomicAdd(grad + id, v);
     }
 }
 
@@ -988,6 +1015,30 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
             if (err || !deterministic) return err;
             accumulate_finish_kernel<float><<<(k + 31) / 32, 256, 0, st>>>(rows, n_rows, grad, k);
             count_launch();
+            return last_error();
+        }
+        // K beyond two tables per SM: one pass of the same kernel per kStripePassBins bins (ids outside the pass fail the
+        // range check and go to the dummy rows).  Distribution-independent and deterministic like the single pass.
+        if (vec_ok && n >= (1 << 16) && k <= kStripeMultiPassMaxK) {
+            float* rows = nullptr;
+            if (deterministic) {
+                void* scratch = nullptr;
+                const int err =
+                    scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * kStripePassBins * sizeof(float), &scratch);
+                if (err) return err;
+                rows = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+            }
+            for (int base = 0; base < k; base += kStripePassBins) {
+                const int kp = (k - base < kStripePassBins) ? k - base : kStripePassBins;
+                int n_rows = 0;
+                const int err = implicit ? launch_striped<true>(idx, val, n, grad, kp, st, rows, &n_rows, base, k)
+                                         : launch_striped<false>(idx, val, n, grad, kp, st, rows, &n_rows, base, k);
+                if (err) return err;
+                if (deterministic) {
+                    accumulate_finish_kernel<float><<<(kp + 31) / 32, 256, 0, st>>>(rows, n_rows, grad + base, kp);
+                    count_launch();
+                }
+            }
             return last_error();
         }
     }
