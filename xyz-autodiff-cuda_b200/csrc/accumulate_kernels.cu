@@ -8,14 +8,15 @@
 //
 // Three kernels, picked by accumulate() below (no floating-point atomics on shared memory anywhere -- fp32 shared
 // atomics are CAS loops on sm_100a, ATOMS.CAST.SPIN):
-//   1. accumulate_striped_kernel   fp32, 16-byte aligned arrays, n >= 2^16, K <= 1810: lane-striped tables shared by
+//   1. accumulate_striped_kernel   fp32 (accumulate_striped64_kernel: fp64), 16-byte aligned arrays, n >= 2^16, K <= 3626
+//                                  in one pass and K <= 16384 in passes of 1810 bins: lane-striped tables shared by
 //                                  turn-taking warps, exact in-register duplicate merge; same cost for every id
 //                                  distribution; deterministic per CTA by construction (the hot path, see below);
-//   2. accumulate_tagged_kernel    fp64, or K up to ~40 K bins: one value table + one byte TAG table per warp,
+//   2. accumulate_tagged_kernel    fp64 beyond its striped range: one value table + one byte TAG table per warp,
 //                                  arbitration by "store my lane id, read it back";
 //   3. accumulate_kernel           small n / unaligned bases: per-warp tables, duplicates grouped with match.any and
 //                                  folded by a fixed-order shuffle tree;
-//   (K too large for shared memory: accumulate_global_kernel, plain global REDs.)
+//   (K too large for shared memory: accumulate_global_kernel, warp-aggregated global REDs.)
 // Every table kernel ends the same way: the CTA folds its tables in a fixed order, then either issues one RED per
 // bin (fast) or writes a partial row that a finishing kernel adds in CTA order (XYZ_FLAG_DETERMINISTIC, and the
 // multi-GPU path whose finishing kernel also exchanges the row over NVLink mailboxes).
@@ -529,11 +530,12 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
     }
 }
 
-// number of striped tables that fit one SM for K bins (a divisor of kStripeWarps), 0 = does not fit twice
+// number of striped tables that fit one SM for K bins (a divisor of kStripeWarps; 1 table up to K = 3626: 57 us for 2^24
+// elements, the 12 warps take turns on it), 0 = does not fit
 inline int stripe_tables(int k) {
     const size_t budget = 227 * 1024 - 256;
     const size_t per_table = (static_cast<size_t>(k) + 2) * 64;
-    const int choices[5] = {12, 6, 4, 3, 2};
+    const int choices[6] = {12, 6, 4, 3, 2, 1};
     for (int c : choices)
         if (per_table * c <= budget) return c;
     return 0;
