@@ -445,7 +445,7 @@ def test_accumulate_striped_tables_variants():
         abs_sum = orc.accumulate_exact(idx, np.abs(val), k)
         return (np.abs(got - exact) <= 1e-4 * abs_sum + 1e-30).all()
     for kk, n in ((1, 70_001), (7, 65_536), (200, 131_072 + 5), (300, 100_000), (500, 99_999), (800, 1 << 17), (1024, 600_000),
-                  (1025, 1 << 17), (1500, 250_001), (1771, 1 << 17)):
+                  (1025, 1 << 17), (1500, 250_001), (1771, 1 << 17), (3000, 1 << 17), (3626, 70_000), (3627, 70_000), (9000, 80_000)):
         for dist in ("uniform", "zipf", "same"):
             i, v = orc.accumulate_inputs(n, kk, dist, seed=kk + n)
             assert tol_ok(run_acc(i, v, kk), i, v, kk), (kk, n, dist)
@@ -457,7 +457,8 @@ def test_accumulate_striped_tables_variants():
         assert (np.abs(got - orc.accumulate_exact(None, v, kk)) <= 1e-4 * orc.accumulate_exact(None, np.abs(v), kk) + 1e-30).all(), kk
     # fp64 flavour (8 copies per bin, two half-warp update phases): every table count, partial units, implicit ids,
     # deterministic bit-identity; the sums are exact to 1e-12 of the sum of |terms|
-    for kk, n in ((1, 70_001), (3, 65_536), (100, 131_072 + 5), (500, 80_000), (700, 99_999), (1024, 600_000), (1500, 250_001), (1770, 1 << 17)):
+    for kk, n in ((1, 70_001), (3, 65_536), (100, 131_072 + 5), (500, 80_000), (700, 99_999), (1024, 600_000), (1500, 250_001), (1770, 1 << 17), (2500, 1 << 17), (3624, 70_000),
+                  (3625, 70_000), (6000, 100_000)):
         for dist in ("uniform", "zipf", "same"):
             i, v = orc.accumulate_inputs(n, kk, dist, seed=kk + n + 1)
             v64 = v.astype(np.float64) * (1.0 + 1e-9)

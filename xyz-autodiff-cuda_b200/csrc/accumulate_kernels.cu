@@ -643,7 +643,7 @@ __device__ __forceinline__ void sts_f64(unsigned addr, double v) {
 template <bool kImplicit, bool kRows>
 __global__ void __launch_bounds__(kStripeWarps * 32, 1)
     accumulate_striped64_kernel(const int32_t* __restrict__ idx, const double* __restrict__ val, long long n, double* grad,
-                                int k, double* partial_rows, int T) {
+                                int k, double* partial_rows, int T, int id_base, int k_ids) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int kThreadsS = kStripeWarps * 32;
     const int GW = kStripeWarps / T;
@@ -670,7 +670,7 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
                 nv[4 * m] = f0.x; nv[4 * m + 1] = f0.y; nv[4 * m + 2] = f1.x; nv[4 * m + 3] = f1.y;
             }
             if constexpr (kImplicit) {
-                const unsigned uk = static_cast<unsigned>(k);
+                const unsigned uk = static_cast<unsigned>(k_ids);
                 const unsigned r0 = static_cast<unsigned>(static_cast<unsigned long long>(e0) % uk);
 #pragma unroll
                 for (int m = 0; m < kB64 / 4; ++m) {
@@ -695,7 +695,7 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
                 for (int c = 0; c < 4; ++c) {
                     const long long e = e0 + 128 * m + c;
                     const bool in = e < n;
-                    na[4 * m + c] = in ? (kImplicit ? static_cast<int>(e % k) : __ldg(idx + e)) : -1;
+                    na[4 * m + c] = in ? (kImplicit ? static_cast<int>(e % k_ids) : __ldg(idx + e)) : -1;
                     nv[4 * m + c] = in ? __ldg(val + e) : 0.0;
                 }
             }
@@ -719,7 +719,7 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
         double v[kB64];
 #pragma unroll
         for (int i = 0; i < kB64; ++i) {
-            a[i] = na[i];
+            a[i] = na[i] - id_base;
             v[i] = nv[i];
         }
         if (u + ustep < n_units) load(u + ustep);
@@ -775,7 +775,7 @@ __global__ void __launch_bounds__(kStripeWarps * 32, 1)
 inline int stripe_tables64(int k) {
     const size_t budget = 227 * 1024 - 256;
     const size_t per_table = (static_cast<size_t>(k) + 4) * 64;
-    const int choices[5] = {12, 6, 4, 3, 2};
+    const int choices[6] = {12, 6, 4, 3, 2, 1};
     for (int c : choices)
         if (per_table * c <= budget) return c;
     return 0;
@@ -783,7 +783,8 @@ inline int stripe_tables64(int k) {
 
 template <bool kImplicit>
 int launch_striped64(const int32_t* idx, const double* val, long long n, double* grad, int k, cudaStream_t st, double* rows,
-                     int* n_rows) {
+                     int* n_rows, int id_base = 0, int k_total = 0) {
+    const int k_ids = k_total > 0 ? k_total : k;
     const int T = stripe_tables64(k);
     const size_t smem = static_cast<size_t>(T) * (k + 4) * 64;
     const long long n_units = (n + kStripeUnit64 - 1) / kStripeUnit64;
@@ -793,11 +794,11 @@ int launch_striped64(const int32_t* idx, const double* val, long long n, double*
     if (rows) {
         auto kern = accumulate_striped64_kernel<kImplicit, true>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        kern<<<grid, kStripeWarps * 32, smem, st>>>(idx, val, n, grad, k, rows, T);
+        kern<<<grid, kStripeWarps * 32, smem, st>>>(idx, val, n, grad ? grad + id_base : nullptr, k, rows, T, id_base, k_ids);
     } else {
         auto kern = accumulate_striped64_kernel<kImplicit, false>;
         cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-        kern<<<grid, kStripeWarps * 32, smem, st>>>(idx, val, n, grad, k, nullptr, T);
+        kern<<<grid, kStripeWarps * 32, smem, st>>>(idx, val, n, grad + id_base, k, nullptr, T, id_base, k_ids);
     }
     count_launch();
     if (n_rows) *n_rows = grid;
@@ -1060,6 +1061,29 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
             if (err || !deterministic) return err;
             accumulate_finish_kernel<double><<<(k + 31) / 32, 256, 0, st>>>(rows, n_rows, grad, k);
             count_launch();
+            return last_error();
+        }
+        if (vec_ok && n >= (1 << 16) && k <= kStripeMultiPassMaxK) {  // passes of kStripePassBins bins, as in fp32
+            double* rows = nullptr;
+            if (deterministic) {
+                void* scratch = nullptr;
+                const int err =
+                    scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * kStripePassBins * sizeof(double), &scratch);
+                if (err) return err;
+                rows = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256);
+            }
+            constexpr int kBins = kStripePassBins - 4;  // four dummy rows in the fp64 layout
+            for (int base = 0; base < k; base += kBins) {
+                const int kp = (k - base < kBins) ? k - base : kBins;
+                int n_rows = 0;
+                const int err = implicit ? launch_striped64<true>(idx, val, n, grad, kp, st, rows, &n_rows, base, k)
+                                         : launch_striped64<false>(idx, val, n, grad, kp, st, rows, &n_rows, base, k);
+                if (err) return err;
+                if (deterministic) {
+                    accumulate_finish_kernel<double><<<(kp + 31) / 32, 256, 0, st>>>(rows, n_rows, grad + base, kp);
+                    count_launch();
+                }
+            }
             return last_error();
         }
     }
