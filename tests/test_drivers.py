@@ -91,3 +91,33 @@ def test_splat_driver_reduces_the_loss(tmp_path):
     r = run([SPLAT, "0.1", "0.01", "0.01", "0.01", "0.01", "--target", "output/target.ppm", "--num-gaussians", "50",
              "--max-iterations", "3", "--no-save-images", "--deterministic"], cwd=str(tmp_path))
     assert r.returncode == 0, r.stdout[-2000:]
+
+
+REF_TRAINER = os.path.join(ROOT, "oracle", "_ref", "ref_trainer")
+REF_TRAINER_B200 = os.path.join(ROOT, "oracle", "_ref", "ref_trainer_on_b200")
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(not (os.path.exists(REF_TRAINER) and os.path.exists(REF_TRAINER_B200)),
+                    reason="oracle/_ref/ref_trainer[_on_b200] not built (needs /root/reference at build time)")
+def test_the_reference_training_application_runs_on_this_library(tmp_path):
+    """The reference's own, unmodified training application (main(), Adam, image code) linked against libxyz_b200.so
+    through the one-symbol shim oracle/launch_shim_b200.cu, next to the same application with its own kernel file.  Both
+    start from clock-seeded random Gaussians, so trajectories are compared statistically: same initial loss level, both
+    reduce the loss by a similar factor; the application's own per-iteration timer shows the difference."""
+    def run_app(exe, n_gauss):
+        r = subprocess.run([exe, "0.01", "0.005", "0.02", "0.01", "0.01", "--target", "no-such-image", "--max-iterations", "41",
+                            "--num-gaussians", str(n_gauss), "--no-save-images"], cwd=tmp_path, stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=600)
+        assert r.returncode == 0 and "Program completed successfully!" in r.stdout, r.stdout[-2000:]
+        rows = re.findall(r"Iteration\s+(\d+) \| average Loss: ([0-9.eE+-]+) \| Time: (\d+)ms", r.stdout)
+        assert len(rows) >= 5, r.stdout[-2000:]
+        return {int(i): float(l) for i, l, _ in rows}, [int(t) for _, _, t in rows]
+    ref_loss, ref_ms = run_app(REF_TRAINER, 300)
+    our_loss, our_ms = run_app(REF_TRAINER_B200, 300)
+    assert abs(our_loss[0] - ref_loss[0]) <= 0.25 * ref_loss[0]          # same scene statistics, different random draws
+    assert ref_loss[40] < 0.9 * ref_loss[0] and our_loss[40] < 0.9 * our_loss[0]
+    assert abs(our_loss[40] / our_loss[0] - ref_loss[40] / ref_loss[0]) < 0.15
+    med = lambda v: sorted(v)[len(v) // 2]  # noqa: E731  (the application prints whole milliseconds)
+    print(f"reference application, 300 Gaussians on 256x256: its own kernel {med(ref_ms)} ms/iteration (median), on "
+          f"libxyz_b200 {med(our_ms)} ms/iteration; loss {ref_loss[0]:.4f} -> {ref_loss[40]:.4f} vs {our_loss[0]:.4f} -> {our_loss[40]:.4f}")
