@@ -167,7 +167,8 @@ XYZ_API int xyz_lsq_grad_f64_allreduce(const xyz_data_point* data, long long n_p
  * Replaces the VariableRef::add_grad pattern (include/xyz_autodiff/variable.cuh:48-50) as
  * exercised by tests/test_parallel_gradient_accumulation.cu:25-49: grad[idx[i]] += val[i].   */
 /* Out-of-range ids are ignored.  idx == NULL with XYZ_FLAG_IMPLICIT_IDS means id = i mod k.  XYZ_FLAG_DETERMINISTIC
- * gives bit-identical results run to run (K <= 16384; larger K has no fixed-order path and returns an error).
+ * gives bit-identical results run to run (K <= 16384 on 16-byte aligned arrays; larger K has no fixed-order path and
+ * returns XYZ_ERR_INVALID_ARGUMENT).
  * Cost regimes on B200 for 2^24 elements (any id distribution unless noted): K <= 1810 one pass, 31 us; K <= 3626 one
  * pass, 57 us; K <= 16384 one pass per 1810 bins (K = 8192: 163 us); beyond that warp-aggregated global atomics
  * (uniform ids 160 us; heavily skewed ids up to ~2 ms).  16-byte aligned arrays (or slices of aligned arrays with the

@@ -472,6 +472,10 @@ def test_accumulate_striped_tables_variants():
         got = run_acc(None, v64, kk, dtype=torch.float64)
         exact = np.zeros(kk); np.add.at(exact, np.arange(n) % kk, v64)
         assert (np.abs(got - exact) <= 1e-12 * np.abs(v64).sum() + 1e-300).all(), kk
+    # a short input with a bin count beyond the small kernel's tables, fixed order requested: striped passes
+    i, v = orc.accumulate_inputs(5000, 12_000, "uniform", seed=2)
+    a = run_acc(i, v, 12_000, x.FLAG_DETERMINISTIC)
+    assert np.array_equal(a, run_acc(i, v, 12_000, x.FLAG_DETERMINISTIC)) and tol_ok(a, i, v, 12_000)
     # nothing but invalid ids: grad stays untouched
     n, k = 1 << 17, 1024
     grad = torch.full((k,), 2.5, device=DEV)

@@ -1022,7 +1022,9 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
         }
         // K beyond two tables per SM: one pass of the same kernel per kStripePassBins bins (ids outside the pass fail the
         // range check and go to the dummy rows).  Distribution-independent and deterministic like the single pass.
-        if (vec_ok && n >= (1 << 16) && k <= kStripeMultiPassMaxK) {
+        // (also for short inputs when a fixed order is requested and the per-warp tables of the small kernel do not fit)
+        if (vec_ok && k <= kStripeMultiPassMaxK &&
+            (n >= (1 << 16) || (deterministic && static_cast<size_t>(kWarps) * k * sizeof(T) > 200 * 1024))) {
             float* rows = nullptr;
             if (deterministic) {
                 void* scratch = nullptr;
