@@ -9,14 +9,21 @@ W = H = 1024; N = 100_000
 params, target = orc.splat_c4_scene(N, W, H, 42)
 tp, tt = torch.from_numpy(params).to(dev), torch.from_numpy(target).to(dev)
 grads = torch.zeros((N, 9), device=dev); img = torch.zeros((W * H, 3), device=dev); loss = torch.zeros(1, device=dev)
-def it():
-    x.zero_gradients(grads); loss.zero_(); x.launch_gaussian_splatting(tp, grads, tt, img, loss, W, H, N)
-ts = []
-for i in range(12):
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    a.record(); it(); b.record(); torch.cuda.synchronize()
-    if i >= 3: ts.append(a.elapsed_time(b))
-ts.sort()
+def it(fl=0):
+    x.zero_gradients(grads); loss.zero_(); x.launch_gaussian_splatting(tp, grads, tt, img, loss, W, H, N, fl)
+def med(fl):
+    ts = []
+    for i in range(12):
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); it(fl); b.record(); torch.cuda.synchronize()
+        if i >= 3: ts.append(a.elapsed_time(b))
+    ts.sort()
+    return ts
+for fl, nm in ((x.FLAG_RADIX_BINNING, "radix binning"), (x.FLAG_DETERMINISTIC, "deterministic"),
+               (x.FLAG_DETERMINISTIC | x.FLAG_RADIX_BINNING, "deterministic, radix binning")):
+    ts = med(fl)
+    print(f"   {nm}: median {ts[len(ts)//2]:.4f} ms, min {ts[0]:.4f} ms")
+ts = med(0)
 import hashlib
 h = hashlib.sha1(img.cpu().numpy().tobytes()).hexdigest()[:16]
 gh = float(grads.abs().sum().item())

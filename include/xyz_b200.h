@@ -77,10 +77,13 @@ enum {
     XYZ_FLAG_NO_CULL       = 8, /* splat: evaluate every (pixel, Gaussian) pair like the reference
                                    kernel does; default skips pairs whose weight is exactly 0 */
     XYZ_FLAG_IMPLICIT_IDS  = 16, /* accumulate: idx == NULL means id = i mod K */
-    XYZ_FLAG_TAIL_CULL     = 32  /* splat, opt-in, NOT result-preserving: also skip pairs with d2 > 56, i.e. with a
+    XYZ_FLAG_TAIL_CULL     = 32, /* splat, opt-in, NOT result-preserving: also skip pairs with d2 > 56, i.e. with a
                                     Gaussian weight below exp(-28) = 6.9e-13 (the default only skips weights that
                                     are exactly 0.0f).  Every pixel changes by at most
                                     N * 6.9e-13 * max|sigmoid(opacity) * color|; ~3x fewer pairs are evaluated. */
+    XYZ_FLAG_RADIX_BINNING = 64  /* splat: build the tile lists with (tile, Gaussian) keys + a stable radix sort -- the
+                                    path images of more than 8192 tiles take anyway -- instead of the default stable
+                                    counting sort by tile.  Same lists bit for bit; for tests and comparisons. */
 };
 
 enum {

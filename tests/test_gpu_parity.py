@@ -594,7 +594,9 @@ def test_splat_tile_binning_is_bit_exact():
     params[:5, 0] = [-500.0, 900.0, 100.0, 50.0, 0.0]        # far off-screen / on the border
     params[5, 2:4] = -30.0                                     # degenerate covariance (det regularised, Q15)
     params[6, 2:4] = 5.0                                       # huge Gaussian: covers the whole image
-    for flags, d2max in ((0, 176.0), (x.FLAG_PRECISE_MATH, 209.0), (x.FLAG_NO_CULL, 176.0)):
+    R, D = x.FLAG_RADIX_BINNING, x.FLAG_DETERMINISTIC   # both binning paths, both payload modes
+    for flags, d2max in ((0, 176.0), (x.FLAG_PRECISE_MATH, 209.0), (x.FLAG_NO_CULL, 176.0), (D, 176.0), (R, 176.0),
+                         (R | x.FLAG_PRECISE_MATH, 209.0), (R | x.FLAG_NO_CULL, 176.0), (R | D, 176.0)):
         run_splat(params, target, W, H, flags)
         st = x.splat_last_stats()
         rects, ranges, ids, recs = x.splat_debug_binning(N, st["tiles"], st["entries"])
@@ -609,6 +611,45 @@ def test_splat_tile_binning_is_bit_exact():
         ok = np.isfinite(want).all(axis=1) & (np.abs(params[:, 2:4]) < 3).all(axis=1)
         scale = np.abs(want[:, 2:5]).max(axis=1, keepdims=True)       # ib cancels when the Gaussian is near-isotropic
         assert (np.abs(recs[ok] - want[ok]) <= 1e-5 * np.maximum(np.abs(want[ok]), scale[ok])).all()
+
+
+def test_splat_counting_sort_binning_equals_the_radix_path():
+    """The default binning (stable counting sort by tile, csrc/splat_host.cu section 2b) and the radix path give the
+    same lists, so image and loss are bit-identical; deterministic gradients too (same rows, same order).  Scenes:
+    many chunks of Gaussians, Gaussians taller than the 16 cached tile rows, a row band, empty tiles, a chunk with
+    no entries at all."""
+    R, D = x.FLAG_RADIX_BINNING, x.FLAG_DETERMINISTIC
+    cases = []
+    W, H, N = 512, 384, 40_000
+    params, target = orc.splat_scene(N, W, H, seed=11)
+    params[100:110, 2:4] = 4.0                                 # huge: every tile, more than 16 tile rows
+    params[200:300, 0] = -4000.0                               # off screen: no entries
+    cases.append((params, target, W, H, None))
+    W2, H2, N2 = 300, 700, 3000
+    p2, t2 = orc.splat_scene(N2, W2, H2, seed=12)
+    p2[:, 0] = np.minimum(p2[:, 0], 120.0)                     # the right part of the image stays empty
+    p2[::7, 2] = 3.0; p2[::7, 3] = 0.0; p2[::7, 4] = 0.3       # tall, thin, rotated
+    cases.append((p2, t2, W2, H2, None))
+    cases.append((p2, t2, W2, H2, (160, 400)))
+    for params, target, W, H, band in cases:
+        N = params.shape[0]
+        for flags in (0, D, x.FLAG_PRECISE_MATH):
+            res = []
+            for extra in (0, R):
+                out = run_splat(params, target, W, H, flags | extra, rows=band)
+                st = x.splat_last_stats()
+                rects, ranges, ids, recs = x.splat_debug_binning(N, st["tiles"], st["entries"])
+                res.append((out, st["entries"], rects.copy(), ranges.copy(), ids.copy()))
+            (ga, oa, la), ea, ra, rga, ida = res[0]
+            (gb, ob, lb), eb, rb, rgb_, idb = res[1]
+            assert ea == eb and np.array_equal(ra, rb) and np.array_equal(ida, idb)
+            nonempty = rgb_[:, 1] > rgb_[:, 0]                 # the radix path leaves empty tiles at (0, 0)
+            assert np.array_equal(rga[nonempty], rgb_[nonempty]) and (rga[~nonempty, 0] == rga[~nonempty, 1]).all()
+            assert np.array_equal(oa, ob, equal_nan=True) and la == lb   # NaN = outside the row band, untouched
+            if flags & D:
+                assert np.array_equal(ga, gb)
+            else:
+                assert np.abs(ga - gb).max() <= 1e-4 * np.abs(gb).max()   # atomics: order differs run to run
 
 
 def test_splat_edge_cases():

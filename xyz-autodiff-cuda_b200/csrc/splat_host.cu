@@ -185,6 +185,280 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// ---- 2b. stable counting sort by tile (the default binning for up to kBinMaxTiles tiles) --------------------------
+// The keys are never materialised.  The Gaussians are cut into `n_chunks` consecutive chunks, one CTA each:
+//   splat_bin_count_kernel    per-chunk tile histogram in shared memory -> hist[chunk][tile]
+//   splat_bin_colscan_kernel  per tile: exclusive prefix over the chunks (in place) + the tile's list length
+//   splat_bin_tilescan_kernel exclusive scan over the tiles -> tile_ranges, the backward work-list offsets, total
+//   splat_bin_scatter_kernel  every chunk walks its Gaussians again in batches of 32 (ascending id): a 32-bit mask
+//                             per tile collects which Gaussians of the batch touch it (shared-memory atomicOr); an
+//                             entry's slot is  tile offset + popc(mask below its own bit)  -- ascending Gaussian id
+//                             inside every tile list = exactly the stable sort the radix path produces (tested
+//                             bit for bit against it and against the CPU restatement).
+// Work distribution inside a batch: one thread per (Gaussian, tile row) = one span of consecutive tiles.
+constexpr int kBinThreads = 256;
+constexpr int kBinBatch = 32;
+constexpr int kBinMaxTiles = 8192;  // 8 bytes of shared memory per tile in the scatter kernel
+
+struct BinRow {
+    int k, g, tile0, width;  // bit of the Gaussian inside its batch, Gaussian id, first tile of the span, tiles in the span
+    unsigned int ebase;      // deterministic mode: position of the span's first entry in Gaussian order
+};
+
+// exclusive prefix of the tile rows of the batch's Gaussians -> s_rowbase[0..32]; call with all threads, then sync
+__device__ __forceinline__ void bin_batch_rows(const int4* __restrict__ rects, const unsigned int* __restrict__ touched,
+                                               int g0, int g_end, int* s_rowbase) {
+    if (threadIdx.x < 32) {
+        const int g = g0 + static_cast<int>(threadIdx.x);
+        int rows = 0;
+        if (g < g_end && touched[g] != 0u) {
+            const int4 r = rects[g];
+            rows = r.w - r.y;
+        }
+        int incl = rows;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int y = __shfl_up_sync(0xffffffffu, incl, d);
+            if (static_cast<int>(threadIdx.x) >= d) incl += y;
+        }
+        s_rowbase[threadIdx.x + 1] = incl;
+        if (threadIdx.x == 0) s_rowbase[0] = 0;
+    }
+}
+
+template <bool kWantEbase>
+__device__ __forceinline__ BinRow bin_row(const SplatView& v, const float4* __restrict__ records,
+                                          const int4* __restrict__ rects, const int2* __restrict__ spans,
+                                          const unsigned int* __restrict__ touched,
+                                          const unsigned long long* __restrict__ offsets_incl, const int* s_rowbase,
+                                          int g0, int rr, float d2max, int no_cull) {
+    int k = 0;  // largest k with s_rowbase[k] <= rr
+#pragma unroll
+    for (int step = 16; step > 0; step >>= 1)
+        if (s_rowbase[k + step] <= rr) k += step;
+    BinRow row;
+    row.k = k;
+    row.g = g0 + k;
+    const int j = rr - s_rowbase[k];
+    const int4 r = rects[row.g];
+    const int ty = r.y + j;
+    int2 s;
+    SpanCoef sc;
+    bool have_sc = false;
+    if (j < kSpanRows) {
+        s = spans[static_cast<size_t>(row.g) * kSpanRows + j];
+    } else {
+        const float4 r0 = __ldg(records + 3 * row.g), r1 = __ldg(records + 3 * row.g + 1);
+        sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
+        have_sc = true;
+        s = tile_row_span(sc, r, ty, v);
+    }
+    row.tile0 = ty * v.tiles_x + s.x;
+    row.width = max(s.y - s.x, 0);
+    row.ebase = 0u;
+    if (kWantEbase) {
+        unsigned int before = 0;  // entries of this Gaussian in earlier tile rows (row-major order inside a Gaussian)
+        for (int jj = 0; jj < j; ++jj) {
+            int2 t;
+            if (jj < kSpanRows) {
+                t = spans[static_cast<size_t>(row.g) * kSpanRows + jj];
+            } else {
+                if (!have_sc) {
+                    const float4 r0 = __ldg(records + 3 * row.g), r1 = __ldg(records + 3 * row.g + 1);
+                    sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
+                    have_sc = true;
+                }
+                t = tile_row_span(sc, r, r.y + jj, v);
+            }
+            before += static_cast<unsigned int>(max(t.y - t.x, 0));
+        }
+        row.ebase = static_cast<unsigned int>(offsets_incl[row.g] - touched[row.g]) + before;
+    }
+    return row;
+}
+
+__global__ void __launch_bounds__(kBinThreads)
+    splat_bin_count_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ rects,
+                           const int2* __restrict__ spans, const unsigned int* __restrict__ touched, int chunk_size,
+                           int n_tiles, unsigned int* __restrict__ hist, float d2max, int no_cull) {
+    extern __shared__ unsigned int s_bin[];  // n_tiles counters
+    __shared__ int s_rowbase[kBinBatch + 1];
+    const int tid = threadIdx.x;
+    const int g_begin = blockIdx.x * chunk_size, g_end = min(g_begin + chunk_size, v.num_gaussians);
+    for (int t = tid; t < n_tiles; t += kBinThreads) s_bin[t] = 0u;
+    for (int g0 = g_begin; g0 < g_end; g0 += kBinBatch) {
+        __syncthreads();  // counters zeroed / previous batch done with s_rowbase
+        bin_batch_rows(rects, touched, g0, g_end, s_rowbase);
+        __syncthreads();
+        const int total_rows = s_rowbase[kBinBatch];
+        for (int rr = tid; rr < total_rows; rr += kBinThreads) {
+            const BinRow row = bin_row<false>(v, records, rects, spans, touched, nullptr, s_rowbase, g0, rr, d2max, no_cull);
+            for (int t = 0; t < row.width; ++t) atomicAdd(&s_bin[row.tile0 + t], 1u);
+        }
+    }
+    __syncthreads();
+    unsigned int* out = hist + static_cast<size_t>(blockIdx.x) * n_tiles;
+    for (int t = tid; t < n_tiles; t += kBinThreads) out[t] = s_bin[t];
+}
+
+// block (32, 8): 32 consecutive tiles x 8 groups of consecutive chunks
+__global__ void __launch_bounds__(256)
+    splat_bin_colscan_kernel(unsigned int* __restrict__ hist, int n_chunks, int n_tiles, unsigned int* __restrict__ tile_total) {
+    __shared__ unsigned int s_part[8][32];
+    const int tx = threadIdx.x, gy = threadIdx.y;
+    const int tile = blockIdx.x * 32 + tx;
+    const int per = (n_chunks + 7) / 8;
+    const int c0 = min(gy * per, n_chunks), c1 = min(c0 + per, n_chunks);
+    unsigned int sum = 0;
+    if (tile < n_tiles)
+        for (int c = c0; c < c1; ++c) sum += hist[static_cast<size_t>(c) * n_tiles + tile];
+    s_part[gy][tx] = sum;
+    __syncthreads();
+    unsigned int run = 0;
+    for (int q = 0; q < gy; ++q) run += s_part[q][tx];
+    if (tile < n_tiles) {
+        for (int c = c0; c < c1; ++c) {
+            const size_t at = static_cast<size_t>(c) * n_tiles + tile;
+            const unsigned int x = hist[at];
+            hist[at] = run;
+            run += x;
+        }
+        if (gy == 7) tile_total[tile] = run;
+    }
+}
+
+// one CTA: exclusive scans over the tiles of (list length) and of ceil(list length / kBwdChunk)
+__global__ void __launch_bounds__(1024)
+    splat_bin_tilescan_kernel(const unsigned int* __restrict__ tile_total, int n_tiles, int2* __restrict__ tile_ranges,
+                              int* __restrict__ chunk_offsets, unsigned long long* __restrict__ total_entries) {
+    __shared__ unsigned long long s_warp[32];
+    __shared__ int s_warp_c[32];
+    __shared__ unsigned long long s_carry;
+    __shared__ int s_carry_c;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) {
+        s_carry = 0ull;
+        s_carry_c = 0;
+    }
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int t = base + tid;
+        const unsigned int len = t < n_tiles ? tile_total[t] : 0u;
+        const int c = static_cast<int>((len + kBwdChunk - 1) / kBwdChunk);
+        unsigned long long x = len;
+        int xc = c;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            const int yc = __shfl_up_sync(0xffffffffu, xc, o);
+            if (lane >= o) {
+                x += y;
+                xc += yc;
+            }
+        }
+        if (lane == 31) {
+            s_warp[warp] = x;
+            s_warp_c[warp] = xc;
+        }
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = s_warp[lane];
+            int wc = s_warp_c[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o);
+                const int yc = __shfl_up_sync(0xffffffffu, wc, o);
+                if (lane >= o) {
+                    w += y;
+                    wc += yc;
+                }
+            }
+            s_warp[lane] = w;  // inclusive over warps
+            s_warp_c[lane] = wc;
+        }
+        __syncthreads();
+        const unsigned long long carry = s_carry;
+        const int carry_c = s_carry_c;
+        if (t < n_tiles) {
+            // beyond 2^31 entries the int ranges are meaningless; the host sees total_entries and refuses the launch
+            const unsigned long long before = carry + (warp > 0 ? s_warp[warp - 1] : 0ull) + (x - len);
+            tile_ranges[t] = make_int2(static_cast<int>(before), static_cast<int>(before + len));
+            chunk_offsets[t] = carry_c + (warp > 0 ? s_warp_c[warp - 1] : 0) + (xc - c);
+        }
+        __syncthreads();
+        if (tid == 1023) {
+            s_carry = carry + s_warp[31];
+            s_carry_c = carry_c + s_warp_c[31];
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        chunk_offsets[n_tiles] = s_carry_c;
+        *total_entries = s_carry;
+    }
+}
+
+template <bool kDeterministic>
+__global__ void __launch_bounds__(kBinThreads)
+    splat_bin_scatter_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ rects,
+                             const int2* __restrict__ spans, const unsigned int* __restrict__ touched,
+                             const unsigned long long* __restrict__ offsets_incl, int chunk_size, int n_tiles,
+                             const unsigned int* __restrict__ hist, const int2* __restrict__ tile_ranges,
+                             unsigned int* __restrict__ vals_out, int* __restrict__ sorted_gid, float d2max, int no_cull) {
+    extern __shared__ unsigned int s_bin[];  // n_tiles next free slots, then n_tiles batch masks
+    __shared__ int s_rowbase[kBinBatch + 1];
+    unsigned int* s_off = s_bin;
+    unsigned int* s_mask = s_bin + n_tiles;
+    const int tid = threadIdx.x;
+    const int g_begin = blockIdx.x * chunk_size, g_end = min(g_begin + chunk_size, v.num_gaussians);
+    const unsigned int* mine = hist + static_cast<size_t>(blockIdx.x) * n_tiles;
+    for (int t = tid; t < n_tiles; t += kBinThreads) {
+        s_off[t] = static_cast<unsigned int>(tile_ranges[t].x) + mine[t];
+        s_mask[t] = 0u;
+    }
+    for (int g0 = g_begin; g0 < g_end; g0 += kBinBatch) {
+        __syncthreads();  // slots / masks of the previous batch settled
+        bin_batch_rows(rects, touched, g0, g_end, s_rowbase);
+        __syncthreads();
+        const int total_rows = s_rowbase[kBinBatch];
+        // the first row of every thread stays in registers for both passes; rows beyond kBinThreads are re-derived
+        BinRow first{};
+        if (tid < total_rows)
+            first = bin_row<kDeterministic>(v, records, rects, spans, touched, offsets_incl, s_rowbase, g0, tid, d2max, no_cull);
+        for (int rr = tid; rr < total_rows; rr += kBinThreads) {
+            const BinRow row = rr == tid ? first
+                                         : bin_row<false>(v, records, rects, spans, touched, nullptr, s_rowbase, g0, rr, d2max, no_cull);
+            const unsigned int bit = 1u << row.k;
+            for (int t = 0; t < row.width; ++t) atomicOr(&s_mask[row.tile0 + t], bit);
+        }
+        __syncthreads();
+        for (int rr = tid; rr < total_rows; rr += kBinThreads) {
+            const BinRow row = rr == tid ? first
+                                         : bin_row<kDeterministic>(v, records, rects, spans, touched, offsets_incl, s_rowbase, g0, rr, d2max, no_cull);
+            const unsigned int below = (1u << row.k) - 1u;
+            for (int t = 0; t < row.width; ++t) {
+                const int tile = row.tile0 + t;
+                const unsigned int pos = s_off[tile] + static_cast<unsigned int>(__popc(s_mask[tile] & below));
+                if (kDeterministic) {
+                    // payload = the entry's position in Gaussian order (its row of entry_grads); ids kept separately
+                    vals_out[pos] = row.ebase + static_cast<unsigned int>(t);
+                    sorted_gid[pos] = row.g;
+                } else {
+                    vals_out[pos] = static_cast<unsigned int>(row.g);
+                }
+            }
+        }
+        __syncthreads();
+        for (int t = tid; t < n_tiles; t += kBinThreads) {
+            const unsigned int m = s_mask[t];
+            if (m) {
+                s_off[t] += static_cast<unsigned int>(__popc(m));
+                s_mask[t] = 0u;
+            }
+        }
+    }
+}
+
 // entry index in Gaussian order -> Gaussian id (binary search over the inclusive scan)
 __device__ __forceinline__ int entry_to_gaussian(const unsigned long long* __restrict__ offsets_incl, int n,
                                                  unsigned int e) {
@@ -331,6 +605,16 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     const int n_tiles = v.tiles_x * v.tiles_y;
     const int ng = N > 0 ? N : 1;
 
+    // binning: stable counting sort by tile (default) or, for very large tile counts / on request, the radix path
+    const bool counting = !(flags & XYZ_FLAG_RADIX_BINNING) && n_tiles <= kBinMaxTiles;
+    int chunk_size = kBinBatch, n_chunks = 1;
+    if (counting) {
+        const int want = 4 * sm_count();  // CTAs of the count / scatter kernels
+        chunk_size = ((ng + want - 1) / want + kBinBatch - 1) / kBinBatch * kBinBatch;
+        n_chunks = (ng + chunk_size - 1) / chunk_size;
+    }
+    const float d2max = (flags & XYZ_FLAG_TAIL_CULL) ? kD2MaxTail : (precise ? kD2MaxPrecise : kD2MaxFast);
+
     // ---- fixed-size scratch (depends on N and the tile count only)
     size_t off = 0;
     auto take = [&off](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
@@ -338,7 +622,9 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
                  o_touched = take(sizeof(unsigned int) * ng), o_spans = take(sizeof(int2) * kSpanRows * ng), o_offsets = take(sizeof(unsigned long long) * ng),
                  o_ranges = take(sizeof(int2) * n_tiles), o_tloss = take(sizeof(float) * n_tiles),
                  o_chunks = take(sizeof(int) * (n_tiles + 1)),
-                 o_rest = take(sizeof(float4) * kTilePixels * static_cast<size_t>(n_tiles));
+                 o_rest = take(sizeof(float4) * kTilePixels * static_cast<size_t>(n_tiles)),
+                 o_hist = take(counting ? sizeof(unsigned int) * static_cast<size_t>(n_chunks) * n_tiles : 0),
+                 o_ttotal = take(sizeof(unsigned int) * n_tiles), o_total = take(sizeof(unsigned long long));
     size_t scan_tmp_bytes = 0;
     cub::DeviceScan::InclusiveSum(nullptr, scan_tmp_bytes, TouchedIter(nullptr, ToU64()),
                                   static_cast<unsigned long long*>(nullptr), ng, st);
@@ -356,6 +642,9 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     b.tile_loss = reinterpret_cast<float*>(base + o_tloss);
     b.chunk_offsets = reinterpret_cast<int*>(base + o_chunks);
     b.rest_tiles = reinterpret_cast<float4*>(base + o_rest);
+    unsigned int* hist = reinterpret_cast<unsigned int*>(base + o_hist);
+    unsigned int* tile_total = reinterpret_cast<unsigned int*>(base + o_ttotal);
+    unsigned long long* total_dev = reinterpret_cast<unsigned long long*>(base + o_total);
 
     cudaError_t ce = cudaMemsetAsync(b.tile_ranges, 0, sizeof(int2) * n_tiles, st);
     if (ce != cudaSuccess) return static_cast<int>(ce);
@@ -363,15 +652,27 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     long long entries = 0;
     if (N > 0) {
         splat_preprocess_kernel<<<(N + 255) / 256, 256, 0, st>>>(v, gaussians, b.records, b.rects, b.touched, b.spans,
-                                                                 (flags & XYZ_FLAG_TAIL_CULL) ? kD2MaxTail : (precise ? kD2MaxPrecise : kD2MaxFast), no_cull);
+                                                                 d2max, no_cull);
         count_launch();
-        ce = cub::DeviceScan::InclusiveSum(base + o_scan_tmp, scan_tmp_bytes, TouchedIter(b.touched, ToU64()), b.offsets,
-                                           N, st);
-        if (ce != cudaSuccess) return static_cast<int>(ce);
-        count_launch();
+        if (!counting || deterministic) {  // positions in Gaussian order: radix keys / rows of entry_grads
+            ce = cub::DeviceScan::InclusiveSum(base + o_scan_tmp, scan_tmp_bytes, TouchedIter(b.touched, ToU64()),
+                                               b.offsets, N, st);
+            if (ce != cudaSuccess) return static_cast<int>(ce);
+            count_launch();
+        }
+        const unsigned long long* total_src = b.offsets + (N - 1);
+        if (counting) {
+            const size_t smem = sizeof(unsigned int) * n_tiles;
+            splat_bin_count_kernel<<<n_chunks, kBinThreads, smem, st>>>(v, b.records, b.rects, b.spans, b.touched,
+                                                                         chunk_size, n_tiles, hist, d2max, no_cull);
+            splat_bin_colscan_kernel<<<(n_tiles + 31) / 32, dim3(32, 8), 0, st>>>(hist, n_chunks, n_tiles, tile_total);
+            splat_bin_tilescan_kernel<<<1, 1024, 0, st>>>(tile_total, n_tiles, b.tile_ranges, b.chunk_offsets, total_dev);
+            count_launch(3);
+            total_src = total_dev;
+        }
         // the list length is data dependent: one 8-byte read-back (the only synchronisation)
         unsigned long long total = 0;
-        ce = cudaMemcpyAsync(&total, b.offsets + (N - 1), sizeof(total), cudaMemcpyDeviceToHost, st);
+        ce = cudaMemcpyAsync(&total, total_src, sizeof(total), cudaMemcpyDeviceToHost, st);
         if (ce != cudaSuccess) return static_cast<int>(ce);
         ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) return static_cast<int>(ce);
@@ -379,19 +680,20 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     }
     if (entries >= (1LL << 31) - 512) return XYZ_ERR_WORKSPACE;
 
-    // ---- entry-sized scratch
+    // ---- entry-sized scratch (counting sort: 4 bytes per entry; radix: keys + payload, ping-pong)
     int key_bits = 1;
     while ((1 << key_bits) < n_tiles) ++key_bits;
     const long long ne = entries > 0 ? entries : 1;
     size_t soff = 0;
     auto stake = [&soff](size_t bytes) { size_t o = soff; soff += align_up(bytes); return o; };
-    const size_t o_kin = stake(4 * ne), o_kout = stake(4 * ne), o_vin = stake(4 * ne), o_vout = stake(4 * ne),
-                 o_gid = stake(deterministic ? 4 * ne : 0),
+    const size_t o_kin = stake(counting ? 0 : 4 * ne), o_kout = stake(counting ? 0 : 4 * ne), o_vin = stake(counting ? 0 : 4 * ne),
+                 o_vout = stake(4 * ne), o_gid = stake(deterministic ? 4 * ne : 0),
                  o_cinfo = stake(sizeof(int4) * static_cast<size_t>(ne / kBwdChunk + n_tiles)), o_eg = stake(deterministic ? 36 * ne : 0);
     size_t sort_tmp_bytes = 0;
-    cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, static_cast<unsigned int*>(nullptr),
-                                    static_cast<unsigned int*>(nullptr), static_cast<unsigned int*>(nullptr),
-                                    static_cast<unsigned int*>(nullptr), static_cast<int>(ne), 0, key_bits, st);
+    if (!counting)
+        cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, static_cast<unsigned int*>(nullptr),
+                                        static_cast<unsigned int*>(nullptr), static_cast<unsigned int*>(nullptr),
+                                        static_cast<unsigned int*>(nullptr), static_cast<int>(ne), 0, key_bits, st);
     const size_t o_sort_tmp = stake(sort_tmp_bytes + 16);
     unsigned char* sbase = nullptr;
     err = scratch_get(SCRATCH_SPLAT_SORT, soff, reinterpret_cast<void**>(&sbase));
@@ -400,28 +702,46 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     b.keys_out = reinterpret_cast<unsigned int*>(sbase + o_kout);
     b.vals_in = reinterpret_cast<unsigned int*>(sbase + o_vin);
     b.vals_out = reinterpret_cast<unsigned int*>(sbase + o_vout);
-    // fast mode: the sort payload is the Gaussian id; deterministic mode: payload = entry position, ids derived
+    // fast mode: the sort payload is the Gaussian id; deterministic mode: payload = entry position, ids kept apart
     b.sorted_gid = deterministic ? reinterpret_cast<int*>(sbase + o_gid) : reinterpret_cast<int*>(b.vals_out);
     b.entry_grads = deterministic ? reinterpret_cast<float*>(sbase + o_eg) : nullptr;
     b.chunk_info = reinterpret_cast<int4*>(sbase + o_cinfo);
 
     if (entries > 0) {
-        splat_emit_keys_kernel<<<(N + 15) / 16, 256, 0, st>>>(
-            v, b.records, b.rects, b.touched, b.offsets, b.spans, b.keys_in, b.vals_in,
-            (flags & XYZ_FLAG_TAIL_CULL) ? kD2MaxTail : (precise ? kD2MaxPrecise : kD2MaxFast), no_cull, deterministic ? 0 : 1);
-        count_launch();
-        ce = cub::DeviceRadixSort::SortPairs(sbase + o_sort_tmp, sort_tmp_bytes, b.keys_in, b.keys_out, b.vals_in,
-                                             b.vals_out, static_cast<int>(entries), 0, key_bits, st);
-        if (ce != cudaSuccess) return static_cast<int>(ce);
-        count_launch(3);
-        splat_ranges_kernel<<<static_cast<unsigned int>((entries + 255) / 256), 256, 0, st>>>(
-            entries, b.keys_out, b.vals_out, b.offsets, N, b.tile_ranges, deterministic ? b.sorted_gid : nullptr);
+        if (counting) {
+            const size_t smem = 2 * sizeof(unsigned int) * n_tiles;
+            if (smem > 48 * 1024) {
+                ce = deterministic ? cudaFuncSetAttribute(splat_bin_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
+                                   : cudaFuncSetAttribute(splat_bin_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+                if (ce != cudaSuccess) return static_cast<int>(ce);
+            }
+            if (deterministic)
+                splat_bin_scatter_kernel<true><<<n_chunks, kBinThreads, smem, st>>>(
+                    v, b.records, b.rects, b.spans, b.touched, b.offsets, chunk_size, n_tiles, hist, b.tile_ranges,
+                    b.vals_out, b.sorted_gid, d2max, no_cull);
+            else
+                splat_bin_scatter_kernel<false><<<n_chunks, kBinThreads, smem, st>>>(
+                    v, b.records, b.rects, b.spans, b.touched, nullptr, chunk_size, n_tiles, hist, b.tile_ranges,
+                    b.vals_out, nullptr, d2max, no_cull);
+            count_launch();
+        } else {
+            splat_emit_keys_kernel<<<(N + 15) / 16, 256, 0, st>>>(v, b.records, b.rects, b.touched, b.offsets, b.spans,
+                                                                  b.keys_in, b.vals_in, d2max, no_cull, deterministic ? 0 : 1);
+            count_launch();
+            ce = cub::DeviceRadixSort::SortPairs(sbase + o_sort_tmp, sort_tmp_bytes, b.keys_in, b.keys_out, b.vals_in,
+                                                 b.vals_out, static_cast<int>(entries), 0, key_bits, st);
+            if (ce != cudaSuccess) return static_cast<int>(ce);
+            count_launch(3);
+            splat_ranges_kernel<<<static_cast<unsigned int>((entries + 255) / 256), 256, 0, st>>>(
+                entries, b.keys_out, b.vals_out, b.offsets, N, b.tile_ranges, deterministic ? b.sorted_gid : nullptr);
+            splat_chunk_scan_kernel<<<1, 1024, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets);
+            count_launch(2);
+        }
         // surplus backward CTAs (the grid is an upper bound) read tile = -1
         ce = cudaMemsetAsync(b.chunk_info, 0xff, sizeof(int4) * static_cast<size_t>(entries / kBwdChunk + n_tiles), st);
         if (ce != cudaSuccess) return static_cast<int>(ce);
-        splat_chunk_scan_kernel<<<1, 1024, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets);
         splat_chunk_fill_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets, b.chunk_info);
-        count_launch(3);
+        count_launch();
     }
 
     err = precise ? splat_forward_launch_precise(v, b, target, output, st)
