@@ -5,6 +5,7 @@
 // IEEE arithmetic: the tile rectangles are integer results that the CPU oracle reproduces
 // bit for bit from the same record floats (oracle/xyz_oracle.cpp::tile_rect).
 #include <algorithm>
+#include <cstdlib>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -199,131 +200,88 @@ __global__ void __launch_bounds__(256)
 constexpr int kBinThreads = 256;
 constexpr int kBinBatch = 32;
 constexpr int kBinMaxTiles = 8192;  // 8 bytes of shared memory per tile in the scatter kernel
+constexpr int kBinRegRows = 2;      // spans per thread kept in registers between the passes of a batch
 
-struct BinRow {
-    int k, g, tile0, width;  // bit of the Gaussian inside its batch, Gaussian id, first tile of the span, tiles in the span
-    unsigned int ebase;      // deterministic mode: position of the span's first entry in Gaussian order
-};
-
-// exclusive prefix of the tile rows of the batch's Gaussians -> s_rowbase[0..32]; call with all threads, then sync
-__device__ __forceinline__ void bin_batch_rows(const int4* __restrict__ rects, const unsigned int* __restrict__ touched,
-                                               int g0, int g_end, int* s_rowbase) {
-    if (threadIdx.x < 32) {
-        const int g = g0 + static_cast<int>(threadIdx.x);
-        int rows = 0;
-        if (g < g_end && touched[g] != 0u) {
-            const int4 r = rects[g];
-            rows = r.w - r.y;
-        }
-        int incl = rows;
-#pragma unroll
-        for (int d = 1; d < 32; d <<= 1) {
-            const int y = __shfl_up_sync(0xffffffffu, incl, d);
-            if (static_cast<int>(threadIdx.x) >= d) incl += y;
-        }
-        s_rowbase[threadIdx.x + 1] = incl;
-        if (threadIdx.x == 0) s_rowbase[0] = 0;
-    }
-}
-
-template <bool kWantEbase>
-__device__ __forceinline__ BinRow bin_row(const SplatView& v, const float4* __restrict__ records,
-                                          const int4* __restrict__ rects, const int2* __restrict__ spans,
-                                          const unsigned int* __restrict__ touched,
-                                          const unsigned long long* __restrict__ offsets_incl, const int* s_rowbase,
-                                          int g0, int rr, float d2max, int no_cull) {
-    int k = 0;  // largest k with s_rowbase[k] <= rr
-#pragma unroll
-    for (int step = 16; step > 0; step >>= 1)
-        if (s_rowbase[k + step] <= rr) k += step;
-    BinRow row;
-    row.k = k;
-    row.g = g0 + k;
-    const int j = rr - s_rowbase[k];
-    const int4 r = rects[row.g];
-    const int ty = r.y + j;
-    int2 s;
-    SpanCoef sc;
-    bool have_sc = false;
-    if (j < kSpanRows) {
-        s = spans[static_cast<size_t>(row.g) * kSpanRows + j];
-    } else {
-        const float4 r0 = __ldg(records + 3 * row.g), r1 = __ldg(records + 3 * row.g + 1);
-        sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
-        have_sc = true;
-        s = tile_row_span(sc, r, ty, v);
-    }
-    row.tile0 = ty * v.tiles_x + s.x;
-    row.width = max(s.y - s.x, 0);
-    row.ebase = 0u;
-    if (kWantEbase) {
-        unsigned int before = 0;  // entries of this Gaussian in earlier tile rows (row-major order inside a Gaussian)
-        for (int jj = 0; jj < j; ++jj) {
-            int2 t;
-            if (jj < kSpanRows) {
-                t = spans[static_cast<size_t>(row.g) * kSpanRows + jj];
-            } else {
-                if (!have_sc) {
-                    const float4 r0 = __ldg(records + 3 * row.g), r1 = __ldg(records + 3 * row.g + 1);
-                    sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
-                    have_sc = true;
-                }
-                t = tile_row_span(sc, r, r.y + jj, v);
-            }
-            before += static_cast<unsigned int>(max(t.y - t.x, 0));
-        }
-        row.ebase = static_cast<unsigned int>(offsets_incl[row.g] - touched[row.g]) + before;
-    }
-    return row;
-}
-
+// Half a warp per Gaussian, one lane per tile row; the next Gaussian's rectangle and spans are in flight while the
+// current one is counted.
 __global__ void __launch_bounds__(kBinThreads)
     splat_bin_count_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ rects,
                            const int2* __restrict__ spans, const unsigned int* __restrict__ touched, int chunk_size,
                            int n_tiles, unsigned int* __restrict__ hist, float d2max, int no_cull) {
     extern __shared__ unsigned int s_bin[];  // n_tiles counters
-    __shared__ int s_rowbase[kBinBatch + 1];
-    const int tid = threadIdx.x;
+    const int tid = threadIdx.x, hl = tid & 15;
     const int g_begin = blockIdx.x * chunk_size, g_end = min(g_begin + chunk_size, v.num_gaussians);
     for (int t = tid; t < n_tiles; t += kBinThreads) s_bin[t] = 0u;
-    for (int g0 = g_begin; g0 < g_end; g0 += kBinBatch) {
-        __syncthreads();  // counters zeroed / previous batch done with s_rowbase
-        bin_batch_rows(rects, touched, g0, g_end, s_rowbase);
-        __syncthreads();
-        const int total_rows = s_rowbase[kBinBatch];
-        for (int rr = tid; rr < total_rows; rr += kBinThreads) {
-            const BinRow row = bin_row<false>(v, records, rects, spans, touched, nullptr, s_rowbase, g0, rr, d2max, no_cull);
-            for (int t = 0; t < row.width; ++t) atomicAdd(&s_bin[row.tile0 + t], 1u);
+    __syncthreads();
+    int g = g_begin + (tid >> 4);
+    unsigned int cnt = 0u;
+    int4 r = make_int4(0, 0, 0, 0);
+    int2 s0 = make_int2(0, 0);
+    if (g < g_end) {
+        cnt = touched[g];
+        r = rects[g];
+        s0 = spans[static_cast<size_t>(g) * kSpanRows + hl];
+    }
+    while (g < g_end) {
+        const int gn = g + kBinThreads / 16;
+        unsigned int cnt_n = 0u;
+        int4 r_n = make_int4(0, 0, 0, 0);
+        int2 s0_n = make_int2(0, 0);
+        if (gn < g_end) {
+            cnt_n = touched[gn];
+            r_n = rects[gn];
+            s0_n = spans[static_cast<size_t>(gn) * kSpanRows + hl];
         }
+        if (cnt != 0u) {
+            for (int rb = r.y; rb < r.w; rb += kSpanRows) {
+                const int ty = rb + hl;
+                if (ty < r.w) {
+                    int2 s = s0;
+                    if (rb != r.y) {
+                        const float4 r0 = __ldg(records + 3 * g), r1 = __ldg(records + 3 * g + 1);
+                        const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
+                        s = tile_row_span(sc, r, ty, v);
+                    }
+                    for (int tx = s.x; tx < s.y; ++tx) atomicAdd(&s_bin[ty * v.tiles_x + tx], 1u);
+                }
+            }
+        }
+        g = gn;
+        cnt = cnt_n;
+        r = r_n;
+        s0 = s0_n;
     }
     __syncthreads();
     unsigned int* out = hist + static_cast<size_t>(blockIdx.x) * n_tiles;
     for (int t = tid; t < n_tiles; t += kBinThreads) out[t] = s_bin[t];
 }
 
-// block (32, 8): 32 consecutive tiles x 8 groups of consecutive chunks
-__global__ void __launch_bounds__(256)
+// block (32, 32): 32 consecutive tiles x 32 groups of consecutive chunks
+__global__ void __launch_bounds__(1024)
     splat_bin_colscan_kernel(unsigned int* __restrict__ hist, int n_chunks, int n_tiles, unsigned int* __restrict__ tile_total) {
-    __shared__ unsigned int s_part[8][32];
+    __shared__ unsigned int s_part[32][33];
     const int tx = threadIdx.x, gy = threadIdx.y;
     const int tile = blockIdx.x * 32 + tx;
-    const int per = (n_chunks + 7) / 8;
+    const int per = (n_chunks + 31) / 32;
     const int c0 = min(gy * per, n_chunks), c1 = min(c0 + per, n_chunks);
     unsigned int sum = 0;
-    if (tile < n_tiles)
+    if (tile < n_tiles) {
+#pragma unroll 4
         for (int c = c0; c < c1; ++c) sum += hist[static_cast<size_t>(c) * n_tiles + tile];
+    }
     s_part[gy][tx] = sum;
     __syncthreads();
     unsigned int run = 0;
     for (int q = 0; q < gy; ++q) run += s_part[q][tx];
     if (tile < n_tiles) {
+#pragma unroll 4
         for (int c = c0; c < c1; ++c) {
             const size_t at = static_cast<size_t>(c) * n_tiles + tile;
             const unsigned int x = hist[at];
             hist[at] = run;
             run += x;
         }
-        if (gy == 7) tile_total[tile] = run;
+        if (gy == 31) tile_total[tile] = run;
     }
 }
 
@@ -398,6 +356,65 @@ __global__ void __launch_bounds__(1024)
     }
 }
 
+// One span of consecutive tiles = one (Gaussian, tile row) of the current batch.
+struct BinRow {
+    int k, tile0, width;  // bit of the Gaussian inside its batch, first tile of the span, tiles in the span
+    unsigned int ebase;   // deterministic mode: position of the span's first entry in Gaussian order
+};
+
+// Shared state of one batch (32 consecutive Gaussians) of the scatter kernel.
+struct __align__(16) BinBatch {
+    int2 spans[kBinBatch * kSpanRows];  // the stored spans of this batch's Gaussians
+    int rowbase[kBinBatch + 1];           // exclusive prefix of the Gaussians' tile-row counts
+    int row_y[kBinBatch];                 // first tile row of each Gaussian's rectangle
+};
+static_assert(kBinThreads * 2 == kBinBatch * kSpanRows, "every thread stages two spans of a batch");
+
+template <bool kWantEbase>
+__device__ __forceinline__ BinRow bin_row(const SplatView& v, const float4* __restrict__ records,
+                                          const int4* __restrict__ rects, const unsigned int* __restrict__ touched,
+                                          const unsigned long long* __restrict__ offsets_incl, const BinBatch& sb, int g0,
+                                          int rr, float d2max, int no_cull) {
+    int k = 0;  // largest k with rowbase[k] <= rr
+#pragma unroll
+    for (int step = kBinBatch / 2; step > 0; step >>= 1)
+        if (sb.rowbase[k + step] <= rr) k += step;
+    BinRow row;
+    row.k = k;
+    const int g = g0 + k;
+    const int j = rr - sb.rowbase[k];
+    const int ty = sb.row_y[k] + j;
+    int2 s;
+    if (j < kSpanRows) {
+        s = sb.spans[k * kSpanRows + j];
+    } else {
+        const float4 r0 = __ldg(records + 3 * g), r1 = __ldg(records + 3 * g + 1);
+        const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
+        s = tile_row_span(sc, rects[g], ty, v);
+    }
+    row.tile0 = ty * v.tiles_x + s.x;
+    row.width = max(s.y - s.x, 0);
+    row.ebase = 0u;
+    if (kWantEbase) {
+        unsigned int before = 0;  // entries of this Gaussian in earlier tile rows (row-major order inside a Gaussian)
+        for (int jj = 0; jj < min(j, kSpanRows); ++jj) {
+            const int2 t = sb.spans[k * kSpanRows + jj];
+            before += static_cast<unsigned int>(max(t.y - t.x, 0));
+        }
+        if (j > kSpanRows) {
+            const float4 r0 = __ldg(records + 3 * g), r1 = __ldg(records + 3 * g + 1);
+            const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
+            const int4 r = rects[g];
+            for (int jj = kSpanRows; jj < j; ++jj) {
+                const int2 t = tile_row_span(sc, r, r.y + jj, v);
+                before += static_cast<unsigned int>(max(t.y - t.x, 0));
+            }
+        }
+        row.ebase = static_cast<unsigned int>(offsets_incl[g] - touched[g]) + before;
+    }
+    return row;
+}
+
 template <bool kDeterministic>
 __global__ void __launch_bounds__(kBinThreads)
     splat_bin_scatter_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ rects,
@@ -405,36 +422,71 @@ __global__ void __launch_bounds__(kBinThreads)
                              const unsigned long long* __restrict__ offsets_incl, int chunk_size, int n_tiles,
                              const unsigned int* __restrict__ hist, const int2* __restrict__ tile_ranges,
                              unsigned int* __restrict__ vals_out, int* __restrict__ sorted_gid, float d2max, int no_cull) {
-    extern __shared__ unsigned int s_bin[];  // n_tiles next free slots, then n_tiles batch masks
-    __shared__ int s_rowbase[kBinBatch + 1];
-    unsigned int* s_off = s_bin;
-    unsigned int* s_mask = s_bin + n_tiles;
+    extern __shared__ __align__(16) unsigned int s_slots[];  // next free slot per tile, then the batch mask per tile
+    __shared__ BinBatch sb;
+    const int n_pad = (n_tiles + 3) & ~3;
+    unsigned int* s_off = s_slots;
+    unsigned int* s_mask = s_slots + n_pad;
     const int tid = threadIdx.x;
     const int g_begin = blockIdx.x * chunk_size, g_end = min(g_begin + chunk_size, v.num_gaussians);
     const unsigned int* mine = hist + static_cast<size_t>(blockIdx.x) * n_tiles;
-    for (int t = tid; t < n_tiles; t += kBinThreads) {
-        s_off[t] = static_cast<unsigned int>(tile_ranges[t].x) + mine[t];
+    for (int t = tid; t < n_pad; t += kBinThreads) {
+        s_off[t] = t < n_tiles ? static_cast<unsigned int>(tile_ranges[t].x) + mine[t] : 0u;
         s_mask[t] = 0u;
     }
+    // prefetch registers: warp 0 holds (tile rows, first tile row) of the next batch's Gaussians, every thread two of
+    // the next batch's 32 x 16 stored spans
+    int pre_rows = 0, pre_y = 0;
+    int4 pre_spans = make_int4(0, 0, 0, 0);
+    auto prefetch = [&](int g0) {
+        if (tid < kBinBatch) {
+            const int g = g0 + tid;
+            pre_rows = 0;
+            pre_y = 0;
+            if (g < g_end && touched[g] != 0u) {
+                const int4 r = rects[g];
+                pre_rows = r.w - r.y;
+                pre_y = r.y;
+            }
+        }
+        const int g = g0 + (tid >> 3);
+        if (g < g_end) pre_spans = *reinterpret_cast<const int4*>(spans + static_cast<size_t>(g) * kSpanRows + (tid & 7) * 2);
+    };
+    prefetch(g_begin);
     for (int g0 = g_begin; g0 < g_end; g0 += kBinBatch) {
-        __syncthreads();  // slots / masks of the previous batch settled
-        bin_batch_rows(rects, touched, g0, g_end, s_rowbase);
-        __syncthreads();
-        const int total_rows = s_rowbase[kBinBatch];
-        // the first row of every thread stays in registers for both passes; rows beyond kBinThreads are re-derived
-        BinRow first{};
-        if (tid < total_rows)
-            first = bin_row<kDeterministic>(v, records, rects, spans, touched, offsets_incl, s_rowbase, g0, tid, d2max, no_cull);
-        for (int rr = tid; rr < total_rows; rr += kBinThreads) {
-            const BinRow row = rr == tid ? first
-                                         : bin_row<false>(v, records, rects, spans, touched, nullptr, s_rowbase, g0, rr, d2max, no_cull);
+        if (tid < kBinBatch) {
+            int incl = pre_rows;
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const int y = __shfl_up_sync(0xffffffffu, incl, d);
+                if (tid >= d) incl += y;
+            }
+            sb.rowbase[tid + 1] = incl;
+            if (tid == 0) sb.rowbase[0] = 0;
+            sb.row_y[tid] = pre_y;
+        }
+        *reinterpret_cast<int4*>(&sb.spans[tid * 2]) = pre_spans;
+        __syncthreads();  // also: slots / masks of the previous batch settled
+        prefetch(g0 + kBinBatch);
+        const int total_rows = sb.rowbase[kBinBatch];
+        // the first spans of every thread stay in registers for both passes; further ones are derived again
+        BinRow reg[kBinRegRows];
+#pragma unroll
+        for (int q = 0; q < kBinRegRows; ++q) {
+            reg[q].k = 0; reg[q].tile0 = 0; reg[q].width = 0; reg[q].ebase = 0u;
+            const int rr = tid + q * kBinThreads;
+            if (rr < total_rows)
+                reg[q] = bin_row<kDeterministic>(v, records, rects, touched, offsets_incl, sb, g0, rr, d2max, no_cull);
+            const unsigned int bit = 1u << reg[q].k;
+            for (int t = 0; t < reg[q].width; ++t) atomicOr(&s_mask[reg[q].tile0 + t], bit);
+        }
+        for (int rr = tid + kBinRegRows * kBinThreads; rr < total_rows; rr += kBinThreads) {
+            const BinRow row = bin_row<false>(v, records, rects, touched, nullptr, sb, g0, rr, d2max, no_cull);
             const unsigned int bit = 1u << row.k;
             for (int t = 0; t < row.width; ++t) atomicOr(&s_mask[row.tile0 + t], bit);
         }
         __syncthreads();
-        for (int rr = tid; rr < total_rows; rr += kBinThreads) {
-            const BinRow row = rr == tid ? first
-                                         : bin_row<kDeterministic>(v, records, rects, spans, touched, offsets_incl, s_rowbase, g0, rr, d2max, no_cull);
+        auto place = [&](const BinRow& row) {
             const unsigned int below = (1u << row.k) - 1u;
             for (int t = 0; t < row.width; ++t) {
                 const int tile = row.tile0 + t;
@@ -442,20 +494,27 @@ __global__ void __launch_bounds__(kBinThreads)
                 if (kDeterministic) {
                     // payload = the entry's position in Gaussian order (its row of entry_grads); ids kept separately
                     vals_out[pos] = row.ebase + static_cast<unsigned int>(t);
-                    sorted_gid[pos] = row.g;
+                    sorted_gid[pos] = g0 + row.k;
                 } else {
-                    vals_out[pos] = static_cast<unsigned int>(row.g);
+                    vals_out[pos] = static_cast<unsigned int>(g0 + row.k);
                 }
             }
-        }
+        };
+#pragma unroll
+        for (int q = 0; q < kBinRegRows; ++q) place(reg[q]);
+        for (int rr = tid + kBinRegRows * kBinThreads; rr < total_rows; rr += kBinThreads)
+            place(bin_row<kDeterministic>(v, records, rects, touched, offsets_incl, sb, g0, rr, d2max, no_cull));
         __syncthreads();
-        for (int t = tid; t < n_tiles; t += kBinThreads) {
-            const unsigned int m = s_mask[t];
-            if (m) {
-                s_off[t] += static_cast<unsigned int>(__popc(m));
-                s_mask[t] = 0u;
+        for (int t = tid * 4; t < n_pad; t += kBinThreads * 4) {
+            const uint4 m = *reinterpret_cast<const uint4*>(s_mask + t);
+            if (m.x | m.y | m.z | m.w) {
+                uint4 o = *reinterpret_cast<uint4*>(s_off + t);
+                o.x += __popc(m.x); o.y += __popc(m.y); o.z += __popc(m.z); o.w += __popc(m.w);
+                *reinterpret_cast<uint4*>(s_off + t) = o;
+                *reinterpret_cast<uint4*>(s_mask + t) = make_uint4(0u, 0u, 0u, 0u);
             }
         }
+        // the barrier at the top of the next batch orders these updates before its passes; nothing reads `sb` here
     }
 }
 
@@ -609,7 +668,12 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     const bool counting = !(flags & XYZ_FLAG_RADIX_BINNING) && n_tiles <= kBinMaxTiles;
     int chunk_size = kBinBatch, n_chunks = 1;
     if (counting) {
-        const int want = 4 * sm_count();  // CTAs of the count / scatter kernels
+        static const int per_sm = [] {  // CTAs of the count / scatter kernels per SM (tuning knob)
+            const char* e = std::getenv("XYZ_SPLAT_BIN_CTAS_PER_SM");
+            const int x = e ? std::atoi(e) : 0;
+            return x > 0 && x <= 64 ? x : 4;
+        }();
+        const int want = per_sm * sm_count();
         chunk_size = ((ng + want - 1) / want + kBinBatch - 1) / kBinBatch * kBinBatch;
         n_chunks = (ng + chunk_size - 1) / chunk_size;
     }
@@ -665,7 +729,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
             const size_t smem = sizeof(unsigned int) * n_tiles;
             splat_bin_count_kernel<<<n_chunks, kBinThreads, smem, st>>>(v, b.records, b.rects, b.spans, b.touched,
                                                                          chunk_size, n_tiles, hist, d2max, no_cull);
-            splat_bin_colscan_kernel<<<(n_tiles + 31) / 32, dim3(32, 8), 0, st>>>(hist, n_chunks, n_tiles, tile_total);
+            splat_bin_colscan_kernel<<<(n_tiles + 31) / 32, dim3(32, 32), 0, st>>>(hist, n_chunks, n_tiles, tile_total);
             splat_bin_tilescan_kernel<<<1, 1024, 0, st>>>(tile_total, n_tiles, b.tile_ranges, b.chunk_offsets, total_dev);
             count_launch(3);
             total_src = total_dev;
@@ -709,7 +773,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
 
     if (entries > 0) {
         if (counting) {
-            const size_t smem = 2 * sizeof(unsigned int) * n_tiles;
+            const size_t smem = 2 * sizeof(unsigned int) * ((n_tiles + 3) & ~3);
             if (smem > 48 * 1024) {
                 ce = deterministic ? cudaFuncSetAttribute(splat_bin_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
                                    : cudaFuncSetAttribute(splat_bin_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
