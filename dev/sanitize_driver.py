@@ -64,3 +64,18 @@ v5 = torch.tensor([0.0, 1.0, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev); g
 assert B.batched_lsq(pts.data_ptr(), n, v5.data_ptr(), g5.data_ptr(), 1) >= 0
 torch.cuda.synchronize()
 print("sanitize_driver ok")
+# splat: counting-sort binning (default) and the radix path, atomics and deterministic rows; Gaussians taller than the
+# 16 cached tile rows, a batch with more spans than register slots, a row band, > 4096 tiles (opt-in shared memory)
+if os.environ.get("SANITIZE_SPLAT", "1") != "0":
+    for (Ws, Hs, Ns, band) in ((320, 400, 1500, None), (320, 400, 1500, (100, 300)), (2048, 1040, 600, None)):
+        params, target = orc.splat_scene(Ns, Ws, Hs, seed=3)
+        params[10:60, 2:4] = 3.5                      # 50 consecutive huge Gaussians: > 512 spans in one batch
+        params[100:140, 0] = -5000.0                  # off screen
+        tp, tt = D(params), D(target)
+        for flags in (0, x.FLAG_DETERMINISTIC, x.FLAG_RADIX_BINNING, x.FLAG_PRECISE_MATH):
+            grads = torch.zeros((Ns, 9), device=dev); img = torch.zeros((Ws * Hs, 3), device=dev)
+            loss = torch.zeros(1, device=dev)
+            x.launch_gaussian_splatting(tp, grads, tt, img, loss, Ws, Hs, Ns, flags, rows=band)
+            torch.cuda.synchronize()
+            assert np.isfinite(grads.cpu().numpy()).all() and np.isfinite(loss.item())
+print("sanitize_driver: ok")

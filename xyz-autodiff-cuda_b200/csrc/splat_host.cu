@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(256)
 constexpr int kBinThreads = 256;
 constexpr int kBinBatch = 32;
 constexpr int kBinMaxTiles = 8192;  // 8 bytes of shared memory per tile in the scatter kernel
+constexpr long long kBinMaxEntries = 48LL << 20;  // predicted list length up to which the counting sort is used
 constexpr int kBinRegRows = 2;      // spans per thread kept in registers between the passes of a batch
 
 // Half a warp per Gaussian, one lane per tile row; the next Gaussian's rectangle and spans are in flight while the
@@ -665,7 +666,16 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     const int ng = N > 0 ? N : 1;
 
     // binning: stable counting sort by tile (default) or, for very large tile counts / on request, the radix path
-    const bool counting = !(flags & XYZ_FLAG_RADIX_BINNING) && n_tiles <= kBinMaxTiles;
+    // Both give the same lists bit for bit, so the choice is a pure cost decision: the counting sort appends 4 bytes at
+    // a time to n_chunks x n_tiles output streams, which stays in L2 up to a few 10^7 entries (measured crossover on
+    // B200 at 1024^2: ~6.6e7 entries, dev/splat_bin_crossover.py); beyond, the radix sort's staged full-sector
+    // writes win.  The list length is not known yet: predicted from this thread's previous launch of the same scene
+    // shape, else from N.
+    const long long predicted = (g_last.valid && g_last.view.num_gaussians == N && g_last.view.width == W &&
+                                 g_last.view.height == H && g_last.view.row_begin == row_begin && g_last.view.row_end == row_end)
+                                    ? g_last.entries
+                                    : static_cast<long long>(N) * 40;
+    const bool counting = !(flags & XYZ_FLAG_RADIX_BINNING) && n_tiles <= kBinMaxTiles && predicted <= kBinMaxEntries;
     int chunk_size = kBinBatch, n_chunks = 1;
     if (counting) {
         static const int per_sm = [] {  // CTAs of the count / scatter kernels per SM (tuning knob)
