@@ -200,7 +200,7 @@ __global__ void __launch_bounds__(256)
 constexpr int kBinThreads = 256;
 constexpr int kBinBatch = 32;
 constexpr int kBinMaxTiles = 8192;  // 8 bytes of shared memory per tile in the scatter kernel
-constexpr long long kBinMaxEntries = 48LL << 20;  // predicted list length up to which the counting sort is used
+constexpr long long kBinLongList = 40LL << 20;  // predicted list length beyond which the chunks become one per SM
 constexpr int kBinRegRows = 2;      // spans per thread kept in registers between the passes of a batch
 
 // Half a warp per Gaussian, one lane per tile row; the next Gaussian's rectangle and spans are in flight while the
@@ -666,23 +666,25 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     const int ng = N > 0 ? N : 1;
 
     // binning: stable counting sort by tile (default) or, for very large tile counts / on request, the radix path
-    // Both give the same lists bit for bit, so the choice is a pure cost decision: the counting sort appends 4 bytes at
-    // a time to n_chunks x n_tiles output streams, which stays in L2 up to a few 10^7 entries (measured crossover on
-    // B200 at 1024^2: ~6.6e7 entries, dev/splat_bin_crossover.py); beyond, the radix sort's staged full-sector
-    // writes win.  The list length is not known yet: predicted from this thread's previous launch of the same scene
-    // shape, else from N.
+    // The counting sort appends 4 bytes at a time to n_chunks x n_tiles output streams; it is fast as long as the open
+    // 32-byte sectors of all streams stay in L2 until they are complete, so long lists get fewer, longer chunks
+    // (measured at 1024^2, dev/splat_knob3m.sh: 4 CTAs per SM win up to ~3e7 entries, 1 per SM beyond -- at 1.2e8
+    // entries 4 per SM are 0.8 ms SLOWER than 1 per SM and lose to the radix sort).  The list length is not known yet:
+    // predicted from this thread's previous launch of the same scene shape, else from N.  Whatever is chosen, the
+    // lists are the same bit for bit.
     const long long predicted = (g_last.valid && g_last.view.num_gaussians == N && g_last.view.width == W &&
                                  g_last.view.height == H && g_last.view.row_begin == row_begin && g_last.view.row_end == row_end)
                                     ? g_last.entries
                                     : static_cast<long long>(N) * 40;
-    const bool counting = !(flags & XYZ_FLAG_RADIX_BINNING) && n_tiles <= kBinMaxTiles && predicted <= kBinMaxEntries;
+    const bool counting = !(flags & XYZ_FLAG_RADIX_BINNING) && n_tiles <= kBinMaxTiles;
     int chunk_size = kBinBatch, n_chunks = 1;
     if (counting) {
-        static const int per_sm = [] {  // CTAs of the count / scatter kernels per SM (tuning knob)
+        static const int forced = [] {  // tuning knob: CTAs of the count / scatter kernels per SM
             const char* e = std::getenv("XYZ_SPLAT_BIN_CTAS_PER_SM");
             const int x = e ? std::atoi(e) : 0;
-            return x > 0 && x <= 64 ? x : 4;
+            return x > 0 && x <= 64 ? x : 0;
         }();
+        const int per_sm = forced ? forced : (predicted <= kBinLongList ? 4 : 1);
         const int want = per_sm * sm_count();
         chunk_size = ((ng + want - 1) / want + kBinBatch - 1) / kBinBatch * kBinBatch;
         n_chunks = (ng + chunk_size - 1) / chunk_size;
