@@ -96,40 +96,92 @@ __device__ __forceinline__ int2 tile_row_span(const SpanCoef& c, const int4& r, 
     return make_int2(max(xi0 / kTile, r.x), min(xi1 / kTile + 1, r.z));
 }
 
+// kCount (counting-sort binning, section 2b): the grid is one CTA per chunk of `chunk_size` consecutive Gaussians and
+// the kernel also builds the chunk's tile histogram in shared memory -> hist[chunk][tile].  A thread counts the tiles
+// of its own Gaussian right where it derives the spans; Gaussians with more than kBigGaussian tiles are left to the
+// whole warp afterwards (one lane per tile row), so that a screen-filling Gaussian costs ~tiles_x + tiles_y steps
+// instead of tiles_x * tiles_y.
+constexpr unsigned int kBigGaussian = 192;
+
+template <bool kCount>
 __global__ void __launch_bounds__(256)
     splat_preprocess_kernel(SplatView v, const xyz_gaussian_params* __restrict__ params, float4* __restrict__ records,
                             int4* __restrict__ rects, unsigned int* __restrict__ touched, int2* __restrict__ spans,
-                            float d2max, int no_cull) {
-    const int g = blockIdx.x * blockDim.x + threadIdx.x;
-    if (g >= v.num_gaussians) return;
-    const xyz_gaussian_params p = params[g];
-    // exp_logic.cuh:17-25, covariance_generation.cuh:154-172, sym_matrix2_inv_logic.cuh:21-40,
-    // math.cuh:200-204 (sigmoid) -- computed once per Gaussian instead of once per pair per pass
-    const float es0 = expf(p.scale[0]), es1 = expf(p.scale[1]);
-    const float ct = cosf(p.rotation[0]), sn = sinf(p.rotation[0]);
-    const float m00 = __fmul_rn(es0, ct), m01 = __fmul_rn(-es1, sn), m10 = __fmul_rn(es0, sn), m11 = __fmul_rn(es1, ct);
-    const float A = __fadd_rn(__fmul_rn(m00, m00), __fmul_rn(m01, m01));
-    const float B = __fadd_rn(__fmul_rn(m00, m10), __fmul_rn(m01, m11));
-    const float C = __fadd_rn(__fmul_rn(m10, m10), __fmul_rn(m11, m11));
-    float det = __fsub_rn(__fmul_rn(A, C), __fmul_rn(B, B));
-    if (fabsf(det) < 1e-8f) det = 1e-8f;
-    const float inv_det = __fdiv_rn(1.0f, det);
-    const float ia = __fmul_rn(C, inv_det), ib = __fmul_rn(-B, inv_det), ic = __fmul_rn(A, inv_det);
-    const float so = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-p.opacity[0])));
-    records[3 * g] = make_float4(p.center[0], p.center[1], ia, ib);
-    records[3 * g + 1] = make_float4(ic, so, p.color[0], p.color[1]);
-    records[3 * g + 2] = make_float4(p.color[2], 0.f, 0.f, 0.f);
-    const int4 r = gaussian_tile_rect(p.center[0], p.center[1], ia, ib, ic, v, d2max, no_cull);
-    rects[g] = r;
-    const SpanCoef sc = span_coef(p.center[0], p.center[1], ia, ib, ic, d2max, no_cull);
-    unsigned int cnt = 0;
-    for (int ty = r.y; ty < r.w; ++ty) {
-        const int2 s = tile_row_span(sc, r, ty, v);
-        cnt += static_cast<unsigned int>(max(s.y - s.x, 0));
-        // the first kSpanRows rows are kept for the key emission (rows beyond that are recomputed there)
-        if (ty - r.y < kSpanRows) spans[static_cast<size_t>(g) * kSpanRows + (ty - r.y)] = make_int2(s.x, max(s.y, s.x));
+                            float d2max, int no_cull, int chunk_size, int n_tiles, unsigned int* __restrict__ hist) {
+    extern __shared__ unsigned int s_cnt[];  // kCount: n_tiles counters
+    const int tid = threadIdx.x;
+    const int per_cta = kCount ? chunk_size : 256;
+    const int g_begin = blockIdx.x * per_cta, g_end = min(g_begin + per_cta, v.num_gaussians);
+    if (kCount) {
+        for (int t = tid; t < n_tiles; t += 256) s_cnt[t] = 0u;
+        __syncthreads();
     }
-    touched[g] = cnt;
+    for (int gb = g_begin; gb < g_end; gb += 256) {  // warp-uniform trip count
+        const int g = gb + tid;
+        const bool live = g < g_end;
+        int4 r = make_int4(0, 0, 0, 0);
+        SpanCoef sc{};
+        unsigned int cnt = 0;
+        bool big_one = false;  // rectangle of more than kBigGaussian tiles: counted by the whole warp below
+        if (live) {
+            const xyz_gaussian_params p = params[g];
+            // exp_logic.cuh:17-25, covariance_generation.cuh:154-172, sym_matrix2_inv_logic.cuh:21-40,
+            // math.cuh:200-204 (sigmoid) -- computed once per Gaussian instead of once per pair per pass
+            const float es0 = expf(p.scale[0]), es1 = expf(p.scale[1]);
+            const float ct = cosf(p.rotation[0]), sn = sinf(p.rotation[0]);
+            const float m00 = __fmul_rn(es0, ct), m01 = __fmul_rn(-es1, sn), m10 = __fmul_rn(es0, sn), m11 = __fmul_rn(es1, ct);
+            const float A = __fadd_rn(__fmul_rn(m00, m00), __fmul_rn(m01, m01));
+            const float B = __fadd_rn(__fmul_rn(m00, m10), __fmul_rn(m01, m11));
+            const float C = __fadd_rn(__fmul_rn(m10, m10), __fmul_rn(m11, m11));
+            float det = __fsub_rn(__fmul_rn(A, C), __fmul_rn(B, B));
+            if (fabsf(det) < 1e-8f) det = 1e-8f;
+            const float inv_det = __fdiv_rn(1.0f, det);
+            const float ia = __fmul_rn(C, inv_det), ib = __fmul_rn(-B, inv_det), ic = __fmul_rn(A, inv_det);
+            const float so = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-p.opacity[0])));
+            records[3 * g] = make_float4(p.center[0], p.center[1], ia, ib);
+            records[3 * g + 1] = make_float4(ic, so, p.color[0], p.color[1]);
+            records[3 * g + 2] = make_float4(p.color[2], 0.f, 0.f, 0.f);
+            r = gaussian_tile_rect(p.center[0], p.center[1], ia, ib, ic, v, d2max, no_cull);
+            rects[g] = r;
+            sc = span_coef(p.center[0], p.center[1], ia, ib, ic, d2max, no_cull);
+            big_one = static_cast<unsigned int>((r.z - r.x) * (r.w - r.y)) > kBigGaussian;
+            for (int ty = r.y; ty < r.w; ++ty) {
+                const int2 s = tile_row_span(sc, r, ty, v);
+                cnt += static_cast<unsigned int>(max(s.y - s.x, 0));
+                // the first kSpanRows rows are kept for the binning kernels (rows beyond that are recomputed there)
+                if (ty - r.y < kSpanRows) spans[static_cast<size_t>(g) * kSpanRows + (ty - r.y)] = make_int2(s.x, max(s.y, s.x));
+                if (kCount && !big_one)
+                    for (int tx = s.x; tx < s.y; ++tx) atomicAdd(&s_cnt[ty * v.tiles_x + tx], 1u);
+            }
+            touched[g] = cnt;
+        }
+        if (kCount) {
+            unsigned int big = __ballot_sync(0xffffffffu, big_one);
+            const int lane = tid & 31;
+            while (big) {
+                const int src = __ffs(big) - 1;
+                big &= big - 1;
+                int4 rb;
+                SpanCoef cb;
+                rb.x = __shfl_sync(0xffffffffu, r.x, src); rb.y = __shfl_sync(0xffffffffu, r.y, src);
+                rb.z = __shfl_sync(0xffffffffu, r.z, src); rb.w = __shfl_sync(0xffffffffu, r.w, src);
+                cb.cx = __shfl_sync(0xffffffffu, sc.cx, src); cb.cy = __shfl_sync(0xffffffffu, sc.cy, src);
+                cb.k = __shfl_sync(0xffffffffu, sc.k, src); cb.a = __shfl_sync(0xffffffffu, sc.a, src);
+                cb.b = __shfl_sync(0xffffffffu, sc.b, src); cb.hxv = __shfl_sync(0xffffffffu, sc.hxv, src);
+                cb.hyv_m = __shfl_sync(0xffffffffu, sc.hyv_m, src); cb.dyR = __shfl_sync(0xffffffffu, sc.dyR, src);
+                cb.ok = __shfl_sync(0xffffffffu, sc.ok, src);
+                for (int ty = rb.y + lane; ty < rb.w; ty += 32) {
+                    const int2 s = tile_row_span(cb, rb, ty, v);
+                    for (int tx = s.x; tx < s.y; ++tx) atomicAdd(&s_cnt[ty * v.tiles_x + tx], 1u);
+                }
+            }
+        }
+    }
+    if (kCount) {
+        __syncthreads();
+        unsigned int* out = hist + static_cast<size_t>(blockIdx.x) * n_tiles;
+        for (int t = tid; t < n_tiles; t += 256) out[t] = s_cnt[t];
+    }
 }
 
 // ---- 2. keys in Gaussian order ----------------------------------------------------------------------
@@ -188,7 +240,7 @@ __global__ void __launch_bounds__(256)
 
 // ---- 2b. stable counting sort by tile (the default binning for up to kBinMaxTiles tiles) --------------------------
 // The keys are never materialised.  The Gaussians are cut into `n_chunks` consecutive chunks, one CTA each:
-//   splat_bin_count_kernel    per-chunk tile histogram in shared memory -> hist[chunk][tile]
+//   splat_preprocess_kernel<true>  also builds the per-chunk tile histogram in shared memory -> hist[chunk][tile]
 //   splat_bin_colscan_kernel  per tile: exclusive prefix over the chunks (in place) + the tile's list length
 //   splat_bin_tilescan_kernel exclusive scan over the tiles -> tile_ranges, the backward work-list offsets, total
 //   splat_bin_scatter_kernel  every chunk walks its Gaussians again in batches of 32 (ascending id): a 32-bit mask
@@ -202,60 +254,6 @@ constexpr int kBinBatch = 32;
 constexpr int kBinMaxTiles = 8192;  // 8 bytes of shared memory per tile in the scatter kernel
 constexpr long long kBinLongList = 40LL << 20;  // predicted list length beyond which the chunks become one per SM
 constexpr int kBinRegRows = 2;      // spans per thread kept in registers between the passes of a batch
-
-// Half a warp per Gaussian, one lane per tile row; the next Gaussian's rectangle and spans are in flight while the
-// current one is counted.
-__global__ void __launch_bounds__(kBinThreads)
-    splat_bin_count_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ rects,
-                           const int2* __restrict__ spans, const unsigned int* __restrict__ touched, int chunk_size,
-                           int n_tiles, unsigned int* __restrict__ hist, float d2max, int no_cull) {
-    extern __shared__ unsigned int s_bin[];  // n_tiles counters
-    const int tid = threadIdx.x, hl = tid & 15;
-    const int g_begin = blockIdx.x * chunk_size, g_end = min(g_begin + chunk_size, v.num_gaussians);
-    for (int t = tid; t < n_tiles; t += kBinThreads) s_bin[t] = 0u;
-    __syncthreads();
-    int g = g_begin + (tid >> 4);
-    unsigned int cnt = 0u;
-    int4 r = make_int4(0, 0, 0, 0);
-    int2 s0 = make_int2(0, 0);
-    if (g < g_end) {
-        cnt = touched[g];
-        r = rects[g];
-        s0 = spans[static_cast<size_t>(g) * kSpanRows + hl];
-    }
-    while (g < g_end) {
-        const int gn = g + kBinThreads / 16;
-        unsigned int cnt_n = 0u;
-        int4 r_n = make_int4(0, 0, 0, 0);
-        int2 s0_n = make_int2(0, 0);
-        if (gn < g_end) {
-            cnt_n = touched[gn];
-            r_n = rects[gn];
-            s0_n = spans[static_cast<size_t>(gn) * kSpanRows + hl];
-        }
-        if (cnt != 0u) {
-            for (int rb = r.y; rb < r.w; rb += kSpanRows) {
-                const int ty = rb + hl;
-                if (ty < r.w) {
-                    int2 s = s0;
-                    if (rb != r.y) {
-                        const float4 r0 = __ldg(records + 3 * g), r1 = __ldg(records + 3 * g + 1);
-                        const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
-                        s = tile_row_span(sc, r, ty, v);
-                    }
-                    for (int tx = s.x; tx < s.y; ++tx) atomicAdd(&s_bin[ty * v.tiles_x + tx], 1u);
-                }
-            }
-        }
-        g = gn;
-        cnt = cnt_n;
-        r = r_n;
-        s0 = s0_n;
-    }
-    __syncthreads();
-    unsigned int* out = hist + static_cast<size_t>(blockIdx.x) * n_tiles;
-    for (int t = tid; t < n_tiles; t += kBinThreads) out[t] = s_bin[t];
-}
 
 // block (32, 32): 32 consecutive tiles x 32 groups of consecutive chunks
 __global__ void __launch_bounds__(1024)
@@ -727,8 +725,12 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
 
     long long entries = 0;
     if (N > 0) {
-        splat_preprocess_kernel<<<(N + 255) / 256, 256, 0, st>>>(v, gaussians, b.records, b.rects, b.touched, b.spans,
-                                                                 d2max, no_cull);
+        if (counting)
+            splat_preprocess_kernel<true><<<n_chunks, 256, sizeof(unsigned int) * n_tiles, st>>>(
+                v, gaussians, b.records, b.rects, b.touched, b.spans, d2max, no_cull, chunk_size, n_tiles, hist);
+        else
+            splat_preprocess_kernel<false><<<(N + 255) / 256, 256, 0, st>>>(
+                v, gaussians, b.records, b.rects, b.touched, b.spans, d2max, no_cull, 0, 0, nullptr);
         count_launch();
         if (!counting || deterministic) {  // positions in Gaussian order: radix keys / rows of entry_grads
             ce = cub::DeviceScan::InclusiveSum(base + o_scan_tmp, scan_tmp_bytes, TouchedIter(b.touched, ToU64()),
@@ -738,12 +740,9 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
         }
         const unsigned long long* total_src = b.offsets + (N - 1);
         if (counting) {
-            const size_t smem = sizeof(unsigned int) * n_tiles;
-            splat_bin_count_kernel<<<n_chunks, kBinThreads, smem, st>>>(v, b.records, b.rects, b.spans, b.touched,
-                                                                         chunk_size, n_tiles, hist, d2max, no_cull);
             splat_bin_colscan_kernel<<<(n_tiles + 31) / 32, dim3(32, 32), 0, st>>>(hist, n_chunks, n_tiles, tile_total);
             splat_bin_tilescan_kernel<<<1, 1024, 0, st>>>(tile_total, n_tiles, b.tile_ranges, b.chunk_offsets, total_dev);
-            count_launch(3);
+            count_launch(2);
             total_src = total_dev;
         }
         // the list length is data dependent: one 8-byte read-back (the only synchronisation)
