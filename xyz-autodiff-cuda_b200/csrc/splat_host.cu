@@ -107,12 +107,14 @@ template <bool kCount>
 __global__ void __launch_bounds__(256)
     splat_preprocess_kernel(SplatView v, const xyz_gaussian_params* __restrict__ params, float4* __restrict__ records,
                             int4* __restrict__ rects, unsigned int* __restrict__ touched, int2* __restrict__ spans,
-                            float d2max, int no_cull, int chunk_size, int n_tiles, unsigned int* __restrict__ hist) {
+                            float d2max, int no_cull, int chunk_size, int n_tiles, unsigned int* __restrict__ hist,
+                            unsigned int* __restrict__ ticket) {
     extern __shared__ unsigned int s_cnt[];  // kCount: n_tiles counters
     const int tid = threadIdx.x;
     const int per_cta = kCount ? chunk_size : 256;
     const int g_begin = blockIdx.x * per_cta, g_end = min(g_begin + per_cta, v.num_gaussians);
     if (kCount) {
+        if (blockIdx.x == 0 && tid == 0) *ticket = 0u;  // for the column-scan kernel that follows
         for (int t = tid; t < n_tiles; t += 256) s_cnt[t] = 0u;
         __syncthreads();
     }
@@ -242,7 +244,7 @@ __global__ void __launch_bounds__(256)
 // The keys are never materialised.  The Gaussians are cut into `n_chunks` consecutive chunks, one CTA each:
 //   splat_preprocess_kernel<true>  also builds the per-chunk tile histogram in shared memory -> hist[chunk][tile]
 //   splat_bin_colscan_kernel  per tile: exclusive prefix over the chunks (in place) + the tile's list length
-//   splat_bin_tilescan_kernel exclusive scan over the tiles -> tile_ranges, the backward work-list offsets, total
+//                             its last CTA: exclusive scan over the tiles -> tile_ranges, backward work-list offsets, total
 //   splat_bin_scatter_kernel  every chunk walks its Gaussians again in batches of 32 (ascending id): a 32-bit mask
 //                             per tile collects which Gaussians of the batch touch it (shared-memory atomicOr); an
 //                             entry's slot is  tile offset + popc(mask below its own bit)  -- ascending Gaussian id
@@ -255,44 +257,15 @@ constexpr int kBinMaxTiles = 8192;  // 8 bytes of shared memory per tile in the 
 constexpr long long kBinLongList = 40LL << 20;  // predicted list length beyond which the chunks become one per SM
 constexpr int kBinRegRows = 2;      // spans per thread kept in registers between the passes of a batch
 
-// block (32, 32): 32 consecutive tiles x 32 groups of consecutive chunks
-__global__ void __launch_bounds__(1024)
-    splat_bin_colscan_kernel(unsigned int* __restrict__ hist, int n_chunks, int n_tiles, unsigned int* __restrict__ tile_total) {
-    __shared__ unsigned int s_part[32][33];
-    const int tx = threadIdx.x, gy = threadIdx.y;
-    const int tile = blockIdx.x * 32 + tx;
-    const int per = (n_chunks + 31) / 32;
-    const int c0 = min(gy * per, n_chunks), c1 = min(c0 + per, n_chunks);
-    unsigned int sum = 0;
-    if (tile < n_tiles) {
-#pragma unroll 4
-        for (int c = c0; c < c1; ++c) sum += hist[static_cast<size_t>(c) * n_tiles + tile];
-    }
-    s_part[gy][tx] = sum;
-    __syncthreads();
-    unsigned int run = 0;
-    for (int q = 0; q < gy; ++q) run += s_part[q][tx];
-    if (tile < n_tiles) {
-#pragma unroll 4
-        for (int c = c0; c < c1; ++c) {
-            const size_t at = static_cast<size_t>(c) * n_tiles + tile;
-            const unsigned int x = hist[at];
-            hist[at] = run;
-            run += x;
-        }
-        if (gy == 31) tile_total[tile] = run;
-    }
-}
-
-// one CTA: exclusive scans over the tiles of (list length) and of ceil(list length / kBwdChunk)
-__global__ void __launch_bounds__(1024)
-    splat_bin_tilescan_kernel(const unsigned int* __restrict__ tile_total, int n_tiles, int2* __restrict__ tile_ranges,
-                              int* __restrict__ chunk_offsets, unsigned long long* __restrict__ total_entries) {
+// one CTA of 1024 threads: exclusive scans over the tiles of (list length) and of ceil(list length / kBwdChunk)
+__device__ __forceinline__ void bin_tilescan(const unsigned int* tile_total, int n_tiles, int2* __restrict__ tile_ranges,
+                                             int* __restrict__ chunk_offsets, unsigned long long* __restrict__ total_entries,
+                                             int tid) {
     __shared__ unsigned long long s_warp[32];
     __shared__ int s_warp_c[32];
     __shared__ unsigned long long s_carry;
     __shared__ int s_carry_c;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lane = tid & 31, warp = tid >> 5;
     if (tid == 0) {
         s_carry = 0ull;
         s_carry_c = 0;
@@ -300,7 +273,7 @@ __global__ void __launch_bounds__(1024)
     __syncthreads();
     for (int base = 0; base < n_tiles; base += 1024) {
         const int t = base + tid;
-        const unsigned int len = t < n_tiles ? tile_total[t] : 0u;
+        const unsigned int len = t < n_tiles ? __ldcg(tile_total + t) : 0u;  // written by other CTAs of this launch
         const int c = static_cast<int>((len + kBwdChunk - 1) / kBwdChunk);
         unsigned long long x = len;
         int xc = c;
@@ -353,6 +326,48 @@ __global__ void __launch_bounds__(1024)
         chunk_offsets[n_tiles] = s_carry_c;
         *total_entries = s_carry;
     }
+}
+
+// block (32, 32): 32 consecutive tiles x 32 groups of consecutive chunks
+// The last CTA to finish (ticket) goes on to scan the tile totals: tile_ranges, the backward work-list offsets and the
+// list length come out of the same launch.  `ticket` is zeroed by the preprocess kernel.
+__global__ void __launch_bounds__(1024)
+    splat_bin_colscan_kernel(unsigned int* __restrict__ hist, int n_chunks, int n_tiles, unsigned int* tile_total,
+                             unsigned int* ticket, int2* __restrict__ tile_ranges, int* __restrict__ chunk_offsets,
+                             unsigned long long* __restrict__ total_entries) {
+    __shared__ unsigned int s_part[32][33];
+    __shared__ bool s_last;
+    const int tx = threadIdx.x, gy = threadIdx.y;
+    const int tile = blockIdx.x * 32 + tx;
+    const int per = (n_chunks + 31) / 32;
+    const int c0 = min(gy * per, n_chunks), c1 = min(c0 + per, n_chunks);
+    unsigned int sum = 0;
+    if (tile < n_tiles) {
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) sum += hist[static_cast<size_t>(c) * n_tiles + tile];
+    }
+    s_part[gy][tx] = sum;
+    __syncthreads();
+    unsigned int run = 0;
+    for (int q = 0; q < gy; ++q) run += s_part[q][tx];
+    if (tile < n_tiles) {
+#pragma unroll 4
+        for (int c = c0; c < c1; ++c) {
+            const size_t at = static_cast<size_t>(c) * n_tiles + tile;
+            const unsigned int x = hist[at];
+            hist[at] = run;
+            run += x;
+        }
+        if (gy == 31) tile_total[tile] = run;
+    }
+    __threadfence();
+    __syncthreads();
+    const int tid = gy * 32 + tx;
+    if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    bin_tilescan(tile_total, n_tiles, tile_ranges, chunk_offsets, total_entries, tid);
 }
 
 // One span of consecutive tiles = one (Gaussian, tile row) of the current batch.
@@ -420,7 +435,8 @@ __global__ void __launch_bounds__(kBinThreads)
                              const int2* __restrict__ spans, const unsigned int* __restrict__ touched,
                              const unsigned long long* __restrict__ offsets_incl, int chunk_size, int n_tiles,
                              const unsigned int* __restrict__ hist, const int2* __restrict__ tile_ranges,
-                             unsigned int* __restrict__ vals_out, int* __restrict__ sorted_gid, float d2max, int no_cull) {
+                             unsigned int* __restrict__ vals_out, int* __restrict__ sorted_gid, float d2max, int no_cull,
+                             const int* __restrict__ chunk_offsets, int4* __restrict__ chunk_info, int chunk_info_size) {
     extern __shared__ __align__(16) unsigned int s_slots[];  // next free slot per tile, then the batch mask per tile
     __shared__ BinBatch sb;
     const int n_pad = (n_tiles + 3) & ~3;
@@ -428,6 +444,14 @@ __global__ void __launch_bounds__(kBinThreads)
     unsigned int* s_mask = s_slots + n_pad;
     const int tid = threadIdx.x;
     const int g_begin = blockIdx.x * chunk_size, g_end = min(g_begin + chunk_size, v.num_gaussians);
+    // the backward work list (one record per backward CTA, see splat_chunk_fill_kernel); surplus records: tile = -1
+    for (int t = blockIdx.x * kBinThreads + tid; t < n_tiles; t += gridDim.x * kBinThreads) {
+        const int2 r = tile_ranges[t];
+        const int first_chunk = chunk_offsets[t], c = chunk_offsets[t + 1] - first_chunk;
+        for (int k = 0; k < c; ++k) chunk_info[first_chunk + k] = make_int4(t, r.x + k * kBwdChunk, r.y, 0);
+    }
+    for (int c = chunk_offsets[n_tiles] + blockIdx.x * kBinThreads + tid; c < chunk_info_size; c += gridDim.x * kBinThreads)
+        chunk_info[c] = make_int4(-1, -1, -1, -1);
     const unsigned int* mine = hist + static_cast<size_t>(blockIdx.x) * n_tiles;
     for (int t = tid; t < n_pad; t += kBinThreads) {
         s_off[t] = t < n_tiles ? static_cast<unsigned int>(tile_ranges[t].x) + mine[t] : 0u;
@@ -698,7 +722,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
                  o_chunks = take(sizeof(int) * (n_tiles + 1)),
                  o_rest = take(sizeof(float4) * kTilePixels * static_cast<size_t>(n_tiles)),
                  o_hist = take(counting ? sizeof(unsigned int) * static_cast<size_t>(n_chunks) * n_tiles : 0),
-                 o_ttotal = take(sizeof(unsigned int) * n_tiles), o_total = take(sizeof(unsigned long long));
+                 o_ttotal = take(sizeof(unsigned int) * n_tiles), o_total = take(2 * sizeof(unsigned long long));
     size_t scan_tmp_bytes = 0;
     cub::DeviceScan::InclusiveSum(nullptr, scan_tmp_bytes, TouchedIter(nullptr, ToU64()),
                                   static_cast<unsigned long long*>(nullptr), ng, st);
@@ -719,6 +743,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     unsigned int* hist = reinterpret_cast<unsigned int*>(base + o_hist);
     unsigned int* tile_total = reinterpret_cast<unsigned int*>(base + o_ttotal);
     unsigned long long* total_dev = reinterpret_cast<unsigned long long*>(base + o_total);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(total_dev + 1);
 
     cudaError_t ce = cudaMemsetAsync(b.tile_ranges, 0, sizeof(int2) * n_tiles, st);
     if (ce != cudaSuccess) return static_cast<int>(ce);
@@ -727,10 +752,10 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     if (N > 0) {
         if (counting)
             splat_preprocess_kernel<true><<<n_chunks, 256, sizeof(unsigned int) * n_tiles, st>>>(
-                v, gaussians, b.records, b.rects, b.touched, b.spans, d2max, no_cull, chunk_size, n_tiles, hist);
+                v, gaussians, b.records, b.rects, b.touched, b.spans, d2max, no_cull, chunk_size, n_tiles, hist, ticket);
         else
             splat_preprocess_kernel<false><<<(N + 255) / 256, 256, 0, st>>>(
-                v, gaussians, b.records, b.rects, b.touched, b.spans, d2max, no_cull, 0, 0, nullptr);
+                v, gaussians, b.records, b.rects, b.touched, b.spans, d2max, no_cull, 0, 0, nullptr, nullptr);
         count_launch();
         if (!counting || deterministic) {  // positions in Gaussian order: radix keys / rows of entry_grads
             ce = cub::DeviceScan::InclusiveSum(base + o_scan_tmp, scan_tmp_bytes, TouchedIter(b.touched, ToU64()),
@@ -740,9 +765,9 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
         }
         const unsigned long long* total_src = b.offsets + (N - 1);
         if (counting) {
-            splat_bin_colscan_kernel<<<(n_tiles + 31) / 32, dim3(32, 32), 0, st>>>(hist, n_chunks, n_tiles, tile_total);
-            splat_bin_tilescan_kernel<<<1, 1024, 0, st>>>(tile_total, n_tiles, b.tile_ranges, b.chunk_offsets, total_dev);
-            count_launch(2);
+            splat_bin_colscan_kernel<<<(n_tiles + 31) / 32, dim3(32, 32), 0, st>>>(
+                hist, n_chunks, n_tiles, tile_total, ticket, b.tile_ranges, b.chunk_offsets, total_dev);
+            count_launch();
             total_src = total_dev;
         }
         // the list length is data dependent: one 8-byte read-back (the only synchronisation)
@@ -782,6 +807,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     b.entry_grads = deterministic ? reinterpret_cast<float*>(sbase + o_eg) : nullptr;
     b.chunk_info = reinterpret_cast<int4*>(sbase + o_cinfo);
 
+    const int chunk_info_size = static_cast<int>(entries / kBwdChunk + n_tiles);
     if (entries > 0) {
         if (counting) {
             const size_t smem = 2 * sizeof(unsigned int) * ((n_tiles + 3) & ~3);
@@ -793,11 +819,11 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
             if (deterministic)
                 splat_bin_scatter_kernel<true><<<n_chunks, kBinThreads, smem, st>>>(
                     v, b.records, b.rects, b.spans, b.touched, b.offsets, chunk_size, n_tiles, hist, b.tile_ranges,
-                    b.vals_out, b.sorted_gid, d2max, no_cull);
+                    b.vals_out, b.sorted_gid, d2max, no_cull, b.chunk_offsets, b.chunk_info, chunk_info_size);
             else
                 splat_bin_scatter_kernel<false><<<n_chunks, kBinThreads, smem, st>>>(
                     v, b.records, b.rects, b.spans, b.touched, nullptr, chunk_size, n_tiles, hist, b.tile_ranges,
-                    b.vals_out, nullptr, d2max, no_cull);
+                    b.vals_out, nullptr, d2max, no_cull, b.chunk_offsets, b.chunk_info, chunk_info_size);
             count_launch();
         } else {
             splat_emit_keys_kernel<<<(N + 15) / 16, 256, 0, st>>>(v, b.records, b.rects, b.touched, b.offsets, b.spans,
@@ -812,11 +838,13 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
             splat_chunk_scan_kernel<<<1, 1024, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets);
             count_launch(2);
         }
-        // surplus backward CTAs (the grid is an upper bound) read tile = -1
-        ce = cudaMemsetAsync(b.chunk_info, 0xff, sizeof(int4) * static_cast<size_t>(entries / kBwdChunk + n_tiles), st);
-        if (ce != cudaSuccess) return static_cast<int>(ce);
-        splat_chunk_fill_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets, b.chunk_info);
-        count_launch();
+        if (!counting) {
+            // surplus backward CTAs (the grid is an upper bound) read tile = -1
+            ce = cudaMemsetAsync(b.chunk_info, 0xff, sizeof(int4) * static_cast<size_t>(chunk_info_size), st);
+            if (ce != cudaSuccess) return static_cast<int>(ce);
+            splat_chunk_fill_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets, b.chunk_info);
+            count_launch();
+        }
     }
 
     err = precise ? splat_forward_launch_precise(v, b, target, output, st)
