@@ -252,10 +252,9 @@ __global__ void __launch_bounds__(256)
 //                             bit for bit against it and against the CPU restatement).
 // Work distribution inside a batch: one thread per (Gaussian, tile row) = one span of consecutive tiles.
 constexpr int kBinThreads = 256;
-constexpr int kBinBatch = 32;
-constexpr int kBinMaxTiles = 8192;  // 8 bytes of shared memory per tile in the scatter kernel
+constexpr int kBinBatch = 32;  // chunk sizes are multiples of this
+constexpr int kBinMaxTiles = 8192;  // 4 bytes of shared memory per tile (histogram / next free slot)
 constexpr long long kBinLongList = 40LL << 20;  // predicted list length beyond which the chunks become one per SM
-constexpr int kBinRegRows = 2;      // spans per thread kept in registers between the passes of a batch
 
 // one CTA of 1024 threads: exclusive scans over the tiles of (list length) and of ceil(list length / kBwdChunk)
 __device__ __forceinline__ void bin_tilescan(const unsigned int* tile_total, int n_tiles, int2* __restrict__ tile_ranges,
@@ -370,65 +369,12 @@ __global__ void __launch_bounds__(1024)
     bin_tilescan(tile_total, n_tiles, tile_ranges, chunk_offsets, total_entries, tid);
 }
 
-// One span of consecutive tiles = one (Gaussian, tile row) of the current batch.
-struct BinRow {
-    int k, tile0, width;  // bit of the Gaussian inside its batch, first tile of the span, tiles in the span
-    unsigned int ebase;   // deterministic mode: position of the span's first entry in Gaussian order
-};
-
-// Shared state of one batch (32 consecutive Gaussians) of the scatter kernel.
-struct __align__(16) BinBatch {
-    int2 spans[kBinBatch * kSpanRows];  // the stored spans of this batch's Gaussians
-    int rowbase[kBinBatch + 1];           // exclusive prefix of the Gaussians' tile-row counts
-    int row_y[kBinBatch];                 // first tile row of each Gaussian's rectangle
-};
-static_assert(kBinThreads * 2 == kBinBatch * kSpanRows, "every thread stages two spans of a batch");
-
-template <bool kWantEbase>
-__device__ __forceinline__ BinRow bin_row(const SplatView& v, const float4* __restrict__ records,
-                                          const int4* __restrict__ rects, const unsigned int* __restrict__ touched,
-                                          const unsigned long long* __restrict__ offsets_incl, const BinBatch& sb, int g0,
-                                          int rr, float d2max, int no_cull) {
-    int k = 0;  // largest k with rowbase[k] <= rr
-#pragma unroll
-    for (int step = kBinBatch / 2; step > 0; step >>= 1)
-        if (sb.rowbase[k + step] <= rr) k += step;
-    BinRow row;
-    row.k = k;
-    const int g = g0 + k;
-    const int j = rr - sb.rowbase[k];
-    const int ty = sb.row_y[k] + j;
-    int2 s;
-    if (j < kSpanRows) {
-        s = sb.spans[k * kSpanRows + j];
-    } else {
-        const float4 r0 = __ldg(records + 3 * g), r1 = __ldg(records + 3 * g + 1);
-        const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
-        s = tile_row_span(sc, rects[g], ty, v);
-    }
-    row.tile0 = ty * v.tiles_x + s.x;
-    row.width = max(s.y - s.x, 0);
-    row.ebase = 0u;
-    if (kWantEbase) {
-        unsigned int before = 0;  // entries of this Gaussian in earlier tile rows (row-major order inside a Gaussian)
-        for (int jj = 0; jj < min(j, kSpanRows); ++jj) {
-            const int2 t = sb.spans[k * kSpanRows + jj];
-            before += static_cast<unsigned int>(max(t.y - t.x, 0));
-        }
-        if (j > kSpanRows) {
-            const float4 r0 = __ldg(records + 3 * g), r1 = __ldg(records + 3 * g + 1);
-            const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
-            const int4 r = rects[g];
-            for (int jj = kSpanRows; jj < j; ++jj) {
-                const int2 t = tile_row_span(sc, r, r.y + jj, v);
-                before += static_cast<unsigned int>(max(t.y - t.x, 0));
-            }
-        }
-        row.ebase = static_cast<unsigned int>(offsets_incl[g] - touched[g]) + before;
-    }
-    return row;
-}
-
+// Scatter: one CTA per chunk, next free slot of every tile in shared memory (start = tile begin + the chunk's column
+// prefix).  Every warp OWNS a band of consecutive tile rows and walks the chunk's Gaussians in ascending id, taking
+// only the spans inside its band: a tile is only ever written by its owner warp, in Gaussian order, and the tiles of
+// one Gaussian are all different -- so `slot = next[tile]++` needs neither atomics nor block barriers, and every tile
+// list comes out ascending in Gaussian id (= the stable sort).  Lanes of a warp: RL tile rows x XP columns phases
+// (8 x 4 for bands of 8 rows), i.e. up to 32 entries of one Gaussian per step.
 template <bool kDeterministic>
 __global__ void __launch_bounds__(kBinThreads)
     splat_bin_scatter_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ rects,
@@ -437,12 +383,9 @@ __global__ void __launch_bounds__(kBinThreads)
                              const unsigned int* __restrict__ hist, const int2* __restrict__ tile_ranges,
                              unsigned int* __restrict__ vals_out, int* __restrict__ sorted_gid, float d2max, int no_cull,
                              const int* __restrict__ chunk_offsets, int4* __restrict__ chunk_info, int chunk_info_size) {
-    extern __shared__ __align__(16) unsigned int s_slots[];  // next free slot per tile, then the batch mask per tile
-    __shared__ BinBatch sb;
-    const int n_pad = (n_tiles + 3) & ~3;
-    unsigned int* s_off = s_slots;
-    unsigned int* s_mask = s_slots + n_pad;
-    const int tid = threadIdx.x;
+    extern __shared__ unsigned int s_next[];  // next free slot per tile
+    __shared__ unsigned char s_hit[kBinThreads / 32][32];  // per warp: rank among the group's hits -> lane
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g_begin = blockIdx.x * chunk_size, g_end = min(g_begin + chunk_size, v.num_gaussians);
     // the backward work list (one record per backward CTA, see splat_chunk_fill_kernel); surplus records: tile = -1
     for (int t = blockIdx.x * kBinThreads + tid; t < n_tiles; t += gridDim.x * kBinThreads) {
@@ -453,91 +396,111 @@ __global__ void __launch_bounds__(kBinThreads)
     for (int c = chunk_offsets[n_tiles] + blockIdx.x * kBinThreads + tid; c < chunk_info_size; c += gridDim.x * kBinThreads)
         chunk_info[c] = make_int4(-1, -1, -1, -1);
     const unsigned int* mine = hist + static_cast<size_t>(blockIdx.x) * n_tiles;
-    for (int t = tid; t < n_pad; t += kBinThreads) {
-        s_off[t] = t < n_tiles ? static_cast<unsigned int>(tile_ranges[t].x) + mine[t] : 0u;
-        s_mask[t] = 0u;
-    }
-    // prefetch registers: warp 0 holds (tile rows, first tile row) of the next batch's Gaussians, every thread two of
-    // the next batch's 32 x 16 stored spans
-    int pre_rows = 0, pre_y = 0;
-    int4 pre_spans = make_int4(0, 0, 0, 0);
-    auto prefetch = [&](int g0) {
-        if (tid < kBinBatch) {
-            const int g = g0 + tid;
-            pre_rows = 0;
-            pre_y = 0;
-            if (g < g_end && touched[g] != 0u) {
-                const int4 r = rects[g];
-                pre_rows = r.w - r.y;
-                pre_y = r.y;
-            }
-        }
-        const int g = g0 + (tid >> 3);
-        if (g < g_end) pre_spans = *reinterpret_cast<const int4*>(spans + static_cast<size_t>(g) * kSpanRows + (tid & 7) * 2);
+    for (int t = tid; t < n_tiles; t += kBinThreads) s_next[t] = static_cast<unsigned int>(tile_ranges[t].x) + mine[t];
+    __syncthreads();
+
+    // this warp's band of tile rows (of the rows this launch renders)
+    constexpr int kWarps = kBinThreads / 32;
+    const int ty_lo = v.row_begin / kTile, ty_hi = (v.row_end + kTile - 1) / kTile;
+    const int band = (ty_hi - ty_lo + kWarps - 1) / kWarps;
+    const int R0 = ty_lo + warp * band, R1 = min(R0 + band, ty_hi);
+    if (R0 >= R1) return;
+    const int rl_bits = band >= 8 ? 3 : (band >= 4 ? 2 : (band >= 2 ? 1 : 0));
+    const int RL = 1 << rl_bits, XP = 32 >> rl_bits;
+    const int rl = lane >> (5 - rl_bits), xl = lane & (XP - 1);
+
+    // Loads are batched so that their latency is paid once per group, not once per Gaussian: the rectangles of the
+    // NEXT 32 candidates are in flight while this group is processed, and the stored spans of up to 8 hits are fetched
+    // by two warp-wide loads (lane (rl, xl) fetches row rl of hits xl and 4 + xl) and handed out by shuffles.
+    auto load_rect = [&](int gb) {
+        const int g = gb + lane;
+        int4 r = make_int4(0, 0, 0, 0);
+        if (g < g_end && touched[g] != 0u) r = rects[g];
+        return r;
     };
-    prefetch(g_begin);
-    for (int g0 = g_begin; g0 < g_end; g0 += kBinBatch) {
-        if (tid < kBinBatch) {
-            int incl = pre_rows;
+    int4 r_next = load_rect(g_begin);
+    for (int gb = g_begin; gb < g_end; gb += 32) {
+        const int4 r = r_next;
+        if (gb + 32 < g_end) r_next = load_rect(gb + 32);
+        const bool hit = r.y < R1 && r.w > R0 && r.w > r.y;
+        const unsigned int hits = __ballot_sync(0xffffffffu, hit);
+        const int n_hits = __popc(hits);
+        __syncwarp();  // the previous group's readers of s_hit are done
+        if (hit) s_hit[warp][__popc(hits & ((1u << lane) - 1u))] = static_cast<unsigned char>(lane);  // rank -> lane
+        __syncwarp();
+        for (int base = 0; base < n_hits; base += 8) {
+            const int n_sub = min(8, n_hits - base);
+            // stage: spans of (hit xl, row rl) and (hit 4 + xl, row rl), first RL rows of the band only
+            int2 staged[2];
 #pragma unroll
-            for (int d = 1; d < 32; d <<= 1) {
-                const int y = __shfl_up_sync(0xffffffffu, incl, d);
-                if (tid >= d) incl += y;
-            }
-            sb.rowbase[tid + 1] = incl;
-            if (tid == 0) sb.rowbase[0] = 0;
-            sb.row_y[tid] = pre_y;
-        }
-        *reinterpret_cast<int4*>(&sb.spans[tid * 2]) = pre_spans;
-        __syncthreads();  // also: slots / masks of the previous batch settled
-        prefetch(g0 + kBinBatch);
-        const int total_rows = sb.rowbase[kBinBatch];
-        // the first spans of every thread stay in registers for both passes; further ones are derived again
-        BinRow reg[kBinRegRows];
-#pragma unroll
-        for (int q = 0; q < kBinRegRows; ++q) {
-            reg[q].k = 0; reg[q].tile0 = 0; reg[q].width = 0; reg[q].ebase = 0u;
-            const int rr = tid + q * kBinThreads;
-            if (rr < total_rows)
-                reg[q] = bin_row<kDeterministic>(v, records, rects, touched, offsets_incl, sb, g0, rr, d2max, no_cull);
-            const unsigned int bit = 1u << reg[q].k;
-            for (int t = 0; t < reg[q].width; ++t) atomicOr(&s_mask[reg[q].tile0 + t], bit);
-        }
-        for (int rr = tid + kBinRegRows * kBinThreads; rr < total_rows; rr += kBinThreads) {
-            const BinRow row = bin_row<false>(v, records, rects, touched, nullptr, sb, g0, rr, d2max, no_cull);
-            const unsigned int bit = 1u << row.k;
-            for (int t = 0; t < row.width; ++t) atomicOr(&s_mask[row.tile0 + t], bit);
-        }
-        __syncthreads();
-        auto place = [&](const BinRow& row) {
-            const unsigned int below = (1u << row.k) - 1u;
-            for (int t = 0; t < row.width; ++t) {
-                const int tile = row.tile0 + t;
-                const unsigned int pos = s_off[tile] + static_cast<unsigned int>(__popc(s_mask[tile] & below));
-                if (kDeterministic) {
-                    // payload = the entry's position in Gaussian order (its row of entry_grads); ids kept separately
-                    vals_out[pos] = row.ebase + static_cast<unsigned int>(t);
-                    sorted_gid[pos] = g0 + row.k;
-                } else {
-                    vals_out[pos] = static_cast<unsigned int>(g0 + row.k);
+            for (int q = 0; q < 2; ++q) {
+                staged[q] = make_int2(0, 0);
+                const int h = 4 * q + (lane & 3);
+                const int src = s_hit[warp][min(base + h, 31)] & 31;  // slots beyond n_hits hold stale lanes: guarded by h < n_sub
+                const int ry = __shfl_sync(0xffffffffu, r.y, src), rw = __shfl_sync(0xffffffffu, r.w, src);
+                if (h < n_sub) {
+                    const int ty = max(R0, ry) + rl, j = ty - ry;
+                    if (ty < min(R1, rw) && j < kSpanRows) staged[q] = spans[static_cast<size_t>(gb + src) * kSpanRows + j];
                 }
             }
-        };
-#pragma unroll
-        for (int q = 0; q < kBinRegRows; ++q) place(reg[q]);
-        for (int rr = tid + kBinRegRows * kBinThreads; rr < total_rows; rr += kBinThreads)
-            place(bin_row<kDeterministic>(v, records, rects, touched, offsets_incl, sb, g0, rr, d2max, no_cull));
-        __syncthreads();
-        for (int t = tid * 4; t < n_pad; t += kBinThreads * 4) {
-            const uint4 m = *reinterpret_cast<const uint4*>(s_mask + t);
-            if (m.x | m.y | m.z | m.w) {
-                uint4 o = *reinterpret_cast<uint4*>(s_off + t);
-                o.x += __popc(m.x); o.y += __popc(m.y); o.z += __popc(m.z); o.w += __popc(m.w);
-                *reinterpret_cast<uint4*>(s_off + t) = o;
-                *reinterpret_cast<uint4*>(s_mask + t) = make_uint4(0u, 0u, 0u, 0u);
+            for (int i = 0; i < n_sub; ++i) {
+                const int src = s_hit[warp][base + i];
+                const int gg = gb + src;
+                const int ry = __shfl_sync(0xffffffffu, r.y, src), rw = __shfl_sync(0xffffffffu, r.w, src);
+                const int row_end = min(R1, rw), row_first = max(R0, ry);
+                // the staged span of (hit i, my row) sits in lane (rl, i & 3), slot i >> 2
+                const int from = (rl << (5 - rl_bits)) | (i & 3);
+                const int sx = __shfl_sync(0xffffffffu, (i >> 2) ? staged[1].x : staged[0].x, from);
+                const int sy = __shfl_sync(0xffffffffu, (i >> 2) ? staged[1].y : staged[0].y, from);
+                for (int rb = row_first; rb < row_end; rb += RL) {
+                    const int ty = rb + rl;
+                    if (ty < row_end) {
+                        const int j = ty - ry;
+                        int2 sp;
+                        if (rb == row_first && j < kSpanRows) {
+                            sp = make_int2(sx, sy);
+                        } else if (j < kSpanRows) {
+                            sp = spans[static_cast<size_t>(gg) * kSpanRows + j];
+                        } else {
+                            const float4 r0 = __ldg(records + 3 * gg), r1 = __ldg(records + 3 * gg + 1);
+                            const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
+                            sp = tile_row_span(sc, rects[gg], ty, v);
+                        }
+                        unsigned int ebase = 0u;
+                        if (kDeterministic) {
+                            // payload = the entry's position in Gaussian order (row-major inside a Gaussian)
+                            unsigned int before = 0u;
+                            for (int jj = 0; jj < min(j, kSpanRows); ++jj) {
+                                const int2 t = spans[static_cast<size_t>(gg) * kSpanRows + jj];
+                                before += static_cast<unsigned int>(max(t.y - t.x, 0));
+                            }
+                            if (j > kSpanRows) {
+                                const float4 r0 = __ldg(records + 3 * gg), r1 = __ldg(records + 3 * gg + 1);
+                                const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
+                                const int4 rr = rects[gg];
+                                for (int jj = kSpanRows; jj < j; ++jj) {
+                                    const int2 t = tile_row_span(sc, rr, ry + jj, v);
+                                    before += static_cast<unsigned int>(max(t.y - t.x, 0));
+                                }
+                            }
+                            ebase = static_cast<unsigned int>(offsets_incl[gg] - touched[gg]) + before;
+                        }
+                        for (int x = sp.x + xl; x < sp.y; x += XP) {
+                            const int tile = ty * v.tiles_x + x;
+                            const unsigned int pos = s_next[tile];
+                            s_next[tile] = pos + 1u;
+                            if (kDeterministic) {
+                                vals_out[pos] = ebase + static_cast<unsigned int>(x - sp.x);
+                                sorted_gid[pos] = gg;
+                            } else {
+                                vals_out[pos] = static_cast<unsigned int>(gg);
+                            }
+                        }
+                    }
+                }
+                __syncwarp();  // the next Gaussian may reach the same tiles from other lanes
             }
         }
-        // the barrier at the top of the next batch orders these updates before its passes; nothing reads `sb` here
     }
 }
 
@@ -810,7 +773,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     const int chunk_info_size = static_cast<int>(entries / kBwdChunk + n_tiles);
     if (entries > 0) {
         if (counting) {
-            const size_t smem = 2 * sizeof(unsigned int) * ((n_tiles + 3) & ~3);
+            const size_t smem = sizeof(unsigned int) * n_tiles;
             if (smem > 48 * 1024) {
                 ce = deterministic ? cudaFuncSetAttribute(splat_bin_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
                                    : cudaFuncSetAttribute(splat_bin_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
