@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(1024)
 // prefix).  Every warp OWNS a band of consecutive tile rows and walks the chunk's Gaussians in ascending id, taking
 // only the spans inside its band: a tile is only ever written by its owner warp, in Gaussian order, and the tiles of
 // one Gaussian are all different -- so `slot = next[tile]++` needs neither atomics nor block barriers, and every tile
-// list comes out ascending in Gaussian id (= the stable sort).  Lanes of a warp: RL tile rows x XP columns phases
+// list comes out ascending in Gaussian id (= the stable sort).  Lanes of a warp: RL tile rows x XP column phases
 // (8 x 4 for bands of 8 rows), i.e. up to 32 entries of one Gaussian per step.
 template <bool kDeterministic>
 __global__ void __launch_bounds__(kBinThreads)
@@ -399,7 +399,9 @@ __global__ void __launch_bounds__(kBinThreads)
     for (int t = tid; t < n_tiles; t += kBinThreads) s_next[t] = static_cast<unsigned int>(tile_ranges[t].x) + mine[t];
     __syncthreads();
 
-    // this warp's band of tile rows (of the rows this launch renders)
+    // this warp's band of tile rows (of the rows this launch renders), taken RL rows at a time: lane = (row rl, column
+    // phase xl); a lane only ever touches the tiles (S0 + rl, x) with x = xl (mod XP), so consecutive Gaussians need
+    // no synchronisation at all -- program order inside the lane is the Gaussian order.
     constexpr int kWarps = kBinThreads / 32;
     const int ty_lo = v.row_begin / kTile, ty_hi = (v.row_end + kTile - 1) / kTile;
     const int band = (ty_hi - ty_lo + kWarps - 1) / kWarps;
@@ -410,63 +412,50 @@ __global__ void __launch_bounds__(kBinThreads)
     const int rl = lane >> (5 - rl_bits), xl = lane & (XP - 1);
 
     // Loads are batched so that their latency is paid once per group, not once per Gaussian: the rectangles of the
-    // NEXT 32 candidates are in flight while this group is processed, and the stored spans of up to 8 hits are fetched
-    // by two warp-wide loads (lane (rl, xl) fetches row rl of hits xl and 4 + xl) and handed out by shuffles.
+    // NEXT 32 candidates are in flight while this group is processed, and the spans of up to 8 hits are fetched by two
+    // warp-wide loads (lane (rl, xl) fetches row rl of hits xl & 3 and 4 + (xl & 3)) and handed out by shuffles.
     auto load_rect = [&](int gb) {
         const int g = gb + lane;
         int4 r = make_int4(0, 0, 0, 0);
         if (g < g_end && touched[g] != 0u) r = rects[g];
         return r;
     };
-    int4 r_next = load_rect(g_begin);
-    for (int gb = g_begin; gb < g_end; gb += 32) {
-        const int4 r = r_next;
-        if (gb + 32 < g_end) r_next = load_rect(gb + 32);
-        const bool hit = r.y < R1 && r.w > R0 && r.w > r.y;
-        const unsigned int hits = __ballot_sync(0xffffffffu, hit);
-        const int n_hits = __popc(hits);
-        __syncwarp();  // the previous group's readers of s_hit are done
-        if (hit) s_hit[warp][__popc(hits & ((1u << lane) - 1u))] = static_cast<unsigned char>(lane);  // rank -> lane
-        __syncwarp();
-        for (int base = 0; base < n_hits; base += 8) {
-            const int n_sub = min(8, n_hits - base);
-            // stage: spans of (hit xl, row rl) and (hit 4 + xl, row rl), first RL rows of the band only
-            int2 staged[2];
+    for (int S0 = R0; S0 < R1; S0 += RL) {
+        const int S1 = min(S0 + RL, R1);
+        const int ty = S0 + rl;  // this lane's tile row
+        unsigned int* row_next = s_next + ty * v.tiles_x;
+        int4 r_next = load_rect(g_begin);
+        for (int gb = g_begin; gb < g_end; gb += 32) {
+            const int4 r = r_next;
+            if (gb + 32 < g_end) r_next = load_rect(gb + 32);
+            const bool hit = r.y < S1 && r.w > S0 && r.w > r.y;
+            const unsigned int hits = __ballot_sync(0xffffffffu, hit);
+            const int n_hits = __popc(hits);
+            __syncwarp();  // the previous group's readers of s_hit are done
+            if (hit) s_hit[warp][__popc(hits & ((1u << lane) - 1u))] = static_cast<unsigned char>(lane);  // rank -> lane
+            __syncwarp();
+            for (int base = 0; base < n_hits; base += 8) {
+                const int n_sub = min(8, n_hits - base);
+                int2 staged[2];
+                unsigned int staged_e[2];
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
-                staged[q] = make_int2(0, 0);
-                const int h = 4 * q + (lane & 3);
-                const int src = s_hit[warp][min(base + h, 31)] & 31;  // slots beyond n_hits hold stale lanes: guarded by h < n_sub
-                const int ry = __shfl_sync(0xffffffffu, r.y, src), rw = __shfl_sync(0xffffffffu, r.w, src);
-                if (h < n_sub) {
-                    const int ty = max(R0, ry) + rl, j = ty - ry;
-                    if (ty < min(R1, rw) && j < kSpanRows) staged[q] = spans[static_cast<size_t>(gb + src) * kSpanRows + j];
-                }
-            }
-            for (int i = 0; i < n_sub; ++i) {
-                const int src = s_hit[warp][base + i];
-                const int gg = gb + src;
-                const int ry = __shfl_sync(0xffffffffu, r.y, src), rw = __shfl_sync(0xffffffffu, r.w, src);
-                const int row_end = min(R1, rw), row_first = max(R0, ry);
-                // the staged span of (hit i, my row) sits in lane (rl, i & 3), slot i >> 2
-                const int from = (rl << (5 - rl_bits)) | (i & 3);
-                const int sx = __shfl_sync(0xffffffffu, (i >> 2) ? staged[1].x : staged[0].x, from);
-                const int sy = __shfl_sync(0xffffffffu, (i >> 2) ? staged[1].y : staged[0].y, from);
-                for (int rb = row_first; rb < row_end; rb += RL) {
-                    const int ty = rb + rl;
-                    if (ty < row_end) {
-                        const int j = ty - ry;
+                for (int q = 0; q < 2; ++q) {
+                    staged[q] = make_int2(0, 0);
+                    staged_e[q] = 0u;
+                    const int h = 4 * q + (lane & 3);
+                    const int src = s_hit[warp][min(base + h, 31)] & 31;  // slots beyond n_hits hold stale lanes: guarded below
+                    const int ry = __shfl_sync(0xffffffffu, r.y, src), rw = __shfl_sync(0xffffffffu, r.w, src);
+                    if (h < n_sub && ty < S1 && ty >= ry && ty < rw) {
+                        const int gg = gb + src, j = ty - ry;
                         int2 sp;
-                        if (rb == row_first && j < kSpanRows) {
-                            sp = make_int2(sx, sy);
-                        } else if (j < kSpanRows) {
+                        if (j < kSpanRows) {
                             sp = spans[static_cast<size_t>(gg) * kSpanRows + j];
                         } else {
                             const float4 r0 = __ldg(records + 3 * gg), r1 = __ldg(records + 3 * gg + 1);
                             const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
                             sp = tile_row_span(sc, rects[gg], ty, v);
                         }
-                        unsigned int ebase = 0u;
+                        staged[q] = sp;
                         if (kDeterministic) {
                             // payload = the entry's position in Gaussian order (row-major inside a Gaussian)
                             unsigned int before = 0u;
@@ -483,22 +472,29 @@ __global__ void __launch_bounds__(kBinThreads)
                                     before += static_cast<unsigned int>(max(t.y - t.x, 0));
                                 }
                             }
-                            ebase = static_cast<unsigned int>(offsets_incl[gg] - touched[gg]) + before;
-                        }
-                        for (int x = sp.x + xl; x < sp.y; x += XP) {
-                            const int tile = ty * v.tiles_x + x;
-                            const unsigned int pos = s_next[tile];
-                            s_next[tile] = pos + 1u;
-                            if (kDeterministic) {
-                                vals_out[pos] = ebase + static_cast<unsigned int>(x - sp.x);
-                                sorted_gid[pos] = gg;
-                            } else {
-                                vals_out[pos] = static_cast<unsigned int>(gg);
-                            }
+                            staged_e[q] = static_cast<unsigned int>(offsets_incl[gg] - touched[gg]) + before;
                         }
                     }
                 }
-                __syncwarp();  // the next Gaussian may reach the same tiles from other lanes
+                for (int i = 0; i < n_sub; ++i) {
+                    const int gg = gb + s_hit[warp][base + i];
+                    // the span of (hit i, my row) was staged by lane (rl, i & 3) in slot i >> 2
+                    const int from = (rl << (5 - rl_bits)) | (i & 3);
+                    const int sx = __shfl_sync(0xffffffffu, (i >> 2) ? staged[1].x : staged[0].x, from);
+                    const int sy = __shfl_sync(0xffffffffu, (i >> 2) ? staged[1].y : staged[0].y, from);
+                    unsigned int eb = 0u;
+                    if (kDeterministic) eb = __shfl_sync(0xffffffffu, (i >> 2) ? staged_e[1] : staged_e[0], from);
+                    for (int x = sx + ((xl - sx) & (XP - 1)); x < sy; x += XP) {
+                        const unsigned int pos = row_next[x];
+                        row_next[x] = pos + 1u;
+                        if (kDeterministic) {
+                            vals_out[pos] = eb + static_cast<unsigned int>(x - sx);
+                            sorted_gid[pos] = gg;
+                        } else {
+                            vals_out[pos] = static_cast<unsigned int>(gg);
+                        }
+                    }
+                }
             }
         }
     }
