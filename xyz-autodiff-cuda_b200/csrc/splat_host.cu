@@ -245,12 +245,10 @@ __global__ void __launch_bounds__(256)
 //   splat_preprocess_kernel<true>  also builds the per-chunk tile histogram in shared memory -> hist[chunk][tile]
 //   splat_bin_colscan_kernel  per tile: exclusive prefix over the chunks (in place) + the tile's list length
 //                             its last CTA: exclusive scan over the tiles -> tile_ranges, backward work-list offsets, total
-//   splat_bin_scatter_kernel  every chunk walks its Gaussians again in batches of 32 (ascending id): a 32-bit mask
-//                             per tile collects which Gaussians of the batch touch it (shared-memory atomicOr); an
-//                             entry's slot is  tile offset + popc(mask below its own bit)  -- ascending Gaussian id
-//                             inside every tile list = exactly the stable sort the radix path produces (tested
-//                             bit for bit against it and against the CPU restatement).
-// Work distribution inside a batch: one thread per (Gaussian, tile row) = one span of consecutive tiles.
+//   splat_bin_scatter_kernel  every chunk walks its Gaussians again, ascending id; every tile is owned by one lane
+//                             (see the kernel), slot = next[tile]++  -- ascending Gaussian id inside every tile list
+//                             = exactly the stable sort the radix path produces (tested bit for bit against it and
+//                             against the CPU restatement).  Also writes the backward work list.
 constexpr int kBinThreads = 256;
 constexpr int kBinBatch = 32;  // chunk sizes are multiples of this
 constexpr int kBinMaxTiles = 8192;  // 4 bytes of shared memory per tile (histogram / next free slot)
