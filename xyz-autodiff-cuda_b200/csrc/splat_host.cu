@@ -767,12 +767,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     const int chunk_info_size = static_cast<int>(entries / kBwdChunk + n_tiles);
     if (entries > 0) {
         if (counting) {
-            const size_t smem = sizeof(unsigned int) * n_tiles;
-            if (smem > 48 * 1024) {
-                ce = deterministic ? cudaFuncSetAttribute(splat_bin_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))
-                                   : cudaFuncSetAttribute(splat_bin_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
-                if (ce != cudaSuccess) return static_cast<int>(ce);
-            }
+            const size_t smem = sizeof(unsigned int) * n_tiles;  // <= 32 KB (kBinMaxTiles)
             if (deterministic)
                 splat_bin_scatter_kernel<true><<<n_chunks, kBinThreads, smem, st>>>(
                     v, b.records, b.rects, b.spans, b.touched, b.offsets, chunk_size, n_tiles, hist, b.tile_ranges,

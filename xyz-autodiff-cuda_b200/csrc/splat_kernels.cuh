@@ -52,9 +52,13 @@ __device__ __forceinline__ float xor_sign(float v, float from) {
 //   dy = y_k - cy ; arg = dy (C2 dy + bdx) + t0 ; e = exp(arg) ; out_k,i += (so c_i) e
 // = 1 shared-memory wavefront, 1 MUFU and ~8.5 issue slots per pair.  Summation runs in ascending Gaussian
 // index per pixel, the reference's order (gaussian_splatting_kernel.cu:33-62).
-constexpr int kFwdThreads = 64;
+#ifndef XYZ_FWD_THREADS
+#define XYZ_FWD_THREADS 64
+#endif
+constexpr int kFwdThreads = XYZ_FWD_THREADS;
 constexpr int kFwdStage = 128;  // Gaussians staged per pass
-constexpr int kFwdRows = kTilePixels / kFwdThreads;  // 4 pixel rows per thread
+constexpr int kFwdRows = kTilePixels / kFwdThreads;  // pixel rows per thread (4)
+constexpr int kFwdRowStep = kFwdThreads / kTile;     // distance between a thread's rows
 
 __global__ void __launch_bounds__(kFwdThreads)
     splat_forward_kernel(SplatView v, const float4* __restrict__ records, const int* __restrict__ sorted_gid,
@@ -69,11 +73,11 @@ __global__ void __launch_bounds__(kFwdThreads)
     const int tile_x = blockIdx.x, tile_y = tile_y0 + blockIdx.y;
     const int tile = tile_y * v.tiles_x + tile_x;
     const int pxi = tile_x * kTile + (tid & (kTile - 1));
-    const int pyi0 = tile_y * kTile + (tid >> 4);  // rows pyi0 + 4 k
+    const int pyi0 = tile_y * kTile + (tid >> 4);  // rows pyi0 + kFwdRowStep k
     const float px = static_cast<float>(pxi);
     float py[kFwdRows];
 #pragma unroll
-    for (int k = 0; k < kFwdRows; ++k) py[k] = static_cast<float>(pyi0 + 4 * k);
+    for (int k = 0; k < kFwdRows; ++k) py[k] = static_cast<float>(pyi0 + kFwdRowStep * k);
 
     const int2 range = tile_ranges[tile];
     float o[kFwdRows][3];
@@ -109,7 +113,7 @@ __global__ void __launch_bounds__(kFwdThreads)
     float l = 0.f;
 #pragma unroll
     for (int k = 0; k < kFwdRows; ++k) {
-        const int pyi = pyi0 + 4 * k;
+        const int pyi = pyi0 + kFwdRowStep * k;
         // rest_sum = target_color - pixel_out (gaussian_splatting_kernel.cu:99-101) for the backward pass, stored
         // tile-major (4 KB contiguous per tile); .w = 1 for pixels of this launch, 0 outside the image / row band
         float4 rest = make_float4(0.f, 0.f, 0.f, 0.f);
