@@ -220,7 +220,12 @@ XYZ_API int xyz_covproj_shared_w_fwd_bwd_f32_allreduce(const float* J, const flo
  * gaussian_splatting_kernel.cu:114-149): renders `output` (overwritten), ADDS the L1 loss into
  * *total_loss and ADDS d(loss)/d(params) into `gradients`.  target/output are P x 3 floats
  * (PixelOutput = ConstArray<float,3>).  Synchronises `stream` once internally (the tile-list
- * length is data dependent); scratch is library-owned and grows on demand.                   */
+ * length is data dependent); scratch is library-owned and grows on demand (4 bytes per
+ * (tile, Gaussian) list entry, 36 more with XYZ_FLAG_DETERMINISTIC).
+ * The per-tile lists come from a stable counting sort by tile (images of up to 8192 tiles) or a
+ * stable radix sort of (tile, Gaussian) keys; the choice never changes a result bit.  Environment
+ * (read once, tuning only): XYZ_SPLAT_BIN_CTAS_PER_SM = CTAs per SM of the counting-sort kernels
+ * (default 4, 1 for predicted lists beyond 4e7 entries).                                        */
 XYZ_API int xyz_launch_gaussian_splatting(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients,
                                   const float* target_image, float* output_image, float* total_loss,
                                   int image_width, int image_height, int num_gaussians,
@@ -237,7 +242,8 @@ XYZ_API int xyz_launch_gaussian_splatting_rows(const xyz_gaussian_params* gaussi
 XYZ_API int xyz_splat_last_stats(long long stats_host[4]);
 /* Copies the integer tile-binning results of the most recent splat launch to host buffers (for the
  * bit-exact integer parity tests): per-Gaussian tile rectangles (N x 4 int32: tx0, ty0, tx1, ty1,
- * half-open), per-tile [begin, end) ranges (tiles x 2 int32), the sorted Gaussian ids
+ * half-open), per-tile [begin, end) ranges (tiles x 2 int32; an empty tile has begin == end --
+ * its running offset from the counting sort, (0, 0) from the radix path), the sorted Gaussian ids
  * (entries int32) and the per-Gaussian float records the rectangles were derived from
  * (N x 12 float: cx, cy, ia, ib, ic, sigmoid(opacity), r, g, b, 0, 0, 0).  Any pointer may be NULL.
  * Synchronises the device. */

@@ -186,7 +186,8 @@ __global__ void __launch_bounds__(256)
     }
 }
 
-// ---- 2. keys in Gaussian order ----------------------------------------------------------------------
+// ---- 2a. radix path: (tile, Gaussian) keys in Gaussian order -----------------------------------------
+// (more than kBinMaxTiles tiles, or XYZ_FLAG_RADIX_BINNING; section 2b is the default)
 // Half a warp per Gaussian: the 16 lanes take the spans of 16 tile rows at a time (stored by the preprocess kernel
 // for the first 16 rows, recomputed beyond), a shuffle scan gives each row its offset, then every row's span is
 // written with consecutive lanes -> coalesced stores.  Order inside a Gaussian: row-major (ty, tx).
