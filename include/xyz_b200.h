@@ -81,9 +81,20 @@ enum {
                                     Gaussian weight below exp(-28) = 6.9e-13 (the default only skips weights that
                                     are exactly 0.0f).  Every pixel changes by at most
                                     N * 6.9e-13 * max|sigmoid(opacity) * color|; ~3x fewer pairs are evaluated. */
-    XYZ_FLAG_RADIX_BINNING = 64  /* splat: build the tile lists with (tile, Gaussian) keys + a stable radix sort -- the
+    XYZ_FLAG_RADIX_BINNING = 64, /* splat: build the tile lists with (tile, Gaussian) keys + a stable radix sort -- the
                                     path images of more than 8192 tiles take anyway -- instead of the default stable
                                     counting sort by tile.  Same lists bit for bit; for tests and comparisons. */
+    XYZ_FLAG_ASYNC         = 128 /* splat, opt-in: no host synchronisation inside the launch (and so capturable in a
+                                    CUDA graph once the scratch has its size).  Takes effect from the second launch of a
+                                    scene shape (N, width, height, rows) on a host thread, with the counting-sort
+                                    binning and without XYZ_FLAG_DETERMINISTIC; otherwise the launch is an ordinary one.
+                                    The entry-sized buffers and the backward grid are sized for 1.5 x the most recent
+                                    list length the host has seen.  If a launch turns out longer, it renders EMPTY
+                                    lists (image 0, loss = sum |target|, no gradients; memory-safe) and the next
+                                    xyz_launch_gaussian_splatting* / xyz_splat_last_stats call on that thread returns
+                                    XYZ_ERR_WORKSPACE once, without launching anything, and the buffers are sized afresh
+                                    from the reported length: repeat the iteration.  Results of a launch that fits are
+                                    the same as without the flag. */
 };
 
 enum {

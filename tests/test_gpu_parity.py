@@ -652,6 +652,38 @@ def test_splat_counting_sort_binning_equals_the_radix_path():
                 assert np.abs(ga - gb).max() <= 1e-4 * np.abs(gb).max()   # atomics: order differs run to run
 
 
+def test_splat_async_launch_equals_the_synchronous_one_and_reports_overflow():
+    """XYZ_FLAG_ASYNC: no host synchronisation from the second launch of a scene shape on; buffers sized for 1.5 x the
+    last known list length.  A launch that fits gives the synchronous results; one that does not renders empty lists
+    (memory-safe), the next call reports XYZ_ERR_WORKSPACE once, and the launch after that is sized afresh."""
+    W, H, N = 256, 192, 5000
+    params, target = orc.splat_scene(N, W, H, seed=21)
+    A = x.FLAG_ASYNC
+    g0, o0, l0 = run_splat(params, target, W, H)               # ordinary launch: the host learns the list length
+    e0 = x.splat_last_stats()["entries"]
+    for _ in range(3):
+        g1, o1, l1 = run_splat(params, target, W, H, A)
+    assert np.array_equal(o1, o0) and l1 == l0
+    assert np.abs(g1 - g0).max() <= 1e-4 * np.abs(g0).max()    # atomics: order differs run to run
+    assert x.splat_last_stats()["entries"] == e0               # fetched from the device on demand
+    p2 = params.copy()
+    p2[:, 0:2] += 0.37                                         # what a training step does: lists change a little
+    g2, o2, l2 = run_splat(p2, target, W, H, A)
+    g2s, o2s, l2s = run_splat(p2, target, W, H)
+    assert np.array_equal(o2, o2s) and l2 == l2s
+    run_splat(p2, target, W, H, A)
+    p3 = params.copy()
+    p3[:, 2:4] += 1.2                                          # every Gaussian 3.3 x larger: far more than 1.5 x the entries
+    g3, o3, l3 = run_splat(p3, target, W, H, A)
+    assert (o3 == 0).all() and (g3 == 0).all() and abs(l3 - np.abs(target).sum()) <= 1e-5 * np.abs(target).sum()
+    with pytest.raises(RuntimeError):
+        run_splat(p3, target, W, H, A)                         # reports the overflow, launches nothing
+    g4, o4, l4 = run_splat(p3, target, W, H, A)                # sized from the reported length
+    g4s, o4s, l4s = run_splat(p3, target, W, H)
+    assert np.array_equal(o4, o4s) and l4 == l4s
+    assert np.abs(g4 - g4s).max() <= 1e-4 * np.abs(g4s).max()
+
+
 def test_splat_edge_cases():
     W, H = 50, 40
     target = orc.test_image(W, H)

@@ -30,6 +30,7 @@ FLAG_NO_CULL = 8
 FLAG_IMPLICIT_IDS = 16
 FLAG_TAIL_CULL = 32
 FLAG_RADIX_BINNING = 64
+FLAG_ASYNC = 128
 
 GAUSSIAN_FLOATS = 9   # center[2] scale[2] rotation[1] color[3] opacity[1]
 ADAM_FLOATS = 18

@@ -256,9 +256,13 @@ constexpr int kBinMaxTiles = 8192;  // 4 bytes of shared memory per tile (histog
 constexpr long long kBinLongList = 40LL << 20;  // predicted list length beyond which the chunks become one per SM
 
 // one CTA of 1024 threads: exclusive scans over the tiles of (list length) and of ceil(list length / kBwdChunk)
+// `capacity` (0 = unlimited) is the list length the entry-sized buffers were sized for (XYZ_FLAG_ASYNC): a longer list
+// publishes EMPTY tile ranges and an empty work list instead and bumps the sticky counter total_entries[1] (which never
+// falls below `overflow_base`, the count the host has seen), so that no later kernel of the launch reads or writes
+// beyond the buffers.
 __device__ __forceinline__ void bin_tilescan(const unsigned int* tile_total, int n_tiles, int2* __restrict__ tile_ranges,
                                              int* __restrict__ chunk_offsets, unsigned long long* __restrict__ total_entries,
-                                             int tid) {
+                                             unsigned long long capacity, unsigned long long overflow_base, int tid) {
     __shared__ unsigned long long s_warp[32];
     __shared__ int s_warp_c[32];
     __shared__ unsigned long long s_carry;
@@ -320,9 +324,19 @@ __device__ __forceinline__ void bin_tilescan(const unsigned int* tile_total, int
         }
         __syncthreads();
     }
+    const bool overflow = capacity != 0ull && s_carry > capacity;  // s_carry: settled by the loop's last barrier
+    if (overflow) {
+        for (int t = tid; t < n_tiles; t += 1024) {
+            tile_ranges[t] = make_int2(0, 0);
+            chunk_offsets[t] = 0;
+        }
+    }
     if (tid == 0) {
-        chunk_offsets[n_tiles] = s_carry_c;
-        *total_entries = s_carry;
+        chunk_offsets[n_tiles] = overflow ? 0 : s_carry_c;
+        total_entries[0] = s_carry;
+        // sticky counter, kept at or above the count the host has already seen (the scratch may have been reallocated)
+        const unsigned long long seen = total_entries[1] > overflow_base ? total_entries[1] : overflow_base;
+        total_entries[1] = overflow ? seen + 1ull : seen;
     }
 }
 
@@ -332,7 +346,8 @@ __device__ __forceinline__ void bin_tilescan(const unsigned int* tile_total, int
 __global__ void __launch_bounds__(1024)
     splat_bin_colscan_kernel(unsigned int* __restrict__ hist, int n_chunks, int n_tiles, unsigned int* tile_total,
                              unsigned int* ticket, int2* __restrict__ tile_ranges, int* __restrict__ chunk_offsets,
-                             unsigned long long* __restrict__ total_entries) {
+                             unsigned long long* __restrict__ total_entries, unsigned long long capacity,
+                             unsigned long long overflow_base) {
     __shared__ unsigned int s_part[32][33];
     __shared__ bool s_last;
     const int tx = threadIdx.x, gy = threadIdx.y;
@@ -365,7 +380,7 @@ __global__ void __launch_bounds__(1024)
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    bin_tilescan(tile_total, n_tiles, tile_ranges, chunk_offsets, total_entries, tid);
+    bin_tilescan(tile_total, n_tiles, tile_ranges, chunk_offsets, total_entries, capacity, overflow_base, tid);
 }
 
 // Scatter: one CTA per chunk, next free slot of every tile in shared memory (start = tile begin + the chunk's column
@@ -381,7 +396,8 @@ __global__ void __launch_bounds__(kBinThreads)
                              const unsigned long long* __restrict__ offsets_incl, int chunk_size, int n_tiles,
                              const unsigned int* __restrict__ hist, const int2* __restrict__ tile_ranges,
                              unsigned int* __restrict__ vals_out, int* __restrict__ sorted_gid, float d2max, int no_cull,
-                             const int* __restrict__ chunk_offsets, int4* __restrict__ chunk_info, int chunk_info_size) {
+                             const int* __restrict__ chunk_offsets, int4* __restrict__ chunk_info, int chunk_info_size,
+                             const unsigned long long* __restrict__ total_entries, unsigned long long capacity) {
     extern __shared__ unsigned int s_next[];  // next free slot per tile
     __shared__ unsigned char s_hit[kBinThreads / 32][32];  // per warp: rank among the group's hits -> lane
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -394,6 +410,7 @@ __global__ void __launch_bounds__(kBinThreads)
     }
     for (int c = chunk_offsets[n_tiles] + blockIdx.x * kBinThreads + tid; c < chunk_info_size; c += gridDim.x * kBinThreads)
         chunk_info[c] = make_int4(-1, -1, -1, -1);
+    if (capacity != 0ull && total_entries[0] > capacity) return;  // XYZ_FLAG_ASYNC overflow: every list is empty
     const unsigned int* mine = hist + static_cast<size_t>(blockIdx.x) * n_tiles;
     for (int t = tid; t < n_tiles; t += kBinThreads) s_next[t] = static_cast<unsigned int>(tile_ranges[t].x) + mine[t];
     __syncthreads();
@@ -620,10 +637,17 @@ struct LastLaunch {
     bool valid = false;
     SplatView view{};
     SplatBuffers buf{};
-    long long entries = 0;
+    long long entries = 0;       // list length; -1: not known on the host yet (XYZ_FLAG_ASYNC launch)
+    long long known_entries = 0;  // most recent length the host has seen for this scene shape
+    long long capacity = 0;      // XYZ_FLAG_ASYNC: the length the entry-sized buffers were sized for
+    const unsigned long long* total_dev = nullptr;  // device: {list length, overflow counter}
     long long stats[4] = {0, 0, 0, 0};
 };
 thread_local LastLaunch g_last;
+// XYZ_FLAG_ASYNC: pinned-host mirror of {list length, overflow counter}, refreshed by every launch without a
+// synchronisation; read at the next call (whatever has arrived by then is a valid earlier value).
+thread_local volatile unsigned long long* g_mirror = nullptr;
+thread_local unsigned long long g_overflows_seen = 0;
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
@@ -653,10 +677,32 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     // predicted from this thread's previous launch of the same scene shape, else from N.  Whatever is chosen, the
     // lists are the same bit for bit.
     const long long predicted = (g_last.valid && g_last.view.num_gaussians == N && g_last.view.width == W &&
-                                 g_last.view.height == H && g_last.view.row_begin == row_begin && g_last.view.row_end == row_end)
-                                    ? g_last.entries
+                                 g_last.view.height == H && g_last.view.row_begin == row_begin && g_last.view.row_end == row_end &&
+                                 g_last.known_entries > 0)
+                                    ? g_last.known_entries
                                     : static_cast<long long>(N) * 40;
     const bool counting = !(flags & XYZ_FLAG_RADIX_BINNING) && n_tiles <= kBinMaxTiles;
+    const bool same_shape = g_last.valid && g_last.view.num_gaussians == N && g_last.view.width == W &&
+                            g_last.view.height == H && g_last.view.row_begin == row_begin && g_last.view.row_end == row_end;
+    // XYZ_FLAG_ASYNC: what an earlier sync-free launch reported meanwhile (list length, overflows)
+    if (g_mirror) {
+        const unsigned long long seen_total = g_mirror[0], seen_overflows = g_mirror[1];
+        if (same_shape && g_last.entries < 0 && seen_total != 0ull) g_last.known_entries = static_cast<long long>(seen_total);
+        if (seen_overflows != g_overflows_seen) {
+            g_overflows_seen = seen_overflows;
+            g_last.capacity = 0;  // sized afresh from the reported length
+            return XYZ_ERR_WORKSPACE;  // an earlier XYZ_FLAG_ASYNC launch was longer than its buffers: its outputs are void
+        }
+    }
+    // sync-free launch: needs the counting sort (no host-side item counts) and a known length of this scene shape
+    const bool async = (flags & XYZ_FLAG_ASYNC) && counting && !deterministic && N > 0 && same_shape &&
+                       g_last.known_entries > 0;
+    long long capacity = 0;
+    if (async) {
+        capacity = g_last.known_entries + g_last.known_entries / 2 + 4096;
+        if (g_last.capacity >= g_last.known_entries + g_last.known_entries / 8) capacity = g_last.capacity;  // keep the buffers
+        if (capacity >= (1LL << 31) - 512) return XYZ_ERR_WORKSPACE;
+    }
     int chunk_size = kBinBatch, n_chunks = 1;
     if (counting) {
         static const int forced = [] {  // tuning knob: CTAs of the count / scatter kernels per SM
@@ -674,13 +720,16 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     // ---- fixed-size scratch (depends on N and the tile count only)
     size_t off = 0;
     auto take = [&off](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
+    // {list length, overflow counter, ticket} come FIRST: the overflow counter is sticky across launches, so its place
+    // must not move with the scene shape (a fresh arena is zero-filled, common.cu)
+    const size_t o_total = take(4 * sizeof(unsigned long long));
     const size_t o_rec = take(sizeof(float4) * 3 * ng), o_rect = take(sizeof(int4) * ng),
                  o_touched = take(sizeof(unsigned int) * ng), o_spans = take(sizeof(int2) * kSpanRows * ng), o_offsets = take(sizeof(unsigned long long) * ng),
                  o_ranges = take(sizeof(int2) * n_tiles), o_tloss = take(sizeof(float) * n_tiles),
                  o_chunks = take(sizeof(int) * (n_tiles + 1)),
                  o_rest = take(sizeof(float4) * kTilePixels * static_cast<size_t>(n_tiles)),
                  o_hist = take(counting ? sizeof(unsigned int) * static_cast<size_t>(n_chunks) * n_tiles : 0),
-                 o_ttotal = take(sizeof(unsigned int) * n_tiles), o_total = take(2 * sizeof(unsigned long long));
+                 o_ttotal = take(sizeof(unsigned int) * n_tiles);
     size_t scan_tmp_bytes = 0;
     cub::DeviceScan::InclusiveSum(nullptr, scan_tmp_bytes, TouchedIter(nullptr, ToU64()),
                                   static_cast<unsigned long long*>(nullptr), ng, st);
@@ -701,7 +750,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     unsigned int* hist = reinterpret_cast<unsigned int*>(base + o_hist);
     unsigned int* tile_total = reinterpret_cast<unsigned int*>(base + o_ttotal);
     unsigned long long* total_dev = reinterpret_cast<unsigned long long*>(base + o_total);
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(total_dev + 1);
+    unsigned int* ticket = reinterpret_cast<unsigned int*>(total_dev + 2);
 
     cudaError_t ce = cudaMemsetAsync(b.tile_ranges, 0, sizeof(int2) * n_tiles, st);
     if (ce != cudaSuccess) return static_cast<int>(ce);
@@ -724,10 +773,26 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
         const unsigned long long* total_src = b.offsets + (N - 1);
         if (counting) {
             splat_bin_colscan_kernel<<<(n_tiles + 31) / 32, dim3(32, 32), 0, st>>>(
-                hist, n_chunks, n_tiles, tile_total, ticket, b.tile_ranges, b.chunk_offsets, total_dev);
+                hist, n_chunks, n_tiles, tile_total, ticket, b.tile_ranges, b.chunk_offsets, total_dev,
+                static_cast<unsigned long long>(capacity), g_overflows_seen);
             count_launch();
             total_src = total_dev;
         }
+        if (async) {
+            // no read-back: the buffers are sized for `capacity`; the length goes to the pinned mirror for later calls
+            if (!g_mirror) {
+                void* m = nullptr;
+                ce = cudaHostAlloc(&m, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
+                if (ce != cudaSuccess) return static_cast<int>(ce);
+                g_mirror = static_cast<volatile unsigned long long*>(m);
+                g_mirror[0] = 0ull;
+                g_mirror[1] = g_overflows_seen;
+            }
+            ce = cudaMemcpyAsync(const_cast<unsigned long long*>(g_mirror), total_dev, 2 * sizeof(unsigned long long),
+                                 cudaMemcpyDeviceToHost, st);
+            if (ce != cudaSuccess) return static_cast<int>(ce);
+            entries = capacity;
+        } else {
         // the list length is data dependent: one 8-byte read-back (the only synchronisation)
         unsigned long long total = 0;
         ce = cudaMemcpyAsync(&total, total_src, sizeof(total), cudaMemcpyDeviceToHost, st);
@@ -735,6 +800,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
         ce = cudaStreamSynchronize(st);
         if (ce != cudaSuccess) return static_cast<int>(ce);
         entries = static_cast<long long>(total);
+        }
     }
     if (entries >= (1LL << 31) - 512) return XYZ_ERR_WORKSPACE;
 
@@ -772,11 +838,12 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
             if (deterministic)
                 splat_bin_scatter_kernel<true><<<n_chunks, kBinThreads, smem, st>>>(
                     v, b.records, b.rects, b.spans, b.touched, b.offsets, chunk_size, n_tiles, hist, b.tile_ranges,
-                    b.vals_out, b.sorted_gid, d2max, no_cull, b.chunk_offsets, b.chunk_info, chunk_info_size);
+                    b.vals_out, b.sorted_gid, d2max, no_cull, b.chunk_offsets, b.chunk_info, chunk_info_size, total_dev, 0ull);
             else
                 splat_bin_scatter_kernel<false><<<n_chunks, kBinThreads, smem, st>>>(
                     v, b.records, b.rects, b.spans, b.touched, nullptr, chunk_size, n_tiles, hist, b.tile_ranges,
-                    b.vals_out, nullptr, d2max, no_cull, b.chunk_offsets, b.chunk_info, chunk_info_size);
+                    b.vals_out, nullptr, d2max, no_cull, b.chunk_offsets, b.chunk_info, chunk_info_size, total_dev,
+                    static_cast<unsigned long long>(capacity));
             count_launch();
         } else {
             splat_emit_keys_kernel<<<(N + 15) / 16, 256, 0, st>>>(v, b.records, b.rects, b.touched, b.offsets, b.spans,
@@ -818,15 +885,43 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
         count_launch();
     }
 
+    const long long known_before = same_shape ? g_last.known_entries : 0;
     g_last.valid = true;
     g_last.view = v;
     g_last.buf = b;
-    g_last.entries = entries;
-    g_last.stats[0] = entries;
+    g_last.entries = async ? -1 : entries;
+    g_last.known_entries = async ? known_before : entries;
+    g_last.capacity = async ? capacity : 0;
+    g_last.total_dev = total_dev;
+    g_last.stats[0] = g_last.entries;
     g_last.stats[1] = n_tiles;
     g_last.stats[2] = -1;  // longest list: filled lazily by xyz_splat_last_stats
-    g_last.stats[3] = entries * kTilePixels;
+    g_last.stats[3] = g_last.entries * kTilePixels;
     return last_error();
+}
+
+// After a XYZ_FLAG_ASYNC launch the host does not know the list length: fetch it (synchronises the device).
+// Returns XYZ_ERR_WORKSPACE if that launch was longer than its buffers (its outputs are void).
+int resolve_async_length() {
+    if (!g_last.valid || g_last.entries >= 0) return 0;
+    unsigned long long both[2] = {0ull, 0ull};
+    cudaError_t e = cudaDeviceSynchronize();
+    if (e != cudaSuccess) return static_cast<int>(e);
+    e = cudaMemcpy(both, g_last.total_dev, sizeof(both), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    g_last.known_entries = static_cast<long long>(both[0]);
+    if (both[1] != g_overflows_seen) {
+        g_overflows_seen = both[1];
+        g_last.entries = 0;  // every list of that launch was published empty
+        g_last.capacity = 0;
+        g_last.stats[0] = 0;
+        g_last.stats[3] = 0;
+        return XYZ_ERR_WORKSPACE;
+    }
+    g_last.entries = static_cast<long long>(both[0]);
+    g_last.stats[0] = g_last.entries;
+    g_last.stats[3] = g_last.entries * kTilePixels;
+    return 0;
 }
 
 }  // namespace
@@ -851,6 +946,7 @@ extern "C" int xyz_launch_gaussian_splatting_rows(const xyz_gaussian_params* gau
 extern "C" int xyz_splat_last_stats(long long stats_host[4]) {
     using namespace xyzb;
     if (!g_last.valid || !stats_host) return XYZ_ERR_NOT_INITIALISED;
+    if (int err = resolve_async_length()) return err;
     if (g_last.stats[2] < 0) {
         const int n_tiles = g_last.view.tiles_x * g_last.view.tiles_y;
         std::vector<int2> r(n_tiles);
@@ -868,6 +964,7 @@ extern "C" int xyz_splat_debug_binning(int32_t* rects_host, int32_t* tile_ranges
                                        float* records_host) {
     using namespace xyzb;
     if (!g_last.valid) return XYZ_ERR_NOT_INITIALISED;
+    if (int err = resolve_async_length()) return err;
     cudaError_t e = cudaDeviceSynchronize();
     if (e != cudaSuccess) return static_cast<int>(e);
     const int n = g_last.view.num_gaussians, n_tiles = g_last.view.tiles_x * g_last.view.tiles_y;
