@@ -10,7 +10,7 @@
 //   2. integer work: per-tile lists of Gaussian ids, each ascending (= the reference's summation
 //      order), built by a stable counting sort by tile (splat_host.cu section 2b) or, for more than
 //      8192 tiles, (tile, Gaussian) keys + a stable radix sort; per-tile [begin, end) ranges;
-//   3. splat_forward_kernel  : one CTA per tile, one pixel per thread, records staged in shared
+//   3. splat_forward_kernel  : one CTA per tile, four pixels per thread, records staged in shared
 //      memory; writes the image and one loss partial per tile;
 //   4. splat_backward_kernel : one THREAD per (tile, Gaussian) list entry looping over the tile's
 //      256 pixels (pixel residuals broadcast from shared memory), 9 adjoint sums in registers,
@@ -53,8 +53,8 @@ struct SplatBuffers {  // device scratch of one launch (library-owned)
     unsigned int* vals_out;   // entries: sorted -> original entry index
     int* sorted_gid;          // entries: Gaussian id per sorted entry (fast mode: aliases vals_out)
     int2* tile_ranges;        // tiles: [begin, end)
-    int* chunk_offsets;       // tiles + 1: exclusive scan of ceil(list length / 256) = backward CTAs before a tile
-    int4* chunk_info;         // backward CTAs (upper bound entries/256 + tiles): {tile or -1, first entry, list end, 0}
+    int* chunk_offsets;       // tiles + 1: exclusive scan of ceil(list length / kBwdChunk) = backward CTAs before a tile
+    int4* chunk_info;         // backward CTAs (upper bound entries/kBwdChunk + tiles): {tile or -1, first entry, list end, 0}
     float4* rest_tiles;       // tiles x 256: (target - output, active) per pixel, tile-major, written by the forward pass
     float* tile_loss;         // tiles
     float* entry_grads;       // deterministic mode: entries x 9 (indexed by ORIGINAL entry index)
