@@ -925,4 +925,160 @@ long long orc_splat_binning(const float* rec, int N, int W, int H, int row_begin
     return total;
 }
 
+
+// Sequential emulation of THIS repo's counting-sort binning (xyz-autodiff-cuda_b200/csrc/splat_host.cu section 2b):
+// same chunking, per-chunk histograms, column scan, tile scan, and the scatter kernel's ownership rule -- warp w of a
+// chunk's CTA owns a band of tile rows, lane (rl, xl) of the warp owns the tiles (S0 + rl, x = xl mod XP), Gaussians in
+// groups of 32 candidates, hits in sub-groups of 8 -- with every index expression transcribed from the kernel.  Lanes
+// and warps run one after the other here; since a tile has exactly one owner lane, any interleaving gives the same
+// lists.  Purpose: the index arithmetic can be swept over image shapes / row bands / chunk counts on the CPU
+// (tests/test_oracle.py); the CUDA kernels themselves are held to orc_splat_binning on the GPU.
+// Outputs: tile_ranges (tiles x 2), sorted_ids (capacity), work list chunk_info (chunk_info_size x 4, surplus = -1).
+// Returns the list length, or -1 if an owner rule is violated (a slot written twice / out of its tile's range).
+long long orc_splat_binning_counting(const float* rec, int N, int W, int H, int row_begin, int row_end, float d2max,
+                                     int no_cull, int ctas_total, int bwd_chunk, int32_t* tile_ranges,
+                                     int32_t* sorted_ids, long long capacity, int32_t* chunk_info, int chunk_info_size) {
+    constexpr int kSpanRowsE = 16, kBatch = 32, kWarps = 8;
+    const int tiles_x = (W + kTile - 1) / kTile, tiles_y = (H + kTile - 1) / kTile, n_tiles = tiles_x * tiles_y;
+    const int ng = N > 0 ? N : 1;
+    const int chunk_size = ((ng + ctas_total - 1) / ctas_total + kBatch - 1) / kBatch * kBatch;
+    const int n_chunks = (ng + chunk_size - 1) / chunk_size;
+    // preprocess: rectangles, stored spans of the first 16 rows, tiles per Gaussian, per-chunk histogram
+    std::vector<int32_t> rects(static_cast<size_t>(ng) * 4, 0), spans(static_cast<size_t>(ng) * kSpanRowsE * 2, 0);
+    std::vector<unsigned int> touched(ng, 0), hist(static_cast<size_t>(n_chunks) * n_tiles, 0);
+    for (int g = 0; g < N; ++g) {
+        int32_t* r = &rects[4 * g];
+        tile_rect(rec + 12 * g, W, H, row_begin, row_end, d2max, no_cull, r);
+        const SpanCoef sc = span_coef(rec + 12 * g, d2max, no_cull);
+        unsigned int cnt = 0;
+        for (int ty = r[1]; ty < r[3]; ++ty) {
+            int s0, s1;
+            tile_row_span(sc, r, ty, W, row_begin, row_end, &s0, &s1);
+            cnt += static_cast<unsigned int>(std::max(s1 - s0, 0));
+            if (ty - r[1] < kSpanRowsE) {
+                spans[(static_cast<size_t>(g) * kSpanRowsE + (ty - r[1])) * 2] = s0;
+                spans[(static_cast<size_t>(g) * kSpanRowsE + (ty - r[1])) * 2 + 1] = std::max(s1, s0);
+            }
+            for (int tx = s0; tx < s1; ++tx) hist[static_cast<size_t>(g / chunk_size) * n_tiles + ty * tiles_x + tx]++;
+        }
+        touched[g] = cnt;
+    }
+    // column scan (exclusive prefix over the chunks, per tile) + tile scan
+    std::vector<unsigned int> tile_total(n_tiles, 0);
+    for (int t = 0; t < n_tiles; ++t) {
+        unsigned int run = 0;
+        for (int c = 0; c < n_chunks; ++c) {
+            const unsigned int x = hist[static_cast<size_t>(c) * n_tiles + t];
+            hist[static_cast<size_t>(c) * n_tiles + t] = run;
+            run += x;
+        }
+        tile_total[t] = run;
+    }
+    std::vector<long long> begin(n_tiles + 1, 0);
+    std::vector<int> chunk_offsets(n_tiles + 1, 0);
+    for (int t = 0; t < n_tiles; ++t) {
+        begin[t + 1] = begin[t] + tile_total[t];
+        chunk_offsets[t + 1] = chunk_offsets[t] + static_cast<int>((tile_total[t] + bwd_chunk - 1) / bwd_chunk);
+        if (tile_ranges) {
+            tile_ranges[2 * t] = static_cast<int32_t>(begin[t]);
+            tile_ranges[2 * t + 1] = static_cast<int32_t>(begin[t + 1]);
+        }
+    }
+    const long long total = begin[n_tiles];
+    if (!sorted_ids || total > capacity) return total;
+    std::vector<char> written(static_cast<size_t>(total > 0 ? total : 1), 0);
+    bool ok = true;
+    // scatter
+    for (int block = 0; block < n_chunks; ++block) {
+        const int g_begin = block * chunk_size, g_end = std::min(g_begin + chunk_size, N);
+        if (chunk_info) {  // the work list, distributed over the CTAs and threads like in the kernel
+            for (int tid = 0; tid < 256; ++tid) {
+                for (int t = block * 256 + tid; t < n_tiles; t += n_chunks * 256) {
+                    const int first = chunk_offsets[t], c = chunk_offsets[t + 1] - first;
+                    for (int k = 0; k < c; ++k) {
+                        int32_t* ci = chunk_info + 4 * static_cast<size_t>(first + k);
+                        ci[0] = t;
+                        ci[1] = static_cast<int32_t>(begin[t]) + k * bwd_chunk;
+                        ci[2] = static_cast<int32_t>(begin[t + 1]);
+                        ci[3] = 0;
+                    }
+                }
+                for (int c = chunk_offsets[n_tiles] + block * 256 + tid; c < chunk_info_size; c += n_chunks * 256) {
+                    int32_t* ci = chunk_info + 4 * static_cast<size_t>(c);
+                    ci[0] = ci[1] = ci[2] = ci[3] = -1;
+                }
+            }
+        }
+        std::vector<unsigned int> s_next(n_tiles);
+        for (int t = 0; t < n_tiles; ++t) s_next[t] = static_cast<unsigned int>(begin[t]) + hist[static_cast<size_t>(block) * n_tiles + t];
+        const int ty_lo = row_begin / kTile, ty_hi = (row_end + kTile - 1) / kTile;
+        const int band = (ty_hi - ty_lo + kWarps - 1) / kWarps;
+        for (int warp = 0; warp < kWarps; ++warp) {
+            const int R0 = ty_lo + warp * band, R1 = std::min(R0 + band, ty_hi);
+            if (R0 >= R1) continue;
+            const int rl_bits = band >= 8 ? 3 : (band >= 4 ? 2 : (band >= 2 ? 1 : 0));
+            const int RL = 1 << rl_bits, XP = 32 >> rl_bits;
+            for (int S0 = R0; S0 < R1; S0 += RL) {
+                const int S1 = std::min(S0 + RL, R1);
+                for (int gb = g_begin; gb < g_end; gb += 32) {
+                    int ry[32], rw[32];
+                    int hit_lane[32];
+                    int n_hits = 0;
+                    for (int lane = 0; lane < 32; ++lane) {
+                        const int g = gb + lane;
+                        ry[lane] = rw[lane] = 0;
+                        if (g < g_end && touched[g] != 0u) { ry[lane] = rects[4 * g + 1]; rw[lane] = rects[4 * g + 3]; }
+                        if (ry[lane] < S1 && rw[lane] > S0 && rw[lane] > ry[lane]) hit_lane[n_hits++] = lane;  // rank -> lane
+                    }
+                    for (int base = 0; base < n_hits; base += 8) {
+                        const int n_sub = std::min(8, n_hits - base);
+                        int st_x[32][2], st_y[32][2];  // what every lane staged
+                        for (int lane = 0; lane < 32; ++lane) {
+                            const int rl = lane >> (5 - rl_bits), ty = S0 + rl;
+                            for (int q = 0; q < 2; ++q) {
+                                st_x[lane][q] = st_y[lane][q] = 0;
+                                const int h = 4 * q + (lane & 3);
+                                if (h >= n_sub) continue;
+                                const int src = hit_lane[base + h];
+                                if (!(ty < S1 && ty >= ry[src] && ty < rw[src])) continue;
+                                const int gg = gb + src, j = ty - ry[src];
+                                int s0, s1;
+                                if (j < kSpanRowsE) {
+                                    s0 = spans[(static_cast<size_t>(gg) * kSpanRowsE + j) * 2];
+                                    s1 = spans[(static_cast<size_t>(gg) * kSpanRowsE + j) * 2 + 1];
+                                } else {
+                                    const SpanCoef sc = span_coef(rec + 12 * gg, d2max, no_cull);
+                                    tile_row_span(sc, &rects[4 * gg], ty, W, row_begin, row_end, &s0, &s1);
+                                }
+                                st_x[lane][q] = s0;
+                                st_y[lane][q] = s1;
+                            }
+                        }
+                        for (int i = 0; i < n_sub; ++i) {
+                            const int gg = gb + hit_lane[base + i];
+                            for (int lane = 0; lane < 32; ++lane) {
+                                const int rl = lane >> (5 - rl_bits), xl = lane & (XP - 1), ty = S0 + rl;
+                                const int from = (rl << (5 - rl_bits)) | (i & 3);
+                                const int sx = st_x[from][i >> 2], sy = st_y[from][i >> 2];
+                                for (int x = sx + ((xl - sx) & (XP - 1)); x < sy; x += XP) {
+                                    const int tile = ty * tiles_x + x;
+                                    const unsigned int pos = s_next[tile]++;
+                                    if (pos >= static_cast<unsigned int>(begin[tile + 1]) || pos < static_cast<unsigned int>(begin[tile]) || written[pos]) {
+                                        ok = false;
+                                    } else {
+                                        written[pos] = 1;
+                                        sorted_ids[pos] = gg;
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+        }
+    }
+    for (long long e = 0; e < total; ++e) ok = ok && written[e];
+    return ok ? total : -1;
+}
+
 }  // extern "C"

@@ -221,6 +221,31 @@ def splat_binning(records, W, H, row_begin=0, row_end=None, d2max=176.0, no_cull
     return rects[:N], ranges, ids[:total]
 
 
+def splat_binning_counting(records, W, H, row_begin=0, row_end=None, d2max=176.0, no_cull=False, ctas_total=592,
+                           bwd_chunk=128):
+    """Sequential emulation of the counting-sort binning kernels (index arithmetic transcribed from
+    csrc/splat_host.cu section 2b).  Returns (tile_ranges, sorted_ids, chunk_info) or raises if a tile slot was written
+    twice / outside its tile's range / not at all."""
+    row_end = H if row_end is None else row_end
+    rec = np.ascontiguousarray(records, np.float32)
+    N = rec.shape[0]
+    ntiles = ((W + 15) // 16) * ((H + 15) // 16)
+    ranges = np.zeros((ntiles, 2), np.int32)
+    L = load("port")
+    fn = L.orc_splat_binning_counting
+    fn.restype = _ll
+    total = fn(_p(rec), N, W, H, row_begin, row_end, ctypes.c_float(d2max), int(no_cull), int(ctas_total), int(bwd_chunk),
+               _p(ranges), None, _ll(0), None, 0)
+    ids = np.full(max(total, 1), -1, np.int32)
+    n_info = total // bwd_chunk + ntiles
+    info = np.full((max(n_info, 1), 4), -7, np.int32)
+    got = fn(_p(rec), N, W, H, row_begin, row_end, ctypes.c_float(d2max), int(no_cull), int(ctas_total), int(bwd_chunk),
+             _p(ranges), _p(ids), _ll(total), _p(info), int(n_info))
+    if got != total:
+        raise AssertionError("counting-sort emulation: a slot was written twice, out of range, or left empty")
+    return ranges, ids[:total], info[:n_info]
+
+
 def kat(which, name, *args, n=64, dtype=np.float64):
     res = np.zeros(n, dtype)
     k = _fn(which, "kat_" + name)(*args, _p(res))

@@ -176,3 +176,35 @@ def test_fp32_conditioning_bound_holds_for_the_reference_kernel(case):
     assert (np.abs(o32 - o) <= tol_i).all()
     assert (np.abs(g32 - g) <= tol_g).all()
     assert abs(l32 - l) <= 1e-4 * abs(l) + tol_i.sum()
+
+
+def test_counting_sort_binning_index_arithmetic_over_shapes():
+    """The counting-sort binning of the CUDA path (chunks, column prefixes, warp-owned bands of tile rows, lane-owned
+    tile classes, groups of 32 candidates, sub-groups of 8 hits) restated sequentially with the kernels' own index
+    expressions: equal to the plain stable binning for image shapes from one tile to more than 64 tile rows, row bands,
+    few and many chunks, Gaussians taller than the 16 stored tile rows, empty scenes."""
+    rng = np.random.default_rng(5)
+    shapes = [(16, 16), (40, 23), (50, 40), (200, 150), (130, 300), (64, 1100), (300, 700), (1024, 90), (333, 515)]
+    for W, H in shapes:
+        for N in (1, 33, 700):
+            params, _ = orc.splat_scene(N, W, H, seed=int(rng.integers(1 << 30)))
+            params[::9, 2:4] = 3.0                              # some cover the whole image (more than 16 tile rows)
+            params[::13, 0] = -4000.0                           # some are off screen
+            rec = orc.splat_records(params)
+            bands = [(0, H)]
+            if H >= 48:
+                bands.append((16 * (H // 48), min(H, 16 * (H // 48) + 16 * max(1, H // 40))))
+            if H >= 30:
+                bands.append((5, H - 3))                        # not tile-aligned
+            for rb, re_ in bands:
+                nc = N == 33 and (rb, re_) == (0, H)            # one no-cull case per shape: every tile, every Gaussian
+                rects, ranges, ids = orc.splat_binning(rec, W, H, rb, re_, no_cull=nc)
+                for ctas in (1, 5, 592):
+                    cr, ci, info = orc.splat_binning_counting(rec, W, H, rb, re_, no_cull=nc, ctas_total=ctas)
+                    assert np.array_equal(cr, ranges) and np.array_equal(ci, ids), (W, H, N, rb, re_, ctas)
+                    # the backward work list: every tile's list cut into chunks of 128, surplus records = -1
+                    want = [(t, b, e) for t, (b0, e) in enumerate(ranges) for b in range(b0, e, 128)]
+                    n_used = len(want)
+                    assert (info[n_used:] == -1).all()
+                    assert [tuple(r[:3]) for r in info[:n_used]] == want
+
