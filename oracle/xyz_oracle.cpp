@@ -360,6 +360,72 @@ T exponent_sensitivity(const PairFwd<T>& f) {
     return mag * (T(1) + det_cond);
 }
 
+// The backward of ONE (pixel, Gaussian) pair: l1_loss.run() of gaussian_splatting_kernel.cu:84-110 with `pix` as the
+// finished pixel_out.  gg (9) += ; absgrads / kinkgrads / condgrads (9 each, optional) as described at splat_pixel.
+template <class T>
+inline void pair_backward(const T* gp, T* gg, const T* tgt, const T* pix, T px, T py, T* margin, T* absgrads, T* kinkgrads,
+                          T* condgrads) {
+    PairFwd<T> f;
+    T before[9];
+    if (absgrads) for (int k = 0; k < 9; ++k) before[k] = gg[k];
+    pair_forward(gp, px, py, f);                            // l1_loss.run() -> forward
+    T sgn[3];
+    bool near_kink = false;
+    for (int i = 0; i < 3; ++i) {
+        T rest = tgt[i] - pix[i];                           // rest_sum = target - pixel_out            :101
+        rest += T(0);                                       // += un-forwarded weighted_color (Q2)      :102
+        const T cd = f.wc[i] - rest;                        // color_diff = weighted_color - rest_sum   :106
+        sgn[i] = cd > T(0) ? T(1) : (cd < T(0) ? T(-1) : T(0));  // l1 backward, seed 1.0
+        if (margin && f.w > T(1e-10) && std::abs(cd) < *margin) *margin = std::abs(cd);
+        // sign(cd) is numerically ambiguous in fp32 when |cd| is within rounding distance of 0
+        // (rest = tgt - out carries the ABSOLUTE rounding error of the fp32 image, ~1e-6 * |out|)
+        if (std::abs(cd) <= T(2e-5) * std::max(std::abs(f.wc[i]), std::max(std::abs(tgt[i]), std::abs(pix[i]))))
+            near_kink = true;
+    }
+    // mul backward (binary/mul_logic.cuh:33-41): color.grad += g*bc ; bc(=weighted_gauss).grad += g*color
+    T g_w = T(0);
+    for (int i = 0; i < 3; ++i) {
+        gg[5 + i] += sgn[i] * f.w;
+        g_w += sgn[i] * gp[5 + i];
+    }
+    // weighted_gauss = gaussian_value * sig_opacity
+    const T g_e = g_w * f.so;
+    const T g_so = g_w * f.e;
+    // gaussian_value chain first (input1), then sigmoid (input2): operation.cuh:235-249
+    const T g_ns = g_e * m_exp(-(f.d2 * T(0.5)));           // exp backward recomputes exp(input)
+    const T g_sd = -g_ns;                                   // neg backward
+    const T g_d2 = g_sd * T(0.5);                           // mul_constant backward
+    // mahalanobis_distance.cuh:100-119
+    const T a = f.inv[0], b = f.inv[1], c = f.inv[2];
+    const T grad_dx = g_d2 * (T(2) * a * f.dx + T(2) * b * f.dy);
+    const T grad_dy = g_d2 * (T(2) * b * f.dx + T(2) * c * f.dy);
+    gg[0] += -grad_dx;
+    gg[1] += -grad_dy;
+    const T g_inv[3] = {g_d2 * f.dx * f.dx, g_d2 * T(2) * f.dx * f.dy, g_d2 * f.dy * f.dy};
+    T g_cov[3] = {T(0), T(0), T(0)};
+    sym_inv_bwd(f.cov, g_inv, g_cov);
+    T g_es[2] = {T(0), T(0)};
+    scale_rot_cov_bwd(f.es, gp[4], g_cov, g_es, &gg[4]);    // rotation leaf: direct accumulate
+    gg[2] += g_es[0] * m_exp(gp[2]);                        // exp backward (recomputed)
+    gg[3] += g_es[1] * m_exp(gp[3]);
+    const T s = m_sigmoid(gp[8]);                           // sigmoid backward (recomputed)
+    gg[8] += g_so * (s * (T(1) - s));
+    if (absgrads)  // sum of |per-pair term|: the scale the 1e-4 tolerance on accumulated sums is stated against
+        for (int k = 0; k < 9; ++k) {
+            const T term = std::abs(gg[k] - before[k]);
+            absgrads[k] += term;
+            // upper bound of what a flipped sign can change: |g_w| <= sum |color_i| instead of |sum s_i color_i|
+            if (kinkgrads && near_kink) kinkgrads[k] += term + std::abs(f.w) + T(1e-30);
+            // every term is proportional to exp(-d2 / 2); an fp32 evaluation of d2 / 2 = sum of three products of
+            // rounded factors carries an ABSOLUTE error of a few ulp of their magnitudes, i.e. the term a RELATIVE
+            // error of (a few 2^-24) x mag.  condgrads = sum |term| x mag is that sensitivity.
+            if (condgrads) {
+                const T mag = exponent_sensitivity(f);
+                condgrads[k] += term * mag;
+            }
+        }
+}
+
 // One pixel of the reference kernel.  grads += ; *loss += ; out[3] written.  `margin` (optional)
 // tracks min |color_diff_i| over all pairs whose weight is not negligible (> 1e-10): the distance of the
 // closest L1 kink (tests use it to make sure a sign cannot flip within fp32 noise).
@@ -380,68 +446,10 @@ void splat_pixel(const T* params, T* grads, const T* tgt, T* out, T* loss, int p
     }
     for (int i = 0; i < 3; ++i) out[i] = pix[i];                // :63
     for (int i = 0; i < 3; ++i) *loss += std::abs(pix[i] - tgt[i]);  // :68-70
-    for (int g = 0; g < N; ++g) {                               // :73-111
-        const T* gp = params + 9 * g;
-        T* gg = grads + 9 * g;
-        T before[9];
-        if (absgrads) for (int k = 0; k < 9; ++k) before[k] = gg[k];
-        pair_forward(gp, px, py, f);                            // l1_loss.run() -> forward
-        T sgn[3];
-        bool near_kink = false;
-        for (int i = 0; i < 3; ++i) {
-            T rest = tgt[i] - pix[i];                           // rest_sum = target - pixel_out            :101
-            rest += T(0);                                       // += un-forwarded weighted_color (Q2)      :102
-            const T cd = f.wc[i] - rest;                        // color_diff = weighted_color - rest_sum   :106
-            sgn[i] = cd > T(0) ? T(1) : (cd < T(0) ? T(-1) : T(0));  // l1 backward, seed 1.0
-            if (margin && f.w > T(1e-10) && std::abs(cd) < *margin) *margin = std::abs(cd);
-            // sign(cd) is numerically ambiguous in fp32 when |cd| is within rounding distance of 0
-            // (rest = tgt - out carries the ABSOLUTE rounding error of the fp32 image, ~1e-6 * |out|)
-            if (std::abs(cd) <= T(2e-5) * std::max(std::abs(f.wc[i]), std::max(std::abs(tgt[i]), std::abs(pix[i]))))
-                near_kink = true;
-        }
-        // mul backward (binary/mul_logic.cuh:33-41): color.grad += g*bc ; bc(=weighted_gauss).grad += g*color
-        T g_w = T(0);
-        for (int i = 0; i < 3; ++i) {
-            gg[5 + i] += sgn[i] * f.w;
-            g_w += sgn[i] * gp[5 + i];
-        }
-        // weighted_gauss = gaussian_value * sig_opacity
-        const T g_e = g_w * f.so;
-        const T g_so = g_w * f.e;
-        // gaussian_value chain first (input1), then sigmoid (input2): operation.cuh:235-249
-        const T g_ns = g_e * m_exp(-(f.d2 * T(0.5)));           // exp backward recomputes exp(input)
-        const T g_sd = -g_ns;                                   // neg backward
-        const T g_d2 = g_sd * T(0.5);                           // mul_constant backward
-        // mahalanobis_distance.cuh:100-119
-        const T a = f.inv[0], b = f.inv[1], c = f.inv[2];
-        const T grad_dx = g_d2 * (T(2) * a * f.dx + T(2) * b * f.dy);
-        const T grad_dy = g_d2 * (T(2) * b * f.dx + T(2) * c * f.dy);
-        gg[0] += -grad_dx;
-        gg[1] += -grad_dy;
-        const T g_inv[3] = {g_d2 * f.dx * f.dx, g_d2 * T(2) * f.dx * f.dy, g_d2 * f.dy * f.dy};
-        T g_cov[3] = {T(0), T(0), T(0)};
-        sym_inv_bwd(f.cov, g_inv, g_cov);
-        T g_es[2] = {T(0), T(0)};
-        scale_rot_cov_bwd(f.es, gp[4], g_cov, g_es, &gg[4]);    // rotation leaf: direct accumulate
-        gg[2] += g_es[0] * m_exp(gp[2]);                        // exp backward (recomputed)
-        gg[3] += g_es[1] * m_exp(gp[3]);
-        const T s = m_sigmoid(gp[8]);                           // sigmoid backward (recomputed)
-        gg[8] += g_so * (s * (T(1) - s));
-        if (absgrads)  // sum of |per-pair term|: the scale the 1e-4 tolerance on accumulated sums is stated against
-            for (int k = 0; k < 9; ++k) {
-                const T term = std::abs(gg[k] - before[k]);
-                absgrads[9 * g + k] += term;
-                // upper bound of what a flipped sign can change: |g_w| <= sum |color_i| instead of |sum s_i color_i|
-                if (kinkgrads && near_kink) kinkgrads[9 * g + k] += term + std::abs(f.w) + T(1e-30);
-                // every term is proportional to exp(-d2 / 2); an fp32 evaluation of d2 / 2 = sum of three products of
-                // rounded factors carries an ABSOLUTE error of a few ulp of their magnitudes, i.e. the term a RELATIVE
-                // error of (a few 2^-24) x mag.  condgrads = sum |term| x mag is that sensitivity.
-                if (condgrads) {
-                    const T mag = exponent_sensitivity(f);
-                    condgrads[9 * g + k] += term * mag;
-                }
-            }
-    }
+    for (int g = 0; g < N; ++g)                                 // :73-111
+        pair_backward(params + 9 * g, grads + 9 * g, tgt, pix, px, py, margin, absgrads ? absgrads + 9 * g : nullptr,
+                      (absgrads && kinkgrads) ? kinkgrads + 9 * g : nullptr,
+                      (absgrads && condgrads) ? condgrads + 9 * g : nullptr);
 }
 
 // Pixel order = the reference launch's block order run sequentially (16x16 tiles, row-major
@@ -489,6 +497,96 @@ int splat_all_pairs(const T* params, T* grads, const T* target, T* output, T* lo
         m = std::min(m, priv_m[t]);
     }
     if (margin_out) *margin_out = m;
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// SAMPLED all-pairs checks for scenes too large to run splat_all_pairs on (100 K Gaussians x 1024^2 is 2 x 10^11 pairs;
+// the reference kernel needs ~50 s of a B200 for it).  Same statements as splat_pixel, restricted to
+//   (a) a set of PIXELS, every Gaussian: the forward loop gaussian_splatting_kernel.cu:33-62 (ascending Gaussian index);
+//   (b) a set of GAUSSIANS, every pixel: the backward loop :73-111 with a GIVEN image as pixel_out (the image under test,
+//       which (a) checks separately) -- the gradient of one Gaussian is a sum over pixels of pair terms that depend on the
+//       other Gaussians only through pixel_out.
+// The per-Gaussian part of pair_forward does not depend on the pixel; (a) evaluates it once per Gaussian through the
+// same functions, so every value is bit-identical to pair_forward's (this file is compiled with -ffp-contract=off).
+// ---------------------------------------------------------------------------------------------
+template <class T>
+struct GaussFwd {
+    T cx, cy, cov[3], inv[3], so, col[3];
+};
+
+template <class T>
+int splat_pixels_sample(const T* params, int N, const int* xy, int n, T* out, T* condimg, int threads) {
+    std::vector<GaussFwd<T>> pre(static_cast<size_t>(N));
+    parallel_ranges(N, threads, [&](int, long long lo, long long hi) {
+        for (long long g = lo; g < hi; ++g) {
+            const T* gp = params + 9 * g;
+            GaussFwd<T>& q = pre[g];
+            T es[2] = {m_exp(gp[2]), m_exp(gp[3])};               // kernel.cu:44
+            scale_rot_cov_fwd(es, gp[4], q.cov);                  // :45
+            sym_inv_fwd(q.cov, q.inv);                            // :46
+            q.cx = gp[0];
+            q.cy = gp[1];
+            q.so = m_sigmoid(gp[8]);                              // :54
+            for (int i = 0; i < 3; ++i) q.col[i] = gp[5 + i];
+        }
+    });
+    constexpr int kBlock = 2048;  // Gaussians per pass over a thread's pixels (keeps them in cache)
+    parallel_ranges(n, threads, [&](int, long long lo, long long hi) {
+        for (long long p = lo; p < hi; ++p)
+            for (int i = 0; i < 3; ++i) {
+                out[3 * p + i] = T(0);
+                if (condimg) condimg[3 * p + i] = T(0);
+            }
+        for (int g0 = 0; g0 < N; g0 += kBlock) {
+            const int g1 = std::min(N, g0 + kBlock);
+            for (long long p = lo; p < hi; ++p) {
+                const T px = static_cast<T>(xy[2 * p]), py = static_cast<T>(xy[2 * p + 1]);
+                T* o = out + 3 * p;
+                for (int g = g0; g < g1; ++g) {                   // ascending g per pixel, like :33-62
+                    const GaussFwd<T>& q = pre[g];
+                    PairFwd<T> f;
+                    f.dx = px - q.cx;                             // :47
+                    f.dy = py - q.cy;
+                    f.d2 = q.inv[0] * f.dx * f.dx + T(2) * q.inv[1] * f.dx * f.dy + q.inv[2] * f.dy * f.dy;
+                    const T sd = f.d2 * T(0.5);                   // :51
+                    const T ns = -sd;                             // :52
+                    f.e = m_exp(ns);                              // :53
+                    f.w = f.e * q.so;                             // :55
+                    for (int i = 0; i < 3; ++i) {
+                        f.wc[i] = q.col[i] * f.w;                 // :56-57
+                        o[i] += f.wc[i];                          // :61
+                    }
+                    if (condimg) {
+                        for (int i = 0; i < 3; ++i) {
+                            f.inv[i] = q.inv[i];
+                            f.cov[i] = q.cov[i];
+                        }
+                        const T mag = exponent_sensitivity(f);
+                        for (int i = 0; i < 3; ++i) condimg[3 * p + i] += std::abs(f.wc[i]) * mag;
+                    }
+                }
+            }
+        }
+    });
+    return 0;
+}
+
+template <class T>
+int splat_grads_sample(const T* params, const int* ids, int m, const T* target, const T* image, int W, int H, T* grads,
+                       T* absgrads, T* kinkgrads, int threads) {
+    parallel_ranges(m, threads, [&](int, long long lo, long long hi) {
+        for (long long s = lo; s < hi; ++s) {
+            const T* gp = params + 9 * static_cast<size_t>(ids[s]);
+            for (int y = 0; y < H; ++y)
+                for (int x = 0; x < W; ++x) {
+                    const size_t p = static_cast<size_t>(y) * W + x;
+                    pair_backward<T>(gp, grads + 9 * s, target + 3 * p, image + 3 * p, static_cast<T>(x), static_cast<T>(y),
+                                     nullptr, absgrads ? absgrads + 9 * s : nullptr,
+                                     (absgrads && kinkgrads) ? kinkgrads + 9 * s : nullptr, nullptr);
+                }
+        }
+    });
     return 0;
 }
 
@@ -715,6 +813,17 @@ int orc_splat_f64_cond(const double* params, double* grads, const double* target
                        double* condimage) {
     return splat_all_pairs<double>(params, grads, target, output, loss, W, H, N, threads, margin, absgrads, kinkgrads,
                                    condgrads, condimage);
+}
+
+// Sampled checks for full-size scenes (see splat_pixels_sample / splat_grads_sample above).
+// xy: n x 2 int32 pixel coordinates; out / condimage: n x 3.
+int orc_splat_pixels_f64(const double* params, int N, const int* xy, int n, double* out, double* condimage, int threads) {
+    return splat_pixels_sample<double>(params, N, xy, n, out, condimage, threads);
+}
+// ids: m Gaussian indices; target / image: full P x 3; grads / absgrads / kinkgrads: m x 9 (+=).
+int orc_splat_grads_sample_f64(const double* params, const int* ids, int m, const double* target, const double* image,
+                               int W, int H, double* grads, double* absgrads, double* kinkgrads, int threads) {
+    return splat_grads_sample<double>(params, ids, m, target, image, W, H, grads, absgrads, kinkgrads, threads);
 }
 
 // Least squares: examples/optimization/tests/test_linear_regression_gradient.cu:52-78 (squared loss),

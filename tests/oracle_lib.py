@@ -130,6 +130,32 @@ def splat_tolerance_fp32(params, target, W, H, rtol=1e-4):
     return g, o, float(l[0]), tol_g, tol_i
 
 
+def splat_pixels(params, xy, cond=False, threads=None):
+    """fp64, EVERY Gaussian summed into the n sampled pixels xy (n x 2: x, y) in ascending index (the forward loop of the
+    reference kernel).  Returns out (n x 3) [, condimage (n x 3)]: the sampled rows of splat()'s output."""
+    threads = threads or os.cpu_count() or 1
+    p = np.ascontiguousarray(params, np.float64)
+    q = np.ascontiguousarray(xy, np.int32)
+    n = q.shape[0]
+    out = np.zeros((n, 3)); ci = np.zeros((n, 3)) if cond else None
+    load("port").orc_splat_pixels_f64(_p(p), p.shape[0], _p(q), n, _p(out), _p(ci), threads)
+    return (out, ci) if cond else out
+
+
+def splat_grads_sample(params, ids, target, image, W, H, rtol=1e-4, threads=None):
+    """fp64 gradients of the m sampled Gaussians `ids` over EVERY pixel, with `image` (P x 3, the image under test) as the
+    finished pixel_out of the backward loop.  Returns (grads (m x 9), tol (m x 9)) with splat_tolerance's bound."""
+    threads = threads or os.cpu_count() or 1
+    p = np.ascontiguousarray(params, np.float64)
+    t = np.ascontiguousarray(target, np.float64)
+    im = np.ascontiguousarray(image, np.float64)
+    ii = np.ascontiguousarray(ids, np.int32)
+    m = ii.shape[0]
+    g = np.zeros((m, 9)); absg = np.zeros((m, 9)); kink = np.zeros((m, 9))
+    load("port").orc_splat_grads_sample_f64(_p(p), _p(ii), m, _p(t), _p(im), W, H, _p(g), _p(absg), _p(kink), threads)
+    return g, rtol * absg + 2.0 * kink + 1e-5 * absg.max(axis=1, keepdims=True) + 1e-30
+
+
 def splat_hard_scene(case: int):
     """Seeded ILL-CONDITIONED scenes: odd image sizes, Gaussians from sub-pixel to image-sized (log-scale in [-1, 2.3]),
     arbitrary rotations, some centres far outside the image.  Returns (params, target, W, H)."""

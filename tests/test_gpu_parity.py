@@ -749,9 +749,80 @@ def test_splat_full_size_properties():
     assert np.isfinite(d0[0]).all() and np.isfinite(d0[1]).all()
     b = run_splat(params, target, W, H, x.FLAG_DETERMINISTIC, rows=(512, 528))
     assert np.array_equal(b[1][512 * W:528 * W], d0[1][512 * W:528 * W])
-    # one tile's worth of pixels against the fp64 oracle restricted to the Gaussians that can reach it
     st = x.splat_last_stats()
     assert st["entries"] > 0
+
+
+def check_splat_sampled(params, target, W, H, got, n_pixels=512, n_gauss=64, seed=0):
+    """Full-size scenes against the fp64 oracle on a SAMPLE (the all-pairs oracle would need 1e11 .. 3e12 pair
+    evaluations): `n_pixels` random pixels plus one whole 16 x 16 tile summed over EVERY Gaussian (the reference's
+    forward loop, gaussian_splatting_kernel.cu:33-62), and `n_gauss` random Gaussians (plus the first and the last)
+    back-propagated over EVERY pixel (:73-111) with the image under test as pixel_out.
+    Image: a pixel is a sequential fp32 sum of 10^3 .. 3 x 10^4 positive terms, i.e. an accumulated sum -> 1e-4 relative
+    to the sum of |terms| (+ the fp32 conditioning of the exponent); the median error must stay below the per-element bar
+    1e-5.  Loss: 1e-4 against the fp64 sum over the image under test.  Gradients: splat_tolerance's bound."""
+    g, o, l = got
+    N = params.shape[0]
+    rr = np.random.default_rng(seed)
+    tx, ty = int(rr.integers(0, (W + 15) // 16)), int(rr.integers(0, (H + 15) // 16))
+    tile = np.stack(np.meshgrid(np.arange(tx * 16, min(W, tx * 16 + 16)), np.arange(ty * 16, min(H, ty * 16 + 16))), -1).reshape(-1, 2)
+    corners = np.array([[0, 0], [W - 1, 0], [0, H - 1], [W - 1, H - 1]])
+    xy = np.concatenate([np.stack([rr.integers(0, W, n_pixels), rr.integers(0, H, n_pixels)], -1), tile, corners]).astype(np.int32)
+    want, cond = orc.splat_pixels(params, xy, cond=True)
+    have = o.reshape(H, W, 3)[xy[:, 1], xy[:, 0]].astype(np.float64)
+    err = np.abs(have - want)
+    tol_i = 1e-4 * np.abs(want) + orc.FP32_EXPONENT_ULPS * 2.0 ** -24 * cond + 1e-30
+    assert (err <= tol_i).all(), f"image: worst {np.max(err / tol_i):.3f} of the bound"
+    assert np.median(err / (np.abs(want) + 1e-30)) <= 1e-5, "image: median relative error above the per-element bar"
+    l64 = np.abs(o.astype(np.float64) - target.astype(np.float64)).sum()
+    assert abs(l - l64) <= 1e-4 * l64, "loss"
+    ids = np.unique(np.concatenate([rr.choice(N, min(n_gauss, N), replace=False), [0, N - 1]])).astype(np.int32)
+    gs, tol = orc.splat_grads_sample(params, ids, target, o, W, H)
+    assert (np.abs(g[ids] - gs) <= tol).all(), f"gradients: worst {np.max(np.abs(g[ids] - gs) / tol):.3f} of the bound"
+    return float(np.max(err / (np.abs(want) + 1e-30))), float(np.max(np.abs(g[ids] - gs) / tol))
+
+
+@pytest.mark.parametrize("flags", [0, 2], ids=["fast", "precise"])
+def test_splat_c4_full_size_against_the_sampled_fp64_oracle(flags):
+    """BASELINE configs[3] at FULL size: 100 000 Gaussians (initialize_random, seed 42), 1024 x 1024 test image."""
+    W, H, N = 1024, 1024, 100_000
+    params, target = orc.splat_c4_scene(N, W, H, seed=42)
+    got = run_splat(params, target, W, H, flags)
+    check_splat_sampled(params, target, W, H, got, seed=flags)
+
+
+def test_splat_c5_size_one_view_against_the_sampled_fp64_oracle():
+    """BASELINE configs[4]'s per-GPU work: 3 000 000 Gaussians, one 1024 x 1024 view (1.2e8 list entries: the
+    one-chunk-per-SM binning policy for lists beyond kBinLongList, 32-bit entry offsets close to their range)."""
+    W, H, N = 1024, 1024, 3_000_000
+    params, target = orc.splat_c4_scene(N, W, H, seed=42)
+    target = np.roll(target.reshape(H, W, 3), shift=(37, 64), axis=(0, 1)).reshape(W * H, 3).copy()  # bench.py's view 1
+    got = run_splat(params, target, W, H, 0)
+    st = x.splat_last_stats()
+    assert st["entries"] > (40 << 20)
+    check_splat_sampled(params, target, W, H, got, n_pixels=256, n_gauss=32, seed=5)
+    x.shutdown()  # give the 1 GB of entry-sized scratch back
+
+
+def test_covproj_full_size_against_the_oracle_on_sampled_rows():
+    """BASELINE configs[2] at FULL size (2^26 elements, 12.9 GB): 100 000 random rows plus the first and the last tiles
+    against the fp64 oracle (byte offsets beyond 2^31 in every array)."""
+    n = 1 << 26
+    gen = torch.Generator(device=DEV).manual_seed(11)
+    ins = [torch.empty((n, k), device=DEV).uniform_(-1, 1, generator=gen) for k in (6, 9, 6, 3)]
+    outs = [torch.full((n, k), float("nan"), device=DEV) for k in (3, 6, 9, 6)]
+    x.covproj_fwd_bwd(*ins, *outs)
+    rr = np.random.default_rng(3)
+    rows = np.unique(np.concatenate([rr.integers(0, n, 100_000), np.arange(0, 300), np.arange(n - 300, n),
+                                     np.arange((1 << 31) // 36 - 150, (1 << 31) // 36 + 150)]))
+    ridx = torch.from_numpy(rows).to(DEV)
+    J, W, S, g = [t[ridx].cpu().numpy() for t in ins]
+    want = orc.covproj(J, W, S, g, np.float64)
+    for a, b, name in zip(outs, want, ("out", "gJ", "gW", "gS")):
+        a = a[ridx].cpu().numpy()
+        assert rel_err(a, b, np.abs(b).max(axis=1, keepdims=True)).max() < 1e-5, name
+    for a in outs:  # every row was written
+        assert not torch.isnan(a).any()
 
 
 # ---------------------------------------------------------------------------------------------------

@@ -208,3 +208,21 @@ def test_counting_sort_binning_index_arithmetic_over_shapes():
                     assert (info[n_used:] == -1).all()
                     assert [tuple(r[:3]) for r in info[:n_used]] == want
 
+
+
+def test_sampled_oracle_equals_the_all_pairs_oracle():
+    """orc_splat_pixels_f64 / orc_splat_grads_sample_f64 (the checkers for scenes too large for the all-pairs oracle)
+    against the all-pairs fp64 oracle on a scene it can run: sampled image rows are bit-identical (same operations in
+    the same order); sampled gradients agree to fp64 reassociation (pixel order instead of tile order)."""
+    W, H, N = 70, 45, 300
+    params, target = orc.splat_scene(N, W, H, seed=11)
+    g, o, l, tol = orc.splat_tolerance(params, target, W, H)
+    rr = np.random.default_rng(5)
+    xy = np.stack([rr.integers(0, W, 200), rr.integers(0, H, 200)], -1).astype(np.int32)
+    out, cond = orc.splat_pixels(params, xy, cond=True)
+    assert np.array_equal(out, o.reshape(H, W, 3)[xy[:, 1], xy[:, 0]])
+    assert (cond >= 0).all() and np.isfinite(cond).all()
+    ids = rr.choice(N, 40, replace=False).astype(np.int32)
+    gs, tols = orc.splat_grads_sample(params, ids, target, o, W, H)
+    assert np.abs(gs - g[ids]).max() <= 1e-12 * max(1.0, np.abs(g).max())
+    assert np.allclose(tols, tol[ids], rtol=1e-9, atol=1e-30)
