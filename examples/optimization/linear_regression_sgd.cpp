@@ -12,8 +12,9 @@
 // Differences from the shipped reference main (all switchable back):
 //   * the gradient kernel runs the WHOLE batch (the reference launches <<<1,1>>> on one sample, "debug", :204-205)
 //     and differentiates the squared residual (the graph of the reference's own gradient test,
-//     examples/optimization/tests/test_linear_regression_gradient.cu:52-71).  --reference-loss switches to the
-//     shipped loss.run() on the residual (XYZ_FLAG_RESIDUAL_ONLY); --batch 1 reproduces the one-sample update;
+//     examples/optimization/tests/test_linear_regression_gradient.cu:52-71).  --reference-loss switches to the graph
+//     and root the shipped kernel really builds (:103-122: un-squared x1 term, loss.run() on the residual;
+//     XYZ_FLAG_LSQ_SHIPPED_GRAPH); --batch 1 reproduces the one-sample update;
 //   * data comes from std::mt19937(--seed) instead of std::random_device, so runs are reproducible.
 //
 //   linear_regression_sgd [--samples N] [--batch B] [--epochs E] [--lr0 x] [--lr1 x] [--seed s]
@@ -146,7 +147,7 @@ int main(int argc, char** argv) {
     CHECK_CUDA_ERROR(cudaMemcpyAsync(d_params.get(), &host, sizeof(host), cudaMemcpyHostToDevice, stream));
     if (!opt.quiet) report(0, opt.lr0, host);
 
-    const int flags = opt.reference_loss ? XYZ_FLAG_RESIDUAL_ONLY : 0;
+    const int flags = opt.reference_loss ? XYZ_FLAG_LSQ_SHIPPED_GRAPH : 0;
     const double decay = std::log(opt.lr1 / opt.lr0) / opt.epochs;
     double* d_grad = d_params.get()->grad;  // device address of the 4 gradients
     const auto t0 = std::chrono::steady_clock::now();

@@ -72,8 +72,9 @@ enum {
     XYZ_FLAG_PRECISE_MATH  = 2, /* splat: IEEE expf/sinf/cosf/div (the reference's test builds);
                                    default is the training app's fast-math/FTZ flavour
                                    (examples/mini-gaussian-splatting/CMakeLists.txt:22-31) */
-    XYZ_FLAG_RESIDUAL_ONLY = 4, /* lsq: differentiate the residual, not its square -- what the
-                                   shipped example runs (linear_regression_sgd.cu:119-122) */
+    XYZ_FLAG_RESIDUAL_ONLY = 4, /* lsq: the SAME graph (test_linear_regression_gradient.cu:52-71) differentiated at
+                                   the residual y_pred - y instead of at its square (root y_diff.run()).  NOT the shipped
+                                   example's graph: see XYZ_FLAG_LSQ_SHIPPED_GRAPH */
     XYZ_FLAG_NO_CULL       = 8, /* splat: evaluate every (pixel, Gaussian) pair like the reference
                                    kernel does; default skips pairs whose weight is exactly 0 */
     XYZ_FLAG_IMPLICIT_IDS  = 16, /* accumulate: idx == NULL means id = i mod K */
@@ -84,7 +85,12 @@ enum {
     XYZ_FLAG_RADIX_BINNING = 64, /* splat: build the tile lists with (tile, Gaussian) keys + a stable radix sort -- the
                                     path images of more than 8192 tiles take anyway -- instead of the default stable
                                     counting sort by tile.  Same lists bit for bit; for tests and comparisons. */
-    XYZ_FLAG_ASYNC         = 128 /* splat, opt-in: no host synchronisation inside the launch (and so capturable in a
+    XYZ_FLAG_LSQ_SHIPPED_GRAPH = 256, /* lsq: the graph parallel_gradient_computation_kernel really builds
+                                   (linear_regression_sgd.cu:103-122): combined_terms adds the UN-squared
+                                   x1_term = a - x1 (x1_term2 is dead code there) and loss.run() differentiates the
+                                   residual:  r = (a - x1) + b (c - x2)^2 + d - y,  dr/d(a, b, c, d) = (1, (c - x2)^2,
+                                   2 b (c - x2), 1).  Reproduces the shipped example's SGD trajectory. */
+    XYZ_FLAG_ASYNC         = 128, /* splat, opt-in: no host synchronisation inside the launch (and so capturable in a
                                     CUDA graph once the scratch has its size).  Takes effect from the second launch of a
                                     scene shape (N, width, height, rows) on a host thread, with the counting-sort
                                     binning and without XYZ_FLAG_DETERMINISTIC; otherwise the launch is an ordinary one.
@@ -115,9 +121,10 @@ XYZ_API void xyz_b200_reset_launch_count(void);
 /* ---- C1: batched least-squares forward+reverse (fp64) --------------------------------------
  * Replaces compute_gradient_kernel<Analytical>
  * (examples/optimization/tests/test_linear_regression_gradient.cu:33-79) and, with
- * XYZ_FLAG_RESIDUAL_ONLY, parallel_gradient_computation_kernel
+ * XYZ_FLAG_LSQ_SHIPPED_GRAPH, parallel_gradient_computation_kernel
  * (examples/optimization/linear_regression_sgd.cu:86-123).  For every data point builds
- * r = (a-x1)^2 + b(c-x2)^2 + d - y, loss = r^2, and ADDS d(loss)/d(a,b,c,d) into params->grad.
+ * r = (a-x1)^2 + b(c-x2)^2 + d - y, loss = r^2, and ADDS d(loss)/d(a,b,c,d) into params->grad
+ * (XYZ_FLAG_RESIDUAL_ONLY: d(r) instead; XYZ_FLAG_LSQ_SHIPPED_GRAPH: the shipped example's r, see the flag).
  * loss_sum (optional, may be NULL) receives += sum of per-point root values.            */
 XYZ_API int xyz_lsq_grad_f64(const xyz_data_point* data, long long n_points, xyz_lsq_parameters* params,
                      double* loss_sum, void* stream, int flags);
@@ -133,7 +140,7 @@ XYZ_API int xyz_lsq_select_batch(const xyz_data_point* data, long long n_total, 
  * the gradients, parallel_gradient_computation_kernel, update_parameters_kernel) in ONE launch: sample i of the
  * batch is data[hash(seed, epoch, i) mod n_total] (the sampling of xyz_lsq_select_batch), params->grad is
  * OVERWRITTEN with the batch gradient, then value -= learning_rate * grad / batch_size.  loss_sum (optional)
- * receives += the batch loss.  Deterministic.  Flags: XYZ_FLAG_RESIDUAL_ONLY.                        */
+ * receives += the batch loss.  Deterministic.  Flags: XYZ_FLAG_RESIDUAL_ONLY, XYZ_FLAG_LSQ_SHIPPED_GRAPH.                        */
 XYZ_API int xyz_lsq_sgd_step_f64(const xyz_data_point* data, long long n_total, xyz_lsq_parameters* params,
                          long long batch_size, uint64_t seed, uint64_t epoch, double learning_rate,
                          double* loss_sum, void* stream, int flags);

@@ -65,6 +65,7 @@ thread_local dim3 gridDim{1, 1, 1};
 #include <xyz_autodiff/operations/unary/l2_norm_logic.cuh>
 #include <xyz_autodiff/operations/unary/sum_logic.cuh>
 #include <xyz_autodiff/operations/unary/broadcast.cuh>
+#include <xyz_autodiff/operations/unary/broadcast_logic.cuh>
 #include <xyz_autodiff/operations/unary/sym_matrix2_inv_logic.cuh>
 #include <xyz_autodiff/operations/unary/to_rotation_matrix_logic.cuh>
 #include <xyz_autodiff/variable_operators.cuh>
@@ -201,7 +202,21 @@ int ref_lsq_grad_f64(const double* data, long long n, double* params /* value[4]
             auto y_pred = op::add(combined_terms, d_var);
             auto y_diff = op::sub_constant(y_pred, yt);
             auto loss = op::squared(y_diff);
-            if (residual_only) {
+            if (residual_only == 2) {
+                // the graph the SHIPPED example builds (linear_regression_sgd.cu:103-122), statement for statement:
+                // combined_terms takes the un-squared x1_term; x1_term2 and loss_2 are built and never run
+                auto s_x1_term = op::sub_constant(a_var, x1);
+                auto s_x1_term2 = op::squared(s_x1_term);
+                auto s_x2_c = op::sub_constant(c_var, x2);
+                auto s_x2_squared = op::squared(s_x2_c);
+                auto s_x2_term = op::mul(b_var, s_x2_squared);
+                auto s_combined = op::add(s_x1_term, s_x2_term);
+                auto s_y_pred = op::add(s_combined, d_var);
+                auto s_loss = op::sub_constant(s_y_pred, yt);
+                auto s_loss_2 = op::squared(s_loss);
+                s_loss.run();
+                g[4] += s_loss[0];
+            } else if (residual_only) {
                 y_diff.run();
                 g[4] += y_diff[0];
             } else {
@@ -255,6 +270,9 @@ int ref_eval_op_f32(int op, int aux, const float* in1, int n1, const float* in2,
 int ref_kat_dag(double* res) { double scratch[8]; return api_eval::kat_dag(res, scratch); }
 int ref_kat_shared_subgraph(double* res) { return api_eval::kat_shared_subgraph(res); }
 int ref_kat_broadcast(double* res) { return api_eval::kat_broadcast(res); }
+int ref_kat_broadcast_logic(double x0, const double* up4, double s0, const double* v3, double* res) {
+    return api_eval::kat_broadcast_logic(x0, up4, s0, v3, res);
+}
 int ref_kat_chain(double x, double y, double z, double up, double* res) { return api_eval::kat_chain(x, y, z, up, res); }
 int ref_kat_operators(const double* a, const double* b, const double* c, const double* d, double* res) {
     return api_eval::kat_operators(a, b, c, d, res);

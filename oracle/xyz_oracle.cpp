@@ -826,8 +826,9 @@ int orc_splat_grads_sample_f64(const double* params, const int* ids, int m, cons
     return splat_grads_sample<double>(params, ids, m, target, image, W, H, grads, absgrads, kinkgrads, threads);
 }
 
-// Least squares: examples/optimization/tests/test_linear_regression_gradient.cu:52-78 (squared loss),
-// or with residual_only the root actually run by linear_regression_sgd.cu:119-122.
+// Least squares: examples/optimization/tests/test_linear_regression_gradient.cu:52-78 (squared loss); residual_only = 1:
+// the same graph differentiated at the residual; residual_only = 2: the graph AND root the shipped example runs
+// (linear_regression_sgd.cu:103-122).
 // params = {value[4], grad[4]}; grad += ; *loss_sum += root values.
 int orc_lsq_grad_f64(const double* data, long long n, double* params, double* loss_sum, int residual_only, int threads) {
     threads = std::max(1, threads);
@@ -842,6 +843,17 @@ int orc_lsq_grad_f64(const double* data, long long n, double* params, double* lo
             const double v = c - x2;            // sub_constant(c, x2)
             const double v2 = v * v;            // squared
             const double bv2 = b * v2;          // mul(b, v2)
+            if (residual_only == 2) {
+                // the graph the SHIPPED example builds (linear_regression_sgd.cu:103-122): combined_terms = x1_term +
+                // x2_term with the UN-squared x1_term = a - x1 (x1_term2 is dead), root = the residual (loss.run())
+                const double r2 = ((u + bv2) + d) - yt;
+                g[4] += r2;
+                g[0] += 1.0;                    // sub_constant backward: a += seed
+                g[1] += 1.0 * v2;
+                g[2] += 1.0 * b * 2.0 * v;
+                g[3] += 1.0;
+                continue;
+            }
             const double comb = u2 + bv2;       // add
             const double ypred = comb + d;      // add(combined, d)
             const double r = ypred - yt;        // sub_constant(y_pred, y)

@@ -39,6 +39,9 @@ int mine_eval_op_f32(int op, int aux, const float* in1, int n1, const float* in2
 int mine_kat_dag(double* res) { double scratch[8]; return api_eval::kat_dag(res, scratch); }
 int mine_kat_shared_subgraph(double* res) { return api_eval::kat_shared_subgraph(res); }
 int mine_kat_broadcast(double* res) { return api_eval::kat_broadcast(res); }
+int mine_kat_broadcast_logic(double x0, const double* up4, double s0, const double* v3, double* res) {
+    return api_eval::kat_broadcast_logic(x0, up4, s0, v3, res);
+}
 int mine_kat_chain(double x, double y, double z, double up, double* res) { return api_eval::kat_chain(x, y, z, up, res); }
 int mine_kat_operators(const double* a, const double* b, const double* c, const double* d, double* res) {
     return api_eval::kat_operators(a, b, c, d, res);

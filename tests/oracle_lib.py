@@ -170,7 +170,8 @@ def splat_hard_scene(case: int):
 
 
 def lsq_grad(data, values, residual_only=False, which="port", threads=1):
-    """Returns (grad[4], loss_sum)."""
+    """Returns (grad[4], loss_sum).  residual_only: False / True (root = residual of the test graph) / 2 (the graph the
+    shipped example builds, linear_regression_sgd.cu:103-122)."""
     d = np.ascontiguousarray(data, np.float64)
     prm = np.concatenate([np.asarray(values, np.float64), np.zeros(4)])
     ls = np.zeros(1)

@@ -187,6 +187,30 @@ def test_host_graphs_match_reference_graphs(host):
     assert ka == kb == 20 and np.allclose(fa[:ka], fb[:kb], rtol=1e-6)
 
 
+def _broadcast_logic_expected(x0, up, s0, v):
+    return [x0] * 4 + [sum(up), 5.0, 5.0] + [s0 * t for t in v] + [sum(v)] + [s0] * 3
+
+
+def test_materialising_broadcast_value_and_gradient(host):
+    """SURVEY 8 row a15b: xyz_autodiff::broadcast<N> (BroadcastLogic, reference operations/unary/broadcast_logic.cuh:11-46)
+    -- values, summed adjoint, run(), run_numerical() and use inside a graph -- against the closed form and, where the
+    reference is built, against the reference's own header evaluating the same source text."""
+    vp, dbl = ctypes.c_void_p, ctypes.c_double
+    host.mine_kat_broadcast_logic.argtypes = [dbl, vp, dbl, vp, vp]
+    up, v = np.array([1.0, -2.5, 0.25, 4.0]), np.array([1.0, 3.0, 5.0])
+    res = np.zeros(64)
+    k = host.mine_kat_broadcast_logic(3.5, P(up), 2.0, P(v), P(res))
+    want = _broadcast_logic_expected(3.5, list(up), 2.0, list(v))
+    assert k == len(want) == 14
+    assert np.allclose(res[:k], want, rtol=0, atol=1e-9) and list(res[:6]) == want[:6]  # only run_numerical is inexact
+    if orc.have_ref():
+        R = orc.load("ref")
+        R.ref_kat_broadcast_logic.argtypes = [dbl, vp, dbl, vp, vp]
+        ref = np.zeros(64)
+        assert R.ref_kat_broadcast_logic(3.5, P(up), 2.0, P(v), P(ref)) == k
+        assert np.array_equal(ref[:k], res[:k])
+
+
 # ---- device side ----------------------------------------------------------------------------------------
 def test_ternary_covariance_projection_node(host):
     """op::covariance_projection (one ternary node, not in the reference) against the oracle's composition of the
@@ -248,6 +272,11 @@ def test_device_known_answers(cuda, host):
     host.mine_kat_math_f64.argtypes = [ctypes.c_double, ctypes.c_void_p]
     host.mine_kat_math_f64(0.73, P(want))
     assert k == 20 and np.allclose(res[:k], want[:k], rtol=1e-13)
+    # a15b on the device: the materialising broadcast
+    inp[:9] = [3.5, 1.0, -2.5, 0.25, 4.0, 2.0, 1.0, 3.0, 5.0]
+    k = cuda.cuda_kat(10, P(inp), P(res), None)
+    want14 = _broadcast_logic_expected(3.5, [1.0, -2.5, 0.25, 4.0], 2.0, [1.0, 3.0, 5.0])
+    assert k == 14 and np.allclose(res[:k], want14, rtol=0, atol=1e-9) and list(res[:6]) == want14[:6]
 
 
 @pytest.mark.gpu

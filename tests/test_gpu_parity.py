@@ -223,10 +223,10 @@ def test_lsq_reference_batch_of_32():
 
 
 @pytest.mark.parametrize("n", [1, 255, 256, 257, 1000, 1_000_000])
-@pytest.mark.parametrize("residual_only", [False, True])
+@pytest.mark.parametrize("residual_only", [False, True, 2])
 def test_lsq_matches_oracle(n, residual_only):
     data = orc.lsq_data(n, seed=42)
-    flags = x.FLAG_RESIDUAL_ONLY if residual_only else 0
+    flags = {False: 0, True: x.FLAG_RESIDUAL_ONLY, 2: x.FLAG_LSQ_SHIPPED_GRAPH}[residual_only]
     got, loss = run_lsq(data, (0.0, 1.0, 0.0, 0.0), flags)
     want, wloss = orc.lsq_grad(data, (0.0, 1.0, 0.0, 0.0), residual_only, threads=8)
     # sums of up to 1e6 terms in a different (tree) order: 1e-10 relative to the sum of |terms| ~ |want|
@@ -914,6 +914,24 @@ def test_against_the_reference_cuda_kernels_on_the_same_gpu():
     assert R.refcuda_accumulate(ti.data_ptr(), tv.data_ptr(), idx.size, grad.data_ptr()) == 0
     torch.cuda.synchronize()
     assert (np.abs(got - grad.cpu().numpy()) <= 2e-4 * orc.accumulate_exact(idx, np.abs(val), 1024) + 1e-30).all()
+    # the SHIPPED example's own kernel (parallel_gradient_computation_kernel, linear_regression_sgd.cu:86-123, compiled
+    # unmodified) against XYZ_FLAG_LSQ_SHIPPED_GRAPH, and one update_parameters_kernel step against xyz_lsq_sgd_update_f64
+    if hasattr(R, "refcuda_lsq_shipped"):
+        R.refcuda_lsq_shipped.argtypes = [vp, ll, vp]
+        R.refcuda_lsq_update.argtypes = [vp, ctypes.c_double, ctypes.c_int]
+        data = orc.lsq_data(8192, seed=6)
+        td = dev(data)
+        ours = torch.zeros(8, dtype=torch.float64, device=DEV)
+        ours[:4] = dev(np.array([0.2, 1.1, -0.3, 0.05]))
+        theirs = ours.clone()
+        x.lsq_grad(td, ours, flags=x.FLAG_LSQ_SHIPPED_GRAPH)
+        assert R.refcuda_lsq_shipped(td.data_ptr(), 8192, theirs.data_ptr()) == 0
+        torch.cuda.synchronize()
+        assert rel_err(ours.cpu().numpy()[4:], theirs.cpu().numpy()[4:]).max() < 1e-10
+        x.lsq_sgd_update(ours, 1e-4, 8192)
+        assert R.refcuda_lsq_update(theirs.data_ptr(), 1e-4, 8192) == 0
+        torch.cuda.synchronize()
+        assert rel_err(ours.cpu().numpy()[:4], theirs.cpu().numpy()[:4]).max() < 1e-12
 
 
 REF_CUDA_OURHDR = os.path.join(os.path.dirname(REF_CUDA), "libxyz_ref_cuda_ourhdr.so")

@@ -101,7 +101,7 @@ def test_port_equals_reference_live_bit_for_bit():
     b = orc.splat(params, target, 70, 50, np.float32, which="port", threads=1)
     assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1]) and a[2] == b[2]
     data = orc.lsq_data(5000, seed=8)
-    for ro in (False, True):
+    for ro in (False, True, 2):  # 2 = the shipped example's graph, built from the reference's own op:: factories in _ref
         assert np.array_equal(orc.lsq_grad(data, (0.1, 0.9, -0.2, 0.3), ro, "ref")[0],
                               orc.lsq_grad(data, (0.1, 0.9, -0.2, 0.3), ro, "port")[0])
     J, W, S, g = orc.covproj_inputs(3000, seed=1)
@@ -226,3 +226,15 @@ def test_sampled_oracle_equals_the_all_pairs_oracle():
     gs, tols = orc.splat_grads_sample(params, ids, target, o, W, H)
     assert np.abs(gs - g[ids]).max() <= 1e-12 * max(1.0, np.abs(g).max())
     assert np.allclose(tols, tol[ids], rtol=1e-9, atol=1e-30)
+
+
+def test_lsq_shipped_example_graph_closed_form():
+    """XYZ_FLAG_LSQ_SHIPPED_GRAPH's oracle: r = (a - x1) + b (c - x2)^2 + d - y, dr/d(a, b, c, d) = (1, (c - x2)^2,
+    2 b (c - x2), 1) -- the graph parallel_gradient_computation_kernel builds (linear_regression_sgd.cu:103-122)."""
+    data = orc.lsq_data(1000, seed=4)
+    a, b, c, d = 0.1, 0.9, -0.2, 0.3
+    g, l = orc.lsq_grad(data, (a, b, c, d), 2)
+    v = c - data[:, 1]
+    want = np.array([len(data), (v * v).sum(), (2 * b * v).sum(), len(data)])
+    assert np.allclose(g, want, rtol=1e-12)
+    assert np.isclose(l, ((a - data[:, 0]) + b * v * v + d - data[:, 2]).sum(), rtol=1e-12)

@@ -31,6 +31,7 @@ FLAG_IMPLICIT_IDS = 16
 FLAG_TAIL_CULL = 32
 FLAG_RADIX_BINNING = 64
 FLAG_ASYNC = 128
+FLAG_LSQ_SHIPPED_GRAPH = 256
 
 GAUSSIAN_FLOATS = 9   # center[2] scale[2] rotation[1] color[3] opacity[1]
 ADAM_FLOATS = 18

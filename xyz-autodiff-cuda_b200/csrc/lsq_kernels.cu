@@ -37,18 +37,28 @@ struct LsqAcc {
     double v[kAcc];
 };
 
+inline int lsq_mode(int flags) {
+    return (flags & XYZ_FLAG_LSQ_SHIPPED_GRAPH) ? 2 : ((flags & XYZ_FLAG_RESIDUAL_ONLY) ? 1 : 0);
+}
+
+// mode 0: the graph of the reference's gradient test (test_linear_regression_gradient.cu:52-71), root = squared residual
+// mode 1: the same graph differentiated at the residual (XYZ_FLAG_RESIDUAL_ONLY)
+// mode 2: the graph the SHIPPED example builds (linear_regression_sgd.cu:103-122, XYZ_FLAG_LSQ_SHIPPED_GRAPH):
+//         combined_terms = x1_term + x2_term takes the UN-squared x1_term = a - x1 (x1_term2 is dead) and the root is
+//         the residual: r = (a - x1) + b (c - x2)^2 + d - y, dr/da = 1
 __device__ __forceinline__ void lsq_point(double x1, double x2, double yt, double a, double b, double c, double d,
-                                          bool residual_only, LsqAcc& acc) {
+                                          int mode, LsqAcc& acc) {
     const double u = a - x1;          // sub_constant(a, x1)
     const double v = c - x2;          // sub_constant(c, x2)
     const double v2 = v * v;          // squared
-    const double r = ((u * u + b * v2) + d) - yt;
-    const double seed = residual_only ? 1.0 : 2.0 * r;  // squared backward: g * 2.0 * x with g = 1
-    acc.v[0] += seed * 2.0 * u;
+    const double first = mode == 2 ? u : u * u;
+    const double r = ((first + b * v2) + d) - yt;
+    const double seed = mode ? 1.0 : 2.0 * r;  // squared backward: g * 2.0 * x with g = 1
+    acc.v[0] += mode == 2 ? seed : seed * 2.0 * u;
     acc.v[1] += seed * v2;
     acc.v[2] += seed * b * 2.0 * v;
     acc.v[3] += seed;
-    acc.v[4] += residual_only ? r : r * r;
+    acc.v[4] += mode ? r : r * r;
 }
 
 __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
@@ -62,7 +72,7 @@ __device__ __forceinline__ uint64_t splitmix64(uint64_t x) {
 template <bool kTma>
 __global__ void __launch_bounds__(kThreads, kCtasPerSM)
     lsq_grad_kernel(const double* __restrict__ data, long long n_points, xyz_lsq_parameters* params, double* loss_sum,
-                    double* partials, unsigned int* ticket, int residual_only, PeerArgs peer) {
+                    double* partials, unsigned int* ticket, int mode, PeerArgs peer) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     LsqSmem& sm = *reinterpret_cast<LsqSmem*>(smem_raw);
     const int tid = threadIdx.x;
@@ -103,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM)
                     bulk_load(sm.pts[s], data + nt * kTileP * 3, kTileP * 24, &sm.full[s]);
                 }
             }
-            lsq_point(x1, x2, yt, a, b, c, d, residual_only != 0, acc);
+            lsq_point(x1, x2, yt, a, b, c, d, mode, acc);
         }
     }
     // tail (and the whole range when the base pointer is not 16-byte aligned): plain loads
@@ -112,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, kCtasPerSM)
         for (long long i = begin + blockIdx.x * static_cast<long long>(kThreads) + tid; i < n_points;
              i += static_cast<long long>(gridDim.x) * kThreads) {
             lsq_point(__ldg(data + 3 * i), __ldg(data + 3 * i + 1), __ldg(data + 3 * i + 2), a, b, c, d,
-                      residual_only != 0, acc);
+                      mode, acc);
         }
     }
 
@@ -197,7 +207,7 @@ __global__ void lsq_select_batch_kernel(const xyz_data_point* __restrict__ data,
 __global__ void __launch_bounds__(kThreads)
     lsq_sgd_step_kernel(const xyz_data_point* __restrict__ data, long long n_total, xyz_lsq_parameters* params,
                         long long batch_size, uint64_t seed, uint64_t epoch, double lr, double* loss_sum,
-                        double* partials, unsigned int* ticket, int residual_only) {
+                        double* partials, unsigned int* ticket, int mode) {
     __shared__ double red[kThreads / 32][kAcc];
     __shared__ int is_last;
     const int tid = threadIdx.x;
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(kThreads)
          i += static_cast<long long>(gridDim.x) * kThreads) {
         const uint64_t h = splitmix64(base + static_cast<uint64_t>(i));
         const double* p = reinterpret_cast<const double*>(data + h % static_cast<uint64_t>(n_total));
-        lsq_point(__ldg(p), __ldg(p + 1), __ldg(p + 2), a, b, c, d, residual_only != 0, acc);
+        lsq_point(__ldg(p), __ldg(p + 1), __ldg(p + 2), a, b, c, d, mode, acc);
     }
 #pragma unroll
     for (int k = 0; k < kAcc; ++k) acc.v[k] = warp_sum(acc.v[k]);
@@ -274,7 +284,7 @@ __global__ void __launch_bounds__(kThreads)
 __global__ void __launch_bounds__(kThreads)
     lsq_sgd_run_kernel(const xyz_data_point* __restrict__ data, long long n_total, xyz_lsq_parameters* params,
                        long long batch_size, uint64_t seed, uint64_t epoch0, int n_epochs, const double* __restrict__ lrs,
-                       double* loss_sum, double* partials, int residual_only) {
+                       double* loss_sum, double* partials, int mode) {
     namespace cg = cooperative_groups;
     cg::grid_group grid = cg::this_grid();
     __shared__ double red[kThreads / 32][kAcc];
@@ -296,7 +306,7 @@ __global__ void __launch_bounds__(kThreads)
              i += static_cast<long long>(gridDim.x) * kThreads) {
             const uint64_t h = splitmix64(base + static_cast<uint64_t>(i));
             const double* p = reinterpret_cast<const double*>(data + h % static_cast<uint64_t>(n_total));
-            lsq_point(__ldg(p), __ldg(p + 1), __ldg(p + 2), a, b, c, d, residual_only != 0, acc);
+            lsq_point(__ldg(p), __ldg(p + 1), __ldg(p + 2), a, b, c, d, mode, acc);
         }
 #pragma unroll
         for (int k = 0; k < kAcc; ++k) acc.v[k] = warp_sum(acc.v[k]);
@@ -375,16 +385,16 @@ int lsq_grad_launch(const xyz_data_point* data, long long n_points, xyz_lsq_para
     // scratch arenas are zero-filled when allocated and every kernel leaves its ticket at zero
     unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
     double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256);
-    const int residual_only = (flags & XYZ_FLAG_RESIDUAL_ONLY) ? 1 : 0;
+    const int mode = lsq_mode(flags);
     const double* d = reinterpret_cast<const double*>(data);
     if (aligned16(data) && n_points >= kTileP) {
         cudaFuncSetAttribute(lsq_grad_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                              static_cast<int>(sizeof(LsqSmem)));
         lsq_grad_kernel<true><<<grid, kThreads, sizeof(LsqSmem), st>>>(d, n_points, params, loss_sum, partials, ticket,
-                                                                       residual_only, peer);
+                                                                       mode, peer);
     } else {
         lsq_grad_kernel<false><<<grid, kThreads, sizeof(LsqSmem), st>>>(d, n_points, params, loss_sum, partials, ticket,
-                                                                        residual_only, peer);
+                                                                        mode, peer);
     }
     count_launch();
     return last_error();
@@ -453,7 +463,7 @@ extern "C" int xyz_lsq_sgd_step_f64(const xyz_data_point* data, long long n_tota
     unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
     double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256);
     lsq_sgd_step_kernel<<<grid, kThreads, 0, st>>>(data, n_total, params, batch_size, seed, epoch, learning_rate, loss_sum,
-                                                    partials, ticket, (flags & XYZ_FLAG_RESIDUAL_ONLY) ? 1 : 0);
+                                                    partials, ticket, lsq_mode(flags));
     count_launch();
     return last_error();
 }
@@ -476,7 +486,7 @@ extern "C" int xyz_lsq_sgd_run_f64(const xyz_data_point* data, long long n_total
     if (ce == cudaSuccess) ce = cudaGetDevice(&dev);
     if (ce == cudaSuccess) ce = cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, dev);
     if (ce != cudaSuccess) return static_cast<int>(ce);
-    const int residual_only = (flags & XYZ_FLAG_RESIDUAL_ONLY) ? 1 : 0;
+    const int mode = lsq_mode(flags);
     if (!coop || static_cast<long long>(per_sm) * sm_count() < grid) {  // cannot be co-resident: one launch per epoch
         for (int e = 0; e < n_epochs; ++e) {
             const int err = xyz_lsq_sgd_step_f64(data, n_total, params, batch_size, seed, epoch_begin + static_cast<uint64_t>(e),
@@ -499,7 +509,7 @@ extern "C" int xyz_lsq_sgd_run_f64(const xyz_data_point* data, long long n_total
         uint64_t epoch0 = epoch_begin + static_cast<uint64_t>(done);
         const double* lrs_arg = lrs_dev;
         void* args[] = {&data, &n_total, &params, &batch_size, &seed, &epoch0, &n, &lrs_arg, &loss_sum, &partials,
-                        const_cast<int*>(&residual_only)};
+                        const_cast<int*>(&mode)};
         ce = cudaLaunchCooperativeKernel(reinterpret_cast<void*>(lsq_sgd_run_kernel), dim3(grid), dim3(kThreads), args, 0, st);
         if (ce != cudaSuccess) return static_cast<int>(ce);
         count_launch();
