@@ -90,6 +90,8 @@ enum {
                                    x1_term = a - x1 (x1_term2 is dead code there) and loss.run() differentiates the
                                    residual:  r = (a - x1) + b (c - x2)^2 + d - y,  dr/d(a, b, c, d) = (1, (c - x2)^2,
                                    2 b (c - x2), 1).  Reproduces the shipped example's SGD trajectory. */
+    XYZ_FLAG_TIMING        = 512, /* splat: record CUDA events between the stages of this launch; read them with
+                                    xyz_splat_last_timing.  A measuring aid (the events cost a little themselves). */
     XYZ_FLAG_ASYNC         = 128, /* splat, opt-in: no host synchronisation inside the launch (and so capturable in a
                                     CUDA graph once the scratch has its size).  Takes effect from the second launch of a
                                     scene shape (N, width, height, rows) on a host thread, with the counting-sort
@@ -106,7 +108,8 @@ enum {
 enum {
     XYZ_ERR_INVALID_ARGUMENT = -1,
     XYZ_ERR_WORKSPACE        = -2,
-    XYZ_ERR_NOT_INITIALISED  = -3
+    XYZ_ERR_NOT_INITIALISED  = -3,
+    XYZ_ERR_COMM             = -4  /* NCCL is missing (dlopen of libnccl.so.2 failed) or returned an error */
 };
 
 /* ---- library ----------------------------------------------------------------------------- */
@@ -237,13 +240,22 @@ XYZ_API int xyz_covproj_shared_w_fwd_bwd_f32_allreduce(const float* J, const flo
  * Replaces launch_gaussian_splatting (gaussian_splatting_kernel.cuh:38-47 /
  * gaussian_splatting_kernel.cu:114-149): renders `output` (overwritten), ADDS the L1 loss into
  * *total_loss and ADDS d(loss)/d(params) into `gradients`.  target/output are P x 3 floats
- * (PixelOutput = ConstArray<float,3>).  Synchronises `stream` once internally (the tile-list
- * length is data dependent); scratch is library-owned and grows on demand (4 bytes per
- * (tile, Gaussian) list entry, 36 more with XYZ_FLAG_DETERMINISTIC).
- * The per-tile lists come from a stable counting sort by tile (images of up to 8192 tiles) or a
- * stable radix sort of (tile, Gaussian) keys; the choice never changes a result bit.  Environment
- * (read once, tuning only): XYZ_SPLAT_BIN_CTAS_PER_SM = CTAs per SM of the counting-sort kernels
- * (default 4, 1 for predicted lists beyond 4e7 entries).                                        */
+ * (PixelOutput = ConstArray<float,3>).
+ *
+ * Two families of entry points:
+ *   xyz_launch_gaussian_splatting[_rows]   the reference's call shape: no workspace argument.  Scratch is library-owned,
+ *       one arena per (device, stream) -- launches on different streams never share buffers -- and grows on demand
+ *       (4 bytes per (tile, Gaussian) list entry, 36 more with XYZ_FLAG_DETERMINISTIC); the call synchronises `stream`
+ *       once (the list length is data dependent) unless XYZ_FLAG_ASYNC applies.  While `stream` is being captured into a
+ *       CUDA graph the scratch cannot grow (XYZ_ERR_WORKSPACE: run the iteration once outside the capture first); a
+ *       buffer a capture has seen is kept alive until xyz_b200_shutdown, so replays stay valid.
+ *   xyz_launch_gaussian_splatting_ws       caller-provided workspace (xyz_splat_workspace_bytes): never allocates, never
+ *       synchronises, keeps no library state -- re-entrant across streams and host threads (one workspace per launch in
+ *       flight), capturable from the first call.
+ * The per-tile lists come from a stable counting sort by tile (row bands of up to 8192 tiles) or a
+ * stable radix sort of (tile, Gaussian) keys (library sort; classic entry points only); the choice never changes a
+ * result bit.  Environment (read once, tuning only): XYZ_SPLAT_BIN_CTAS_PER_SM = CTAs per SM of the counting-sort
+ * kernels (default 4, 1 for predicted lists beyond 4e7 entries).                                        */
 XYZ_API int xyz_launch_gaussian_splatting(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients,
                                   const float* target_image, float* output_image, float* total_loss,
                                   int image_width, int image_height, int num_gaussians,
@@ -254,17 +266,43 @@ XYZ_API int xyz_launch_gaussian_splatting_rows(const xyz_gaussian_params* gaussi
                                        const float* target_image, float* output_image, float* total_loss,
                                        int image_width, int image_height, int num_gaussians,
                                        int row_begin, int row_end, void* stream, int flags);
-/* Statistics of the most recent splat launch on this host thread's device (host values):
- * stats[0] = (tile, Gaussian) list entries, stats[1] = tiles, stats[2] = longest tile list,
- * stats[3] = pixel-Gaussian pairs evaluated per pass. */
+/* Workspace variant.  `workspace` is device memory of at least
+ *   xyz_splat_workspace_bytes(width, height, N, row_begin, row_end, max_entries, flags)
+ * bytes, 256-byte aligned, whose first 256 bytes were zeroed once (xyz_splat_workspace_init); the flags must be the ones
+ * the size was asked for (XYZ_FLAG_RADIX_BINNING and row bands of more than 8192 tiles are not available here:
+ * XYZ_ERR_INVALID_ARGUMENT; the size query returns 0).  max_entries bounds the number of (tile, Gaussian) list entries
+ * -- at BASELINE's distributions about 42 per Gaussian for a 1024^2 image.  If a scene needs more, that launch renders
+ * EMPTY lists (image 0, loss = sum |target|, no gradients; memory-safe) and counts an overflow in the workspace header;
+ * nothing is reported by the call itself (it does not wait for the GPU): ask xyz_splat_workspace_status when convenient.
+ * Header (the first 32 bytes, device memory, 4 x uint64): {list length of the most recent launch, number of launches that
+ * did not fit (sticky), internal, max_entries of the most recent launch}.                                              */
+XYZ_API size_t xyz_splat_workspace_bytes(int image_width, int image_height, int num_gaussians, int row_begin, int row_end,
+                                 long long max_entries, int flags);
+XYZ_API int xyz_splat_workspace_init(void* workspace, size_t workspace_bytes, void* stream);
+XYZ_API int xyz_launch_gaussian_splatting_ws(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients,
+                                     const float* target_image, float* output_image, float* total_loss,
+                                     int image_width, int image_height, int num_gaussians, int row_begin, int row_end,
+                                     void* workspace, size_t workspace_bytes, long long max_entries,
+                                     void* stream, int flags);
+/* Synchronises `stream`, then status_host = {list length of the most recent launch on this workspace, overflow count
+ * (sticky), its max_entries, 1 if that launch overflowed (its outputs are void) else 0}. */
+XYZ_API int xyz_splat_workspace_status(const void* workspace, void* stream, long long status_host[4]);
+
+/* Statistics of the most recent splat launch of this host thread (host values; synchronises that launch's stream if
+ * its list length is not known yet): stats[0] = (tile, Gaussian) list entries, stats[1] = tiles, stats[2] = longest tile
+ * list, stats[3] = pixel-Gaussian pairs evaluated per pass.  XYZ_ERR_NOT_INITIALISED if there is none or its scratch has
+ * been reallocated or freed since; XYZ_ERR_WORKSPACE if it overflowed. */
 XYZ_API int xyz_splat_last_stats(long long stats_host[4]);
+/* Stage times of this host thread's most recent splat launch made with XYZ_FLAG_TIMING, in microseconds (waits for that
+ * launch): {per-Gaussian records + tile histograms, column / tile scans, list scatter, forward + loss, backward, total}. */
+XYZ_API int xyz_splat_last_timing(float stage_us_host[6]);
 /* Copies the integer tile-binning results of the most recent splat launch to host buffers (for the
  * bit-exact integer parity tests): per-Gaussian tile rectangles (N x 4 int32: tx0, ty0, tx1, ty1,
  * half-open), per-tile [begin, end) ranges (tiles x 2 int32; an empty tile has begin == end --
  * its running offset from the counting sort, (0, 0) from the radix path), the sorted Gaussian ids
  * (entries int32) and the per-Gaussian float records the rectangles were derived from
- * (N x 12 float: cx, cy, ia, ib, ic, sigmoid(opacity), r, g, b, 0, 0, 0).  Any pointer may be NULL.
- * Synchronises the device. */
+ * (N x 12 float: cx, cy, ia, ib, ic, sigmoid(opacity), r, g, b, and three floats that are left untouched).  Tiles outside
+ * the launch's row band are reported as (0, 0).  Any pointer may be NULL.  Synchronises the launch's stream. */
 XYZ_API int xyz_splat_debug_binning(int32_t* rects_host, int32_t* tile_ranges_host, int32_t* sorted_ids_host,
                             float* records_host);
 
@@ -284,6 +322,60 @@ XYZ_API int xyz_adam_step_individual_zero_grads(xyz_gaussian_params* params, xyz
 XYZ_API int xyz_adam_step(xyz_gaussian_params* params, const xyz_gaussian_grads* grads, xyz_adam_state* adam,
                   int num_gaussians, float learning_rate, float beta1, float beta2, float epsilon,
                   int iteration, void* stream);
+
+/* ---- multi-GPU: exchange of the shared-parameter gradients of C4/C5 (N x 9 floats, up to 108 MB) ---------------------
+ * The reference is single-GPU (cudaSetDevice(0), gaussian_splatting_training.cu:209).  When views (C5) or row bands (C4)
+ * are sharded over the GPUs of one NVSwitch box, every rank holds a partial gradient of ALL Gaussians.
+ *
+ * (1) NCCL (xyz_comm_init / xyz_allreduce_grads).  libnccl.so.2 is bound at run time (dlopen; the copy already
+ *     loaded into the process, e.g. PyTorch's, is preferred), so the library itself has no link-time dependency.
+ *     Either adopt a communicator the application already has (xyz_comm_init), or create one: rank 0 calls
+ *     xyz_comm_unique_id, the 128 bytes travel by any host channel, every rank calls xyz_comm_init_rank with its device
+ *     current; a single process driving several GPUs uses xyz_comm_init_all.  Collectives are enqueued on `stream`
+ *     right behind the kernels that produced the gradients (no host synchronisation), in place.                       */
+typedef struct xyz_comm xyz_comm;
+XYZ_API int xyz_comm_unique_id(unsigned char id_out[128]);
+XYZ_API int xyz_comm_init_rank(xyz_comm** comm_out, const unsigned char id[128], int rank, int world);
+XYZ_API int xyz_comm_init(xyz_comm** comm_out, void* nccl_comm /* ncclComm_t, stays owned by the caller */, int rank, int world);
+XYZ_API int xyz_comm_init_all(xyz_comm** comms_out /* ndev */, int ndev, const int* devices /* NULL: 0 .. ndev-1 */);
+XYZ_API int xyz_comm_destroy(xyz_comm* comm);
+XYZ_API int xyz_comm_rank(const xyz_comm* comm);
+XYZ_API int xyz_comm_world(const xyz_comm* comm);
+/* Bracket calls on SEVERAL communicators issued by ONE host thread (ncclGroupStart / ncclGroupEnd). */
+XYZ_API int xyz_comm_group_start(void);
+XYZ_API int xyz_comm_group_end(void);
+/* grads[i] = sum over ranks, fp32, in place (ncclAllReduce).  n = number of floats (N x 9 for the gradient buffer). */
+XYZ_API int xyz_allreduce_grads(xyz_comm* comm, float* grads, long long n, void* stream);
+XYZ_API int xyz_allreduce_f64(xyz_comm* comm, double* values, long long n, void* stream);
+/* The optimiser step of a sharded iteration without redundant work: reduce-scatter of the gradients by Gaussian range,
+ * adam_step_individual (+ fused zero-grad of the WHOLE local gradient buffer) on this rank's range only, all-gather of the
+ * updated parameters -- the same bytes on the wire as the all-reduce, Adam at 1 / world of its cost.  AdamState rows
+ * outside the rank's range are not touched.  *total_loss (optional) is all-reduced too. */
+XYZ_API int xyz_adam_step_individual_sharded(xyz_comm* comm, xyz_gaussian_params* params, xyz_gaussian_grads* grads,
+                                     xyz_adam_state* adam, int num_gaussians, const float lr_host[5], float beta1,
+                                     float beta2, float epsilon, int iteration, float* total_loss, void* stream);
+
+/* (2) The same step as ONE kernel over NVLink peer memory, no NCCL call: every rank's parameter and gradient buffers are
+ *     mapped into every other rank (CUDA IPC between processes: xyz_peer_alloc + xyz_peer_mailbox_open; plain peer access
+ *     inside one process).  The kernel waits until every rank's gradients are complete (sequence flags in the
+ *     mailboxes, st.release.sys / ld.acquire.sys), then the owner of a Gaussian range LOADS that range of every rank's
+ *     gradient buffer over NVLink and adds the rows in rank order, applies adam_step_individual, STORES the new
+ *     parameters into every rank's parameter buffer and zeroes the range in every rank's gradient buffer; a second
+ *     flag round makes sure all remote stores have landed before any rank's next kernel runs.  Parameters are therefore
+ *     bit-identical on all ranks by construction; the loss is summed in rank order on every rank.
+ *     The exchange keeps its sequence numbers in the mailboxes (device memory; separate from the sequence space of the
+ *     other fused exchanges), so the call is the same every time and a captured CUDA graph of a whole iteration can be
+ *     replayed.  iteration >= 1 is the reference's Adam step number (bias correction); iteration == 0 means "count the
+ *     steps on the device" (first call = step 1) -- what a replayed graph needs.  Every rank must make the same calls. */
+typedef struct xyz_peer_splat_buffers {
+    xyz_gaussian_params* params[XYZ_PEER_MAX_WORLD]; /* index = rank; [rank] = this rank's own buffer */
+    xyz_gaussian_grads* grads[XYZ_PEER_MAX_WORLD];
+} xyz_peer_splat_buffers;
+/* cudaMalloc + zero-fill + IPC handle, for buffers other ranks will map (open / close / destroy: xyz_peer_mailbox_*). */
+XYZ_API int xyz_peer_alloc(size_t bytes, void** local_ptr, unsigned char ipc_handle_out[64]);
+XYZ_API int xyz_adam_step_individual_peer(const xyz_peer_group* group, const xyz_peer_splat_buffers* buffers,
+                                  xyz_adam_state* adam, int num_gaussians, const float lr_host[5], float beta1,
+                                  float beta2, float epsilon, int iteration, float* total_loss, void* stream);
 
 #ifdef __cplusplus
 }

@@ -826,6 +826,230 @@ def test_covproj_full_size_against_the_oracle_on_sampled_rows():
 
 
 # ---------------------------------------------------------------------------------------------------
+# Caller-provided workspace (no allocation, no synchronisation, no library state) and stream re-entrancy
+# ---------------------------------------------------------------------------------------------------
+def run_splat_ws(ws, params, target, W, H, stream=None, flags=None):
+    N = params.shape[0]
+    grads = torch.zeros((N, 9), dtype=torch.float32, device=DEV)
+    out = torch.full((W * H, 3), float("nan"), dtype=torch.float32, device=DEV)
+    loss = torch.zeros(1, dtype=torch.float32, device=DEV)
+    ws.launch(dev(params) if N else torch.empty((0, 9), device=DEV), grads, dev(target), out, loss, flags=flags, stream=stream)
+    return grads, out, loss
+
+
+@pytest.mark.parametrize("flags", [0, 2, 1, 3], ids=["fast", "precise", "fast-det", "precise-det"])
+def test_splat_workspace_launch_equals_the_classic_launch(flags):
+    """xyz_launch_gaussian_splatting_ws on a caller-owned workspace: image and loss bit-identical to the classic entry
+    point, gradients bit-identical in deterministic mode (and to the atomics' tolerance otherwise); row bands; the
+    header reports the list length; xyz_splat_last_stats works on it."""
+    W, H, N = 256, 192, 5000
+    params, target = orc.splat_scene(N, W, H, seed=21)
+    g0, o0, l0 = run_splat(params, target, W, H, flags)
+    e0 = x.splat_last_stats()["entries"]
+    ws = x.SplatWorkspace(W, H, N, e0 + 1000, flags)
+    g, o, l = run_splat_ws(ws, params, target, W, H)
+    torch.cuda.synchronize()
+    assert np.array_equal(o.cpu().numpy(), o0) and l.item() == l0
+    if flags & x.FLAG_DETERMINISTIC:
+        assert np.array_equal(g.cpu().numpy(), g0)
+    else:
+        assert np.abs(g.cpu().numpy() - g0).max() <= 1e-4 * np.abs(g0).max()
+    st = ws.status()
+    assert st == {"entries": e0, "overflows": 0, "max_entries": e0 + 1000, "overflowed": False}
+    assert x.splat_last_stats()["entries"] == e0
+    # a row band on its own workspace
+    wsb = x.SplatWorkspace(W, H, N, e0, flags, rows=(64, 144))
+    gb, ob, lb = run_splat_ws(wsb, params, target, W, H)
+    g0b, o0b, l0b = run_splat(params, target, W, H, flags, rows=(64, 144))
+    assert np.array_equal(ob.cpu().numpy()[64 * W:144 * W], o0b[64 * W:144 * W]) and lb.item() == l0b
+    assert np.abs(gb.cpu().numpy() - g0b).max() <= 1e-4 * np.abs(g0b).max()
+    assert wsb.bytes < ws.bytes
+
+
+def test_splat_workspace_overflow_is_memory_safe_and_reported():
+    W, H, N = 256, 192, 5000
+    params, target = orc.splat_scene(N, W, H, seed=21)
+    run_splat(params, target, W, H)
+    e0 = x.splat_last_stats()["entries"]
+    ws = x.SplatWorkspace(W, H, N, e0 // 2)
+    g, o, l = run_splat_ws(ws, params, target, W, H)
+    torch.cuda.synchronize()
+    st = ws.status()
+    assert st["overflowed"] and st["overflows"] == 1 and st["entries"] == e0
+    assert (o == 0).all() and (g == 0).all() and abs(l.item() - np.abs(target).sum()) <= 1e-5 * np.abs(target).sum()
+    with pytest.raises(RuntimeError):
+        x.splat_last_stats()                                   # XYZ_ERR_WORKSPACE: that launch's outputs are void
+    # the same workspace keeps working for a scene that fits; the counter is sticky
+    small = params.copy()
+    small[:, 2:4] -= 1.5
+    g2, o2, l2 = run_splat_ws(ws, small, target, W, H)
+    g2s, o2s, l2s = run_splat(small, target, W, H)
+    assert np.array_equal(o2.cpu().numpy(), o2s) and l2.item() == l2s
+    st = ws.status()
+    assert not st["overflowed"] and st["overflows"] == 1
+    # wrong sizes are refused, not executed
+    with pytest.raises(RuntimeError):
+        lib_ws = x.SplatWorkspace(W, H, N, 1000)
+        lib_ws.max_entries = 10 ** 7                           # claims more entries than the buffer was sized for
+        run_splat_ws(lib_ws, params, target, W, H)
+    with pytest.raises(ValueError):
+        x.SplatWorkspace(W, H, N, 1000, x.FLAG_RADIX_BINNING)
+
+
+def test_splat_two_streams_in_flight_equal_sequential_launches():
+    """Re-entrancy (the way 8 views run on fewer GPUs): two views rendered concurrently on two streams -- once through
+    two workspaces, once through the classic entry point (library scratch is per stream) -- equal the sequential
+    results bit for bit (image, loss; deterministic gradients)."""
+    W, H, N = 320, 256, 8000
+    params, target = orc.splat_scene(N, W, H, seed=5)
+    target2 = np.roll(target.reshape(H, W, 3), (13, 29), (0, 1)).reshape(W * H, 3).copy()
+    F = x.FLAG_DETERMINISTIC
+    ref = [run_splat(params, t, W, H, F) for t in (target, target2)]
+    e0 = x.splat_last_stats()["entries"]
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    tp, t1, t2 = dev(params), dev(target), dev(target2)
+    torch.cuda.synchronize()
+    for mode in ("workspace", "classic"):
+        for rep in range(3):
+            outs = []
+            wss = [x.SplatWorkspace(W, H, N, e0 + 64, F) for _ in range(2)] if mode == "workspace" else [None, None]
+            for st, tt, ws in ((s1, t1, wss[0]), (s2, t2, wss[1])):
+                with torch.cuda.stream(st):
+                    g = torch.zeros((N, 9), device=DEV); o = torch.zeros((W * H, 3), device=DEV); l = torch.zeros(1, device=DEV)
+                    st.wait_stream(torch.cuda.default_stream())
+                    if ws is not None:
+                        ws.launch(tp, g, tt, o, l, stream=st)
+                    else:
+                        x.launch_gaussian_splatting(tp, g, tt, o, l, W, H, N, F, stream=st)
+                    outs.append((g, o, l))
+            torch.cuda.synchronize()
+            for (g, o, l), (rg, ro, rl) in zip(outs, ref):
+                assert np.array_equal(o.cpu().numpy(), ro) and l.item() == rl and np.array_equal(g.cpu().numpy(), rg), (mode, rep)
+
+
+def test_splat_workspace_launch_captured_from_the_first_call():
+    """No allocation and no synchronisation inside the workspace launch: a whole iteration (zero-grad, launch, Adam) is
+    captured into a CUDA graph WITHOUT a warm-up call and replays to the eager result."""
+    W, H, N = 256, 192, 5000
+    params, target = orc.splat_scene(N, W, H, seed=21)
+    lr = (0.5, 0.01, 0.01, 0.01, 0.02)
+    def fresh():
+        return (dev(params), torch.zeros((N, 9), device=DEV), torch.zeros((N, 18), device=DEV),
+                torch.zeros((W * H, 3), device=DEV), torch.zeros(1, device=DEV))
+    tt = dev(target)
+    # eager trajectory, classic entry points
+    p, g, a, o, l = fresh()
+    losses = []
+    for it in range(1, 4):
+        l.zero_()
+        x.launch_gaussian_splatting(p, g, tt, o, l, W, H, N, x.FLAG_DETERMINISTIC)
+        x.adam_step_individual(p, g, a, *lr, iteration=1, zero_grads=True)   # fixed bias correction: the graph bakes it in
+        losses.append(l.item())
+    want_p = p.cpu().numpy()
+    # the same as ONE captured graph replayed three times
+    p, g, a, o, l = fresh()
+    ws = x.SplatWorkspace(W, H, N, 80 * N, x.FLAG_DETERMINISTIC)
+    st = torch.cuda.Stream()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(graph, stream=st, capture_error_mode="thread_local"):
+            l.zero_()
+            ws.launch(p, g, tt, o, l, stream=st)
+            x.adam_step_individual(p, g, a, *lr, iteration=1, zero_grads=True, stream=st)
+    got = []
+    for it in range(3):
+        graph.replay()
+        torch.cuda.synchronize()
+        got.append(l.item())
+    assert got == losses
+    assert np.array_equal(p.cpu().numpy(), want_p)
+    assert not ws.status()["overflowed"]
+
+
+def test_classic_launch_refuses_to_grow_scratch_inside_a_capture():
+    """Library-owned scratch cannot grow while its stream is capturing: XYZ_ERR_WORKSPACE instead of a cudaMalloc /
+    synchronisation inside the capture (and instead of freeing a buffer a graph may replay on)."""
+    W, H, N = 128, 96, 700
+    params, target = orc.splat_scene(N, W, H, seed=2)
+    tp, tt = dev(params), dev(target)
+    g, o, l = torch.zeros((N, 9), device=DEV), torch.zeros((W * H, 3), device=DEV), torch.zeros(1, device=DEV)
+    st = torch.cuda.Stream()      # a fresh stream: its arenas are empty
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(graph, stream=st, capture_error_mode="thread_local"):
+            code = x.lib().xyz_launch_gaussian_splatting(tp.data_ptr(), g.data_ptr(), tt.data_ptr(), o.data_ptr(), l.data_ptr(),
+                                                         W, H, N, st.cuda_stream, x.FLAG_ASYNC)
+    torch.cuda.synchronize()
+    assert code == -2      # XYZ_ERR_WORKSPACE, nothing was enqueued
+    # outside a capture the same stream works, and a later capture on the warmed-up stream is accepted
+    x.launch_gaussian_splatting(tp, g, tt, o, l, W, H, N, 0, stream=st)
+    x.launch_gaussian_splatting(tp, g, tt, o, l, W, H, N, x.FLAG_ASYNC, stream=st)
+    torch.cuda.synchronize()
+    with torch.cuda.stream(st):
+        with torch.cuda.graph(graph, stream=st, capture_error_mode="thread_local"):
+            code = x.lib().xyz_launch_gaussian_splatting(tp.data_ptr(), g.data_ptr(), tt.data_ptr(), o.data_ptr(), l.data_ptr(),
+                                                         W, H, N, st.cuda_stream, x.FLAG_ASYNC)
+    assert code == 0
+    graph.replay()
+    torch.cuda.synchronize()
+
+
+def test_comm_and_peer_optimiser_step_on_one_rank():
+    """World size 1 of the multi-GPU entry points (the N-rank cases run in tests/test_gpu_multi.py): the library's NCCL
+    communicator initialises, the sharded and the fused peer-memory optimiser steps equal adam_step_individual + zero-grad."""
+    N = 10_001
+    rng = np.random.default_rng(4)
+    p0 = rng.normal(size=(N, 9)).astype(np.float32)
+    g0 = rng.normal(size=(N, 9)).astype(np.float32)
+    a0 = np.abs(rng.normal(size=(N, 18))).astype(np.float32) * 0.1
+    lr = (0.1, 0.01, 0.001, 0.02, 0.05)
+    p, g, a = dev(p0), dev(g0), dev(a0)
+    x.adam_step_individual(p, g, a, *lr, iteration=4)
+    comm = x.Comm(0, 1, lambda b: b)
+    p1, g1, a1, l1 = dev(p0), dev(g0), dev(a0), torch.full((1,), 2.5, device=DEV)
+    comm.allreduce_grads(g1)
+    assert torch.equal(g1, dev(g0))
+    comm.adam_step_individual_sharded(p1, g1, a1, *lr, iteration=4, total_loss=l1)
+    assert torch.equal(p1, p) and torch.equal(a1, a) and (g1 == 0).all() and l1.item() == 2.5
+    comm.destroy()
+    grp = x.PeerGroup(0, 1, lambda h: [h])
+    ps = x.PeerSplat(grp, N, lambda h: [h])
+    ps.params.copy_(dev(p0)); ps.grads.copy_(dev(g0)); ps.adam.copy_(dev(a0))
+    for it in range(3):                                        # several calls: sequence numbers, ticket reset
+        if it:
+            ps.params.copy_(dev(p0)); ps.grads.copy_(dev(g0)); ps.adam.copy_(dev(a0))
+        l2 = torch.full((1,), 2.5, device=DEV)
+        ps.adam_step(*lr, iteration=4, total_loss=l2)
+        torch.cuda.synchronize()
+        assert l2.item() == 2.5 and (ps.grads == 0).all()
+        assert np.allclose(ps.params.cpu().numpy(), p.cpu().numpy(), rtol=1e-6, atol=1e-7)
+        assert np.allclose(ps.adam.cpu().numpy(), a.cpu().numpy(), rtol=1e-6, atol=1e-7)
+    ps.close(); grp.close()
+
+
+def test_python_bindings_reject_mismatched_sizes_and_devices():
+    """Wrong element counts are Python errors, not out-of-bounds kernels."""
+    N, W, H = 100, 32, 32
+    params, target = orc.splat_scene(N, W, H, seed=1)
+    tp, tt = dev(params), dev(target)
+    g, o, l = torch.zeros((N, 9), device=DEV), torch.zeros((W * H, 3), device=DEV), torch.zeros(1, device=DEV)
+    with pytest.raises(ValueError):
+        x.launch_gaussian_splatting(tp, g, tt, o, l, W, H, N + 1)
+    with pytest.raises(ValueError):
+        x.launch_gaussian_splatting(tp, g, tt, o[:-1], l, W, H, N)
+    with pytest.raises(ValueError):
+        x.adam_step_individual(tp, g, torch.zeros((N, 17), device=DEV), 0.1, 0.1, 0.1, 0.1, 0.1)
+    with pytest.raises(ValueError):
+        x.covproj_fwd_bwd(*[torch.zeros((10, k), device=DEV) for k in (6, 9, 6, 3)],
+                          *[torch.zeros((10, k), device=DEV) for k in (3, 6, 8, 6)])
+    with pytest.raises(ValueError):
+        x.lsq_grad(torch.zeros((10, 3), dtype=torch.float64, device=DEV), torch.zeros(7, dtype=torch.float64, device=DEV))
+    if torch.cuda.device_count() > 1:
+        with pytest.raises(ValueError):
+            x.zero_gradients(torch.zeros((N, 9), device="cuda:1"))
+
+
+# ---------------------------------------------------------------------------------------------------
 # Adam / zero-grad (SURVEY 8f rank 1)
 # ---------------------------------------------------------------------------------------------------
 def test_zero_gradients_and_adam_match_oracle():

@@ -901,7 +901,7 @@ int launch_tables(const int32_t* idx, const T* val, long long n, T* grad, int k,
                   int grid, size_t smem) {
     if (deterministic) {
         void* scratch = nullptr;
-        int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(grid) * k * sizeof(T), &scratch);
+        int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(grid) * k * sizeof(T), &scratch, st);
         if (err) return err;
         T* rows = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(scratch) + 256);
         auto kern = accumulate_kernel<T, kVec, kImplicit, true>;
@@ -928,7 +928,7 @@ int launch_tagged(const int32_t* idx, const T* val, long long n, T* grad, int k,
     if (deterministic) {
         // rows per CTA (static element -> warp -> CTA assignment, lane-ordered duplicate folding), summed in CTA order
         void* scratch = nullptr;
-        int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(grid) * k * sizeof(T), &scratch);
+        int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(grid) * k * sizeof(T), &scratch, st);
         if (err) return err;
         T* rows = reinterpret_cast<T*>(reinterpret_cast<unsigned char*>(scratch) + 256);
         auto kern = accumulate_tagged_kernel<T, W, kImplicit, true, true>;
@@ -1009,7 +1009,7 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
             int n_rows = 0;
             if (deterministic) {
                 void* scratch = nullptr;
-                const int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * k * sizeof(float), &scratch);
+                const int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * k * sizeof(float), &scratch, st);
                 if (err) return err;
                 rows = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
             }
@@ -1029,7 +1029,7 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
             if (deterministic) {
                 void* scratch = nullptr;
                 const int err =
-                    scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * kStripePassBins * sizeof(float), &scratch);
+                    scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * kStripePassBins * sizeof(float), &scratch, st);
                 if (err) return err;
                 rows = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
             }
@@ -1054,7 +1054,7 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
             int n_rows = 0;
             if (deterministic) {
                 void* scratch = nullptr;
-                const int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * k * sizeof(double), &scratch);
+                const int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * k * sizeof(double), &scratch, st);
                 if (err) return err;
                 rows = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256);
             }
@@ -1070,7 +1070,7 @@ int accumulate(const int32_t* idx, const T* val, long long n, T* grad, int k, vo
             if (deterministic) {
                 void* scratch = nullptr;
                 const int err =
-                    scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * kStripePassBins * sizeof(double), &scratch);
+                    scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count()) * kStripePassBins * sizeof(double), &scratch, st);
                 if (err) return err;
                 rows = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256);
             }
@@ -1149,7 +1149,7 @@ extern "C" int xyz_accumulate_f32_allreduce(const int32_t* idx, const float* val
     }
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     void* scratch = nullptr;
-    int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count() + 1) * k * sizeof(float), &scratch);
+    int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(sm_count() + 1) * k * sizeof(float), &scratch, st);
     if (err) return err;
     float* rows = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);
     int n_rows = 0;

@@ -79,6 +79,15 @@ int adam_launch(xyz_gaussian_params* params, const xyz_gaussian_grads* grads, xy
 }
 
 }  // namespace
+
+// adam_step_individual on the Gaussians [g_begin, g_end) only (sharded optimiser step, csrc/comm.cu)
+int adam_launch_range(xyz_gaussian_params* params, const xyz_gaussian_grads* grads, xyz_adam_state* adam, int g_begin,
+                      int g_end, const float lr[5], float beta1, float beta2, float eps, int iteration, void* stream) {
+    if (g_begin < 0 || g_end < g_begin) return XYZ_ERR_INVALID_ARGUMENT;
+    return adam_launch(params + g_begin, grads + g_begin, adam + g_begin, g_end - g_begin, lr, beta1, beta2, eps, iteration,
+                       stream);
+}
+
 }  // namespace xyzb
 
 extern "C" int xyz_zero_gradients(xyz_gaussian_grads* gradients, int num_gaussians, void* stream) {

@@ -23,10 +23,13 @@ inline void count_launch(int n = 1) { g_launch_count.fetch_add(static_cast<uint6
 
 inline int last_error() { return static_cast<int>(cudaGetLastError()); }
 
-// Library-owned scratch, one growable arena per (device, slot).  Grown with cudaMalloc on first use
-// or when a launch needs more; never shrinks; freed by xyz_b200_shutdown().
+// Library-owned scratch, one growable arena per (device, STREAM, slot): calls in flight on different streams never share
+// tickets, partial rows or tile lists.  Grown with cudaMalloc on first use or when a launch needs more (never while
+// the stream is capturing: XYZ_ERR_WORKSPACE); never shrinks; a buffer handed out during a capture is never freed
+// before xyz_b200_shutdown() (a graph may replay on it).  `generation` changes whenever the arena's pointer does.
 enum ScratchSlot : int { SCRATCH_REDUCE = 0, SCRATCH_SPLAT = 1, SCRATCH_SPLAT_SORT = 2, SCRATCH_SLOTS = 3 };
-int scratch_get(ScratchSlot slot, size_t bytes, void** ptr);  // returns cudaError_t
+int scratch_get(ScratchSlot slot, size_t bytes, void** ptr, cudaStream_t stream, uint64_t* generation = nullptr);
+bool scratch_is_current(ScratchSlot slot, cudaStream_t stream, uint64_t generation);
 void scratch_free_all();
 int sm_count();  // SMs of the current device (148 on B200)
 
@@ -37,6 +40,13 @@ struct PeerMailbox {
     double data[2][XYZ_PEER_MAX_WORLD][XYZ_PEER_SLOT_DOUBLES];   // small rows (least squares: 5 doubles)
     unsigned long long flag[XYZ_PEER_MAX_WORLD];                 // shared by both areas: one sequence per group
     float vec[2][XYZ_PEER_MAX_WORLD][XYZ_PEER_VEC_FLOATS];       // K-bin rows (accumulation), K <= XYZ_PEER_VEC_FLOATS
+    // the splat optimiser exchange (xyz_adam_step_individual_peer) has its own sequence space, kept ON THE DEVICE so that
+    // a captured CUDA graph can be replayed: every rank's kernel reads splat_seq / splat_iter of its OWN mailbox and
+    // advances them when it is done (all ranks make the same calls, so the counters agree)
+    unsigned long long flag_splat[XYZ_PEER_MAX_WORLD];
+    double loss_splat[2][XYZ_PEER_MAX_WORLD];
+    unsigned long long splat_seq;   // last sequence number used (two per call)
+    unsigned long long splat_iter;  // optimiser steps taken with iteration == 0 ("count them yourself")
 };
 struct PeerArgs {  // passed to kernels by value; world <= 1 means "no exchange"
     PeerMailbox* box[XYZ_PEER_MAX_WORLD];

@@ -492,7 +492,7 @@ int covproj_sharedw_launch(const float* J, const float* W9, const float* S, cons
     const long long want = (n + kTileE - 1) / kTileE;
     const int grid = static_cast<int>(want < 1 ? 1 : (want < max_ctas ? want : max_ctas));
     void* scratch = nullptr;
-    const int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(max_ctas) * kSwAcc * sizeof(float), &scratch);
+    const int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(max_ctas) * kSwAcc * sizeof(float), &scratch, st);
     if (err) return err;
     unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
     float* partials = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(scratch) + 256);

@@ -380,7 +380,7 @@ int lsq_grad_launch(const xyz_data_point* data, long long n_points, xyz_lsq_para
     const int grid = static_cast<int>(want < 1 ? 1 : (want < max_ctas ? want : max_ctas));  // >= 1: a rank with no
     void* scratch = nullptr;                                                                // points still exchanges
     const size_t bytes = 256 + static_cast<size_t>(max_ctas) * kAcc * sizeof(double);
-    int err = scratch_get(SCRATCH_REDUCE, bytes, &scratch);
+    int err = scratch_get(SCRATCH_REDUCE, bytes, &scratch, st);
     if (err) return err;
     // scratch arenas are zero-filled when allocated and every kernel leaves its ticket at zero
     unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
@@ -458,7 +458,7 @@ extern "C" int xyz_lsq_sgd_step_f64(const xyz_data_point* data, long long n_tota
     const long long want = (batch_size + kThreads - 1) / kThreads;
     const int grid = static_cast<int>(want < max_ctas ? want : max_ctas);
     void* scratch = nullptr;
-    int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(max_ctas) * kAcc * sizeof(double), &scratch);
+    int err = scratch_get(SCRATCH_REDUCE, 256 + static_cast<size_t>(max_ctas) * kAcc * sizeof(double), &scratch, st);
     if (err) return err;
     unsigned int* ticket = reinterpret_cast<unsigned int*>(scratch);
     double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256);
@@ -498,7 +498,7 @@ extern "C" int xyz_lsq_sgd_run_f64(const xyz_data_point* data, long long n_total
     constexpr int kMaxEpochsPerLaunch = 4096;
     void* scratch = nullptr;
     const size_t rows_bytes = 2 * static_cast<size_t>(max_ctas) * kAcc * sizeof(double);
-    int err = scratch_get(SCRATCH_REDUCE, 256 + rows_bytes + kMaxEpochsPerLaunch * sizeof(double), &scratch);
+    int err = scratch_get(SCRATCH_REDUCE, 256 + rows_bytes + kMaxEpochsPerLaunch * sizeof(double), &scratch, st);
     if (err) return err;
     double* partials = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256);
     double* lrs_dev = reinterpret_cast<double*>(reinterpret_cast<unsigned char*>(scratch) + 256 + rows_bytes);

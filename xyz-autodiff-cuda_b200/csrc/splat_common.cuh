@@ -5,7 +5,7 @@
 // (:48-50, :90-92) is dead code.  This pipeline produces the same image, loss and
 // gradients from
 //   1. splat_preprocess_kernel : per Gaussian, once: exp(scale), R(theta), Sigma, Sigma^-1,
-//      sigmoid(opacity) -> a 48-byte record; plus the rectangle of 16x16 tiles outside which the
+//      sigmoid(opacity) -> a 64-byte record; plus the rectangle of 16x16 tiles outside which the
 //      pair weight exp(-d2/2) is EXACTLY 0.0f (so skipping those pairs cannot change any result);
 //   2. integer work: per-tile lists of Gaussian ids, each ascending (= the reference's summation
 //      order), built by a stable counting sort by tile (splat_host.cu section 2b) or, for more than
@@ -26,7 +26,7 @@ constexpr int kTile = 16;                 // TILE_SIZE, gaussian_splatting_kerne
 constexpr int kTilePixels = kTile * kTile;
 constexpr int kBwdChunk = 128;             // list entries (= threads) per backward CTA; chunks never straddle tiles
 constexpr int kSpanRows = 16;              // tile-row spans kept per Gaussian between preprocess and key emission
-constexpr int kRecFloats = 12;            // {cx, cy, ia, ib, ic, sigmoid(opacity), r, g, b, 0, 0, 0}
+constexpr int kRecFloats = 16;            // {cx, cy, ia, ib | ic, sigmoid(opacity), r, g | b, exp(s0), exp(s1), cos | sin, 0, 0, 0}
 
 // exp(-d2/2) == 0.0f exactly beyond these:
 //   fast-math/FTZ (ex2.approx.ftz): 0.5*d2*log2(e) > 126   <=> 0.5*d2 > 87.34 ; margin -> 88
@@ -42,7 +42,7 @@ struct SplatView {  // what one launch renders
 };
 
 struct SplatBuffers {  // device scratch of one launch (library-owned)
-    float4* records;          // N x 3 float4
+    float4* records;          // N x 4 float4 (kRecFloats)
     int4* rects;              // N: tx0, ty0, tx1, ty1 (half-open)
     unsigned int* touched;    // N: tiles per Gaussian
     int2* spans;              // N x kSpanRows: [tx0, tx1) of the first kSpanRows tile rows of the rectangle
@@ -66,11 +66,10 @@ int splat_forward_launch_fast(const SplatView&, const SplatBuffers&, const float
                               cudaStream_t);
 int splat_forward_launch_precise(const SplatView&, const SplatBuffers&, const float* target, float* output,
                                  cudaStream_t);
-int splat_backward_launch_fast(const SplatView&, const SplatBuffers&, const xyz_gaussian_params* params,
-                               xyz_gaussian_grads* grads, const float* target, const float* output,
-                               long long entries, bool deterministic, cudaStream_t);
-int splat_backward_launch_precise(const SplatView&, const SplatBuffers&, const xyz_gaussian_params* params,
-                                  xyz_gaussian_grads* grads, const float* target, const float* output,
-                                  long long entries, bool deterministic, cudaStream_t);
+// bwd_ctas = size of the backward work list (an upper bound of the CTAs needed; surplus records hold tile = -1)
+int splat_backward_launch_fast(const SplatView&, const SplatBuffers&, xyz_gaussian_grads* grads, long long bwd_ctas,
+                               bool deterministic, cudaStream_t);
+int splat_backward_launch_precise(const SplatView&, const SplatBuffers&, xyz_gaussian_grads* grads, long long bwd_ctas,
+                                  bool deterministic, cudaStream_t);
 
 }  // namespace xyzb

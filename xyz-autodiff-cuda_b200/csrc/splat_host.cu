@@ -6,6 +6,9 @@
 // bit for bit from the same record floats (oracle/xyz_oracle.cpp::tile_rect).
 #include <algorithm>
 #include <cstdlib>
+#include <map>
+#include <mutex>
+#include <utility>
 #include <vector>
 
 #include <cub/device/device_radix_sort.cuh>
@@ -108,16 +111,22 @@ __global__ void __launch_bounds__(256)
     splat_preprocess_kernel(SplatView v, const xyz_gaussian_params* __restrict__ params, float4* __restrict__ records,
                             int4* __restrict__ rects, unsigned int* __restrict__ touched, int2* __restrict__ spans,
                             float d2max, int no_cull, int chunk_size, int n_tiles, unsigned int* __restrict__ hist,
-                            unsigned int* __restrict__ ticket) {
-    extern __shared__ unsigned int s_cnt[];  // kCount: n_tiles counters
+                            unsigned int* __restrict__ ticket, unsigned int* __restrict__ chunk_total) {
+    // kCount: n_tiles counters, one per tile of THIS launch's row band (tile ids relative to the band's first tile row:
+    // a band of 1/8 of the image has 1/8 of the counters, of the histogram traffic and of the column scan)
+    extern __shared__ unsigned int s_cnt[];
+    __shared__ unsigned int s_total;
     const int tid = threadIdx.x;
     const int per_cta = kCount ? chunk_size : 256;
     const int g_begin = blockIdx.x * per_cta, g_end = min(g_begin + per_cta, v.num_gaussians);
+    const int ty_lo = v.row_begin / kTile;
     if (kCount) {
         if (blockIdx.x == 0 && tid == 0) *ticket = 0u;  // for the column-scan kernel that follows
+        if (tid == 0) s_total = 0u;
         for (int t = tid; t < n_tiles; t += 256) s_cnt[t] = 0u;
         __syncthreads();
     }
+    unsigned int my_total = 0u;
     for (int gb = g_begin; gb < g_end; gb += 256) {  // warp-uniform trip count
         const int g = gb + tid;
         const bool live = g < g_end;
@@ -140,9 +149,12 @@ __global__ void __launch_bounds__(256)
             const float inv_det = __fdiv_rn(1.0f, det);
             const float ia = __fmul_rn(C, inv_det), ib = __fmul_rn(-B, inv_det), ic = __fmul_rn(A, inv_det);
             const float so = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-p.opacity[0])));
-            records[3 * g] = make_float4(p.center[0], p.center[1], ia, ib);
-            records[3 * g + 1] = make_float4(ic, so, p.color[0], p.color[1]);
-            records[3 * g + 2] = make_float4(p.color[2], 0.f, 0.f, 0.f);
+            records[4 * g] = make_float4(p.center[0], p.center[1], ia, ib);
+            records[4 * g + 1] = make_float4(ic, so, p.color[0], p.color[1]);
+            // exp(scale), cos and sin ride along for the backward pass: its per-Gaussian chain rule is applied at exactly
+            // the Sigma the forward pass used, in both math flavours (this translation unit is always IEEE)
+            records[4 * g + 2] = make_float4(p.color[2], es0, es1, ct);
+            records[4 * g + 3] = make_float4(sn, 0.f, 0.f, 0.f);
             r = gaussian_tile_rect(p.center[0], p.center[1], ia, ib, ic, v, d2max, no_cull);
             rects[g] = r;
             sc = span_coef(p.center[0], p.center[1], ia, ib, ic, d2max, no_cull);
@@ -153,9 +165,10 @@ __global__ void __launch_bounds__(256)
                 // the first kSpanRows rows are kept for the binning kernels (rows beyond that are recomputed there)
                 if (ty - r.y < kSpanRows) spans[static_cast<size_t>(g) * kSpanRows + (ty - r.y)] = make_int2(s.x, max(s.y, s.x));
                 if (kCount && !big_one)
-                    for (int tx = s.x; tx < s.y; ++tx) atomicAdd(&s_cnt[ty * v.tiles_x + tx], 1u);
+                    for (int tx = s.x; tx < s.y; ++tx) atomicAdd(&s_cnt[(ty - ty_lo) * v.tiles_x + tx], 1u);
             }
             touched[g] = cnt;
+            my_total += cnt;
         }
         if (kCount) {
             unsigned int big = __ballot_sync(0xffffffffu, big_one);
@@ -174,15 +187,20 @@ __global__ void __launch_bounds__(256)
                 cb.ok = __shfl_sync(0xffffffffu, sc.ok, src);
                 for (int ty = rb.y + lane; ty < rb.w; ty += 32) {
                     const int2 s = tile_row_span(cb, rb, ty, v);
-                    for (int tx = s.x; tx < s.y; ++tx) atomicAdd(&s_cnt[ty * v.tiles_x + tx], 1u);
+                    for (int tx = s.x; tx < s.y; ++tx) atomicAdd(&s_cnt[(ty - ty_lo) * v.tiles_x + tx], 1u);
                 }
             }
         }
     }
     if (kCount) {
+        // the chunk's number of list entries (integer adds: order-independent), for the deterministic mode's
+        // positions in Gaussian order (scanned over the chunks by the column-scan kernel's last CTA)
+        my_total = warp_sum(my_total);
+        if ((tid & 31) == 0 && my_total) atomicAdd(&s_total, my_total);
         __syncthreads();
         unsigned int* out = hist + static_cast<size_t>(blockIdx.x) * n_tiles;
         for (int t = tid; t < n_tiles; t += 256) out[t] = s_cnt[t];
+        if (tid == 0) chunk_total[blockIdx.x] = s_total;
     }
 }
 
@@ -211,7 +229,7 @@ __global__ void __launch_bounds__(256)
             if (rb == r.y) {
                 s = spans[static_cast<size_t>(g) * kSpanRows + hl];
             } else {
-                const float4 r0 = __ldg(records + 3 * g), r1 = __ldg(records + 3 * g + 1);
+                const float4 r0 = __ldg(records + 4 * g), r1 = __ldg(records + 4 * g + 1);
                 const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
                 s = tile_row_span(sc, r, ty, v);
             }
@@ -260,6 +278,42 @@ constexpr long long kBinLongList = 40LL << 20;  // predicted list length beyond 
 // publishes EMPTY tile ranges and an empty work list instead and bumps the sticky counter total_entries[1] (which never
 // falls below `overflow_base`, the count the host has seen), so that no later kernel of the launch reads or writes
 // beyond the buffers.
+// Exclusive scan (64-bit) of n unsigned ints by one CTA of 1024 threads: out[i] = in[0] + ... + in[i - 1].
+__device__ __forceinline__ void cta_exclusive_scan_u32_to_u64(const unsigned int* in, int n, unsigned long long* out, int tid) {
+    __shared__ unsigned long long s_w[32];
+    __shared__ unsigned long long s_c;
+    const int lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) s_c = 0ull;
+    __syncthreads();
+    for (int base = 0; base < n; base += 1024) {
+        const int i = base + tid;
+        const unsigned long long mine = i < n ? static_cast<unsigned long long>(__ldcg(in + i)) : 0ull;
+        unsigned long long x = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned long long y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_w[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned long long w = s_w[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_w[lane] = w;
+        }
+        __syncthreads();
+        const unsigned long long carry = s_c;
+        if (i < n) out[i] = carry + (warp > 0 ? s_w[warp - 1] : 0ull) + (x - mine);
+        __syncthreads();
+        if (tid == 1023) s_c = carry + s_w[31];
+        __syncthreads();
+    }
+}
+
 __device__ __forceinline__ void bin_tilescan(const unsigned int* tile_total, int n_tiles, int2* __restrict__ tile_ranges,
                                              int* __restrict__ chunk_offsets, unsigned long long* __restrict__ total_entries,
                                              unsigned long long capacity, unsigned long long overflow_base, int tid) {
@@ -337,6 +391,7 @@ __device__ __forceinline__ void bin_tilescan(const unsigned int* tile_total, int
         // sticky counter, kept at or above the count the host has already seen (the scratch may have been reallocated)
         const unsigned long long seen = total_entries[1] > overflow_base ? total_entries[1] : overflow_base;
         total_entries[1] = overflow ? seen + 1ull : seen;
+        total_entries[3] = capacity;  // what this launch was sized for (xyz_splat_workspace_status)
     }
 }
 
@@ -347,7 +402,8 @@ __global__ void __launch_bounds__(1024)
     splat_bin_colscan_kernel(unsigned int* __restrict__ hist, int n_chunks, int n_tiles, unsigned int* tile_total,
                              unsigned int* ticket, int2* __restrict__ tile_ranges, int* __restrict__ chunk_offsets,
                              unsigned long long* __restrict__ total_entries, unsigned long long capacity,
-                             unsigned long long overflow_base) {
+                             unsigned long long overflow_base, const unsigned int* chunk_total,
+                             unsigned long long* __restrict__ chunk_base) {
     __shared__ unsigned int s_part[32][33];
     __shared__ bool s_last;
     const int tx = threadIdx.x, gy = threadIdx.y;
@@ -381,6 +437,9 @@ __global__ void __launch_bounds__(1024)
     if (!s_last) return;
     __threadfence();
     bin_tilescan(tile_total, n_tiles, tile_ranges, chunk_offsets, total_entries, capacity, overflow_base, tid);
+    // deterministic mode: list entries before every chunk, in Gaussian order (the scatter kernel turns them into
+    // per-Gaussian positions) -- what used to be a library scan over all Gaussians
+    if (chunk_base) cta_exclusive_scan_u32_to_u64(chunk_total, n_chunks, chunk_base, tid);
 }
 
 // Scatter: one CTA per chunk, next free slot of every tile in shared memory (start = tile begin + the chunk's column
@@ -393,11 +452,12 @@ template <bool kDeterministic>
 __global__ void __launch_bounds__(kBinThreads)
     splat_bin_scatter_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ rects,
                              const int2* __restrict__ spans, const unsigned int* __restrict__ touched,
-                             const unsigned long long* __restrict__ offsets_incl, int chunk_size, int n_tiles,
+                             unsigned long long* __restrict__ offsets_incl, int chunk_size, int n_tiles, int tile0,
                              const unsigned int* __restrict__ hist, const int2* __restrict__ tile_ranges,
                              unsigned int* __restrict__ vals_out, int* __restrict__ sorted_gid, float d2max, int no_cull,
                              const int* __restrict__ chunk_offsets, int4* __restrict__ chunk_info, int chunk_info_size,
-                             const unsigned long long* __restrict__ total_entries, unsigned long long capacity) {
+                             const unsigned long long* __restrict__ total_entries, unsigned long long capacity,
+                             const unsigned long long* __restrict__ chunk_base) {
     extern __shared__ unsigned int s_next[];  // next free slot per tile
     __shared__ unsigned char s_hit[kBinThreads / 32][32];  // per warp: rank among the group's hits -> lane
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -406,13 +466,39 @@ __global__ void __launch_bounds__(kBinThreads)
     for (int t = blockIdx.x * kBinThreads + tid; t < n_tiles; t += gridDim.x * kBinThreads) {
         const int2 r = tile_ranges[t];
         const int first_chunk = chunk_offsets[t], c = chunk_offsets[t + 1] - first_chunk;
-        for (int k = 0; k < c; ++k) chunk_info[first_chunk + k] = make_int4(t, r.x + k * kBwdChunk, r.y, 0);
+        for (int k = 0; k < c; ++k) chunk_info[first_chunk + k] = make_int4(tile0 + t, r.x + k * kBwdChunk, r.y, 0);
     }
     for (int c = chunk_offsets[n_tiles] + blockIdx.x * kBinThreads + tid; c < chunk_info_size; c += gridDim.x * kBinThreads)
         chunk_info[c] = make_int4(-1, -1, -1, -1);
     if (capacity != 0ull && total_entries[0] > capacity) return;  // XYZ_FLAG_ASYNC overflow: every list is empty
     const unsigned int* mine = hist + static_cast<size_t>(blockIdx.x) * n_tiles;
     for (int t = tid; t < n_tiles; t += kBinThreads) s_next[t] = static_cast<unsigned int>(tile_ranges[t].x) + mine[t];
+    if (kDeterministic) {
+        // offsets_incl[g] = list entries of Gaussians 0 .. g (Gaussian order) = the end of g's block of entry_grads rows
+        __shared__ unsigned long long s_scan_w[kBinThreads / 32];
+        unsigned long long carry = chunk_base[blockIdx.x];
+        for (int gb = g_begin; gb < g_end; gb += kBinThreads) {
+            const int g = gb + tid;
+            const unsigned long long mine_c = g < g_end ? touched[g] : 0u;
+            unsigned long long xs = mine_c;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned long long y = __shfl_up_sync(0xffffffffu, xs, o);
+                if (lane >= o) xs += y;
+            }
+            __syncthreads();  // the previous round's readers of s_scan_w are done
+            if (lane == 31) s_scan_w[warp] = xs;
+            __syncthreads();
+            unsigned long long before = 0ull, total = 0ull;
+#pragma unroll
+            for (int w = 0; w < kBinThreads / 32; ++w) {
+                if (w < warp) before += s_scan_w[w];
+                total += s_scan_w[w];
+            }
+            if (g < g_end) offsets_incl[g] = carry + before + xs;
+            carry += total;
+        }
+    }
     __syncthreads();
 
     // this warp's band of tile rows (of the rows this launch renders), taken RL rows at a time: lane = (row rl, column
@@ -439,7 +525,7 @@ __global__ void __launch_bounds__(kBinThreads)
     for (int S0 = R0; S0 < R1; S0 += RL) {
         const int S1 = min(S0 + RL, R1);
         const int ty = S0 + rl;  // this lane's tile row
-        unsigned int* row_next = s_next + ty * v.tiles_x;
+        unsigned int* row_next = s_next + (ty - ty_lo) * v.tiles_x;  // counters are relative to the band's first tile row
         int4 r_next = load_rect(g_begin);
         for (int gb = g_begin; gb < g_end; gb += 32) {
             const int4 r = r_next;
@@ -467,7 +553,7 @@ __global__ void __launch_bounds__(kBinThreads)
                         if (j < kSpanRows) {
                             sp = spans[static_cast<size_t>(gg) * kSpanRows + j];
                         } else {
-                            const float4 r0 = __ldg(records + 3 * gg), r1 = __ldg(records + 3 * gg + 1);
+                            const float4 r0 = __ldg(records + 4 * gg), r1 = __ldg(records + 4 * gg + 1);
                             const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
                             sp = tile_row_span(sc, rects[gg], ty, v);
                         }
@@ -480,7 +566,7 @@ __global__ void __launch_bounds__(kBinThreads)
                                 before += static_cast<unsigned int>(max(t.y - t.x, 0));
                             }
                             if (j > kSpanRows) {
-                                const float4 r0 = __ldg(records + 3 * gg), r1 = __ldg(records + 3 * gg + 1);
+                                const float4 r0 = __ldg(records + 4 * gg), r1 = __ldg(records + 4 * gg + 1);
                                 const SpanCoef sc = span_coef(r0.x, r0.y, r0.z, r0.w, r1.x, d2max, no_cull);
                                 const int4 rr = rects[gg];
                                 for (int jj = kSpanRows; jj < j; ++jj) {
@@ -631,296 +717,489 @@ __global__ void __launch_bounds__(256)
 struct ToU64 {
     __host__ __device__ unsigned long long operator()(unsigned int x) const { return x; }
 };
-using TouchedIter = cub::TransformInputIterator<unsigned long long, ToU64, const unsigned int*>;
-
-struct LastLaunch {
-    bool valid = false;
-    SplatView view{};
-    SplatBuffers buf{};
-    long long entries = 0;       // list length; -1: not known on the host yet (XYZ_FLAG_ASYNC launch)
-    long long known_entries = 0;  // most recent length the host has seen for this scene shape
-    long long capacity = 0;      // XYZ_FLAG_ASYNC: the length the entry-sized buffers were sized for
-    const unsigned long long* total_dev = nullptr;  // device: {list length, overflow counter}
-    long long stats[4] = {0, 0, 0, 0};
-};
-thread_local LastLaunch g_last;
-// XYZ_FLAG_ASYNC: pinned-host mirror of {list length, overflow counter}, refreshed by every launch without a
-// synchronisation; read at the next call (whatever has arrived by then is a valid earlier value).
-thread_local volatile unsigned long long* g_mirror = nullptr;
-thread_local unsigned long long g_overflows_seen = 0;
+using TouchedIter = cub::TransformInputIterator<unsigned long long, ToU64, const unsigned int*>;  // radix path only
 
 inline size_t align_up(size_t x, size_t a = 256) { return (x + a - 1) / a * a; }
 
-int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients, const float* target,
-                 float* output, float* total_loss, int W, int H, int N, int row_begin, int row_end, void* stream,
-                 int flags) {
-    if (W <= 0 || H <= 0 || N < 0 || row_begin < 0 || row_end > H || row_begin > row_end) return XYZ_ERR_INVALID_ARGUMENT;
-    if (!target || !output || !total_loss || (N > 0 && (!gaussians || !gradients))) return XYZ_ERR_INVALID_ARGUMENT;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const bool precise = (flags & XYZ_FLAG_PRECISE_MATH) != 0;
-    const bool deterministic = (flags & XYZ_FLAG_DETERMINISTIC) != 0;
-    const int no_cull = (flags & XYZ_FLAG_NO_CULL) ? 1 : 0;
+// ---- the plan of one launch: what runs and where every buffer lives --------------------------------------------------
+// A workspace is  [header 256 B][fixed part: depends on N, the image and the chunking][entry part: depends on the list
+// capacity].  The library-owned scratch of the classic entry points keeps the two parts in two arenas (the entry part
+// grows with the scene); xyz_launch_gaussian_splatting_ws lays both out in the caller's buffer.
+constexpr size_t kHeaderBytes = 256;  // u64 {list length, overflow counter (sticky), ticket, capacity of that launch}
 
+struct SplatPlan {
     SplatView v;
-    v.width = W; v.height = H; v.num_gaussians = N;
-    v.row_begin = row_begin; v.row_end = row_end;
-    v.tiles_x = (W + kTile - 1) / kTile;
-    v.tiles_y = (H + kTile - 1) / kTile;
-    const int n_tiles = v.tiles_x * v.tiles_y;
-    const int ng = N > 0 ? N : 1;
+    int n_tiles;             // whole image
+    int tile0, n_tiles_l;    // tiles of the launch's row band: global ids [tile0, tile0 + n_tiles_l)
+    bool counting, deterministic, precise;
+    int no_cull;
+    float d2max;
+    int chunk_size, n_chunks;
+    size_t o_rec, o_rect, o_touched, o_spans, o_offsets, o_ranges, o_tloss, o_chunks, o_rest, o_hist, o_ttotal, o_ctotal,
+        o_cbase, o_scan_tmp;
+    size_t scan_tmp_bytes;
+    size_t fixed_bytes;  // without the header
+};
 
-    // binning: stable counting sort by tile (default) or, for very large tile counts / on request, the radix path
+struct EntryLayout {
+    size_t o_kin, o_kout, o_vin, o_vout, o_gid, o_cinfo, o_eg, o_sort_tmp;
+    size_t sort_tmp_bytes;
+    size_t bytes;
+    int key_bits;
+    int chunk_info_size;
+};
+
+// predicted_entries: only a tuning input (CTAs per SM of the counting sort); never changes a result bit.
+int make_plan(SplatPlan& p, int W, int H, int N, int row_begin, int row_end, int flags, long long predicted_entries,
+              cudaStream_t st) {
+    if (W <= 0 || H <= 0 || N < 0 || row_begin < 0 || row_end > H || row_begin > row_end) return XYZ_ERR_INVALID_ARGUMENT;
+    p.v.width = W; p.v.height = H; p.v.num_gaussians = N;
+    p.v.row_begin = row_begin; p.v.row_end = row_end;
+    p.v.tiles_x = (W + kTile - 1) / kTile;
+    p.v.tiles_y = (H + kTile - 1) / kTile;
+    p.n_tiles = p.v.tiles_x * p.v.tiles_y;
+    p.precise = (flags & XYZ_FLAG_PRECISE_MATH) != 0;
+    p.deterministic = (flags & XYZ_FLAG_DETERMINISTIC) != 0;
+    p.no_cull = (flags & XYZ_FLAG_NO_CULL) ? 1 : 0;
+    p.d2max = (flags & XYZ_FLAG_TAIL_CULL) ? kD2MaxTail : (p.precise ? kD2MaxPrecise : kD2MaxFast);
+    const int ty_lo = row_begin / kTile, ty_hi = (row_end + kTile - 1) / kTile;
+    const int band_tiles = (ty_hi - ty_lo) * p.v.tiles_x;
+    if (band_tiles <= 0) p.v.num_gaussians = N = 0;  // an empty row band renders nothing: no kernel has work
+    // binning: stable counting sort by tile (default) or, for very large tile counts / on request, the radix path.
     // The counting sort appends 4 bytes at a time to n_chunks x n_tiles output streams; it is fast as long as the open
     // 32-byte sectors of all streams stay in L2 until they are complete, so long lists get fewer, longer chunks
     // (measured at 1024^2, dev/splat_knob3m.sh: 4 CTAs per SM win up to ~3e7 entries, 1 per SM beyond -- at 1.2e8
-    // entries 4 per SM are 0.8 ms SLOWER than 1 per SM and lose to the radix sort).  The list length is not known yet:
-    // predicted from this thread's previous launch of the same scene shape, else from N.  Whatever is chosen, the
-    // lists are the same bit for bit.
-    const long long predicted = (g_last.valid && g_last.view.num_gaussians == N && g_last.view.width == W &&
-                                 g_last.view.height == H && g_last.view.row_begin == row_begin && g_last.view.row_end == row_end &&
-                                 g_last.known_entries > 0)
-                                    ? g_last.known_entries
-                                    : static_cast<long long>(N) * 40;
-    const bool counting = !(flags & XYZ_FLAG_RADIX_BINNING) && n_tiles <= kBinMaxTiles;
-    const bool same_shape = g_last.valid && g_last.view.num_gaussians == N && g_last.view.width == W &&
-                            g_last.view.height == H && g_last.view.row_begin == row_begin && g_last.view.row_end == row_end;
-    // XYZ_FLAG_ASYNC: what an earlier sync-free launch reported meanwhile (list length, overflows)
-    if (g_mirror) {
-        const unsigned long long seen_total = g_mirror[0], seen_overflows = g_mirror[1];
-        if (same_shape && g_last.entries < 0 && seen_total != 0ull) g_last.known_entries = static_cast<long long>(seen_total);
-        if (seen_overflows != g_overflows_seen) {
-            g_overflows_seen = seen_overflows;
-            g_last.capacity = 0;  // sized afresh from the reported length
-            return XYZ_ERR_WORKSPACE;  // an earlier XYZ_FLAG_ASYNC launch was longer than its buffers: its outputs are void
-        }
-    }
-    // sync-free launch: needs the counting sort (no host-side item counts) and a known length of this scene shape
-    const bool async = (flags & XYZ_FLAG_ASYNC) && counting && !deterministic && N > 0 && same_shape &&
-                       g_last.known_entries > 0;
-    long long capacity = 0;
-    if (async) {
-        capacity = g_last.known_entries + g_last.known_entries / 2 + 4096;
-        if (g_last.capacity >= g_last.known_entries + g_last.known_entries / 8) capacity = g_last.capacity;  // keep the buffers
-        if (capacity >= (1LL << 31) - 512) return XYZ_ERR_WORKSPACE;
-    }
-    int chunk_size = kBinBatch, n_chunks = 1;
-    if (counting) {
+    // entries 4 per SM are 0.8 ms SLOWER than 1 per SM and lose to the radix sort).
+    p.counting = !(flags & XYZ_FLAG_RADIX_BINNING) && band_tiles <= kBinMaxTiles;
+    p.tile0 = p.counting ? ty_lo * p.v.tiles_x : 0;
+    p.n_tiles_l = p.counting ? band_tiles : p.n_tiles;
+    const int ng = N > 0 ? N : 1;
+    p.chunk_size = kBinBatch;
+    p.n_chunks = 1;
+    if (p.counting) {
         static const int forced = [] {  // tuning knob: CTAs of the count / scatter kernels per SM
             const char* e = std::getenv("XYZ_SPLAT_BIN_CTAS_PER_SM");
             const int x = e ? std::atoi(e) : 0;
             return x > 0 && x <= 64 ? x : 0;
         }();
-        const int per_sm = forced ? forced : (predicted <= kBinLongList ? 4 : 1);
+        const int per_sm = forced ? forced : (predicted_entries <= kBinLongList ? 4 : 1);
         const int want = per_sm * sm_count();
-        chunk_size = ((ng + want - 1) / want + kBinBatch - 1) / kBinBatch * kBinBatch;
-        n_chunks = (ng + chunk_size - 1) / chunk_size;
+        p.chunk_size = ((ng + want - 1) / want + kBinBatch - 1) / kBinBatch * kBinBatch;
+        p.n_chunks = (ng + p.chunk_size - 1) / p.chunk_size;
     }
-    const float d2max = (flags & XYZ_FLAG_TAIL_CULL) ? kD2MaxTail : (precise ? kD2MaxPrecise : kD2MaxFast);
-
-    // ---- fixed-size scratch (depends on N and the tile count only)
     size_t off = 0;
     auto take = [&off](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
-    // {list length, overflow counter, ticket} come FIRST: the overflow counter is sticky across launches, so its place
-    // must not move with the scene shape (a fresh arena is zero-filled, common.cu)
-    const size_t o_total = take(4 * sizeof(unsigned long long));
-    const size_t o_rec = take(sizeof(float4) * 3 * ng), o_rect = take(sizeof(int4) * ng),
-                 o_touched = take(sizeof(unsigned int) * ng), o_spans = take(sizeof(int2) * kSpanRows * ng), o_offsets = take(sizeof(unsigned long long) * ng),
-                 o_ranges = take(sizeof(int2) * n_tiles), o_tloss = take(sizeof(float) * n_tiles),
-                 o_chunks = take(sizeof(int) * (n_tiles + 1)),
-                 o_rest = take(sizeof(float4) * kTilePixels * static_cast<size_t>(n_tiles)),
-                 o_hist = take(counting ? sizeof(unsigned int) * static_cast<size_t>(n_chunks) * n_tiles : 0),
-                 o_ttotal = take(sizeof(unsigned int) * n_tiles);
-    size_t scan_tmp_bytes = 0;
-    cub::DeviceScan::InclusiveSum(nullptr, scan_tmp_bytes, TouchedIter(nullptr, ToU64()),
-                                  static_cast<unsigned long long*>(nullptr), ng, st);
-    const size_t o_scan_tmp = take(scan_tmp_bytes + 16);
-    unsigned char* base = nullptr;
-    int err = scratch_get(SCRATCH_SPLAT, off, reinterpret_cast<void**>(&base));
-    if (err) return err;
-    SplatBuffers b{};
-    b.records = reinterpret_cast<float4*>(base + o_rec);
-    b.rects = reinterpret_cast<int4*>(base + o_rect);
-    b.touched = reinterpret_cast<unsigned int*>(base + o_touched);
-    b.spans = reinterpret_cast<int2*>(base + o_spans);
-    b.offsets = reinterpret_cast<unsigned long long*>(base + o_offsets);
-    b.tile_ranges = reinterpret_cast<int2*>(base + o_ranges);
-    b.tile_loss = reinterpret_cast<float*>(base + o_tloss);
-    b.chunk_offsets = reinterpret_cast<int*>(base + o_chunks);
-    b.rest_tiles = reinterpret_cast<float4*>(base + o_rest);
-    unsigned int* hist = reinterpret_cast<unsigned int*>(base + o_hist);
-    unsigned int* tile_total = reinterpret_cast<unsigned int*>(base + o_ttotal);
-    unsigned long long* total_dev = reinterpret_cast<unsigned long long*>(base + o_total);
-    unsigned int* ticket = reinterpret_cast<unsigned int*>(total_dev + 2);
+    const size_t nl = static_cast<size_t>(p.n_tiles_l > 0 ? p.n_tiles_l : 1);
+    p.o_rec = take(sizeof(float4) * 4 * ng);
+    p.o_rect = take(sizeof(int4) * ng);
+    p.o_touched = take(sizeof(unsigned int) * ng);
+    p.o_spans = take(sizeof(int2) * kSpanRows * ng);
+    p.o_offsets = take((p.deterministic || !p.counting) ? sizeof(unsigned long long) * ng : 0);
+    p.o_ranges = take(sizeof(int2) * p.n_tiles);
+    p.o_tloss = take(sizeof(float) * p.n_tiles);
+    p.o_chunks = take(sizeof(int) * (nl + 1));
+    p.o_rest = take(sizeof(float4) * kTilePixels * static_cast<size_t>(p.n_tiles));
+    p.o_hist = take(p.counting ? sizeof(unsigned int) * static_cast<size_t>(p.n_chunks) * nl : 0);
+    p.o_ttotal = take(sizeof(unsigned int) * nl);
+    p.o_ctotal = take(sizeof(unsigned int) * p.n_chunks);
+    p.o_cbase = take(sizeof(unsigned long long) * p.n_chunks);
+    p.scan_tmp_bytes = 0;
+    if (!p.counting)
+        cub::DeviceScan::InclusiveSum(nullptr, p.scan_tmp_bytes, TouchedIter(nullptr, ToU64()),
+                                      static_cast<unsigned long long*>(nullptr), ng, st);
+    p.o_scan_tmp = take(p.counting ? 0 : p.scan_tmp_bytes + 16);
+    p.fixed_bytes = off;
+    return 0;
+}
 
-    cudaError_t ce = cudaMemsetAsync(b.tile_ranges, 0, sizeof(int2) * n_tiles, st);
-    if (ce != cudaSuccess) return static_cast<int>(ce);
-
-    long long entries = 0;
-    if (N > 0) {
-        if (counting)
-            splat_preprocess_kernel<true><<<n_chunks, 256, sizeof(unsigned int) * n_tiles, st>>>(
-                v, gaussians, b.records, b.rects, b.touched, b.spans, d2max, no_cull, chunk_size, n_tiles, hist, ticket);
-        else
-            splat_preprocess_kernel<false><<<(N + 255) / 256, 256, 0, st>>>(
-                v, gaussians, b.records, b.rects, b.touched, b.spans, d2max, no_cull, 0, 0, nullptr, nullptr);
-        count_launch();
-        if (!counting || deterministic) {  // positions in Gaussian order: radix keys / rows of entry_grads
-            ce = cub::DeviceScan::InclusiveSum(base + o_scan_tmp, scan_tmp_bytes, TouchedIter(b.touched, ToU64()),
-                                               b.offsets, N, st);
-            if (ce != cudaSuccess) return static_cast<int>(ce);
-            count_launch();
-        }
-        const unsigned long long* total_src = b.offsets + (N - 1);
-        if (counting) {
-            splat_bin_colscan_kernel<<<(n_tiles + 31) / 32, dim3(32, 32), 0, st>>>(
-                hist, n_chunks, n_tiles, tile_total, ticket, b.tile_ranges, b.chunk_offsets, total_dev,
-                static_cast<unsigned long long>(capacity), g_overflows_seen);
-            count_launch();
-            total_src = total_dev;
-        }
-        if (async) {
-            // no read-back: the buffers are sized for `capacity`; the length goes to the pinned mirror for later calls
-            if (!g_mirror) {
-                void* m = nullptr;
-                ce = cudaHostAlloc(&m, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
-                if (ce != cudaSuccess) return static_cast<int>(ce);
-                g_mirror = static_cast<volatile unsigned long long*>(m);
-                g_mirror[0] = 0ull;
-                g_mirror[1] = g_overflows_seen;
-            }
-            ce = cudaMemcpyAsync(const_cast<unsigned long long*>(g_mirror), total_dev, 2 * sizeof(unsigned long long),
-                                 cudaMemcpyDeviceToHost, st);
-            if (ce != cudaSuccess) return static_cast<int>(ce);
-            entries = capacity;
-        } else {
-        // the list length is data dependent: one 8-byte read-back (the only synchronisation)
-        unsigned long long total = 0;
-        ce = cudaMemcpyAsync(&total, total_src, sizeof(total), cudaMemcpyDeviceToHost, st);
-        if (ce != cudaSuccess) return static_cast<int>(ce);
-        ce = cudaStreamSynchronize(st);
-        if (ce != cudaSuccess) return static_cast<int>(ce);
-        entries = static_cast<long long>(total);
-        }
-    }
-    if (entries >= (1LL << 31) - 512) return XYZ_ERR_WORKSPACE;
-
-    // ---- entry-sized scratch (counting sort: 4 bytes per entry; radix: keys + payload, ping-pong)
-    int key_bits = 1;
-    while ((1 << key_bits) < n_tiles) ++key_bits;
-    const long long ne = entries > 0 ? entries : 1;
+// capacity = list entries the entry part is laid out for
+EntryLayout make_entry_layout(const SplatPlan& p, long long capacity, cudaStream_t st) {
+    EntryLayout L{};
+    L.key_bits = 1;
+    while ((1 << L.key_bits) < p.n_tiles) ++L.key_bits;
+    const long long ne = capacity > 0 ? capacity : 1;
     size_t soff = 0;
     auto stake = [&soff](size_t bytes) { size_t o = soff; soff += align_up(bytes); return o; };
-    const size_t o_kin = stake(counting ? 0 : 4 * ne), o_kout = stake(counting ? 0 : 4 * ne), o_vin = stake(counting ? 0 : 4 * ne),
-                 o_vout = stake(4 * ne), o_gid = stake(deterministic ? 4 * ne : 0),
-                 o_cinfo = stake(sizeof(int4) * static_cast<size_t>(ne / kBwdChunk + n_tiles)), o_eg = stake(deterministic ? 36 * ne : 0);
-    size_t sort_tmp_bytes = 0;
-    if (!counting)
-        cub::DeviceRadixSort::SortPairs(nullptr, sort_tmp_bytes, static_cast<unsigned int*>(nullptr),
+    L.o_kin = stake(p.counting ? 0 : 4 * ne);
+    L.o_kout = stake(p.counting ? 0 : 4 * ne);
+    L.o_vin = stake(p.counting ? 0 : 4 * ne);
+    L.o_vout = stake(4 * ne);
+    L.o_gid = stake(p.deterministic ? 4 * ne : 0);
+    L.chunk_info_size = static_cast<int>(capacity / kBwdChunk + p.n_tiles_l);
+    L.o_cinfo = stake(sizeof(int4) * static_cast<size_t>(ne / kBwdChunk + p.n_tiles_l));
+    L.o_eg = stake(p.deterministic ? 36 * ne : 0);
+    L.sort_tmp_bytes = 0;
+    if (!p.counting)
+        cub::DeviceRadixSort::SortPairs(nullptr, L.sort_tmp_bytes, static_cast<unsigned int*>(nullptr),
                                         static_cast<unsigned int*>(nullptr), static_cast<unsigned int*>(nullptr),
-                                        static_cast<unsigned int*>(nullptr), static_cast<int>(ne), 0, key_bits, st);
-    const size_t o_sort_tmp = stake(sort_tmp_bytes + 16);
-    unsigned char* sbase = nullptr;
-    err = scratch_get(SCRATCH_SPLAT_SORT, soff, reinterpret_cast<void**>(&sbase));
-    if (err) return err;
-    b.keys_in = reinterpret_cast<unsigned int*>(sbase + o_kin);
-    b.keys_out = reinterpret_cast<unsigned int*>(sbase + o_kout);
-    b.vals_in = reinterpret_cast<unsigned int*>(sbase + o_vin);
-    b.vals_out = reinterpret_cast<unsigned int*>(sbase + o_vout);
+                                        static_cast<unsigned int*>(nullptr), static_cast<int>(ne), 0, L.key_bits, st);
+    L.o_sort_tmp = stake(p.counting ? 0 : L.sort_tmp_bytes + 16);
+    L.bytes = soff;
+    return L;
+}
+
+// XYZ_FLAG_TIMING: CUDA events between the stages of a launch (a measuring aid: the events cost a little themselves)
+struct StageEvents {
+    cudaEvent_t ev[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};  // begin | preprocess | scans | scatter | forward | backward
+    bool armed = false;
+    int ensure() {
+        for (auto& e : ev)
+            if (!e) {
+                cudaError_t ce = cudaEventCreate(&e);
+                if (ce != cudaSuccess) return static_cast<int>(ce);
+            }
+        return 0;
+    }
+};
+inline void mark(StageEvents* t, int i, cudaStream_t st) {
+    if (t) cudaEventRecord(t->ev[i], st);
+}
+
+struct Bound {  // a plan bound to memory
+    SplatBuffers b{};
+    unsigned long long* header = nullptr;  // {list length, overflow counter, ticket, capacity}
+    unsigned int* hist = nullptr;
+    unsigned int* tile_total = nullptr;
+    unsigned int* chunk_total = nullptr;
+    unsigned long long* chunk_base = nullptr;
+    unsigned char* scan_tmp = nullptr;
+    unsigned char* sort_tmp = nullptr;
+};
+
+void bind_fixed(const SplatPlan& p, unsigned char* header, unsigned char* base, Bound& o) {
+    o.header = reinterpret_cast<unsigned long long*>(header);
+    o.b.records = reinterpret_cast<float4*>(base + p.o_rec);
+    o.b.rects = reinterpret_cast<int4*>(base + p.o_rect);
+    o.b.touched = reinterpret_cast<unsigned int*>(base + p.o_touched);
+    o.b.spans = reinterpret_cast<int2*>(base + p.o_spans);
+    o.b.offsets = reinterpret_cast<unsigned long long*>(base + p.o_offsets);
+    o.b.tile_ranges = reinterpret_cast<int2*>(base + p.o_ranges);
+    o.b.tile_loss = reinterpret_cast<float*>(base + p.o_tloss);
+    o.b.chunk_offsets = reinterpret_cast<int*>(base + p.o_chunks);
+    o.b.rest_tiles = reinterpret_cast<float4*>(base + p.o_rest);
+    o.hist = reinterpret_cast<unsigned int*>(base + p.o_hist);
+    o.tile_total = reinterpret_cast<unsigned int*>(base + p.o_ttotal);
+    o.chunk_total = reinterpret_cast<unsigned int*>(base + p.o_ctotal);
+    o.chunk_base = reinterpret_cast<unsigned long long*>(base + p.o_cbase);
+    o.scan_tmp = base + p.o_scan_tmp;
+}
+
+void bind_entry(const SplatPlan& p, const EntryLayout& L, unsigned char* sbase, Bound& o) {
+    o.b.keys_in = reinterpret_cast<unsigned int*>(sbase + L.o_kin);
+    o.b.keys_out = reinterpret_cast<unsigned int*>(sbase + L.o_kout);
+    o.b.vals_in = reinterpret_cast<unsigned int*>(sbase + L.o_vin);
+    o.b.vals_out = reinterpret_cast<unsigned int*>(sbase + L.o_vout);
     // fast mode: the sort payload is the Gaussian id; deterministic mode: payload = entry position, ids kept apart
-    b.sorted_gid = deterministic ? reinterpret_cast<int*>(sbase + o_gid) : reinterpret_cast<int*>(b.vals_out);
-    b.entry_grads = deterministic ? reinterpret_cast<float*>(sbase + o_eg) : nullptr;
-    b.chunk_info = reinterpret_cast<int4*>(sbase + o_cinfo);
+    o.b.sorted_gid = p.deterministic ? reinterpret_cast<int*>(sbase + L.o_gid) : reinterpret_cast<int*>(o.b.vals_out);
+    o.b.entry_grads = p.deterministic ? reinterpret_cast<float*>(sbase + L.o_eg) : nullptr;
+    o.b.chunk_info = reinterpret_cast<int4*>(sbase + L.o_cinfo);
+    o.sort_tmp = sbase + L.o_sort_tmp;
+}
 
-    const int chunk_info_size = static_cast<int>(entries / kBwdChunk + n_tiles);
-    if (entries > 0) {
-        if (counting) {
-            const size_t smem = sizeof(unsigned int) * n_tiles;  // <= 32 KB (kBinMaxTiles)
-            if (deterministic)
-                splat_bin_scatter_kernel<true><<<n_chunks, kBinThreads, smem, st>>>(
-                    v, b.records, b.rects, b.spans, b.touched, b.offsets, chunk_size, n_tiles, hist, b.tile_ranges,
-                    b.vals_out, b.sorted_gid, d2max, no_cull, b.chunk_offsets, b.chunk_info, chunk_info_size, total_dev, 0ull);
-            else
-                splat_bin_scatter_kernel<false><<<n_chunks, kBinThreads, smem, st>>>(
-                    v, b.records, b.rects, b.spans, b.touched, nullptr, chunk_size, n_tiles, hist, b.tile_ranges,
-                    b.vals_out, nullptr, d2max, no_cull, b.chunk_offsets, b.chunk_info, chunk_info_size, total_dev,
-                    static_cast<unsigned long long>(capacity));
-            count_launch();
-        } else {
-            splat_emit_keys_kernel<<<(N + 15) / 16, 256, 0, st>>>(v, b.records, b.rects, b.touched, b.offsets, b.spans,
-                                                                  b.keys_in, b.vals_in, d2max, no_cull, deterministic ? 0 : 1);
-            count_launch();
-            ce = cub::DeviceRadixSort::SortPairs(sbase + o_sort_tmp, sort_tmp_bytes, b.keys_in, b.keys_out, b.vals_in,
-                                                 b.vals_out, static_cast<int>(entries), 0, key_bits, st);
-            if (ce != cudaSuccess) return static_cast<int>(ce);
-            count_launch(3);
-            splat_ranges_kernel<<<static_cast<unsigned int>((entries + 255) / 256), 256, 0, st>>>(
-                entries, b.keys_out, b.vals_out, b.offsets, N, b.tile_ranges, deterministic ? b.sorted_gid : nullptr);
-            splat_chunk_scan_kernel<<<1, 1024, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets);
-            count_launch(2);
-        }
-        if (!counting) {
-            // surplus backward CTAs (the grid is an upper bound) read tile = -1
-            ce = cudaMemsetAsync(b.chunk_info, 0xff, sizeof(int4) * static_cast<size_t>(chunk_info_size), st);
-            if (ce != cudaSuccess) return static_cast<int>(ce);
-            splat_chunk_fill_kernel<<<(n_tiles + 255) / 256, 256, 0, st>>>(b.tile_ranges, n_tiles, b.chunk_offsets, b.chunk_info);
-            count_launch();
-        }
+// ---- front half: records, rectangles, histograms, tile ranges, the list length (on the device) -----------------------
+// capacity != 0: the entry part holds `capacity` entries and nobody will look at the length before the back half runs
+// (sync-free launches): a longer list is published EMPTY and the header's overflow counter goes up.
+int enqueue_front(const SplatPlan& p, const Bound& o, const xyz_gaussian_params* gaussians, unsigned long long capacity,
+                  unsigned long long overflow_base, cudaStream_t st, const unsigned long long** total_src,
+                  StageEvents* tm) {
+    const int N = p.v.num_gaussians;
+    *total_src = o.header;
+    mark(tm, 0, st);
+    if (N <= 0) {
+        mark(tm, 1, st);
+        mark(tm, 2, st);
+        return 0;
     }
-
-    err = precise ? splat_forward_launch_precise(v, b, target, output, st)
-                  : splat_forward_launch_fast(v, b, target, output, st);
-    if (err) return err;
-    {
-        const int ty0 = row_begin / kTile, ty1 = (row_end + kTile - 1) / kTile;
-        if (ty1 > ty0) {
-            splat_loss_finish_kernel<<<1, 256, 0, st>>>(b.tile_loss, ty0 * v.tiles_x, ty1 * v.tiles_x, total_loss);
-            count_launch();
-        }
-    }
-    err = precise ? splat_backward_launch_precise(v, b, gaussians, gradients, target, output, entries, deterministic, st)
-                  : splat_backward_launch_fast(v, b, gaussians, gradients, target, output, entries, deterministic, st);
-    if (err) return err;
-    if (deterministic && entries > 0) {
-        splat_grads_finish_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, b.touched, b.offsets, b.entry_grads, gradients);
+    if (p.counting) {
+        splat_preprocess_kernel<true><<<p.n_chunks, 256, sizeof(unsigned int) * p.n_tiles_l, st>>>(
+            p.v, gaussians, o.b.records, o.b.rects, o.b.touched, o.b.spans, p.d2max, p.no_cull, p.chunk_size, p.n_tiles_l,
+            o.hist, reinterpret_cast<unsigned int*>(o.header + 2), o.chunk_total);
         count_launch();
+        mark(tm, 1, st);
+        splat_bin_colscan_kernel<<<(p.n_tiles_l + 31) / 32, dim3(32, 32), 0, st>>>(
+            o.hist, p.n_chunks, p.n_tiles_l, o.tile_total, reinterpret_cast<unsigned int*>(o.header + 2),
+            o.b.tile_ranges + p.tile0, o.b.chunk_offsets, o.header, capacity, overflow_base, o.chunk_total,
+            p.deterministic ? o.chunk_base : nullptr);
+        count_launch();
+        mark(tm, 2, st);
+        return last_error();
     }
-
-    const long long known_before = same_shape ? g_last.known_entries : 0;
-    g_last.valid = true;
-    g_last.view = v;
-    g_last.buf = b;
-    g_last.entries = async ? -1 : entries;
-    g_last.known_entries = async ? known_before : entries;
-    g_last.capacity = async ? capacity : 0;
-    g_last.total_dev = total_dev;
-    g_last.stats[0] = g_last.entries;
-    g_last.stats[1] = n_tiles;
-    g_last.stats[2] = -1;  // longest list: filled lazily by xyz_splat_last_stats
-    g_last.stats[3] = g_last.entries * kTilePixels;
+    // radix path: positions in Gaussian order come from a library scan (more than kBinMaxTiles tiles / on request)
+    cudaError_t ce = cudaMemsetAsync(o.b.tile_ranges, 0, sizeof(int2) * p.n_tiles, st);  // empty tiles: (0, 0)
+    if (ce != cudaSuccess) return static_cast<int>(ce);
+    splat_preprocess_kernel<false><<<(N + 255) / 256, 256, 0, st>>>(p.v, gaussians, o.b.records, o.b.rects, o.b.touched,
+                                                                    o.b.spans, p.d2max, p.no_cull, 0, 0, nullptr, nullptr,
+                                                                    nullptr);
+    count_launch();
+    mark(tm, 1, st);
+    size_t tmp = p.scan_tmp_bytes;
+    ce = cub::DeviceScan::InclusiveSum(o.scan_tmp, tmp, TouchedIter(o.b.touched, ToU64()), o.b.offsets, N, st);
+    if (ce != cudaSuccess) return static_cast<int>(ce);
+    count_launch();
+    mark(tm, 2, st);
+    *total_src = o.b.offsets + (N - 1);
     return last_error();
 }
 
-// After a XYZ_FLAG_ASYNC launch the host does not know the list length: fetch it (synchronises the device).
+// ---- back half: lists, forward, loss, backward ------------------------------------------------------------------------
+// entries: the list length where the host knows it (radix path: must), else the capacity the buffers were sized for.
+int enqueue_back(const SplatPlan& p, const EntryLayout& L, const Bound& o, const xyz_gaussian_params* gaussians,
+                 xyz_gaussian_grads* gradients, const float* target, float* output, float* total_loss, long long entries,
+                 unsigned long long capacity, cudaStream_t st, StageEvents* tm) {
+    const int N = p.v.num_gaussians;
+    const SplatBuffers& b = o.b;
+    if (entries > 0) {
+        if (p.counting) {
+            const size_t smem = sizeof(unsigned int) * p.n_tiles_l;  // <= 32 KB (kBinMaxTiles)
+            if (p.deterministic)
+                splat_bin_scatter_kernel<true><<<p.n_chunks, kBinThreads, smem, st>>>(
+                    p.v, b.records, b.rects, b.spans, b.touched, b.offsets, p.chunk_size, p.n_tiles_l, p.tile0, o.hist,
+                    b.tile_ranges + p.tile0, b.vals_out, b.sorted_gid, p.d2max, p.no_cull, b.chunk_offsets, b.chunk_info,
+                    L.chunk_info_size, o.header, capacity, o.chunk_base);
+            else
+                splat_bin_scatter_kernel<false><<<p.n_chunks, kBinThreads, smem, st>>>(
+                    p.v, b.records, b.rects, b.spans, b.touched, nullptr, p.chunk_size, p.n_tiles_l, p.tile0, o.hist,
+                    b.tile_ranges + p.tile0, b.vals_out, nullptr, p.d2max, p.no_cull, b.chunk_offsets, b.chunk_info,
+                    L.chunk_info_size, o.header, capacity, nullptr);
+            count_launch();
+        } else {
+            splat_emit_keys_kernel<<<(N + 15) / 16, 256, 0, st>>>(p.v, b.records, b.rects, b.touched, b.offsets, b.spans,
+                                                                  b.keys_in, b.vals_in, p.d2max, p.no_cull,
+                                                                  p.deterministic ? 0 : 1);
+            count_launch();
+            size_t tmp = L.sort_tmp_bytes;
+            cudaError_t ce = cub::DeviceRadixSort::SortPairs(o.sort_tmp, tmp, b.keys_in, b.keys_out, b.vals_in, b.vals_out,
+                                                             static_cast<int>(entries), 0, L.key_bits, st);
+            if (ce != cudaSuccess) return static_cast<int>(ce);
+            count_launch(3);
+            splat_ranges_kernel<<<static_cast<unsigned int>((entries + 255) / 256), 256, 0, st>>>(
+                entries, b.keys_out, b.vals_out, b.offsets, N, b.tile_ranges, p.deterministic ? b.sorted_gid : nullptr);
+            splat_chunk_scan_kernel<<<1, 1024, 0, st>>>(b.tile_ranges, p.n_tiles, b.chunk_offsets);
+            count_launch(2);
+            // surplus backward CTAs (the grid is an upper bound) read tile = -1
+            ce = cudaMemsetAsync(b.chunk_info, 0xff, sizeof(int4) * static_cast<size_t>(L.chunk_info_size), st);
+            if (ce != cudaSuccess) return static_cast<int>(ce);
+            splat_chunk_fill_kernel<<<(p.n_tiles + 255) / 256, 256, 0, st>>>(b.tile_ranges, p.n_tiles, b.chunk_offsets,
+                                                                           b.chunk_info);
+            count_launch();
+        }
+    } else if (p.counting && N > 0) {
+        // no entries: the column scan has published empty ranges for the band already
+    } else {
+        const int ty0 = p.v.row_begin / kTile, ty1 = (p.v.row_end + kTile - 1) / kTile;
+        if (ty1 > ty0) {
+            cudaError_t ce = cudaMemsetAsync(b.tile_ranges + ty0 * p.v.tiles_x, 0,
+                                             sizeof(int2) * static_cast<size_t>(ty1 - ty0) * p.v.tiles_x, st);
+            if (ce != cudaSuccess) return static_cast<int>(ce);
+        }
+    }
+    mark(tm, 3, st);
+    int err = p.precise ? splat_forward_launch_precise(p.v, b, target, output, st)
+                        : splat_forward_launch_fast(p.v, b, target, output, st);
+    if (err) return err;
+    {
+        const int ty0 = p.v.row_begin / kTile, ty1 = (p.v.row_end + kTile - 1) / kTile;
+        if (ty1 > ty0) {
+            splat_loss_finish_kernel<<<1, 256, 0, st>>>(b.tile_loss, ty0 * p.v.tiles_x, ty1 * p.v.tiles_x, total_loss);
+            count_launch();
+        }
+    }
+    mark(tm, 4, st);
+    const long long bwd_ctas = entries > 0 ? static_cast<long long>(L.chunk_info_size) : 0;
+    err = p.precise ? splat_backward_launch_precise(p.v, b, gradients, bwd_ctas, p.deterministic, st)
+                    : splat_backward_launch_fast(p.v, b, gradients, bwd_ctas, p.deterministic, st);
+    if (err) return err;
+    if (p.deterministic && entries > 0) {
+        splat_grads_finish_kernel<<<(N + 255) / 256, 256, 0, st>>>(N, b.touched, b.offsets, b.entry_grads, gradients);
+        count_launch();
+    }
+    mark(tm, 5, st);
+    return last_error();
+}
+
+// ---- what the classic entry points remember between launches, per (device, stream) -------------------------------------
+struct SplatState {
+    bool valid = false;
+    bool external = false;       // buffers live in a caller-provided workspace (no generation to check)
+    SplatView view{};
+    SplatBuffers buf{};
+    long long entries = 0;       // list length; -1: not known on the host yet (sync-free launch)
+    long long known_entries = 0;  // most recent length the host has seen for this scene shape
+    long long capacity = 0;      // sync-free launches: the length the entry part was sized for
+    const unsigned long long* header = nullptr;
+    long long stats[4] = {0, 0, 0, 0};
+    uint64_t gen_fixed = 0, gen_entry = 0;
+    cudaStream_t stream = nullptr;
+    // XYZ_FLAG_ASYNC: pinned-host mirror of {list length, overflow counter}, refreshed by every launch without a
+    // synchronisation; read at the next call (whatever has arrived by then is a valid earlier value)
+    volatile unsigned long long* mirror = nullptr;
+    unsigned long long overflows_seen = 0;
+    StageEvents timing;
+};
+std::mutex g_state_mu;
+std::map<std::pair<int, cudaStream_t>, SplatState> g_states;  // node addresses are stable
+thread_local SplatState* g_last = nullptr;                     // the state this host thread launched on last
+thread_local SplatState g_last_ws;                             // ... or its last workspace launch
+
+SplatState* state_for(cudaStream_t st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(g_state_mu);
+    return &g_states[{dev, st}];
+}
+
+bool state_usable(const SplatState* s) {
+    if (!s || !s->valid) return false;
+    if (s->external) return true;
+    return scratch_is_current(SCRATCH_SPLAT, s->stream, s->gen_fixed) &&
+           scratch_is_current(SCRATCH_SPLAT_SORT, s->stream, s->gen_entry);
+}
+
+void remember(SplatState& s, const SplatPlan& p, const Bound& o, long long entries, long long known, long long capacity) {
+    s.valid = true;
+    s.view = p.v;
+    s.buf = o.b;
+    s.entries = entries;
+    s.known_entries = known;
+    s.capacity = capacity;
+    s.header = o.header;
+    s.stats[0] = entries;
+    s.stats[1] = p.n_tiles;
+    s.stats[2] = -1;  // longest list: filled lazily by xyz_splat_last_stats
+    s.stats[3] = entries * kTilePixels;
+}
+
+int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients, const float* target,
+                 float* output, float* total_loss, int W, int H, int N, int row_begin, int row_end, void* stream,
+                 int flags) {
+    if (!target || !output || !total_loss || (N > 0 && (!gaussians || !gradients))) return XYZ_ERR_INVALID_ARGUMENT;
+    if (W <= 0 || H <= 0 || N < 0 || row_begin < 0 || row_end > H || row_begin > row_end) return XYZ_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SplatState* sp = state_for(st);
+    if (!sp) return XYZ_ERR_NOT_INITIALISED;
+    SplatState& S = *sp;
+    S.stream = st;
+    const bool same_shape = state_usable(&S) && S.view.num_gaussians == N && S.view.width == W && S.view.height == H &&
+                            S.view.row_begin == row_begin && S.view.row_end == row_end;
+    if (!same_shape) S.valid = false;
+    // XYZ_FLAG_ASYNC: what an earlier sync-free launch on this stream reported meanwhile (list length, overflows)
+    if (S.mirror) {
+        const unsigned long long seen_total = S.mirror[0], seen_overflows = S.mirror[1];
+        if (same_shape && S.entries < 0 && seen_total != 0ull) S.known_entries = static_cast<long long>(seen_total);
+        if (seen_overflows != S.overflows_seen) {
+            S.overflows_seen = seen_overflows;
+            S.capacity = 0;            // sized afresh from the reported length
+            return XYZ_ERR_WORKSPACE;  // an earlier XYZ_FLAG_ASYNC launch was longer than its buffers: its outputs are void
+        }
+    }
+    const long long predicted = (same_shape && S.known_entries > 0) ? S.known_entries : static_cast<long long>(N) * 40;
+    SplatPlan p;
+    int err = make_plan(p, W, H, N, row_begin, row_end, flags, predicted, st);
+    if (err) return err;
+    // sync-free launch: needs the counting sort (no host-side item counts) and a known length of this scene shape
+    N = p.v.num_gaussians;  // 0 for an empty row band
+    const bool async = (flags & XYZ_FLAG_ASYNC) && p.counting && N > 0 && same_shape && S.known_entries > 0;
+    long long capacity = 0;
+    if (async) {
+        capacity = S.known_entries + S.known_entries / 2 + 4096;
+        if (S.capacity >= S.known_entries + S.known_entries / 8) capacity = S.capacity;  // keep the buffers
+        if (capacity >= (1LL << 31) - 512) return XYZ_ERR_WORKSPACE;
+    }
+    // the header {list length, overflow counter, ticket} comes FIRST in the arena: the overflow counter is sticky across
+    // launches, so its place must not move with the scene shape (a fresh arena is zero-filled, common.cu)
+    unsigned char* base = nullptr;
+    uint64_t gen_fixed = 0, gen_entry = 0;
+    err = scratch_get(SCRATCH_SPLAT, kHeaderBytes + p.fixed_bytes, reinterpret_cast<void**>(&base), st, &gen_fixed);
+    if (err) return err;
+    Bound o;
+    bind_fixed(p, base, base + kHeaderBytes, o);
+    const unsigned long long* total_src = nullptr;
+    StageEvents* tm = nullptr;
+    S.timing.armed = false;
+    if (flags & XYZ_FLAG_TIMING) {
+        if ((err = S.timing.ensure())) return err;
+        tm = &S.timing;
+    }
+    err = enqueue_front(p, o, gaussians, static_cast<unsigned long long>(capacity), S.overflows_seen, st, &total_src, tm);
+    if (err) return err;
+    long long entries = 0;
+    if (N > 0) {
+        if (async) {
+            // no read-back: the buffers are sized for `capacity`; the length goes to the pinned mirror for later calls
+            if (!S.mirror) {
+                void* m = nullptr;
+                cudaError_t ce = cudaHostAlloc(&m, 2 * sizeof(unsigned long long), cudaHostAllocDefault);
+                if (ce != cudaSuccess) return static_cast<int>(ce);
+                S.mirror = static_cast<volatile unsigned long long*>(m);
+                S.mirror[0] = 0ull;
+                S.mirror[1] = S.overflows_seen;
+            }
+            cudaError_t ce = cudaMemcpyAsync(const_cast<unsigned long long*>(S.mirror), o.header,
+                                             2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, st);
+            if (ce != cudaSuccess) return static_cast<int>(ce);
+            entries = capacity;
+        } else {
+            // the list length is data dependent: one 8-byte read-back (the only synchronisation of this entry point;
+            // xyz_launch_gaussian_splatting_ws has none)
+            unsigned long long total = 0;
+            cudaError_t ce = cudaMemcpyAsync(&total, total_src, sizeof(total), cudaMemcpyDeviceToHost, st);
+            if (ce != cudaSuccess) return static_cast<int>(ce);
+            ce = cudaStreamSynchronize(st);
+            if (ce != cudaSuccess) return static_cast<int>(ce);
+            entries = static_cast<long long>(total);
+        }
+    }
+    if (entries >= (1LL << 31) - 512) return XYZ_ERR_WORKSPACE;
+    const EntryLayout L = make_entry_layout(p, entries, st);
+    unsigned char* sbase = nullptr;
+    err = scratch_get(SCRATCH_SPLAT_SORT, L.bytes, reinterpret_cast<void**>(&sbase), st, &gen_entry);
+    if (err) return err;
+    bind_entry(p, L, sbase, o);
+    err = enqueue_back(p, L, o, gaussians, gradients, target, output, total_loss, entries,
+                       static_cast<unsigned long long>(capacity), st, tm);
+    if (err) return err;
+    S.timing.armed = tm != nullptr;
+    const long long known_before = same_shape ? S.known_entries : 0;
+    S.external = false;
+    S.gen_fixed = gen_fixed;
+    S.gen_entry = gen_entry;
+    remember(S, p, o, async ? -1 : entries, async ? known_before : entries, async ? capacity : 0);
+    g_last = &S;
+    return last_error();
+}
+
+// After a sync-free launch the host does not know the list length: fetch it (synchronises the stream).
 // Returns XYZ_ERR_WORKSPACE if that launch was longer than its buffers (its outputs are void).
-int resolve_async_length() {
-    if (!g_last.valid || g_last.entries >= 0) return 0;
+int resolve_async_length(SplatState& S) {
+    if (!S.valid || S.entries >= 0) return 0;
     unsigned long long both[2] = {0ull, 0ull};
-    cudaError_t e = cudaDeviceSynchronize();
+    cudaError_t e = cudaStreamSynchronize(S.stream);
     if (e != cudaSuccess) return static_cast<int>(e);
-    e = cudaMemcpy(both, g_last.total_dev, sizeof(both), cudaMemcpyDeviceToHost);
+    e = cudaMemcpy(both, S.header, sizeof(both), cudaMemcpyDeviceToHost);
     if (e != cudaSuccess) return static_cast<int>(e);
-    g_last.known_entries = static_cast<long long>(both[0]);
-    if (both[1] != g_overflows_seen) {
-        g_overflows_seen = both[1];
-        g_last.entries = 0;  // every list of that launch was published empty
-        g_last.capacity = 0;
-        g_last.stats[0] = 0;
-        g_last.stats[3] = 0;
+    S.known_entries = static_cast<long long>(both[0]);
+    if (both[1] != S.overflows_seen) {
+        S.overflows_seen = both[1];
+        S.entries = 0;  // every list of that launch was published empty
+        S.capacity = 0;
+        S.stats[0] = 0;
+        S.stats[3] = 0;
         return XYZ_ERR_WORKSPACE;
     }
-    g_last.entries = static_cast<long long>(both[0]);
-    g_last.stats[0] = g_last.entries;
-    g_last.stats[3] = g_last.entries * kTilePixels;
+    S.entries = static_cast<long long>(both[0]);
+    S.stats[0] = S.entries;
+    S.stats[3] = S.entries * kTilePixels;
+    return 0;
+}
+
+int ws_plan(SplatPlan& p, EntryLayout& L, int W, int H, int N, int row_begin, int row_end, long long max_entries, int flags,
+            cudaStream_t st) {
+    if (max_entries < 0 || max_entries >= (1LL << 31) - 512) return XYZ_ERR_INVALID_ARGUMENT;
+    if (flags & XYZ_FLAG_RADIX_BINNING) return XYZ_ERR_INVALID_ARGUMENT;
+    int err = make_plan(p, W, H, N, row_begin, row_end, flags, max_entries, st);
+    if (err) return err;
+    if (!p.counting) return XYZ_ERR_INVALID_ARGUMENT;  // more than 8192 tiles: the radix path needs host-side counts
+    L = make_entry_layout(p, max_entries, st);
     return 0;
 }
 
@@ -943,46 +1222,167 @@ extern "C" int xyz_launch_gaussian_splatting_rows(const xyz_gaussian_params* gau
                               num_gaussians, row_begin, row_end, stream, flags);
 }
 
+// ---- caller-provided workspace: no allocation, no synchronisation, no library state ----------------------------------
+extern "C" size_t xyz_splat_workspace_bytes(int image_width, int image_height, int num_gaussians, int row_begin,
+                                            int row_end, long long max_entries, int flags) {
+    using namespace xyzb;
+    SplatPlan p;
+    EntryLayout L;
+    if (ws_plan(p, L, image_width, image_height, num_gaussians, row_begin, row_end, max_entries, flags, nullptr)) return 0;
+    return kHeaderBytes + align_up(p.fixed_bytes) + L.bytes;
+}
+
+extern "C" int xyz_splat_workspace_init(void* workspace, size_t workspace_bytes, void* stream) {
+    if (!workspace || workspace_bytes < xyzb::kHeaderBytes) return XYZ_ERR_INVALID_ARGUMENT;
+    return static_cast<int>(cudaMemsetAsync(workspace, 0, xyzb::kHeaderBytes, static_cast<cudaStream_t>(stream)));
+}
+
+extern "C" int xyz_launch_gaussian_splatting_ws(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradients,
+                                                const float* target_image, float* output_image, float* total_loss,
+                                                int image_width, int image_height, int num_gaussians, int row_begin,
+                                                int row_end, void* workspace, size_t workspace_bytes,
+                                                long long max_entries, void* stream, int flags) {
+    using namespace xyzb;
+    if (!workspace || (reinterpret_cast<uintptr_t>(workspace) & 255u)) return XYZ_ERR_INVALID_ARGUMENT;
+    if (!target_image || !output_image || !total_loss || (num_gaussians > 0 && (!gaussians || !gradients)))
+        return XYZ_ERR_INVALID_ARGUMENT;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    SplatPlan p;
+    EntryLayout L;
+    int err = ws_plan(p, L, image_width, image_height, num_gaussians, row_begin, row_end, max_entries, flags, st);
+    if (err) return err;
+    if (workspace_bytes < kHeaderBytes + align_up(p.fixed_bytes) + L.bytes) return XYZ_ERR_WORKSPACE;
+    unsigned char* w = static_cast<unsigned char*>(workspace);
+    Bound o;
+    bind_fixed(p, w, w + kHeaderBytes, o);
+    bind_entry(p, L, w + kHeaderBytes + align_up(p.fixed_bytes), o);
+    const unsigned long long* total_src = nullptr;
+    // capacity 0 would mean "unlimited" to the kernels: a workspace for zero entries still bounds the lists at 0 + 1
+    const unsigned long long capacity = static_cast<unsigned long long>(max_entries > 0 ? max_entries : 1);
+    num_gaussians = p.v.num_gaussians;  // 0 for an empty row band
+    if (num_gaussians == 0) {           // no kernel will write the header: the list is empty
+        cudaError_t ce = cudaMemsetAsync(o.header, 0, sizeof(unsigned long long), st);
+        if (ce != cudaSuccess) return static_cast<int>(ce);
+    }
+    SplatState& S = g_last_ws;
+    StageEvents* tm = nullptr;
+    S.timing.armed = false;
+    if (flags & XYZ_FLAG_TIMING) {
+        if ((err = S.timing.ensure())) return err;
+        tm = &S.timing;
+    }
+    err = enqueue_front(p, o, gaussians, capacity, 0ull, st, &total_src, tm);
+    if (err) return err;
+    err = enqueue_back(p, L, o, gaussians, gradients, target_image, output_image, total_loss,
+                       num_gaussians > 0 ? static_cast<long long>(capacity) : 0, capacity, st, tm);
+    if (err) return err;
+    S.timing.armed = tm != nullptr;
+    S.external = true;
+    S.stream = st;
+    remember(S, p, o, num_gaussians > 0 ? -1 : 0, 0, static_cast<long long>(capacity));
+    cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(st, &cap);
+    S.overflows_seen = ~0ull;  // unknown: xyz_splat_last_stats compares with the header's own previous value instead
+    g_last = (cap == cudaStreamCaptureStatusNone) ? &S : nullptr;  // a captured launch has not run: nothing to report
+    return last_error();
+}
+
+extern "C" int xyz_splat_workspace_status(const void* workspace, void* stream, long long status_host[4]) {
+    if (!workspace || !status_host) return XYZ_ERR_INVALID_ARGUMENT;
+    cudaError_t e = cudaStreamSynchronize(static_cast<cudaStream_t>(stream));
+    if (e != cudaSuccess) return static_cast<int>(e);
+    unsigned long long h[4] = {0, 0, 0, 0};
+    e = cudaMemcpy(h, workspace, sizeof(h), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    status_host[0] = static_cast<long long>(h[0]);  // list length of the most recent launch
+    status_host[1] = static_cast<long long>(h[1]);  // launches that did not fit (sticky)
+    status_host[2] = static_cast<long long>(h[3]);  // max_entries of the most recent launch
+    status_host[3] = h[3] != 0 && h[0] > h[3] ? 1 : 0;  // did the most recent launch overflow?
+    return 0;
+}
+
 extern "C" int xyz_splat_last_stats(long long stats_host[4]) {
     using namespace xyzb;
-    if (!g_last.valid || !stats_host) return XYZ_ERR_NOT_INITIALISED;
-    if (int err = resolve_async_length()) return err;
-    if (g_last.stats[2] < 0) {
-        const int n_tiles = g_last.view.tiles_x * g_last.view.tiles_y;
+    if (!stats_host || !g_last || !state_usable(g_last)) return XYZ_ERR_NOT_INITIALISED;
+    SplatState& S = *g_last;
+    if (S.external) {
+        // workspace launch: read the header (synchronises the stream)
+        long long st4[4];
+        int err = xyz_splat_workspace_status(S.header, S.stream, st4);
+        if (err) return err;
+        if (st4[3]) return XYZ_ERR_WORKSPACE;
+        S.entries = st4[0];
+        S.stats[0] = S.entries;
+        S.stats[3] = S.entries * kTilePixels;
+    } else if (int err = resolve_async_length(S)) {
+        return err;
+    }
+    if (S.stats[2] < 0) {
+        const int n_tiles = S.view.tiles_x * S.view.tiles_y;
+        const int ty0 = S.view.row_begin / kTile, ty1 = (S.view.row_end + kTile - 1) / kTile;
         std::vector<int2> r(n_tiles);
-        cudaError_t e = cudaMemcpy(r.data(), g_last.buf.tile_ranges, sizeof(int2) * n_tiles, cudaMemcpyDeviceToHost);
+        cudaError_t e = cudaMemcpy(r.data(), S.buf.tile_ranges, sizeof(int2) * n_tiles, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return static_cast<int>(e);
         long long mx = 0;
-        for (const int2& t : r) mx = std::max<long long>(mx, t.y - t.x);
-        g_last.stats[2] = mx;
+        for (int t = ty0 * S.view.tiles_x; t < ty1 * S.view.tiles_x; ++t) mx = std::max<long long>(mx, r[t].y - r[t].x);
+        S.stats[2] = mx;
     }
-    for (int i = 0; i < 4; ++i) stats_host[i] = g_last.stats[i];
+    for (int i = 0; i < 4; ++i) stats_host[i] = S.stats[i];
     return 0;
 }
 
 extern "C" int xyz_splat_debug_binning(int32_t* rects_host, int32_t* tile_ranges_host, int32_t* sorted_ids_host,
                                        float* records_host) {
     using namespace xyzb;
-    if (!g_last.valid) return XYZ_ERR_NOT_INITIALISED;
-    if (int err = resolve_async_length()) return err;
-    cudaError_t e = cudaDeviceSynchronize();
+    if (!g_last || !state_usable(g_last)) return XYZ_ERR_NOT_INITIALISED;
+    long long st4[4];
+    if (int err = xyz_splat_last_stats(st4)) return err;
+    SplatState& S = *g_last;
+    cudaError_t e = cudaStreamSynchronize(S.stream);
     if (e != cudaSuccess) return static_cast<int>(e);
-    const int n = g_last.view.num_gaussians, n_tiles = g_last.view.tiles_x * g_last.view.tiles_y;
+    const int n = S.view.num_gaussians, n_tiles = S.view.tiles_x * S.view.tiles_y;
     if (rects_host && n > 0) {
-        e = cudaMemcpy(rects_host, g_last.buf.rects, sizeof(int4) * n, cudaMemcpyDeviceToHost);
+        e = cudaMemcpy(rects_host, S.buf.rects, sizeof(int4) * n, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return static_cast<int>(e);
     }
     if (tile_ranges_host) {
-        e = cudaMemcpy(tile_ranges_host, g_last.buf.tile_ranges, sizeof(int2) * n_tiles, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) return static_cast<int>(e);
+        // tiles outside the launch's row band were not binned: reported as (0, 0)
+        const int ty0 = S.view.row_begin / kTile, ty1 = (S.view.row_end + kTile - 1) / kTile;
+        memset(tile_ranges_host, 0, sizeof(int2) * n_tiles);
+        if (ty1 > ty0) {
+            e = cudaMemcpy(tile_ranges_host + 2 * ty0 * S.view.tiles_x, S.buf.tile_ranges + ty0 * S.view.tiles_x,
+                           sizeof(int2) * static_cast<size_t>(ty1 - ty0) * S.view.tiles_x, cudaMemcpyDeviceToHost);
+            if (e != cudaSuccess) return static_cast<int>(e);
+        }
     }
-    if (sorted_ids_host && g_last.entries > 0) {
-        e = cudaMemcpy(sorted_ids_host, g_last.buf.sorted_gid, sizeof(int) * g_last.entries, cudaMemcpyDeviceToHost);
+    if (sorted_ids_host && S.entries > 0) {
+        e = cudaMemcpy(sorted_ids_host, S.buf.sorted_gid, sizeof(int) * S.entries, cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return static_cast<int>(e);
     }
     if (records_host && n > 0) {
-        e = cudaMemcpy(records_host, g_last.buf.records, sizeof(float4) * 3 * n, cudaMemcpyDeviceToHost);
+        // the first 9 floats of every 16-float device record into the documented 12-float rows (9..11 stay untouched)
+        e = cudaMemcpy2D(records_host, 12 * sizeof(float), S.buf.records, 16 * sizeof(float), 9 * sizeof(float), n,
+                         cudaMemcpyDeviceToHost);
         if (e != cudaSuccess) return static_cast<int>(e);
     }
+    return 0;
+}
+
+extern "C" int xyz_splat_last_timing(float stage_us_host[6]) {
+    using namespace xyzb;
+    if (!stage_us_host || !g_last || !g_last->timing.armed) return XYZ_ERR_NOT_INITIALISED;
+    SplatState& S = *g_last;
+    cudaError_t e = cudaEventSynchronize(S.timing.ev[5]);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    float total = 0.f;
+    for (int i = 0; i < 5; ++i) {
+        float ms = 0.f;
+        e = cudaEventElapsedTime(&ms, S.timing.ev[i], S.timing.ev[i + 1]);
+        if (e != cudaSuccess) return static_cast<int>(e);
+        stage_us_host[i] = ms * 1000.0f;
+    }
+    e = cudaEventElapsedTime(&total, S.timing.ev[0], S.timing.ev[5]);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    stage_us_host[5] = total * 1000.0f;
     return 0;
 }

@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(kFwdThreads)
         __syncthreads();
         for (int t = tid; t < n; t += kFwdThreads) {
             const int g = sorted_gid[base + t];
-            const float4 r0 = __ldg(records + 3 * g), r1 = __ldg(records + 3 * g + 1), r2 = __ldg(records + 3 * g + 2);
+            const float4 r0 = __ldg(records + 4 * g), r1 = __ldg(records + 4 * g + 1), r2 = __ldg(records + 4 * g + 2);
             s_a[t] = make_float4(r0.x, r0.y, kKappa * r0.z, (2.0f * kKappa) * r0.w);
             s_b[t] = make_float4(kKappa * r1.x, r1.y * r1.z, r1.y * r1.w, r1.y * r2.x);
         }
@@ -285,8 +285,8 @@ __device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_r
 __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
     splat_backward_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ chunk_info,
                           const float4* __restrict__ rest_tiles, const int* __restrict__ sorted_gid,
-                          const unsigned int* __restrict__ sorted_orig, const xyz_gaussian_params* __restrict__ params,
-                          xyz_gaussian_grads* grads, float* __restrict__ entry_grads) {
+                          const unsigned int* __restrict__ sorted_orig, xyz_gaussian_grads* grads,
+                          float* __restrict__ entry_grads) {
     __shared__ RestPair s_rest[kTilePixels / 2];  // -(tgt - out) and the active mask, pixel pairs (see RestPair)
 
     const int tid = threadIdx.x;
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
     int g = 0;
     if (valid) {
         g = sorted_gid[i];
-        const float4 r0 = __ldg(records + 3 * g), r1 = __ldg(records + 3 * g + 1), r2 = __ldg(records + 3 * g + 2);
+        const float4 r0 = __ldg(records + 4 * g), r1 = __ldg(records + 4 * g + 1), r2 = __ldg(records + 4 * g + 2);
         cx = r0.x; cy = r0.y; ia = r0.z; ib = r0.w;
         ic = r1.x; so = r1.y; c0 = r1.z; c1 = r1.w; c2 = r2.x;
     }
@@ -340,10 +340,12 @@ __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
     const float a_so = T[0];
 
     // Per-Gaussian chain rule, once per entry (linear in the sums above).
-    const xyz_gaussian_params gp = params[g];
-    // sym_matrix2_inv backward (sym_matrix2_inv_logic.cuh:43-77) needs Sigma = (A, B, C):
-    const float es0 = expf(gp.scale[0]), es1 = expf(gp.scale[1]);  // exp_logic.cuh:17-36
-    const float ct = cosf(gp.rotation[0]), sn = sinf(gp.rotation[0]);
+    // sym_matrix2_inv backward (sym_matrix2_inv_logic.cuh:43-77) needs Sigma = (A, B, C): rebuilt from exp(scale), cos
+    // and sin AS THE PREPROCESS KERNEL COMPUTED THEM (IEEE expf / cosf / sinf in both flavours, kept in the record), so
+    // the chain rule is applied at the Sigma whose inverse the forward pass rendered with -- the fast-math flavour's
+    // ex2.approx / sin.approx (no range reduction) never enter it.  exp_logic.cuh:17-36, covariance_generation.cuh:154-172
+    const float4 q2 = __ldg(records + 4 * g + 2), q3 = __ldg(records + 4 * g + 3);
+    const float es0 = q2.y, es1 = q2.z, ct = q2.w, sn = q3.x;
     const float m00 = es0 * ct, m01 = -es1 * sn, m10 = es0 * sn, m11 = es1 * ct;  // covariance_generation.cuh:154-172
     const float A = m00 * m00 + m01 * m01, B = m00 * m10 + m01 * m11, C = m10 * m10 + m11 * m11;
     float det = A * C - B * B;
@@ -396,19 +398,11 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
     return last_error();
 }
 
-int XYZ_CAT(splat_backward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const SplatBuffers& b,
-                                                      const xyz_gaussian_params* params, xyz_gaussian_grads* grads,
-                                                      const float* target, const float* output, long long entries,
-                                                      bool deterministic, cudaStream_t st) {
-    if (entries <= 0) return 0;
-    const int n_tiles = v.tiles_x * v.tiles_y;
-    // upper bound of sum over tiles of ceil(len / kBwdChunk)
-    const long long blocks = entries / kBwdChunk + n_tiles;
-    (void)target;
-    (void)output;
-    splat_backward_kernel<<<static_cast<unsigned int>(blocks), kBwdChunk, 0, st>>>(
-        v, b.records, b.chunk_info, b.rest_tiles, b.sorted_gid, b.vals_out, params, grads,
-        deterministic ? b.entry_grads : nullptr);
+int XYZ_CAT(splat_backward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const SplatBuffers& b, xyz_gaussian_grads* grads,
+                                                      long long bwd_ctas, bool deterministic, cudaStream_t st) {
+    if (bwd_ctas <= 0) return 0;
+    splat_backward_kernel<<<static_cast<unsigned int>(bwd_ctas), kBwdChunk, 0, st>>>(
+        v, b.records, b.chunk_info, b.rest_tiles, b.sorted_gid, b.vals_out, grads, deterministic ? b.entry_grads : nullptr);
     count_launch();
     return last_error();
 }
