@@ -1,22 +1,37 @@
 #!/usr/bin/env python
 """bench.py -- the driver's benchmark contract for the xyz-autodiff-cuda hot path on B200.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload covproj|splat_c5|splat_c4_rows]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
   torchrun --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W        (N > 1)
 
-Headline workload (BASELINE.json configs[2], the largest single-GPU "gradient evals/s" configuration and the
-only one whose working set (12.9 GB) exceeds L2): batched covariance projection S' = (J W) S (J W)^T,
-forward + reverse, 2^26 elements, fp32.  A step = one pass of the kernel over the batch.
-  value     evals/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks)
-  e2e       the same through the host-buffer pipeline (pinned host arrays -> H2D -> kernel -> D2H)
-  roofline  192 algorithmic bytes per eval / kernel time, against MEASURED_PEAKS.json hbm_gbs
-  cpu_baseline  the reference's own op::matmul graph compiled for the host (oracle/_ref), all host
-            cores, on a bounded sample
-The other BASELINE configs (least squares 1M, accumulation 16M->1K, splat 100K Gaussians 1024^2) are timed
-briefly at N=1 and reported under "also" in the same JSON line.
+BASELINE.json's metric has two halves, "fwd+bwd gradient evals/sec" and "splat fwd+bwd ms/iter at 1/2/4/8 B200"; ONE
+JSON line carries both, at every N:
+
+  headline (metric / value / e2e / roofline / cpu_baseline)   BASELINE configs[2]: batched covariance projection
+      S' = (J W) S (J W)^T forward + reverse, 2^26 elements per GPU, fp32 -- the largest single-GPU "gradient evals/s"
+      configuration and the only one whose working set (12.9 GB) exceeds L2.  Element ranges per GPU, no collective (weak
+      scaling).  value = evals/s with inputs resident in HBM (CUDA events on the launching stream, max over ranks); e2e =
+      the same through the host-buffer pipeline (pinned host -> H2D -> kernel -> D2H); roofline = 192 algorithmic bytes
+      per eval / kernel time against MEASURED_PEAKS.json hbm_gbs; cpu_baseline = the reference's own op::matmul graph
+      compiled for the host (oracle/_ref) on all host cores, bounded sample.
+  config.splat / roofline.splat / e2e.splat                   the splat half, measured in the same run:
+      c4        configs[3], 100 K Gaussians, 1024^2, one GPU (rank 0): ms per iteration (zero-grad + loss reset + launch),
+                stage times, pairs per pass; the same iteration + Adam as one CUDA graph
+      c4_rows   configs[3] on N GPUs: ONE image split into row bands, strong scaling: the three gradient exchanges (NCCL
+                all-reduce + replicated Adam | NCCL reduce-scatter / sharded Adam / all-gather | one fused peer-memory kernel,
+                whole iteration as one CUDA graph) with a stage breakdown
+      c5        configs[4], 3 M Gaussians, 8 views sharded over the N GPUs (8 / N views per GPU), NCCL all-reduce of the
+                108 MB gradient buffer + Adam (as BASELINE names it), and the fused peer-memory exchange next to it
+      roofline.splat   forward against its MUFU floor (one ex2 per pair), backward against its FMA-pipe floor (13 lane
+                operations per pair)
+      e2e.splat        host_api.SplatHostIteration: params H2D from pinned memory, loss + gradients D2H, per iteration
+  config.other_configs (N = 1)   configs[0], [1] and variant B of [2], briefly
+  config.reference_cuda (N = 1)  the reference's own CUDA kernels built for sm_100a on the same GPU (splat at three
+                Gaussian counts: its cost per pair is measured, not assumed)
+  config.multi_gpu (N > 1)       the fused in-kernel all-reduces of C1 / C2 / C3-B next to kernel + NCCL, and a parity check
+                of every sharded path against the single-rank result ("parity": "ok")
+
 --impl reference times the reference's CPU path alone (rank 0 only).
---workload splat_c5        BASELINE configs[4]: 3M Gaussians, 8 views sharded over the ranks, NCCL all-reduce of the gradients.
---workload splat_c4_rows   BASELINE configs[3] with ONE image split into row bands over the ranks (strong scaling).
 """
 import argparse
 import json
@@ -34,14 +49,30 @@ METRIC = "fwd+bwd gradient evals/sec"
 UNIT = "evals/s"
 COVPROJ_BYTES = 192  # per eval: in J6 W9 S6 g3, out out3 gJ6 gW9 gS6, fp32
 FULL_E = 1 << 26
+SM_COUNT = 148
+FMA_LANES_PER_SM = 128      # fp32 lanes of the FMA pipe per SM per clock
+MUFU_PER_SM = 16            # special-function results per SM per clock
+BWD_FMA_OPS_PER_PAIR = 13   # csrc/splat_kernels.cuh: 2 exponent, 3 residual signs, 3 colour sums, 3 for t, 2 moments
 
 
-def measured_peak_gbs():
+def sig(v, digits=5):
+    """Round floats for a compact JSON line."""
+    if isinstance(v, float):
+        return float(f"{v:.{digits}g}")
+    if isinstance(v, dict):
+        return {k: sig(w, digits) for k, w in v.items()}
+    if isinstance(v, (list, tuple)):
+        return [sig(w, digits) for w in v]
+    return v
+
+
+def measured_peaks():
     try:
         with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
-            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)"
+            j = json.load(f)
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, copy kernel)", float(j.get("sm_max_mhz", 1965.0))
     except Exception:
-        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+        return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)", 1965.0
 
 
 class ClockSampler:
@@ -96,6 +127,9 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(sm)}
 
 
+# ---------------------------------------------------------------------------------------------------------------------
+# CPU legs (the only places that execute oracle/)
+# ---------------------------------------------------------------------------------------------------------------------
 def cpu_covproj(sample_elems, repeats=1):
     """The reference's matmul graph on the host cores (oracle/_ref if present, else the port)."""
     import numpy as np
@@ -137,193 +171,14 @@ def run_reference(args):
                                    "each step = a bounded sample of 2^23 elements on the host cores"},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
-
-
-def time_kernel(fn, steps, warmup, stream):
-    import torch
-    for _ in range(warmup):
-        fn()
-    torch.cuda.synchronize()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
-    ev[0].record(stream)
-    for i in range(steps):
-        fn()
-        ev[i + 1].record(stream)
-    torch.cuda.synchronize()
-    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
-    return ev[0].elapsed_time(ev[steps]), per
-
-
-def also_workloads(dev, peak_gbs):
-    """Brief device-resident timings of the other BASELINE configs (N=1 only)."""
-    import numpy as np
-    import torch
-    import oracle_lib as orc
-    import xyz_autodiff_cuda_b200 as x
-    out = {}
-    st = torch.cuda.current_stream()
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
-
-    def timed(fn, reps=10, flush_l2=True):
-        ts = []
-        for i in range(reps + 3):
-            if flush_l2:
-                flush.zero_()
-            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            a.record(st)
-            fn()
-            b.record(st)
-            torch.cuda.synchronize()
-            if i >= 3:
-                ts.append(a.elapsed_time(b))
-        ts.sort()
-        return ts[len(ts) // 2]
-
-    def timed_rotating(make_call, n_sets, rounds=6):
-        """Back-to-back launches over n_sets DIFFERENT input sets (together larger than L2, so every launch still reads
-        from HBM) between one pair of events: the steady-state cost per launch, without the event / launch gap that a
-        single ~20 us launch between two events carries."""
-        calls = [make_call(i) for i in range(n_sets)]
-        for c in calls:
-            c()
-        torch.cuda.synchronize()
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record(st)
-        for _ in range(rounds):
-            for c in calls:
-                c()
-        b.record(st)
-        torch.cuda.synchronize()
-        return a.elapsed_time(b) / (rounds * n_sets)
-
-    # C1: least squares, 1M residuals fp64 (24 MB)
-    n = 1_000_000
-    data = torch.from_numpy(orc.lsq_data(n, 42)).to(dev)
-    prm = torch.zeros(8, dtype=torch.float64, device=dev)
-    prm[1] = 1.0
-    ms = timed(lambda: x.lsq_grad(data, prm))
-    out["c1_lsq_1M_f64"] = {"evals_per_s": n / (ms / 1e3), "ms": ms, "gbs": 24 * n / (ms / 1e3) / 1e9,
-                            "hbm_frac": 24 * n / (ms / 1e3) / 1e9 / peak_gbs, "l2": "flushed between iterations"}
-    sets = [data] + [data.clone() for _ in range(7)]   # 8 x 24 MB = 192 MB > L2
-    ms_rot = timed_rotating(lambda i: (lambda: x.lsq_grad(sets[i], prm)), len(sets))
-    out["c1_lsq_1M_f64"].update({"ms_back_to_back": ms_rot, "hbm_frac_back_to_back": 24 * n / (ms_rot / 1e3) / 1e9 / peak_gbs,
-                                 "back_to_back": "8 input sets (192 MB > L2) launched back to back, 48 launches between two events"})
-    del sets
-    n2 = 1 << 28
-    data2 = torch.empty((n2, 3), dtype=torch.float64, device=dev).uniform_(-5, 5)
-    ms = timed(lambda: x.lsq_grad(data2, prm), reps=5, flush_l2=False)
-    out["c1_lsq_2^28_f64"] = {"evals_per_s": n2 / (ms / 1e3), "ms": ms, "gbs": 24 * n2 / (ms / 1e3) / 1e9,
-                              "hbm_frac": 24 * n2 / (ms / 1e3) / 1e9 / peak_gbs, "l2": "6.4 GB input > L2"}
-    del data2
-    # C2: accumulation 2^24 -> 1024
-    n = 1 << 24
-    for dist in ("uniform", "zipf", "same"):
-        idx, val = orc.accumulate_inputs(n, 1024, dist, 42)
-        ti, tv = torch.from_numpy(idx).to(dev), torch.from_numpy(val).to(dev)
-        grad = torch.zeros(1024, device=dev)
-        ms = timed(lambda: x.accumulate(ti, tv, grad))
-        out[f"c2_accumulate_2^24_{dist}"] = {"elems_per_s": n / (ms / 1e3), "ms": ms, "gbs": 8 * n / (ms / 1e3) / 1e9,
-                                             "hbm_frac": 8 * n / (ms / 1e3) / 1e9 / peak_gbs,
-                                             "l2": "flushed between iterations"}
-        if dist == "uniform":
-            pairs = [(ti, tv)] + [(ti.clone(), tv.clone()) for _ in range(7)]   # 8 x 134 MB > L2
-            ms_rot = timed_rotating(lambda i: (lambda: x.accumulate(pairs[i][0], pairs[i][1], grad)), len(pairs))
-            out[f"c2_accumulate_2^24_{dist}"].update({
-                "ms_back_to_back": ms_rot, "hbm_frac_back_to_back": 8 * n / (ms_rot / 1e3) / 1e9 / peak_gbs,
-                "back_to_back": "8 input sets (1.07 GB > L2) launched back to back, 48 launches between two events"})
-            del pairs
-    # C3 variant B: one shared W, per-element adjoints of W accumulated into 9 gradients; 2^26 elements (8 GB > L2)
-    n3 = 1 << 26
-    ins3 = [torch.empty((n3, w), device=dev).uniform_(-1, 1) for w in (6, 6, 3)]
-    outs3 = [torch.empty((n3, w), device=dev) for w in (3, 6, 6)]
-    w9 = torch.empty(9, device=dev).uniform_(-1, 1)
-    gw9 = torch.zeros(9, device=dev)
-    ms = timed(lambda: x.covproj_shared_w_fwd_bwd(ins3[0], w9, ins3[1], ins3[2], outs3[0], outs3[1], gw9, outs3[2]),
-               reps=5, flush_l2=False)
-    out["c3b_covproj_shared_w_2^26"] = {"evals_per_s": n3 / (ms / 1e3), "ms": ms, "bytes_per_eval": 120,
-                                        "gbs": 120 * n3 / (ms / 1e3) / 1e9, "hbm_frac": 120 * n3 / (ms / 1e3) / 1e9 / peak_gbs,
-                                        "l2": "8.05 GB per step > L2"}
-    del ins3, outs3
-    torch.cuda.empty_cache()
-    # the same two graphs written by a USER with the public op:: API and run through include/xyz_autodiff/batched.cuh
-    # (tests/csrc/batched_probe.cu; the probe library is built by __graft_entry__.build())
     try:
-        import ctypes
-        so = os.path.join(ROOT, "tests", "csrc", "_build", "libxyz_batched.so")
-        if os.path.exists(so):
-            B = ctypes.CDLL(so)
-            B.batched_chain.restype = ctypes.c_float
-            B.batched_chain.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
-            B.batched_lsq.restype = ctypes.c_float
-            B.batched_lsq.argtypes = [ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
-            nb = 1 << 26
-            tin = torch.empty((nb, 15), device=dev).uniform_(-1, 1)
-            tout = torch.empty((nb, 15), device=dev)
-            w18 = torch.empty(18, device=dev).uniform_(-1, 1)
-            gw18 = torch.zeros(18, device=dev)
-            B.batched_chain(tin.data_ptr(), tout.data_ptr(), nb, w18.data_ptr(), gw18.data_ptr(), 2)
-            ms = B.batched_chain(tin.data_ptr(), tout.data_ptr(), nb, w18.data_ptr(), gw18.data_ptr(), 5)
-            out["batched_for_each_matmul_chain_shared_w_2^26"] = {
-                "evals_per_s": nb / (ms / 1e3), "ms": ms, "gbs": 120 * nb / (ms / 1e3) / 1e9,
-                "hbm_frac": 120 * nb / (ms / 1e3) / 1e9 / peak_gbs,
-                "what": "user graph of op::matmul nodes through batched::for_each (include/xyz_autodiff/batched.cuh)"}
-            del tin, tout
-            torch.cuda.empty_cache()
-            mb = 1 << 28
-            dpts = torch.empty((mb, 3), dtype=torch.float64, device=dev).uniform_(-5, 5)
-            v5 = torch.tensor([0.0, 1.0, 0.0, 0.0, 0.0], dtype=torch.float64, device=dev)
-            g5 = torch.zeros(5, dtype=torch.float64, device=dev)
-            B.batched_lsq(dpts.data_ptr(), mb, v5.data_ptr(), g5.data_ptr(), 2)
-            ms = B.batched_lsq(dpts.data_ptr(), mb, v5.data_ptr(), g5.data_ptr(), 5)
-            out["batched_for_each_least_squares_2^28_f64"] = {
-                "evals_per_s": mb / (ms / 1e3), "ms": ms, "gbs": 24 * mb / (ms / 1e3) / 1e9,
-                "hbm_frac": 24 * mb / (ms / 1e3) / 1e9 / peak_gbs,
-                "what": "user graph of op:: nodes (fp64) through batched::for_each"}
-            del dpts
-            torch.cuda.empty_cache()
+        line["config"]["splat_cpu"] = cpu_reference_other_configs(only_splat=True)
     except Exception as e:
-        out["batched_for_each"] = {"error": repr(e)}
-    # C4: splat 100K Gaussians, 1024^2
-    W = H = 1024
-    N = 100_000
-    params, target = orc.splat_c4_scene(N, W, H, 42)
-    tp, tt = torch.from_numpy(params).to(dev), torch.from_numpy(target).to(dev)
-    grads = torch.zeros((N, 9), device=dev)
-    img = torch.zeros((W * H, 3), device=dev)
-    loss = torch.zeros(1, device=dev)
-
-    def splat_iter():
-        x.zero_gradients(grads)
-        loss.zero_()
-        x.launch_gaussian_splatting(tp, grads, tt, img, loss, W, H, N)
-
-    ms = timed(splat_iter, reps=5, flush_l2=False)
-    stats = x.splat_last_stats()
-    out["c4_splat_100K_1024x1024"] = {"ms_per_iter": ms, "tile_list_entries": stats["entries"],
-                                      "pairs_per_pass": stats["pairs_per_pass"],
-                                      "pair_evals_per_s": 2 * stats["pairs_per_pass"] / (ms / 1e3),
-                                      "reference_pairs_per_pass": N * W * H,
-                                      "iteration": "zero_grad + loss reset + launch (fwd + bwd), fast-math flavour"}
-    def splat_iter_tail():
-        x.zero_gradients(grads)
-        loss.zero_()
-        x.launch_gaussian_splatting(tp, grads, tt, img, loss, W, H, N, x.FLAG_TAIL_CULL)
-
-    ms_tail = timed(splat_iter_tail, reps=5, flush_l2=False)
-    out["c4_splat_100K_1024x1024_tail_cull_opt_in"] = {
-        "ms_per_iter": ms_tail, "tile_list_entries": x.splat_last_stats()["entries"],
-        "note": "XYZ_FLAG_TAIL_CULL: NOT the parity path -- also skips pairs with weight < exp(-28) (bounded error, "
-                "include/xyz_b200.h); the headline c4 number above is the result-preserving default"}
-    out["reference_cuda_same_b200"] = reference_cuda(dev, timed, x, tp, tt, W, H, N, ms)
-    try:
-        out["reference_cpu_host_path"] = cpu_reference_other_configs()
-    except Exception as e:
-        out["reference_cpu_host_path"] = {"error": repr(e)}
-    return out
+        line["config"]["splat_cpu"] = {"error": repr(e)}
+    print(json.dumps(sig(line, 8)), flush=True)
 
 
-def cpu_reference_other_configs():
+def cpu_reference_other_configs(only_splat=False):
     """The reference's host-compiled path (oracle/_ref, else the port) on all host cores for the configs that are
     not the headline: C1 at full size, C2 on a 2^22-element sample, C4 on a reduced shape scaled by the pair count
     (the reference evaluates every (pixel, Gaussian) pair, so its cost is exactly proportional to pairs)."""
@@ -341,33 +196,203 @@ def cpu_reference_other_configs():
             ts.append(time.perf_counter() - t0)
         return min(ts)
 
-    data = orc.lsq_data(1_000_000, 42)
-    t = best(lambda: orc.lsq_grad(data, (0.0, 1.0, 0.0, 0.0), which=which, threads=cores))
-    out["c1_lsq_1M_f64"] = {"evals_per_s": data.shape[0] / t, "ms": t * 1e3, "sample": "all 10^6 points"}
-    n = 1 << 22
-    idx, val = orc.accumulate_inputs(n, 1024, "uniform", 42)
-    t = best(lambda: orc.accumulate(idx, val, 1024, which=which, threads=cores))
-    out["c2_accumulate_uniform"] = {"elems_per_s": n / t, "ms_scaled_to_2^24": t * 1e3 * 4, "sample": "2^22 of 2^24 elements"}
+    if not only_splat:
+        data = orc.lsq_data(1_000_000, 42)
+        t = best(lambda: orc.lsq_grad(data, (0.0, 1.0, 0.0, 0.0), which=which, threads=cores))
+        out["c1_lsq_1M_evals_per_s"] = data.shape[0] / t
+        n = 1 << 22
+        idx, val = orc.accumulate_inputs(n, 1024, "uniform", 42)
+        t = best(lambda: orc.accumulate(idx, val, 1024, which=which, threads=cores))
+        out["c2_accumulate_elems_per_s"] = n / t
     W = H = 256
     N = 1000
     params, target = orc.splat_c4_scene(N, W, H, 42)
     t = best(lambda: orc.splat(params, target, W, H, np.float32, which=which, threads=cores), reps=1)
     pairs = N * W * H
-    full_pairs = 100_000 * 1024 * 1024
-    out["c4_splat"] = {"pairs_per_s_both_passes": pairs / t, "ms_at_sample": t * 1e3,
-                       "ms_per_iter_scaled_to_100K_1024x1024": t * 1e3 * full_pairs / pairs,
-                       "sample": f"{N} Gaussians on {W}x{H} ({pairs} pairs), scaled by pair count"}
+    out["c4_splat_ms_per_iter_scaled_to_100K_1024x1024"] = t * 1e3 * (100_000 * 1024 * 1024) / pairs
+    out["c4_sample"] = f"{N} Gaussians on {W}x{H}, scaled by pair count (all-pairs kernel)"
     return out
 
 
-def reference_cuda(dev, timed, x, tp, tt, W, H, N, ours_splat_ms):
-    """The reference's own CUDA kernels built unmodified for sm_100a (oracle/_ref/libxyz_ref_cuda.so), timed on
-    the same GPU with the same CUDA-event harness.  Splat is run at a reduced Gaussian count and scaled by N
-    (its cost is exactly linear in N: every pixel visits every Gaussian)."""
-    import ctypes
-    import numpy as np
+# ---------------------------------------------------------------------------------------------------------------------
+# timing helpers
+# ---------------------------------------------------------------------------------------------------------------------
+def time_kernel(fn, steps, warmup, stream):
+    import torch
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(steps + 1)]
+    ev[0].record(stream)
+    for i in range(steps):
+        fn()
+        ev[i + 1].record(stream)
+    torch.cuda.synchronize()
+    per = [ev[i].elapsed_time(ev[i + 1]) for i in range(steps)]
+    return ev[0].elapsed_time(ev[steps]), per
+
+
+class Timers:
+    def __init__(self, dev, world):
+        import torch
+        self.torch, self.dev, self.world = torch, dev, world
+        self.st = torch.cuda.current_stream()
+        self.flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def barrier(self):
+        if self.world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        self.torch.cuda.synchronize()
+
+    def max_over_ranks(self, v):
+        if self.world == 1:
+            return v
+        import torch.distributed as dist
+        t = self.torch.tensor([v], dtype=self.torch.float64, device=self.dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    def median_flushed(self, fn, reps=10, flush_l2=True):
+        """median of `reps` single launches, each between two events, L2 flushed in between"""
+        torch = self.torch
+        ts = []
+        for i in range(reps + 3):
+            if flush_l2:
+                self.flush.zero_()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(self.st)
+            fn()
+            b.record(self.st)
+            torch.cuda.synchronize()
+            if i >= 3:
+                ts.append(a.elapsed_time(b))
+        ts.sort()
+        return ts[len(ts) // 2]
+
+    def rotating(self, make_call, n_sets, rounds=6):
+        """Back-to-back launches over n_sets DIFFERENT input sets (together larger than L2) between one pair of events."""
+        torch = self.torch
+        calls = [make_call(i) for i in range(n_sets)]
+        for c in calls:
+            c()
+        torch.cuda.synchronize()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(self.st)
+        for _ in range(rounds):
+            for c in calls:
+                c()
+        b.record(self.st)
+        torch.cuda.synchronize()
+        return a.elapsed_time(b) / (rounds * n_sets)
+
+    def loop(self, fn, steps, warmup=3, stream=None):
+        """ms per call of `steps` back-to-back calls after a barrier, max over ranks (multi-GPU safe)."""
+        torch = self.torch
+        st = stream if stream is not None else self.st
+        for i in range(warmup):
+            fn(i)
+        self.barrier()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(st)
+        for i in range(steps):
+            fn(warmup + i)
+        b.record(st)
+        self.barrier()
+        return self.max_over_ranks(a.elapsed_time(b)) / steps
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the other gradient-evals configs (N = 1)
+# ---------------------------------------------------------------------------------------------------------------------
+def other_configs(T, peak_gbs):
     import torch
     import oracle_lib as orc
+    import xyz_autodiff_cuda_b200 as x
+    dev = T.dev
+    out = {}
+    # C1: least squares, 1M residuals fp64 (24 MB)
+    n = 1_000_000
+    data = torch.from_numpy(orc.lsq_data(n, 42)).to(dev)
+    prm = torch.zeros(8, dtype=torch.float64, device=dev)
+    prm[1] = 1.0
+    ms = T.median_flushed(lambda: x.lsq_grad(data, prm))
+    sets = [data] + [data.clone() for _ in range(7)]   # 8 x 24 MB = 192 MB > L2
+    ms_rot = T.rotating(lambda i: (lambda: x.lsq_grad(sets[i], prm)), len(sets))
+    out["c1_lsq_1M_f64"] = {"us": ms * 1e3, "evals_per_s": n / (ms / 1e3), "hbm_frac": 24 * n / (ms / 1e3) / 1e9 / peak_gbs,
+                            "us_back_to_back": ms_rot * 1e3, "hbm_frac_back_to_back": 24 * n / (ms_rot / 1e3) / 1e9 / peak_gbs,
+                            "l2": "flushed per launch | 8 input sets (192 MB) back to back"}
+    del sets
+    n2 = 1 << 28
+    data2 = torch.empty((n2, 3), dtype=torch.float64, device=dev).uniform_(-5, 5)
+    ms = T.median_flushed(lambda: x.lsq_grad(data2, prm), reps=5, flush_l2=False)
+    out["c1_lsq_2^28_f64"] = {"ms": ms, "evals_per_s": n2 / (ms / 1e3), "hbm_frac": 24 * n2 / (ms / 1e3) / 1e9 / peak_gbs}
+    del data2
+    # C2: accumulation 2^24 -> 1024
+    n = 1 << 24
+    c2 = {}
+    for dist in ("uniform", "zipf", "same"):
+        idx, val = orc.accumulate_inputs(n, 1024, dist, 42)
+        ti, tv = torch.from_numpy(idx).to(dev), torch.from_numpy(val).to(dev)
+        grad = torch.zeros(1024, device=dev)
+        ms = T.median_flushed(lambda: x.accumulate(ti, tv, grad))
+        c2[dist + "_us"] = ms * 1e3
+        if dist == "uniform":
+            c2["hbm_frac"] = 8 * n / (ms / 1e3) / 1e9 / peak_gbs
+            c2["elems_per_s"] = n / (ms / 1e3)
+            pairs = [(ti, tv)] + [(ti.clone(), tv.clone()) for _ in range(7)]   # 8 x 134 MB > L2
+            ms_rot = T.rotating(lambda i: (lambda: x.accumulate(pairs[i][0], pairs[i][1], grad)), len(pairs))
+            c2["us_back_to_back"] = ms_rot * 1e3
+            c2["hbm_frac_back_to_back"] = 8 * n / (ms_rot / 1e3) / 1e9 / peak_gbs
+            del pairs
+    out["c2_accumulate_2^24_to_1024"] = c2
+    # C3 variant B: one shared W, per-element adjoints of W accumulated into 9 gradients; 2^26 elements (8 GB > L2)
+    n3 = 1 << 26
+    ins3 = [torch.empty((n3, w), device=dev).uniform_(-1, 1) for w in (6, 6, 3)]
+    outs3 = [torch.empty((n3, w), device=dev) for w in (3, 6, 6)]
+    w9 = torch.empty(9, device=dev).uniform_(-1, 1)
+    gw9 = torch.zeros(9, device=dev)
+    ms = T.median_flushed(lambda: x.covproj_shared_w_fwd_bwd(ins3[0], w9, ins3[1], ins3[2], outs3[0], outs3[1], gw9, outs3[2]),
+                          reps=5, flush_l2=False)
+    out["c3b_covproj_shared_w_2^26"] = {"ms": ms, "evals_per_s": n3 / (ms / 1e3), "bytes_per_eval": 120,
+                                        "hbm_frac": 120 * n3 / (ms / 1e3) / 1e9 / peak_gbs}
+    del ins3, outs3
+    torch.cuda.empty_cache()
+    # a USER graph of op:: nodes through include/xyz_autodiff/batched.cuh (tests/csrc/batched_probe.cu)
+    try:
+        import ctypes
+        so = os.path.join(ROOT, "tests", "csrc", "_build", "libxyz_batched.so")
+        if os.path.exists(so):
+            B = ctypes.CDLL(so)
+            B.batched_chain.restype = ctypes.c_float
+            B.batched_chain.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_longlong, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int]
+            nb = 1 << 26
+            tin = torch.empty((nb, 15), device=dev).uniform_(-1, 1)
+            tout = torch.empty((nb, 15), device=dev)
+            w18 = torch.empty(18, device=dev).uniform_(-1, 1)
+            gw18 = torch.zeros(18, device=dev)
+            B.batched_chain(tin.data_ptr(), tout.data_ptr(), nb, w18.data_ptr(), gw18.data_ptr(), 2)
+            ms = B.batched_chain(tin.data_ptr(), tout.data_ptr(), nb, w18.data_ptr(), gw18.data_ptr(), 5)
+            out["batched_for_each_user_matmul_graph_2^26"] = {"ms": ms, "hbm_frac": 120 * nb / (ms / 1e3) / 1e9 / peak_gbs}
+            del tin, tout
+            torch.cuda.empty_cache()
+    except Exception as e:
+        out["batched_for_each"] = {"error": repr(e)}
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# the reference's CUDA kernels on the same GPU (N = 1)
+# ---------------------------------------------------------------------------------------------------------------------
+def reference_cuda(T, tp, tt, W, H, N, ours_splat_ms):
+    """oracle/_ref/libxyz_ref_cuda.so = the reference's own CUDA kernels built unmodified for sm_100a, timed with the same
+    CUDA-event harness.  The splat kernel visits every (pixel, Gaussian) pair, so it is timed at THREE reduced Gaussian
+    counts: if the cost per pair agrees, the figure at 100 K Gaussians is that rate times the pair count."""
+    import ctypes
+    import torch
+    import oracle_lib as orc
+    import xyz_autodiff_cuda_b200 as x
+    dev = T.dev
     path = os.path.join(ROOT, "oracle", "_ref", "libxyz_ref_cuda.so")
     if not os.path.exists(path):
         return {"unavailable": "oracle/_ref/libxyz_ref_cuda.so not built (needs /root/reference at build time)"}
@@ -378,72 +403,78 @@ def reference_cuda(dev, timed, x, tp, tt, W, H, N, ours_splat_ms):
     R.refcuda_accumulate.argtypes = [vp, vp, ll, vp]
     R.refcuda_covproj.argtypes = [vp] * 8 + [ll]
     res = {}
-    # splat, reduced N
-    n_ref = 256
-    grads = torch.zeros((n_ref, 9), device=dev)
     img = torch.zeros((W * H, 3), device=dev)
     loss = torch.zeros(1, device=dev)
-    sub = tp[:n_ref].contiguous()
-    ms = timed(lambda: R.refcuda_splat(sub.data_ptr(), grads.data_ptr(), tt.data_ptr(), img.data_ptr(), loss.data_ptr(),
-                                       W, H, n_ref), reps=3, flush_l2=False)
-    scaled = ms * N / n_ref
-    res["c4_splat"] = {"ms_at_N": {str(n_ref): ms}, "ms_per_iter_scaled_to_100K": scaled,
+    ns_per_pair = {}
+    for n_ref, reps in ((256, 3), (1024, 2), (4096, 1)):
+        grads = torch.zeros((n_ref, 9), device=dev)
+        sub = tp[:n_ref].contiguous()
+        ms = T.median_flushed(lambda: R.refcuda_splat(sub.data_ptr(), grads.data_ptr(), tt.data_ptr(), img.data_ptr(),
+                                                      loss.data_ptr(), W, H, n_ref), reps=reps, flush_l2=False)
+        ns_per_pair[str(n_ref)] = ms * 1e6 / (n_ref * W * H)
+    rates = list(ns_per_pair.values())
+    spread = (max(rates) - min(rates)) / min(rates)
+    scaled = rates[-1] * 1e-6 * N * W * H
+    # this repo at the same reduced size WITHOUT its cull (every pair evaluated, like the reference): the kernel factor
+    n_nc = 4096
+    sub = tp[:n_nc].contiguous()
+    g_nc = torch.zeros((n_nc, 9), device=dev)
+
+    def ours_nocull():
+        loss.zero_()
+        x.launch_gaussian_splatting(sub, g_nc, tt, img, loss, W, H, n_nc, x.FLAG_NO_CULL)
+
+    ms_nc = T.median_flushed(ours_nocull, reps=3, flush_l2=False)
+    ours_ns_per_pair = ms_nc * 1e6 / (n_nc * W * H)
+    res["c4_splat"] = {"reference_ns_per_pair_both_passes": ns_per_pair, "linearity_spread": spread,
+                       "reference_ms_per_iter_at_100K": scaled,
+                       "how": "measured rate at N=4096 x (100000 x 1024^2 pairs); three N agree to `linearity_spread`",
                        "speedup_of_this_repo": scaled / ours_splat_ms,
-                       "note": "reference kernel cost is linear in N (all pairs, 9 atomics per pair)"}
-    # the same reference sources compiled against THIS repo's headers (warp-aggregated add_grad): drop-in speed-up of
-    # unmodified user kernels
+                       "this_repo_no_cull_ns_per_pair": ours_ns_per_pair,
+                       "kernel_factor_per_pair": rates[-1] / ours_ns_per_pair,
+                       "algorithmic_factor_pairs_skipped": (scaled / ours_splat_ms) / (rates[-1] / ours_ns_per_pair)}
+    # the same reference sources compiled against THIS repo's headers (warp-aggregated add_grad)
     path2 = os.path.join(ROOT, "oracle", "_ref", "libxyz_ref_cuda_ourhdr.so")
-    R2 = None
     if os.path.exists(path2):
         R2 = ctypes.CDLL(path2)
         R2.refcuda_splat.argtypes = [vp] * 5 + [ctypes.c_int] * 3
-        R2.refcuda_lsq.argtypes = [vp, ll, vp]
-        R2.refcuda_accumulate.argtypes = [vp, vp, ll, vp]
-        ms2 = timed(lambda: R2.refcuda_splat(sub.data_ptr(), grads.data_ptr(), tt.data_ptr(), img.data_ptr(), loss.data_ptr(),
-                                             W, H, n_ref), reps=3, flush_l2=False)
-        res["c4_splat"]["reference_source_on_this_repos_headers_ms_at_N"] = {str(n_ref): ms2}
-        res["c4_splat"]["header_drop_in_speedup"] = ms / ms2
+        n_ref = 256
+        grads = torch.zeros((n_ref, 9), device=dev)
+        sub2 = tp[:n_ref].contiguous()
+        ms2 = T.median_flushed(lambda: R2.refcuda_splat(sub2.data_ptr(), grads.data_ptr(), tt.data_ptr(), img.data_ptr(),
+                                                        loss.data_ptr(), W, H, n_ref), reps=3, flush_l2=False)
+        res["c4_splat"]["reference_source_on_this_repos_headers_speedup"] = ns_per_pair["256"] * 1e-6 * n_ref * W * H / ms2
     # covproj 2^24
     n = 1 << 24
     ins = [torch.empty((n, w), device=dev).uniform_(-1, 1) for w in (6, 9, 6, 3)]
     outs = [torch.empty((n, w), device=dev) for w in (3, 6, 9, 6)]
-    ms_ref = timed(lambda: R.refcuda_covproj(*[t.data_ptr() for t in ins], *[t.data_ptr() for t in outs], n), reps=5,
-                   flush_l2=False)
-    ms_our = timed(lambda: x.covproj_fwd_bwd(*ins, *outs), reps=5, flush_l2=False)
-    res["c3_covproj_2^24"] = {"reference_ms": ms_ref, "this_repo_ms": ms_our, "speedup_of_this_repo": ms_ref / ms_our}
+    ms_ref = T.median_flushed(lambda: R.refcuda_covproj(*[t.data_ptr() for t in ins], *[t.data_ptr() for t in outs], n),
+                              reps=5, flush_l2=False)
+    ms_our = T.median_flushed(lambda: x.covproj_fwd_bwd(*ins, *outs), reps=5, flush_l2=False)
+    res["c3_covproj_2^24"] = {"reference_ms": ms_ref, "this_repo_ms": ms_our, "speedup": ms_ref / ms_our}
     del ins, outs
-    # least squares 1M
     n = 1_000_000
     data = torch.from_numpy(orc.lsq_data(n, 42)).to(dev)
     prm = torch.zeros(8, dtype=torch.float64, device=dev)
     prm[1] = 1.0
-    ms_ref = timed(lambda: R.refcuda_lsq(data.data_ptr(), n, prm.data_ptr()), reps=5)
-    ms_our = timed(lambda: x.lsq_grad(data, prm), reps=5)
-    res["c1_lsq_1M"] = {"reference_ms": ms_ref, "this_repo_ms": ms_our, "speedup_of_this_repo": ms_ref / ms_our}
-    if R2 is not None:
-        res["c1_lsq_1M"]["reference_source_on_this_repos_headers_ms"] = timed(
-            lambda: R2.refcuda_lsq(data.data_ptr(), n, prm.data_ptr()), reps=5)
-    # accumulation 2^24 -> 1024, uniform ids
+    ms_ref = T.median_flushed(lambda: R.refcuda_lsq(data.data_ptr(), n, prm.data_ptr()), reps=5)
+    ms_our = T.median_flushed(lambda: x.lsq_grad(data, prm), reps=5)
+    res["c1_lsq_1M"] = {"reference_ms": ms_ref, "this_repo_ms": ms_our, "speedup": ms_ref / ms_our}
     n = 1 << 24
     idx, val = orc.accumulate_inputs(n, 1024, "uniform", 42)
     ti, tv = torch.from_numpy(idx).to(dev), torch.from_numpy(val).to(dev)
     grad = torch.zeros(1024, device=dev)
-    ms_ref = timed(lambda: R.refcuda_accumulate(ti.data_ptr(), tv.data_ptr(), n, grad.data_ptr()), reps=5)
-    ms_our = timed(lambda: x.accumulate(ti, tv, grad), reps=5)
-    res["c2_accumulate_2^24_uniform"] = {"reference_ms": ms_ref, "this_repo_ms": ms_our,
-                                         "speedup_of_this_repo": ms_ref / ms_our}
-    if R2 is not None:
-        res["c2_accumulate_2^24_uniform"]["reference_source_on_this_repos_headers_ms"] = timed(
-            lambda: R2.refcuda_accumulate(ti.data_ptr(), tv.data_ptr(), n, grad.data_ptr()), reps=5)
+    ms_ref = T.median_flushed(lambda: R.refcuda_accumulate(ti.data_ptr(), tv.data_ptr(), n, grad.data_ptr()), reps=5)
+    ms_our = T.median_flushed(lambda: x.accumulate(ti, tv, grad), reps=5)
+    res["c2_accumulate_2^24"] = {"reference_ms": ms_ref, "this_repo_ms": ms_our, "speedup": ms_ref / ms_our}
     return res
 
 
-def run_splat_c5(args):
-    """BASELINE configs[4]: N Gaussians replicated, V views (targets) sharded round-robin over the ranks; one
-    iteration = zero_grad + this rank's views (forward + backward each) + NCCL all-reduce of the N x 9 gradient
-    buffer and the loss + Adam on every replica.  Strong scaling: V is fixed, ranks share it.
-    The reference has one target image only; view v = the reference's test image rolled by 64 v pixels in x and
-    37 v in y (our definition)."""
+# ---------------------------------------------------------------------------------------------------------------------
+# the splat half of the metric
+# ---------------------------------------------------------------------------------------------------------------------
+def splat_section(T, args, rank, world, comm, group, gather, sm_mhz):
+    """Returns (config.splat, roofline.splat, e2e.splat, launches, c4 inputs for the reference-CUDA comparison)."""
     import numpy as np
     import torch
     import torch.distributed as dist
@@ -451,152 +482,289 @@ def run_splat_c5(args):
     import xyz_autodiff_cuda_b200 as x
     from importlib import import_module
     par = import_module("xyz_autodiff_cuda_b200.parallel")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+    host_api = import_module("xyz_autodiff_cuda_b200.host_api")
+    dev = T.dev
     W = H = 1024
-    N, V = args.gaussians, args.views
+    N = 100_000
+    steps = max(3, min(args.steps, 20))
+    cfg, roof, e2e = {}, {}, {}
     params, target = orc.splat_c4_scene(N, W, H, 42)
-    tp = torch.from_numpy(params).to(dev)
-    base = torch.from_numpy(target).to(dev).reshape(H, W, 3)
-    mine = par.views_for_rank(V, rank, world)
-    targets = [torch.roll(base, shifts=(37 * v, 64 * v), dims=(0, 1)).reshape(W * H, 3).contiguous() for v in mine]
-    outs = [torch.zeros((W * H, 3), device=dev) for _ in mine]
-    grads = torch.zeros((N, 9), device=dev)
-    loss = torch.zeros(1, device=dev)
-    adam = torch.zeros((N, 18), device=dev)
-    st = torch.cuda.current_stream()
-    ar_ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    tp, tt = torch.from_numpy(params).to(dev), torch.from_numpy(target).to(dev)
+    x.reset_launch_count()
 
-    def step(it):
+    # ---- c4: one GPU (every rank runs it; rank 0's figures are reported)
+    grads = torch.zeros((N, 9), device=dev)
+    img = torch.zeros((W * H, 3), device=dev)
+    loss = torch.zeros(1, device=dev)
+
+    def c4_iter(i, flags=0):
         x.zero_gradients(grads)
         loss.zero_()
-        for t, o in zip(targets, outs):
-            x.launch_gaussian_splatting(tp, grads, t, o, loss, W, H, N)
-        ar_ev[0].record(st)
-        par.allreduce_shared_grads(grads, loss)
-        ar_ev[1].record(st)
-        x.adam_step_individual(tp, grads, adam, 0.1, 0.01, 0.001, 0.02, 0.05, iteration=it + 1)
+        x.launch_gaussian_splatting(tp, grads, tt, img, loss, W, H, N, flags)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
-    for i in range(max(3, args.warmup)):
-        step(i)
-    barrier()
-    x.reset_launch_count()
+    ms_c4 = T.loop(c4_iter, steps)
+    stats = x.splat_last_stats()
+    stage = {k: 0.0 for k in ("preprocess_hist_us", "scans_us", "scatter_us", "forward_loss_us", "backward_us", "total_us")}
+    for i in range(5):
+        c4_iter(i, x.FLAG_TIMING)
+        for k, v in x.splat_last_timing().items():
+            stage[k] += v / 5
+    pairs = stats["pairs_per_pass"]
+    # the training iteration (zero-grad fused into Adam) as ONE CUDA graph on a workspace
+    tr = par.ShardedSplatTrainer(x, tp, [tt], W, H, exchange="peer", group=x.PeerGroup(0, 1, lambda h: [h]),
+                                 gather=lambda h: [h], max_entries=int(stats["entries"] * 1.3))
+    tr.capture()
+    ms_graph = T.loop(lambda i: tr.replay(), steps, stream=tr.stream)
+    tr.close()
+    cfg["c4"] = {"workload": "100000 Gaussians, 1024x1024 (BASELINE configs[3]), fast-math flavour, result-preserving cull",
+                 "ms_per_iter": ms_c4, "iteration": "zero_grad + loss reset + launch (fwd + bwd)",
+                 "tile_list_entries": stats["entries"], "pairs_per_pass": pairs,
+                 "pair_evals_per_s": 2 * pairs / (ms_c4 / 1e3), "reference_pairs_per_pass": N * W * H,
+                 "stage_us": stage,
+                 "ms_per_training_iter_one_cuda_graph": ms_graph,
+                 "graph": "loss reset + workspace launch + Adam with fused zero-grad, captured once, replayed"}
+    clk = sm_mhz * 1e6
+    fwd_floor = pairs / (MUFU_PER_SM * SM_COUNT * clk) * 1e3
+    bwd_floor = pairs * BWD_FMA_OPS_PER_PAIR / (FMA_LANES_PER_SM * SM_COUNT * clk) * 1e3
+    roof = {"bound": "forward: MUFU pipe (one ex2 per pair); backward: FP32 FMA pipe (13 lane operations per pair)",
+            "sm_mhz": sm_mhz, "pairs_per_pass": pairs,
+            "forward": {"floor_ms": fwd_floor, "ms": stage["forward_loss_us"] / 1e3, "frac": fwd_floor / (stage["forward_loss_us"] / 1e3)},
+            "backward": {"floor_ms": bwd_floor, "ms": stage["backward_us"] / 1e3, "frac": bwd_floor / (stage["backward_us"] / 1e3)},
+            "iteration": {"floor_ms": fwd_floor + bwd_floor, "ms": ms_c4, "frac": (fwd_floor + bwd_floor) / ms_c4},
+            "hbm_minimum_bytes": N * 72 + W * H * 24, "note": "HBM is not the bound: 32.4 MB minimum traffic = 5 us"}
+    # ---- e2e.splat: parameters from pinned host memory, loss + gradients back, every iteration
+    host_it = host_api.SplatHostIteration(N, W, H, tt, int(stats["entries"] * 1.3), dev)
+    ph = torch.from_numpy(params).pin_memory()
+    for _ in range(3):
+        host_it.run(ph)
+    T.barrier()
+    t0 = time.perf_counter()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    a.record(st)
-    for i in range(args.steps):
-        step(i)
-    b.record(st)
-    barrier()
-    launches = x.launch_count()
-    t = torch.tensor([a.elapsed_time(b), ar_ev[0].elapsed_time(ar_ev[1])], dtype=torch.float64, device=dev)
+    a.record(T.st)
+    for _ in range(steps):
+        host_it.run(ph)
+    b.record(T.st)
+    torch.cuda.synchronize()
+    wall = (time.perf_counter() - t0) / steps * 1e3
+    e2e = {"ms_per_iter": max(a.elapsed_time(b) / steps, wall), "unit": "ms/iter", "h2d_bytes_per_step": host_it.h2d_bytes,
+           "d2h_bytes_per_step": host_it.d2h_bytes,
+           "api": "host_api.SplatHostIteration.run: pinned params -> H2D -> zero_grad + launch -> D2H loss + gradients, one sync"}
+    del host_it
+
+    # ---- c4_rows: ONE image over the ranks in row bands (strong scaling), three exchanges
+    r0, r1 = par.row_bands(H, world)[rank]
+    rows_cfg = {"workload": f"configs[3] on {world} GPU(s): one 1024x1024 image in {world} tile-aligned row band(s), Gaussians "
+                            "replicated, exchange of the N x 9 gradients + loss, Adam", "rows_per_gpu": r1 - r0}
+    variants = [("peer_graph", "peer", True)]
     if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t[0].item() / args.steps
-    if rank == 0:
-        stats = x.splat_last_stats()
-        print(json.dumps({
-            "metric": "splat fwd+bwd ms/iter", "value": ms, "unit": "ms/iter", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"mini-gaussian-splatting {N} Gaussians, {V} views of 1024x1024 sharded over "
-                                   f"{world} GPUs, NCCL all-reduce of N x 9 grads (BASELINE configs[4])",
-                       "views_per_gpu": len(mine), "allreduce_bytes": N * 36 + 4,
-                       "allreduce_ms_last_iter_max_over_ranks": t[1].item(),
-                       "tile_list_entries_per_view": stats["entries"], "l2": "per-iteration working set "
-                       f"{(stats['entries'] * 16 + N * 160) / 1e6:.0f} MB"},
-            "gpu_launches": int(launches)}), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        variants = [("nccl_allreduce", "nccl", False), ("nccl_sharded_adam", "nccl_sharded", False), ("peer", "peer", False),
+                    ("peer_graph", "peer", True)]
+    for name, exch, graph in variants:
+        tr = par.ShardedSplatTrainer(x, tp, [tt], W, H, rank, world, rows=(r0, r1), exchange=exch, comm=comm, group=group,
+                                     gather=gather)
+        if graph:
+            tr.capture()
+            ms = T.loop(lambda i: tr.replay(), steps, stream=tr.stream)
+        else:
+            ms = T.loop(lambda i: tr.iteration(i + 1), steps)
+        rows_cfg[name + "_ms_per_iter"] = ms
+        if name == "peer":
+            # stage breakdown (events between the stages; the exchange timed around its call)
+            st_sum = {k: 0.0 for k in stage}
+            ex_us = 0.0
+            ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            for i in range(5):
+                T.barrier()
+                tr.loss.zero_()
+                if tr.ws is not None:
+                    tr.ws.launch(tr.params, tr.grads, tt, tr.outputs[0], tr.loss, flags=x.FLAG_TIMING)
+                ea.record(T.st)
+                tr.ps.adam_step(*tr.lr, iteration=i + 1, total_loss=tr.loss)
+                eb.record(T.st)
+                torch.cuda.synchronize()
+                if tr.ws is not None:
+                    for k, v in x.splat_last_timing().items():
+                        st_sum[k] += v / 5
+                ex_us += ea.elapsed_time(eb) * 1e3 / 5
+            bd = {"preprocess_us": st_sum["preprocess_hist_us"], "bin_us": st_sum["scans_us"] + st_sum["scatter_us"],
+                  "fwd_us": st_sum["forward_loss_us"], "bwd_us": st_sum["backward_us"],
+                  "exchange_adam_zero_us": ex_us}
+            bd = {k: T.max_over_ranks(v) for k, v in bd.items()}
+            bd["gaps_us"] = ms * 1e3 - sum(bd.values())
+            rows_cfg["breakdown_us_max_over_ranks"] = bd
+        tr.close()
+        T.barrier()
+    cfg["c4_rows"] = rows_cfg
+
+    # ---- c5: 3 M Gaussians, 8 views sharded over the ranks
+    N5, V = args.gaussians, args.views
+    del tp, grads
+    torch.cuda.empty_cache()
+    params5, target5 = orc.splat_c4_scene(N5, W, H, 42)
+    tp5 = torch.from_numpy(params5).to(dev)
+    base = torch.from_numpy(target5).to(dev).reshape(H, W, 3)
+    mine = par.views_for_rank(V, rank, world)
+    targets = [torch.roll(base, shifts=(37 * v, 64 * v), dims=(0, 1)).reshape(W * H, 3).contiguous() for v in mine]
+    c5 = {"workload": f"{N5} Gaussians, {V} views of 1024x1024 sharded over {world} GPU(s) (BASELINE configs[4]); view v = the "
+                      "reference's test image rolled by (64 v, 37 v) pixels", "views_per_gpu": len(mine),
+          "allreduce_bytes": N5 * 36 + 4}
+    c5_steps = max(2, min(args.steps, 5))
+    variants5 = [("nccl_allreduce", "nccl")] + ([("peer", "peer")] if world > 1 else [])
+    me = None
+    for name, exch in variants5:
+        tr = par.ShardedSplatTrainer(x, tp5, targets, W, H, rank, world, exchange=exch, comm=comm, group=group, gather=gather,
+                                     max_entries=me)
+        me = tr.max_entries if tr.ws is not None else me
+        x.shutdown()  # the classic scratch of the sizing launch (1 GB at 3 M Gaussians) is not needed any more
+        ms = T.loop(lambda i: tr.iteration(i + 1), c5_steps, warmup=2)
+        c5[name + "_ms_per_iter"] = ms
+        if name == "nccl_allreduce":
+            if tr.ws is not None:
+                c5["tile_list_entries_per_view"] = tr.ws.status()["entries"]
+            if world > 1:
+                ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                T.barrier()
+                ea.record(T.st)
+                comm.allreduce_grads(tr.grads)
+                eb.record(T.st)
+                torch.cuda.synchronize()
+                ar = T.max_over_ranks(ea.elapsed_time(eb))
+                c5["allreduce_ms"] = ar
+                c5["allreduce_algbw_gbs"] = N5 * 36 / (ar / 1e3) / 1e9
+        tr.close()
+        del tr
+        torch.cuda.empty_cache()
+        T.barrier()
+    cfg["c5"] = c5
+    return cfg, roof, e2e, x.launch_count(), (params, tt)
 
 
-
-def run_splat_c4_rows(args):
-    """BASELINE configs[3] on G GPUs (north_star: partition "by image tile"): ONE 1024 x 1024 target, Gaussians replicated,
-    every rank renders and back-propagates a tile-aligned band of rows, then the N x 9 gradients + loss are
-    all-reduced (NCCL, in place) and Adam runs on every replica.  Strong scaling."""
+# ---------------------------------------------------------------------------------------------------------------------
+# multi-GPU: fused exchanges of the small shared-gradient vectors + parity of every sharded path
+# ---------------------------------------------------------------------------------------------------------------------
+def multi_gpu_section(T, rank, world, comm, group, gather):
+    import numpy as np
     import torch
     import torch.distributed as dist
     import oracle_lib as orc
     import xyz_autodiff_cuda_b200 as x
     from importlib import import_module
     par = import_module("xyz_autodiff_cuda_b200.parallel")
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    W = H = 1024
-    N = args.gaussians if args.gaussians != 3_000_000 else 100_000
-    params, target = orc.splat_c4_scene(N, W, H, 42)
-    tp, tt = torch.from_numpy(params).to(dev), torch.from_numpy(target).to(dev)
-    out = torch.zeros((W * H, 3), device=dev)
-    grads = torch.zeros((N, 9), device=dev)
-    loss = torch.zeros(1, device=dev)
-    adam = torch.zeros((N, 18), device=dev)
-    st = torch.cuda.current_stream()
+    dev = T.dev
+    D = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
+    out = {}
+    problems = []
 
-    def step(it):
-        x.zero_gradients(grads)
-        loss.zero_()
-        par.splat_iteration_sharded(x, tp, grads, [tt], [out], loss, W, H, mode="rows")
-        x.adam_step_individual(tp, grads, adam, 0.1, 0.01, 0.001, 0.02, 0.05, iteration=it + 1)
+    def check(ok, what):
+        if not ok:
+            problems.append(what)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    # C1: 1 M points over the ranks; kernel + NCCL all-reduce of the 4 sums vs the exchange inside the kernel
+    data = orc.lsq_data(1_000_000, 42)
+    vals = (0.0, 1.0, 0.0, 0.0)
+    b, e = par.shard_range(data.shape[0], rank, world)
+    dd = D(data[b:e])
+    buf = torch.zeros(8, dtype=torch.float64, device=dev)
+    buf[:4] = torch.tensor(vals, dtype=torch.float64)
+
+    def c1_nccl(i):
+        x.lsq_grad(dd, buf, None)
+        comm.allreduce_f64(buf[4:])
+
+    def c1_fused(i):
+        x.lsq_grad_allreduce(dd, buf, group, None)
+
+    out["c1_lsq_1M"] = {"kernel_plus_nccl_us": T.loop(c1_nccl, 200, 20) * 1e3, "fused_peer_kernel_us": T.loop(c1_fused, 200, 20) * 1e3}
+    prm = torch.zeros(8, dtype=torch.float64, device=dev)
+    prm[:4] = torch.tensor(vals, dtype=torch.float64)
+    x.lsq_grad_allreduce(dd, prm, group, None)
+    torch.cuda.synchronize()
+    full_g, _ = orc.lsq_grad(data, vals, threads=os.cpu_count() or 1)
+    check(np.allclose(prm[4:].cpu().numpy(), full_g, rtol=1e-10), "c1 sharded gradient vs oracle")
+    same = prm.clone()
+    dist.broadcast(same, 0)
+    check(torch.equal(same, prm), "c1 ranks disagree bitwise")
+    # C2: 2^24 -> 1024
+    idx, val = orc.accumulate_inputs(1 << 24, 1024, "uniform", 42)
+    b, e = par.shard_range(idx.size, rank, world)
+    ti, tv = D(idx[b:e]), D(val[b:e])
+    grad = torch.zeros(1024, device=dev)
+
+    def c2_nccl(i):
+        x.accumulate(ti, tv, grad)
+        comm.allreduce_grads(grad)
+
+    def c2_fused(i):
+        x.accumulate_allreduce(ti, tv, grad, group)
+
+    out["c2_accumulate_2^24"] = {"kernel_plus_nccl_us": T.loop(c2_nccl, 100, 10) * 1e3, "fused_peer_finish_us": T.loop(c2_fused, 100, 10) * 1e3}
+    grad.zero_()
+    x.accumulate_allreduce(ti, tv, grad, group)
+    torch.cuda.synchronize()
+    exact = orc.accumulate_exact(idx, val, 1024)
+    check((np.abs(grad.cpu().numpy() - exact) <= 1e-4 * orc.accumulate_exact(idx, np.abs(val), 1024) + 1e-30).all(),
+          "c2 sharded sums vs exact")
+    del ti, tv
+    # C3-B: shared W, 2^24 elements per rank, the 9 shared gradients exchanged by the kernel's last CTA
+    n3 = 1 << 24
+    ins3 = [torch.empty((n3, w), device=dev).uniform_(-1, 1) for w in (6, 6, 3)]
+    outs3 = [torch.empty((n3, w), device=dev) for w in (3, 6, 6)]
+    w9 = torch.full((9,), 0.25, device=dev)
+    gw9 = torch.zeros(9, device=dev)
+
+    def c3b_fused(i):
+        x.covproj_shared_w_fwd_bwd(ins3[0], w9, ins3[1], ins3[2], outs3[0], outs3[1], gw9, outs3[2], group=group)
+
+    def c3b_plain(i):
+        x.covproj_shared_w_fwd_bwd(ins3[0], w9, ins3[1], ins3[2], outs3[0], outs3[1], gw9, outs3[2])
+
+    out["c3b_covproj_shared_w_2^24_per_gpu"] = {"kernel_only_ms": T.loop(c3b_plain, 10, 3), "fused_allreduce_ms": T.loop(c3b_fused, 10, 3)}
+    gw9.zero_()
+    c3b_fused(0)
+    torch.cuda.synchronize()
+    same = gw9.clone()
+    dist.broadcast(same, 0)
+    check(torch.equal(same, gw9), "c3b ranks disagree bitwise")
+    del ins3, outs3
+    torch.cuda.empty_cache()
+    # splat: row bands + fused peer exchange against ONE rank doing the whole image (small scene, 3 iterations)
+    W, H, N = 160, 128, 300
+    params, target = orc.splat_scene(N, W, H, seed=21)
+    tt = D(target)
+    r0, r1 = par.row_bands(H, world)[rank]
+    tr = par.ShardedSplatTrainer(x, D(params), [tt], W, H, rank, world, rows=(r0, r1), exchange="peer", group=group,
+                                 gather=gather, lr=(0.5, 0.01, 0.01, 0.01, 0.02), max_entries=80 * N)
+    p1, g1, a1 = D(params), torch.zeros((N, 9), device=dev), torch.zeros((N, 18), device=dev)
+    l1, o1 = torch.zeros(1, device=dev), torch.zeros((W * H, 3), device=dev)
+    for it in range(1, 4):
+        tr.iteration(it)
+        l1.zero_()
+        x.launch_gaussian_splatting(p1, g1, tt, o1, l1, W, H, N)
+        x.adam_step_individual(p1, g1, a1, 0.5, 0.01, 0.01, 0.01, 0.02, iteration=it, zero_grads=True)
         torch.cuda.synchronize()
-
-    for i in range(max(3, args.warmup)):
-        step(i)
-    barrier()
-    x.reset_launch_count()
-    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    barrier()
-    a.record(st)
-    for i in range(args.steps):
-        step(i)
-    b.record(st)
-    barrier()
-    launches = x.launch_count()
-    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = t[0].item() / args.steps
-    if rank == 0:
-        print(json.dumps({
-            "metric": "splat fwd+bwd ms/iter", "value": ms, "unit": "ms/iter", "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms, "higher_is_better": False, "scaling": "strong",
-            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": f"mini-gaussian-splatting {N} Gaussians, one 1024x1024 image split into {world} row bands, "
-                                   f"NCCL all-reduce of N x 9 grads + Adam on every replica (BASELINE configs[3] on {world} GPUs)",
-                       "rows_per_gpu": H // world, "allreduce_bytes": N * 36 + 4,
-                       "l2": "per-iteration working set (entries + records + rest tiles) streamed once; Adam moves the Gaussians every step"},
-            "gpu_launches": int(launches)}), flush=True)
-    if world > 1:
-        dist.barrier()
-        dist.destroy_process_group()
+        check(abs(tr.loss.item() - l1.item()) <= 1e-4 * abs(l1.item()), f"row bands: loss at iteration {it}")
+        check(np.allclose(tr.params.cpu().numpy(), p1.cpu().numpy(), rtol=1e-3, atol=1e-3), f"row bands: parameters at iteration {it}")
+        if r1 > r0 and it == 1:
+            check(torch.equal(tr.outputs[0].reshape(H, W, 3)[r0:r1], o1.reshape(H, W, 3)[r0:r1]), "row bands: image rows differ")
+        same = tr.params.clone()
+        dist.broadcast(same, 0)
+        check(torch.equal(same, tr.params), "row bands: ranks disagree bitwise")
+    tr.close()
+    flag = torch.tensor([len(problems)], device=dev)
+    dist.all_reduce(flag)
+    out["parity"] = "ok" if flag.item() == 0 else "FAILED: " + "; ".join(problems)
+    out["parity_checks"] = "c1 / c2 / c3b fused exchanges vs oracle and bitwise between ranks; splat row bands + fused peer optimiser step vs one rank, 3 iterations"
+    return out
 
 
+# ---------------------------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
     import torch.distributed as dist
     import xyz_autodiff_cuda_b200 as x
     from importlib import import_module
     host_api = import_module("xyz_autodiff_cuda_b200.host_api")
+    par = import_module("xyz_autodiff_cuda_b200.parallel")
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -608,9 +776,10 @@ def run_ours(args):
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     x.lib()
-    peak_gbs, peak_src = measured_peak_gbs()
+    peak_gbs, peak_src, sm_max_mhz = measured_peaks()
+    T = Timers(dev, world)
 
-    # weak scaling: every rank owns E elements; the path has no data-path collective (per-element gradients)
+    # ---- headline: weak scaling, every rank owns E elements; no data-path collective (per-element gradients)
     E = args.elems
     gen = torch.Generator(device=dev).manual_seed(42 + rank)
     ins = [torch.empty((E, w), dtype=torch.float32, device=dev) for w in (6, 9, 6, 3)]
@@ -622,26 +791,18 @@ def run_ours(args):
     def step():
         x.covproj_fwd_bwd(*ins, *outs)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
-        torch.cuda.synchronize()
-
     for _ in range(max(3, args.warmup)):
         step()
-    barrier()
+    T.barrier()
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     x.reset_launch_count()
-    barrier()
+    T.barrier()
     total_ms, per = time_kernel(step, args.steps, 0, st)
     launches = x.launch_count()
-    barrier()
-    t = torch.tensor([total_ms], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = t.item()
+    T.barrier()
+    total_ms = T.max_over_ranks(total_ms)
     ms_per_step = total_ms / args.steps
     value = world * E / (ms_per_step / 1e3)
     kernel_ms = sum(per) / len(per)  # one launch per step: the kernel's average launch duration on this rank
@@ -658,19 +819,57 @@ def run_ours(args):
     h2d = d2h = 0
     for _ in range(2):
         h2d, d2h = pipe.run(h_in, h_out)
-    barrier()
+    T.barrier()
     e2e_steps = max(1, min(args.steps, 5))
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     a.record(st)
     for _ in range(e2e_steps):
         pipe.run(h_in, h_out)
     b.record(st)
-    barrier()
-    t = torch.tensor([a.elapsed_time(b)], dtype=torch.float64, device=dev)
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * e2e_elems * e2e_steps / (t.item() / 1e3)
+    T.barrier()
+    e2e_value = world * e2e_elems * e2e_steps / (T.max_over_ranks(a.elapsed_time(b)) / 1e3)
     clocks = sampler.stop() if rank == 0 else None
+    del ins, h_in, h_out, pipe
+    torch.cuda.empty_cache()
+
+    # ---- the communicators of the splat / multi-GPU sections (host channel: torch.distributed object collectives)
+    comm = group = None
+
+    def gather(obj):
+        if world == 1:
+            return [obj]
+        box = [None] * world
+        dist.all_gather_object(box, obj)
+        return box
+
+    def bcast(obj):
+        if world == 1:
+            return obj
+        box = [obj]
+        dist.broadcast_object_list(box, 0)
+        return box[0]
+
+    splat_cfg = splat_roof = splat_e2e = multi = None
+    splat_launches = 0
+    err = {}
+    if not args.no_splat:
+        try:
+            if world > 1:
+                comm = x.Comm(rank, world, bcast)
+            group = x.PeerGroup(rank, world, gather)
+            if world > 1:
+                dist.barrier()
+            sm_mhz = (clocks or {}).get("sm_mhz") or sm_max_mhz
+            sm_mhz = bcast(sm_mhz)
+            splat_cfg, splat_roof, splat_e2e, splat_launches, c4_inputs = splat_section(T, args, rank, world, comm, group, gather,
+                                                                                       float(sm_mhz))
+        except Exception as ex:  # the headline must still be printed
+            err["splat"] = repr(ex)
+        if world > 1 and "splat" not in err:
+            try:
+                multi = multi_gpu_section(T, rank, world, comm, group, gather)
+            except Exception as ex:
+                err["multi_gpu"] = repr(ex)
 
     if rank == 0:
         line = {
@@ -691,16 +890,6 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "clocks": clocks,
         }
-        if world == 1:
-            base, _ = cpu_covproj(1 << 23)
-            line["cpu_baseline"] = base
-            if not args.no_also:
-                del ins, h_in, h_out, pipe
-                torch.cuda.empty_cache()
-                try:
-                    line["also"] = also_workloads(dev, peak_gbs)
-                except Exception as e:  # the headline must still be printed
-                    line["also"] = {"error": repr(e)}
         traffic_file = os.path.join(ROOT, "profiles", "covproj_traffic.json")
         if os.path.exists(traffic_file):
             try:
@@ -710,9 +899,39 @@ def run_ours(args):
                 line["roofline"]["traffic_source"] = tr.get("source")
             except Exception:
                 pass
-        print(json.dumps(line), flush=True)
+        if splat_cfg is not None:
+            line["config"]["splat"] = splat_cfg
+            line["roofline"]["splat"] = splat_roof
+            line["e2e"]["splat"] = splat_e2e
+            line["config"]["splat"]["gpu_launches_rank0"] = int(splat_launches)
+        if multi is not None:
+            line["config"]["multi_gpu"] = multi
+        if err:
+            line["config"]["errors"] = err
+        if world == 1:
+            base, _ = cpu_covproj(1 << 23)
+            line["cpu_baseline"] = base
+            if not args.no_other:
+                try:
+                    line["config"]["other_configs"] = other_configs(T, peak_gbs)
+                except Exception as ex:
+                    line["config"]["other_configs"] = {"error": repr(ex)}
+                if splat_cfg is not None:
+                    try:
+                        params, tt = c4_inputs
+                        tp = torch.from_numpy(params).to(dev)
+                        line["config"]["reference_cuda"] = reference_cuda(T, tp, tt, 1024, 1024, 100_000, splat_cfg["c4"]["ms_per_iter"])
+                    except Exception as ex:
+                        line["config"]["reference_cuda"] = {"error": repr(ex)}
+                try:
+                    line["config"]["reference_cpu_other_configs"] = cpu_reference_other_configs()
+                except Exception as ex:
+                    line["config"]["reference_cpu_other_configs"] = {"error": repr(ex)}
+        print(json.dumps(sig(line, 6)), flush=True)
     if world > 1:
         dist.barrier()
+        if comm is not None:
+            comm.destroy()
         dist.destroy_process_group()
 
 
@@ -724,19 +943,13 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--elems", type=int, default=FULL_E, help="elements per GPU (default 2^26, BASELINE configs[2])")
     ap.add_argument("--e2e-elems", type=int, default=1 << 25, help="elements per e2e step (host pinned memory bound)")
-    ap.add_argument("--no-also", action="store_true", help="skip the brief timings of the other configs")
-    ap.add_argument("--workload", default="covproj", choices=["covproj", "splat_c5", "splat_c4_rows"],
-                    help="covproj = the headline (BASELINE configs[2]); splat_c5 = configs[4], views sharded over the ranks; "
-                         "splat_c4_rows = configs[3] with ONE image split into row bands over the ranks")
-    ap.add_argument("--gaussians", type=int, default=3_000_000, help="splat_c5: number of Gaussians")
-    ap.add_argument("--views", type=int, default=8, help="splat_c5: number of views (targets)")
+    ap.add_argument("--no-splat", action="store_true", help="skip the splat half of the metric (and the multi-GPU section)")
+    ap.add_argument("--no-other", action="store_true", help="N = 1: skip the brief timings of the other configs / the reference CUDA kernels")
+    ap.add_argument("--gaussians", type=int, default=3_000_000, help="c5: number of Gaussians")
+    ap.add_argument("--views", type=int, default=8, help="c5: number of views (targets)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
-    elif args.workload == "splat_c5":
-        run_splat_c5(args)
-    elif args.workload == "splat_c4_rows":
-        run_splat_c4_rows(args)
     else:
         run_ours(args)
 

@@ -64,3 +64,19 @@ def test_splat_iteration_host_equals_the_device_call():
     x.launch_gaussian_splatting(torch.from_numpy(params).to(DEV), g2, tt, o2, l2, W, H, N, x.FLAG_DETERMINISTIC)
     torch.cuda.synchronize()
     assert torch.equal(grads, g2.cpu()) and torch.equal(loss, l2.cpu()) and torch.equal(out, o2)
+
+
+def test_splat_host_iteration_class_equals_the_device_call():
+    """host_api.SplatHostIteration (pinned params in, pinned loss + gradients out, workspace launch): what bench.py times
+    as the splat e2e."""
+    W, H, N = 96, 64, 200
+    params, target = orc.splat_scene(N, W, H, seed=5)
+    tt = torch.from_numpy(target).to(DEV)
+    it = host_api.SplatHostIteration(N, W, H, tt, 100 * N, DEV, flags=x.FLAG_DETERMINISTIC)
+    ph = torch.from_numpy(params).pin_memory()
+    g = torch.zeros((N, 9), device=DEV); o = torch.zeros((W * H, 3), device=DEV); l = torch.zeros(1, device=DEV)
+    x.launch_gaussian_splatting(torch.from_numpy(params).to(DEV), g, tt, o, l, W, H, N, x.FLAG_DETERMINISTIC)
+    for _ in range(2):
+        loss, grads = it.run(ph)
+        assert loss.item() == l.item() and torch.equal(grads, g.cpu()) and torch.equal(it.output, o)
+    assert it.h2d_bytes == N * 36 and it.d2h_bytes == N * 36 + 4

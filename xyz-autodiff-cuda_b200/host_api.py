@@ -100,3 +100,40 @@ def splat_iteration_host(params_host: torch.Tensor, target_dev: torch.Tensor, ou
     loss = torch.zeros(1, dtype=torch.float32, device=device)
     x.launch_gaussian_splatting(params, grads, target_dev, output_dev, loss, width, height, n, flags)
     return loss.cpu(), grads.cpu()
+
+
+class SplatHostIteration:
+    """The device work of one iteration of the reference's training loop (gaussian_splatting_training.cu:127-151:
+    zero gradients, reset the loss, launch_gaussian_splatting, read the loss back) for a caller whose Gaussians live in
+    HOST memory: the parameters come from a pinned host array every iteration, the loss and the gradients go back to
+    pinned host arrays.  Everything is queued on one stream through a caller-owned workspace
+    (xyz_launch_gaussian_splatting_ws: no allocation, no synchronisation inside); `run` returns after ONE stream
+    synchronisation.  This is what bench.py times as the splat `e2e`."""
+
+    def __init__(self, num_gaussians: int, width: int, height: int, target_dev: torch.Tensor, max_entries: int,
+                 device, flags: int = 0):
+        self.n, self.w, self.h, self.device = num_gaussians, width, height, device
+        self.target = target_dev
+        f = torch.float32
+        self.params = torch.empty((num_gaussians, 9), dtype=f, device=device)
+        self.grads = torch.empty((num_gaussians, 9), dtype=f, device=device)
+        self.output = torch.empty((width * height, 3), dtype=f, device=device)
+        self.loss = torch.zeros(1, dtype=f, device=device)
+        self.grads_host = torch.empty((num_gaussians, 9), dtype=f).pin_memory()
+        self.loss_host = torch.zeros(1, dtype=f).pin_memory()
+        self.ws = x.SplatWorkspace(width, height, num_gaussians, max_entries, flags, device=device)
+        self.h2d_bytes = num_gaussians * 36
+        self.d2h_bytes = num_gaussians * 36 + 4
+
+    def run(self, params_host: torch.Tensor, stream=None):
+        """params_host: pinned (N, 9) float32.  Returns (loss_host (1,), grads_host (N, 9)) -- pinned, reused per call."""
+        st = stream if stream is not None else torch.cuda.current_stream(self.device)
+        with torch.cuda.stream(st):
+            self.params.copy_(params_host, non_blocking=True)
+            x.zero_gradients(self.grads, stream=st)
+            self.loss.zero_()
+            self.ws.launch(self.params, self.grads, self.target, self.output, self.loss, stream=st)
+            self.loss_host.copy_(self.loss, non_blocking=True)
+            self.grads_host.copy_(self.grads, non_blocking=True)
+        st.synchronize()
+        return self.loss_host, self.grads_host

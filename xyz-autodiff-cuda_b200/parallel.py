@@ -90,3 +90,105 @@ def make_peer_group(x):
     if world > 1:
         dist.barrier()  # every rank has opened every mailbox before the first kernel stores into them
     return group
+
+
+class ShardedSplatTrainer:
+    """One rank of the reference's training loop (GaussianSplattingTrainer::train, gaussian_splatting_training.cu:127-158:
+    zero gradients, reset the loss, launch, Adam) sharded over the GPUs of one box -- by VIEW (C5: `targets` = this rank's
+    views, whole image each) or by ROW BAND of one image (C4 on G GPUs: `rows` = this rank's band).  Gaussians are
+    replicated; per iteration the ranks exchange the N x 9 gradients (+ the loss):
+
+      exchange = "nccl"          xyz_allreduce_grads (the library's own NCCL communicator) + Adam on every replica
+                                 (the form BASELINE configs[4] names)
+      exchange = "nccl_sharded"  xyz_adam_step_individual_sharded: reduce-scatter, Adam on the rank's range, all-gather
+      exchange = "peer"          xyz_adam_step_individual_peer: ONE kernel over NVLink peer memory, no NCCL call; with
+                                 `graph=True` the whole iteration is one captured CUDA graph (no host work per iteration)
+
+    Every launch goes through a caller-owned workspace (no allocation / synchronisation inside the iteration)."""
+
+    LR = (0.1, 0.01, 0.001, 0.02, 0.05)
+
+    def __init__(self, x, params, targets, width, height, rank=0, world=1, rows=None, exchange="nccl", comm=None,
+                 group=None, gather=None, flags=0, lr=None, max_entries=None):
+        self.x, self.w, self.h, self.rank, self.world = x, width, height, rank, world
+        self.exchange, self.comm, self.flags = exchange, comm, flags
+        self.lr = tuple(lr) if lr is not None else self.LR
+        self.targets = list(targets)
+        dev = torch.device("cuda", torch.cuda.current_device())
+        n = params.shape[0]
+        self.n = n
+        self.rows = rows
+        self.ps = None
+        if exchange == "peer":
+            self.ps = x.PeerSplat(group, n, gather)
+            self.params, self.grads, self.adam = self.ps.params, self.ps.grads, self.ps.adam
+            self.params.copy_(params)
+        else:
+            if world > 1 and comm is None:
+                raise ValueError("exchange over NCCL needs a Comm")
+            self.params = params.clone()
+            self.grads = torch.zeros((n, 9), dtype=torch.float32, device=dev)
+            self.adam = torch.zeros((n, 18), dtype=torch.float32, device=dev)
+        self.loss = torch.zeros(1, dtype=torch.float32, device=dev)
+        self.outputs = [torch.zeros((width * height, 3), dtype=torch.float32, device=dev) for _ in self.targets]
+        self.empty = rows is not None and rows[1] <= rows[0]
+        self.ws = None
+        if self.targets and not self.empty:
+            if max_entries is None:  # learn the list length of this scene once (one ordinary launch), + 30 % head-room
+                scratch_g = torch.zeros((n, 9), dtype=torch.float32, device=dev)
+                x.launch_gaussian_splatting(self.params, scratch_g, self.targets[0], self.outputs[0], self.loss, width, height,
+                                            n, flags, rows=rows)
+                max_entries = int(x.splat_last_stats()["entries"] * 1.3) + 4096
+                self.loss.zero_()
+            self.max_entries = max_entries
+            self.ws = x.SplatWorkspace(width, height, n, max_entries, flags, rows=rows)
+        self.graph = None
+        self.stream = None
+
+    def _enqueue(self, it, stream=None, flags=None):
+        x = self.x
+        if stream is None:
+            self.loss.zero_()
+        else:
+            with torch.cuda.stream(stream):
+                self.loss.zero_()
+        if self.ws is not None:
+            for tgt, out in zip(self.targets, self.outputs):
+                self.ws.launch(self.params, self.grads, tgt, out, self.loss, flags=flags, stream=stream)
+        if self.exchange == "peer":
+            self.ps.adam_step(*self.lr, iteration=it, total_loss=self.loss, stream=stream)
+        elif self.exchange == "nccl_sharded" and self.world > 1:
+            self.comm.adam_step_individual_sharded(self.params, self.grads, self.adam, *self.lr, iteration=max(it, 1),
+                                                   total_loss=self.loss, stream=stream)
+        else:
+            if self.world > 1:
+                self.comm.allreduce_grads(self.grads, stream=stream)
+                self.comm.allreduce_grads(self.loss, stream=stream)
+            x.adam_step_individual(self.params, self.grads, self.adam, *self.lr, iteration=max(it, 1), stream=stream,
+                                   zero_grads=True)
+
+    def iteration(self, it, flags=None):
+        """Enqueue iteration `it` (1-based) on the current stream; nothing waits for the GPU."""
+        self._enqueue(it, None, flags)
+
+    def capture(self):
+        """Capture one iteration as a CUDA graph (exchange == "peer": the optimiser step counts its iterations on the
+        device, so every replay is the next Adam step)."""
+        if self.exchange != "peer":
+            raise ValueError("graph capture needs the device-side step counter of the peer exchange")
+        self.stream = torch.cuda.Stream()
+        self.graph = torch.cuda.CUDAGraph()
+        self.stream.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(self.stream):
+            with torch.cuda.graph(self.graph, stream=self.stream, capture_error_mode="thread_local"):
+                self._enqueue(0, self.stream)
+        torch.cuda.current_stream().wait_stream(self.stream)
+
+    def replay(self):
+        self.graph.replay()
+
+    def close(self):
+        self.graph = None
+        if self.ps is not None:
+            self.ps.close()
+            self.ps = None
