@@ -47,6 +47,7 @@ struct PeerMailbox {
     double loss_splat[2][XYZ_PEER_MAX_WORLD];
     unsigned long long splat_seq;   // last sequence number used (two per call)
     unsigned long long splat_iter;  // optimiser steps taken with iteration == 0 ("count them yourself")
+    unsigned int splat_ticket;      // last-CTA election of the owner's kernel (left at 0 by every launch)
 };
 struct PeerArgs {  // passed to kernels by value; world <= 1 means "no exchange"
     PeerMailbox* box[XYZ_PEER_MAX_WORLD];

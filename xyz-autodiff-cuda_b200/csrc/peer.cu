@@ -135,13 +135,14 @@ constexpr int kPeerAdamThreads = 256;
 
 __global__ void __launch_bounds__(kPeerAdamThreads)
     peer_adam_kernel(PeerArgs pa, PeerAdamArgs a, float* __restrict__ adam, long long n_floats, float* total_loss,
-                     unsigned int* ticket, int iteration, float lr0, float lr1, float lr2, float lr3, float lr4) {
+                     int iteration, float lr0, float lr1, float lr2, float lr3, float lr4) {
     __shared__ int s_ok;
     __shared__ int s_last;
     __shared__ float s_lr[5];
     const int tid = threadIdx.x;
     const int W = pa.world, R = pa.rank;
     PeerMailbox* const me = pa.box[R];
+    unsigned int* const ticket = &me->splat_ticket;  // in the mailbox, not in library scratch: nothing to allocate, ever
     // sequence numbers live on the device (graph replays): this call uses seq (round 1) and seq + 1 (round 2).
     // Nobody changes splat_seq / splat_iter before the LAST CTA of this launch has read them (it does so below).
     const unsigned long long seq = me->splat_seq + 1ull;
@@ -265,17 +266,13 @@ extern "C" int xyz_adam_step_individual_peer(const xyz_peer_group* group, const 
     pa.world = group->world;
     pa.seq = 0;  // unused: the sequence lives in the mailbox
     a.beta1 = beta1; a.beta2 = beta2; a.eps = epsilon;
-    void* scratch = nullptr;
-    int err = scratch_get(SCRATCH_REDUCE, 256, &scratch, st);
-    if (err) return err;
     const long long n_floats = static_cast<long long>(num_gaussians) * 9;
     const long long mine4 = n_floats / 4 / group->world + 1;
     long long want = (mine4 + kPeerAdamThreads - 1) / kPeerAdamThreads;
     const long long cap = 4LL * sm_count();
     const int grid = static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
-    peer_adam_kernel<<<grid, kPeerAdamThreads, 0, st>>>(pa, a, reinterpret_cast<float*>(adam), n_floats, total_loss,
-                                                        static_cast<unsigned int*>(scratch), iteration, lr_host[0], lr_host[1],
-                                                        lr_host[2], lr_host[3], lr_host[4]);
+    peer_adam_kernel<<<grid, kPeerAdamThreads, 0, st>>>(pa, a, reinterpret_cast<float*>(adam), n_floats, total_loss, iteration,
+                                                        lr_host[0], lr_host[1], lr_host[2], lr_host[3], lr_host[4]);
     count_launch();
     return last_error();
 }
