@@ -17,7 +17,7 @@ import xyz_autodiff_cuda_b200 as x  # noqa: E402
 
 dev = torch.device("cuda:0")
 reps = int(os.environ.get("PROF_REPS", "2"))
-which = os.environ.get("PROF_ONLY", "covproj,covproj_shared_w,batched,lsq,accumulate,splat,adam").split(",")
+which = os.environ.get("PROF_ONLY", "covproj,covproj_shared_w,batched,lsq,accumulate,splat,adam,splat_band").split(",")
 
 if "covproj" in which:
     E = 1 << 26
@@ -106,4 +106,24 @@ if "splat" in which or "adam" in which:
         if "adam" in which:
             x.adam_step_individual(tp, grads, adam, 0.1, 0.01, 0.001, 0.02, 0.05, iteration=it + 1)
     torch.cuda.synchronize()
+if "splat_band" in which:
+    # round 2: what ONE rank of the 8-GPU row-band configuration runs per iteration: a 128-row band of the C4 scene through
+    # a caller-owned workspace (band-local histograms, three-deep staging in the forward pass), then the fused
+    # peer-memory optimiser step (world size 1 here: the reduce-scatter / all-gather degenerate to local traffic)
+    W = H = 1024
+    N = 100_000
+    params, target = orc.splat_c4_scene(N, W, H, 42)
+    tt = torch.from_numpy(target).to(dev)
+    grp = x.PeerGroup(0, 1, lambda h: [h])
+    ps = x.PeerSplat(grp, N, lambda h: [h])
+    ps.params.copy_(torch.from_numpy(params).to(dev))
+    img = torch.zeros((W * H, 3), device=dev)
+    loss = torch.zeros(1, device=dev)
+    ws = x.SplatWorkspace(W, H, N, 1_200_000, rows=(448, 576))
+    for it in range(reps):
+        loss.zero_()
+        ws.launch(ps.params, ps.grads, tt, img, loss)
+        ps.adam_step(0.1, 0.01, 0.001, 0.02, 0.05, iteration=it + 1, total_loss=loss)
+    torch.cuda.synchronize()
+    assert not ws.status()["overflowed"]
 print("prof_driver done", x.launch_count(), "launches")

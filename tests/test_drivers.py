@@ -121,3 +121,49 @@ def test_the_reference_training_application_runs_on_this_library(tmp_path):
     med = lambda v: sorted(v)[len(v) // 2]  # noqa: E731  (the application prints whole milliseconds)
     print(f"reference application, 300 Gaussians on 256x256: its own kernel {med(ref_ms)} ms/iteration (median), on "
           f"libxyz_b200 {med(our_ms)} ms/iteration; loss {ref_loss[0]:.4f} -> {ref_loss[40]:.4f} vs {our_loss[0]:.4f} -> {our_loss[40]:.4f}")
+
+
+MULTI = os.path.join(BUILD, "gaussian_splatting_training_multi_gpu")
+
+
+def _losses(stdout):
+    return [float(v) for v in re.findall(r"average Loss: ([0-9.eE+-]+)", stdout)]
+
+
+def test_multi_gpu_driver_rejects_bad_arguments():
+    assert run([MULTI, "--bogus"]).returncode == 2
+    assert run([MULTI, "--image", "12"]).returncode == 2
+
+
+@pytest.mark.gpu
+def test_multi_gpu_driver_trains_with_every_exchange():
+    """The C++ multi-GPU counterpart of GaussianSplattingTrainer::train() (one host thread per GPU, C ABI only).  On one GPU
+    every exchange reduces to the single-GPU loop: the loss goes down, and the fused peer-memory step (eager and as ONE
+    captured graph per iteration) follows the NCCL-shaped step's trajectory.  With >= 2 GPUs the sharded runs (views and
+    row bands) must reproduce the 1-GPU trajectory."""
+    import torch
+    base = ["--num-gaussians", "400", "--image", "192x128", "--max-iterations", "40", "--report", "10", "--views", "4"]
+    ref = run([MULTI, "--gpus", "1", "--exchange", "nccl"] + base)
+    assert ref.returncode == 0, ref.stdout[-2000:]
+    want = _losses(ref.stdout)
+    assert len(want) == 5 and want[-1] < 0.8 * want[0], want
+    configs = [["--gpus", "1", "--exchange", "peer"], ["--gpus", "1", "--exchange", "peer", "--graph"]]
+    g = min(torch.cuda.device_count(), 4)
+    if g >= 2:
+        configs += [["--gpus", str(g), "--exchange", e] for e in ("peer", "nccl", "nccl-sharded")]
+        configs += [["--gpus", str(g), "--exchange", "peer", "--graph"]]
+    for cfg in configs:
+        r = run([MULTI] + cfg + base)
+        assert r.returncode == 0, (cfg, r.stdout[-2000:])
+        got = _losses(r.stdout)
+        # Adam amplifies last-bit differences of the gradients (atomics, summation order) over 40 steps
+        assert len(got) == len(want) and all(abs(a - b) <= 2e-2 * b for a, b in zip(got, want)), (cfg, got, want)
+        print("multi-GPU driver", " ".join(cfg), re.search(r"([0-9.]+) ms/iteration", r.stdout).group(1), "ms/iteration")
+    # one image in row bands: same trajectory as one GPU rendering the whole image
+    ref = run([MULTI, "--gpus", "1", "--mode", "rows"] + base)
+    assert ref.returncode == 0, ref.stdout[-2000:]
+    if g >= 2:
+        r = run([MULTI, "--gpus", str(g), "--mode", "rows", "--graph"] + base)
+        assert r.returncode == 0, r.stdout[-2000:]
+        a, b = _losses(r.stdout), _losses(ref.stdout)
+        assert len(a) == len(b) and all(abs(u - v) <= 2e-2 * v for u, v in zip(a, b)), (a, b)

@@ -191,22 +191,30 @@ __global__ void __launch_bounds__(kPeerAdamThreads)
         for (long long i = b4 + blockIdx.x * static_cast<long long>(kPeerAdamThreads) + tid; i < e4;
              i += static_cast<long long>(gridDim.x) * kPeerAdamThreads) {
             const long long f0 = 4 * i;
-            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = 0; q < W; ++q) {
-                const float4 v = ld_peer_f4(a.grads[q] + f0);
-                s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-            }
+            // all ranks' rows first (up to 8 independent NVLink loads in flight), then the sum in rank order
+            float4 v[XYZ_PEER_MAX_WORLD];
+#pragma unroll
+            for (int q = 0; q < XYZ_PEER_MAX_WORLD; ++q)
+                if (q < W) v[q] = ld_peer_f4(a.grads[q] + f0);
             const float4 p = *reinterpret_cast<const float4*>(a.params[R] + f0);
+            float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int q = 0; q < XYZ_PEER_MAX_WORLD; ++q)
+                if (q < W) {
+                    s.x += v[q].x; s.y += v[q].y; s.z += v[q].z; s.w += v[q].w;
+                }
             float4 np;
             np.x = adam_component(adam, f0, s.x, p.x, a, s_lr);
             np.y = adam_component(adam, f0 + 1, s.y, p.y, a, s_lr);
             np.z = adam_component(adam, f0 + 2, s.z, p.z, a, s_lr);
             np.w = adam_component(adam, f0 + 3, s.w, p.w, a, s_lr);
             const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-            for (int q = 0; q < W; ++q) {
-                *reinterpret_cast<float4*>(a.params[q] + f0) = np;
-                *reinterpret_cast<float4*>(a.grads[q] + f0) = z;
-            }
+#pragma unroll
+            for (int q = 0; q < XYZ_PEER_MAX_WORLD; ++q)
+                if (q < W) {
+                    *reinterpret_cast<float4*>(a.params[q] + f0) = np;
+                    *reinterpret_cast<float4*>(a.grads[q] + f0) = z;
+                }
         }
         if (R == W - 1 && blockIdx.x == 0 && tid < static_cast<int>(n_floats - 4 * n4)) {
             const long long f = 4 * n4 + tid;

@@ -33,6 +33,10 @@ constexpr int kRecFloats = 16;            // {cx, cy, ia, ib | ic, sigmoid(opaci
 //   IEEE expf:                      0.5*d2 > 103.98 (below half the smallest denormal) ; margin -> 104.5
 constexpr float kD2MaxFast = 176.0f;
 constexpr float kD2MaxPrecise = 209.0f;
+// exp(-d2 / 2) as one special-function op on a pre-scaled conic: fast flavour ex2(kappa d2) with kappa = -0.5 log2(e)
+// (what -use_fast_math makes of expf), IEEE flavour expf(kappa d2) with kappa = -0.5
+constexpr float kKappaFast = -0.72134752044448170368f;
+constexpr float kKappaPrecise = -0.5f;
 constexpr float kD2MaxTail = 56.0f;  // XYZ_FLAG_TAIL_CULL (opt-in, bounded error): weights below exp(-28)
 
 struct SplatView {  // what one launch renders
@@ -43,6 +47,7 @@ struct SplatView {  // what one launch renders
 
 struct SplatBuffers {  // device scratch of one launch (library-owned)
     float4* records;          // N x 4 float4 (kRecFloats)
+    float4* fwd_records;      // N x 2 float4: {cx, cy, kappa ia, 2 kappa ib} {kappa ic, so r, so g, so b} (forward staging)
     int4* rects;              // N: tx0, ty0, tx1, ty1 (half-open)
     unsigned int* touched;    // N: tiles per Gaussian
     int2* spans;              // N x kSpanRows: [tx0, tx1) of the first kSpanRows tile rows of the rectangle

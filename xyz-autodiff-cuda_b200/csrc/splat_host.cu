@@ -111,7 +111,8 @@ __global__ void __launch_bounds__(256)
     splat_preprocess_kernel(SplatView v, const xyz_gaussian_params* __restrict__ params, float4* __restrict__ records,
                             int4* __restrict__ rects, unsigned int* __restrict__ touched, int2* __restrict__ spans,
                             float d2max, int no_cull, int chunk_size, int n_tiles, unsigned int* __restrict__ hist,
-                            unsigned int* __restrict__ ticket, unsigned int* __restrict__ chunk_total) {
+                            unsigned int* __restrict__ ticket, unsigned int* __restrict__ chunk_total,
+                            float4* __restrict__ fwd_records, float kappa) {
     // kCount: n_tiles counters, one per tile of THIS launch's row band (tile ids relative to the band's first tile row:
     // a band of 1/8 of the image has 1/8 of the counters, of the histogram traffic and of the column scan)
     extern __shared__ unsigned int s_cnt[];
@@ -155,6 +156,11 @@ __global__ void __launch_bounds__(256)
             // the Sigma the forward pass used, in both math flavours (this translation unit is always IEEE)
             records[4 * g + 2] = make_float4(p.color[2], es0, es1, ct);
             records[4 * g + 3] = make_float4(sn, 0.f, 0.f, 0.f);
+            // what the forward pass stages per Gaussian, ready to copy (cp.async): the conic pre-scaled by
+            // kappa (-0.5 log2(e) for the fast-math flavour's ex2, -0.5 for expf) and the colours by sigmoid(opacity)
+            fwd_records[2 * g] = make_float4(p.center[0], p.center[1], __fmul_rn(kappa, ia), __fmul_rn(2.0f * kappa, ib));
+            fwd_records[2 * g + 1] = make_float4(__fmul_rn(kappa, ic), __fmul_rn(so, p.color[0]), __fmul_rn(so, p.color[1]),
+                                                 __fmul_rn(so, p.color[2]));
             r = gaussian_tile_rect(p.center[0], p.center[1], ia, ib, ic, v, d2max, no_cull);
             rects[g] = r;
             sc = span_coef(p.center[0], p.center[1], ia, ib, ic, d2max, no_cull);
@@ -735,7 +741,7 @@ struct SplatPlan {
     int no_cull;
     float d2max;
     int chunk_size, n_chunks;
-    size_t o_rec, o_rect, o_touched, o_spans, o_offsets, o_ranges, o_tloss, o_chunks, o_rest, o_hist, o_ttotal, o_ctotal,
+    size_t o_rec, o_frec, o_rect, o_touched, o_spans, o_offsets, o_ranges, o_tloss, o_chunks, o_rest, o_hist, o_ttotal, o_ctotal,
         o_cbase, o_scan_tmp;
     size_t scan_tmp_bytes;
     size_t fixed_bytes;  // without the header
@@ -791,6 +797,7 @@ int make_plan(SplatPlan& p, int W, int H, int N, int row_begin, int row_end, int
     auto take = [&off](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
     const size_t nl = static_cast<size_t>(p.n_tiles_l > 0 ? p.n_tiles_l : 1);
     p.o_rec = take(sizeof(float4) * 4 * ng);
+    p.o_frec = take(sizeof(float4) * 2 * ng);
     p.o_rect = take(sizeof(int4) * ng);
     p.o_touched = take(sizeof(unsigned int) * ng);
     p.o_spans = take(sizeof(int2) * kSpanRows * ng);
@@ -869,6 +876,7 @@ struct Bound {  // a plan bound to memory
 void bind_fixed(const SplatPlan& p, unsigned char* header, unsigned char* base, Bound& o) {
     o.header = reinterpret_cast<unsigned long long*>(header);
     o.b.records = reinterpret_cast<float4*>(base + p.o_rec);
+    o.b.fwd_records = reinterpret_cast<float4*>(base + p.o_frec);
     o.b.rects = reinterpret_cast<int4*>(base + p.o_rect);
     o.b.touched = reinterpret_cast<unsigned int*>(base + p.o_touched);
     o.b.spans = reinterpret_cast<int2*>(base + p.o_spans);
@@ -903,6 +911,7 @@ int enqueue_front(const SplatPlan& p, const Bound& o, const xyz_gaussian_params*
                   unsigned long long overflow_base, cudaStream_t st, const unsigned long long** total_src,
                   StageEvents* tm) {
     const int N = p.v.num_gaussians;
+    const float kappa = p.precise ? kKappaPrecise : kKappaFast;
     *total_src = o.header;
     mark(tm, 0, st);
     if (N <= 0) {
@@ -913,7 +922,7 @@ int enqueue_front(const SplatPlan& p, const Bound& o, const xyz_gaussian_params*
     if (p.counting) {
         splat_preprocess_kernel<true><<<p.n_chunks, 256, sizeof(unsigned int) * p.n_tiles_l, st>>>(
             p.v, gaussians, o.b.records, o.b.rects, o.b.touched, o.b.spans, p.d2max, p.no_cull, p.chunk_size, p.n_tiles_l,
-            o.hist, reinterpret_cast<unsigned int*>(o.header + 2), o.chunk_total);
+            o.hist, reinterpret_cast<unsigned int*>(o.header + 2), o.chunk_total, o.b.fwd_records, kappa);
         count_launch();
         mark(tm, 1, st);
         splat_bin_colscan_kernel<<<(p.n_tiles_l + 31) / 32, dim3(32, 32), 0, st>>>(
@@ -929,7 +938,7 @@ int enqueue_front(const SplatPlan& p, const Bound& o, const xyz_gaussian_params*
     if (ce != cudaSuccess) return static_cast<int>(ce);
     splat_preprocess_kernel<false><<<(N + 255) / 256, 256, 0, st>>>(p.v, gaussians, o.b.records, o.b.rects, o.b.touched,
                                                                     o.b.spans, p.d2max, p.no_cull, 0, 0, nullptr, nullptr,
-                                                                    nullptr);
+                                                                    nullptr, o.b.fwd_records, kappa);
     count_launch();
     mark(tm, 1, st);
     size_t tmp = p.scan_tmp_bytes;

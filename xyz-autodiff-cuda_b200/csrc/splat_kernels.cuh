@@ -6,6 +6,8 @@
 // :84-110 and the Logic structs cited inline.
 #pragma once
 
+#include <cstdlib>
+
 #include "splat_common.cuh"
 
 #ifndef XYZ_SPLAT_FLAVOR
@@ -30,10 +32,10 @@ namespace {
 //   precise kappa = -0.5,           e = expf(arg)             (IEEE flavour)
 // Both underflow to exactly 0.0f beyond the d2 bounds in splat_common.cuh (checked by the cull parity test).
 #if XYZ_SPLAT_IS_FAST
-constexpr float kKappa = -0.72134752044448170368f;
+constexpr float kKappa = kKappaFast;
 __device__ __forceinline__ float pair_exp(float arg) { return exp2f(arg); }
 #else
-constexpr float kKappa = -0.5f;
+constexpr float kKappa = kKappaPrecise;
 __device__ __forceinline__ float pair_exp(float arg) { return expf(arg); }
 #endif
 
@@ -52,56 +54,93 @@ __device__ __forceinline__ float xor_sign(float v, float from) {
 //   dy = y_k - cy ; arg = dy (C2 dy + bdx) + t0 ; e = exp(arg) ; out_k,i += (so c_i) e
 // = 1 shared-memory wavefront, 1 MUFU and ~8.5 issue slots per pair.  Summation runs in ascending Gaussian
 // index per pixel, the reference's order (gaussian_splatting_kernel.cu:33-62).
-#ifndef XYZ_FWD_THREADS
-#define XYZ_FWD_THREADS 64
-#endif
-constexpr int kFwdThreads = XYZ_FWD_THREADS;
+// kThreads per tile = 64 (four pixels per thread, the throughput configuration: 4096 tiles keep every SM full), or 128 /
+// 256 (two / one pixel per thread) for launches with FEW tiles -- a row band of an image sharded over 8 GPUs has 512
+// tiles = 3.5 CTAs per SM, which at 64 threads is 7 warps per SM and cannot keep the MUFU pipe busy; the wider CTAs
+// trade shared-memory reads per pair for warps in flight.  Same arithmetic per pixel in every configuration: the image is
+// bit-identical (tested).
 constexpr int kFwdStage = 128;  // Gaussians staged per pass
-constexpr int kFwdRows = kTilePixels / kFwdThreads;  // pixel rows per thread (4)
-constexpr int kFwdRowStep = kFwdThreads / kTile;     // distance between a thread's rows
 
-__global__ void __launch_bounds__(kFwdThreads)
-    splat_forward_kernel(SplatView v, const float4* __restrict__ records, const int* __restrict__ sorted_gid,
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Staging is a three-deep software pipeline per CTA, so that a CTA never waits for global memory even when it is alone
+// on its SM sub-partition (row bands of a sharded image: 3.5 tiles per SM): while stage s is being rendered, the
+// 32-byte forward records of stage s + 1 are in flight (cp.async into the other shared-memory buffer) and the Gaussian
+// ids of stage s + 2 are in flight into registers.
+template <int kThreads>
+__global__ void __launch_bounds__(kThreads)
+    splat_forward_kernel(SplatView v, const float4* __restrict__ fwd_records, const int* __restrict__ sorted_gid,
                          const int2* __restrict__ tile_ranges, const float* __restrict__ target,
                          float* __restrict__ output, float* __restrict__ tile_loss, float4* __restrict__ rest_tiles,
                          int tile_y0) {
-    __shared__ float4 s_a[kFwdStage];
-    __shared__ float4 s_b[kFwdStage];
-    __shared__ float s_red[kFwdThreads / 32];
+    constexpr int kRows = kTilePixels / kThreads;   // pixel rows per thread (4, 2, 1)
+    constexpr int kRowStep = kThreads / kTile;      // distance between a thread's rows
+    constexpr int kPerThread = (kFwdStage + kThreads - 1) / kThreads;  // Gaussians a thread stages per pass
+    __shared__ __align__(16) float4 s_a[2][kFwdStage];
+    __shared__ __align__(16) float4 s_b[2][kFwdStage];
 
     const int tid = threadIdx.x;
     const int tile_x = blockIdx.x, tile_y = tile_y0 + blockIdx.y;
     const int tile = tile_y * v.tiles_x + tile_x;
     const int pxi = tile_x * kTile + (tid & (kTile - 1));
-    const int pyi0 = tile_y * kTile + (tid >> 4);  // rows pyi0 + kFwdRowStep k
+    const int pyi0 = tile_y * kTile + (tid >> 4);  // rows pyi0 + kRowStep k
     const float px = static_cast<float>(pxi);
-    float py[kFwdRows];
+    float py[kRows];
 #pragma unroll
-    for (int k = 0; k < kFwdRows; ++k) py[k] = static_cast<float>(pyi0 + kFwdRowStep * k);
+    for (int k = 0; k < kRows; ++k) py[k] = static_cast<float>(pyi0 + kRowStep * k);
 
     const int2 range = tile_ranges[tile];
-    float o[kFwdRows][3];
+    float o[kRows][3];
 #pragma unroll
-    for (int k = 0; k < kFwdRows; ++k) o[k][0] = o[k][1] = o[k][2] = 0.f;
-    for (int base = range.x; base < range.y; base += kFwdStage) {
-        const int n = min(kFwdStage, range.y - base);
-        __syncthreads();
-        for (int t = tid; t < n; t += kFwdThreads) {
-            const int g = sorted_gid[base + t];
-            const float4 r0 = __ldg(records + 4 * g), r1 = __ldg(records + 4 * g + 1), r2 = __ldg(records + 4 * g + 2);
-            s_a[t] = make_float4(r0.x, r0.y, kKappa * r0.z, (2.0f * kKappa) * r0.w);
-            s_b[t] = make_float4(kKappa * r1.x, r1.y * r1.z, r1.y * r1.w, r1.y * r2.x);
+    for (int k = 0; k < kRows; ++k) o[k][0] = o[k][1] = o[k][2] = 0.f;
+
+    int gid[kPerThread];  // ids of the stage that is fetched next
+    auto load_ids = [&](int base) {
+#pragma unroll
+        for (int q = 0; q < kPerThread; ++q) {
+            const int t = tid + q * kThreads;
+            gid[q] = (t < kFwdStage && base + t < range.y) ? __ldg(sorted_gid + base + t) : -1;
         }
+    };
+    auto fetch = [&](int buf) {  // records of the ids in gid[] -> shared-memory buffer `buf` (asynchronous)
+#pragma unroll
+        for (int q = 0; q < kPerThread; ++q) {
+            const int t = tid + q * kThreads;
+            if (gid[q] >= 0) {
+                cp_async16(&s_a[buf][t], fwd_records + 2 * gid[q]);
+                cp_async16(&s_b[buf][t], fwd_records + 2 * gid[q] + 1);
+            }
+        }
+        cp_async_commit();
+    };
+    load_ids(range.x);
+    fetch(0);
+    load_ids(range.x + kFwdStage);
+    int buf = 0;
+    for (int base = range.x; base < range.y; base += kFwdStage, buf ^= 1) {
+        const int n = min(kFwdStage, range.y - base);
+        // every thread is done READING buffer buf ^ 1 (the previous stage) before anybody refills it
         __syncthreads();
+        fetch(buf ^ 1);                        // stage s + 1 (an empty group past the end)
+        load_ids(base + 2 * kFwdStage);        // ids of stage s + 2
+        cp_async_wait<1>();                    // this thread's copies of stage s have landed ...
+        __syncthreads();                       // ... and everybody else's
+        const float4* __restrict__ sa = s_a[buf];
+        const float4* __restrict__ sb = s_b[buf];
 #pragma unroll 4
         for (int j = 0; j < n; ++j) {
-            const float4 a = s_a[j];
-            const float4 b = s_b[j];
+            const float4 a = sa[j];
+            const float4 b = sb[j];
             const float dx = px - a.x;
             const float t0 = (a.z * dx) * dx;
             const float bdx = a.w * dx;
 #pragma unroll
-            for (int k = 0; k < kFwdRows; ++k) {
+            for (int k = 0; k < kRows; ++k) {
                 const float dy = py[k] - a.y;
                 const float e = pair_exp(fmaf(dy, fmaf(b.x, dy, bdx), t0));
                 o[k][0] = fmaf(b.y, e, o[k][0]);
@@ -110,13 +149,15 @@ __global__ void __launch_bounds__(kFwdThreads)
             }
         }
     }
-    float l = 0.f;
+    cp_async_wait<0>();
+    __shared__ float s_l[kTilePixels];  // per-pixel |out - target|, summed below in an order that does not depend on kThreads
 #pragma unroll
-    for (int k = 0; k < kFwdRows; ++k) {
-        const int pyi = pyi0 + kFwdRowStep * k;
+    for (int k = 0; k < kRows; ++k) {
+        const int pyi = pyi0 + kRowStep * k;
         // rest_sum = target_color - pixel_out (gaussian_splatting_kernel.cu:99-101) for the backward pass, stored
         // tile-major (4 KB contiguous per tile); .w = 1 for pixels of this launch, 0 outside the image / row band
         float4 rest = make_float4(0.f, 0.f, 0.f, 0.f);
+        float l = 0.f;
         if (pxi < v.width && pyi >= v.row_begin && pyi < v.row_end) {
             const size_t p = static_cast<size_t>(pyi) * v.width + pxi;
             output[3 * p] = o[k][0];
@@ -127,18 +168,20 @@ __global__ void __launch_bounds__(kFwdThreads)
             rest.z = __ldg(target + 3 * p + 2) - o[k][2];
             rest.w = 1.f;
             // gaussian_splatting_kernel.cu:68-70: |out - target|
-            l += fabsf(rest.x) + fabsf(rest.y) + fabsf(rest.z);
+            l = fabsf(rest.x) + fabsf(rest.y) + fabsf(rest.z);
         }
-        rest_tiles[static_cast<size_t>(tile) * kTilePixels + (tid + kFwdThreads * k)] = rest;
+        rest_tiles[static_cast<size_t>(tile) * kTilePixels + (tid + kThreads * k)] = rest;
+        s_l[tid + kThreads * k] = l;
     }
-    l = warp_sum(l);
-    if ((tid & 31) == 0) s_red[tid >> 5] = l;
     __syncthreads();
-    if (tid == 0) {
-        float s = 0.f;
+    // the tile's loss partial: lane i adds pixels i, i + 32, ..., then a shuffle tree -- the same order whatever kThreads
+    // is, so a row band rendered with wide CTAs reports the same bits as the whole image rendered with narrow ones
+    if (tid < 32) {
+        float l = 0.f;
 #pragma unroll
-        for (int w = 0; w < kFwdThreads / 32; ++w) s += s_red[w];
-        tile_loss[tile] = s;
+        for (int j = 0; j < kTilePixels / 32; ++j) l += s_l[tid + 32 * j];
+        l = warp_sum(l);
+        if (tid == 0) tile_loss[tile] = l;
     }
 }
 
@@ -392,8 +435,24 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
     const int ty0 = v.row_begin / kTile, ty1 = (v.row_end + kTile - 1) / kTile;
     if (ty1 <= ty0) return 0;
     dim3 grid(v.tiles_x, ty1 - ty0);
-    splat_forward_kernel<<<grid, kFwdThreads, 0, st>>>(v, b.records, b.sorted_gid, b.tile_ranges, target, output,
-                                                       b.tile_loss, b.rest_tiles, ty0);
+    // threads per tile by how many tiles an SM gets (see the kernel); XYZ_SPLAT_FWD_THREADS = 64 | 128 | 256 overrides
+    static const int forced = [] {
+        const char* e = std::getenv("XYZ_SPLAT_FWD_THREADS");
+        const int x = e ? std::atoi(e) : 0;
+        return (x == 64 || x == 128 || x == 256) ? x : 0;
+    }();
+    const long long tiles = static_cast<long long>(grid.x) * grid.y;
+    const int sms = sm_count();
+    const int threads = forced ? forced : (tiles >= 12LL * sms ? 64 : (tiles >= 5LL * sms ? 128 : 256));
+    if (threads == 64)
+        splat_forward_kernel<64><<<grid, 64, 0, st>>>(v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output, b.tile_loss,
+                                                      b.rest_tiles, ty0);
+    else if (threads == 128)
+        splat_forward_kernel<128><<<grid, 128, 0, st>>>(v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output,
+                                                        b.tile_loss, b.rest_tiles, ty0);
+    else
+        splat_forward_kernel<256><<<grid, 256, 0, st>>>(v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output,
+                                                        b.tile_loss, b.rest_tiles, ty0);
     count_launch();
     return last_error();
 }
