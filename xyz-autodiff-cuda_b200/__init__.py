@@ -21,7 +21,7 @@ from typing import Optional
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libxyz_b200.so")
+LIB_PATH = os.environ.get("XYZ_B200_LIB") or os.path.join(_HERE, "lib", "libxyz_b200.so")  # override: kernel variants (dev/)
 
 FLAG_DETERMINISTIC = 1
 FLAG_PRECISE_MATH = 2

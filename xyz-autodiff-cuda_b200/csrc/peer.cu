@@ -227,10 +227,14 @@ __global__ void __launch_bounds__(kPeerAdamThreads)
             }
         }
     }
-    // ---- round 2: all my remote stores have landed; wait until everybody else's have landed here
-    __threadfence_system();
+    // ---- round 2: all my remote stores have landed; wait until everybody else's have landed here.
+    // One system-scope fence per CTA, by the thread that takes the ticket: the CTA barrier orders every thread's stores
+    // before it, and fences are cumulative (a membar.sys in all 256 threads costs microseconds per CTA).
     __syncthreads();
-    if (tid == 0) s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    if (tid == 0) {
+        __threadfence_system();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
+    }
     __syncthreads();
     if (!s_last) return;
     __threadfence_system();

@@ -67,10 +67,12 @@ struct SplatBuffers {  // device scratch of one launch (library-owned)
 
 // flavour launchers (splat_fast.cu is built with -use_fast_math like the reference's training app,
 // splat_precise.cu without, like the reference's tests)
-int splat_forward_launch_fast(const SplatView&, const SplatBuffers&, const float* target, float* output,
-                              cudaStream_t);
+// ticket: one unsigned int that is zero before the launch (the last CTA resets it): the forward pass itself adds the
+// per-tile loss partials, in tile order, to *total_loss
+int splat_forward_launch_fast(const SplatView&, const SplatBuffers&, const float* target, float* output, float* total_loss,
+                              unsigned int* ticket, cudaStream_t);
 int splat_forward_launch_precise(const SplatView&, const SplatBuffers&, const float* target, float* output,
-                                 cudaStream_t);
+                                 float* total_loss, unsigned int* ticket, cudaStream_t);
 // bwd_ctas = size of the backward work list (an upper bound of the CTAs needed; surplus records hold tile = -1)
 int splat_backward_launch_fast(const SplatView&, const SplatBuffers&, xyz_gaussian_grads* grads, long long bwd_ctas,
                                bool deterministic, cudaStream_t);

@@ -163,7 +163,9 @@ __global__ void __launch_bounds__(256)
                                                  __fmul_rn(so, p.color[2]));
             r = gaussian_tile_rect(p.center[0], p.center[1], ia, ib, ic, v, d2max, no_cull);
             rects[g] = r;
-            sc = span_coef(p.center[0], p.center[1], ia, ib, ic, d2max, no_cull);
+            // (a rectangle that misses the image / the row band is empty: no spans to derive -- 7 of 8 Gaussians when
+            // one image is split over 8 GPUs)
+            if (r.w > r.y && r.z > r.x) sc = span_coef(p.center[0], p.center[1], ia, ib, ic, d2max, no_cull);
             big_one = static_cast<unsigned int>((r.z - r.x) * (r.w - r.y)) > kBigGaussian;
             for (int ty = r.y; ty < r.w; ++ty) {
                 const int2 s = tile_row_span(sc, r, ty, v);
@@ -416,24 +418,52 @@ __global__ void __launch_bounds__(1024)
     const int tile = blockIdx.x * 32 + tx;
     const int per = (n_chunks + 31) / 32;
     const int c0 = min(gy * per, n_chunks), c1 = min(c0 + per, n_chunks);
+    // A thread owns `per` consecutive chunks of one tile column.  Up to kColRegs of them stay in registers between the
+    // two passes: all loads of the column are in flight together and nothing is read twice (592 chunks: per = 19).  The
+    // kernel is one latency chain (1 MB of histograms, 16 .. 128 CTAs): round trips are what it costs.
+    constexpr int kColRegs = 24;
     unsigned int sum = 0;
-    if (tile < n_tiles) {
-#pragma unroll 4
-        for (int c = c0; c < c1; ++c) sum += hist[static_cast<size_t>(c) * n_tiles + tile];
-    }
-    s_part[gy][tx] = sum;
-    __syncthreads();
-    unsigned int run = 0;
-    for (int q = 0; q < gy; ++q) run += s_part[q][tx];
-    if (tile < n_tiles) {
-#pragma unroll 4
-        for (int c = c0; c < c1; ++c) {
-            const size_t at = static_cast<size_t>(c) * n_tiles + tile;
-            const unsigned int x = hist[at];
-            hist[at] = run;
-            run += x;
+    if (per <= kColRegs) {
+        unsigned int x[kColRegs];
+#pragma unroll
+        for (int k = 0; k < kColRegs; ++k) {
+            const int c = c0 + k;
+            x[k] = (tile < n_tiles && c < c1) ? hist[static_cast<size_t>(c) * n_tiles + tile] : 0u;
         }
-        if (gy == 31) tile_total[tile] = run;
+#pragma unroll
+        for (int k = 0; k < kColRegs; ++k) sum += x[k];
+        s_part[gy][tx] = sum;
+        __syncthreads();
+        unsigned int run = 0;
+        for (int q = 0; q < gy; ++q) run += s_part[q][tx];
+        if (tile < n_tiles) {
+#pragma unroll
+            for (int k = 0; k < kColRegs; ++k) {
+                const int c = c0 + k;
+                if (c < c1) hist[static_cast<size_t>(c) * n_tiles + tile] = run;
+                run += x[k];
+            }
+            if (gy == 31) tile_total[tile] = run;
+        }
+    } else {
+        if (tile < n_tiles) {
+#pragma unroll 4
+            for (int c = c0; c < c1; ++c) sum += hist[static_cast<size_t>(c) * n_tiles + tile];
+        }
+        s_part[gy][tx] = sum;
+        __syncthreads();
+        unsigned int run = 0;
+        for (int q = 0; q < gy; ++q) run += s_part[q][tx];
+        if (tile < n_tiles) {
+#pragma unroll 4
+            for (int c = c0; c < c1; ++c) {
+                const size_t at = static_cast<size_t>(c) * n_tiles + tile;
+                const unsigned int x = hist[at];
+                hist[at] = run;
+                run += x;
+            }
+            if (gy == 31) tile_total[tile] = run;
+        }
     }
     __threadfence();
     __syncthreads();
@@ -524,8 +554,11 @@ __global__ void __launch_bounds__(kBinThreads)
     // warp-wide loads (lane (rl, xl) fetches row rl of hits xl & 3 and 4 + (xl & 3)) and handed out by shuffles.
     auto load_rect = [&](int gb) {
         const int g = gb + lane;
+        // an empty rectangle (culled, or outside the row band) has r.w == r.y and never hits; a non-empty rectangle whose
+        // spans all turn out empty hits, finds nothing to write and costs a few instructions -- cheaper than a dependent
+        // load of touched[g] in front of every rectangle
         int4 r = make_int4(0, 0, 0, 0);
-        if (g < g_end && touched[g] != 0u) r = rects[g];
+        if (g < g_end) r = rects[g];
         return r;
     };
     for (int S0 = R0; S0 < R1; S0 += RL) {
@@ -685,21 +718,6 @@ __global__ void __launch_bounds__(256)
     const int2 r = tile_ranges[t];
     const int first = chunk_offsets[t], c = chunk_offsets[t + 1] - first;
     for (int k = 0; k < c; ++k) chunk_info[first + k] = make_int4(t, r.x + k * kBwdChunk, r.y, 0);
-}
-
-// ---- loss: tile partials summed in tile order (no float atomics) ---------------------------------------
-__global__ void __launch_bounds__(256) splat_loss_finish_kernel(const float* __restrict__ tile_loss, int tile_begin,
-                                                                 int tile_end, float* total_loss) {
-    __shared__ float s[256];
-    float acc = 0.f;
-    for (int t = tile_begin + threadIdx.x; t < tile_end; t += 256) acc += tile_loss[t];
-    s[threadIdx.x] = acc;
-    __syncthreads();
-    for (int w = 128; w > 0; w >>= 1) {
-        if (threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
-        __syncthreads();
-    }
-    if (threadIdx.x == 0) *total_loss += s[0];  // the reference accumulates into the caller's value
 }
 
 // ---- deterministic mode: per-Gaussian sum of its entries' rows, in entry order ----------------------------
@@ -1003,16 +1021,10 @@ int enqueue_back(const SplatPlan& p, const EntryLayout& L, const Bound& o, const
         }
     }
     mark(tm, 3, st);
-    int err = p.precise ? splat_forward_launch_precise(p.v, b, target, output, st)
-                        : splat_forward_launch_fast(p.v, b, target, output, st);
+    unsigned int* fwd_ticket = reinterpret_cast<unsigned int*>(o.header + 2) + 1;  // next to the column scan's ticket
+    int err = p.precise ? splat_forward_launch_precise(p.v, b, target, output, total_loss, fwd_ticket, st)
+                        : splat_forward_launch_fast(p.v, b, target, output, total_loss, fwd_ticket, st);
     if (err) return err;
-    {
-        const int ty0 = p.v.row_begin / kTile, ty1 = (p.v.row_end + kTile - 1) / kTile;
-        if (ty1 > ty0) {
-            splat_loss_finish_kernel<<<1, 256, 0, st>>>(b.tile_loss, ty0 * p.v.tiles_x, ty1 * p.v.tiles_x, total_loss);
-            count_launch();
-        }
-    }
     mark(tm, 4, st);
     const long long bwd_ctas = entries > 0 ? static_cast<long long>(L.chunk_info_size) : 0;
     err = p.precise ? splat_backward_launch_precise(p.v, b, gradients, bwd_ctas, p.deterministic, st)

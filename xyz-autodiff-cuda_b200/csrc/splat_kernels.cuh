@@ -19,6 +19,14 @@
 #ifndef XYZ_BWD_DX2
 #define XYZ_BWD_DX2 1  // backward pixel loop keeps dx^2 in registers: 13 instead of 14 FMA-pipe operations per pixel
 #endif
+#ifndef XYZ_BWD_ROW_UNROLL
+#define XYZ_BWD_ROW_UNROLL 1  // rows of the tile per iteration of the backward pixel loop
+#endif
+#ifndef XYZ_FWD_UNROLL
+#define XYZ_FWD_UNROLL 4      // Gaussians per iteration of the forward loop
+#endif
+#define XYZ_PRAGMA(x) _Pragma(#x)
+#define XYZ_UNROLL(n) XYZ_PRAGMA(unroll n)
 #define XYZ_CAT2(a, b) a##b
 #define XYZ_CAT(a, b) XYZ_CAT2(a, b)
 
@@ -77,7 +85,7 @@ __global__ void __launch_bounds__(kThreads)
     splat_forward_kernel(SplatView v, const float4* __restrict__ fwd_records, const int* __restrict__ sorted_gid,
                          const int2* __restrict__ tile_ranges, const float* __restrict__ target,
                          float* __restrict__ output, float* __restrict__ tile_loss, float4* __restrict__ rest_tiles,
-                         int tile_y0) {
+                         int tile_y0, unsigned int* __restrict__ ticket, float* total_loss) {
     constexpr int kRows = kTilePixels / kThreads;   // pixel rows per thread (4, 2, 1)
     constexpr int kRowStep = kThreads / kTile;      // distance between a thread's rows
     constexpr int kPerThread = (kFwdStage + kThreads - 1) / kThreads;  // Gaussians a thread stages per pass
@@ -132,7 +140,7 @@ __global__ void __launch_bounds__(kThreads)
         __syncthreads();                       // ... and everybody else's
         const float4* __restrict__ sa = s_a[buf];
         const float4* __restrict__ sb = s_b[buf];
-#pragma unroll 4
+        XYZ_UNROLL(XYZ_FWD_UNROLL)
         for (int j = 0; j < n; ++j) {
             const float4 a = sa[j];
             const float4 b = sb[j];
@@ -176,12 +184,38 @@ __global__ void __launch_bounds__(kThreads)
     __syncthreads();
     // the tile's loss partial: lane i adds pixels i, i + 32, ..., then a shuffle tree -- the same order whatever kThreads
     // is, so a row band rendered with wide CTAs reports the same bits as the whole image rendered with narrow ones
+    __shared__ int s_last;
     if (tid < 32) {
         float l = 0.f;
 #pragma unroll
         for (int j = 0; j < kTilePixels / 32; ++j) l += s_l[tid + 32 * j];
         l = warp_sum(l);
-        if (tid == 0) tile_loss[tile] = l;
+        if (tid == 0) {
+            tile_loss[tile] = l;
+            // the last CTA of the launch adds the tile partials to the caller's loss (in tile order: no float atomics,
+            // the reference's 3 atomicAdds per pixel on one address become one add per launch)
+            __threadfence();
+            s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+        }
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // threads 0..63 (every configuration has them) add the launch's tiles t, t + 64, ... ; then a fixed tree
+    const int t_begin = tile_y0 * v.tiles_x, t_end = t_begin + static_cast<int>(gridDim.x * gridDim.y);
+    if (tid < 64) {
+        float acc = 0.f;
+        for (int t = t_begin + tid; t < t_end; t += 64) acc += __ldcg(tile_loss + t);
+        s_l[tid] = acc;
+    }
+    __syncthreads();
+    if (tid < 32) {
+        float l = s_l[tid] + s_l[tid + 32];
+        l = warp_sum(l);
+        if (tid == 0) {
+            *total_loss += l;  // the reference accumulates into the caller's value (gaussian_splatting_kernel.cu:68-70)
+            *ticket = 0u;
+        }
     }
 }
 
@@ -267,7 +301,7 @@ __device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_r
     const F2 A2p = f2_pack(A2, A2);
     const F2 cs0p = f2_pack(cs0, cs0), cs1p = f2_pack(cs1, cs1), cs2p = f2_pack(cs2, cs2);
     const F2 c0p = f2_pack(c0, c0), c1p = f2_pack(c1, c1), c2p = f2_pack(c2, c2);
-#pragma unroll 1
+    XYZ_UNROLL(XYZ_BWD_ROW_UNROLL)
     for (int r = 0; r < kTile; ++r) {
         const float dy = (py0 + static_cast<float>(r)) - cy;
         const float u = B2 * dy;
@@ -431,7 +465,7 @@ __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
 }  // namespace
 
 int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const SplatBuffers& b, const float* target,
-                                                     float* output, cudaStream_t st) {
+                                                     float* output, float* total_loss, unsigned int* ticket, cudaStream_t st) {
     const int ty0 = v.row_begin / kTile, ty1 = (v.row_end + kTile - 1) / kTile;
     if (ty1 <= ty0) return 0;
     dim3 grid(v.tiles_x, ty1 - ty0);
@@ -443,16 +477,18 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
     }();
     const long long tiles = static_cast<long long>(grid.x) * grid.y;
     const int sms = sm_count();
-    const int threads = forced ? forced : (tiles >= 12LL * sms ? 64 : (tiles >= 5LL * sms ? 128 : 256));
+    // measured (dev/fwd_threads_sweep.py, profiles/fwd_threads_sweep_r02.log): 64 wins from 12 tiles per SM on, 128 below;
+    // 256 (one pixel per thread, shared-memory bound) never wins and stays reachable through the override only
+    const int threads = forced ? forced : (tiles >= 12LL * sms ? 64 : 128);
     if (threads == 64)
         splat_forward_kernel<64><<<grid, 64, 0, st>>>(v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output, b.tile_loss,
-                                                      b.rest_tiles, ty0);
+                                                      b.rest_tiles, ty0, ticket, total_loss);
     else if (threads == 128)
         splat_forward_kernel<128><<<grid, 128, 0, st>>>(v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output,
-                                                        b.tile_loss, b.rest_tiles, ty0);
+                                                        b.tile_loss, b.rest_tiles, ty0, ticket, total_loss);
     else
         splat_forward_kernel<256><<<grid, 256, 0, st>>>(v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output,
-                                                        b.tile_loss, b.rest_tiles, ty0);
+                                                        b.tile_loss, b.rest_tiles, ty0, ticket, total_loss);
     count_launch();
     return last_error();
 }
