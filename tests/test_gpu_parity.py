@@ -876,6 +876,34 @@ def test_splat_workspace_launch_equals_the_classic_launch(flags):
     assert wsb.bytes < ws.bytes
 
 
+def test_splat_forward_configurations_give_identical_bits():
+    """The forward pass picks its CTA shape by the number of tiles (whole tiles with 64 / 128 / 256 threads, or two
+    half-tile CTAs): image AND loss must be bit-identical in every configuration (XYZ_SPLAT_FWD_THREADS is read once per
+    process, so each configuration runs in its own interpreter)."""
+    import hashlib
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import sys, hashlib, numpy as np, torch\n"
+        f"sys.path.insert(0, {root!r}); sys.path.insert(0, {os.path.join(root, 'tests')!r})\n"
+        "import oracle_lib as orc, xyz_autodiff_cuda_b200 as x\n"
+        "W, H, N = 200, 150, 3000\n"
+        "p, t = orc.splat_scene(N, W, H, seed=8)\n"
+        "d = lambda a: torch.from_numpy(a).to('cuda:0')\n"
+        "g = torch.zeros((N, 9), device='cuda:0'); o = torch.zeros((W * H, 3), device='cuda:0'); l = torch.zeros(1, device='cuda:0')\n"
+        "x.launch_gaussian_splatting(d(p), g, d(t), o, l, W, H, N, x.FLAG_DETERMINISTIC)\n"
+        "torch.cuda.synchronize()\n"
+        "print('HASH', hashlib.sha256(o.cpu().numpy().tobytes()).hexdigest(), l.item().hex(), hashlib.sha256(g.cpu().numpy().tobytes()).hexdigest())\n")
+    seen = {}
+    for cfg in ("32", "64", "128", "256"):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, XYZ_SPLAT_FWD_THREADS=cfg), stdout=subprocess.PIPE,
+                           stderr=subprocess.STDOUT, text=True, timeout=300)
+        assert r.returncode == 0, r.stdout[-2000:]
+        seen[cfg] = [ln for ln in r.stdout.splitlines() if ln.startswith("HASH")][0]
+    assert len(set(seen.values())) == 1, seen
+
+
 def test_splat_workspace_overflow_is_memory_safe_and_reported():
     W, H, N = 256, 192, 5000
     params, target = orc.splat_scene(N, W, H, seed=21)

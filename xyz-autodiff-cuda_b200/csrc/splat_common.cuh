@@ -61,7 +61,7 @@ struct SplatBuffers {  // device scratch of one launch (library-owned)
     int* chunk_offsets;       // tiles + 1: exclusive scan of ceil(list length / kBwdChunk) = backward CTAs before a tile
     int4* chunk_info;         // backward CTAs (upper bound entries/kBwdChunk + tiles): {tile or -1, first entry, list end, 0}
     float4* rest_tiles;       // tiles x 256: (target - output, active) per pixel, tile-major, written by the forward pass
-    float* tile_loss;         // tiles
+    float* tile_loss;         // 2 x tiles: one partial per half tile (rows 0..7, rows 8..15)
     float* entry_grads;       // deterministic mode: entries x 9 (indexed by ORIGINAL entry index)
 };
 

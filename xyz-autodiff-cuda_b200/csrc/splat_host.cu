@@ -821,7 +821,7 @@ int make_plan(SplatPlan& p, int W, int H, int N, int row_begin, int row_end, int
     p.o_spans = take(sizeof(int2) * kSpanRows * ng);
     p.o_offsets = take((p.deterministic || !p.counting) ? sizeof(unsigned long long) * ng : 0);
     p.o_ranges = take(sizeof(int2) * p.n_tiles);
-    p.o_tloss = take(sizeof(float) * p.n_tiles);
+    p.o_tloss = take(sizeof(float) * 2 * p.n_tiles);  // one loss partial per half tile
     p.o_chunks = take(sizeof(int) * (nl + 1));
     p.o_rest = take(sizeof(float4) * kTilePixels * static_cast<size_t>(p.n_tiles));
     p.o_hist = take(p.counting ? sizeof(unsigned int) * static_cast<size_t>(p.n_chunks) * nl : 0);

@@ -62,13 +62,6 @@ __device__ __forceinline__ float xor_sign(float v, float from) {
 //   dy = y_k - cy ; arg = dy (C2 dy + bdx) + t0 ; e = exp(arg) ; out_k,i += (so c_i) e
 // = 1 shared-memory wavefront, 1 MUFU and ~8.5 issue slots per pair.  Summation runs in ascending Gaussian
 // index per pixel, the reference's order (gaussian_splatting_kernel.cu:33-62).
-// kThreads per tile = 64 (four pixels per thread, the throughput configuration: 4096 tiles keep every SM full), or 128 /
-// 256 (two / one pixel per thread) for launches with FEW tiles -- a row band of an image sharded over 8 GPUs has 512
-// tiles = 3.5 CTAs per SM, which at 64 threads is 7 warps per SM and cannot keep the MUFU pipe busy; the wider CTAs
-// trade shared-memory reads per pair for warps in flight.  Same arithmetic per pixel in every configuration: the image is
-// bit-identical (tested).
-constexpr int kFwdStage = 128;  // Gaussians staged per pass
-
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -77,26 +70,41 @@ template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // Staging is a three-deep software pipeline per CTA, so that a CTA never waits for global memory even when it is alone
-// on its SM sub-partition (row bands of a sharded image: 3.5 tiles per SM): while stage s is being rendered, the
-// 32-byte forward records of stage s + 1 are in flight (cp.async into the other shared-memory buffer) and the Gaussian
-// ids of stage s + 2 are in flight into registers.
-template <int kThreads>
+// on its SM sub-partition: while stage s is being rendered, the 32-byte forward records of stage s + 1 are in flight
+// (cp.async into the other shared-memory buffer) and the Gaussian ids of stage s + 2 are in flight into registers.
+//
+// kParts = CTAs per tile.  1: one CTA renders the 16 x 16 tile (kThreads = 64: four pixels per thread, the throughput
+// configuration).  2: two CTAs of 64 threads render the upper and the lower 16 x 8 half (two pixels per thread) -- for
+// launches with FEW tiles: a row band of an image sharded over 8 GPUs has 512 tiles = 3.46 per SM, all resident at once,
+// so SMs with 4 tiles run 33 % longer than SMs with 3 and the kernel ends with a fifth of the machine idle (ncu,
+// profiles/ncu_r02_band_kernels.csv); with 1024 half tiles the quantum halves.  Per pixel the arithmetic and the
+// summation order are the same in every configuration: the image is bit-identical (tested).
+// The loss partial is kept per HALF tile (tile_loss[2 tile + half], each a fixed tree over its 128 pixels), so the sum
+// the last CTA forms over the launch's half tiles has the same bits in every configuration too.
+constexpr int kFwdStage = 128;  // Gaussians staged per pass
+constexpr int kHalfPixels = kTilePixels / 2;
+
+template <int kThreads, int kParts>
 __global__ void __launch_bounds__(kThreads)
     splat_forward_kernel(SplatView v, const float4* __restrict__ fwd_records, const int* __restrict__ sorted_gid,
                          const int2* __restrict__ tile_ranges, const float* __restrict__ target,
                          float* __restrict__ output, float* __restrict__ tile_loss, float4* __restrict__ rest_tiles,
                          int tile_y0, unsigned int* __restrict__ ticket, float* total_loss) {
-    constexpr int kRows = kTilePixels / kThreads;   // pixel rows per thread (4, 2, 1)
+    static_assert(kParts == 1 || (kParts == 2 && kThreads == 64), "half tiles are rendered by 64 threads");
+    constexpr int kPixels = kTilePixels / kParts;   // pixels of this CTA
+    constexpr int kRows = kPixels / kThreads;       // pixel rows per thread (4, 2, 1)
     constexpr int kRowStep = kThreads / kTile;      // distance between a thread's rows
     constexpr int kPerThread = (kFwdStage + kThreads - 1) / kThreads;  // Gaussians a thread stages per pass
     __shared__ __align__(16) float4 s_a[2][kFwdStage];
     __shared__ __align__(16) float4 s_b[2][kFwdStage];
 
     const int tid = threadIdx.x;
-    const int tile_x = blockIdx.x, tile_y = tile_y0 + blockIdx.y;
+    const int tile_x = blockIdx.x, tile_y = tile_y0 + static_cast<int>(blockIdx.y) / kParts;
+    const int part = static_cast<int>(blockIdx.y) % kParts;  // 0: rows 0..7 (or the whole tile), 1: rows 8..15
     const int tile = tile_y * v.tiles_x + tile_x;
     const int pxi = tile_x * kTile + (tid & (kTile - 1));
-    const int pyi0 = tile_y * kTile + (tid >> 4);  // rows pyi0 + kRowStep k
+    const int row0 = part * (kTile / kParts) + (tid >> 4);  // this thread's rows inside the tile: row0 + kRowStep k
+    const int pyi0 = tile_y * kTile + row0;
     const float px = static_cast<float>(pxi);
     float py[kRows];
 #pragma unroll
@@ -158,10 +166,11 @@ __global__ void __launch_bounds__(kThreads)
         }
     }
     cp_async_wait<0>();
-    __shared__ float s_l[kTilePixels];  // per-pixel |out - target|, summed below in an order that does not depend on kThreads
+    __shared__ float s_l[kTilePixels];  // per-pixel |out - target| by pixel index inside the tile (row-major)
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
-        const int pyi = pyi0 + kRowStep * k;
+        const int row = row0 + kRowStep * k, pyi = pyi0 + kRowStep * k;
+        const int pix = row * kTile + (tid & (kTile - 1));
         // rest_sum = target_color - pixel_out (gaussian_splatting_kernel.cu:99-101) for the backward pass, stored
         // tile-major (4 KB contiguous per tile); .w = 1 for pixels of this launch, 0 outside the image / row band
         float4 rest = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -178,34 +187,39 @@ __global__ void __launch_bounds__(kThreads)
             // gaussian_splatting_kernel.cu:68-70: |out - target|
             l = fabsf(rest.x) + fabsf(rest.y) + fabsf(rest.z);
         }
-        rest_tiles[static_cast<size_t>(tile) * kTilePixels + (tid + kThreads * k)] = rest;
-        s_l[tid + kThreads * k] = l;
+        rest_tiles[static_cast<size_t>(tile) * kTilePixels + pix] = rest;
+        s_l[pix] = l;
     }
     __syncthreads();
-    // the tile's loss partial: lane i adds pixels i, i + 32, ..., then a shuffle tree -- the same order whatever kThreads
-    // is, so a row band rendered with wide CTAs reports the same bits as the whole image rendered with narrow ones
+    // loss partial of a half tile: lane i adds its pixels i, i + 32, i + 64, i + 96, then a shuffle tree.  One warp per
+    // half this CTA owns (every configuration has at least two warps).
     __shared__ int s_last;
-    if (tid < 32) {
-        float l = 0.f;
+    {
+        const int warp = tid >> 5, lane = tid & 31;
+        if (warp < 2 / kParts) {
+            const int half = kParts == 2 ? part : warp;
+            float l = 0.f;
 #pragma unroll
-        for (int j = 0; j < kTilePixels / 32; ++j) l += s_l[tid + 32 * j];
-        l = warp_sum(l);
-        if (tid == 0) {
-            tile_loss[tile] = l;
-            // the last CTA of the launch adds the tile partials to the caller's loss (in tile order: no float atomics,
-            // the reference's 3 atomicAdds per pixel on one address become one add per launch)
-            __threadfence();
-            s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+            for (int j = 0; j < kHalfPixels / 32; ++j) l += s_l[half * kHalfPixels + lane + 32 * j];
+            l = warp_sum(l);
+            if (lane == 0) tile_loss[2 * tile + half] = l;
         }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        // the last CTA of the launch adds the partials to the caller's loss (in half-tile order: no float atomics, the
+        // reference's 3 atomicAdds per pixel on one address become one add per launch)
+        __threadfence();
+        s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // threads 0..63 (every configuration has them) add the launch's tiles t, t + 64, ... ; then a fixed tree
-    const int t_begin = tile_y0 * v.tiles_x, t_end = t_begin + static_cast<int>(gridDim.x * gridDim.y);
+    // threads 0..63 add the launch's half tiles h, h + 64, ... ; then a fixed tree
+    const int h_begin = 2 * tile_y0 * v.tiles_x, h_end = h_begin + 2 * static_cast<int>(gridDim.x * gridDim.y) / kParts;
     if (tid < 64) {
         float acc = 0.f;
-        for (int t = t_begin + tid; t < t_end; t += 64) acc += __ldcg(tile_loss + t);
+        for (int h = h_begin + tid; h < h_end; h += 64) acc += __ldcg(tile_loss + h);
         s_l[tid] = acc;
     }
     __syncthreads();
@@ -468,27 +482,25 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
                                                      float* output, float* total_loss, unsigned int* ticket, cudaStream_t st) {
     const int ty0 = v.row_begin / kTile, ty1 = (v.row_end + kTile - 1) / kTile;
     if (ty1 <= ty0) return 0;
-    dim3 grid(v.tiles_x, ty1 - ty0);
-    // threads per tile by how many tiles an SM gets (see the kernel); XYZ_SPLAT_FWD_THREADS = 64 | 128 | 256 overrides
+    // configuration by how many tiles an SM gets (see the kernel); XYZ_SPLAT_FWD_THREADS = 64 | 128 | 256 (threads of a
+    // whole-tile CTA) or 32 (two half-tile CTAs of 64 threads) overrides.  Measured (dev/fwd_threads_sweep.py,
+    // profiles/fwd_threads_sweep_r02.log): whole tiles with 64 threads win from 12 tiles per SM on, half tiles below;
+    // 128 / 256 threads per tile (more shared-memory reads per pair) never win.
     static const int forced = [] {
         const char* e = std::getenv("XYZ_SPLAT_FWD_THREADS");
         const int x = e ? std::atoi(e) : 0;
-        return (x == 64 || x == 128 || x == 256) ? x : 0;
+        return (x == 32 || x == 64 || x == 128 || x == 256) ? x : 0;
     }();
-    const long long tiles = static_cast<long long>(grid.x) * grid.y;
+    const long long tiles = static_cast<long long>(v.tiles_x) * (ty1 - ty0);
     const int sms = sm_count();
-    // measured (dev/fwd_threads_sweep.py, profiles/fwd_threads_sweep_r02.log): 64 wins from 12 tiles per SM on, 128 below;
-    // 256 (one pixel per thread, shared-memory bound) never wins and stays reachable through the override only
-    const int threads = forced ? forced : (tiles >= 12LL * sms ? 64 : 128);
-    if (threads == 64)
-        splat_forward_kernel<64><<<grid, 64, 0, st>>>(v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output, b.tile_loss,
-                                                      b.rest_tiles, ty0, ticket, total_loss);
-    else if (threads == 128)
-        splat_forward_kernel<128><<<grid, 128, 0, st>>>(v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output,
-                                                        b.tile_loss, b.rest_tiles, ty0, ticket, total_loss);
-    else
-        splat_forward_kernel<256><<<grid, 256, 0, st>>>(v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output,
-                                                        b.tile_loss, b.rest_tiles, ty0, ticket, total_loss);
+    const int cfg = forced ? forced : (tiles >= 12LL * sms ? 64 : 32);
+    const dim3 grid(v.tiles_x, (ty1 - ty0) * (cfg == 32 ? 2 : 1));
+#define XYZ_FWD_ARGS v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output, b.tile_loss, b.rest_tiles, ty0, ticket, total_loss
+    if (cfg == 32) splat_forward_kernel<64, 2><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
+    else if (cfg == 64) splat_forward_kernel<64, 1><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
+    else if (cfg == 128) splat_forward_kernel<128, 1><<<grid, 128, 0, st>>>(XYZ_FWD_ARGS);
+    else splat_forward_kernel<256, 1><<<grid, 256, 0, st>>>(XYZ_FWD_ARGS);
+#undef XYZ_FWD_ARGS
     count_launch();
     return last_error();
 }

@@ -40,6 +40,46 @@ def row_bands(height: int, world: int) -> List[Tuple[int, int]]:
     return bands
 
 
+def balanced_row_bands(tile_row_cost, height: int, world: int) -> List[Tuple[int, int]]:
+    """Tile-aligned row bands with EQUALISED cost instead of equal height: `tile_row_cost[r]` is the work of tile row r
+    (e.g. its number of (tile, Gaussian) list entries, from one launch over the whole image).  Gaussians near the image
+    border reach fewer tiles, so equal-height bands give the border ranks ~30 % less work than the middle ones and every
+    iteration waits for the slowest rank.  Contiguous partition minimising the largest band (binary search on the bound);
+    every rank computes the same bands from the same costs."""
+    cost = [float(c) for c in tile_row_cost]
+    n = len(cost)
+    if n != (height + TILE - 1) // TILE:
+        raise ValueError("one cost per tile row expected")
+    if world >= n:
+        cuts = list(range(n)) + [n] * (world - n + 1)
+    else:
+        def parts_needed(bound):
+            parts, acc = 1, 0.0
+            for c in cost:
+                if acc + c > bound and acc > 0.0:
+                    parts, acc = parts + 1, 0.0
+                acc += c
+            return parts
+        lo, hi = max(cost + [0.0]), sum(cost) + 1.0
+        for _ in range(60):
+            mid = 0.5 * (lo + hi)
+            if parts_needed(mid) <= world:
+                hi = mid
+            else:
+                lo = mid
+        cuts, acc = [0], 0.0
+        for r, c in enumerate(cost):
+            remaining_rows, remaining_parts = n - r, world - (len(cuts) - 1)
+            if r > cuts[-1] and (acc + c > hi or remaining_rows < remaining_parts) and len(cuts) < world:
+                cuts.append(r)
+                acc = 0.0
+            acc += c
+        while len(cuts) < world:   # fewer parts were needed than ranks: split the tail rows off one by one
+            cuts.append(min(n, cuts[-1] + 1) if cuts[-1] < n else n)
+        cuts = sorted(cuts) + [n]
+    return [(min(height, cuts[r] * TILE), min(height, cuts[r + 1] * TILE)) for r in range(world)]
+
+
 def views_for_rank(num_views: int, rank: int, world: int) -> List[int]:
     return list(range(rank, num_views, world))
 
