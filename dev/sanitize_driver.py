@@ -79,3 +79,52 @@ if os.environ.get("SANITIZE_SPLAT", "1") != "0":
             torch.cuda.synchronize()
             assert np.isfinite(grads.cpu().numpy()).all() and np.isfinite(loss.item())
 print("sanitize_driver: ok")
+# round 2: workspace launches (band-local histograms, deterministic offsets without the library scan, every forward CTA
+# shape is reached by the image sizes above / below), two workspaces in flight on two streams, empty band, N = 0, an
+# overflowing launch, more than 8192 tiles through the opt-in shared memory, the fused peer-memory optimiser step
+if os.environ.get("SANITIZE_R02", "1") != "0":
+    for (Ws, Hs, Ns, band) in ((320, 400, 1500, None), (320, 400, 1500, (96, 304)), (2080, 1040, 800, None)):
+        params, target = orc.splat_scene(Ns, Ws, Hs, seed=4)
+        params[10:40, 2:4] = 3.0
+        tp, tt = D(params), D(target)
+        for flags in (0, x.FLAG_DETERMINISTIC, x.FLAG_PRECISE_MATH | x.FLAG_DETERMINISTIC):
+            ws = x.SplatWorkspace(Ws, Hs, Ns, 400 * Ns, flags, rows=band)
+            grads = torch.zeros((Ns, 9), device=dev); img = torch.zeros((Ws * Hs, 3), device=dev); loss = torch.zeros(1, device=dev)
+            ws.launch(tp, grads, tt, img, loss)
+            assert not ws.status()["overflowed"]
+            assert np.isfinite(grads.cpu().numpy()).all() and np.isfinite(loss.item())
+    Ws, Hs, Ns = 320, 400, 1500
+    params, target = orc.splat_scene(Ns, Ws, Hs, seed=4)
+    tp, tt = D(params), D(target)
+    s1, s2 = torch.cuda.Stream(), torch.cuda.Stream()
+    torch.cuda.synchronize()
+    keep = []
+    for st in (s1, s2):
+        ws = x.SplatWorkspace(Ws, Hs, Ns, 300 * Ns, x.FLAG_DETERMINISTIC)
+        grads = torch.zeros((Ns, 9), device=dev); img = torch.zeros((Ws * Hs, 3), device=dev); loss = torch.zeros(1, device=dev)
+        with torch.cuda.stream(st):
+            ws.launch(tp, grads, tt, img, loss, stream=st)
+        keep.append((ws, grads, img, loss))
+    torch.cuda.synchronize()
+    assert torch.equal(keep[0][1], keep[1][1]) and torch.equal(keep[0][2], keep[1][2])
+    for rows, n in (((64, 64), Ns), (None, 0)):
+        ws = x.SplatWorkspace(Ws, Hs, n, 1000, 0, rows=rows)
+        grads = torch.zeros((max(n, 1), 9), device=dev); img = torch.zeros((Ws * Hs, 3), device=dev); loss = torch.zeros(1, device=dev)
+        ws.launch(tp[:n] if n else torch.empty((0, 9), device=dev), grads[:n] if n else torch.empty((0, 9), device=dev), tt, img, loss)
+        assert ws.status()["entries"] == 0 and (grads == 0).all()
+    ws = x.SplatWorkspace(Ws, Hs, Ns, 500, 0)        # far too small: empty lists, memory-safe
+    grads = torch.zeros((Ns, 9), device=dev); img = torch.ones((Ws * Hs, 3), device=dev); loss = torch.zeros(1, device=dev)
+    ws.launch(tp, grads, tt, img, loss)
+    assert ws.status()["overflowed"] and (img == 0).all() and (grads == 0).all()
+    grp = x.PeerGroup(0, 1, lambda h: [h])
+    for n in (3, 4097, 50_001):
+        ps = x.PeerSplat(grp, n, lambda h: [h])
+        ps.params.normal_(); ps.grads.normal_()
+        l = torch.ones(1, device=dev)
+        for it in (1, 0, 0):
+            ps.adam_step(0.1, 0.01, 0.001, 0.02, 0.05, iteration=it, total_loss=l)
+        torch.cuda.synchronize()
+        assert (ps.grads == 0).all() and np.isfinite(ps.params.cpu().numpy()).all() and l.item() == 1.0
+        ps.close()
+    grp.close()
+    print("sanitize_driver: round-2 paths ok")

@@ -83,7 +83,7 @@ enum {
                                     are exactly 0.0f).  Every pixel changes by at most
                                     N * 6.9e-13 * max|sigmoid(opacity) * color|; ~3x fewer pairs are evaluated. */
     XYZ_FLAG_RADIX_BINNING = 64, /* splat: build the tile lists with (tile, Gaussian) keys + a stable radix sort -- the
-                                    path images of more than 8192 tiles take anyway -- instead of the default stable
+                                    path row bands of more than 57 344 tiles (14.7 Mpixel) take anyway -- instead of the default stable
                                     counting sort by tile.  Same lists bit for bit; for tests and comparisons. */
     XYZ_FLAG_LSQ_SHIPPED_GRAPH = 256, /* lsq: the graph parallel_gradient_computation_kernel really builds
                                    (linear_regression_sgd.cu:103-122): combined_terms adds the UN-squared
@@ -252,7 +252,7 @@ XYZ_API int xyz_covproj_shared_w_fwd_bwd_f32_allreduce(const float* J, const flo
  *   xyz_launch_gaussian_splatting_ws       caller-provided workspace (xyz_splat_workspace_bytes): never allocates, never
  *       synchronises, keeps no library state -- re-entrant across streams and host threads (one workspace per launch in
  *       flight), capturable from the first call.
- * The per-tile lists come from a stable counting sort by tile (row bands of up to 8192 tiles) or a
+ * The per-tile lists come from a stable counting sort by tile (row bands of up to 57 344 tiles = 14.7 Mpixel) or a
  * stable radix sort of (tile, Gaussian) keys (library sort; classic entry points only); the choice never changes a
  * result bit.  Environment (read once, tuning only): XYZ_SPLAT_BIN_CTAS_PER_SM = CTAs per SM of the counting-sort
  * kernels (default 4, 1 for predicted lists beyond 4e7 entries).                                        */
@@ -269,7 +269,7 @@ XYZ_API int xyz_launch_gaussian_splatting_rows(const xyz_gaussian_params* gaussi
 /* Workspace variant.  `workspace` is device memory of at least
  *   xyz_splat_workspace_bytes(width, height, N, row_begin, row_end, max_entries, flags)
  * bytes, 256-byte aligned, whose first 256 bytes were zeroed once (xyz_splat_workspace_init); the flags must be the ones
- * the size was asked for (XYZ_FLAG_RADIX_BINNING and row bands of more than 8192 tiles are not available here:
+ * the size was asked for (XYZ_FLAG_RADIX_BINNING and row bands of more than 57 344 tiles are not available here:
  * XYZ_ERR_INVALID_ARGUMENT; the size query returns 0).  max_entries bounds the number of (tile, Gaussian) list entries
  * -- at BASELINE's distributions about 42 per Gaussian for a 1024^2 image.  If a scene needs more, that launch renders
  * EMPTY lists (image 0, loss = sum |target|, no gradients; memory-safe) and counts an overflow in the workspace header;

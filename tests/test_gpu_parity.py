@@ -652,6 +652,33 @@ def test_splat_counting_sort_binning_equals_the_radix_path():
                 assert np.abs(ga - gb).max() <= 1e-4 * np.abs(gb).max()   # atomics: order differs run to run
 
 
+def test_splat_counting_sort_beyond_8192_tiles_equals_the_radix_path():
+    """Row bands of more than 8192 tiles (here 130 x 65 = 8450) keep the counting sort -- the kernels opt in to the SM's
+    full shared memory -- and give the lists of the radix path bit for bit; the workspace entry point accepts them."""
+    W, H, N = 2080, 1040, 20_000
+    params, target = orc.splat_scene(N, W, H, seed=31, small=False)
+    params[:50, 2:4] = 3.5                                      # a few very large Gaussians
+    R, D = x.FLAG_RADIX_BINNING, x.FLAG_DETERMINISTIC
+    res = []
+    for extra in (0, R):
+        out = run_splat(params, target, W, H, D | extra)
+        st = x.splat_last_stats()
+        assert st["tiles"] == 8450
+        rects, ranges, ids, recs = x.splat_debug_binning(N, st["tiles"], st["entries"])
+        res.append((out, st["entries"], rects.copy(), ranges.copy(), ids.copy()))
+    (ga, oa, la), ea, ra, rga, ida = res[0]
+    (gb, ob, lb), eb, rb, rgb_, idb = res[1]
+    assert ea == eb and np.array_equal(ra, rb) and np.array_equal(ida, idb)
+    nonempty = rgb_[:, 1] > rgb_[:, 0]
+    assert np.array_equal(rga[nonempty], rgb_[nonempty])
+    assert np.array_equal(oa, ob) and la == lb and np.array_equal(ga, gb)
+    ws = x.SplatWorkspace(W, H, N, ea + 100, D)
+    g, o, l = run_splat_ws(ws, params, target, W, H)
+    torch.cuda.synchronize()
+    assert np.array_equal(o.cpu().numpy(), oa) and l.item() == la and np.array_equal(g.cpu().numpy(), ga)
+    x.shutdown()
+
+
 def test_splat_async_launch_equals_the_synchronous_one_and_reports_overflow():
     """XYZ_FLAG_ASYNC: no host synchronisation from the second launch of a scene shape on; buffers sized for 1.5 x the
     last known list length.  A launch that fits gives the synchronous results; one that does not renders empty lists

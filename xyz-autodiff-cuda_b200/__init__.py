@@ -375,7 +375,7 @@ class SplatWorkspace:
         self.bytes = int(lib().xyz_splat_workspace_bytes(image_width, image_height, num_gaussians, self.rows[0], self.rows[1],
                                                          self.max_entries, self.flags))
         if self.bytes == 0:
-            raise ValueError("xyz_splat_workspace_bytes: unsupported shape / flags (radix binning, more than 8192 tiles "
+            raise ValueError("xyz_splat_workspace_bytes: unsupported shape / flags (radix binning, more than 57344 tiles "
                              "in the row band, or invalid sizes)")
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
         self.buffer = torch.zeros(self.bytes + 256, dtype=torch.uint8, device=dev)

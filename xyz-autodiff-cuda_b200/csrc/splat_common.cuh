@@ -9,7 +9,7 @@
 //      pair weight exp(-d2/2) is EXACTLY 0.0f (so skipping those pairs cannot change any result);
 //   2. integer work: per-tile lists of Gaussian ids, each ascending (= the reference's summation
 //      order), built by a stable counting sort by tile (splat_host.cu section 2b) or, for more than
-//      8192 tiles, (tile, Gaussian) keys + a stable radix sort; per-tile [begin, end) ranges;
+//      57 344 tiles per row band, (tile, Gaussian) keys + a stable radix sort; per-tile [begin, end) ranges;
 //   3. splat_forward_kernel  : one CTA per tile, four pixels per thread, records staged in shared
 //      memory; writes the image and one loss partial per tile;
 //   4. splat_backward_kernel : one THREAD per (tile, Gaussian) list entry looping over the tile's

@@ -278,7 +278,12 @@ __global__ void __launch_bounds__(256)
 //                             against the CPU restatement).  Also writes the backward work list.
 constexpr int kBinThreads = 256;
 constexpr int kBinBatch = 32;  // chunk sizes are multiples of this
-constexpr int kBinMaxTiles = 8192;  // 4 bytes of shared memory per tile (histogram / next free slot)
+// 4 bytes of shared memory per tile of the launch's row band (histogram / next free slot): up to 32 KB (8192 tiles, e.g.
+// 2048 x 1024) the kernels keep several CTAs per SM; beyond that they opt in to the SM's full 227 KB (57 344 tiles =
+// 14.7 Mpixel per band) with fewer CTAs per SM.  Only bands larger than that fall back to the radix path.
+constexpr int kBinMaxTiles = 57344;
+constexpr int kBinSmallTiles = 8192;
+constexpr size_t kBinSmemBudget = 220 * 1024;
 constexpr long long kBinLongList = 40LL << 20;  // predicted list length beyond which the chunks become one per SM
 
 // one CTA of 1024 threads: exclusive scans over the tiles of (list length) and of ceil(list length / kBwdChunk)
@@ -806,7 +811,9 @@ int make_plan(SplatPlan& p, int W, int H, int N, int row_begin, int row_end, int
             const int x = e ? std::atoi(e) : 0;
             return x > 0 && x <= 64 ? x : 0;
         }();
-        const int per_sm = forced ? forced : (predicted_entries <= kBinLongList ? 4 : 1);
+        int per_sm = forced ? forced : (predicted_entries <= kBinLongList ? 4 : 1);
+        if (band_tiles > kBinSmallTiles)  // CTAs that fit next to each other with 4 bytes of shared memory per tile
+            per_sm = std::max(1, std::min(per_sm, static_cast<int>(kBinSmemBudget / (sizeof(unsigned int) * band_tiles))));
         const int want = per_sm * sm_count();
         p.chunk_size = ((ng + want - 1) / want + kBinBatch - 1) / kBinBatch * kBinBatch;
         p.n_chunks = (ng + p.chunk_size - 1) / p.chunk_size;
@@ -938,6 +945,18 @@ int enqueue_front(const SplatPlan& p, const Bound& o, const xyz_gaussian_params*
         return 0;
     }
     if (p.counting) {
+        if (p.n_tiles_l > kBinSmallTiles) {  // more than 32 KB of counters: opt in to the large shared-memory carve-out
+            static const cudaError_t once = [] {
+                const int bytes = static_cast<int>(sizeof(unsigned int) * kBinMaxTiles);
+                cudaError_t e = cudaFuncSetAttribute(splat_preprocess_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+                if (e == cudaSuccess)
+                    e = cudaFuncSetAttribute(splat_bin_scatter_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+                if (e == cudaSuccess)
+                    e = cudaFuncSetAttribute(splat_bin_scatter_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+                return e;
+            }();
+            if (once != cudaSuccess) return static_cast<int>(once);
+        }
         splat_preprocess_kernel<true><<<p.n_chunks, 256, sizeof(unsigned int) * p.n_tiles_l, st>>>(
             p.v, gaussians, o.b.records, o.b.rects, o.b.touched, o.b.spans, p.d2max, p.no_cull, p.chunk_size, p.n_tiles_l,
             o.hist, reinterpret_cast<unsigned int*>(o.header + 2), o.chunk_total, o.b.fwd_records, kappa);
@@ -977,7 +996,7 @@ int enqueue_back(const SplatPlan& p, const EntryLayout& L, const Bound& o, const
     const SplatBuffers& b = o.b;
     if (entries > 0) {
         if (p.counting) {
-            const size_t smem = sizeof(unsigned int) * p.n_tiles_l;  // <= 32 KB (kBinMaxTiles)
+            const size_t smem = sizeof(unsigned int) * p.n_tiles_l;  // <= 224 KB (kBinMaxTiles; opt-in set by enqueue_front)
             if (p.deterministic)
                 splat_bin_scatter_kernel<true><<<p.n_chunks, kBinThreads, smem, st>>>(
                     p.v, b.records, b.rects, b.spans, b.touched, b.offsets, p.chunk_size, p.n_tiles_l, p.tile0, o.hist,
@@ -1219,7 +1238,7 @@ int ws_plan(SplatPlan& p, EntryLayout& L, int W, int H, int N, int row_begin, in
     if (flags & XYZ_FLAG_RADIX_BINNING) return XYZ_ERR_INVALID_ARGUMENT;
     int err = make_plan(p, W, H, N, row_begin, row_end, flags, max_entries, st);
     if (err) return err;
-    if (!p.counting) return XYZ_ERR_INVALID_ARGUMENT;  // more than 8192 tiles: the radix path needs host-side counts
+    if (!p.counting) return XYZ_ERR_INVALID_ARGUMENT;  // more than 57 344 tiles in the band: the radix path needs host-side counts
     L = make_entry_layout(p, max_entries, st);
     return 0;
 }
