@@ -102,6 +102,7 @@ if os.environ.get("SANITIZE_R02", "1") != "0":
     for st in (s1, s2):
         ws = x.SplatWorkspace(Ws, Hs, Ns, 300 * Ns, x.FLAG_DETERMINISTIC)
         grads = torch.zeros((Ns, 9), device=dev); img = torch.zeros((Ws * Hs, 3), device=dev); loss = torch.zeros(1, device=dev)
+        st.wait_stream(torch.cuda.current_stream())   # the zero fills above ran on the current stream
         with torch.cuda.stream(st):
             ws.launch(tp, grads, tt, img, loss, stream=st)
         keep.append((ws, grads, img, loss))
