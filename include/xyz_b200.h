@@ -103,6 +103,14 @@ enum {
                                     XYZ_ERR_WORKSPACE once, without launching anything, and the buffers are sized afresh
                                     from the reported length: repeat the iteration.  Results of a launch that fits are
                                     the same as without the flag. */
+    XYZ_FLAG_BWD_ALL_PAIRS = 1024, /* splat: the backward pass visits every pair of the tile lists, like the forward
+                                    pass.  By default it leaves out the 16 x 8 half tiles of a (tile, Gaussian) entry on
+                                    which d2 > 64 everywhere: every gradient term of such a pair carries the factor
+                                    exp(-d2 / 2) < exp(-32) = 1.3e-14 (2^-46), five orders of magnitude below the fp32
+                                    resolution of the sums it would be added to and nine below the 1e-4 bar of
+                                    atomically accumulated sums; 61 % of the listed pixels at 100 K Gaussians x 1024^2.
+                                    Image and loss are not affected (the forward pass always renders the full lists).
+                                    XYZ_FLAG_NO_CULL implies this flag. */
 };
 
 enum {

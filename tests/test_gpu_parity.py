@@ -571,6 +571,27 @@ def test_splat_cull_is_result_preserving_and_deterministic():
         assert (np.abs(d0[0] - g0) <= tol).all()
 
 
+def test_splat_backward_cull_drops_only_terms_below_fp32_resolution():
+    """The backward pass leaves out (entry, half tile) items with d2 > 64 everywhere (weights below exp(-32)).  In
+    deterministic mode every kept entry is computed by the same instructions with and without the cull, so the difference
+    between the two IS the dropped terms: it must stay below 1e-9 of the sum of |terms| (the parity bar is 1e-4), the
+    image and the loss must not move at all, and the atomic mode must agree to the usual tolerance."""
+    for (W, H, N, seed, small) in ((160, 128, 400, 21, True), (256, 192, 300, 5, False)):
+        params, target = orc.splat_scene(N, W, H, seed=seed, small=small)
+        rg, ro, rl, tol = orc.splat_tolerance(params, target, W, H)
+        absg = (tol - 1e-30) / 1e-4   # an upper bound of sum|terms| per component (it also holds the kink terms)
+        for flags in (0, x.FLAG_PRECISE_MATH):
+            D, A = x.FLAG_DETERMINISTIC, x.FLAG_BWD_ALL_PAIRS
+            g_cut, o_cut, l_cut = run_splat(params, target, W, H, flags | D)
+            g_all, o_all, l_all = run_splat(params, target, W, H, flags | D | A)
+            assert np.array_equal(o_cut, o_all) and l_cut == l_all
+            assert (np.abs(g_cut - g_all) <= 1e-9 * absg).all()
+            g_atomic = run_splat(params, target, W, H, flags)[0]
+            g_atomic_all = run_splat(params, target, W, H, flags | A)[0]
+            assert (np.abs(g_atomic - rg) <= tol).all() and (np.abs(g_atomic_all - rg) <= tol).all()
+            assert (np.abs(g_atomic - g_all) <= tol).all()
+
+
 def test_splat_tail_cull_stays_inside_the_stated_bound():
     """XYZ_FLAG_TAIL_CULL (opt-in) drops pairs with weight < exp(-28): the image moves by at most
     N * exp(-28) * max|sigmoid(opacity) * color| and the result still meets the fp64 tolerances."""

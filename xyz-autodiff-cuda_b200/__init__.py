@@ -33,6 +33,7 @@ FLAG_RADIX_BINNING = 64
 FLAG_ASYNC = 128
 FLAG_LSQ_SHIPPED_GRAPH = 256
 FLAG_TIMING = 512
+FLAG_BWD_ALL_PAIRS = 1024
 
 GAUSSIAN_FLOATS = 9   # center[2] scale[2] rotation[1] color[3] opacity[1]
 ADAM_FLOATS = 18

@@ -24,7 +24,7 @@ namespace xyzb {
 
 constexpr int kTile = 16;                 // TILE_SIZE, gaussian_splatting_kernel.cuh:21
 constexpr int kTilePixels = kTile * kTile;
-constexpr int kBwdChunk = 128;             // list entries (= threads) per backward CTA; chunks never straddle tiles
+constexpr int kBwdChunk = 128;             // work items (= threads) per backward CTA; chunks never straddle tiles
 constexpr int kSpanRows = 16;              // tile-row spans kept per Gaussian between preprocess and key emission
 constexpr int kRecFloats = 16;            // {cx, cy, ia, ib | ic, sigmoid(opacity), r, g | b, exp(s0), exp(s1), cos | sin, 0, 0, 0}
 
@@ -38,6 +38,9 @@ constexpr float kD2MaxPrecise = 209.0f;
 constexpr float kKappaFast = -0.72134752044448170368f;
 constexpr float kKappaPrecise = -0.5f;
 constexpr float kD2MaxTail = 56.0f;  // XYZ_FLAG_TAIL_CULL (opt-in, bounded error): weights below exp(-28)
+// Backward cull: (entry, half tile) items on which min d2 exceeds this are left out of the gradient sums -- every term
+// of such a pair carries exp(-d2 / 2) < exp(-32) = 2^-46 (see splat_kernels.cuh; XYZ_FLAG_BWD_ALL_PAIRS turns it off)
+constexpr float kD2Backward = 64.0f;
 
 struct SplatView {  // what one launch renders
     int width, height, num_gaussians;
@@ -63,16 +66,20 @@ struct SplatBuffers {  // device scratch of one launch (library-owned)
     float4* rest_tiles;       // tiles x 256: (target - output, active) per pixel, tile-major, written by the forward pass
     float* tile_loss;         // 2 x tiles: one partial per half tile (rows 0..7, rows 8..15)
     float* entry_grads;       // deterministic mode: entries x 9 (indexed by ORIGINAL entry index)
+    int* bwd_items;           // 2 x entries: the backward work items of every tile, written by the forward pass: tile t's
+                              // list of half h at [2 begin + h len, + bwd_count[2 t + h])  (splat_kernels.cuh)
+    int* bwd_count;           // 2 x tiles
 };
 
 // flavour launchers (splat_fast.cu is built with -use_fast_math like the reference's training app,
 // splat_precise.cu without, like the reference's tests)
 // ticket: one unsigned int that is zero before the launch (the last CTA resets it): the forward pass itself adds the
 // per-tile loss partials, in tile order, to *total_loss
+// d2_bwd: the backward cull's bound on d2 (infinity: every listed pair becomes a backward work item)
 int splat_forward_launch_fast(const SplatView&, const SplatBuffers&, const float* target, float* output, float* total_loss,
-                              unsigned int* ticket, cudaStream_t);
+                              unsigned int* ticket, bool deterministic, float d2_bwd, cudaStream_t);
 int splat_forward_launch_precise(const SplatView&, const SplatBuffers&, const float* target, float* output,
-                                 float* total_loss, unsigned int* ticket, cudaStream_t);
+                                 float* total_loss, unsigned int* ticket, bool deterministic, float d2_bwd, cudaStream_t);
 // bwd_ctas = size of the backward work list (an upper bound of the CTAs needed; surplus records hold tile = -1)
 int splat_backward_launch_fast(const SplatView&, const SplatBuffers&, xyz_gaussian_grads* grads, long long bwd_ctas,
                                bool deterministic, cudaStream_t);

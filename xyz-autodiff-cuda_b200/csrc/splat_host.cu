@@ -763,15 +763,16 @@ struct SplatPlan {
     bool counting, deterministic, precise;
     int no_cull;
     float d2max;
+    float d2_bwd;            // backward cull (splat_kernels.cuh); infinity = every listed pair
     int chunk_size, n_chunks;
     size_t o_rec, o_frec, o_rect, o_touched, o_spans, o_offsets, o_ranges, o_tloss, o_chunks, o_rest, o_hist, o_ttotal, o_ctotal,
-        o_cbase, o_scan_tmp;
+        o_cbase, o_bcount, o_scan_tmp;
     size_t scan_tmp_bytes;
     size_t fixed_bytes;  // without the header
 };
 
 struct EntryLayout {
-    size_t o_kin, o_kout, o_vin, o_vout, o_gid, o_cinfo, o_eg, o_sort_tmp;
+    size_t o_kin, o_kout, o_vin, o_vout, o_gid, o_cinfo, o_eg, o_items, o_sort_tmp;
     size_t sort_tmp_bytes;
     size_t bytes;
     int key_bits;
@@ -791,6 +792,7 @@ int make_plan(SplatPlan& p, int W, int H, int N, int row_begin, int row_end, int
     p.deterministic = (flags & XYZ_FLAG_DETERMINISTIC) != 0;
     p.no_cull = (flags & XYZ_FLAG_NO_CULL) ? 1 : 0;
     p.d2max = (flags & XYZ_FLAG_TAIL_CULL) ? kD2MaxTail : (p.precise ? kD2MaxPrecise : kD2MaxFast);
+    p.d2_bwd = (flags & (XYZ_FLAG_BWD_ALL_PAIRS | XYZ_FLAG_NO_CULL)) ? INFINITY : kD2Backward;
     const int ty_lo = row_begin / kTile, ty_hi = (row_end + kTile - 1) / kTile;
     const int band_tiles = (ty_hi - ty_lo) * p.v.tiles_x;
     if (band_tiles <= 0) p.v.num_gaussians = N = 0;  // an empty row band renders nothing: no kernel has work
@@ -835,6 +837,7 @@ int make_plan(SplatPlan& p, int W, int H, int N, int row_begin, int row_end, int
     p.o_ttotal = take(sizeof(unsigned int) * nl);
     p.o_ctotal = take(sizeof(unsigned int) * p.n_chunks);
     p.o_cbase = take(sizeof(unsigned long long) * p.n_chunks);
+    p.o_bcount = take(sizeof(int) * 2 * p.n_tiles);  // lengths of the two backward item lists of every tile
     p.scan_tmp_bytes = 0;
     if (!p.counting)
         cub::DeviceScan::InclusiveSum(nullptr, p.scan_tmp_bytes, TouchedIter(nullptr, ToU64()),
@@ -860,6 +863,7 @@ EntryLayout make_entry_layout(const SplatPlan& p, long long capacity, cudaStream
     L.chunk_info_size = static_cast<int>(capacity / kBwdChunk + p.n_tiles_l);
     L.o_cinfo = stake(sizeof(int4) * static_cast<size_t>(ne / kBwdChunk + p.n_tiles_l));
     L.o_eg = stake(p.deterministic ? 36 * ne : 0);
+    L.o_items = stake(8 * ne);  // the backward work items: up to two per entry
     L.sort_tmp_bytes = 0;
     if (!p.counting)
         cub::DeviceRadixSort::SortPairs(nullptr, L.sort_tmp_bytes, static_cast<unsigned int*>(nullptr),
@@ -914,6 +918,7 @@ void bind_fixed(const SplatPlan& p, unsigned char* header, unsigned char* base, 
     o.tile_total = reinterpret_cast<unsigned int*>(base + p.o_ttotal);
     o.chunk_total = reinterpret_cast<unsigned int*>(base + p.o_ctotal);
     o.chunk_base = reinterpret_cast<unsigned long long*>(base + p.o_cbase);
+    o.b.bwd_count = reinterpret_cast<int*>(base + p.o_bcount);
     o.scan_tmp = base + p.o_scan_tmp;
 }
 
@@ -926,6 +931,7 @@ void bind_entry(const SplatPlan& p, const EntryLayout& L, unsigned char* sbase, 
     o.b.sorted_gid = p.deterministic ? reinterpret_cast<int*>(sbase + L.o_gid) : reinterpret_cast<int*>(o.b.vals_out);
     o.b.entry_grads = p.deterministic ? reinterpret_cast<float*>(sbase + L.o_eg) : nullptr;
     o.b.chunk_info = reinterpret_cast<int4*>(sbase + L.o_cinfo);
+    o.b.bwd_items = reinterpret_cast<int*>(sbase + L.o_items);
     o.sort_tmp = sbase + L.o_sort_tmp;
 }
 
@@ -1041,8 +1047,8 @@ int enqueue_back(const SplatPlan& p, const EntryLayout& L, const Bound& o, const
     }
     mark(tm, 3, st);
     unsigned int* fwd_ticket = reinterpret_cast<unsigned int*>(o.header + 2) + 1;  // next to the column scan's ticket
-    int err = p.precise ? splat_forward_launch_precise(p.v, b, target, output, total_loss, fwd_ticket, st)
-                        : splat_forward_launch_fast(p.v, b, target, output, total_loss, fwd_ticket, st);
+    int err = p.precise ? splat_forward_launch_precise(p.v, b, target, output, total_loss, fwd_ticket, p.deterministic, p.d2_bwd, st)
+                        : splat_forward_launch_fast(p.v, b, target, output, total_loss, fwd_ticket, p.deterministic, p.d2_bwd, st);
     if (err) return err;
     mark(tm, 4, st);
     const long long bwd_ctas = entries > 0 ? static_cast<long long>(L.chunk_info_size) : 0;

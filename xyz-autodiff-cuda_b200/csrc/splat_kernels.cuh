@@ -81,6 +81,21 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // summation order are the same in every configuration: the image is bit-identical (tested).
 // The loss partial is kept per HALF tile (tile_loss[2 tile + half], each a fixed tree over its 128 pixels), so the sum
 // the last CTA forms over the launch's half tiles has the same bits in every configuration too.
+// Smallest value of the conic form q(dx, dy) = ia dx^2 + 2 ib dx dy + ic dy^2 (positive definite) over the pixel
+// rectangle [x0, x1] x [y0, y1] given relative to the Gaussian's centre: 0 when the centre lies inside, else the smallest
+// of the four edge minima (q is convex; on an edge it is a parabola whose vertex is clamped to the edge).
+__device__ __forceinline__ float conic_min_over_rect(float ia, float ib, float ic, float kx, float ky, float x0, float x1,
+                                                     float y0, float y1) {
+    if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return 0.f;
+    const float ib2 = 2.0f * ib;
+    auto q = [&](float dx, float dy) { return fmaf(dx, fmaf(ia, dx, ib2 * dy), (ic * dy) * dy); };
+    float m = q(fminf(fmaxf(kx * y0, x0), x1), y0);
+    m = fminf(m, q(fminf(fmaxf(kx * y1, x0), x1), y1));
+    m = fminf(m, q(x0, fminf(fmaxf(ky * x0, y0), y1)));
+    m = fminf(m, q(x1, fminf(fmaxf(ky * x1, y0), y1)));
+    return m;
+}
+
 constexpr int kFwdStage = 128;  // Gaussians staged per pass
 constexpr int kHalfPixels = kTilePixels / 2;
 
@@ -89,7 +104,9 @@ __global__ void __launch_bounds__(kThreads)
     splat_forward_kernel(SplatView v, const float4* __restrict__ fwd_records, const int* __restrict__ sorted_gid,
                          const int2* __restrict__ tile_ranges, const float* __restrict__ target,
                          float* __restrict__ output, float* __restrict__ tile_loss, float4* __restrict__ rest_tiles,
-                         int tile_y0, unsigned int* __restrict__ ticket, float* total_loss) {
+                         int tile_y0, unsigned int* __restrict__ ticket, float* total_loss, int* __restrict__ bwd_items,
+                         int* __restrict__ bwd_count, float d2_bwd_scaled, const unsigned int* __restrict__ sorted_orig,
+                         float* __restrict__ entry_grads) {
     static_assert(kParts == 1 || (kParts == 2 && kThreads == 64), "half tiles are rendered by 64 threads");
     constexpr int kPixels = kTilePixels / kParts;   // pixels of this CTA
     constexpr int kRows = kPixels / kThreads;       // pixel rows per thread (4, 2, 1)
@@ -97,6 +114,7 @@ __global__ void __launch_bounds__(kThreads)
     constexpr int kPerThread = (kFwdStage + kThreads - 1) / kThreads;  // Gaussians a thread stages per pass
     __shared__ __align__(16) float4 s_a[2][kFwdStage];
     __shared__ __align__(16) float4 s_b[2][kFwdStage];
+    __shared__ int s_items[2];  // lengths of the tile's two lists of backward work items
 
     const int tid = threadIdx.x;
     const int tile_x = blockIdx.x, tile_y = tile_y0 + static_cast<int>(blockIdx.y) / kParts;
@@ -134,7 +152,17 @@ __global__ void __launch_bounds__(kThreads)
         }
         cp_async_commit();
     };
+    // backward work items (see "backward work items" below): which halves of the tile this CTA tests, where they go
+    const bool whole = entry_grads != nullptr;  // deterministic mode: one list of whole-tile items, filled by part 0
+    const float tx0 = static_cast<float>(tile_x * kTile), ty0 = static_cast<float>(tile_y * kTile);
+    int* const items0 = bwd_items + 2 * static_cast<size_t>(range.x);
+    const int list_len = range.y - range.x;
+    if (tid < 2) s_items[tid] = 0;  // (the barriers at the top of the loop / after it order this with every use)
+
     load_ids(range.x);
+    int id_cur[kPerThread];  // ids of the stage being rendered
+#pragma unroll
+    for (int q = 0; q < kPerThread; ++q) id_cur[q] = gid[q];
     fetch(0);
     load_ids(range.x + kFwdStage);
     int buf = 0;
@@ -142,12 +170,56 @@ __global__ void __launch_bounds__(kThreads)
         const int n = min(kFwdStage, range.y - base);
         // every thread is done READING buffer buf ^ 1 (the previous stage) before anybody refills it
         __syncthreads();
+        int id_nxt[kPerThread];
+#pragma unroll
+        for (int q = 0; q < kPerThread; ++q) id_nxt[q] = gid[q];
         fetch(buf ^ 1);                        // stage s + 1 (an empty group past the end)
         load_ids(base + 2 * kFwdStage);        // ids of stage s + 2
         cp_async_wait<1>();                    // this thread's copies of stage s have landed ...
         __syncthreads();                       // ... and everybody else's
         const float4* __restrict__ sa = s_a[buf];
         const float4* __restrict__ sb = s_b[buf];
+        // the stage's backward work items: min d2 over each half of the tile against the backward cull's bound, on the
+        // staged (kappa-scaled, hence negated) conic
+#pragma unroll
+        for (int q = 0; q < kPerThread; ++q) {
+            const int t = tid + q * kThreads;
+            int keep = 0;  // bit h: the item of half h (whole-tile items: bit 0)
+            if (t < n && (kParts == 1 || !whole || part == 0)) {
+                const float4 a = sa[t];
+                const float ia = -a.z, ib = -0.5f * a.w, ic = -sb[t].x;
+                // anything but a positive definite conic of finite numbers is kept (the comparisons fail on NaN)
+                const bool pd = ia > 0.f && ic > 0.f && ia * ic > ib * ib;
+                const float kx = -ib / ia, ky = -ib / ic;
+                const float x0 = tx0 - a.x, x1 = x0 + static_cast<float>(kTile - 1), y0 = ty0 - a.y;
+                const float ym = y0 + static_cast<float>(kTile / 2);
+                if (whole) {
+                    keep = (pd && conic_min_over_rect(ia, ib, ic, kx, ky, x0, x1, y0, y0 + static_cast<float>(kTile - 1)) > d2_bwd_scaled) ? 0 : 1;
+                    if (!keep) {  // the per-Gaussian sum reads every entry's row
+                        float* row = entry_grads + static_cast<size_t>(sorted_orig[base + t]) * 9;
+#pragma unroll
+                        for (int k = 0; k < 9; ++k) row[k] = 0.f;
+                    }
+                } else {
+                    if (kParts == 1 || part == 0)
+                        keep |= (pd && conic_min_over_rect(ia, ib, ic, kx, ky, x0, x1, y0, ym - 1.0f) > d2_bwd_scaled) ? 0 : 1;
+                    if (kParts == 1 || part == 1)
+                        keep |= (pd && conic_min_over_rect(ia, ib, ic, kx, ky, x0, x1, ym, ym + static_cast<float>(kTile / 2 - 1)) > d2_bwd_scaled) ? 0 : 2;
+                }
+            }
+            const int item = whole ? base + t : id_cur[q];
+#pragma unroll
+            for (int h = 0; h < 2; ++h) {
+                if (kParts == 2 && h != part && !(whole && h == 0)) continue;
+                const unsigned int votes = __ballot_sync(0xffffffffu, (keep >> h) & 1);
+                if (votes == 0u) continue;
+                const int lane = tid & 31;
+                int at = 0;
+                if (lane == 0) at = atomicAdd(&s_items[h], __popc(votes));
+                at = __shfl_sync(0xffffffffu, at, 0) + __popc(votes & ((1u << lane) - 1u));
+                if ((keep >> h) & 1) items0[static_cast<size_t>(h) * list_len + at] = item;
+            }
+        }
         XYZ_UNROLL(XYZ_FWD_UNROLL)
         for (int j = 0; j < n; ++j) {
             const float4 a = sa[j];
@@ -164,6 +236,8 @@ __global__ void __launch_bounds__(kThreads)
                 o[k][2] = fmaf(b.w, e, o[k][2]);
             }
         }
+#pragma unroll
+        for (int q = 0; q < kPerThread; ++q) id_cur[q] = id_nxt[q];
     }
     cp_async_wait<0>();
     __shared__ float s_l[kTilePixels];  // per-pixel |out - target| by pixel index inside the tile (row-major)
@@ -191,6 +265,7 @@ __global__ void __launch_bounds__(kThreads)
         s_l[pix] = l;
     }
     __syncthreads();
+    if (tid < 2 && (kParts == 1 || tid == part)) bwd_count[2 * tile + tid] = s_items[tid];  // (the list part 1 leaves empty in deterministic mode: 0)
     // loss partial of a half tile: lane i adds its pixels i, i + 32, i + 64, i + 96, then a shuffle tree.  One warp per
     // half this CTA owns (every configuration has at least two warps).
     __shared__ int s_last;
@@ -301,8 +376,8 @@ struct RestPair {
 template <bool kMasked>
 __device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_rest, float px0, float py0, float cx,
                                                 float cy, float A2, float B2, float C2, float cs0, float cs1,
-                                                float cs2, float c0, float c1, float c2, float (&ac)[3],
-                                                float (&T)[6]) {
+                                                float cs2, float c0, float c1, float c2, int row0, int nrows,
+                                                float (&ac)[3], float (&T)[6]) {
     const float dx0 = px0 - cx;
     F2 dxs[kTile / 2];  // (px0 - cx) + j: one rounding more than the forward pass
 #pragma unroll
@@ -316,7 +391,7 @@ __device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_r
     const F2 cs0p = f2_pack(cs0, cs0), cs1p = f2_pack(cs1, cs1), cs2p = f2_pack(cs2, cs2);
     const F2 c0p = f2_pack(c0, c0), c1p = f2_pack(c1, c1), c2p = f2_pack(c2, c2);
     XYZ_UNROLL(XYZ_BWD_ROW_UNROLL)
-    for (int r = 0; r < kTile; ++r) {
+    for (int r = row0; r < row0 + nrows; ++r) {
         const float dy = (py0 + static_cast<float>(r)) - cy;
         const float u = B2 * dy;
         const float t = (C2 * dy) * dy;
@@ -371,24 +446,47 @@ __device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_r
     }
 }
 
-// One CTA = up to kBwdChunk consecutive list entries of ONE tile: chunk_info[c] = {tile, first entry, end of the tile's
-// list, -} written by splat_chunk_scan_kernel; the grid is an upper bound, surplus CTAs see tile = -1 and exit.
+// ---- backward work items (written by the forward pass, see splat_forward_kernel) ----
+// The tile lists hold every pair whose weight is not EXACTLY zero (d2 <= 176: 13 sigma), which the forward pass needs for
+// a bit-identical image.  A gradient is an atomically accumulated sum held to 1e-4 of the sum of its terms' magnitudes, and
+// the terms of a pair carry the factor e = exp(-d2 / 2): beyond d2 = d2_bwd (default 64: e < 2^-46) they are far below
+// the fp32 resolution of the sums they would join.  So the backward pass works on ITEMS = (list entry, 16 x 8 half of the
+// tile) and leaves out the items on which min d2 > d2_bwd -- 61 % of the listed pixels at BASELINE's C4.  The forward
+// CTA of a tile has every entry's record in shared memory anyway: it tests the two halves of each entry and appends the
+// survivors to the tile's two item lists
+//     bwd_items[2 begin + h len + j],  j < bwd_count[2 tile + h]      (begin, len: the tile's range in the sorted list)
+// (deterministic mode: ONE list of whole-tile items per tile -- one row of entry_grads per entry; rows of entries that
+// are left out are zeroed here).  An item is the Gaussian id (deterministic mode: the entry's index, which leads to the
+// id and to the row).  The order of a list depends on warp timing and never enters a result.
+// XYZ_FLAG_BWD_ALL_PAIRS / XYZ_FLAG_NO_CULL pass d2_bwd = inf: every entry yields both items.
+//
+// One backward CTA = up to kBwdChunk (= threads) consecutive items of one half of one tile; the grid is the raw work list
+// chunk_info[c] = {tile, first entry, end of the tile's list, -} (one record per kBwdChunk raw entries, surplus records
+// hold tile = -1) x the two halves: CTA (c, h) takes the items [k kBwdChunk, (k + 1) kBwdChunk) of list h, k = c's
+// position inside its tile, and exits when the list is shorter -- an upper bound of the CTAs needed that the host knows
+// without reading anything back.
 __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
     splat_backward_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ chunk_info,
-                          const float4* __restrict__ rest_tiles, const int* __restrict__ sorted_gid,
-                          const unsigned int* __restrict__ sorted_orig, xyz_gaussian_grads* grads,
-                          float* __restrict__ entry_grads) {
+                          const int2* __restrict__ tile_ranges, const int* __restrict__ bwd_items,
+                          const int* __restrict__ bwd_count, const float4* __restrict__ rest_tiles,
+                          const int* __restrict__ sorted_gid, const unsigned int* __restrict__ sorted_orig,
+                          xyz_gaussian_grads* grads, float* __restrict__ entry_grads) {
     __shared__ RestPair s_rest[kTilePixels / 2];  // -(tgt - out) and the active mask, pixel pairs (see RestPair)
 
     const int tid = threadIdx.x;
     const int4 info = __ldg(chunk_info + blockIdx.x);
     const int tile = info.x;
     if (tile < 0) return;
-    const int i = info.y + tid;
-    const bool valid = i < info.z;
+    const bool whole = entry_grads != nullptr;  // deterministic mode: whole-tile items, one list
+    const int half = blockIdx.y;
+    const int2 range = __ldg(tile_ranges + tile);
+    const int first = info.y - range.x;  // this CTA's first item inside list `half`
+    const int count = __ldg(bwd_count + 2 * tile + half);
+    if (first >= count) return;
+    const bool valid = first + tid < count;
     const int tile_x = tile % v.tiles_x, tile_y = tile / v.tiles_x;
-#pragma unroll
-    for (int p = tid; p < kTilePixels; p += kBwdChunk) {
+    const int row0 = half * (kTile / 2), nrows = whole ? kTile : kTile / 2;
+    for (int p = row0 * kTile + tid; p < (row0 + nrows) * kTile; p += kBwdChunk) {
         const float4 rest = __ldg(rest_tiles + static_cast<size_t>(tile) * kTilePixels + p);
         float* pair = reinterpret_cast<float*>(&s_rest[p >> 1]) + (p & 1);
         pair[0] = -rest.x;
@@ -400,86 +498,91 @@ __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
                             (tile_y * kTile + kTile <= v.row_end);
 
     float cx = 0.f, cy = 0.f, ia = 0.f, ib = 0.f, ic = 0.f, so = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-    int g = 0;
+    int g = 0, item = 0;
+    float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
-        g = sorted_gid[i];
-        const float4 r0 = __ldg(records + 4 * g), r1 = __ldg(records + 4 * g + 1), r2 = __ldg(records + 4 * g + 2);
+        item = __ldg(bwd_items + 2 * static_cast<size_t>(range.x) + static_cast<size_t>(half) * (range.y - range.x) + first + tid);
+        g = whole ? sorted_gid[item] : item;
+        const float4 r0 = __ldg(records + 4 * g), r1 = __ldg(records + 4 * g + 1);
+        r2 = __ldg(records + 4 * g + 2);
         cx = r0.x; cy = r0.y; ia = r0.z; ib = r0.w;
         ic = r1.x; so = r1.y; c0 = r1.z; c1 = r1.w; c2 = r2.x;
     }
     __syncthreads();
     if (!valid) return;
-
-    float ac[3] = {0.f, 0.f, 0.f};
-    float T[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // sum t {1, dx, dy, dx^2, dx dy, dy^2}
     {
-        const float px0 = static_cast<float>(tile_x * kTile), py0 = static_cast<float>(tile_y * kTile);
-        const float A2 = kKappa * ia, B2 = (2.0f * kKappa) * ib, C2 = kKappa * ic;
-        const float cs0 = so * c0, cs1 = so * c1, cs2 = so * c2;
-        if (all_active)
-            entry_tile_pass<false>(s_rest, px0, py0, cx, cy, A2, B2, C2, cs0, cs1, cs2, c0, c1, c2, ac, T);
-        else
-            entry_tile_pass<true>(s_rest, px0, py0, cx, cy, A2, B2, C2, cs0, cs1, cs2, c0, c1, c2, ac, T);
-    }
-    // per-pair g_d2 = gamma * t with gamma = -0.5 so
-    const float gamma = -0.5f * so;
-    const float Gx = gamma * T[1], Gy = gamma * T[2];
-    const float a_ia = gamma * T[3], a_ib = 2.0f * (gamma * T[4]), a_ic = gamma * T[5];
-    const float ib2 = 2.0f * ib;
-    const float a_cx = -(2.0f * ia * Gx + ib2 * Gy);
-    const float a_cy = -(ib2 * Gx + 2.0f * ic * Gy);
-    const float a_so = T[0];
+        float ac[3] = {0.f, 0.f, 0.f};
+        float T[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};  // sum t {1, dx, dy, dx^2, dx dy, dy^2}
+        {
+            const float px0 = static_cast<float>(tile_x * kTile), py0 = static_cast<float>(tile_y * kTile);
+            const float A2 = kKappa * ia, B2 = (2.0f * kKappa) * ib, C2 = kKappa * ic;
+            const float cs0 = so * c0, cs1 = so * c1, cs2 = so * c2;
+            if (all_active)
+                entry_tile_pass<false>(s_rest, px0, py0, cx, cy, A2, B2, C2, cs0, cs1, cs2, c0, c1, c2, row0, nrows, ac, T);
+            else
+                entry_tile_pass<true>(s_rest, px0, py0, cx, cy, A2, B2, C2, cs0, cs1, cs2, c0, c1, c2, row0, nrows, ac, T);
+        }
+        // per-pair g_d2 = gamma * t with gamma = -0.5 so
+        const float gamma = -0.5f * so;
+        const float Gx = gamma * T[1], Gy = gamma * T[2];
+        const float a_ia = gamma * T[3], a_ib = 2.0f * (gamma * T[4]), a_ic = gamma * T[5];
+        const float ib2 = 2.0f * ib;
+        const float a_cx = -(2.0f * ia * Gx + ib2 * Gy);
+        const float a_cy = -(ib2 * Gx + 2.0f * ic * Gy);
+        const float a_so = T[0];
 
-    // Per-Gaussian chain rule, once per entry (linear in the sums above).
-    // sym_matrix2_inv backward (sym_matrix2_inv_logic.cuh:43-77) needs Sigma = (A, B, C): rebuilt from exp(scale), cos
-    // and sin AS THE PREPROCESS KERNEL COMPUTED THEM (IEEE expf / cosf / sinf in both flavours, kept in the record), so
-    // the chain rule is applied at the Sigma whose inverse the forward pass rendered with -- the fast-math flavour's
-    // ex2.approx / sin.approx (no range reduction) never enter it.  exp_logic.cuh:17-36, covariance_generation.cuh:154-172
-    const float4 q2 = __ldg(records + 4 * g + 2), q3 = __ldg(records + 4 * g + 3);
-    const float es0 = q2.y, es1 = q2.z, ct = q2.w, sn = q3.x;
-    const float m00 = es0 * ct, m01 = -es1 * sn, m10 = es0 * sn, m11 = es1 * ct;  // covariance_generation.cuh:154-172
-    const float A = m00 * m00 + m01 * m01, B = m00 * m10 + m01 * m11, C = m10 * m10 + m11 * m11;
-    float det = A * C - B * B;
-    if (fabsf(det) < 1e-8f) det = 1e-8f;
-    const float inv_det = 1.0f / det;
-    const float inv_det2 = inv_det * inv_det;
-    const float g_A = a_ia * (-C * C * inv_det2) + a_ib * (B * C * inv_det2) + a_ic * (inv_det - A * C * inv_det2);
-    const float g_B = a_ia * (2.0f * C * B * inv_det2) + a_ib * (-inv_det - 2.0f * B * B * inv_det2) +
-                      a_ic * (2.0f * A * B * inv_det2);
-    const float g_C = a_ia * (inv_det - A * C * inv_det2) + a_ib * (A * B * inv_det2) + a_ic * (-A * A * inv_det2);
-    // scale_rotation_to_covariance_3param backward (covariance_generation.cuh:175-211)
-    const float g00 = g_A * 2.0f * m00 + g_B * m10;
-    const float g01 = g_A * 2.0f * m01 + g_B * m11;
-    const float g10 = g_B * m00 + g_C * 2.0f * m10;
-    const float g11 = g_B * m01 + g_C * 2.0f * m11;
-    const float g_es0 = g00 * ct + g10 * sn;
-    const float g_es1 = g01 * (-sn) + g11 * ct;
-    const float g_theta = g00 * (-es0 * sn) + g01 * (-es1 * ct) + g10 * (es0 * ct) + g11 * (-es1 * sn);
-    float out9[9];
-    out9[0] = a_cx;
-    out9[1] = a_cy;
-    out9[2] = g_es0 * es0;  // exp backward recomputes exp(scale)
-    out9[3] = g_es1 * es1;
-    out9[4] = g_theta;
-    out9[5] = so * ac[0];  // sum s_i w = so * sum s_i e
-    out9[6] = so * ac[1];
-    out9[7] = so * ac[2];
-    out9[8] = a_so * (so * (1.0f - so));  // sigmoid_logic.cuh:27-36
-    if (entry_grads) {
-        float* row = entry_grads + static_cast<size_t>(sorted_orig[i]) * 9;
+        // Per-Gaussian chain rule, once per entry (linear in the sums above).
+        // sym_matrix2_inv backward (sym_matrix2_inv_logic.cuh:43-77) needs Sigma = (A, B, C): rebuilt from exp(scale), cos
+        // and sin AS THE PREPROCESS KERNEL COMPUTED THEM (IEEE expf / cosf / sinf in both flavours, kept in the record), so
+        // the chain rule is applied at the Sigma whose inverse the forward pass rendered with -- the fast-math flavour's
+        // ex2.approx / sin.approx (no range reduction) never enter it.  exp_logic.cuh:17-36, covariance_generation.cuh:154-172
+        const float sn = __ldg(reinterpret_cast<const float*>(records + 4 * g + 3));
+        const float es0 = r2.y, es1 = r2.z, ct = r2.w;
+        const float m00 = es0 * ct, m01 = -es1 * sn, m10 = es0 * sn, m11 = es1 * ct;  // covariance_generation.cuh:154-172
+        const float A = m00 * m00 + m01 * m01, B = m00 * m10 + m01 * m11, C = m10 * m10 + m11 * m11;
+        float det = A * C - B * B;
+        if (fabsf(det) < 1e-8f) det = 1e-8f;
+        const float inv_det = 1.0f / det;
+        const float inv_det2 = inv_det * inv_det;
+        const float g_A = a_ia * (-C * C * inv_det2) + a_ib * (B * C * inv_det2) + a_ic * (inv_det - A * C * inv_det2);
+        const float g_B = a_ia * (2.0f * C * B * inv_det2) + a_ib * (-inv_det - 2.0f * B * B * inv_det2) +
+                          a_ic * (2.0f * A * B * inv_det2);
+        const float g_C = a_ia * (inv_det - A * C * inv_det2) + a_ib * (A * B * inv_det2) + a_ic * (-A * A * inv_det2);
+        // scale_rotation_to_covariance_3param backward (covariance_generation.cuh:175-211)
+        const float g00 = g_A * 2.0f * m00 + g_B * m10;
+        const float g01 = g_A * 2.0f * m01 + g_B * m11;
+        const float g10 = g_B * m00 + g_C * 2.0f * m10;
+        const float g11 = g_B * m01 + g_C * 2.0f * m11;
+        const float g_es0 = g00 * ct + g10 * sn;
+        const float g_es1 = g01 * (-sn) + g11 * ct;
+        const float g_theta = g00 * (-es0 * sn) + g01 * (-es1 * ct) + g10 * (es0 * ct) + g11 * (-es1 * sn);
+        float out9[9];
+        out9[0] = a_cx;
+        out9[1] = a_cy;
+        out9[2] = g_es0 * es0;  // exp backward recomputes exp(scale)
+        out9[3] = g_es1 * es1;
+        out9[4] = g_theta;
+        out9[5] = so * ac[0];  // sum s_i w = so * sum s_i e
+        out9[6] = so * ac[1];
+        out9[7] = so * ac[2];
+        out9[8] = a_so * (so * (1.0f - so));  // sigmoid_logic.cuh:27-36
+        if (entry_grads) {
+            float* row = entry_grads + static_cast<size_t>(sorted_orig[item]) * 9;
 #pragma unroll
-        for (int k = 0; k < 9; ++k) row[k] = out9[k];
-    } else {
-        float* gg = reinterpret_cast<float*>(grads + g);
+            for (int k = 0; k < 9; ++k) row[k] = out9[k];
+        } else {
+            float* gg = reinterpret_cast<float*>(grads + g);
 #pragma unroll
-        for (int k = 0; k < 9; ++k) atomicAdd(gg + k, out9[k]);  // VariableRef::add_grad, variable.cuh:48-50
+            for (int k = 0; k < 9; ++k) atomicAdd(gg + k, out9[k]);  // VariableRef::add_grad, variable.cuh:48-50
+        }
     }
 }
 
 }  // namespace
 
 int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const SplatBuffers& b, const float* target,
-                                                     float* output, float* total_loss, unsigned int* ticket, cudaStream_t st) {
+                                                     float* output, float* total_loss, unsigned int* ticket, bool deterministic,
+                                                     float d2_bwd, cudaStream_t st) {
     const int ty0 = v.row_begin / kTile, ty1 = (v.row_end + kTile - 1) / kTile;
     if (ty1 <= ty0) return 0;
     // configuration by how many tiles an SM gets (see the kernel); XYZ_SPLAT_FWD_THREADS = 64 | 128 | 256 (threads of a
@@ -495,7 +598,9 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
     const int sms = sm_count();
     const int cfg = forced ? forced : (tiles >= 12LL * sms ? 64 : 32);
     const dim3 grid(v.tiles_x, (ty1 - ty0) * (cfg == 32 ? 2 : 1));
-#define XYZ_FWD_ARGS v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output, b.tile_loss, b.rest_tiles, ty0, ticket, total_loss
+    const float d2s = -kKappa * d2_bwd;  // on the staged conic (scaled by kappa < 0); inf stays inf
+#define XYZ_FWD_ARGS v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output, b.tile_loss, b.rest_tiles, ty0, ticket, total_loss, \
+                     b.bwd_items, b.bwd_count, d2s, b.vals_out, deterministic ? b.entry_grads : nullptr
     if (cfg == 32) splat_forward_kernel<64, 2><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
     else if (cfg == 64) splat_forward_kernel<64, 1><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
     else if (cfg == 128) splat_forward_kernel<128, 1><<<grid, 128, 0, st>>>(XYZ_FWD_ARGS);
@@ -508,8 +613,9 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
 int XYZ_CAT(splat_backward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const SplatBuffers& b, xyz_gaussian_grads* grads,
                                                       long long bwd_ctas, bool deterministic, cudaStream_t st) {
     if (bwd_ctas <= 0) return 0;
-    splat_backward_kernel<<<static_cast<unsigned int>(bwd_ctas), kBwdChunk, 0, st>>>(
-        v, b.records, b.chunk_info, b.rest_tiles, b.sorted_gid, b.vals_out, grads, deterministic ? b.entry_grads : nullptr);
+    splat_backward_kernel<<<dim3(static_cast<unsigned int>(bwd_ctas), deterministic ? 1 : 2), kBwdChunk, 0, st>>>(
+        v, b.records, b.chunk_info, b.tile_ranges, b.bwd_items, b.bwd_count, b.rest_tiles, b.sorted_gid, b.vals_out, grads,
+        deterministic ? b.entry_grads : nullptr);
     count_launch();
     return last_error();
 }
