@@ -1054,7 +1054,8 @@ long long orc_splat_binning(const float* rec, int N, int W, int H, int row_begin
 // and warps run one after the other here; since a tile has exactly one owner lane, any interleaving gives the same
 // lists.  Purpose: the index arithmetic can be swept over image shapes / row bands / chunk counts on the CPU
 // (tests/test_oracle.py); the CUDA kernels themselves are held to orc_splat_binning on the GPU.
-// Outputs: tile_ranges (tiles x 2), sorted_ids (capacity), work list chunk_info (chunk_info_size x 4, surplus = -1).
+// Outputs: tile_ranges (tiles x 2), sorted_ids (capacity), backward work records chunk_info (chunk_info_size x 4: the
+// binning only marks the records beyond those set aside for the tiles with -1).
 // Returns the list length, or -1 if an owner rule is violated (a slot written twice / out of its tile's range).
 long long orc_splat_binning_counting(const float* rec, int N, int W, int H, int row_begin, int row_end, float d2max,
                                      int no_cull, int ctas_total, int bwd_chunk, int32_t* tile_ranges,
@@ -1099,7 +1100,8 @@ long long orc_splat_binning_counting(const float* rec, int N, int W, int H, int 
     std::vector<int> chunk_offsets(n_tiles + 1, 0);
     for (int t = 0; t < n_tiles; ++t) {
         begin[t + 1] = begin[t] + tile_total[t];
-        chunk_offsets[t + 1] = chunk_offsets[t] + static_cast<int>((tile_total[t] + bwd_chunk - 1) / bwd_chunk);
+        // backward work records set aside per tile: ceil(len / chunk) + 2 for a non-empty list (the forward pass fills them in)
+        chunk_offsets[t + 1] = chunk_offsets[t] + (tile_total[t] ? static_cast<int>((tile_total[t] + bwd_chunk - 1) / bwd_chunk) + 2 : 0);
         if (tile_ranges) {
             tile_ranges[2 * t] = static_cast<int32_t>(begin[t]);
             tile_ranges[2 * t + 1] = static_cast<int32_t>(begin[t + 1]);
@@ -1112,18 +1114,8 @@ long long orc_splat_binning_counting(const float* rec, int N, int W, int H, int 
     // scatter
     for (int block = 0; block < n_chunks; ++block) {
         const int g_begin = block * chunk_size, g_end = std::min(g_begin + chunk_size, N);
-        if (chunk_info) {  // the work list, distributed over the CTAs and threads like in the kernel
+        if (chunk_info) {  // the work records beyond the tiles' own: none (distributed over the CTAs and threads like in the kernel)
             for (int tid = 0; tid < 256; ++tid) {
-                for (int t = block * 256 + tid; t < n_tiles; t += n_chunks * 256) {
-                    const int first = chunk_offsets[t], c = chunk_offsets[t + 1] - first;
-                    for (int k = 0; k < c; ++k) {
-                        int32_t* ci = chunk_info + 4 * static_cast<size_t>(first + k);
-                        ci[0] = t;
-                        ci[1] = static_cast<int32_t>(begin[t]) + k * bwd_chunk;
-                        ci[2] = static_cast<int32_t>(begin[t + 1]);
-                        ci[3] = 0;
-                    }
-                }
                 for (int c = chunk_offsets[n_tiles] + block * 256 + tid; c < chunk_info_size; c += n_chunks * 256) {
                     int32_t* ci = chunk_info + 4 * static_cast<size_t>(c);
                     ci[0] = ci[1] = ci[2] = ci[3] = -1;

@@ -61,25 +61,28 @@ struct SplatBuffers {  // device scratch of one launch (library-owned)
     unsigned int* vals_out;   // entries: sorted -> original entry index
     int* sorted_gid;          // entries: Gaussian id per sorted entry (fast mode: aliases vals_out)
     int2* tile_ranges;        // tiles: [begin, end)
-    int* chunk_offsets;       // tiles + 1: exclusive scan of ceil(list length / kBwdChunk) = backward CTAs before a tile
-    int4* chunk_info;         // backward CTAs (upper bound entries/kBwdChunk + tiles): {tile or -1, first entry, list end, 0}
+    int* chunk_offsets;       // tiles of the launch + 1: exclusive scan of the backward work records set aside per tile
+                              // (ceil(list length / kBwdChunk) + 2 for a non-empty list)
+    int4* chunk_info;         // backward work records = CTAs (entries / kBwdChunk + 3 tiles, an upper bound):
+                              // {tile or -1, first item's slot, items, list}, written by the forward pass
     float4* rest_tiles;       // tiles x 256: (target - output, active) per pixel, tile-major, written by the forward pass
     float* tile_loss;         // 2 x tiles: one partial per half tile (rows 0..7, rows 8..15)
     float* entry_grads;       // deterministic mode: entries x 9 (indexed by ORIGINAL entry index)
-    int* bwd_items;           // 2 x entries: the backward work items of every tile, written by the forward pass: tile t's
-                              // list of half h at [2 begin + h len, + bwd_count[2 t + h])  (splat_kernels.cuh)
-    int* bwd_count;           // 2 x tiles
+    int* bwd_items;           // 2 x entries: the backward work items, written by the forward pass into the 2 len slots
+                              // of every tile (three lists, see splat_kernels.cuh)
 };
 
 // flavour launchers (splat_fast.cu is built with -use_fast_math like the reference's training app,
 // splat_precise.cu without, like the reference's tests)
 // ticket: one unsigned int that is zero before the launch (the last CTA resets it): the forward pass itself adds the
 // per-tile loss partials, in tile order, to *total_loss
-// d2_bwd: the backward cull's bound on d2 (infinity: every listed pair becomes a backward work item)
+// d2_bwd: the backward cull's bound on d2 (infinity: every listed pair becomes a backward work item);
+// first_tile: the tile chunk_offsets[0] belongs to (the first tile of the row band; 0 on the radix path)
 int splat_forward_launch_fast(const SplatView&, const SplatBuffers&, const float* target, float* output, float* total_loss,
-                              unsigned int* ticket, bool deterministic, float d2_bwd, cudaStream_t);
+                              unsigned int* ticket, bool deterministic, float d2_bwd, int first_tile, cudaStream_t);
 int splat_forward_launch_precise(const SplatView&, const SplatBuffers&, const float* target, float* output,
-                                 float* total_loss, unsigned int* ticket, bool deterministic, float d2_bwd, cudaStream_t);
+                                 float* total_loss, unsigned int* ticket, bool deterministic, float d2_bwd, int first_tile,
+                                 cudaStream_t);
 // bwd_ctas = size of the backward work list (an upper bound of the CTAs needed; surplus records hold tile = -1)
 int splat_backward_launch_fast(const SplatView&, const SplatBuffers&, xyz_gaussian_grads* grads, long long bwd_ctas,
                                bool deterministic, cudaStream_t);

@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(256)
 //   splat_bin_scatter_kernel  every chunk walks its Gaussians again, ascending id; every tile is owned by one lane
 //                             (see the kernel), slot = next[tile]++  -- ascending Gaussian id inside every tile list
 //                             = exactly the stable sort the radix path produces (tested bit for bit against it and
-//                             against the CPU restatement).  Also writes the backward work list.
+//                             against the CPU restatement).  Also marks the unused backward work records.
 constexpr int kBinThreads = 256;
 constexpr int kBinBatch = 32;  // chunk sizes are multiples of this
 // 4 bytes of shared memory per tile of the launch's row band (histogram / next free slot): up to 32 KB (8192 tiles, e.g.
@@ -286,7 +286,7 @@ constexpr int kBinSmallTiles = 8192;
 constexpr size_t kBinSmemBudget = 220 * 1024;
 constexpr long long kBinLongList = 40LL << 20;  // predicted list length beyond which the chunks become one per SM
 
-// one CTA of 1024 threads: exclusive scans over the tiles of (list length) and of ceil(list length / kBwdChunk)
+// one CTA of 1024 threads: exclusive scans over the tiles of (list length) and of the backward work records per tile
 // `capacity` (0 = unlimited) is the list length the entry-sized buffers were sized for (XYZ_FLAG_ASYNC): a longer list
 // publishes EMPTY tile ranges and an empty work list instead and bumps the sticky counter total_entries[1] (which never
 // falls below `overflow_base`, the count the host has seen), so that no later kernel of the launch reads or writes
@@ -327,6 +327,12 @@ __device__ __forceinline__ void cta_exclusive_scan_u32_to_u64(const unsigned int
     }
 }
 
+// backward work records set aside for a tile with `len` list entries: the forward pass sorts every entry into at most
+// one of three item lists and each list takes ceil(items / kBwdChunk) records (splat_kernels.cuh)
+__host__ __device__ __forceinline__ int bwd_records_of(unsigned int len) {
+    return len ? static_cast<int>((len + kBwdChunk - 1) / kBwdChunk) + 2 : 0;
+}
+
 __device__ __forceinline__ void bin_tilescan(const unsigned int* tile_total, int n_tiles, int2* __restrict__ tile_ranges,
                                              int* __restrict__ chunk_offsets, unsigned long long* __restrict__ total_entries,
                                              unsigned long long capacity, unsigned long long overflow_base, int tid) {
@@ -343,7 +349,7 @@ __device__ __forceinline__ void bin_tilescan(const unsigned int* tile_total, int
     for (int base = 0; base < n_tiles; base += 1024) {
         const int t = base + tid;
         const unsigned int len = t < n_tiles ? __ldcg(tile_total + t) : 0u;  // written by other CTAs of this launch
-        const int c = static_cast<int>((len + kBwdChunk - 1) / kBwdChunk);
+        const int c = bwd_records_of(len);
         unsigned long long x = len;
         int xc = c;
 #pragma unroll
@@ -503,12 +509,7 @@ __global__ void __launch_bounds__(kBinThreads)
     __shared__ unsigned char s_hit[kBinThreads / 32][32];  // per warp: rank among the group's hits -> lane
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g_begin = blockIdx.x * chunk_size, g_end = min(g_begin + chunk_size, v.num_gaussians);
-    // the backward work list (one record per backward CTA, see splat_chunk_fill_kernel); surplus records: tile = -1
-    for (int t = blockIdx.x * kBinThreads + tid; t < n_tiles; t += gridDim.x * kBinThreads) {
-        const int2 r = tile_ranges[t];
-        const int first_chunk = chunk_offsets[t], c = chunk_offsets[t + 1] - first_chunk;
-        for (int k = 0; k < c; ++k) chunk_info[first_chunk + k] = make_int4(tile0 + t, r.x + k * kBwdChunk, r.y, 0);
-    }
+    // the backward work records of the tiles are written by the forward pass; the records beyond them: tile = -1
     for (int c = chunk_offsets[n_tiles] + blockIdx.x * kBinThreads + tid; c < chunk_info_size; c += gridDim.x * kBinThreads)
         chunk_info[c] = make_int4(-1, -1, -1, -1);
     if (capacity != 0ull && total_entries[0] > capacity) return;  // XYZ_FLAG_ASYNC overflow: every list is empty
@@ -671,7 +672,7 @@ __global__ void __launch_bounds__(256)
     if (sorted_gid) sorted_gid[i] = entry_to_gaussian(offsets_incl, n, vals_sorted[i]);
 }
 
-// ---- backward work list: exclusive scan over the tiles of ceil(list length / kBwdChunk) -------------------------
+// ---- backward work records (radix path): exclusive scan over the tiles of bwd_records_of(list length) ------------
 __global__ void __launch_bounds__(1024)
     splat_chunk_scan_kernel(const int2* __restrict__ tile_ranges, int n_tiles, int* __restrict__ chunk_offsets) {
     __shared__ int s_warp[32];
@@ -684,7 +685,7 @@ __global__ void __launch_bounds__(1024)
         int c = 0;
         if (t < n_tiles) {
             const int2 r = tile_ranges[t];
-            c = (r.y - r.x + kBwdChunk - 1) / kBwdChunk;
+            c = bwd_records_of(static_cast<unsigned int>(r.y - r.x));
         }
         int x = c;
 #pragma unroll
@@ -712,17 +713,6 @@ __global__ void __launch_bounds__(1024)
         __syncthreads();
     }
     if (tid == 0) chunk_offsets[n_tiles] = s_carry;
-}
-
-// one record per backward CTA: {tile, first entry, end of the tile's list, 0}
-__global__ void __launch_bounds__(256)
-    splat_chunk_fill_kernel(const int2* __restrict__ tile_ranges, int n_tiles, const int* __restrict__ chunk_offsets,
-                            int4* __restrict__ chunk_info) {
-    const int t = blockIdx.x * blockDim.x + threadIdx.x;
-    if (t >= n_tiles) return;
-    const int2 r = tile_ranges[t];
-    const int first = chunk_offsets[t], c = chunk_offsets[t + 1] - first;
-    for (int k = 0; k < c; ++k) chunk_info[first + k] = make_int4(t, r.x + k * kBwdChunk, r.y, 0);
 }
 
 // ---- deterministic mode: per-Gaussian sum of its entries' rows, in entry order ----------------------------
@@ -766,7 +756,7 @@ struct SplatPlan {
     float d2_bwd;            // backward cull (splat_kernels.cuh); infinity = every listed pair
     int chunk_size, n_chunks;
     size_t o_rec, o_frec, o_rect, o_touched, o_spans, o_offsets, o_ranges, o_tloss, o_chunks, o_rest, o_hist, o_ttotal, o_ctotal,
-        o_cbase, o_bcount, o_scan_tmp;
+        o_cbase, o_scan_tmp;
     size_t scan_tmp_bytes;
     size_t fixed_bytes;  // without the header
 };
@@ -837,7 +827,6 @@ int make_plan(SplatPlan& p, int W, int H, int N, int row_begin, int row_end, int
     p.o_ttotal = take(sizeof(unsigned int) * nl);
     p.o_ctotal = take(sizeof(unsigned int) * p.n_chunks);
     p.o_cbase = take(sizeof(unsigned long long) * p.n_chunks);
-    p.o_bcount = take(sizeof(int) * 2 * p.n_tiles);  // lengths of the two backward item lists of every tile
     p.scan_tmp_bytes = 0;
     if (!p.counting)
         cub::DeviceScan::InclusiveSum(nullptr, p.scan_tmp_bytes, TouchedIter(nullptr, ToU64()),
@@ -860,8 +849,8 @@ EntryLayout make_entry_layout(const SplatPlan& p, long long capacity, cudaStream
     L.o_vin = stake(p.counting ? 0 : 4 * ne);
     L.o_vout = stake(4 * ne);
     L.o_gid = stake(p.deterministic ? 4 * ne : 0);
-    L.chunk_info_size = static_cast<int>(capacity / kBwdChunk + p.n_tiles_l);
-    L.o_cinfo = stake(sizeof(int4) * static_cast<size_t>(ne / kBwdChunk + p.n_tiles_l));
+    L.chunk_info_size = static_cast<int>(capacity / kBwdChunk + 3LL * p.n_tiles_l);  // sum of ceil(len / chunk) + 2
+    L.o_cinfo = stake(sizeof(int4) * static_cast<size_t>(ne / kBwdChunk + 3LL * p.n_tiles_l));
     L.o_eg = stake(p.deterministic ? 36 * ne : 0);
     L.o_items = stake(8 * ne);  // the backward work items: up to two per entry
     L.sort_tmp_bytes = 0;
@@ -918,7 +907,6 @@ void bind_fixed(const SplatPlan& p, unsigned char* header, unsigned char* base, 
     o.tile_total = reinterpret_cast<unsigned int*>(base + p.o_ttotal);
     o.chunk_total = reinterpret_cast<unsigned int*>(base + p.o_ctotal);
     o.chunk_base = reinterpret_cast<unsigned long long*>(base + p.o_cbase);
-    o.b.bwd_count = reinterpret_cast<int*>(base + p.o_bcount);
     o.scan_tmp = base + p.o_scan_tmp;
 }
 
@@ -1028,12 +1016,9 @@ int enqueue_back(const SplatPlan& p, const EntryLayout& L, const Bound& o, const
                 entries, b.keys_out, b.vals_out, b.offsets, N, b.tile_ranges, p.deterministic ? b.sorted_gid : nullptr);
             splat_chunk_scan_kernel<<<1, 1024, 0, st>>>(b.tile_ranges, p.n_tiles, b.chunk_offsets);
             count_launch(2);
-            // surplus backward CTAs (the grid is an upper bound) read tile = -1
+            // work records nobody writes (the forward pass fills in those of its tiles) read tile = -1
             ce = cudaMemsetAsync(b.chunk_info, 0xff, sizeof(int4) * static_cast<size_t>(L.chunk_info_size), st);
             if (ce != cudaSuccess) return static_cast<int>(ce);
-            splat_chunk_fill_kernel<<<(p.n_tiles + 255) / 256, 256, 0, st>>>(b.tile_ranges, p.n_tiles, b.chunk_offsets,
-                                                                           b.chunk_info);
-            count_launch();
         }
     } else if (p.counting && N > 0) {
         // no entries: the column scan has published empty ranges for the band already
@@ -1047,8 +1032,8 @@ int enqueue_back(const SplatPlan& p, const EntryLayout& L, const Bound& o, const
     }
     mark(tm, 3, st);
     unsigned int* fwd_ticket = reinterpret_cast<unsigned int*>(o.header + 2) + 1;  // next to the column scan's ticket
-    int err = p.precise ? splat_forward_launch_precise(p.v, b, target, output, total_loss, fwd_ticket, p.deterministic, p.d2_bwd, st)
-                        : splat_forward_launch_fast(p.v, b, target, output, total_loss, fwd_ticket, p.deterministic, p.d2_bwd, st);
+    int err = p.precise ? splat_forward_launch_precise(p.v, b, target, output, total_loss, fwd_ticket, p.deterministic, p.d2_bwd, p.tile0, st)
+                        : splat_forward_launch_fast(p.v, b, target, output, total_loss, fwd_ticket, p.deterministic, p.d2_bwd, p.tile0, st);
     if (err) return err;
     mark(tm, 4, st);
     const long long bwd_ctas = entries > 0 ? static_cast<long long>(L.chunk_info_size) : 0;

@@ -105,8 +105,8 @@ __global__ void __launch_bounds__(kThreads)
                          const int2* __restrict__ tile_ranges, const float* __restrict__ target,
                          float* __restrict__ output, float* __restrict__ tile_loss, float4* __restrict__ rest_tiles,
                          int tile_y0, unsigned int* __restrict__ ticket, float* total_loss, int* __restrict__ bwd_items,
-                         int* __restrict__ bwd_count, float d2_bwd_scaled, const unsigned int* __restrict__ sorted_orig,
-                         float* __restrict__ entry_grads) {
+                         const int* __restrict__ chunk_offsets, int4* __restrict__ chunk_info, int first_tile,
+                         float d2_bwd_scaled, const unsigned int* __restrict__ sorted_orig, float* __restrict__ entry_grads) {
     static_assert(kParts == 1 || (kParts == 2 && kThreads == 64), "half tiles are rendered by 64 threads");
     constexpr int kPixels = kTilePixels / kParts;   // pixels of this CTA
     constexpr int kRows = kPixels / kThreads;       // pixel rows per thread (4, 2, 1)
@@ -114,7 +114,7 @@ __global__ void __launch_bounds__(kThreads)
     constexpr int kPerThread = (kFwdStage + kThreads - 1) / kThreads;  // Gaussians a thread stages per pass
     __shared__ __align__(16) float4 s_a[2][kFwdStage];
     __shared__ __align__(16) float4 s_b[2][kFwdStage];
-    __shared__ int s_items[2];  // lengths of the tile's two lists of backward work items
+    __shared__ int s_items[3];  // lengths of the tile's three lists of backward work items
 
     const int tid = threadIdx.x;
     const int tile_x = blockIdx.x, tile_y = tile_y0 + static_cast<int>(blockIdx.y) / kParts;
@@ -152,12 +152,13 @@ __global__ void __launch_bounds__(kThreads)
         }
         cp_async_commit();
     };
-    // backward work items (see "backward work items" below): which halves of the tile this CTA tests, where they go
-    const bool whole = entry_grads != nullptr;  // deterministic mode: one list of whole-tile items, filled by part 0
+    // backward work items (see "backward work items" below); with two CTAs per tile the upper one lists them
+    const bool lists_items = kParts == 1 || part == 0;
+    const bool whole = entry_grads != nullptr;  // deterministic mode: every item covers the whole tile
     const float tx0 = static_cast<float>(tile_x * kTile), ty0 = static_cast<float>(tile_y * kTile);
     int* const items0 = bwd_items + 2 * static_cast<size_t>(range.x);
     const int list_len = range.y - range.x;
-    if (tid < 2) s_items[tid] = 0;  // (the barriers at the top of the loop / after it order this with every use)
+    if (tid < 3) s_items[tid] = 0;  // (the barriers at the top of the loop / after it order this with every use)
 
     load_ids(range.x);
     int id_cur[kPerThread];  // ids of the stage being rendered
@@ -181,43 +182,45 @@ __global__ void __launch_bounds__(kThreads)
         const float4* __restrict__ sb = s_b[buf];
         // the stage's backward work items: min d2 over each half of the tile against the backward cull's bound, on the
         // staged (kappa-scaled, hence negated) conic
+        if (lists_items) {
 #pragma unroll
-        for (int q = 0; q < kPerThread; ++q) {
-            const int t = tid + q * kThreads;
-            int keep = 0;  // bit h: the item of half h (whole-tile items: bit 0)
-            if (t < n && (kParts == 1 || !whole || part == 0)) {
-                const float4 a = sa[t];
-                const float ia = -a.z, ib = -0.5f * a.w, ic = -sb[t].x;
-                // anything but a positive definite conic of finite numbers is kept (the comparisons fail on NaN)
-                const bool pd = ia > 0.f && ic > 0.f && ia * ic > ib * ib;
-                const float kx = -ib / ia, ky = -ib / ic;
-                const float x0 = tx0 - a.x, x1 = x0 + static_cast<float>(kTile - 1), y0 = ty0 - a.y;
-                const float ym = y0 + static_cast<float>(kTile / 2);
-                if (whole) {
-                    keep = (pd && conic_min_over_rect(ia, ib, ic, kx, ky, x0, x1, y0, y0 + static_cast<float>(kTile - 1)) > d2_bwd_scaled) ? 0 : 1;
-                    if (!keep) {  // the per-Gaussian sum reads every entry's row
-                        float* row = entry_grads + static_cast<size_t>(sorted_orig[base + t]) * 9;
+            for (int q = 0; q < kPerThread; ++q) {
+                const int t = tid + q * kThreads;
+                int keep = 0;  // bit 0: rows 0..7, bit 1: rows 8..15 hold pixels with d2 <= the bound
+                if (t < n) {
+                    const float4 a = sa[t];
+                    const float ia = -a.z, ib = -0.5f * a.w, ic = -sb[t].x;
+                    // anything but a positive definite conic of finite numbers is kept (the comparisons fail on NaN)
+                    const bool pd = ia > 0.f && ic > 0.f && ia * ic > ib * ib;
+                    const float kx = -ib / ia, ky = -ib / ic;
+                    const float x0 = tx0 - a.x, x1 = x0 + static_cast<float>(kTile - 1), y0 = ty0 - a.y;
+                    const float ym = y0 + static_cast<float>(kTile / 2);
+                    keep = ((pd && conic_min_over_rect(ia, ib, ic, kx, ky, x0, x1, y0, ym - 1.0f) > d2_bwd_scaled) ? 0 : 1) |
+                           ((pd && conic_min_over_rect(ia, ib, ic, kx, ky, x0, x1, ym, ym + static_cast<float>(kTile / 2 - 1)) > d2_bwd_scaled) ? 0 : 2);
+                    if (whole) {
+                        if (keep) {
+                            keep = 3;
+                        } else {  // the per-Gaussian sum reads every entry's row
+                            float* row = entry_grads + static_cast<size_t>(sorted_orig[base + t]) * 9;
 #pragma unroll
-                        for (int k = 0; k < 9; ++k) row[k] = 0.f;
+                            for (int k = 0; k < 9; ++k) row[k] = 0.f;
+                        }
                     }
-                } else {
-                    if (kParts == 1 || part == 0)
-                        keep |= (pd && conic_min_over_rect(ia, ib, ic, kx, ky, x0, x1, y0, ym - 1.0f) > d2_bwd_scaled) ? 0 : 1;
-                    if (kParts == 1 || part == 1)
-                        keep |= (pd && conic_min_over_rect(ia, ib, ic, kx, ky, x0, x1, ym, ym + static_cast<float>(kTile / 2 - 1)) > d2_bwd_scaled) ? 0 : 2;
                 }
-            }
-            const int item = whole ? base + t : id_cur[q];
-#pragma unroll
-            for (int h = 0; h < 2; ++h) {
-                if (kParts == 2 && h != part && !(whole && h == 0)) continue;
-                const unsigned int votes = __ballot_sync(0xffffffffu, (keep >> h) & 1);
-                if (votes == 0u) continue;
+                const int item = whole ? base + t : id_cur[q];
                 const int lane = tid & 31;
-                int at = 0;
-                if (lane == 0) at = atomicAdd(&s_items[h], __popc(votes));
-                at = __shfl_sync(0xffffffffu, at, 0) + __popc(votes & ((1u << lane) - 1u));
-                if ((keep >> h) & 1) items0[static_cast<size_t>(h) * list_len + at] = item;
+                // list 0: both halves (grows up from slot 0), list 1: rows 0..7 only (grows down from slot len - 1), list 2:
+                // rows 8..15 only (grows up from slot len); an entry is in at most one list
+#pragma unroll
+                for (int l = 0; l < 3; ++l) {
+                    const bool mine = keep == (l == 0 ? 3 : l);
+                    const unsigned int votes = __ballot_sync(0xffffffffu, mine);
+                    if (votes == 0u) continue;
+                    int at = 0;
+                    if (lane == 0) at = atomicAdd(&s_items[l], __popc(votes));
+                    at = __shfl_sync(0xffffffffu, at, 0) + __popc(votes & ((1u << lane) - 1u));
+                    if (mine) items0[l == 0 ? at : (l == 1 ? list_len - 1 - at : list_len + at)] = item;
+                }
             }
         }
         XYZ_UNROLL(XYZ_FWD_UNROLL)
@@ -265,7 +268,27 @@ __global__ void __launch_bounds__(kThreads)
         s_l[pix] = l;
     }
     __syncthreads();
-    if (tid < 2 && (kParts == 1 || tid == part)) bwd_count[2 * tile + tid] = s_items[tid];  // (the list part 1 leaves empty in deterministic mode: 0)
+    if (lists_items && list_len > 0) {  // (no entries: no records set aside, and with no Gaussians at all no offsets either)
+        // the tile's backward work records: one per kBwdChunk items of a list, in the records the tile scan set aside for
+        // this tile (ceil(len / kBwdChunk) + 2: an entry is in at most one of three lists); the rest of them: none
+        const int lt = tile - first_tile;
+        const int rec0 = chunk_offsets[lt], rec1 = chunk_offsets[lt + 1];
+        const int n0 = s_items[0], n1 = s_items[1], n2 = s_items[2];
+        const int c0 = (n0 + kBwdChunk - 1) / kBwdChunk, c1 = (n1 + kBwdChunk - 1) / kBwdChunk, c2 = (n2 + kBwdChunk - 1) / kBwdChunk;
+        const unsigned int slot0 = 2u * static_cast<unsigned int>(range.x);
+        for (int r = rec0 + tid; r < rec1; r += kThreads) {
+            int k = r - rec0;
+            int4 w = make_int4(-1, -1, -1, -1);
+            if (k < c0) {
+                w = make_int4(tile, static_cast<int>(slot0 + k * kBwdChunk), min(kBwdChunk, n0 - k * kBwdChunk), 0);
+            } else if ((k -= c0) < c1) {
+                w = make_int4(tile, static_cast<int>(slot0 + list_len - 1 - k * kBwdChunk), min(kBwdChunk, n1 - k * kBwdChunk), 1);
+            } else if ((k -= c1) < c2) {
+                w = make_int4(tile, static_cast<int>(slot0 + list_len + k * kBwdChunk), min(kBwdChunk, n2 - k * kBwdChunk), 2);
+            }
+            chunk_info[r] = w;
+        }
+    }
     // loss partial of a half tile: lane i adds its pixels i, i + 32, i + 64, i + 96, then a shuffle tree.  One warp per
     // half this CTA owns (every configuration has at least two warps).
     __shared__ int s_last;
@@ -451,24 +474,24 @@ __device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_r
 // a bit-identical image.  A gradient is an atomically accumulated sum held to 1e-4 of the sum of its terms' magnitudes, and
 // the terms of a pair carry the factor e = exp(-d2 / 2): beyond d2 = d2_bwd (default 64: e < 2^-46) they are far below
 // the fp32 resolution of the sums they would join.  So the backward pass works on ITEMS = (list entry, 16 x 8 half of the
-// tile) and leaves out the items on which min d2 > d2_bwd -- 61 % of the listed pixels at BASELINE's C4.  The forward
+// tile) and leaves out the halves on which min d2 > d2_bwd -- 61 % of the listed pixels at BASELINE's C4.  The forward
 // CTA of a tile has every entry's record in shared memory anyway: it tests the two halves of each entry and appends the
-// survivors to the tile's two item lists
-//     bwd_items[2 begin + h len + j],  j < bwd_count[2 tile + h]      (begin, len: the tile's range in the sorted list)
-// (deterministic mode: ONE list of whole-tile items per tile -- one row of entry_grads per entry; rows of entries that
-// are left out are zeroed here).  An item is the Gaussian id (deterministic mode: the entry's index, which leads to the
-// id and to the row).  The order of a list depends on warp timing and never enters a result.
-// XYZ_FLAG_BWD_ALL_PAIRS / XYZ_FLAG_NO_CULL pass d2_bwd = inf: every entry yields both items.
+// entry to one of three lists in the tile's 2 len slots of bwd_items (begin, len: the tile's range in the sorted list):
+// both halves / rows 0..7 only / rows 8..15 only (deterministic mode: whole-tile items for every entry with a surviving
+// half -- one row of entry_grads per entry; rows of entries that are left out are zeroed here).  An item is the Gaussian
+// id (deterministic mode: the entry's index, which leads to the id and to the row).  The order of a list depends on warp
+// timing and never enters a result.  XYZ_FLAG_BWD_ALL_PAIRS / XYZ_FLAG_NO_CULL pass d2_bwd = inf: every entry is a
+// whole-tile item.
 //
-// One backward CTA = up to kBwdChunk (= threads) consecutive items of one half of one tile; the grid is the raw work list
-// chunk_info[c] = {tile, first entry, end of the tile's list, -} (one record per kBwdChunk raw entries, surplus records
-// hold tile = -1) x the two halves: CTA (c, h) takes the items [k kBwdChunk, (k + 1) kBwdChunk) of list h, k = c's
-// position inside its tile, and exits when the list is shorter -- an upper bound of the CTAs needed that the host knows
-// without reading anything back.
+// The forward CTA also writes the tile's work records, one per backward CTA:
+//     chunk_info[c] = {tile, slot of the CTA's first item, items (1 .. kBwdChunk), list}     (tile = -1: nothing to do)
+// list 0: both halves hold pixels inside the bound (the thread walks 16 rows; slots ascending), 1: rows 0..7 only (slots
+// DEscending), 2: rows 8..15 only.  The tile scan sets aside ceil(len / kBwdChunk) + 2 records per tile with a non-empty
+// list, so the grid (all records) is an upper bound the host knows without reading anything back; at C4 about half
+// of the CTAs find tile = -1 and leave at once.
 __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
     splat_backward_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ chunk_info,
-                          const int2* __restrict__ tile_ranges, const int* __restrict__ bwd_items,
-                          const int* __restrict__ bwd_count, const float4* __restrict__ rest_tiles,
+                          const int* __restrict__ bwd_items, const float4* __restrict__ rest_tiles,
                           const int* __restrict__ sorted_gid, const unsigned int* __restrict__ sorted_orig,
                           xyz_gaussian_grads* grads, float* __restrict__ entry_grads) {
     __shared__ RestPair s_rest[kTilePixels / 2];  // -(tgt - out) and the active mask, pixel pairs (see RestPair)
@@ -477,15 +500,12 @@ __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
     const int4 info = __ldg(chunk_info + blockIdx.x);
     const int tile = info.x;
     if (tile < 0) return;
-    const bool whole = entry_grads != nullptr;  // deterministic mode: whole-tile items, one list
-    const int half = blockIdx.y;
-    const int2 range = __ldg(tile_ranges + tile);
-    const int first = info.y - range.x;  // this CTA's first item inside list `half`
-    const int count = __ldg(bwd_count + 2 * tile + half);
-    if (first >= count) return;
-    const bool valid = first + tid < count;
+    const bool valid = tid < info.z;
+    const unsigned int slot = static_cast<unsigned int>(info.y) + (info.w == 1 ? -tid : tid);
+    const int item = valid ? __ldg(bwd_items + slot) : 0;
+    const bool whole = entry_grads != nullptr;  // deterministic mode: the item is the entry's index
     const int tile_x = tile % v.tiles_x, tile_y = tile / v.tiles_x;
-    const int row0 = half * (kTile / 2), nrows = whole ? kTile : kTile / 2;
+    const int row0 = info.w == 2 ? kTile / 2 : 0, nrows = info.w == 0 ? kTile : kTile / 2;
     for (int p = row0 * kTile + tid; p < (row0 + nrows) * kTile; p += kBwdChunk) {
         const float4 rest = __ldg(rest_tiles + static_cast<size_t>(tile) * kTilePixels + p);
         float* pair = reinterpret_cast<float*>(&s_rest[p >> 1]) + (p & 1);
@@ -498,10 +518,9 @@ __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
                             (tile_y * kTile + kTile <= v.row_end);
 
     float cx = 0.f, cy = 0.f, ia = 0.f, ib = 0.f, ic = 0.f, so = 0.f, c0 = 0.f, c1 = 0.f, c2 = 0.f;
-    int g = 0, item = 0;
+    int g = 0;
     float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
-        item = __ldg(bwd_items + 2 * static_cast<size_t>(range.x) + static_cast<size_t>(half) * (range.y - range.x) + first + tid);
         g = whole ? sorted_gid[item] : item;
         const float4 r0 = __ldg(records + 4 * g), r1 = __ldg(records + 4 * g + 1);
         r2 = __ldg(records + 4 * g + 2);
@@ -582,7 +601,7 @@ __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
 
 int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const SplatBuffers& b, const float* target,
                                                      float* output, float* total_loss, unsigned int* ticket, bool deterministic,
-                                                     float d2_bwd, cudaStream_t st) {
+                                                     float d2_bwd, int first_tile, cudaStream_t st) {
     const int ty0 = v.row_begin / kTile, ty1 = (v.row_end + kTile - 1) / kTile;
     if (ty1 <= ty0) return 0;
     // configuration by how many tiles an SM gets (see the kernel); XYZ_SPLAT_FWD_THREADS = 64 | 128 | 256 (threads of a
@@ -600,7 +619,7 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
     const dim3 grid(v.tiles_x, (ty1 - ty0) * (cfg == 32 ? 2 : 1));
     const float d2s = -kKappa * d2_bwd;  // on the staged conic (scaled by kappa < 0); inf stays inf
 #define XYZ_FWD_ARGS v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output, b.tile_loss, b.rest_tiles, ty0, ticket, total_loss, \
-                     b.bwd_items, b.bwd_count, d2s, b.vals_out, deterministic ? b.entry_grads : nullptr
+                     b.bwd_items, b.chunk_offsets, b.chunk_info, first_tile, d2s, b.vals_out, deterministic ? b.entry_grads : nullptr
     if (cfg == 32) splat_forward_kernel<64, 2><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
     else if (cfg == 64) splat_forward_kernel<64, 1><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
     else if (cfg == 128) splat_forward_kernel<128, 1><<<grid, 128, 0, st>>>(XYZ_FWD_ARGS);
@@ -613,8 +632,8 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
 int XYZ_CAT(splat_backward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const SplatBuffers& b, xyz_gaussian_grads* grads,
                                                       long long bwd_ctas, bool deterministic, cudaStream_t st) {
     if (bwd_ctas <= 0) return 0;
-    splat_backward_kernel<<<dim3(static_cast<unsigned int>(bwd_ctas), deterministic ? 1 : 2), kBwdChunk, 0, st>>>(
-        v, b.records, b.chunk_info, b.tile_ranges, b.bwd_items, b.bwd_count, b.rest_tiles, b.sorted_gid, b.vals_out, grads,
+    splat_backward_kernel<<<static_cast<unsigned int>(bwd_ctas), kBwdChunk, 0, st>>>(
+        v, b.records, b.chunk_info, b.bwd_items, b.rest_tiles, b.sorted_gid, b.vals_out, grads,
         deterministic ? b.entry_grads : nullptr);
     count_launch();
     return last_error();
