@@ -24,7 +24,10 @@ namespace xyzb {
 
 constexpr int kTile = 16;                 // TILE_SIZE, gaussian_splatting_kernel.cuh:21
 constexpr int kTilePixels = kTile * kTile;
-constexpr int kBwdChunk = 128;             // work items (= threads) per backward CTA; chunks never straddle tiles
+#ifndef XYZ_BWD_CHUNK
+#define XYZ_BWD_CHUNK 128
+#endif
+constexpr int kBwdChunk = XYZ_BWD_CHUNK;   // work items (= threads) per backward CTA; chunks never straddle tiles
 constexpr int kSpanRows = 16;              // tile-row spans kept per Gaussian between preprocess and key emission
 constexpr int kRecFloats = 16;            // {cx, cy, ia, ib | ic, sigmoid(opacity), r, g | b, exp(s0), exp(s1), cos | sin, 0, 0, 0}
 
@@ -68,6 +71,7 @@ struct SplatBuffers {  // device scratch of one launch (library-owned)
     float4* rest_tiles;       // tiles x 256: (target - output, active) per pixel, tile-major, written by the forward pass
     float* tile_loss;         // 2 x tiles: one partial per half tile (rows 0..7, rows 8..15)
     float* entry_grads;       // deterministic mode: entries x 9 (indexed by ORIGINAL entry index)
+    int* tile_order;          // tiles of the launch: band-local tile ids, longest list first (launch order of the forward CTAs)
     int* bwd_items;           // 2 x entries: the backward work items, written by the forward pass into the 2 len slots
                               // of every tile (three lists, see splat_kernels.cuh)
 };
@@ -77,12 +81,13 @@ struct SplatBuffers {  // device scratch of one launch (library-owned)
 // ticket: one unsigned int that is zero before the launch (the last CTA resets it): the forward pass itself adds the
 // per-tile loss partials, in tile order, to *total_loss
 // d2_bwd: the backward cull's bound on d2 (infinity: every listed pair becomes a backward work item);
-// first_tile: the tile chunk_offsets[0] belongs to (the first tile of the row band; 0 on the radix path)
+// first_tile: the tile chunk_offsets[0] belongs to (the first tile of the row band; 0 on the radix path);
+// tile_order: launch order of the tiles of the band (ids relative to first_tile), or nullptr = row-major
 int splat_forward_launch_fast(const SplatView&, const SplatBuffers&, const float* target, float* output, float* total_loss,
-                              unsigned int* ticket, bool deterministic, float d2_bwd, int first_tile, cudaStream_t);
+                              unsigned int* ticket, bool deterministic, float d2_bwd, int first_tile, const int* tile_order, cudaStream_t);
 int splat_forward_launch_precise(const SplatView&, const SplatBuffers&, const float* target, float* output,
                                  float* total_loss, unsigned int* ticket, bool deterministic, float d2_bwd, int first_tile,
-                                 cudaStream_t);
+                                 const int* tile_order, cudaStream_t);
 // bwd_ctas = size of the backward work list (an upper bound of the CTAs needed; surplus records hold tile = -1)
 int splat_backward_launch_fast(const SplatView&, const SplatBuffers&, xyz_gaussian_grads* grads, long long bwd_ctas,
                                bool deterministic, cudaStream_t);

@@ -335,7 +335,8 @@ __host__ __device__ __forceinline__ int bwd_records_of(unsigned int len) {
 
 __device__ __forceinline__ void bin_tilescan(const unsigned int* tile_total, int n_tiles, int2* __restrict__ tile_ranges,
                                              int* __restrict__ chunk_offsets, unsigned long long* __restrict__ total_entries,
-                                             unsigned long long capacity, unsigned long long overflow_base, int tid) {
+                                             unsigned long long capacity, unsigned long long overflow_base, int tid,
+                                             int* __restrict__ tile_order) {
     __shared__ unsigned long long s_warp[32];
     __shared__ int s_warp_c[32];
     __shared__ unsigned long long s_carry;
@@ -397,6 +398,49 @@ __device__ __forceinline__ void bin_tilescan(const unsigned int* tile_total, int
         }
         __syncthreads();
     }
+    // Launch order of the forward CTAs: longest lists first (a counting sort into 1024 length classes), so that the
+    // hardware's in-order CTA dispatch is longest-processing-time-first list scheduling and the kernel does not end with
+    // a few SMs finishing the heaviest tiles.  Ties inside a class fall in arrival order; no result depends on the order.
+    if (tile_order) {
+        __shared__ unsigned int s_class[1024];
+        __shared__ unsigned int s_cw[32];
+        __shared__ unsigned int s_longest;
+        s_class[tid] = 0u;
+        if (tid == 0) s_longest = 0u;
+        __syncthreads();
+        unsigned int longest = 0u;
+        for (int t = tid; t < n_tiles; t += 1024) longest = max(longest, __ldcg(tile_total + t));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) longest = max(longest, __shfl_xor_sync(0xffffffffu, longest, o));
+        if (lane == 0) atomicMax(&s_longest, longest);
+        __syncthreads();
+        const float scale = s_longest ? 1023.0f / static_cast<float>(s_longest) : 0.0f;
+        auto class_of = [&](unsigned int len) { return 1023u - min(1023u, static_cast<unsigned int>(static_cast<float>(len) * scale)); };
+        for (int t = tid; t < n_tiles; t += 1024) atomicAdd(&s_class[class_of(__ldcg(tile_total + t))], 1u);
+        __syncthreads();
+        const unsigned int mine = s_class[tid];
+        unsigned int x = mine;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const unsigned int y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_cw[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            unsigned int w = s_cw[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const unsigned int y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            s_cw[lane] = w;
+        }
+        __syncthreads();
+        s_class[tid] = (warp > 0 ? s_cw[warp - 1] : 0u) + (x - mine);  // first position of the class
+        __syncthreads();
+        for (int t = tid; t < n_tiles; t += 1024) tile_order[atomicAdd(&s_class[class_of(__ldcg(tile_total + t))], 1u)] = t;
+    }
     const bool overflow = capacity != 0ull && s_carry > capacity;  // s_carry: settled by the loop's last barrier
     if (overflow) {
         for (int t = tid; t < n_tiles; t += 1024) {
@@ -422,7 +466,7 @@ __global__ void __launch_bounds__(1024)
                              unsigned int* ticket, int2* __restrict__ tile_ranges, int* __restrict__ chunk_offsets,
                              unsigned long long* __restrict__ total_entries, unsigned long long capacity,
                              unsigned long long overflow_base, const unsigned int* chunk_total,
-                             unsigned long long* __restrict__ chunk_base) {
+                             unsigned long long* __restrict__ chunk_base, int* __restrict__ tile_order) {
     __shared__ unsigned int s_part[32][33];
     __shared__ bool s_last;
     const int tx = threadIdx.x, gy = threadIdx.y;
@@ -483,7 +527,7 @@ __global__ void __launch_bounds__(1024)
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    bin_tilescan(tile_total, n_tiles, tile_ranges, chunk_offsets, total_entries, capacity, overflow_base, tid);
+    bin_tilescan(tile_total, n_tiles, tile_ranges, chunk_offsets, total_entries, capacity, overflow_base, tid, tile_order);
     // deterministic mode: list entries before every chunk, in Gaussian order (the scatter kernel turns them into
     // per-Gaussian positions) -- what used to be a library scan over all Gaussians
     if (chunk_base) cta_exclusive_scan_u32_to_u64(chunk_total, n_chunks, chunk_base, tid);
@@ -756,7 +800,7 @@ struct SplatPlan {
     float d2_bwd;            // backward cull (splat_kernels.cuh); infinity = every listed pair
     int chunk_size, n_chunks;
     size_t o_rec, o_frec, o_rect, o_touched, o_spans, o_offsets, o_ranges, o_tloss, o_chunks, o_rest, o_hist, o_ttotal, o_ctotal,
-        o_cbase, o_scan_tmp;
+        o_cbase, o_order, o_scan_tmp;
     size_t scan_tmp_bytes;
     size_t fixed_bytes;  // without the header
 };
@@ -827,6 +871,7 @@ int make_plan(SplatPlan& p, int W, int H, int N, int row_begin, int row_end, int
     p.o_ttotal = take(sizeof(unsigned int) * nl);
     p.o_ctotal = take(sizeof(unsigned int) * p.n_chunks);
     p.o_cbase = take(sizeof(unsigned long long) * p.n_chunks);
+    p.o_order = take(sizeof(int) * nl);  // launch order of the forward CTAs (counting path)
     p.scan_tmp_bytes = 0;
     if (!p.counting)
         cub::DeviceScan::InclusiveSum(nullptr, p.scan_tmp_bytes, TouchedIter(nullptr, ToU64()),
@@ -907,6 +952,7 @@ void bind_fixed(const SplatPlan& p, unsigned char* header, unsigned char* base, 
     o.tile_total = reinterpret_cast<unsigned int*>(base + p.o_ttotal);
     o.chunk_total = reinterpret_cast<unsigned int*>(base + p.o_ctotal);
     o.chunk_base = reinterpret_cast<unsigned long long*>(base + p.o_cbase);
+    o.b.tile_order = reinterpret_cast<int*>(base + p.o_order);
     o.scan_tmp = base + p.o_scan_tmp;
 }
 
@@ -959,7 +1005,7 @@ int enqueue_front(const SplatPlan& p, const Bound& o, const xyz_gaussian_params*
         splat_bin_colscan_kernel<<<(p.n_tiles_l + 31) / 32, dim3(32, 32), 0, st>>>(
             o.hist, p.n_chunks, p.n_tiles_l, o.tile_total, reinterpret_cast<unsigned int*>(o.header + 2),
             o.b.tile_ranges + p.tile0, o.b.chunk_offsets, o.header, capacity, overflow_base, o.chunk_total,
-            p.deterministic ? o.chunk_base : nullptr);
+            p.deterministic ? o.chunk_base : nullptr, o.b.tile_order);
         count_launch();
         mark(tm, 2, st);
         return last_error();
@@ -1032,8 +1078,10 @@ int enqueue_back(const SplatPlan& p, const EntryLayout& L, const Bound& o, const
     }
     mark(tm, 3, st);
     unsigned int* fwd_ticket = reinterpret_cast<unsigned int*>(o.header + 2) + 1;  // next to the column scan's ticket
-    int err = p.precise ? splat_forward_launch_precise(p.v, b, target, output, total_loss, fwd_ticket, p.deterministic, p.d2_bwd, p.tile0, st)
-                        : splat_forward_launch_fast(p.v, b, target, output, total_loss, fwd_ticket, p.deterministic, p.d2_bwd, p.tile0, st);
+    // (the launch order comes out of the counting path's tile scan, which only runs when there are Gaussians)
+    const int* order = (p.counting && N > 0) ? b.tile_order : nullptr;
+    int err = p.precise ? splat_forward_launch_precise(p.v, b, target, output, total_loss, fwd_ticket, p.deterministic, p.d2_bwd, p.tile0, order, st)
+                        : splat_forward_launch_fast(p.v, b, target, output, total_loss, fwd_ticket, p.deterministic, p.d2_bwd, p.tile0, order, st);
     if (err) return err;
     mark(tm, 4, st);
     const long long bwd_ctas = entries > 0 ? static_cast<long long>(L.chunk_info_size) : 0;

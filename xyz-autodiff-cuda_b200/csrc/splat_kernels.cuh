@@ -106,7 +106,8 @@ __global__ void __launch_bounds__(kThreads)
                          float* __restrict__ output, float* __restrict__ tile_loss, float4* __restrict__ rest_tiles,
                          int tile_y0, unsigned int* __restrict__ ticket, float* total_loss, int* __restrict__ bwd_items,
                          const int* __restrict__ chunk_offsets, int4* __restrict__ chunk_info, int first_tile,
-                         float d2_bwd_scaled, const unsigned int* __restrict__ sorted_orig, float* __restrict__ entry_grads) {
+                         float d2_bwd_scaled, const unsigned int* __restrict__ sorted_orig, float* __restrict__ entry_grads,
+                         const int* __restrict__ tile_order) {
     static_assert(kParts == 1 || (kParts == 2 && kThreads == 64), "half tiles are rendered by 64 threads");
     constexpr int kPixels = kTilePixels / kParts;   // pixels of this CTA
     constexpr int kRows = kPixels / kThreads;       // pixel rows per thread (4, 2, 1)
@@ -117,8 +118,11 @@ __global__ void __launch_bounds__(kThreads)
     __shared__ int s_items[3];  // lengths of the tile's three lists of backward work items
 
     const int tid = threadIdx.x;
-    const int tile_x = blockIdx.x, tile_y = tile_y0 + static_cast<int>(blockIdx.y) / kParts;
-    const int part = static_cast<int>(blockIdx.y) % kParts;  // 0: rows 0..7 (or the whole tile), 1: rows 8..15
+    // grid: (tiles of the band) x kParts CTAs, a tile's parts next to each other; tile_order = the tiles by falling list length
+    const int slot = static_cast<int>(blockIdx.x) / kParts;
+    const int band_tile = tile_order ? __ldg(tile_order + slot) : slot;
+    const int tile_x = band_tile % v.tiles_x, tile_y = tile_y0 + band_tile / v.tiles_x;
+    const int part = static_cast<int>(blockIdx.x) % kParts;  // 0: rows 0..7 (or the whole tile), 1: rows 8..15
     const int tile = tile_y * v.tiles_x + tile_x;
     const int pxi = tile_x * kTile + (tid & (kTile - 1));
     const int row0 = part * (kTile / kParts) + (tid >> 4);  // this thread's rows inside the tile: row0 + kRowStep k
@@ -294,8 +298,8 @@ __global__ void __launch_bounds__(kThreads)
     __shared__ int s_last;
     {
         const int warp = tid >> 5, lane = tid & 31;
-        if (warp < 2 / kParts) {
-            const int half = kParts == 2 ? part : warp;
+        for (int w = warp; w < 2 / kParts; w += kThreads / 32) {
+            const int half = kParts == 2 ? part : w;
             float l = 0.f;
 #pragma unroll
             for (int j = 0; j < kHalfPixels / 32; ++j) l += s_l[half * kHalfPixels + lane + 32 * j];
@@ -308,17 +312,17 @@ __global__ void __launch_bounds__(kThreads)
         // the last CTA of the launch adds the partials to the caller's loss (in half-tile order: no float atomics, the
         // reference's 3 atomicAdds per pixel on one address become one add per launch)
         __threadfence();
-        s_last = atomicAdd(ticket, 1u) == gridDim.x * gridDim.y - 1;
+        s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // threads 0..63 add the launch's half tiles h, h + 64, ... ; then a fixed tree
-    const int h_begin = 2 * tile_y0 * v.tiles_x, h_end = h_begin + 2 * static_cast<int>(gridDim.x * gridDim.y) / kParts;
-    if (tid < 64) {
+    // 64 partial sums over the launch's half tiles h, h + 64, ... ; then a fixed tree
+    const int h_begin = 2 * tile_y0 * v.tiles_x, h_end = h_begin + 2 * static_cast<int>(gridDim.x) / kParts;
+    for (int t = tid; t < 64; t += kThreads) {
         float acc = 0.f;
-        for (int h = h_begin + tid; h < h_end; h += 64) acc += __ldcg(tile_loss + h);
-        s_l[tid] = acc;
+        for (int h = h_begin + t; h < h_end; h += 64) acc += __ldcg(tile_loss + h);
+        s_l[t] = acc;
     }
     __syncthreads();
     if (tid < 32) {
@@ -601,7 +605,7 @@ __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
 
 int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const SplatBuffers& b, const float* target,
                                                      float* output, float* total_loss, unsigned int* ticket, bool deterministic,
-                                                     float d2_bwd, int first_tile, cudaStream_t st) {
+                                                     float d2_bwd, int first_tile, const int* tile_order, cudaStream_t st) {
     const int ty0 = v.row_begin / kTile, ty1 = (v.row_end + kTile - 1) / kTile;
     if (ty1 <= ty0) return 0;
     // configuration by how many tiles an SM gets (see the kernel); XYZ_SPLAT_FWD_THREADS = 64 | 128 | 256 (threads of a
@@ -611,16 +615,18 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
     static const int forced = [] {
         const char* e = std::getenv("XYZ_SPLAT_FWD_THREADS");
         const int x = e ? std::atoi(e) : 0;
-        return (x == 32 || x == 64 || x == 128 || x == 256) ? x : 0;
+        return (x == 8 || x == 32 || x == 64 || x == 128 || x == 256) ? x : 0;
     }();
     const long long tiles = static_cast<long long>(v.tiles_x) * (ty1 - ty0);
     const int sms = sm_count();
     const int cfg = forced ? forced : (tiles >= 12LL * sms ? 64 : 32);
-    const dim3 grid(v.tiles_x, (ty1 - ty0) * (cfg == 32 ? 2 : 1));
+    const unsigned int grid = static_cast<unsigned int>(tiles) * (cfg == 32 ? 2u : 1u);
     const float d2s = -kKappa * d2_bwd;  // on the staged conic (scaled by kappa < 0); inf stays inf
 #define XYZ_FWD_ARGS v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output, b.tile_loss, b.rest_tiles, ty0, ticket, total_loss, \
-                     b.bwd_items, b.chunk_offsets, b.chunk_info, first_tile, d2s, b.vals_out, deterministic ? b.entry_grads : nullptr
-    if (cfg == 32) splat_forward_kernel<64, 2><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
+                     b.bwd_items, b.chunk_offsets, b.chunk_info, first_tile, d2s, b.vals_out, deterministic ? b.entry_grads : nullptr, \
+                     tile_order
+    if (cfg == 8) splat_forward_kernel<32, 1><<<grid, 32, 0, st>>>(XYZ_FWD_ARGS);  // one warp per tile, 8 pixels per thread
+    else if (cfg == 32) splat_forward_kernel<64, 2><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
     else if (cfg == 64) splat_forward_kernel<64, 1><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
     else if (cfg == 128) splat_forward_kernel<128, 1><<<grid, 128, 0, st>>>(XYZ_FWD_ARGS);
     else splat_forward_kernel<256, 1><<<grid, 256, 0, st>>>(XYZ_FWD_ARGS);
