@@ -522,6 +522,8 @@ def splat_section(T, args, rank, world, comm, group, gather, sm_mhz):
 
     ms_c4 = T.loop(c4_iter, steps)
     stats = x.splat_last_stats()
+    bstats = x.splat_last_backward_stats()
+    ms_c4_all = T.loop(lambda i: c4_iter(i, x.FLAG_BWD_ALL_PAIRS), steps)  # backward over every listed pair (r01 / r02 behaviour)
     stage = {k: 0.0 for k in ("preprocess_hist_us", "scans_us", "scatter_us", "forward_loss_us", "backward_us", "total_us")}
     for i in range(5):
         c4_iter(i, x.FLAG_TIMING)
@@ -537,15 +539,19 @@ def splat_section(T, args, rank, world, comm, group, gather, sm_mhz):
     cfg["c4"] = {"workload": "100000 Gaussians, 1024x1024 (BASELINE configs[3]), fast-math flavour, result-preserving cull",
                  "ms_per_iter": ms_c4, "iteration": "zero_grad + loss reset + launch (fwd + bwd)",
                  "tile_list_entries": stats["entries"], "pairs_per_pass": pairs,
-                 "pair_evals_per_s": 2 * pairs / (ms_c4 / 1e3), "reference_pairs_per_pass": N * W * H,
+                 "backward_pairs_per_pass": bstats["pairs"], "backward_work_items": bstats["items"],
+                 "backward_cull": "half tiles of an entry with d2 > 64 everywhere (weights < 2^-46) are left out of the "
+                                  "gradient sums; image and loss untouched; XYZ_FLAG_BWD_ALL_PAIRS turns it off",
+                 "ms_per_iter_backward_all_pairs": ms_c4_all,
+                 "pair_evals_per_s": (pairs + bstats["pairs"]) / (ms_c4 / 1e3), "reference_pairs_per_pass": N * W * H,
                  "stage_us": stage,
                  "ms_per_training_iter_one_cuda_graph": ms_graph,
                  "graph": "loss reset + workspace launch + Adam with fused zero-grad, captured once, replayed"}
     clk = sm_mhz * 1e6
     fwd_floor = pairs / (MUFU_PER_SM * SM_COUNT * clk) * 1e3
-    bwd_floor = pairs * BWD_FMA_OPS_PER_PAIR / (FMA_LANES_PER_SM * SM_COUNT * clk) * 1e3
-    roof = {"bound": "forward: MUFU pipe (one ex2 per pair); backward: FP32 FMA pipe (13 lane operations per pair)",
-            "sm_mhz": sm_mhz, "pairs_per_pass": pairs,
+    bwd_floor = bstats["pairs"] * BWD_FMA_OPS_PER_PAIR / (FMA_LANES_PER_SM * SM_COUNT * clk) * 1e3
+    roof = {"bound": "forward: MUFU pipe (one ex2 per pair); backward: FP32 FMA pipe (13 lane operations per pair it evaluates)",
+            "sm_mhz": sm_mhz, "pairs_per_pass": pairs, "backward_pairs_per_pass": bstats["pairs"],
             "forward": {"floor_ms": fwd_floor, "ms": stage["forward_loss_us"] / 1e3, "frac": fwd_floor / (stage["forward_loss_us"] / 1e3)},
             "backward": {"floor_ms": bwd_floor, "ms": stage["backward_us"] / 1e3, "frac": bwd_floor / (stage["backward_us"] / 1e3)},
             "iteration": {"floor_ms": fwd_floor + bwd_floor, "ms": ms_c4, "frac": (fwd_floor + bwd_floor) / ms_c4},

@@ -301,6 +301,10 @@ XYZ_API int xyz_splat_workspace_status(const void* workspace, void* stream, long
  * list, stats[3] = pixel-Gaussian pairs evaluated per pass.  XYZ_ERR_NOT_INITIALISED if there is none or its scratch has
  * been reallocated or freed since; XYZ_ERR_WORKSPACE if it overflowed. */
 XYZ_API int xyz_splat_last_stats(long long stats_host[4]);
+/* What the backward pass of that launch worked on (waits for the launch and reads its work records back):
+ * stats[0] = work items ((entry, half tile) or (entry, whole tile), see XYZ_FLAG_BWD_ALL_PAIRS), stats[1] = pixel-Gaussian
+ * pairs it evaluated, stats[2] = backward CTAs with work.  Same error codes as xyz_splat_last_stats. */
+XYZ_API int xyz_splat_last_backward_stats(long long stats_host[3]);
 /* Stage times of this host thread's most recent splat launch made with XYZ_FLAG_TIMING, in microseconds (waits for that
  * launch): {per-Gaussian records + tile histograms, column / tile scans, list scatter, forward + loss, backward, total}. */
 XYZ_API int xyz_splat_last_timing(float stage_us_host[6]);

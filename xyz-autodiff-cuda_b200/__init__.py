@@ -45,6 +45,7 @@ EXPORTS = [
     "xyz_accumulate_f32", "xyz_accumulate_f64", "xyz_covproj_fwd_bwd_f32", "xyz_covproj_shared_w_fwd_bwd_f32",
     "xyz_covproj_shared_w_fwd_bwd_f32_allreduce",
     "xyz_launch_gaussian_splatting", "xyz_launch_gaussian_splatting_rows", "xyz_splat_last_stats",
+    "xyz_splat_last_backward_stats",
     "xyz_splat_debug_binning", "xyz_zero_gradients", "xyz_adam_step_individual", "xyz_adam_step",
     "xyz_adam_step_individual_zero_grads",
     "xyz_splat_workspace_bytes", "xyz_splat_workspace_init", "xyz_launch_gaussian_splatting_ws", "xyz_splat_workspace_status",
@@ -105,6 +106,7 @@ def lib() -> ctypes.CDLL:
         L.xyz_launch_gaussian_splatting.argtypes = [_vp] * 5 + [_i, _i, _i, _vp, _i]
         L.xyz_launch_gaussian_splatting_rows.argtypes = [_vp] * 5 + [_i, _i, _i, _i, _i, _vp, _i]
         L.xyz_splat_last_stats.argtypes = [_vp]
+        L.xyz_splat_last_backward_stats.argtypes = [_vp]
         L.xyz_splat_debug_binning.argtypes = [_vp, _vp, _vp, _vp]
         L.xyz_zero_gradients.argtypes = [_vp, _i, _vp]
         L.xyz_adam_step_individual.argtypes = [_vp, _vp, _vp, _i, _vp, ctypes.c_float, ctypes.c_float,
@@ -401,6 +403,13 @@ def splat_last_stats() -> dict:
     buf = (ctypes.c_longlong * 4)()
     _check(lib().xyz_splat_last_stats(buf), "xyz_splat_last_stats")
     return {"entries": buf[0], "tiles": buf[1], "longest_tile_list": buf[2], "pairs_per_pass": buf[3]}
+
+
+def splat_last_backward_stats() -> dict:
+    """What the backward pass of this thread's most recent launch worked on (reads its work records back)."""
+    buf = (ctypes.c_longlong * 3)()
+    _check(lib().xyz_splat_last_backward_stats(buf), "xyz_splat_last_backward_stats")
+    return {"items": buf[0], "pairs": buf[1], "ctas": buf[2]}
 
 
 def splat_last_timing() -> dict:

@@ -1107,6 +1107,7 @@ struct SplatState {
     long long capacity = 0;      // sync-free launches: the length the entry part was sized for
     const unsigned long long* header = nullptr;
     long long stats[4] = {0, 0, 0, 0};
+    int work_records = 0;        // size of buf.chunk_info (the backward grid)
     uint64_t gen_fixed = 0, gen_entry = 0;
     cudaStream_t stream = nullptr;
     // XYZ_FLAG_ASYNC: pinned-host mirror of {list length, overflow counter}, refreshed by every launch without a
@@ -1243,6 +1244,7 @@ int splat_launch(const xyz_gaussian_params* gaussians, xyz_gaussian_grads* gradi
     S.gen_fixed = gen_fixed;
     S.gen_entry = gen_entry;
     remember(S, p, o, async ? -1 : entries, async ? known_before : entries, async ? capacity : 0);
+    S.work_records = entries > 0 ? L.chunk_info_size : 0;
     g_last = &S;
     return last_error();
 }
@@ -1359,6 +1361,7 @@ extern "C" int xyz_launch_gaussian_splatting_ws(const xyz_gaussian_params* gauss
     S.external = true;
     S.stream = st;
     remember(S, p, o, num_gaussians > 0 ? -1 : 0, 0, static_cast<long long>(capacity));
+    S.work_records = num_gaussians > 0 ? L.chunk_info_size : 0;
     cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(st, &cap);
     S.overflows_seen = ~0ull;  // unknown: xyz_splat_last_stats compares with the header's own previous value instead
@@ -1407,6 +1410,28 @@ extern "C" int xyz_splat_last_stats(long long stats_host[4]) {
         S.stats[2] = mx;
     }
     for (int i = 0; i < 4; ++i) stats_host[i] = S.stats[i];
+    return 0;
+}
+
+extern "C" int xyz_splat_last_backward_stats(long long stats_host[3]) {
+    using namespace xyzb;
+    if (!stats_host) return XYZ_ERR_INVALID_ARGUMENT;
+    long long st4[4];
+    if (int err = xyz_splat_last_stats(st4)) return err;  // (also: the launch did not overflow)
+    SplatState& S = *g_last;
+    cudaError_t e = cudaStreamSynchronize(S.stream);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    stats_host[0] = stats_host[1] = stats_host[2] = 0;
+    if (S.work_records <= 0 || st4[0] <= 0) return 0;
+    std::vector<int4> rec(static_cast<size_t>(S.work_records));
+    e = cudaMemcpy(rec.data(), S.buf.chunk_info, sizeof(int4) * rec.size(), cudaMemcpyDeviceToHost);
+    if (e != cudaSuccess) return static_cast<int>(e);
+    for (const int4& r : rec) {
+        if (r.x < 0) continue;
+        stats_host[0] += r.z;
+        stats_host[1] += static_cast<long long>(r.z) * (r.w == 0 ? kTilePixels : kTilePixels / 2);
+        stats_host[2] += 1;
+    }
     return 0;
 }
 
