@@ -24,6 +24,16 @@ namespace xyzb {
 
 constexpr int kTile = 16;                 // TILE_SIZE, gaussian_splatting_kernel.cuh:21
 constexpr int kTilePixels = kTile * kTile;
+// Forward staging record: 2 float4 {cx, cy, kappa ia, 2 kappa ib} {kappa ic, so r, so g, so b}, or -- XYZ_FWD_PACKED, the
+// colour sums of two pixels run on packed fp32 (FFMA2) -- 3 float4 with every colour twice, so that a 64-bit half of an
+// LDS.128 is a packed operand: {cx, cy, kappa ia, 2 kappa ib} {kappa ic, 0, so r, so r} {so g, so g, so b, so b}.
+// Measured (C4, same box): 136 instead of 148 issue slots per 16 pairs and the same bits, but 391 us against 387 -- the
+// loop is held by the MUFU / MIO queue, not by issue slots -- so the scalar form stays the default.
+#ifndef XYZ_FWD_PACKED
+#define XYZ_FWD_PACKED 0
+#endif
+constexpr int kFwdRecVecs = XYZ_FWD_PACKED ? 3 : 2;
+
 #ifndef XYZ_BWD_CHUNK
 #define XYZ_BWD_CHUNK 128
 #endif
@@ -53,7 +63,7 @@ struct SplatView {  // what one launch renders
 
 struct SplatBuffers {  // device scratch of one launch (library-owned)
     float4* records;          // N x 4 float4 (kRecFloats)
-    float4* fwd_records;      // N x 2 float4: {cx, cy, kappa ia, 2 kappa ib} {kappa ic, so r, so g, so b} (forward staging)
+    float4* fwd_records;      // N x kFwdRecVecs float4 (forward staging, see above)
     int4* rects;              // N: tx0, ty0, tx1, ty1 (half-open)
     unsigned int* touched;    // N: tiles per Gaussian
     int2* spans;              // N x kSpanRows: [tx0, tx1) of the first kSpanRows tile rows of the rectangle

@@ -54,6 +54,45 @@ __device__ __forceinline__ float xor_sign(float v, float from) {
     return __uint_as_float(r);
 }
 
+// Packed fp32 (Blackwell FFMA2 / FADD2 / FMUL2 = PTX fma/add/mul.rn.f32x2): two independent IEEE operations per instruction
+// on the halves of 64-bit registers; the same bits as two scalar operations.
+struct F2 {
+    unsigned long long v;
+};
+#if XYZ_SPLAT_IS_FAST
+#define XYZ_F2_FTZ ".ftz"
+#else
+#define XYZ_F2_FTZ ""
+#endif
+__device__ __forceinline__ F2 f2_pack(float lo, float hi) {
+    F2 r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void f2_unpack(F2 a, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
+}
+__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
+    F2 r;
+    asm("fma.rn" XYZ_F2_FTZ ".f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
+    F2 r;
+    asm("mul.rn" XYZ_F2_FTZ ".f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
+    F2 r;
+    asm("add.rn" XYZ_F2_FTZ ".f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
+    return r;
+}
+__device__ __forceinline__ float f2_hsum(F2 a) {
+    float lo, hi;
+    f2_unpack(a, lo, hi);
+    return lo + hi;
+}
+
 // ---- forward: one CTA (64 threads) per tile, four pixels per thread -------------------------------------
 // Staged per Gaussian (shared memory, 32 B): {cx, cy, A2, B2} {C2, so*r, so*g, so*b}.  ncu on the one-pixel-per-
 // thread version: 87 % of the shared-memory pipe (two broadcast LDS.128 = 4 wavefronts per pair per warp), so a
@@ -115,6 +154,9 @@ __global__ void __launch_bounds__(kThreads)
     constexpr int kPerThread = (kFwdStage + kThreads - 1) / kThreads;  // Gaussians a thread stages per pass
     __shared__ __align__(16) float4 s_a[2][kFwdStage];
     __shared__ __align__(16) float4 s_b[2][kFwdStage];
+#if XYZ_FWD_PACKED
+    __shared__ __align__(16) float4 s_c[2][kFwdStage];
+#endif
     __shared__ int s_items[3];  // lengths of the tile's three lists of backward work items
 
     const int tid = threadIdx.x;
@@ -136,6 +178,12 @@ __global__ void __launch_bounds__(kThreads)
     float o[kRows][3];
 #pragma unroll
     for (int k = 0; k < kRows; ++k) o[k][0] = o[k][1] = o[k][2] = 0.f;
+#if XYZ_FWD_PACKED
+    static_assert(kRows % 2 == 0, "the packed colour sums pair a thread's rows");
+    F2 o2[kRows / 2][3];  // rows (k, k + 1) of colour i in the halves of one 64-bit register
+#pragma unroll
+    for (int k = 0; k < kRows / 2; ++k) o2[k][0] = o2[k][1] = o2[k][2] = f2_pack(0.f, 0.f);
+#endif
 
     int gid[kPerThread];  // ids of the stage that is fetched next
     auto load_ids = [&](int base) {
@@ -150,8 +198,11 @@ __global__ void __launch_bounds__(kThreads)
         for (int q = 0; q < kPerThread; ++q) {
             const int t = tid + q * kThreads;
             if (gid[q] >= 0) {
-                cp_async16(&s_a[buf][t], fwd_records + 2 * gid[q]);
-                cp_async16(&s_b[buf][t], fwd_records + 2 * gid[q] + 1);
+                cp_async16(&s_a[buf][t], fwd_records + kFwdRecVecs * gid[q]);
+                cp_async16(&s_b[buf][t], fwd_records + kFwdRecVecs * gid[q] + 1);
+#if XYZ_FWD_PACKED
+                cp_async16(&s_c[buf][t], fwd_records + kFwdRecVecs * gid[q] + 2);
+#endif
             }
         }
         cp_async_commit();
@@ -227,6 +278,29 @@ __global__ void __launch_bounds__(kThreads)
                 }
             }
         }
+#if XYZ_FWD_PACKED
+        const float4* __restrict__ sc = s_c[buf];
+        XYZ_UNROLL(XYZ_FWD_UNROLL)
+        for (int j = 0; j < n; ++j) {
+            const float4 a = sa[j];
+            const float4 b = sb[j];
+            const float4 c = sc[j];
+            const float dx = px - a.x;
+            const float t0 = (a.z * dx) * dx;
+            const float bdx = a.w * dx;
+            const F2 c0 = f2_pack(b.z, b.w), c1 = f2_pack(c.x, c.y), c2 = f2_pack(c.z, c.w);  // (so c_i, so c_i)
+#pragma unroll
+            for (int k = 0; k < kRows; k += 2) {
+                const float dy0 = py[k] - a.y, dy1 = py[k + 1] - a.y;
+                const float e0 = pair_exp(fmaf(dy0, fmaf(b.x, dy0, bdx), t0));
+                const float e1 = pair_exp(fmaf(dy1, fmaf(b.x, dy1, bdx), t0));
+                const F2 e = f2_pack(e0, e1);
+                o2[k / 2][0] = f2_fma(c0, e, o2[k / 2][0]);
+                o2[k / 2][1] = f2_fma(c1, e, o2[k / 2][1]);
+                o2[k / 2][2] = f2_fma(c2, e, o2[k / 2][2]);
+            }
+        }
+#else
         XYZ_UNROLL(XYZ_FWD_UNROLL)
         for (int j = 0; j < n; ++j) {
             const float4 a = sa[j];
@@ -243,10 +317,18 @@ __global__ void __launch_bounds__(kThreads)
                 o[k][2] = fmaf(b.w, e, o[k][2]);
             }
         }
+#endif
 #pragma unroll
         for (int q = 0; q < kPerThread; ++q) id_cur[q] = id_nxt[q];
     }
     cp_async_wait<0>();
+#if XYZ_FWD_PACKED
+#pragma unroll
+    for (int k = 0; k < kRows; k += 2) {
+#pragma unroll
+        for (int i = 0; i < 3; ++i) f2_unpack(o2[k / 2][i], o[k][i], o[k + 1][i]);
+    }
+#endif
     __shared__ float s_l[kTilePixels];  // per-pixel |out - target| by pixel index inside the tile (row-major)
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
@@ -356,43 +438,6 @@ __global__ void __launch_bounds__(kThreads)
 // cost 7.5 issue slots; only the exponential (MUFU) and the sign transfer (LOP3) work on single lanes.
 // Measured on B200 (dev/pipe_lab.cu): FFMA2 issues at half the FFMA rate (same flops) but leaves the other issue
 // slots to the ALU / MUFU pipes -- the scalar version of this loop was issue bound (ncu: 79 % issue active).
-struct F2 {
-    unsigned long long v;
-};
-#if XYZ_SPLAT_IS_FAST
-#define XYZ_F2_FTZ ".ftz"
-#else
-#define XYZ_F2_FTZ ""
-#endif
-__device__ __forceinline__ F2 f2_pack(float lo, float hi) {
-    F2 r;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(r.v) : "f"(lo), "f"(hi));
-    return r;
-}
-__device__ __forceinline__ void f2_unpack(F2 a, float& lo, float& hi) {
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(a.v));
-}
-__device__ __forceinline__ F2 f2_fma(F2 a, F2 b, F2 c) {
-    F2 r;
-    asm("fma.rn" XYZ_F2_FTZ ".f32x2 %0, %1, %2, %3;" : "=l"(r.v) : "l"(a.v), "l"(b.v), "l"(c.v));
-    return r;
-}
-__device__ __forceinline__ F2 f2_mul(F2 a, F2 b) {
-    F2 r;
-    asm("mul.rn" XYZ_F2_FTZ ".f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-    return r;
-}
-__device__ __forceinline__ F2 f2_add(F2 a, F2 b) {
-    F2 r;
-    asm("add.rn" XYZ_F2_FTZ ".f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v));
-    return r;
-}
-__device__ __forceinline__ float f2_hsum(F2 a) {
-    float lo, hi;
-    f2_unpack(a, lo, hi);
-    return lo + hi;
-}
-
 // Shared-memory layout of the residuals for the packed loop: per pixel pair (2p, 2p+1) two float4
 //   A = {-rest.x[2p], -rest.x[2p+1], -rest.y[2p], -rest.y[2p+1]}   B = {-rest.z[2p], -rest.z[2p+1], m[2p], m[2p+1]}
 // (negated so cd_i = fma(cs_i, e, -rest_i) takes them as the addend; m = 1 active / 0 inactive pixel).
@@ -615,7 +660,7 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
     static const int forced = [] {
         const char* e = std::getenv("XYZ_SPLAT_FWD_THREADS");
         const int x = e ? std::atoi(e) : 0;
-        return (x == 8 || x == 32 || x == 64 || x == 128 || x == 256) ? x : 0;
+        return (x == 8 || x == 32 || x == 64 || x == 128) ? x : 0;
     }();
     const long long tiles = static_cast<long long>(v.tiles_x) * (ty1 - ty0);
     const int sms = sm_count();
@@ -628,8 +673,7 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
     if (cfg == 8) splat_forward_kernel<32, 1><<<grid, 32, 0, st>>>(XYZ_FWD_ARGS);  // one warp per tile, 8 pixels per thread
     else if (cfg == 32) splat_forward_kernel<64, 2><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
     else if (cfg == 64) splat_forward_kernel<64, 1><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
-    else if (cfg == 128) splat_forward_kernel<128, 1><<<grid, 128, 0, st>>>(XYZ_FWD_ARGS);
-    else splat_forward_kernel<256, 1><<<grid, 256, 0, st>>>(XYZ_FWD_ARGS);
+    else splat_forward_kernel<128, 1><<<grid, 128, 0, st>>>(XYZ_FWD_ARGS);
 #undef XYZ_FWD_ARGS
     count_launch();
     return last_error();
