@@ -572,7 +572,7 @@ def test_splat_cull_is_result_preserving_and_deterministic():
 
 
 def test_splat_backward_cull_drops_only_terms_below_fp32_resolution():
-    """The backward pass leaves out (entry, half tile) items with d2 > 64 everywhere (weights below exp(-32)).  In
+    """The backward pass leaves out (entry, half tile) items with d2 > 48 everywhere (weights below exp(-24)).  In
     deterministic mode every kept entry is computed by the same instructions with and without the cull, so the difference
     between the two IS the dropped terms: it must stay below 1e-9 of the sum of |terms| (the parity bar is 1e-4), the
     image and the loss must not move at all, and the atomic mode must agree to the usual tolerance."""

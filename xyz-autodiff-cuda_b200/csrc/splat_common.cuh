@@ -52,8 +52,13 @@ constexpr float kKappaFast = -0.72134752044448170368f;
 constexpr float kKappaPrecise = -0.5f;
 constexpr float kD2MaxTail = 56.0f;  // XYZ_FLAG_TAIL_CULL (opt-in, bounded error): weights below exp(-28)
 // Backward cull: (entry, half tile) items on which min d2 exceeds this are left out of the gradient sums -- every term
-// of such a pair carries exp(-d2 / 2) < exp(-32) = 2^-46 (see splat_kernels.cuh; XYZ_FLAG_BWD_ALL_PAIRS turns it off)
-constexpr float kD2Backward = 64.0f;
+// of such a pair carries exp(-d2 / 2) < exp(-24) = 3.8e-11 (see splat_kernels.cuh; XYZ_FLAG_BWD_ALL_PAIRS turns it off).
+// The bound is chosen from a measurement of what the cull changes, in deterministic mode where every kept entry is
+// computed by the same instructions with and without it (dev/bwd_cull_sweep.py, profiles/bwd_cull_sweep_r02.log, C4 scene,
+// change of the fp32 sums relative to the fp64 sum of |terms|): D = 64: 3e-15, 56: 1e-13, 48: 1.1e-11, 40: 1.2e-7, 32: 5e-7
+// -- at 48 the sums move by less than 1/5000 of one fp32 epsilon (the parity bar for accumulated sums is 1e-4), at 40
+// the change reaches fp32 resolution.  Backward time at C4: 324 / 301 / 273 / 244 / 223 us.
+constexpr float kD2Backward = 48.0f;
 
 struct SplatView {  // what one launch renders
     int width, height, num_gaussians;

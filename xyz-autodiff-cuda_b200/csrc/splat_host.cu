@@ -831,7 +831,12 @@ int make_plan(SplatPlan& p, int W, int H, int N, int row_begin, int row_end, int
     p.deterministic = (flags & XYZ_FLAG_DETERMINISTIC) != 0;
     p.no_cull = (flags & XYZ_FLAG_NO_CULL) ? 1 : 0;
     p.d2max = (flags & XYZ_FLAG_TAIL_CULL) ? kD2MaxTail : (p.precise ? kD2MaxPrecise : kD2MaxFast);
-    p.d2_bwd = (flags & (XYZ_FLAG_BWD_ALL_PAIRS | XYZ_FLAG_NO_CULL)) ? INFINITY : kD2Backward;
+    static const float d2_bwd_default = [] {  // measuring knob (dev/bwd_cull_sweep.py): the bound of the backward cull
+        const char* e = std::getenv("XYZ_SPLAT_BWD_D2");
+        const float x = e ? static_cast<float>(std::atof(e)) : 0.0f;
+        return x > 0.0f ? x : kD2Backward;
+    }();
+    p.d2_bwd = (flags & (XYZ_FLAG_BWD_ALL_PAIRS | XYZ_FLAG_NO_CULL)) ? INFINITY : d2_bwd_default;
     const int ty_lo = row_begin / kTile, ty_hi = (row_end + kTile - 1) / kTile;
     const int band_tiles = (ty_hi - ty_lo) * p.v.tiles_x;
     if (band_tiles <= 0) p.v.num_gaussians = N = 0;  // an empty row band renders nothing: no kernel has work

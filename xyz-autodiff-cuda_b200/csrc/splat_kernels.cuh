@@ -521,9 +521,9 @@ __device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_r
 // ---- backward work items (written by the forward pass, see splat_forward_kernel) ----
 // The tile lists hold every pair whose weight is not EXACTLY zero (d2 <= 176: 13 sigma), which the forward pass needs for
 // a bit-identical image.  A gradient is an atomically accumulated sum held to 1e-4 of the sum of its terms' magnitudes, and
-// the terms of a pair carry the factor e = exp(-d2 / 2): beyond d2 = d2_bwd (default 64: e < 2^-46) they are far below
+// the terms of a pair carry the factor e = exp(-d2 / 2): beyond d2 = d2_bwd (default 48: e < 3.8e-11) they are far below
 // the fp32 resolution of the sums they would join.  So the backward pass works on ITEMS = (list entry, 16 x 8 half of the
-// tile) and leaves out the halves on which min d2 > d2_bwd -- 61 % of the listed pixels at BASELINE's C4.  The forward
+// tile) and leaves out the halves on which min d2 > d2_bwd -- 70 % of the listed pixels at BASELINE's C4.  The forward
 // CTA of a tile has every entry's record in shared memory anyway: it tests the two halves of each entry and appends the
 // entry to one of three lists in the tile's 2 len slots of bwd_items (begin, len: the tile's range in the sorted list):
 // both halves / rows 0..7 only / rows 8..15 only (deterministic mode: whole-tile items for every entry with a surviving
