@@ -106,10 +106,10 @@ enum {
     XYZ_FLAG_BWD_ALL_PAIRS = 1024, /* splat: the backward pass visits every pair of the tile lists, like the forward
                                     pass.  By default it leaves out the 16 x 8 half tiles of a (tile, Gaussian) entry on
                                     which d2 > 48 everywhere: every gradient term of such a pair carries the factor
-                                    exp(-d2 / 2) < exp(-24) = 3.8e-11.  Measured at 100 K Gaussians x 1024^2 (fixed-order
-                                    sums with and without the cull): the gradient sums change by at most 1.1e-11 of the
-                                    sum of their terms' magnitudes -- 1/5000 of one fp32 epsilon, seven orders below the
-                                    1e-4 bar of atomically accumulated sums -- while 70 % of the listed pixels drop out.
+                                    exp(-d2 / 2) < exp(-24) = 3.8e-11; what is left out of a gradient sum is below 1e-9
+                                    of the sum of its terms' magnitudes (1/60 of an fp32 epsilon: at most the last bit of
+                                    the fp32 sum moves; the bar for atomically accumulated sums is 1e-4), and 70 % of the
+                                    listed pixels drop out at 100 K Gaussians x 1024^2.
                                     Image and loss are not affected (the forward pass always renders the full lists).
                                     XYZ_FLAG_NO_CULL implies this flag. */
 };

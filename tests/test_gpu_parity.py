@@ -574,8 +574,10 @@ def test_splat_cull_is_result_preserving_and_deterministic():
 def test_splat_backward_cull_drops_only_terms_below_fp32_resolution():
     """The backward pass leaves out (entry, half tile) items with d2 > 48 everywhere (weights below exp(-24)).  In
     deterministic mode every kept entry is computed by the same instructions with and without the cull, so the difference
-    between the two IS the dropped terms: it must stay below 1e-9 of the sum of |terms| (the parity bar is 1e-4), the
-    image and the loss must not move at all, and the atomic mode must agree to the usual tolerance."""
+    between the two IS the dropped terms: below 1e-8 of the sum of |terms| (the tail integral of the largest coefficient,
+    d2 exp(-d2 / 2) beyond 48, is 1e-9 of its total) -- which can still move the rounding of an fp32 sum by its last bit,
+    so one ulp of the gradient is allowed on top (the parity bar is 1e-4).  The image and the loss must not move at all,
+    and the atomic mode must agree to the usual tolerance."""
     for (W, H, N, seed, small) in ((160, 128, 400, 21, True), (256, 192, 300, 5, False)):
         params, target = orc.splat_scene(N, W, H, seed=seed, small=small)
         rg, ro, rl, tol = orc.splat_tolerance(params, target, W, H)
@@ -585,7 +587,7 @@ def test_splat_backward_cull_drops_only_terms_below_fp32_resolution():
             g_cut, o_cut, l_cut = run_splat(params, target, W, H, flags | D)
             g_all, o_all, l_all = run_splat(params, target, W, H, flags | D | A)
             assert np.array_equal(o_cut, o_all) and l_cut == l_all
-            assert (np.abs(g_cut - g_all) <= 1e-9 * absg).all()
+            assert (np.abs(g_cut - g_all) <= 1e-8 * absg + 2.0 ** -23 * np.abs(g_all)).all(), float((np.abs(g_cut - g_all) / absg).max())
             g_atomic = run_splat(params, target, W, H, flags)[0]
             g_atomic_all = run_splat(params, target, W, H, flags | A)[0]
             assert (np.abs(g_atomic - rg) <= tol).all() and (np.abs(g_atomic_all - rg) <= tol).all()

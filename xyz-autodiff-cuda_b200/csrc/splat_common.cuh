@@ -24,16 +24,6 @@ namespace xyzb {
 
 constexpr int kTile = 16;                 // TILE_SIZE, gaussian_splatting_kernel.cuh:21
 constexpr int kTilePixels = kTile * kTile;
-// Forward staging record: 2 float4 {cx, cy, kappa ia, 2 kappa ib} {kappa ic, so r, so g, so b}, or -- XYZ_FWD_PACKED, the
-// colour sums of two pixels run on packed fp32 (FFMA2) -- 3 float4 with every colour twice, so that a 64-bit half of an
-// LDS.128 is a packed operand: {cx, cy, kappa ia, 2 kappa ib} {kappa ic, 0, so r, so r} {so g, so g, so b, so b}.
-// Measured (C4, same box): 136 instead of 148 issue slots per 16 pairs and the same bits, but 391 us against 387 -- the
-// loop is held by the MUFU / MIO queue, not by issue slots -- so the scalar form stays the default.
-#ifndef XYZ_FWD_PACKED
-#define XYZ_FWD_PACKED 0
-#endif
-constexpr int kFwdRecVecs = XYZ_FWD_PACKED ? 3 : 2;
-
 #ifndef XYZ_BWD_CHUNK
 #define XYZ_BWD_CHUNK 128
 #endif
@@ -55,9 +45,11 @@ constexpr float kD2MaxTail = 56.0f;  // XYZ_FLAG_TAIL_CULL (opt-in, bounded erro
 // of such a pair carries exp(-d2 / 2) < exp(-24) = 3.8e-11 (see splat_kernels.cuh; XYZ_FLAG_BWD_ALL_PAIRS turns it off).
 // The bound is chosen from a measurement of what the cull changes, in deterministic mode where every kept entry is
 // computed by the same instructions with and without it (dev/bwd_cull_sweep.py, profiles/bwd_cull_sweep_r02.log, C4 scene,
-// change of the fp32 sums relative to the fp64 sum of |terms|): D = 64: 3e-15, 56: 1e-13, 48: 1.1e-11, 40: 1.2e-7, 32: 5e-7
-// -- at 48 the sums move by less than 1/5000 of one fp32 epsilon (the parity bar for accumulated sums is 1e-4), at 40
-// the change reaches fp32 resolution.  Backward time at C4: 324 / 301 / 273 / 244 / 223 us.
+// largest change of an fp32 gradient sum relative to the fp64 sum of |terms|, 66 sampled Gaussians): D = 64: 3e-15,
+// 56: 1e-13, 48: 1.1e-11, 40: 1.2e-7, 32: 5e-7.  In exact arithmetic the dropped tail of the largest coefficient
+// (d2 exp(-d2 / 2)) beyond 48 is 1e-9 of its total: 1/60 of an fp32 epsilon -- it can move the rounding of a sum by its last
+// bit and no further (tests/test_gpu_parity.py); beyond 40 whole ulps go.  The parity bar for accumulated sums is 1e-4.
+// Backward time at C4 for D = 64 / 56 / 48 / 40 / 32: 324 / 301 / 273 / 244 / 223 us.
 constexpr float kD2Backward = 48.0f;
 
 struct SplatView {  // what one launch renders
@@ -68,7 +60,7 @@ struct SplatView {  // what one launch renders
 
 struct SplatBuffers {  // device scratch of one launch (library-owned)
     float4* records;          // N x 4 float4 (kRecFloats)
-    float4* fwd_records;      // N x kFwdRecVecs float4 (forward staging, see above)
+    float4* fwd_records;      // N x 2 float4: {cx, cy, kappa ia, 2 kappa ib} {kappa ic, so r, so g, so b} (forward staging)
     int4* rects;              // N: tx0, ty0, tx1, ty1 (half-open)
     unsigned int* touched;    // N: tiles per Gaussian
     int2* spans;              // N x kSpanRows: [tx0, tx1) of the first kSpanRows tile rows of the rectangle

@@ -158,14 +158,9 @@ __global__ void __launch_bounds__(256)
             records[4 * g + 3] = make_float4(sn, 0.f, 0.f, 0.f);
             // what the forward pass stages per Gaussian, ready to copy (cp.async): the conic pre-scaled by
             // kappa (-0.5 log2(e) for the fast-math flavour's ex2, -0.5 for expf) and the colours by sigmoid(opacity)
-            fwd_records[kFwdRecVecs * g] = make_float4(p.center[0], p.center[1], __fmul_rn(kappa, ia), __fmul_rn(2.0f * kappa, ib));
-            const float sr = __fmul_rn(so, p.color[0]), sg = __fmul_rn(so, p.color[1]), sb = __fmul_rn(so, p.color[2]);
-#if XYZ_FWD_PACKED
-            fwd_records[3 * g + 1] = make_float4(__fmul_rn(kappa, ic), 0.f, sr, sr);
-            fwd_records[3 * g + 2] = make_float4(sg, sg, sb, sb);
-#else
-            fwd_records[2 * g + 1] = make_float4(__fmul_rn(kappa, ic), sr, sg, sb);
-#endif
+            fwd_records[2 * g] = make_float4(p.center[0], p.center[1], __fmul_rn(kappa, ia), __fmul_rn(2.0f * kappa, ib));
+            fwd_records[2 * g + 1] = make_float4(__fmul_rn(kappa, ic), __fmul_rn(so, p.color[0]), __fmul_rn(so, p.color[1]),
+                                                 __fmul_rn(so, p.color[2]));
             r = gaussian_tile_rect(p.center[0], p.center[1], ia, ib, ic, v, d2max, no_cull);
             rects[g] = r;
             // (a rectangle that misses the image / the row band is empty: no spans to derive -- 7 of 8 Gaussians when
@@ -868,7 +863,7 @@ int make_plan(SplatPlan& p, int W, int H, int N, int row_begin, int row_end, int
     auto take = [&off](size_t bytes) { size_t o = off; off += align_up(bytes); return o; };
     const size_t nl = static_cast<size_t>(p.n_tiles_l > 0 ? p.n_tiles_l : 1);
     p.o_rec = take(sizeof(float4) * 4 * ng);
-    p.o_frec = take(sizeof(float4) * kFwdRecVecs * ng);
+    p.o_frec = take(sizeof(float4) * 2 * ng);
     p.o_rect = take(sizeof(int4) * ng);
     p.o_touched = take(sizeof(unsigned int) * ng);
     p.o_spans = take(sizeof(int2) * kSpanRows * ng);

@@ -154,9 +154,6 @@ __global__ void __launch_bounds__(kThreads)
     constexpr int kPerThread = (kFwdStage + kThreads - 1) / kThreads;  // Gaussians a thread stages per pass
     __shared__ __align__(16) float4 s_a[2][kFwdStage];
     __shared__ __align__(16) float4 s_b[2][kFwdStage];
-#if XYZ_FWD_PACKED
-    __shared__ __align__(16) float4 s_c[2][kFwdStage];
-#endif
     __shared__ int s_items[3];  // lengths of the tile's three lists of backward work items
 
     const int tid = threadIdx.x;
@@ -178,12 +175,6 @@ __global__ void __launch_bounds__(kThreads)
     float o[kRows][3];
 #pragma unroll
     for (int k = 0; k < kRows; ++k) o[k][0] = o[k][1] = o[k][2] = 0.f;
-#if XYZ_FWD_PACKED
-    static_assert(kRows % 2 == 0, "the packed colour sums pair a thread's rows");
-    F2 o2[kRows / 2][3];  // rows (k, k + 1) of colour i in the halves of one 64-bit register
-#pragma unroll
-    for (int k = 0; k < kRows / 2; ++k) o2[k][0] = o2[k][1] = o2[k][2] = f2_pack(0.f, 0.f);
-#endif
 
     int gid[kPerThread];  // ids of the stage that is fetched next
     auto load_ids = [&](int base) {
@@ -198,11 +189,8 @@ __global__ void __launch_bounds__(kThreads)
         for (int q = 0; q < kPerThread; ++q) {
             const int t = tid + q * kThreads;
             if (gid[q] >= 0) {
-                cp_async16(&s_a[buf][t], fwd_records + kFwdRecVecs * gid[q]);
-                cp_async16(&s_b[buf][t], fwd_records + kFwdRecVecs * gid[q] + 1);
-#if XYZ_FWD_PACKED
-                cp_async16(&s_c[buf][t], fwd_records + kFwdRecVecs * gid[q] + 2);
-#endif
+                cp_async16(&s_a[buf][t], fwd_records + 2 * gid[q]);
+                cp_async16(&s_b[buf][t], fwd_records + 2 * gid[q] + 1);
             }
         }
         cp_async_commit();
@@ -278,29 +266,6 @@ __global__ void __launch_bounds__(kThreads)
                 }
             }
         }
-#if XYZ_FWD_PACKED
-        const float4* __restrict__ sc = s_c[buf];
-        XYZ_UNROLL(XYZ_FWD_UNROLL)
-        for (int j = 0; j < n; ++j) {
-            const float4 a = sa[j];
-            const float4 b = sb[j];
-            const float4 c = sc[j];
-            const float dx = px - a.x;
-            const float t0 = (a.z * dx) * dx;
-            const float bdx = a.w * dx;
-            const F2 c0 = f2_pack(b.z, b.w), c1 = f2_pack(c.x, c.y), c2 = f2_pack(c.z, c.w);  // (so c_i, so c_i)
-#pragma unroll
-            for (int k = 0; k < kRows; k += 2) {
-                const float dy0 = py[k] - a.y, dy1 = py[k + 1] - a.y;
-                const float e0 = pair_exp(fmaf(dy0, fmaf(b.x, dy0, bdx), t0));
-                const float e1 = pair_exp(fmaf(dy1, fmaf(b.x, dy1, bdx), t0));
-                const F2 e = f2_pack(e0, e1);
-                o2[k / 2][0] = f2_fma(c0, e, o2[k / 2][0]);
-                o2[k / 2][1] = f2_fma(c1, e, o2[k / 2][1]);
-                o2[k / 2][2] = f2_fma(c2, e, o2[k / 2][2]);
-            }
-        }
-#else
         XYZ_UNROLL(XYZ_FWD_UNROLL)
         for (int j = 0; j < n; ++j) {
             const float4 a = sa[j];
@@ -317,18 +282,10 @@ __global__ void __launch_bounds__(kThreads)
                 o[k][2] = fmaf(b.w, e, o[k][2]);
             }
         }
-#endif
 #pragma unroll
         for (int q = 0; q < kPerThread; ++q) id_cur[q] = id_nxt[q];
     }
     cp_async_wait<0>();
-#if XYZ_FWD_PACKED
-#pragma unroll
-    for (int k = 0; k < kRows; k += 2) {
-#pragma unroll
-        for (int i = 0; i < 3; ++i) f2_unpack(o2[k / 2][i], o[k][i], o[k + 1][i]);
-    }
-#endif
     __shared__ float s_l[kTilePixels];  // per-pixel |out - target| by pixel index inside the tile (row-major)
 #pragma unroll
     for (int k = 0; k < kRows; ++k) {
