@@ -610,14 +610,15 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
                                                      float d2_bwd, int first_tile, const int* tile_order, cudaStream_t st) {
     const int ty0 = v.row_begin / kTile, ty1 = (v.row_end + kTile - 1) / kTile;
     if (ty1 <= ty0) return 0;
-    // configuration by how many tiles an SM gets (see the kernel); XYZ_SPLAT_FWD_THREADS = 64 | 128 | 256 (threads of a
+    // configuration by how many tiles an SM gets (see the kernel); XYZ_SPLAT_FWD_THREADS = 64 | 128 (threads of a
     // whole-tile CTA) or 32 (two half-tile CTAs of 64 threads) overrides.  Measured (dev/fwd_threads_sweep.py,
     // profiles/fwd_threads_sweep_r02.log): whole tiles with 64 threads win from 12 tiles per SM on, half tiles below;
-    // 128 / 256 threads per tile (more shared-memory reads per pair) never win.
+    // 128 / 256 threads per tile (more shared-memory reads per pair) never win, nor does one warp per tile with eight
+    // pixels per lane (fewer issue slots per pair, 96 registers: 388 us against 387 at C4).
     static const int forced = [] {
         const char* e = std::getenv("XYZ_SPLAT_FWD_THREADS");
         const int x = e ? std::atoi(e) : 0;
-        return (x == 8 || x == 32 || x == 64 || x == 128) ? x : 0;
+        return (x == 32 || x == 64 || x == 128) ? x : 0;
     }();
     const long long tiles = static_cast<long long>(v.tiles_x) * (ty1 - ty0);
     const int sms = sm_count();
@@ -627,8 +628,7 @@ int XYZ_CAT(splat_forward_launch_, XYZ_SPLAT_FLAVOR)(const SplatView& v, const S
 #define XYZ_FWD_ARGS v, b.fwd_records, b.sorted_gid, b.tile_ranges, target, output, b.tile_loss, b.rest_tiles, ty0, ticket, total_loss, \
                      b.bwd_items, b.chunk_offsets, b.chunk_info, first_tile, d2s, b.vals_out, deterministic ? b.entry_grads : nullptr, \
                      tile_order
-    if (cfg == 8) splat_forward_kernel<32, 1><<<grid, 32, 0, st>>>(XYZ_FWD_ARGS);  // one warp per tile, 8 pixels per thread
-    else if (cfg == 32) splat_forward_kernel<64, 2><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
+    if (cfg == 32) splat_forward_kernel<64, 2><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
     else if (cfg == 64) splat_forward_kernel<64, 1><<<grid, 64, 0, st>>>(XYZ_FWD_ARGS);
     else splat_forward_kernel<128, 1><<<grid, 128, 0, st>>>(XYZ_FWD_ARGS);
 #undef XYZ_FWD_ARGS
