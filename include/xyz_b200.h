@@ -315,7 +315,9 @@ XYZ_API int xyz_splat_last_timing(float stage_us_host[6]);
  * its running offset from the counting sort, (0, 0) from the radix path), the sorted Gaussian ids
  * (entries int32) and the per-Gaussian float records the rectangles were derived from
  * (N x 12 float: cx, cy, ia, ib, ic, sigmoid(opacity), r, g, b, and three floats that are left untouched).  Tiles outside
- * the launch's row band are reported as (0, 0).  Any pointer may be NULL.  Synchronises the launch's stream. */
+ * the launch's row band are reported as (0, 0); a launch that renders a row band does not write the records of
+ * Gaussians that cannot reach the band (their rectangles are empty).  Any pointer may be NULL.  Synchronises the
+ * launch's stream. */
 XYZ_API int xyz_splat_debug_binning(int32_t* rects_host, int32_t* tile_ranges_host, int32_t* sorted_ids_host,
                             float* records_host);
 

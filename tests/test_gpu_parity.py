@@ -636,6 +636,33 @@ def test_splat_tile_binning_is_bit_exact():
         assert (np.abs(recs[ok] - want[ok]) <= 1e-5 * np.maximum(np.abs(want[ok]), scale[ok])).all()
 
 
+def test_splat_row_band_prefilter_keeps_the_integer_results():
+    """A launch that renders a row band skips, ahead of the records, the Gaussians that cannot reach the band (bound on the
+    ellipse's reach from max(exp(scale))).  Rectangles, lists and ranges of the band must equal the CPU restatement run on
+    the records of a FULL launch (the band launch does not write the records of the Gaussians it skips); degenerate,
+    huge, off-screen and strongly anisotropic Gaussians take the full path."""
+    W, H, N = 200, 400, 3000
+    params, target = orc.splat_scene(N, W, H, seed=9)
+    params[:5, 0] = [-500.0, 900.0, 100.0, 50.0, 0.0]
+    params[5, 2:4] = -30.0                                     # degenerate covariance (det regularised, Q15): full path
+    params[6, 2:4] = 5.0                                       # covers the whole image
+    params[7, 2:4] = [-4.0, 3.0]                               # axes 1100 : 1, rotated: full path
+    run_splat(params, target, W, H, 0)
+    st = x.splat_last_stats()
+    recs = x.splat_debug_binning(N, st["tiles"], st["entries"])[3]
+    for rb, re_ in ((0, 64), (112, 240), (304, 400), (37, 41)):
+        for flags in (0, x.FLAG_RADIX_BINNING, x.FLAG_DETERMINISTIC):
+            run_splat(params, target, W, H, flags, rows=(rb, re_))
+            st = x.splat_last_stats()
+            rects, ranges, ids, _ = x.splat_debug_binning(N, st["tiles"], st["entries"])
+            orects, oranges, oids = orc.splat_binning(recs, W, H, rb, re_)
+            assert np.array_equal(rects, orects), (rb, re_, flags)
+            assert np.array_equal(ids, oids) and st["entries"] == oids.size, (rb, re_, flags)
+            nonempty = oranges[:, 1] > oranges[:, 0]
+            assert np.array_equal(ranges[nonempty], oranges[nonempty]), (rb, re_, flags)
+            assert (rects[:, 3] > rects[:, 1]).sum() < N // 2     # most Gaussians miss the band
+
+
 def test_splat_counting_sort_binning_equals_the_radix_path():
     """The default binning (stable counting sort by tile, csrc/splat_host.cu section 2b) and the radix path give the
     same lists, so image and loss are bit-identical; deterministic gradients too (same rows, same order).  Scenes:

@@ -121,6 +121,7 @@ __global__ void __launch_bounds__(256)
     const int per_cta = kCount ? chunk_size : 256;
     const int g_begin = blockIdx.x * per_cta, g_end = min(g_begin + per_cta, v.num_gaussians);
     const int ty_lo = v.row_begin / kTile;
+    const bool band_only = !no_cull && (v.row_begin > 0 || v.row_end < v.height);
     if (kCount) {
         if (blockIdx.x == 0 && tid == 0) *ticket = 0u;  // for the column-scan kernel that follows
         if (tid == 0) s_total = 0u;
@@ -135,11 +136,30 @@ __global__ void __launch_bounds__(256)
         SpanCoef sc{};
         unsigned int cnt = 0;
         bool big_one = false;  // rectangle of more than kBigGaussian tiles: counted by the whole warp below
+        bool misses_band = false;
         if (live) {
             const xyz_gaussian_params p = params[g];
             // exp_logic.cuh:17-25, covariance_generation.cuh:154-172, sym_matrix2_inv_logic.cuh:21-40,
             // math.cuh:200-204 (sigmoid) -- computed once per Gaussian instead of once per pair per pass
             const float es0 = expf(p.scale[0]), es1 = expf(p.scale[1]);
+            if (band_only) {
+                // A launch that renders a row band of the image (one of G GPUs): 1 - 1/G of the Gaussians cannot reach it.
+                // Sigma_yy <= max(exp s)^2, so the ellipse d2 <= d2max stays within sqrt(d2max) max(exp s) rows of the
+                // centre; with the margins of gaussian_tile_rect (0.1 % + 1 pixel + the rounding of its own chain) a
+                // Gaussian beyond that has the EMPTY rectangle there too -- same integer result, without the sine, the
+                // inverse, the records and the spans.  Only for a covariance the det rule (Q15) leaves alone and whose
+                // axes differ by less than 64 x (the rectangle's own "positive definite in fp32" test then holds with a
+                // margin of 1e-3; anything else takes the full path and is kept as before).
+                const float reach = fmaf(sqrtf(d2max) * fmaxf(es0, es1), 1.002f, 2.0f);
+                const float cy = p.center[1];
+                if (es0 * es1 > 1.1e-4f && fmaxf(es0, es1) < 64.0f * fminf(es0, es1) && isfinite(reach) && isfinite(cy) && isfinite(p.center[0]) &&
+                    (cy + reach < static_cast<float>(v.row_begin) || cy - reach > static_cast<float>(v.row_end - 1))) {
+                    rects[g] = make_int4(0, 0, 0, 0);
+                    touched[g] = 0u;
+                    misses_band = true;
+                }
+            }
+            if (!misses_band) {
             const float ct = cosf(p.rotation[0]), sn = sinf(p.rotation[0]);
             const float m00 = __fmul_rn(es0, ct), m01 = __fmul_rn(-es1, sn), m10 = __fmul_rn(es0, sn), m11 = __fmul_rn(es1, ct);
             const float A = __fadd_rn(__fmul_rn(m00, m00), __fmul_rn(m01, m01));
@@ -177,6 +197,7 @@ __global__ void __launch_bounds__(256)
             }
             touched[g] = cnt;
             my_total += cnt;
+            }
         }
         if (kCount) {
             unsigned int big = __ballot_sync(0xffffffffu, big_one);
