@@ -104,12 +104,12 @@ enum {
                                     from the reported length: repeat the iteration.  Results of a launch that fits are
                                     the same as without the flag. */
     XYZ_FLAG_BWD_ALL_PAIRS = 1024, /* splat: the backward pass visits every pair of the tile lists, like the forward
-                                    pass.  By default it leaves out the 16 x 8 half tiles of a (tile, Gaussian) entry on
-                                    which d2 > 48 everywhere: every gradient term of such a pair carries the factor
+                                    pass.  By default it leaves out the (tile, Gaussian) entries with d2 > 48 on all of
+                                    the tile: every gradient term of such a pair carries the factor
                                     exp(-d2 / 2) < exp(-24) = 3.8e-11; what is left out of a gradient sum is below 1e-9
                                     of the sum of its terms' magnitudes (1/60 of an fp32 epsilon: at most the last bit of
-                                    the fp32 sum moves; the bar for atomically accumulated sums is 1e-4), and 70 % of the
-                                    listed pixels drop out at 100 K Gaussians x 1024^2.
+                                    the fp32 sum moves; the bar for atomically accumulated sums is 1e-4), and 65 % of the
+                                    list entries drop out at 100 K Gaussians x 1024^2.
                                     Image and loss are not affected (the forward pass always renders the full lists).
                                     XYZ_FLAG_NO_CULL implies this flag. */
 };
@@ -254,7 +254,7 @@ XYZ_API int xyz_covproj_shared_w_fwd_bwd_f32_allreduce(const float* J, const flo
  * Two families of entry points:
  *   xyz_launch_gaussian_splatting[_rows]   the reference's call shape: no workspace argument.  Scratch is library-owned,
  *       one arena per (device, stream) -- launches on different streams never share buffers -- and grows on demand
- *       (4 bytes per (tile, Gaussian) list entry, 36 more with XYZ_FLAG_DETERMINISTIC); the call synchronises `stream`
+ *       (8 bytes per (tile, Gaussian) list entry, 40 more with XYZ_FLAG_DETERMINISTIC); the call synchronises `stream`
  *       once (the list length is data dependent) unless XYZ_FLAG_ASYNC applies.  While `stream` is being captured into a
  *       CUDA graph the scratch cannot grow (XYZ_ERR_WORKSPACE: run the iteration once outside the capture first); a
  *       buffer a capture has seen is kept alive until xyz_b200_shutdown, so replays stay valid.
@@ -303,7 +303,7 @@ XYZ_API int xyz_splat_workspace_status(const void* workspace, void* stream, long
  * been reallocated or freed since; XYZ_ERR_WORKSPACE if it overflowed. */
 XYZ_API int xyz_splat_last_stats(long long stats_host[4]);
 /* What the backward pass of that launch worked on (waits for the launch and reads its work records back):
- * stats[0] = work items ((entry, half tile) or (entry, whole tile), see XYZ_FLAG_BWD_ALL_PAIRS), stats[1] = pixel-Gaussian
+ * stats[0] = work items (list entries the backward pass keeps, see XYZ_FLAG_BWD_ALL_PAIRS), stats[1] = pixel-Gaussian
  * pairs it evaluated, stats[2] = backward CTAs with work.  Same error codes as xyz_splat_last_stats. */
 XYZ_API int xyz_splat_last_backward_stats(long long stats_host[3]);
 /* Stage times of this host thread's most recent splat launch made with XYZ_FLAG_TIMING, in microseconds (waits for that

@@ -1100,8 +1100,8 @@ long long orc_splat_binning_counting(const float* rec, int N, int W, int H, int 
     std::vector<int> chunk_offsets(n_tiles + 1, 0);
     for (int t = 0; t < n_tiles; ++t) {
         begin[t + 1] = begin[t] + tile_total[t];
-        // backward work records set aside per tile: ceil(len / chunk) + 2 for a non-empty list (the forward pass fills them in)
-        chunk_offsets[t + 1] = chunk_offsets[t] + (tile_total[t] ? static_cast<int>((tile_total[t] + bwd_chunk - 1) / bwd_chunk) + 2 : 0);
+        // backward work records set aside per tile: ceil(len / chunk) (the forward pass fills them in)
+        chunk_offsets[t + 1] = chunk_offsets[t] + static_cast<int>((tile_total[t] + bwd_chunk - 1) / bwd_chunk);
         if (tile_ranges) {
             tile_ranges[2 * t] = static_cast<int32_t>(begin[t]);
             tile_ranges[2 * t + 1] = static_cast<int32_t>(begin[t + 1]);

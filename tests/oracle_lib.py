@@ -264,7 +264,7 @@ def splat_binning_counting(records, W, H, row_begin=0, row_end=None, d2max=176.0
     total = fn(_p(rec), N, W, H, row_begin, row_end, ctypes.c_float(d2max), int(no_cull), int(ctas_total), int(bwd_chunk),
                _p(ranges), None, _ll(0), None, 0)
     ids = np.full(max(total, 1), -1, np.int32)
-    n_info = total // bwd_chunk + 3 * ntiles
+    n_info = total // bwd_chunk + ntiles
     info = np.full((max(n_info, 1), 4), -7, np.int32)
     got = fn(_p(rec), N, W, H, row_begin, row_end, ctypes.c_float(d2max), int(no_cull), int(ctas_total), int(bwd_chunk),
              _p(ranges), _p(ids), _ll(total), _p(info), int(n_info))

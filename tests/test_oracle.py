@@ -202,9 +202,9 @@ def test_counting_sort_binning_index_arithmetic_over_shapes():
                 for ctas in (1, 5, 592):
                     cr, ci, info = orc.splat_binning_counting(rec, W, H, rb, re_, no_cull=nc, ctas_total=ctas)
                     assert np.array_equal(cr, ranges) and np.array_equal(ci, ids), (W, H, N, rb, re_, ctas)
-                    # the backward work records: ceil(len / 128) + 2 set aside per non-empty tile (left for the forward
-                    # pass to fill in: untouched here), every record beyond them = -1
-                    n_kept = sum((e - b + 127) // 128 + 2 for b, e in ranges if e > b)
+                    # the backward work records: ceil(len / 128) set aside per tile (left for the forward pass to fill
+                    # in: untouched here), every record beyond them = -1
+                    n_kept = sum((e - b + 127) // 128 for b, e in ranges)
                     assert (info[n_kept:] == -1).all() and (info[:n_kept] == -7).all()
 
 

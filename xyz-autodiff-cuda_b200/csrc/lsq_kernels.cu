@@ -22,8 +22,14 @@ namespace {
 
 constexpr int kThreads = 256;
 constexpr int kTileP = 256;  // points per tile
-constexpr int kStages = 4;
-constexpr int kCtasPerSM = 4;
+#ifndef XYZ_LSQ_STAGES
+#define XYZ_LSQ_STAGES 4
+#endif
+#ifndef XYZ_LSQ_CTAS_PER_SM
+#define XYZ_LSQ_CTAS_PER_SM 4
+#endif
+constexpr int kStages = XYZ_LSQ_STAGES;
+constexpr int kCtasPerSM = XYZ_LSQ_CTAS_PER_SM;
 constexpr int kAcc = 5;  // ga gb gc gd loss
 
 struct LsqSmem {

@@ -41,7 +41,7 @@ constexpr float kD2MaxPrecise = 209.0f;
 constexpr float kKappaFast = -0.72134752044448170368f;
 constexpr float kKappaPrecise = -0.5f;
 constexpr float kD2MaxTail = 56.0f;  // XYZ_FLAG_TAIL_CULL (opt-in, bounded error): weights below exp(-28)
-// Backward cull: (entry, half tile) items on which min d2 exceeds this are left out of the gradient sums -- every term
+// Backward cull: list entries with min d2 over their tile beyond this are left out of the gradient sums -- every term
 // of such a pair carries exp(-d2 / 2) < exp(-24) = 3.8e-11 (see splat_kernels.cuh; XYZ_FLAG_BWD_ALL_PAIRS turns it off).
 // The bound is chosen from a measurement of what the cull changes, in deterministic mode where every kept entry is
 // computed by the same instructions with and without it (dev/bwd_cull_sweep.py, profiles/bwd_cull_sweep_r02.log, C4 scene,
@@ -49,7 +49,8 @@ constexpr float kD2MaxTail = 56.0f;  // XYZ_FLAG_TAIL_CULL (opt-in, bounded erro
 // 56: 1e-13, 48: 1.1e-11, 40: 1.2e-7, 32: 5e-7.  In exact arithmetic the dropped tail of the largest coefficient
 // (d2 exp(-d2 / 2)) beyond 48 is 1e-9 of its total: 1/60 of an fp32 epsilon -- it can move the rounding of a sum by its last
 // bit and no further (tests/test_gpu_parity.py); beyond 40 whole ulps go.  The parity bar for accumulated sums is 1e-4.
-// Backward time at C4 for D = 64 / 56 / 48 / 40 / 32: 324 / 301 / 273 / 244 / 223 us.
+// Backward time at C4 for D = 64 / 56 / 48 / 40 / 32: 324 / 301 / 273 / 244 / 223 us (measured with half-tile items; whole-tile
+// items, the final form, take the same 275 us at 48).
 constexpr float kD2Backward = 48.0f;
 
 struct SplatView {  // what one launch renders
@@ -72,15 +73,15 @@ struct SplatBuffers {  // device scratch of one launch (library-owned)
     int* sorted_gid;          // entries: Gaussian id per sorted entry (fast mode: aliases vals_out)
     int2* tile_ranges;        // tiles: [begin, end)
     int* chunk_offsets;       // tiles of the launch + 1: exclusive scan of the backward work records set aside per tile
-                              // (ceil(list length / kBwdChunk) + 2 for a non-empty list)
-    int4* chunk_info;         // backward work records = CTAs (entries / kBwdChunk + 3 tiles, an upper bound):
-                              // {tile or -1, first item's slot, items, list}, written by the forward pass
+                              // (ceil(list length / kBwdChunk))
+    int4* chunk_info;         // backward work records = CTAs (entries / kBwdChunk + tiles, an upper bound):
+                              // {tile or -1, first item's slot, items, -}, written by the forward pass
     float4* rest_tiles;       // tiles x 256: (target - output, active) per pixel, tile-major, written by the forward pass
     float* tile_loss;         // 2 x tiles: one partial per half tile (rows 0..7, rows 8..15)
     float* entry_grads;       // deterministic mode: entries x 9 (indexed by ORIGINAL entry index)
     int* tile_order;          // tiles of the launch: band-local tile ids, longest list first (launch order of the forward CTAs)
-    int* bwd_items;           // 2 x entries: the backward work items, written by the forward pass into the 2 len slots
-                              // of every tile (three lists, see splat_kernels.cuh)
+    int* bwd_items;           // entries: the backward work items, written by the forward pass into the first slots of
+                              // every tile's range (see splat_kernels.cuh)
 };
 
 // flavour launchers (splat_fast.cu is built with -use_fast_math like the reference's training app,

@@ -348,10 +348,10 @@ __device__ __forceinline__ void cta_exclusive_scan_u32_to_u64(const unsigned int
     }
 }
 
-// backward work records set aside for a tile with `len` list entries: the forward pass sorts every entry into at most
-// one of three item lists and each list takes ceil(items / kBwdChunk) records (splat_kernels.cuh)
+// backward work records set aside for a tile with `len` list entries: the forward pass keeps at most `len` work items
+// and each record takes kBwdChunk of them (splat_kernels.cuh)
 __host__ __device__ __forceinline__ int bwd_records_of(unsigned int len) {
-    return len ? static_cast<int>((len + kBwdChunk - 1) / kBwdChunk) + 2 : 0;
+    return static_cast<int>((len + kBwdChunk - 1) / kBwdChunk);
 }
 
 __device__ __forceinline__ void bin_tilescan(const unsigned int* tile_total, int n_tiles, int2* __restrict__ tile_ranges,
@@ -920,10 +920,10 @@ EntryLayout make_entry_layout(const SplatPlan& p, long long capacity, cudaStream
     L.o_vin = stake(p.counting ? 0 : 4 * ne);
     L.o_vout = stake(4 * ne);
     L.o_gid = stake(p.deterministic ? 4 * ne : 0);
-    L.chunk_info_size = static_cast<int>(capacity / kBwdChunk + 3LL * p.n_tiles_l);  // sum of ceil(len / chunk) + 2
-    L.o_cinfo = stake(sizeof(int4) * static_cast<size_t>(ne / kBwdChunk + 3LL * p.n_tiles_l));
+    L.chunk_info_size = static_cast<int>(capacity / kBwdChunk + p.n_tiles_l);  // an upper bound of the sum of ceil(len / chunk)
+    L.o_cinfo = stake(sizeof(int4) * static_cast<size_t>(ne / kBwdChunk + p.n_tiles_l));
     L.o_eg = stake(p.deterministic ? 36 * ne : 0);
-    L.o_items = stake(8 * ne);  // the backward work items: up to two per entry
+    L.o_items = stake(4 * ne);  // the backward work items: at most one per entry
     L.sort_tmp_bytes = 0;
     if (!p.counting)
         cub::DeviceRadixSort::SortPairs(nullptr, L.sort_tmp_bytes, static_cast<unsigned int*>(nullptr),
@@ -1455,7 +1455,7 @@ extern "C" int xyz_splat_last_backward_stats(long long stats_host[3]) {
     for (const int4& r : rec) {
         if (r.x < 0) continue;
         stats_host[0] += r.z;
-        stats_host[1] += static_cast<long long>(r.z) * (r.w == 0 ? kTilePixels : kTilePixels / 2);
+        stats_host[1] += static_cast<long long>(r.z) * kTilePixels;
         stats_host[2] += 1;
     }
     return 0;

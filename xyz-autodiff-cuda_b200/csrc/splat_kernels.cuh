@@ -154,7 +154,7 @@ __global__ void __launch_bounds__(kThreads)
     constexpr int kPerThread = (kFwdStage + kThreads - 1) / kThreads;  // Gaussians a thread stages per pass
     __shared__ __align__(16) float4 s_a[2][kFwdStage];
     __shared__ __align__(16) float4 s_b[2][kFwdStage];
-    __shared__ int s_items[3];  // lengths of the tile's three lists of backward work items
+    __shared__ int s_items;  // length of the tile's list of backward work items
 
     const int tid = threadIdx.x;
     // grid: (tiles of the band) x kParts CTAs, a tile's parts next to each other; tile_order = the tiles by falling list length
@@ -197,11 +197,11 @@ __global__ void __launch_bounds__(kThreads)
     };
     // backward work items (see "backward work items" below); with two CTAs per tile the upper one lists them
     const bool lists_items = kParts == 1 || part == 0;
-    const bool whole = entry_grads != nullptr;  // deterministic mode: every item covers the whole tile
+    const bool by_entry = entry_grads != nullptr;  // deterministic mode: an item is the entry's index (one row per entry)
     const float tx0 = static_cast<float>(tile_x * kTile), ty0 = static_cast<float>(tile_y * kTile);
-    int* const items0 = bwd_items + 2 * static_cast<size_t>(range.x);
+    int* const items0 = bwd_items + range.x;  // the tile's items take the first slots of its range
     const int list_len = range.y - range.x;
-    if (tid < 3) s_items[tid] = 0;  // (the barriers at the top of the loop / after it order this with every use)
+    if (tid == 0) s_items = 0;  // (the barriers at the top of the loop / after it order this with every use)
 
     load_ids(range.x);
     int id_cur[kPerThread];  // ids of the stage being rendered
@@ -223,47 +223,34 @@ __global__ void __launch_bounds__(kThreads)
         __syncthreads();                       // ... and everybody else's
         const float4* __restrict__ sa = s_a[buf];
         const float4* __restrict__ sb = s_b[buf];
-        // the stage's backward work items: min d2 over each half of the tile against the backward cull's bound, on the
-        // staged (kappa-scaled, hence negated) conic
+        // the stage's backward work items: min d2 over the tile against the backward cull's bound, on the staged
+        // (kappa-scaled, hence negated) conic
         if (lists_items) {
 #pragma unroll
             for (int q = 0; q < kPerThread; ++q) {
                 const int t = tid + q * kThreads;
-                int keep = 0;  // bit 0: rows 0..7, bit 1: rows 8..15 hold pixels with d2 <= the bound
+                bool keep = false;
                 if (t < n) {
                     const float4 a = sa[t];
                     const float ia = -a.z, ib = -0.5f * a.w, ic = -sb[t].x;
                     // anything but a positive definite conic of finite numbers is kept (the comparisons fail on NaN)
                     const bool pd = ia > 0.f && ic > 0.f && ia * ic > ib * ib;
-                    const float kx = -ib / ia, ky = -ib / ic;
-                    const float x0 = tx0 - a.x, x1 = x0 + static_cast<float>(kTile - 1), y0 = ty0 - a.y;
-                    const float ym = y0 + static_cast<float>(kTile / 2);
-                    keep = ((pd && conic_min_over_rect(ia, ib, ic, kx, ky, x0, x1, y0, ym - 1.0f) > d2_bwd_scaled) ? 0 : 1) |
-                           ((pd && conic_min_over_rect(ia, ib, ic, kx, ky, x0, x1, ym, ym + static_cast<float>(kTile / 2 - 1)) > d2_bwd_scaled) ? 0 : 2);
-                    if (whole) {
-                        if (keep) {
-                            keep = 3;
-                        } else {  // the per-Gaussian sum reads every entry's row
-                            float* row = entry_grads + static_cast<size_t>(sorted_orig[base + t]) * 9;
+                    const float x0 = tx0 - a.x, y0 = ty0 - a.y;
+                    keep = !(pd && conic_min_over_rect(ia, ib, ic, -ib / ia, -ib / ic, x0, x0 + static_cast<float>(kTile - 1), y0,
+                                                       y0 + static_cast<float>(kTile - 1)) > d2_bwd_scaled);
+                    if (by_entry && !keep) {  // the per-Gaussian sum reads every entry's row
+                        float* row = entry_grads + static_cast<size_t>(sorted_orig[base + t]) * 9;
 #pragma unroll
-                            for (int k = 0; k < 9; ++k) row[k] = 0.f;
-                        }
+                        for (int k = 0; k < 9; ++k) row[k] = 0.f;
                     }
                 }
-                const int item = whole ? base + t : id_cur[q];
+                const unsigned int votes = __ballot_sync(0xffffffffu, keep);
+                if (votes == 0u) continue;
                 const int lane = tid & 31;
-                // list 0: both halves (grows up from slot 0), list 1: rows 0..7 only (grows down from slot len - 1), list 2:
-                // rows 8..15 only (grows up from slot len); an entry is in at most one list
-#pragma unroll
-                for (int l = 0; l < 3; ++l) {
-                    const bool mine = keep == (l == 0 ? 3 : l);
-                    const unsigned int votes = __ballot_sync(0xffffffffu, mine);
-                    if (votes == 0u) continue;
-                    int at = 0;
-                    if (lane == 0) at = atomicAdd(&s_items[l], __popc(votes));
-                    at = __shfl_sync(0xffffffffu, at, 0) + __popc(votes & ((1u << lane) - 1u));
-                    if (mine) items0[l == 0 ? at : (l == 1 ? list_len - 1 - at : list_len + at)] = item;
-                }
+                int at = 0;
+                if (lane == 0) at = atomicAdd(&s_items, __popc(votes));
+                at = __shfl_sync(0xffffffffu, at, 0) + __popc(votes & ((1u << lane) - 1u));
+                if (keep) items0[at] = by_entry ? base + t : id_cur[q];
             }
         }
         XYZ_UNROLL(XYZ_FWD_UNROLL)
@@ -312,24 +299,15 @@ __global__ void __launch_bounds__(kThreads)
     }
     __syncthreads();
     if (lists_items && list_len > 0) {  // (no entries: no records set aside, and with no Gaussians at all no offsets either)
-        // the tile's backward work records: one per kBwdChunk items of a list, in the records the tile scan set aside for
-        // this tile (ceil(len / kBwdChunk) + 2: an entry is in at most one of three lists); the rest of them: none
+        // the tile's backward work records: one per kBwdChunk items, in the ceil(len / kBwdChunk) records the tile scan
+        // set aside for this tile; the rest of them: none
         const int lt = tile - first_tile;
         const int rec0 = chunk_offsets[lt], rec1 = chunk_offsets[lt + 1];
-        const int n0 = s_items[0], n1 = s_items[1], n2 = s_items[2];
-        const int c0 = (n0 + kBwdChunk - 1) / kBwdChunk, c1 = (n1 + kBwdChunk - 1) / kBwdChunk, c2 = (n2 + kBwdChunk - 1) / kBwdChunk;
-        const unsigned int slot0 = 2u * static_cast<unsigned int>(range.x);
+        const int n_items = s_items;
         for (int r = rec0 + tid; r < rec1; r += kThreads) {
-            int k = r - rec0;
-            int4 w = make_int4(-1, -1, -1, -1);
-            if (k < c0) {
-                w = make_int4(tile, static_cast<int>(slot0 + k * kBwdChunk), min(kBwdChunk, n0 - k * kBwdChunk), 0);
-            } else if ((k -= c0) < c1) {
-                w = make_int4(tile, static_cast<int>(slot0 + list_len - 1 - k * kBwdChunk), min(kBwdChunk, n1 - k * kBwdChunk), 1);
-            } else if ((k -= c1) < c2) {
-                w = make_int4(tile, static_cast<int>(slot0 + list_len + k * kBwdChunk), min(kBwdChunk, n2 - k * kBwdChunk), 2);
-            }
-            chunk_info[r] = w;
+            const int first = (r - rec0) * kBwdChunk;
+            chunk_info[r] = first < n_items ? make_int4(tile, range.x + first, min(kBwdChunk, n_items - first), 0)
+                                            : make_int4(-1, -1, -1, -1);
         }
     }
     // loss partial of a half tile: lane i adds its pixels i, i + 32, i + 64, i + 96, then a shuffle tree.  One warp per
@@ -405,8 +383,8 @@ struct RestPair {
 template <bool kMasked>
 __device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_rest, float px0, float py0, float cx,
                                                 float cy, float A2, float B2, float C2, float cs0, float cs1,
-                                                float cs2, float c0, float c1, float c2, int row0, int nrows,
-                                                float (&ac)[3], float (&T)[6]) {
+                                                float cs2, float c0, float c1, float c2, float (&ac)[3],
+                                                float (&T)[6]) {
     const float dx0 = px0 - cx;
     F2 dxs[kTile / 2];  // (px0 - cx) + j: one rounding more than the forward pass
 #pragma unroll
@@ -420,7 +398,7 @@ __device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_r
     const F2 cs0p = f2_pack(cs0, cs0), cs1p = f2_pack(cs1, cs1), cs2p = f2_pack(cs2, cs2);
     const F2 c0p = f2_pack(c0, c0), c1p = f2_pack(c1, c1), c2p = f2_pack(c2, c2);
     XYZ_UNROLL(XYZ_BWD_ROW_UNROLL)
-    for (int r = row0; r < row0 + nrows; ++r) {
+    for (int r = 0; r < kTile; ++r) {
         const float dy = (py0 + static_cast<float>(r)) - cy;
         const float u = B2 * dy;
         const float t = (C2 * dy) * dy;
@@ -479,22 +457,20 @@ __device__ __forceinline__ void entry_tile_pass(const RestPair* __restrict__ s_r
 // The tile lists hold every pair whose weight is not EXACTLY zero (d2 <= 176: 13 sigma), which the forward pass needs for
 // a bit-identical image.  A gradient is an atomically accumulated sum held to 1e-4 of the sum of its terms' magnitudes, and
 // the terms of a pair carry the factor e = exp(-d2 / 2): beyond d2 = d2_bwd (default 48: e < 3.8e-11) they are far below
-// the fp32 resolution of the sums they would join.  So the backward pass works on ITEMS = (list entry, 16 x 8 half of the
-// tile) and leaves out the halves on which min d2 > d2_bwd -- 70 % of the listed pixels at BASELINE's C4.  The forward
-// CTA of a tile has every entry's record in shared memory anyway: it tests the two halves of each entry and appends the
-// entry to one of three lists in the tile's 2 len slots of bwd_items (begin, len: the tile's range in the sorted list):
-// both halves / rows 0..7 only / rows 8..15 only (deterministic mode: whole-tile items for every entry with a surviving
-// half -- one row of entry_grads per entry; rows of entries that are left out are zeroed here).  An item is the Gaussian
-// id (deterministic mode: the entry's index, which leads to the id and to the row).  The order of a list depends on warp
-// timing and never enters a result.  XYZ_FLAG_BWD_ALL_PAIRS / XYZ_FLAG_NO_CULL pass d2_bwd = inf: every entry is a
-// whole-tile item.
+// the fp32 resolution of the sums they would join (splat_common.cuh: kD2Backward).  So the backward pass works on ITEMS =
+// the list entries of a tile on which min d2 over the tile is within the bound -- 35 % of the entries at BASELINE's C4.
+// The forward CTA of a tile has every entry's record in shared memory anyway: it takes the minimum of the conic form over
+// the tile (closed form, conic_min_over_rect) and appends the surviving entries to the tile's slots of bwd_items.  An item
+// is the Gaussian id (deterministic mode: the entry's index, which leads to the id and to the entry's row of
+// entry_grads; rows of entries that are left out are zeroed by the forward pass).  The order of the items depends on warp
+// timing and never enters a result.  XYZ_FLAG_BWD_ALL_PAIRS / XYZ_FLAG_NO_CULL pass d2_bwd = inf: every entry is an item.
+// (Measured: items of 16 x 8 half tiles -- three lists per tile: both halves / upper / lower -- evaluate 14 % fewer
+// pixels and take the same time, 273 against 275 us at C4: more, shorter, emptier CTAs.  Whole tiles it is.)
 //
 // The forward CTA also writes the tile's work records, one per backward CTA:
-//     chunk_info[c] = {tile, slot of the CTA's first item, items (1 .. kBwdChunk), list}     (tile = -1: nothing to do)
-// list 0: both halves hold pixels inside the bound (the thread walks 16 rows; slots ascending), 1: rows 0..7 only (slots
-// DEscending), 2: rows 8..15 only.  The tile scan sets aside ceil(len / kBwdChunk) + 2 records per tile with a non-empty
-// list, so the grid (all records) is an upper bound the host knows without reading anything back; at C4 about half
-// of the CTAs find tile = -1 and leave at once.
+//     chunk_info[c] = {tile, slot of the CTA's first item, items (1 .. kBwdChunk), -}     (tile = -1: nothing to do)
+// The tile scan sets aside ceil(len / kBwdChunk) records per tile, so the grid (all records) is an upper bound the host
+// knows without reading anything back; at C4 two thirds of the CTAs find tile = -1 and leave at once.
 __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
     splat_backward_kernel(SplatView v, const float4* __restrict__ records, const int4* __restrict__ chunk_info,
                           const int* __restrict__ bwd_items, const float4* __restrict__ rest_tiles,
@@ -507,12 +483,11 @@ __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
     const int tile = info.x;
     if (tile < 0) return;
     const bool valid = tid < info.z;
-    const unsigned int slot = static_cast<unsigned int>(info.y) + (info.w == 1 ? -tid : tid);
-    const int item = valid ? __ldg(bwd_items + slot) : 0;
-    const bool whole = entry_grads != nullptr;  // deterministic mode: the item is the entry's index
+    const int item = valid ? __ldg(bwd_items + info.y + tid) : 0;
+    const bool by_entry = entry_grads != nullptr;  // deterministic mode: the item is the entry's index
     const int tile_x = tile % v.tiles_x, tile_y = tile / v.tiles_x;
-    const int row0 = info.w == 2 ? kTile / 2 : 0, nrows = info.w == 0 ? kTile : kTile / 2;
-    for (int p = row0 * kTile + tid; p < (row0 + nrows) * kTile; p += kBwdChunk) {
+#pragma unroll
+    for (int p = tid; p < kTilePixels; p += kBwdChunk) {
         const float4 rest = __ldg(rest_tiles + static_cast<size_t>(tile) * kTilePixels + p);
         float* pair = reinterpret_cast<float*>(&s_rest[p >> 1]) + (p & 1);
         pair[0] = -rest.x;
@@ -527,7 +502,7 @@ __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
     int g = 0;
     float4 r2 = make_float4(0.f, 0.f, 0.f, 0.f);
     if (valid) {
-        g = whole ? sorted_gid[item] : item;
+        g = by_entry ? sorted_gid[item] : item;
         const float4 r0 = __ldg(records + 4 * g), r1 = __ldg(records + 4 * g + 1);
         r2 = __ldg(records + 4 * g + 2);
         cx = r0.x; cy = r0.y; ia = r0.z; ib = r0.w;
@@ -543,9 +518,9 @@ __global__ void __launch_bounds__(kBwdChunk, XYZ_BWD_MINBLOCKS)
             const float A2 = kKappa * ia, B2 = (2.0f * kKappa) * ib, C2 = kKappa * ic;
             const float cs0 = so * c0, cs1 = so * c1, cs2 = so * c2;
             if (all_active)
-                entry_tile_pass<false>(s_rest, px0, py0, cx, cy, A2, B2, C2, cs0, cs1, cs2, c0, c1, c2, row0, nrows, ac, T);
+                entry_tile_pass<false>(s_rest, px0, py0, cx, cy, A2, B2, C2, cs0, cs1, cs2, c0, c1, c2, ac, T);
             else
-                entry_tile_pass<true>(s_rest, px0, py0, cx, cy, A2, B2, C2, cs0, cs1, cs2, c0, c1, c2, row0, nrows, ac, T);
+                entry_tile_pass<true>(s_rest, px0, py0, cx, cy, A2, B2, C2, cs0, cs1, cs2, c0, c1, c2, ac, T);
         }
         // per-pair g_d2 = gamma * t with gamma = -0.5 so
         const float gamma = -0.5f * so;
