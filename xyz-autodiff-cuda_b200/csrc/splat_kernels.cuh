@@ -138,8 +138,11 @@ __device__ __forceinline__ float conic_min_over_rect(float ia, float ib, float i
 constexpr int kFwdStage = 128;  // Gaussians staged per pass
 constexpr int kHalfPixels = kTilePixels / 2;
 
+#ifndef XYZ_FWD_MINBLOCKS
+#define XYZ_FWD_MINBLOCKS 20  // resident whole-tile forward CTAs per SM the register budget is sized for: 48 registers, no spills
+#endif                        // (56 unconstrained = 18 CTAs: 373 us at C4 against 367; 24 CTAs = 40 registers spill: 401)
 template <int kThreads, int kParts>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, kThreads == 64 ? XYZ_FWD_MINBLOCKS : 1)
     splat_forward_kernel(SplatView v, const float4* __restrict__ fwd_records, const int* __restrict__ sorted_gid,
                          const int2* __restrict__ tile_ranges, const float* __restrict__ target,
                          float* __restrict__ output, float* __restrict__ tile_loss, float4* __restrict__ rest_tiles,
