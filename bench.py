@@ -540,7 +540,7 @@ def splat_section(T, args, rank, world, comm, group, gather, sm_mhz):
                  "ms_per_iter": ms_c4, "iteration": "zero_grad + loss reset + launch (fwd + bwd)",
                  "tile_list_entries": stats["entries"], "pairs_per_pass": pairs,
                  "backward_pairs_per_pass": bstats["pairs"], "backward_work_items": bstats["items"],
-                 "backward_cull": "half tiles of an entry with d2 > 48 everywhere (weights < exp(-24) = 3.8e-11) are left out of the "
+                 "backward_cull": "list entries with d2 > 48 on all of their tile (weights < exp(-24) = 3.8e-11) are left out of the "
                                   "gradient sums; image and loss untouched; XYZ_FLAG_BWD_ALL_PAIRS turns it off",
                  "ms_per_iter_backward_all_pairs": ms_c4_all,
                  "pair_evals_per_s": (pairs + bstats["pairs"]) / (ms_c4 / 1e3), "reference_pairs_per_pass": N * W * H,

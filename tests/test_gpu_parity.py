@@ -572,7 +572,7 @@ def test_splat_cull_is_result_preserving_and_deterministic():
 
 
 def test_splat_backward_cull_drops_only_terms_below_fp32_resolution():
-    """The backward pass leaves out (entry, half tile) items with d2 > 48 everywhere (weights below exp(-24)).  In
+    """The backward pass leaves out the list entries with d2 > 48 on all of their tile (weights below exp(-24)).  In
     deterministic mode every kept entry is computed by the same instructions with and without the cull, so the difference
     between the two IS the dropped terms: below 1e-8 of the sum of |terms| (the tail integral of the largest coefficient,
     d2 exp(-d2 / 2) beyond 48, is 1e-9 of its total) -- which can still move the rounding of an fp32 sum by its last bit,
