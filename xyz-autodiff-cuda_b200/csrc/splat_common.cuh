@@ -10,12 +10,14 @@
 //   2. integer work: per-tile lists of Gaussian ids, each ascending (= the reference's summation
 //      order), built by a stable counting sort by tile (splat_host.cu section 2b) or, for more than
 //      57 344 tiles per row band, (tile, Gaussian) keys + a stable radix sort; per-tile [begin, end) ranges;
-//   3. splat_forward_kernel  : one CTA per tile, four pixels per thread, records staged in shared
-//      memory; writes the image and one loss partial per tile;
-//   4. splat_backward_kernel : one THREAD per (tile, Gaussian) list entry looping over the tile's
-//      256 pixels (pixel residuals broadcast from shared memory), 9 adjoint sums in registers,
-//      the per-Gaussian chain rule applied once per entry, then 9 REDs (or a partial row in
-//      deterministic mode) -- instead of 9 atomics per PAIR.
+//   3. splat_forward_kernel  : one CTA per tile (longest list first), four pixels per thread, records
+//      staged in shared memory; writes the image, one loss partial per half tile, the residuals for the
+//      backward pass -- and lists the backward work items: the tile's entries that reach a weight of
+//      exp(-24) somewhere on the tile (kD2Backward below; everything else is left out of the gradient sums);
+//   4. splat_backward_kernel : one THREAD per work item looping over the tile's 256 pixels (pixel
+//      residuals broadcast from shared memory), 9 adjoint sums in registers, the per-Gaussian chain
+//      rule applied once per item, then 9 REDs (or a partial row in deterministic mode) -- instead
+//      of 9 atomics per PAIR.
 #pragma once
 
 #include "common.cuh"
