@@ -530,6 +530,18 @@ def splat_section(T, args, rank, world, comm, group, gather, sm_mhz):
         for k, v in x.splat_last_timing().items():
             stage[k] += v / 5
     pairs = stats["pairs_per_pass"]
+    # the same iteration through the workspace entry point: nothing allocates, nothing waits (the classic call reads the
+    # list length back between the scans and the scatter: the GPU idles for one host round trip)
+    ws = x.SplatWorkspace(W, H, N, int(stats["entries"] * 1.3), 0)
+
+    def c4_iter_ws(i):
+        x.zero_gradients(grads)
+        loss.zero_()
+        ws.launch(tp, grads, tt, img, loss)
+
+    ms_c4_ws = T.loop(c4_iter_ws, steps)
+    assert not ws.status()["overflowed"]
+    del ws
     # the training iteration (zero-grad fused into Adam) as ONE CUDA graph on a workspace
     tr = par.ShardedSplatTrainer(x, tp, [tt], W, H, exchange="peer", group=x.PeerGroup(0, 1, lambda h: [h]),
                                  gather=lambda h: [h], max_entries=int(stats["entries"] * 1.3))
@@ -543,6 +555,7 @@ def splat_section(T, args, rank, world, comm, group, gather, sm_mhz):
                  "backward_cull": "list entries with d2 > 48 on all of their tile (weights < exp(-24) = 3.8e-11) are left out of the "
                                   "gradient sums; image and loss untouched; XYZ_FLAG_BWD_ALL_PAIRS turns it off",
                  "ms_per_iter_backward_all_pairs": ms_c4_all,
+                 "ms_per_iter_workspace_launch": ms_c4_ws,
                  "pair_evals_per_s": (pairs + bstats["pairs"]) / (ms_c4 / 1e3), "reference_pairs_per_pass": N * W * H,
                  "stage_us": stage,
                  "ms_per_training_iter_one_cuda_graph": ms_graph,
