@@ -237,3 +237,36 @@ def test_lsq_shipped_example_graph_closed_form():
     want = np.array([len(data), (v * v).sum(), (2 * b * v).sum(), len(data)])
     assert np.allclose(g, want, rtol=1e-12)
     assert np.isclose(l, ((a - data[:, 0]) + b * v * v + d - data[:, 2]).sum(), rtol=1e-12)
+
+
+def test_conic_min_over_rect_closed_form():
+    """The backward cull (csrc/splat_kernels.cuh: conic_min_over_rect) keeps a list entry when the minimum of
+    q = ia dx^2 + 2 ib dx dy + ic dy^2 over the tile's pixel rectangle is within the bound.  The closed form used there --
+    0 if the centre lies inside, else the smallest of the four edge minima with the parabola's vertex clamped to the edge
+    -- restated here in numpy: it must be a lower bound of q over the rectangle's pixels (so no pixel within the bound is
+    ever dropped) and equal the minimum over a dense sampling of the rectangle."""
+    rng = np.random.default_rng(11)
+
+    def closed_form(ia, ib, ic, x0, x1, y0, y1):
+        if x0 <= 0 <= x1 and y0 <= 0 <= y1:
+            return 0.0
+        q = lambda dx, dy: ia * dx * dx + 2 * ib * dx * dy + ic * dy * dy
+        kx, ky = -ib / ia, -ib / ic
+        return min(q(min(max(kx * y0, x0), x1), y0), q(min(max(kx * y1, x0), x1), y1),
+                   q(x0, min(max(ky * x0, y0), y1)), q(x1, min(max(ky * x1, y0), y1)))
+
+    for _ in range(400):
+        s0, s1, th = np.exp(rng.uniform(-1, 2.3)), np.exp(rng.uniform(-1, 2.3)), rng.uniform(-np.pi, np.pi)
+        R = np.array([[np.cos(th), -np.sin(th)], [np.sin(th), np.cos(th)]]) @ np.diag([s0, s1])
+        inv = np.linalg.inv(R @ R.T)
+        ia, ib, ic = inv[0, 0], inv[0, 1], inv[1, 1]
+        cx, cy = rng.uniform(-40, 60, 2)
+        x0, y0 = -cx, -cy                                   # a 16 x 16 tile at the origin, relative to the centre
+        m = closed_form(ia, ib, ic, x0, x0 + 15, y0, y0 + 15)
+        px, py = np.meshgrid(x0 + np.arange(16), y0 + np.arange(16))
+        q_pixels = ia * px * px + 2 * ib * px * py + ic * py * py
+        assert m <= q_pixels.min() * (1 + 1e-12) + 1e-12
+        fx, fy = np.meshgrid(np.linspace(x0, x0 + 15, 301), np.linspace(y0, y0 + 15, 301))
+        q_dense = ia * fx * fx + 2 * ib * fx * fy + ic * fy * fy
+        assert m <= q_dense.min() + 1e-9 and abs(m - q_dense.min()) <= 2e-2 * max(q_dense.min(), 1.0)
+
