@@ -120,9 +120,13 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // summation order are the same in every configuration: the image is bit-identical (tested).
 // The loss partial is kept per HALF tile (tile_loss[2 tile + half], each a fixed tree over its 128 pixels), so the sum
 // the last CTA forms over the launch's half tiles has the same bits in every configuration too.
+// The CTAs run longest list first (tile_order, from the tile scan), and the CTA of a tile (its upper half with two
+// CTAs per tile) also lists the backward work items of the tile: see "backward work items" below.
+
 // Smallest value of the conic form q(dx, dy) = ia dx^2 + 2 ib dx dy + ic dy^2 (positive definite) over the pixel
 // rectangle [x0, x1] x [y0, y1] given relative to the Gaussian's centre: 0 when the centre lies inside, else the smallest
-// of the four edge minima (q is convex; on an edge it is a parabola whose vertex is clamped to the edge).
+// of the four edge minima (q is convex; on an edge it is a parabola whose vertex is clamped to the edge).  A lower bound
+// of q over the rectangle's pixels (tests/test_oracle.py restates it against a dense sampling).
 __device__ __forceinline__ float conic_min_over_rect(float ia, float ib, float ic, float kx, float ky, float x0, float x1,
                                                      float y0, float y1) {
     if (x0 <= 0.f && x1 >= 0.f && y0 <= 0.f && y1 >= 0.f) return 0.f;
