@@ -594,6 +594,26 @@ def test_splat_backward_cull_drops_only_terms_below_fp32_resolution():
             assert (np.abs(g_atomic - g_all) <= tol).all()
 
 
+def test_splat_backward_stats_count_the_work_items():
+    """xyz_splat_last_backward_stats: with XYZ_FLAG_BWD_ALL_PAIRS every list entry is a work item; with the default cull
+    fewer; every item stands for a whole tile of pairs; the classic and the workspace entry point agree."""
+    W, H, N = 256, 192, 300
+    params, target = orc.splat_scene(N, W, H, seed=5, small=False)
+    run_splat(params, target, W, H, x.FLAG_BWD_ALL_PAIRS)
+    entries = x.splat_last_stats()["entries"]
+    b_all = x.splat_last_backward_stats()
+    assert b_all["items"] == entries and b_all["pairs"] == 256 * entries and b_all["ctas"] >= (entries + 127) // 128
+    run_splat(params, target, W, H, 0)
+    b_cut = x.splat_last_backward_stats()
+    assert 0 < b_cut["items"] < entries and b_cut["pairs"] == 256 * b_cut["items"]
+    ws = x.SplatWorkspace(W, H, N, entries + 64, 0)
+    run_splat_ws(ws, params, target, W, H)
+    torch.cuda.synchronize()
+    assert x.splat_last_backward_stats() == b_cut
+    run_splat(params, target, W, H, x.FLAG_DETERMINISTIC)
+    assert x.splat_last_backward_stats()["items"] == b_cut["items"]
+
+
 def test_splat_tail_cull_stays_inside_the_stated_bound():
     """XYZ_FLAG_TAIL_CULL (opt-in) drops pairs with weight < exp(-28): the image moves by at most
     N * exp(-28) * max|sigmoid(opacity) * color| and the result still meets the fp64 tolerances."""
