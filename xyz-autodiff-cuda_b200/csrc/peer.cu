@@ -156,8 +156,12 @@ __global__ void __launch_bounds__(kPeerAdamThreads)
         const float c = sqrtf(1.0f - b2t) / (1.0f - b1t);
         s_lr[0] = lr0 * c; s_lr[1] = lr1 * c; s_lr[2] = lr2 * c; s_lr[3] = lr3 * c; s_lr[4] = lr4 * c;
     }
+    // A group of ONE rank has nobody to wait for and nothing to publish: no flags, no system-scope fences (ncu: the two
+    // rounds and their three membar.sys cost ~25 of this kernel's 35 us, whatever the number of ranks) -- the kernel is
+    // then the Adam step with the zero-gradient pass fused in.
+    const bool alone = W == 1;
     // ---- round 1: gradients (and the loss) of every rank are complete
-    if (blockIdx.x == 0) {
+    if (blockIdx.x == 0 && !alone) {
         if (tid == 0 && total_loss) {
             const double mine = static_cast<double>(*total_loss);
             for (int p = 0; p < W; ++p) pa.box[p]->loss_splat[par][R] = mine;
@@ -167,7 +171,7 @@ __global__ void __launch_bounds__(kPeerAdamThreads)
         if (tid < W) st_release_sys(&pa.box[tid]->flag_splat[R], seq);
     }
     __syncthreads();
-    if (tid < W) {
+    if (tid < W && !alone) {
         const unsigned long long* f = &me->flag_splat[tid];
         const unsigned long long t0 = global_timer_ns();
         while (ld_acquire_sys(f) < seq) {
@@ -179,7 +183,7 @@ __global__ void __launch_bounds__(kPeerAdamThreads)
     }
     __syncthreads();
     const bool ok = s_ok != 0;
-    if (blockIdx.x == 0 && tid == 0 && total_loss) {
+    if (blockIdx.x == 0 && tid == 0 && total_loss && !alone) {
         double s = 0.0;
         for (int q = 0; q < W; ++q) s += ld_relaxed_sys_f64(&me->loss_splat[par][q]);  // rank order: same bits everywhere
         *total_loss = ok ? static_cast<float>(s) : __int_as_float(0x7fc00000);
@@ -232,18 +236,19 @@ __global__ void __launch_bounds__(kPeerAdamThreads)
     // before it, and fences are cumulative (a membar.sys in all 256 threads costs microseconds per CTA).
     __syncthreads();
     if (tid == 0) {
-        __threadfence_system();
+        if (alone) __threadfence();
+        else __threadfence_system();
         s_last = atomicAdd(ticket, 1u) == gridDim.x - 1;
     }
     __syncthreads();
     if (!s_last) return;
-    __threadfence_system();
+    if (!alone) __threadfence_system();
     if (tid == 0) {
         *ticket = 0u;  // ready for the next launch
         me->splat_seq = seq + 1ull;
         me->splat_iter = me->splat_iter + 1ull;
     }
-    if (tid < W) {
+    if (tid < W && !alone) {
         st_release_sys(&pa.box[tid]->flag_splat[R], seq + 1ull);
         const unsigned long long* f = &me->flag_splat[tid];
         const unsigned long long t0 = global_timer_ns();
