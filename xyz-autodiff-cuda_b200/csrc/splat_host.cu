@@ -160,43 +160,43 @@ __global__ void __launch_bounds__(256)
                 }
             }
             if (!misses_band) {
-            const float ct = cosf(p.rotation[0]), sn = sinf(p.rotation[0]);
-            const float m00 = __fmul_rn(es0, ct), m01 = __fmul_rn(-es1, sn), m10 = __fmul_rn(es0, sn), m11 = __fmul_rn(es1, ct);
-            const float A = __fadd_rn(__fmul_rn(m00, m00), __fmul_rn(m01, m01));
-            const float B = __fadd_rn(__fmul_rn(m00, m10), __fmul_rn(m01, m11));
-            const float C = __fadd_rn(__fmul_rn(m10, m10), __fmul_rn(m11, m11));
-            float det = __fsub_rn(__fmul_rn(A, C), __fmul_rn(B, B));
-            if (fabsf(det) < 1e-8f) det = 1e-8f;
-            const float inv_det = __fdiv_rn(1.0f, det);
-            const float ia = __fmul_rn(C, inv_det), ib = __fmul_rn(-B, inv_det), ic = __fmul_rn(A, inv_det);
-            const float so = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-p.opacity[0])));
-            records[4 * g] = make_float4(p.center[0], p.center[1], ia, ib);
-            records[4 * g + 1] = make_float4(ic, so, p.color[0], p.color[1]);
-            // exp(scale), cos and sin ride along for the backward pass: its per-Gaussian chain rule is applied at exactly
-            // the Sigma the forward pass used, in both math flavours (this translation unit is always IEEE)
-            records[4 * g + 2] = make_float4(p.color[2], es0, es1, ct);
-            records[4 * g + 3] = make_float4(sn, 0.f, 0.f, 0.f);
-            // what the forward pass stages per Gaussian, ready to copy (cp.async): the conic pre-scaled by
-            // kappa (-0.5 log2(e) for the fast-math flavour's ex2, -0.5 for expf) and the colours by sigmoid(opacity)
-            fwd_records[2 * g] = make_float4(p.center[0], p.center[1], __fmul_rn(kappa, ia), __fmul_rn(2.0f * kappa, ib));
-            fwd_records[2 * g + 1] = make_float4(__fmul_rn(kappa, ic), __fmul_rn(so, p.color[0]), __fmul_rn(so, p.color[1]),
-                                                 __fmul_rn(so, p.color[2]));
-            r = gaussian_tile_rect(p.center[0], p.center[1], ia, ib, ic, v, d2max, no_cull);
-            rects[g] = r;
-            // (a rectangle that misses the image / the row band is empty: no spans to derive -- 7 of 8 Gaussians when
-            // one image is split over 8 GPUs)
-            if (r.w > r.y && r.z > r.x) sc = span_coef(p.center[0], p.center[1], ia, ib, ic, d2max, no_cull);
-            big_one = static_cast<unsigned int>((r.z - r.x) * (r.w - r.y)) > kBigGaussian;
-            for (int ty = r.y; ty < r.w; ++ty) {
-                const int2 s = tile_row_span(sc, r, ty, v);
-                cnt += static_cast<unsigned int>(max(s.y - s.x, 0));
-                // the first kSpanRows rows are kept for the binning kernels (rows beyond that are recomputed there)
-                if (ty - r.y < kSpanRows) spans[static_cast<size_t>(g) * kSpanRows + (ty - r.y)] = make_int2(s.x, max(s.y, s.x));
-                if (kCount && !big_one)
-                    for (int tx = s.x; tx < s.y; ++tx) atomicAdd(&s_cnt[(ty - ty_lo) * v.tiles_x + tx], 1u);
-            }
-            touched[g] = cnt;
-            my_total += cnt;
+                const float ct = cosf(p.rotation[0]), sn = sinf(p.rotation[0]);
+                const float m00 = __fmul_rn(es0, ct), m01 = __fmul_rn(-es1, sn), m10 = __fmul_rn(es0, sn), m11 = __fmul_rn(es1, ct);
+                const float A = __fadd_rn(__fmul_rn(m00, m00), __fmul_rn(m01, m01));
+                const float B = __fadd_rn(__fmul_rn(m00, m10), __fmul_rn(m01, m11));
+                const float C = __fadd_rn(__fmul_rn(m10, m10), __fmul_rn(m11, m11));
+                float det = __fsub_rn(__fmul_rn(A, C), __fmul_rn(B, B));
+                if (fabsf(det) < 1e-8f) det = 1e-8f;
+                const float inv_det = __fdiv_rn(1.0f, det);
+                const float ia = __fmul_rn(C, inv_det), ib = __fmul_rn(-B, inv_det), ic = __fmul_rn(A, inv_det);
+                const float so = __fdiv_rn(1.0f, __fadd_rn(1.0f, expf(-p.opacity[0])));
+                records[4 * g] = make_float4(p.center[0], p.center[1], ia, ib);
+                records[4 * g + 1] = make_float4(ic, so, p.color[0], p.color[1]);
+                // exp(scale), cos and sin ride along for the backward pass: its per-Gaussian chain rule is applied at exactly
+                // the Sigma the forward pass used, in both math flavours (this translation unit is always IEEE)
+                records[4 * g + 2] = make_float4(p.color[2], es0, es1, ct);
+                records[4 * g + 3] = make_float4(sn, 0.f, 0.f, 0.f);
+                // what the forward pass stages per Gaussian, ready to copy (cp.async): the conic pre-scaled by
+                // kappa (-0.5 log2(e) for the fast-math flavour's ex2, -0.5 for expf) and the colours by sigmoid(opacity)
+                fwd_records[2 * g] = make_float4(p.center[0], p.center[1], __fmul_rn(kappa, ia), __fmul_rn(2.0f * kappa, ib));
+                fwd_records[2 * g + 1] = make_float4(__fmul_rn(kappa, ic), __fmul_rn(so, p.color[0]), __fmul_rn(so, p.color[1]),
+                                                     __fmul_rn(so, p.color[2]));
+                r = gaussian_tile_rect(p.center[0], p.center[1], ia, ib, ic, v, d2max, no_cull);
+                rects[g] = r;
+                // (a rectangle that misses the image / the row band is empty: no spans to derive -- 7 of 8 Gaussians when
+                // one image is split over 8 GPUs)
+                if (r.w > r.y && r.z > r.x) sc = span_coef(p.center[0], p.center[1], ia, ib, ic, d2max, no_cull);
+                big_one = static_cast<unsigned int>((r.z - r.x) * (r.w - r.y)) > kBigGaussian;
+                for (int ty = r.y; ty < r.w; ++ty) {
+                    const int2 s = tile_row_span(sc, r, ty, v);
+                    cnt += static_cast<unsigned int>(max(s.y - s.x, 0));
+                    // the first kSpanRows rows are kept for the binning kernels (rows beyond that are recomputed there)
+                    if (ty - r.y < kSpanRows) spans[static_cast<size_t>(g) * kSpanRows + (ty - r.y)] = make_int2(s.x, max(s.y, s.x));
+                    if (kCount && !big_one)
+                        for (int tx = s.x; tx < s.y; ++tx) atomicAdd(&s_cnt[(ty - ty_lo) * v.tiles_x + tx], 1u);
+                }
+                touched[g] = cnt;
+                my_total += cnt;
             }
         }
         if (kCount) {
