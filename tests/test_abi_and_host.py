@@ -89,6 +89,83 @@ def test_sharding_helpers():
     assert par.views_for_rank(8, 1, 4) == [1, 5] and sum(len(par.views_for_rank(8, r, 3)) for r in range(3)) == 8
 
 
+def test_balanced_row_bands_partition_is_valid_and_minimises_the_largest_band():
+    """parallel.balanced_row_bands against a dynamic-programming optimum of the same contiguous partition problem."""
+    import random
+    from importlib import import_module
+    par = import_module("xyz_autodiff_cuda_b200.parallel")
+
+    def optimum(cost, world):
+        n, pre = len(cost), [0.0]
+        for c in cost:
+            pre.append(pre[-1] + c)
+        dp = [[float("inf")] * (n + 1) for _ in range(world + 1)]
+        dp[0][0] = 0.0
+        for k in range(1, world + 1):
+            for i in range(n + 1):
+                dp[k][i] = min([dp[k - 1][i]] + [max(dp[k - 1][j], pre[i] - pre[j]) for j in range(i)])
+        return dp[world][n]
+
+    rng = random.Random(3)
+    for trial in range(400):
+        n, world = rng.randint(1, 20), rng.choice([1, 2, 3, 4, 8])
+        h = n * 16 - rng.randint(0, 15)
+        kind = trial % 4
+        cost = ([rng.randint(0, 5) for _ in range(n)], [rng.random() * 100 for _ in range(n)],
+                [rng.choice([0, 0, 1000, 3]) for _ in range(n)], [0] * n)[kind]
+        b = par.balanced_row_bands(cost, h, world)
+        assert len(b) == world and b[0][0] == 0 and b[-1][1] == h
+        assert all(p[1] == q[0] for p, q in zip(b, b[1:])) and all(p[0] <= p[1] for p in b)
+        assert all(p[0] % 16 == 0 or p[0] == h for p in b)           # tile aligned (empty bands sit at the end)
+        largest = max(sum(cost[p[0] // 16:(p[1] + 15) // 16]) for p in b)
+        assert largest <= optimum(cost, world) * (1 + 1e-6) + 1e-9, (cost, world, b)
+    with pytest.raises(ValueError):
+        par.balanced_row_bands([1, 2, 3], 1024, 2)                    # one cost per tile row expected
+
+
+def test_splat_workspace_size_query_is_host_arithmetic():
+    """xyz_splat_workspace_bytes needs no GPU: sizes grow with the list bound, the deterministic flag adds its rows per
+    entry, a row band needs less than the whole image, and what the workspace launch cannot do asks for 0 bytes."""
+    L = x.lib()
+    f = L.xyz_splat_workspace_bytes
+    full = f(1024, 1024, 100_000, 0, 1024, 4_200_000, 0)
+    assert full > 0 and full % 256 == 0
+    more = f(1024, 1024, 100_000, 0, 1024, 8_400_000, 0)
+    per_entry = (more - full) / 4_200_000
+    assert 8.0 <= per_entry <= 8.5                                    # 4 B list + 4 B backward item (+ work records)
+    det = f(1024, 1024, 100_000, 0, 1024, 4_200_000, x.FLAG_DETERMINISTIC)
+    assert 39.9 <= (det - full) / 4_200_000 <= 40.3                   # + 4 B ids + 36 B gradient row per entry
+    band = f(1024, 1024, 100_000, 0, 128, 4_200_000, 0)
+    assert 0 < band < full
+    assert f(1024, 1024, 100_000, 512, 512, 100, 0) > 0                # an empty band is a valid (empty) launch
+    assert f(1024, 1024, 0, 0, 1024, 0, 0) > 0
+    assert f(1024, 1024, 100_000, 0, 1024, 4_200_000, x.FLAG_RADIX_BINNING) == 0
+    assert f(16384, 16384, 10, 0, 16384, 100, 0) == 0                 # more than 57 344 tiles in the band
+    assert f(0, 1024, 10, 0, 1024, 10, 0) == 0 and f(1024, 1024, 10, 0, 1025, 10, 0) == 0
+    assert f(1024, 1024, 10, 8, 4, 10, 0) == 0 and f(1024, 1024, 10, 0, 1024, -1, 0) == 0
+    assert f(1024, 1024, 10, 0, 1024, 1 << 31, 0) == 0
+
+
+def test_entry_points_reject_bad_arguments_before_any_cuda_call():
+    """Argument errors are reported as XYZ_ERR_INVALID_ARGUMENT (-1) / XYZ_ERR_NOT_INITIALISED (-3) by host code alone."""
+    L = x.lib()
+    null = ctypes.c_void_p(0)
+    four = (ctypes.c_longlong * 4)()
+    assert L.xyz_launch_gaussian_splatting_ws(null, null, null, null, null, 16, 16, 0, 0, 16, null, 0, 0, null, 0) == -1
+    assert L.xyz_splat_workspace_init(null, 4096, null) == -1
+    assert L.xyz_splat_workspace_status(null, null, four) == -1
+    assert L.xyz_splat_last_stats(None) == -3
+    assert L.xyz_comm_rank(null) == -1 and L.xyz_comm_world(null) == -1
+    assert L.xyz_comm_destroy(null) == 0
+    assert L.xyz_allreduce_grads(null, null, 9, null) == -1
+    assert L.xyz_allreduce_f64(null, null, 1, null) == -1
+    lr = (ctypes.c_float * 5)(1e-3, 1e-3, 1e-3, 1e-3, 1e-3)
+    assert L.xyz_adam_step_individual_sharded(null, null, null, null, 10, lr, 0.9, 0.999, 1e-8, 1, null, null) == -1
+    assert L.xyz_comm_init_rank(null, None, 0, 1) == -1
+    assert L.xyz_comm_init_all(null, 0, None) == -1
+    assert L.xyz_comm_unique_id(None) == -1
+
+
 WORKER = r'''
 import os, sys
 import numpy as np, torch, torch.distributed as dist
