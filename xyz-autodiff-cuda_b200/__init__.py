@@ -240,21 +240,21 @@ def lsq_grad_allreduce(data: torch.Tensor, params: torch.Tensor, group: PeerGrou
     """lsq_grad on this rank's points, with the sum over all ranks of the 4 gradients (+ loss) done inside the
     kernel over NVLink peer memory: params.grad += global sum on every rank (bit-identical)."""
     n = data.shape[0]
-    dp = _dev(data, torch.float64, "data") if n > 0 else None
-    _check(lib().xyz_lsq_grad_f64_allreduce(dp, n, _dev(params, torch.float64, "params"),
-                                            _dev(loss_sum, torch.float64, "loss_sum") if loss_sum is not None else None,
+    dp = _dev(data, torch.float64, "data", 3 * n) if n > 0 else None
+    _check(lib().xyz_lsq_grad_f64_allreduce(dp, n, _dev(params, torch.float64, "params", 8),
+                                            _dev(loss_sum, torch.float64, "loss_sum", 1) if loss_sum is not None else None,
                                             ctypes.byref(group.struct), group.next_seq(), _stream(stream), flags),
            "xyz_lsq_grad_f64_allreduce")
 
 
 def lsq_sgd_update(params: torch.Tensor, lr: float, batch: int, stream=None) -> None:
-    _check(lib().xyz_lsq_sgd_update_f64(_dev(params, torch.float64, "params"), lr, batch, _stream(stream)),
+    _check(lib().xyz_lsq_sgd_update_f64(_dev(params, torch.float64, "params", 8), lr, batch, _stream(stream)),
            "xyz_lsq_sgd_update_f64")
 
 
 def lsq_select_batch(data: torch.Tensor, batch: torch.Tensor, seed: int, epoch: int, stream=None) -> None:
-    _check(lib().xyz_lsq_select_batch(_dev(data, torch.float64, "data"), data.shape[0],
-                                      _dev(batch, torch.float64, "batch"), batch.shape[0], seed, epoch,
+    _check(lib().xyz_lsq_select_batch(_dev(data, torch.float64, "data", 3 * data.shape[0]), data.shape[0],
+                                      _dev(batch, torch.float64, "batch", 3 * batch.shape[0]), batch.shape[0], seed, epoch,
                                       _stream(stream)), "xyz_lsq_select_batch")
 
 
@@ -262,9 +262,9 @@ def lsq_sgd_step(data: torch.Tensor, params: torch.Tensor, batch: int, seed: int
                  loss_sum: Optional[torch.Tensor] = None, flags: int = 0, stream=None) -> None:
     """One SGD epoch in one launch: sample the batch (same hash as lsq_select_batch), params.grad = batch gradient,
     params.value -= lr * grad / batch."""
-    _check(lib().xyz_lsq_sgd_step_f64(_dev(data, torch.float64, "data"), data.shape[0],
-                                      _dev(params, torch.float64, "params"), batch, seed, epoch, lr,
-                                      _dev(loss_sum, torch.float64, "loss_sum") if loss_sum is not None else None,
+    _check(lib().xyz_lsq_sgd_step_f64(_dev(data, torch.float64, "data", 3 * data.shape[0]), data.shape[0],
+                                      _dev(params, torch.float64, "params", 8), batch, seed, epoch, lr,
+                                      _dev(loss_sum, torch.float64, "loss_sum", 1) if loss_sum is not None else None,
                                       _stream(stream), flags), "xyz_lsq_sgd_step_f64")
 
 
@@ -274,9 +274,9 @@ def lsq_sgd_run(data: torch.Tensor, params: torch.Tensor, batch: int, seed: int,
     bit-identical to calling lsq_sgd_step once per epoch."""
     lrs = [float(v) for v in learning_rates]
     arr = (ctypes.c_double * len(lrs))(*lrs)
-    _check(lib().xyz_lsq_sgd_run_f64(_dev(data, torch.float64, "data"), data.shape[0],
-                                     _dev(params, torch.float64, "params"), batch, seed, epoch_begin, len(lrs), arr,
-                                     _dev(loss_sum, torch.float64, "loss_sum") if loss_sum is not None else None,
+    _check(lib().xyz_lsq_sgd_run_f64(_dev(data, torch.float64, "data", 3 * data.shape[0]), data.shape[0],
+                                     _dev(params, torch.float64, "params", 8), batch, seed, epoch_begin, len(lrs), arr,
+                                     _dev(loss_sum, torch.float64, "loss_sum", 1) if loss_sum is not None else None,
                                      _stream(stream), flags), "xyz_lsq_sgd_run_f64")
 
 
@@ -303,7 +303,7 @@ def accumulate_allreduce(idx: Optional[torch.Tensor], val: torch.Tensor, grad: t
     n, k = val.numel(), grad.numel()
     if idx is None:
         flags |= FLAG_IMPLICIT_IDS
-    ip = _dev(idx, torch.int32, "idx") if (idx is not None and n > 0) else None
+    ip = _dev(idx, torch.int32, "idx", n) if (idx is not None and n > 0) else None
     vp = _dev(val, torch.float32, "val") if n > 0 else None
     _check(lib().xyz_accumulate_f32_allreduce(ip, vp, n, _dev(grad, torch.float32, "grad"), k,
                                               ctypes.byref(group.struct), group.next_seq(), _stream(stream), flags),
@@ -557,7 +557,8 @@ class PeerSplat:
         iteration=0: the step number is counted on the device (for replayed CUDA graphs)."""
         lr = (ctypes.c_float * 5)(lr_center, lr_scale, lr_rotation, lr_color, lr_opacity)
         _check(lib().xyz_adam_step_individual_peer(
-            ctypes.byref(self.group.struct), ctypes.byref(self.struct), _dev(self.adam, torch.float32, "adam"), self.n,
+            ctypes.byref(self.group.struct), ctypes.byref(self.struct),
+            _dev(self.adam, torch.float32, "adam", ADAM_FLOATS * self.n), self.n,
             lr, beta1, beta2, epsilon, iteration,
             _dev(total_loss, torch.float32, "total_loss", 1) if total_loss is not None else None, _stream(stream)),
             "xyz_adam_step_individual_peer")
