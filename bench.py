@@ -49,6 +49,7 @@ METRIC = "fwd+bwd gradient evals/sec"
 UNIT = "evals/s"
 COVPROJ_BYTES = 192  # per eval: in J6 W9 S6 g3, out out3 gJ6 gW9 gS6, fp32
 FULL_E = 1 << 26
+WORKLOAD = "covproj_fwd_bwd 3x3 chain S'=(JW)S(JW)^T fwd+bwd (BASELINE configs[2])"  # both arms name it identically
 SM_COUNT = 148
 FMA_LANES_PER_SM = 128      # fp32 lanes of the FMA pipe per SM per clock
 MUFU_PER_SM = 16            # special-function results per SM per clock
@@ -167,8 +168,9 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "covproj_fwd_bwd 3x3 chain S'=(JW)S(JW)^T, 2^26 elems (BASELINE configs[2]); "
-                                   "each step = a bounded sample of 2^23 elements on the host cores"},
+            "config": {"workload": WORKLOAD, "elems_per_gpu": args.elems, "bytes_per_eval": COVPROJ_BYTES,
+                       "sample": f"each step = a bounded sample of {sample} of the {args.elems} elements on the host cores "
+                                 "(evals/s is size-normalised)"},
             "cpu_baseline": base,
             "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     try:
@@ -908,7 +910,7 @@ def run_ours(args):
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic",
-            "config": {"workload": "covproj_fwd_bwd 3x3 chain S'=(JW)S(JW)^T fwd+bwd (BASELINE configs[2])",
+            "config": {"workload": WORKLOAD,
                        "elems_per_gpu": E, "bytes_per_eval": COVPROJ_BYTES, "l2": "inputs larger than L2 "
                        f"({COVPROJ_BYTES * E / 1e9:.1f} GB per step per GPU)", "parallelism": f"dp{world} by element range, no collective"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak_gbs, "unit": "GB/s", "frac": achieved / peak_gbs,
