@@ -532,6 +532,24 @@ def splat_section(T, args, rank, world, comm, group, gather, sm_mhz):
         for k, v in x.splat_last_timing().items():
             stage[k] += v / 5
     pairs = stats["pairs_per_pass"]
+    # opt-in XYZ_FLAG_TAIL_CULL (N = 1 only; not the default, not the parity path): lists without the pairs whose weight is
+    # below exp(-28).  Reported next to the default with the measured change of the image, so that the price of the
+    # result-preserving default (lists out to the exact-zero bound d2 = 176) is a number.  Failure here loses only this key.
+    tail = None
+    if world == 1:
+        try:
+            img_default = img.clone()  # the image of the default launch (the stage-timing launches above)
+            ms_tail = T.loop(lambda i: c4_iter(i, x.FLAG_TAIL_CULL), steps)
+            tstats = x.splat_last_stats()
+            moved = float((img - img_default).abs().max())
+            tail = {"ms_per_iter": ms_tail, "tile_list_entries": tstats["entries"], "pairs_per_pass": tstats["pairs_per_pass"],
+                    "max_abs_image_change": moved, "max_abs_image_value": float(img_default.abs().max()),
+                    "stated_bound": float(N * np.exp(-28.0) * np.abs(params[:, 5:8]).max()),
+                    "note": "opt-in flag, bounded error (tests/test_gpu_parity.py::test_splat_tail_cull_stays_inside_the_stated_"
+                            "bound); every other splat figure of this line is the default, result-preserving cull"}
+            c4_iter(0, 0)  # leave the default launch's lists and statistics behind
+        except Exception as ex:
+            tail = {"error": repr(ex)}
     # the same iteration through the workspace entry point: nothing allocates, nothing waits (the classic call reads the
     # list length back between the scans and the scatter: the GPU idles for one host round trip)
     ws = x.SplatWorkspace(W, H, N, int(stats["entries"] * 1.3), 0)
@@ -562,6 +580,8 @@ def splat_section(T, args, rank, world, comm, group, gather, sm_mhz):
                  "stage_us": stage,
                  "ms_per_training_iter_one_cuda_graph": ms_graph,
                  "graph": "loss reset + workspace launch + Adam with fused zero-grad, captured once, replayed"}
+    if tail is not None:
+        cfg["c4"]["tail_cull_opt_in"] = tail
     clk = sm_mhz * 1e6
     fwd_floor = pairs / (MUFU_PER_SM * SM_COUNT * clk) * 1e3
     bwd_floor = bstats["pairs"] * BWD_FMA_OPS_PER_PAIR / (FMA_LANES_PER_SM * SM_COUNT * clk) * 1e3
