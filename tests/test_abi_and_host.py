@@ -200,6 +200,19 @@ tg = torch.from_numpy(g.copy()); tl = torch.tensor([l], dtype=torch.float64)
 par.allreduce_shared_grads(tg, tl)
 want = sum(orc.splat(params, t_, W, H, np.float64)[0] for t_ in targets)
 assert np.allclose(tg.numpy(), want, rtol=1e-12, atol=1e-12)
+# C4 on G ranks: ONE image in tile-aligned row bands, Gaussians replicated; a band is rendered as its own image with the
+# centres moved up by the band's first row (fp64: the move costs nothing); gradients and loss add up to the whole image's
+W, H, N = 40, 48, 25
+params, target = orc.splat_scene(N, W, H, seed=11)
+params[:, 1] = np.round(params[:, 1] * 64.0) / 64.0      # so that cy - row_begin is exact in the fp32 parameter array
+r0, r1 = par.row_bands(H, world)[rank]
+shifted = params.copy(); shifted[:, 1] -= r0
+g, o, l, _ = orc.splat(shifted, target.reshape(H, W, 3)[r0:r1].reshape(-1, 3).copy(), W, r1 - r0, np.float64)
+tg = torch.from_numpy(g.copy()); tl = torch.tensor([l], dtype=torch.float64)
+par.allreduce_shared_grads(tg, tl)
+fg, fo, fl, _ = orc.splat(params, target, W, H, np.float64)
+assert np.allclose(o, fo.reshape(H, W, 3)[r0:r1].reshape(-1, 3), rtol=1e-9, atol=1e-12)
+assert np.allclose(tg.numpy(), fg, rtol=1e-9, atol=1e-12) and abs(tl.item() - fl) <= 1e-9 * abs(fl)
 dist.barrier(); dist.destroy_process_group()
 print("rank", rank, "ok")
 '''
