@@ -74,6 +74,8 @@ __global__ void kat_kernel(KatArgs* a) {
         case 8: a->n = api_eval::kat_math<float>(float(a->in[0]), a->fres); break;
         case 9: a->n = api_eval::kat_matrices(a->fres); break;
         case 10: a->n = api_eval::kat_broadcast_logic(a->in[0], a->in + 1, a->in[5], a->in + 6, a->res); break;
+        case 11: a->n = api_eval::kat_const_array(a->fres); break;
+        case 12: a->n = api_eval::kat_variable(a->res, a->scratch); break;
         default: a->n = -1;
     }
 }

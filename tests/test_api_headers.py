@@ -237,6 +237,45 @@ def test_ternary_covariance_projection_node(host):
     assert (np.abs(res[:21] - res[21:]) <= 1e-5 * np.maximum(1.0, np.abs(res[:21]))).all()
 
 
+VARIABLE_KNOWN = ([1, 2, 3, 4, 0, 2, 4, 6] + [0, 0, 0] + [10, 11, 12, 0, 3, 6]          # tests/test_variable.cu:91-181
+                  + [7, -3, 0, 2.5] + [4, 10, 4, 10])
+
+
+def test_variable_leaves_known_answers(host):
+    """VariableRef (external buffers, data() / grad(), zero_grad, add_grad) and Variable (own
+    buffers, ref() view) -- the reference tests' known answers (tests/test_variable.cu) and bit for bit the reference's
+    header on the same source text."""
+    res = np.zeros(64)
+    k = host.mine_kat_variable(P(res))
+    assert k == 25 and list(res[:k]) == VARIABLE_KNOWN
+    if orc.have_ref():
+        rb = np.zeros(64)
+        assert orc.load("ref").ref_kat_variable(P(rb)) == k and np.array_equal(res[:k], rb[:k])
+
+
+CONST_ARRAY_KNOWN = ([1, 2, 3, 3] + [10, 20, 30] + [100, 200, 300]                        # tests/test_const_array.cu:167-217
+                     + [10, 20, 30, 15, 35, 55, 10, 20, 30, 20, 50, 80]                   # :247-305
+                     + [150, 250, 350, 100, 200, 300, 160, 260, 360]                      # :307-333
+                     + [10, 20, 30, 40, 4, 1, 2, 3, 4, 5, 5])                             # :219-245
+
+
+def test_const_array_known_answers(host):
+    """ConstArray<T, N> (reference const_array.cuh:7-223) -- element access, array constructor, copy,
+    compound and binary operators between arrays and with any ConstArrayLike type on either side: the reference tests'
+    own known answers (tests/test_const_array.cu), and bit for bit the reference's header on the same source text."""
+    fa = np.zeros(64, np.float32)
+    ka = host.mine_kat_const_array(P(fa))
+    assert ka == 60 and list(fa[:42]) == CONST_ARRAY_KNOWN
+    a1, a2 = np.array([1.5, -2.0, 8.0], np.float32), np.array([4.0, 0.25, -3.0], np.float32)
+    half = np.float32(0.5)
+    want = np.concatenate([a1 * a2, a1 * a2 / half, a1 * a2, a1 / a2, half * a1, half / a2])
+    assert np.array_equal(fa[42:60], want.astype(np.float32))
+    if orc.have_ref():
+        fb = np.zeros(64, np.float32)
+        kb = orc.load("ref").ref_kat_const_array(P(fb))
+        assert kb == ka and np.array_equal(fa[:ka], fb[:kb])
+
+
 @pytest.mark.gpu
 def test_device_headers_match_reference_ops(cuda):
     """The same op table evaluated INSIDE a kernel on the B200 against the reference's host-compiled Logic
@@ -277,6 +316,13 @@ def test_device_known_answers(cuda, host):
     k = cuda.cuda_kat(10, P(inp), P(res), None)
     want14 = _broadcast_logic_expected(3.5, [1.0, -2.5, 0.25, 4.0], 2.0, [1.0, 3.0, 5.0])
     assert k == 14 and np.allclose(res[:k], want14, rtol=0, atol=1e-9) and list(res[:6]) == want14[:6]
+    # a19 on the device: ConstArray (the reference's device kernels, tests/test_const_array.cu:85-165) = the host path
+    k = cuda.cuda_kat(11, None, None, P(fres))
+    fwant = np.zeros(64, np.float32)
+    assert k == host.mine_kat_const_array(P(fwant)) == 60
+    assert list(fres[:42]) == CONST_ARRAY_KNOWN and np.array_equal(fres[:k], fwant[:k])
+    k = cuda.cuda_kat(12, None, P(res), None)                               # a1 / a2 on the device (atomic add_grad)
+    assert k == 25 and list(res[:k]) == VARIABLE_KNOWN
 
 
 @pytest.mark.gpu
