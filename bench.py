@@ -591,6 +591,12 @@ def splat_section(T, args, rank, world, comm, group, gather, sm_mhz):
             "backward": {"floor_ms": bwd_floor, "ms": stage["backward_us"] / 1e3, "frac": bwd_floor / (stage["backward_us"] / 1e3)},
             "iteration": {"floor_ms": fwd_floor + bwd_floor, "ms": ms_c4, "frac": (fwd_floor + bwd_floor) / ms_c4},
             "hbm_minimum_bytes": N * 72 + W * H * 24, "note": "HBM is not the bound: 32.4 MB minimum traffic = 5 us"}
+    try:  # RED rate and, for completeness, the HBM figure (derived from the values above; never fatal)
+        roof["backward"]["red_ops_per_s"] = 9.0 * bstats["items"] / (stage["backward_us"] * 1e-6)
+        roof["backward"]["red_note"] = "9 red.global.add.f32 per backward work item (one per 256 pairs); the reference: 9 per pair"
+        roof["hbm_gbs_at_minimum_traffic"] = (N * 72 + W * H * 24) / (ms_c4 * 1e-3) / 1e9
+    except Exception:
+        pass
     # ---- e2e.splat: parameters from pinned host memory, loss + gradients back, every iteration
     host_it = host_api.SplatHostIteration(N, W, H, tt, int(stats["entries"] * 1.3), dev)
     ph = torch.from_numpy(params).pin_memory()
