@@ -253,6 +253,20 @@ def test_variable_leaves_known_answers(host):
         assert orc.load("ref").ref_kat_variable(P(rb)) == k and np.array_equal(res[:k], rb[:k])
 
 
+def test_matrix_types_more_known_answers(host):
+    """SURVEY 8 row a20, second helping: DenseMatrix as a Variable (flat access, gradients start at 0, zero_grad keeps the
+    values, (i, j) == flat, data() / grad()), transpose twice, and the transpose of a diagonal view -- the known answers
+    of tests/test_dense_matrix.cu:99-185 and tests/test_matrix_transpose.cu:111-177; host = the reference's headers."""
+    fa = np.zeros(64, np.float32)
+    k = host.mine_kat_matrices2(P(fa))
+    want = ([1, 2, 3, 4, 5, 6] + [0] * 6 + [1, 2, 3, 2, 4, 6] + [0] * 6 + [1, 1, 1]
+            + [1, 4, 2, 5, 3, 6, 1, 6] + [1, 2, 3, 0, 0])
+    assert k == 40 and list(fa[:k]) == want
+    if orc.have_ref():
+        fb = np.zeros(64, np.float32)
+        assert orc.load("ref").ref_kat_matrices2(P(fb)) == k and np.array_equal(fa[:k], fb[:k])
+
+
 CONST_ARRAY_KNOWN = ([1, 2, 3, 3] + [10, 20, 30] + [100, 200, 300]                        # tests/test_const_array.cu:167-217
                      + [10, 20, 30, 15, 35, 55, 10, 20, 30, 20, 50, 80]                   # :247-305
                      + [150, 250, 350, 100, 200, 300, 160, 260, 360]                      # :307-333
