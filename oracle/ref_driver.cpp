@@ -286,6 +286,10 @@ int ref_kat_math_f64(double x, double* res) { return api_eval::kat_math<double>(
 int ref_kat_math_f32(float x, float* res) { return api_eval::kat_math<float>(x, res); }
 int ref_kat_matrices(float* res) { return api_eval::kat_matrices(res); }
 int ref_kat_const_array(float* res) { return api_eval::kat_const_array(res); }
+int ref_kat_networks(const double* p, double delta, double* res) {
+    double scratch[8];
+    return api_eval::kat_networks(p, delta, res, scratch);
+}
 int ref_kat_matrices2(float* res) { return api_eval::kat_matrices2(res); }
 int ref_kat_variable(double* res) { double scratch[8]; return api_eval::kat_variable(res, scratch); }
 

@@ -267,6 +267,44 @@ def test_matrix_types_more_known_answers(host):
         assert orc.load("ref").ref_kat_matrices2(P(fb)) == k and np.array_equal(fa[:k], fb[:k])
 
 
+NETWORK_CASES = [  # (a, b, c, d, x1, x2, y_target), delta, tolerance: tests/operation/base/test_linear_regression_network.cu:186-325
+    ((1.0, 1.5, 0.5, 0.2, 2.0, 1.5, 3.0), 1e-6, 1e-5),               # SimpleLinearRegressionNetwork
+    ((0.8, 1.2, -0.3, 0.5, 1.0, 0.8, 2.5), 1e-6, 1e-5),              # RegularizedLinearRegressionNetwork
+    ((1.0, 0.0, 0.0, 0.0, 2.0, 0.0, 0.0), 1e-7, 1e-5),               # SubtractSquareOperation
+    ((0.5, 0.8, 0.3, 0.2, 1.0, 0.5, 1.5), 1e-6, 1e-5),               # DuplicateAddNetwork
+    ((10.0, 15.0, -8.0, 5.0, 20.0, -10.0, 100.0), 1e-5, 1e-3),       # StressTestWithLargeValues
+    ((0.001, 0.002, -0.001, 0.0001, 0.01, -0.01, 0.001), 1e-8, 1e-5),  # EdgeCaseNearZero
+]
+
+
+def test_reference_network_graphs_analytic_and_numerical(host):
+    """The networks of the reference's network-gradient tests, written with the operator sugar exactly as there: the
+    duplicate-add graph (both leaves feed two nodes: gradients 2 and 2), (a - x1)^2, and the least-squares loss --
+    closed form, analytic against numerical under the reference's acceptance rule min(abs, rel) <= tolerance, and this
+    repo's headers against the reference's on the same source text."""
+    vp, dbl = ctypes.c_void_p, ctypes.c_double
+    host.mine_kat_networks.argtypes = [vp, dbl, vp]
+    ref = orc.load("ref") if orc.have_ref() else None
+    if ref is not None:
+        ref.ref_kat_networks.argtypes = [vp, dbl, vp]
+    for prm, delta, tol in NETWORK_CASES:
+        p, res = np.array(prm), np.zeros(32)
+        assert host.mine_kat_networks(P(p), delta, P(res)) == 17
+        a, b, c, d, x1, x2, y = prm
+        assert res[0] == 2 * (a + b) and list(res[1:3]) == [2.0, 2.0]
+        assert np.isclose(res[5], (a - x1) ** 2, rtol=1e-15) and np.isclose(res[6], 2 * (a - x1), rtol=1e-15)
+        r = (a - x1) ** 2 + b * (c - x2) ** 2 + d - y
+        want = 2 * r * np.array([2 * (a - x1), (c - x2) ** 2, 2 * b * (c - x2), 1.0])
+        assert np.isclose(res[8], r * r, rtol=1e-12) and np.allclose(res[9:13], want, rtol=1e-12, atol=1e-300)
+        for ana, num in ((res[1:3], res[3:5]), (res[6:7], res[7:8]), (res[9:13], res[13:17])):
+            err = np.abs(ana - num)
+            assert (np.minimum(err, err / (np.abs(ana) + 1e-15)) <= tol).all(), (prm, ana, num)
+        if ref is not None:
+            rb = np.zeros(32)
+            assert ref.ref_kat_networks(P(p), delta, P(rb)) == 17
+            assert np.allclose(res[:17], rb[:17], rtol=1e-13, atol=1e-300)
+
+
 CONST_ARRAY_KNOWN = ([1, 2, 3, 3] + [10, 20, 30] + [100, 200, 300]                        # tests/test_const_array.cu:167-217
                      + [10, 20, 30, 15, 35, 55, 10, 20, 30, 20, 50, 80]                   # :247-305
                      + [150, 250, 350, 100, 200, 300, 160, 260, 360]                      # :307-333
