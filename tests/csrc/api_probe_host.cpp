@@ -55,6 +55,7 @@ int mine_kat_math_f64(double x, double* res) { return api_eval::kat_math<double>
 int mine_kat_math_f32(float x, float* res) { return api_eval::kat_math<float>(x, res); }
 int mine_kat_matrices(float* res) { return api_eval::kat_matrices(res); }
 int mine_kat_const_array(float* res) { return api_eval::kat_const_array(res); }
+int mine_kat_matrices3(float* res) { float scratch[12]; return api_eval::kat_matrices3(res, scratch); }
 int mine_kat_networks(const double* p, double delta, double* res) {
     double scratch[8];
     return api_eval::kat_networks(p, delta, res, scratch);

@@ -265,6 +265,15 @@ def test_matrix_types_more_known_answers(host):
     if orc.have_ref():
         fb = np.zeros(64, np.float32)
         assert orc.load("ref").ref_kat_matrices2(P(fb)) == k and np.array_equal(fa[:k], fb[:k])
+    # diagonal / symmetric views the way the reference's tests use them (default template argument, make_* helpers,
+    # flat-index storage, symmetric transpose): tests/test_diagonal_matrix.cu:105-187, tests/test_symmetric_matrix.cu:118-192
+    k3 = host.mine_kat_matrices3(P(fa))
+    want3 = ([1, 0, 0, 0, 2, 0, 0, 0, 3] + [1, 2, 6, 8, 15, 18] + [1, 4, 9, 4, 10, 18] + [1, 2, 2, 4, 3, 6, 2, 5]
+             + [1, 2, 2, 4, 5, 5] + [1, 2, 3, 4, 5, 6, 2, 3, 5])
+    assert k3 == 44 and list(fa[:k3]) == want3
+    if orc.have_ref():
+        fb = np.zeros(64, np.float32)
+        assert orc.load("ref").ref_kat_matrices3(P(fb)) == k3 and np.array_equal(fa[:k3], fb[:k3])
 
 
 NETWORK_CASES = [  # (a, b, c, d, x1, x2, y_target), delta, tolerance: tests/operation/base/test_linear_regression_network.cu:186-325
