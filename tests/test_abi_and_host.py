@@ -222,8 +222,12 @@ def test_world_size_2_gloo_shared_gradient_allreduce():
     with tempfile.TemporaryDirectory() as d:
         w = os.path.join(d, "worker.py")
         open(w, "w").write(WORKER)
+        import socket
+        with socket.socket() as sock:  # a port nobody holds right now (a fixed one may be taken by a parallel run)
+            sock.bind(("127.0.0.1", 0))
+            port = sock.getsockname()[1]
         res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2",
-                              "--master-addr", "127.0.0.1", "--master-port", "29611", w, ROOT],
+                              "--master-addr", "127.0.0.1", "--master-port", str(port), w, ROOT],
                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, timeout=240)
         assert res.returncode == 0, res.stdout[-3000:]
         assert res.stdout.count("ok") >= 2
